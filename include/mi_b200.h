@@ -1,0 +1,188 @@
+/*
+ * mi_b200.h -- C ABI of the B200-native MAML inner-loop hot path of
+ * myungsub/meta-interpolation (libmi_b200.so, sm_100a only).
+ *
+ * Conventions ("Operator/FFI level"):
+ *   - every entry point returns 0 on success or a non-zero cudaError_t /
+ *     MI_ERR_* code (the reference's native extensions use the same int-error
+ *     convention, dain/my_package/FilterInterpolation/filterinterpolation_cuda.cc:18-60);
+ *   - the caller owns every buffer; nothing here allocates, frees or
+ *     synchronises; every call is asynchronous on `stream`
+ *     (the reference launches on torch.cuda.current_stream(),
+ *     sepconv/sepconv_op/sepconv.py:276-291);
+ *   - activations are NHWC fp32 with an explicit pixel stride `ld*` (floats,
+ *     >= channels), which also expresses channel slices of a concat buffer;
+ *   - conv weights are [Cout][kh][kw][ldw] ("KRSC", ldw = Cin rounded up to 4,
+ *     pad lanes zero); the reference's OIHW nn.Parameter is a permuted VIEW of
+ *     the same storage, so no copy exists between the two.
+ *
+ * Each function cites the reference interface it replaces.
+ */
+#ifndef MI_B200_H_
+#define MI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mi_stream_t; /* cudaStream_t */
+
+enum { MI_OK = 0, MI_ERR_BAD_ARG = 10001, MI_ERR_UNSUPPORTED = 10002, MI_ERR_WORKSPACE = 10003 };
+
+/* activation kinds fused into conv epilogues and their backward masks */
+enum { MI_ACT_NONE = 0, MI_ACT_RELU = 1, MI_ACT_LEAKY = 2, MI_ACT_SIGMOID = 3, MI_ACT_TANH = 4 };
+
+/* conv engines: 0 = pick (tcgen05 when the shape is eligible), 1 = force SIMT fp32, 2 = force tcgen05 TF32 */
+enum { MI_ENGINE_AUTO = 0, MI_ENGINE_SIMT = 1, MI_ENGINE_TC = 2 };
+
+/* what the weight-gradient finishing stage does with the reduced gradient g */
+enum {
+    MI_WG_STORE = 0,     /* grad_out = g                                             */
+    MI_WG_ACCUM = 1,     /* grad_out += scale * g           (outer meta-gradient)    */
+    MI_WG_SGD_SCALAR = 2,/* w_out = w_in - lr[0] * g        (LSLR, inner_loop_optimizers.py:136-147) */
+    MI_WG_SGD_TENSOR = 3 /* w_out = w_in - lr[i] * g[i]     (Meta-SGD, inner_loop_optimizers.py:324-332) */
+};
+
+int mi_version(void);
+const char* mi_error_string(int code);
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+unsigned long long mi_launch_count(void);
+/* 1 if the tcgen05 path was compiled in and the current device is sm_100 */
+int mi_tc_available(void);
+
+/* ------------------------------------------------------------------ convolution
+ * Replaces F.conv2d in MetaConv2dLayer.forward (model_utils.py:360) and its
+ * autograd backward; stride 1, padding k/2, dilation 1, groups 1 (the only
+ * configuration any of the five backbones uses).
+ *
+ * y[n,oy,ox,co] = act( bias[co] + sum_{ky,kx,ci} x[n,oy+ky-k/2,ox+kx-k/2,ci] * w[co,ky,kx,ci] )
+ */
+int mi_conv2d_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias,
+                    float* y, int ldy, int n, int h, int wd, int cin, int cout, int k,
+                    int act, float slope, int engine, mi_stream_t stream);
+
+/* dx = conv_transpose(dy, w) [* act'(mask_y)] ; accumulate!=0 adds into dx.
+ * `wt` is the dgrad weight layout produced by mi_weight_to_dgrad:
+ * wt[ci][k-1-ky][k-1-kx][co] = w[co][ky][kx][ci]  (ldwt = Cout rounded up to 4).
+ * mask_y (optional) is the POST-activation tensor that fed this conv
+ * (dx is then the gradient w.r.t. that producer's pre-activation). */
+int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt,
+                    float* dx, int lddx, const float* mask_y, int ldmask, int mask_act, float mask_slope,
+                    int accumulate, int n, int h, int wd, int cin, int cout, int k,
+                    int engine, mi_stream_t stream);
+
+int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, mi_stream_t stream);
+
+/* workspace bytes mi_conv2d_wgrad needs for this shape */
+size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k, int engine);
+
+/* g_w[co,ky,kx,ci] = sum_{n,oy,ox} dy[n,oy,ox,co] * x[n,oy+ky-k/2,ox+kx-k/2,ci];  g_b[co] = sum dy.
+ * The finishing stage applies `mode` (MI_WG_*) to weights and bias alike, so
+ * the inner-loop update needs no separate elementwise launch
+ * (replaces autograd.grad + update_params, meta_learning_system.py:291-307).
+ *   grad_w/grad_b : STORE/ACCUM target (may be NULL in the SGD modes)
+ *   w_in,b_in -> w_out,b_out : SGD modes (may alias)
+ *   lr_w, lr_b : device pointers; scalar (mode 2) or same shape as w / b (mode 3)
+ *   gsum_w,gsum_b : optional running sum of g over inner steps (Meta-SGD outer grad of alpha, SURVEY Appx E4)
+ *   scale : multiplies g in ACCUM mode. */
+int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy,
+                    int n, int h, int wd, int cin, int cout, int k, int ldw,
+                    int mode, float scale,
+                    float* grad_w, float* grad_b,
+                    const float* w_in, const float* b_in, float* w_out, float* b_out,
+                    const float* lr_w, const float* lr_b, float* gsum_w, float* gsum_b,
+                    void* workspace, size_t workspace_bytes, int engine, mi_stream_t stream);
+
+/* ------------------------------------------------------------------ pointwise / resampling
+ * avg/max pool 2x2 s2  : sepconv/model.py:197-209, voxel_flow.py:243, superslomo/model.py:69, rrin/unet.py:139
+ * bilinear x2 upsample : sepconv/model.py:191 (align_corners=True); voxel_flow.py:400, superslomo/model.py:139,
+ *                        rrin/unet.py:184 (align_corners=False) */
+int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t stream);
+int mi_avgpool2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c, mi_stream_t stream);
+int mi_maxpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t stream);
+int mi_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx, int accumulate,
+                    int n, int h, int wd, int c, mi_stream_t stream);
+int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners, mi_stream_t stream);
+int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
+                     int align_corners, mi_stream_t stream);
+/* y = a + b  (skip adds, sepconv/model.py:294-309) ; a,b,y may alias */
+int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t stream);
+/* dst (+)= src over a channel slice; used for concat/split and gradient fan-in */
+int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size_t pixels, int c, mi_stream_t stream);
+/* in place: dy *= act'(y) with y the post-activation tensor */
+int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c, mi_stream_t stream);
+int mi_fill(float* p, float v, size_t count, mi_stream_t stream);
+
+/* ------------------------------------------------------------------ frames in / prediction out
+ * Builds the NHWC network input from two NCHW frames with the reference's
+ * padding folded in: canvas[n,y,x,0:3]=f0, [3:6]=f1 sampled at
+ * (clamp|reflect)(y - pad_top, x - pad_left).  mode 0 = replicate
+ * (sepconv/model.py:254-269), 1 = reflect (model_utils.py:17-28, voxel_flow.py:360-368). */
+int mi_frames_to_canvas(const float* f0, const float* f1, float* canvas, int ldc,
+                        int n, int h, int wd, int ch, int cw, int pad_top, int pad_left, int mode, mi_stream_t stream);
+/* NHWC window -> NCHW [n,c,h,w] (the crop of sepconv/model.py:349) and back (gradient of the crop, zero elsewhere is the caller's fill) */
+int mi_nhwc_window_to_nchw(const float* src, int lds, float* dst, int n, int hs, int ws, int y0, int x0, int h, int wd, int c, mi_stream_t stream);
+int mi_nchw_to_nhwc_window(const float* src, float* dst, int ldd, int n, int hs, int ws, int y0, int x0, int h, int wd, int c, mi_stream_t stream);
+
+/* ------------------------------------------------------------------ adaptive separable convolution
+ * Replaces FunctionSepconv (sepconv/sepconv_op/sepconv.py:247-380; kernels :5-30, :138-190).
+ *   frame : NCHW [n,c,fh,fw] fp32 (c <= 4)
+ *   vert, horiz : NHWC [n,gh,gw,ldf] with F taps per pixel (reference layout is [n,F,gh,gw])
+ *   out   : NCHW [n,c,oh,ow] -- output pixel (i,j) uses vert/horiz at grid (gy0+i, gx0+j) and the FxF window whose
+ *           top-left input sample is frame[clamp(i+iy0+fy), clamp(j+ix0+fx)] (replicate border).
+ * With gy0=gx0=0, iy0=ix0=0, fh=oh+F-1 this is exactly the reference op on a pre-padded input; with
+ * gy0=gx0=25, iy0=ix0=-25 on the raw frame it is the op fused with modulePaddingInput, modulePad and
+ * modulePaddingOutput (SURVEY Appx A.1).  No gradient w.r.t. frame is ever needed (sepconv.py:319). */
+int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, int ldf, float* out,
+                   int n, int c, int fh, int fw, int gh, int gw, int oh, int ow,
+                   int gy0, int gx0, int iy0, int ix0, int taps, mi_stream_t stream);
+/* g_vert/g_horiz get the gradient inside the window; the caller zero-fills the rest of the grid. */
+int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
+                   float* g_vert, float* g_horiz, int ldg,
+                   int n, int c, int fh, int fw, int gh, int gw, int oh, int ow,
+                   int gy0, int gx0, int iy0, int ix0, int taps, mi_stream_t stream);
+
+/* ------------------------------------------------------------------ bilinear backward warp (grid_sample)
+ * variant 0: superslomo backWarp / rrin warp (superslomo/model.py:292-302, rrin/model.py:8-21):
+ *            sample at (x+u-0.5, y+v-0.5), zeros outside (SURVEY Appx E2)
+ * variant 1: voxelflow (voxel_flow.py:471-503): sample at clip(x + sx*u*(W-1)/2... see DESIGN.md), border clamp.
+ *   img : NHWC [n,h,w,c] (data, no gradient), flow : NHWC [n,h,w,2] (u,v), out : NHWC [n,h,w,c] */
+int mi_warp_fwd(const float* img, int ldi, const float* flow, int ldfl, float* out, int ldo,
+                int n, int h, int wd, int c, int variant, float flow_scale_x, float flow_scale_y, mi_stream_t stream);
+int mi_warp_bwd(const float* img, int ldi, const float* flow, int ldfl, const float* grad_out, int ldgo,
+                float* grad_flow, int ldgf, float* grad_img, int ldgi, int accumulate,
+                int n, int h, int wd, int c, int variant, float flow_scale_x, float flow_scale_y, mi_stream_t stream);
+
+/* ------------------------------------------------------------------ losses and metrics
+ * L1 / MSE mean (loss.py:287-290): loss_out[0] += weight * mean(f(pred-target)); grad = weight * f'(.)/count.
+ * pred, target NCHW contiguous of `count` elements. kind 0 = L1, 1 = MSE. grad may be NULL. */
+int mi_loss_fwd_bwd(const float* pred, const float* target, float* grad, float* loss_out, size_t count,
+                    int kind, float weight, mi_stream_t stream);
+/* utils.py:171-204: sum over elements of ((q(p)-q(t))/255)^2 into sq_out[0] (double); psnr = -10 log10(sq/count + 1e-8) on host */
+int mi_psnr_accumulate(const float* pred, const float* target, double* sq_out, size_t count, mi_stream_t stream);
+
+/* ------------------------------------------------------------------ inner-loop rules on flat arenas
+ * (inner_loop_optimizers.py:150-244, 335-426).  `seg` maps each 1024-float chunk of the arena to a tensor id;
+ * lr is indexed [seg*lr_stride + num_step] (LSLR) or per element (Meta-SGD, lr_per_element=1).
+ * rule 0 = SGD, 1 = Adam, 2 = Adamax(LSLR quirk: exp_avg persists, exp_inf stateless),
+ * 3 = Adamax(Meta-SGD quirk: fully stateless).  skip[seg]!=0 leaves w_out = w_in (None gradient). */
+int mi_inner_update(const float* w_in, const float* g, float* w_out, float* exp_avg, float* exp_avg_sq,
+                    const float* lr, int lr_per_element, int lr_stride, int num_step,
+                    const int32_t* seg, const uint8_t* skip, size_t count, int rule, int step_count, mi_stream_t stream);
+/* outer optimizer (meta_learning_system.py:132-143): kind 0 = SGD, 1 = Adam(amsgrad off), 2 = Adamax */
+int mi_outer_step(float* p, const float* g, float* m, float* v, size_t count, int kind, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, mi_stream_t stream);
+/* y[i] = a*x[i] + b*y[i] */
+int mi_axpby(const float* x, float a, float* y, float b, size_t count, mi_stream_t stream);
+/* y[i] += a * x1[i] * x2[i]  (Meta-SGD alpha gradient  -gsum (.) G, SURVEY Appx E4) */
+int mi_addcmul(float* y, float a, const float* x1, const float* x2, size_t count, mi_stream_t stream);
+/* out[t] = sum over tensor t of a[i]*b[i]  (lr / gamma outer gradients, SURVEY Appx E4); segs as above; out zeroed by caller */
+int mi_segment_dot(const float* a, const float* b, const int32_t* seg, float* out, size_t count, mi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MI_B200_H_ */

@@ -1,0 +1,213 @@
+"""Common machinery of the model plugins (the reference's ``net`` objects).
+
+A plugin keeps the reference's plugin API:
+``net.forward(frame0, frame1, params=dict_or_None, **kwargs) -> Tensor[1,3,H,W]``,
+``net.zero_grad(params=None)``, ``net.restore_backup_stats()``, and
+``named_parameters()`` with the reference's names and OIHW shapes -- but its
+parameters are views into one flat arena and its compute is a tape of sm_100a
+kernels.  ``forward`` is a single ``torch.autograd.Function`` so the reference's
+own calling pattern (``torch.autograd.grad(loss, fast_weights.values(),
+allow_unused=True)``, meta_learning_system.py:291-292) keeps working, including
+``None`` gradients for tensors the reference never routes.
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import ops as ops_mod
+from .arena import Arena, Layout, pad4
+from .ops import WG_STORE, WgradSpec
+from .tape import ConvParam, Tape, Var
+
+_default_ops = None
+
+
+def default_ops():
+    """The process-wide CUDA operator table (raises when the library or the GPU is missing)."""
+    global _default_ops
+    if _default_ops is None:
+        _default_ops = ops_mod.CudaOps()
+    return _default_ops
+
+
+def set_default_ops(ops):
+    """Test hook: inject another operator table (the CPU suite injects the oracle's)."""
+    global _default_ops
+    _default_ops = ops
+
+
+class _ConvSlot(nn.Module):
+    """Holds the reference-visible ``weight`` / ``bias`` Parameters of one conv (views into the arena)."""
+
+    def __init__(self, weight, bias):
+        super().__init__()
+        self.weight = weight
+        if bias is not None:
+            self.bias = bias
+
+
+def kernel_weight_view(ops, t):
+    """OIHW tensor -> KRSC kernel view; zero-copy when ``t`` already aliases KRSC storage."""
+    kv = t.permute(0, 2, 3, 1)
+    co, k, _, ci = kv.shape
+    ld = kv.stride(2)
+    ok = (kv.stride(3) == 1 and ld >= ci and ld % 4 == 0 and kv.stride(1) == k * ld and kv.stride(0) == k * k * ld
+          and kv.data_ptr() % 16 == 0)
+    if ok:
+        return kv
+    w = ops.empty_weight(co, ci, k)
+    w.copy_(kv)   # layout conversion at the API boundary only (foreign OIHW tensors)
+    return w
+
+
+class StoreSink:
+    """Weight-gradient sink of the compat path: plain gradients, only where autograd asks for them."""
+
+    def __init__(self, ops, wanted):
+        self.ops = ops
+        self.wanted = wanted          # set of parameter names whose gradient is needed
+        self.grads = {}
+
+    def weight_grad(self, p, x, dy, k):
+        wn, bn = p.name + ".weight", p.name + ".bias"
+        if wn not in self.wanted and bn not in self.wanted:
+            return
+        cout, _, _, cin = p.w.shape
+        gw = self.ops.empty_weight(cout, cin, k)
+        gb = torch.zeros(cout, device=gw.device, dtype=gw.dtype) if p.b is not None else None
+        self.ops.conv_wgrad(x, dy, k, gw.stride(2), WgradSpec(WG_STORE, grad_w=gw, grad_b=gb))
+        self.grads[wn] = gw
+        if gb is not None:
+            self.grads[bn] = gb
+
+
+class _BackboneFunction(torch.autograd.Function):
+    """forward: tape forward; backward: tape backward with a StoreSink."""
+
+    @staticmethod
+    def forward(ctx, net, frame0, frame1, names, *tensors):
+        ops = net.ops
+        table = dict(zip(names, tensors))
+        cache = {}
+
+        def provider(name):
+            p = cache.get(name)
+            if p is None:
+                w = kernel_weight_view(ops, table[name + ".weight"].detach())
+                b = table.get(name + ".bias")
+                p = ConvParam(name, w, None if b is None else b.detach().contiguous())
+                cache[name] = p
+            return p
+
+        tape = Tape(ops, provider, sink=None)
+        out = net.build_graph(tape, frame0.detach().contiguous(), frame1.detach().contiguous())
+        ctx.tape, ctx.out_var, ctx.names, ctx.net = tape, out, names, net
+        ctx.shapes = [tuple(t.shape) for t in tensors]
+        return out.data.clone() if net.clone_output else out.data
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        net, tape = ctx.net, ctx.tape
+        needs = ctx.needs_input_grad[4:]
+        wanted = {n for n, need in zip(ctx.names, needs) if need}
+        sink = StoreSink(net.ops, wanted)
+        tape.sink = sink
+        ctx.out_var.grad = grad_out.contiguous()
+        tape.backward()
+        grads = []
+        for n, need in zip(ctx.names, needs):
+            g = sink.grads.get(n) if need else None
+            if g is not None and g.dim() == 4:
+                g = g.permute(0, 3, 1, 2)
+            grads.append(g)
+        ctx.tape = ctx.out_var = None
+        return (None, None, None, None) + tuple(grads)
+
+
+class MetaBackbone(nn.Module):
+    """Base of the five plugins.  Subclasses define ``conv_specs``, ``is_routed`` and ``build_graph``."""
+
+    clone_output = False
+
+    def __init__(self, ops=None):
+        super().__init__()
+        self.ops = ops if ops is not None else default_ops()
+
+    # -- subclasses -----------------------------------------------------------------------------
+    def conv_specs(self):
+        """Ordered [(name, cin, cout, k, has_bias)] in the reference's registration order."""
+        raise NotImplementedError
+
+    def is_routed(self, param_name):
+        """Does the reference feed this tensor from ``params``?  """
+        return True
+
+    def build_graph(self, tape, frame0, frame1):
+        raise NotImplementedError
+
+    # -- construction ---------------------------------------------------------------------------
+    def _build_parameters(self, init_fn):
+        """Create the arena and the reference-named Parameters; ``init_fn(name, shape) -> CPU tensor`` is
+        called in registration order so the CPU RNG stream matches the reference's constructors."""
+        specs = self.conv_specs()
+        named_shapes = []
+        for name, cin, cout, k, has_bias in specs:
+            named_shapes.append((name + ".weight", (cout, cin, k, k)))
+            if has_bias:
+                named_shapes.append((name + ".bias", (cout,)))
+        self.layout = Layout(named_shapes)
+        self.arena = Arena(self.layout, self.ops.device)
+        self.param_names = [n for n, _ in named_shapes]
+        self.conv_names = [s[0] for s in specs]
+        self._spec = {s[0]: s for s in specs}
+        for name, cin, cout, k, has_bias in specs:
+            wv = self.arena.reference_view(name + ".weight")
+            wv.copy_(init_fn(name + ".weight", (cout, cin, k, k)))
+            weight = nn.Parameter(wv)
+            bias = None
+            if has_bias:
+                bv = self.arena.reference_view(name + ".bias")
+                bv.copy_(init_fn(name + ".bias", (cout,)))
+                bias = nn.Parameter(bv)
+            self._register(name, _ConvSlot(weight, bias))
+
+    def _register(self, dotted, slot):
+        parts = dotted.split(".")
+        mod = self
+        for p in parts[:-1]:
+            if not hasattr(mod, p):
+                mod.add_module(p, nn.Module())
+            mod = getattr(mod, p)
+        mod.add_module(parts[-1], slot)
+
+    # -- parameter providers ----------------------------------------------------------------------
+    def meta_param(self, name):
+        w = self.arena.kernel_view(name + ".weight")
+        b = self.arena.kernel_view(name + ".bias") if self._spec[name][4] else None
+        return ConvParam(name, w, b)
+
+    # -- reference plugin API ---------------------------------------------------------------------
+    def forward(self, frame0, frame1, params=None, **kwargs):
+        own = dict(self.named_parameters())
+        names, tensors = [], []
+        for n in self.param_names:
+            t = own[n]
+            if params is not None and n in params and self.is_routed(n):
+                t = params[n]
+            names.append(n)
+            tensors.append(t)
+        return _BackboneFunction.apply(self, frame0, frame1, tuple(names), *tensors)
+
+    def zero_grad(self, params=None, set_to_none=True):
+        # reference sepconv/model.py:352-367 (host-syncing prints dropped; semantics: clear .grad)
+        if params is None:
+            for p in self.parameters():
+                p.grad = None
+        else:
+            for p in params.values():
+                if p is not None and p.requires_grad and p.is_leaf:
+                    p.grad = None
+
+    def restore_backup_stats(self):
+        pass  # no batch statistics on any of the five backbones

@@ -1,0 +1,422 @@
+// fp32 SIMT implicit-GEMM convolution (fprop / dgrad / wgrad) for NHWC tensors.
+//
+// This is the exact-fp32 engine: it serves every shape the tcgen05 path does
+// not take (k=5/7 stems with Cin 6/20, Cout<=5 heads, unaligned strides) and is
+// the on-device cross-check of the TF32 tensor-core engine in conv_tc.cu.
+// Replaces F.conv2d + its autograd (reference model_utils.py:360).
+#include "mi_common.cuh"
+
+std::atomic<unsigned long long> g_mi_launches{0};
+
+namespace {
+
+constexpr int BM = 64;   // output pixels per CTA
+constexpr int BN = 64;   // output channels per CTA
+constexpr int BK = 16;   // reduction slice
+constexpr int PADS = 4;  // smem row padding (floats)
+
+// ---------------------------------------------------------------------------------------------
+// fprop (also dgrad when fed dy and the rotated/transposed weights)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_fprop_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, int ldw,
+                       const float* __restrict__ bias, float* __restrict__ y, int ldy,
+                       const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope, int accumulate,
+                       int n, int h, int wd, int cin, int cout, int k, int act, float slope, int vec_ok) {
+    __shared__ float As[BK][BM + PADS];
+    __shared__ float Bs[BK][BN + PADS];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15;   // channel direction
+    const int ty = tid >> 4;   // pixel direction
+    const long long m_total = (long long)n * h * wd;
+    const long long m_base = (long long)blockIdx.x * BM;
+    const int co_base = blockIdx.y * BN;
+    const int pad = k >> 1;
+
+    // this thread's loader assignment: one pixel (or one cout row) and 4 consecutive reduction lanes
+    const int l_row = tid >> 2;         // 0..63
+    const int l_c4 = (tid & 3) << 2;    // 0,4,8,12
+    const long long lm = m_base + l_row;
+    int ln = 0, loy = 0, lox = 0;
+    const bool lm_ok = lm < m_total;
+    if (lm_ok) {
+        ln = (int)(lm / ((long long)h * wd));
+        int r = (int)(lm - (long long)ln * h * wd);
+        loy = r / wd;
+        lox = r - loy * wd;
+    }
+    const int lco = co_base + l_row;
+    const bool lco_ok = lco < cout;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int ky = 0; ky < k; ++ky) {
+        const int iy = loy + ky - pad;
+        for (int kx = 0; kx < k; ++kx) {
+            const int ix = lox + kx - pad;
+            const bool in_ok = lm_ok && iy >= 0 && iy < h && ix >= 0 && ix < wd;
+            const float* xp = x + ((long long)(ln * h + iy) * wd + ix) * ldx;
+            const float* wp = w + ((long long)lco * k * k + ky * k + kx) * ldw;
+            for (int c0 = 0; c0 < cin; c0 += BK) {
+                const int c = c0 + l_c4;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+                if (in_ok) {
+                    if (vec_ok && c + 3 < cin) {
+                        float4 v = *reinterpret_cast<const float4*>(xp + c);
+                        a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w;
+                    } else {
+                        if (c < cin) a0 = xp[c];
+                        if (c + 1 < cin) a1 = xp[c + 1];
+                        if (c + 2 < cin) a2 = xp[c + 2];
+                        if (c + 3 < cin) a3 = xp[c + 3];
+                    }
+                }
+                if (lco_ok) {
+                    if (vec_ok && c + 3 < cin) {
+                        float4 v = *reinterpret_cast<const float4*>(wp + c);
+                        b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
+                    } else {
+                        if (c < cin) b0 = wp[c];
+                        if (c + 1 < cin) b1 = wp[c + 1];
+                        if (c + 2 < cin) b2 = wp[c + 2];
+                        if (c + 3 < cin) b3 = wp[c + 3];
+                    }
+                }
+                __syncthreads();
+                As[l_c4 + 0][l_row] = a0; As[l_c4 + 1][l_row] = a1; As[l_c4 + 2][l_row] = a2; As[l_c4 + 3][l_row] = a3;
+                Bs[l_c4 + 0][l_row] = b0; Bs[l_c4 + 1][l_row] = b1; Bs[l_c4 + 2][l_row] = b2; Bs[l_c4 + 3][l_row] = b3;
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < BK; ++kk) {
+                    const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty << 2]);
+                    const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx << 2]);
+                    const float a[4] = {av.x, av.y, av.z, av.w};
+                    const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m_base + (ty << 2) + i;
+        if (m >= m_total) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int co = co_base + (tx << 2) + j;
+            if (co >= cout) continue;
+            float v = acc[i][j] + (bias ? bias[co] : 0.f);
+            v = mi_act_apply(v, act, slope);
+            if (mask_y) v *= mi_act_grad(mask_y[m * ldmask + co], mask_act, mask_slope);
+            float* yp = y + m * ldy + co;
+            if (accumulate) v += *yp;
+            *yp = v;
+        }
+    }
+}
+
+// wt[ci][k-1-ky][k-1-kx][co] = w[co][ky][kx][ci]
+__global__ void weight_to_dgrad_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt,
+                                       int cin, int cout, int k) {
+    const long long total = (long long)cin * k * k * ldwt;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % ldwt);
+        long long r = i / ldwt;
+        const int tap = (int)(r % (k * k));
+        const int ci = (int)(r / (k * k));
+        float v = 0.f;
+        if (co < cout) v = w[((long long)co * k * k + (k * k - 1 - tap)) * ldw + ci];
+        wt[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: split-K partial sums into the workspace, identical layout to the weights ([cout][k*k][ldw])
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_wgrad_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
+                       float* __restrict__ ws_w, float* __restrict__ ws_b, int n, int h, int wd, int cin, int cout,
+                       int k, int ldw, int co_tiles, int ci_tiles, long long chunk_per_split, int vec_x, int vec_dy) {
+    __shared__ float As[BK][BN + PADS];  // [pixel][cout]
+    __shared__ float Bs[BK][BM + PADS];  // [pixel][cin]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15;  // cin direction
+    const int ty = tid >> 4;  // cout direction
+    int bid = blockIdx.x;
+    const int ci_tile = bid % ci_tiles; bid /= ci_tiles;
+    const int co_tile = bid % co_tiles; bid /= co_tiles;
+    const int tap = bid;
+    const int ky = tap / k, kx = tap - ky * k;
+    const int pad = k >> 1;
+    const int split = blockIdx.y;
+    const long long m_total = (long long)n * h * wd;
+    const long long m0 = (long long)split * chunk_per_split;
+    long long m1 = m0 + chunk_per_split;
+    if (m1 > m_total) m1 = m_total;
+    const int co_base = co_tile * BN, ci_base = ci_tile * BM;
+
+    const int l_p = tid >> 4;         // pixel within chunk 0..15
+    const int l_c4 = (tid & 15) << 2; // channel group 0..60
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool do_bias = (tap == 0 && ci_tile == 0 && tx == 0);
+
+    for (long long mc = m0; mc < m1; mc += BK) {
+        const long long m = mc + l_p;
+        float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < m1) {
+            const float* dp = dy + m * lddy;
+            const int co = co_base + l_c4;
+            if (vec_dy && co + 3 < cout) {
+                float4 v = *reinterpret_cast<const float4*>(dp + co);
+                a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (co + q < cout) a[q] = dp[co + q];
+            }
+            const int nn = (int)(m / ((long long)h * wd));
+            const int r = (int)(m - (long long)nn * h * wd);
+            const int oy = r / wd, ox = r - oy * wd;
+            const int iy = oy + ky - pad, ix = ox + kx - pad;
+            if (iy >= 0 && iy < h && ix >= 0 && ix < wd) {
+                const float* xp = x + ((long long)(nn * h + iy) * wd + ix) * ldx;
+                const int ci = ci_base + l_c4;
+                if (vec_x && ci + 3 < cin) {
+                    float4 v = *reinterpret_cast<const float4*>(xp + ci);
+                    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if (ci + q < cin) b[q] = xp[ci + q];
+                }
+            }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&As[l_p][l_c4]) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(&Bs[l_p][l_c4]) = make_float4(b[0], b[1], b[2], b[3]);
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < BK; ++p) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[p][ty << 2]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[p][tx << 2]);
+            const float aa[4] = {av.x, av.y, av.z, av.w};
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+                if (do_bias) bacc[i] += aa[i];
+            }
+        }
+    }
+
+    const long long wsz = (long long)cout * k * k * ldw;
+    float* wsp = ws_w + (long long)split * wsz;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co_base + (ty << 2) + i;
+        if (co >= cout) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ci = ci_base + (tx << 2) + j;
+            if (ci >= cin) continue;
+            wsp[((long long)co * k * k + tap) * ldw + ci] = acc[i][j];
+        }
+        if (do_bias) ws_b[(long long)split * cout + co] = bacc[i];
+    }
+}
+
+// reduce the split-K partials and apply the requested epilogue (store / accumulate / fused inner update)
+__global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float* __restrict__ ws_b, int splits,
+                                    int cin, int cout, int kk, int ldw, int mode, float scale,
+                                    float* __restrict__ grad_w, float* __restrict__ grad_b,
+                                    const float* __restrict__ w_in, const float* __restrict__ b_in,
+                                    float* __restrict__ w_out, float* __restrict__ b_out,
+                                    const float* __restrict__ lr_w, const float* __restrict__ lr_b,
+                                    float* __restrict__ gsum_w, float* __restrict__ gsum_b) {
+    const long long wsz = (long long)cout * kk * ldw;
+    const long long total = wsz + cout;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const bool is_b = i >= wsz;
+        const long long e = is_b ? i - wsz : i;
+        if (!is_b && (int)(e % ldw) >= cin) continue;  // pad lanes stay zero
+        const float* src = is_b ? ws_b : ws_w;
+        const long long stride = is_b ? cout : wsz;
+        float g = 0.f;
+        for (int s = 0; s < splits; ++s) g += src[(long long)s * stride + e];
+        float* gout = is_b ? grad_b : grad_w;
+        const float* pin = is_b ? b_in : w_in;
+        float* pout = is_b ? b_out : w_out;
+        const float* lr = is_b ? lr_b : lr_w;
+        float* gs = is_b ? gsum_b : gsum_w;
+        if (is_b && ((mode <= MI_WG_ACCUM && !gout) || (mode > MI_WG_ACCUM && (!pin || !pout || !lr)))) continue;
+        if (mode == MI_WG_STORE) {
+            gout[e] = g;
+        } else if (mode == MI_WG_ACCUM) {
+            gout[e] += scale * g;
+        } else {
+            const float l = (mode == MI_WG_SGD_SCALAR) ? lr[0] : lr[e];
+            pout[e] = pin[e] - l * g;
+            if (gout) gout[e] = g;
+        }
+        if (gs) gs[e] += g;
+    }
+}
+
+}  // namespace
+
+int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
+    const long long m_total = (long long)n * h * wd;
+    const long long base = (long long)k * k * mi_cdiv(cout, BN) * mi_cdiv(cin, BM);
+    long long splits = (148 * 4 + base - 1) / base;
+    const long long max_splits = (m_total + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 256) splits = 256;
+    return (int)splits;
+}
+
+int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int cin, int cout, int k, int ldw,
+                           int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
+                           float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
+                           float* gsum_b, cudaStream_t stream) {
+    const long long total = (long long)cout * k * k * ldw + cout;
+    int blocks = mi_cdiv(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, cin, cout, k * k, ldw, mode, scale, grad_w,
+                                                    grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+                             const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n,
+                             int h, int wd, int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
+    const long long m_total = (long long)n * h * wd;
+    dim3 grid(mi_cdiv(m_total, BM), mi_cdiv(cout, BN));
+    const int vec_ok = (ldx % 4 == 0) && (ldw % 4 == 0) && mi_al16(x) && mi_al16(w);
+    conv_fprop_simt_kernel<<<grid, 256, 0, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask, mask_act,
+                                                     mask_slope, accumulate, n, h, wd, cin, cout, k, act, slope,
+                                                     vec_ok);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+extern "C" {
+
+int mi_conv2d_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy, int n,
+                    int h, int wd, int cin, int cout, int k, int act, float slope, int engine, mi_stream_t stream) {
+    if (!x || !w || !y || n <= 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || (k & 1) == 0 || ldx < cin ||
+        ldw < cin || ldy < cout)
+        return MI_ERR_BAD_ARG;
+    if (engine != MI_ENGINE_SIMT && mi_tc_fprop_eligible(x, ldx, w, ldw, y, ldy, n, h, wd, cin, cout, k))
+        return mi_tc_fprop(x, ldx, w, ldw, bias, y, ldy, nullptr, 0, 0, 0.f, 0, n, h, wd, cin, cout, k, act, slope,
+                           mi_cs(stream));
+    if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
+    return fprop_simt_launch(x, ldx, w, ldw, bias, y, ldy, nullptr, 0, 0, 0.f, 0, n, h, wd, cin, cout, k, act, slope,
+                             mi_cs(stream));
+}
+
+int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt, float* dx, int lddx, const float* mask_y,
+                    int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd, int cin,
+                    int cout, int k, int engine, mi_stream_t stream) {
+    if (!dy || !wt || !dx || n <= 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || (k & 1) == 0 || lddy < cout ||
+        ldwt < cout || lddx < cin)
+        return MI_ERR_BAD_ARG;
+    // dgrad == fprop over dy with the rotated/transposed filter: roles of cin/cout swap
+    if (engine != MI_ENGINE_SIMT && mi_tc_fprop_eligible(dy, lddy, wt, ldwt, dx, lddx, n, h, wd, cout, cin, k))
+        return mi_tc_fprop(dy, lddy, wt, ldwt, nullptr, dx, lddx, mask_y, ldmask, mask_act, mask_slope, accumulate, n,
+                           h, wd, cout, cin, k, MI_ACT_NONE, 0.f, mi_cs(stream));
+    if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
+    return fprop_simt_launch(dy, lddy, wt, ldwt, nullptr, dx, lddx, mask_y, ldmask, mask_act, mask_slope, accumulate,
+                             n, h, wd, cout, cin, k, MI_ACT_NONE, 0.f, mi_cs(stream));
+}
+
+int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, mi_stream_t stream) {
+    if (!w || !wt || ldw < cin || ldwt < cout) return MI_ERR_BAD_ARG;
+    const long long total = (long long)cin * k * k * ldwt;
+    int blocks = mi_cdiv(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    weight_to_dgrad_kernel<<<blocks, 256, 0, mi_cs(stream)>>>(w, ldw, wt, ldwt, cin, cout, k);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k, int engine) {
+    (void)engine;
+    const int ldw = (cin + 3) & ~3;
+    const size_t splits = (size_t)mi_wgrad_splits(n, h, wd, cin, cout, k);
+    return splits * ((size_t)cout * k * k * ldw + (size_t)cout) * sizeof(float) + 256;
+}
+
+int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
+                    int k, int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in,
+                    const float* b_in, float* w_out, float* b_out, const float* lr_w, const float* lr_b,
+                    float* gsum_w, float* gsum_b, void* workspace, size_t workspace_bytes, int engine,
+                    mi_stream_t stream) {
+    if (!x || !dy || !workspace || n <= 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || (k & 1) == 0 ||
+        ldx < cin || lddy < cout || ldw < cin)
+        return MI_ERR_BAD_ARG;
+    if ((mode == MI_WG_STORE || mode == MI_WG_ACCUM) && (!grad_w)) return MI_ERR_BAD_ARG;
+    if ((mode == MI_WG_SGD_SCALAR || mode == MI_WG_SGD_TENSOR) && (!w_in || !w_out || !lr_w)) return MI_ERR_BAD_ARG;
+    const int splits = mi_wgrad_splits(n, h, wd, cin, cout, k);
+    const size_t wsz = (size_t)cout * k * k * ldw;
+    const size_t need = (size_t)splits * (wsz + cout) * sizeof(float);
+    if (workspace_bytes < need) return MI_ERR_WORKSPACE;
+    float* ws_w = reinterpret_cast<float*>(workspace);
+    float* ws_b = ws_w + (size_t)splits * wsz;
+    cudaStream_t st = mi_cs(stream);
+    int rc = MI_ERR_UNSUPPORTED;
+    if (engine != MI_ENGINE_SIMT && mi_tc_wgrad_eligible(x, ldx, dy, lddy, n, h, wd, cin, cout, k))
+        rc = mi_tc_wgrad_partials(x, ldx, dy, lddy, n, h, wd, cin, cout, k, ldw, ws_w, ws_b, splits, st);
+    if (rc == MI_ERR_UNSUPPORTED) {
+        if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
+        const long long m_total = (long long)n * h * wd;
+        long long chunk = (m_total + splits - 1) / splits;
+        chunk = (chunk + BK - 1) / BK * BK;
+        const int co_tiles = mi_cdiv(cout, BN), ci_tiles = mi_cdiv(cin, BM);
+        dim3 grid(k * k * co_tiles * ci_tiles, splits);
+        const int vec_x = (ldx % 4 == 0) && mi_al16(x);
+        const int vec_dy = (lddy % 4 == 0) && mi_al16(dy);
+        conv_wgrad_simt_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, ws_w, ws_b, n, h, wd, cin, cout, k, ldw,
+                                                     co_tiles, ci_tiles, chunk, vec_x, vec_dy);
+        MI_LAUNCHED();
+        rc = (int)cudaPeekAtLastError();
+    }
+    if (rc != 0) return rc;
+    return mi_wgrad_finish_launch(ws_w, ws_b, splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
+                                  w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, st);
+}
+
+int mi_version(void) { return 100; }
+
+unsigned long long mi_launch_count(void) { return g_mi_launches.load(); }
+
+const char* mi_error_string(int code) {
+    switch (code) {
+        case MI_OK: return "ok";
+        case MI_ERR_BAD_ARG: return "mi_b200: bad argument";
+        case MI_ERR_UNSUPPORTED: return "mi_b200: shape not supported by the requested engine";
+        case MI_ERR_WORKSPACE: return "mi_b200: workspace too small";
+        default: return cudaGetErrorString((cudaError_t)code);
+    }
+}
+
+}  // extern "C"

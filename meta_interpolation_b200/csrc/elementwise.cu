@@ -1,0 +1,548 @@
+// HBM-bound pointwise / resampling / loss / optimizer kernels (NHWC fp32).
+// One thread handles 4 consecutive channels of one pixel (float4 when the
+// strides allow), grids are sized in multiples of the 148 SMs.
+#include "mi_common.cuh"
+
+namespace {
+
+constexpr int TPB = 256;
+inline int grid_for(long long work) {
+    long long b = (work + TPB - 1) / TPB;
+    const long long cap = 148LL * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+#define GRID_STRIDE(i, total) \
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (total); i += (long long)gridDim.x * blockDim.x)
+
+// ----------------------------------------------------------------------------- pooling
+__global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
+                                    int wd, int c) {
+    const int oh = h >> 1, ow = wd >> 1;
+    const long long total = (long long)n * oh * ow * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        long long p = i / c;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        const float* s = x + ((long long)(nn * h + 2 * oy) * wd + 2 * ox) * ldx + ch;
+        const float v = (s[0] + s[ldx]) + (s[(long long)wd * ldx] + s[(long long)wd * ldx + ldx]);
+        y[((long long)(nn * oh + oy) * ow + ox) * ldy + ch] = 0.25f * v;
+    }
+}
+
+__global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
+                                    int accumulate, int n, int h, int wd, int c) {
+    const int oh = h >> 1, ow = wd >> 1;
+    const long long total = (long long)n * h * wd * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        long long p = i / c;
+        const int xx = (int)(p % wd); p /= wd;
+        const int yy = (int)(p % h);
+        const int nn = (int)(p / h);
+        float v = 0.f;
+        if ((yy >> 1) < oh && (xx >> 1) < ow)
+            v = 0.25f * dy[((long long)(nn * oh + (yy >> 1)) * ow + (xx >> 1)) * lddy + ch];
+        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + ch;
+        *d = accumulate ? *d + v : v;
+    }
+}
+
+__global__ void maxpool2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
+                                    int wd, int c) {
+    const int oh = h >> 1, ow = wd >> 1;
+    const long long total = (long long)n * oh * ow * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        long long p = i / c;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        const float* s = x + ((long long)(nn * h + 2 * oy) * wd + 2 * ox) * ldx + ch;
+        float m = s[0];
+        m = fmaxf(m, s[ldx]);
+        m = fmaxf(m, s[(long long)wd * ldx]);
+        m = fmaxf(m, s[(long long)wd * ldx + ldx]);
+        y[((long long)(nn * oh + oy) * ow + ox) * ldy + ch] = m;
+    }
+}
+
+// gradient goes to the FIRST maximal element in row-major window order (ATen max_pool2d semantics)
+__global__ void maxpool2_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
+                                    float* __restrict__ dx, int lddx, int accumulate, int n, int h, int wd, int c) {
+    const int oh = h >> 1, ow = wd >> 1;
+    const long long total = (long long)n * oh * ow * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        long long p = i / c;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        const long long base = ((long long)(nn * h + 2 * oy) * wd + 2 * ox);
+        const float* s = x + base * ldx + ch;
+        const float v[4] = {s[0], s[ldx], s[(long long)wd * ldx], s[(long long)wd * ldx + ldx]};
+        int arg = 0;
+        float m = v[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) if (v[q] > m) { m = v[q]; arg = q; }
+        const float g = dy[((long long)(nn * oh + oy) * ow + ox) * lddy + ch];
+        float* d = dx + base * lddx + ch;
+        const long long off[4] = {0, lddx, (long long)wd * lddx, (long long)wd * lddx + lddx};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float gv = (q == arg) ? g : 0.f;
+            d[off[q]] = accumulate ? d[off[q]] + gv : gv;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- bilinear x2
+// source coordinate of output index o (ATen upsample_bilinear2d, scale factor 2)
+__device__ __forceinline__ void up2_src(int o, int in_size, int align, int& i0, int& i1, float& t) {
+    float s;
+    if (align) {
+        const int out_size = in_size * 2;
+        const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+        s = scale * (float)o;
+    } else {
+        s = 0.5f * ((float)o + 0.5f) - 0.5f;
+        if (s < 0.f) s = 0.f;
+    }
+    i0 = (int)s;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    t = s - (float)i0;
+}
+
+__global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
+                                     int wd, int c, int align) {
+    const int oh = h * 2, ow = wd * 2;
+    const long long total = (long long)n * oh * ow * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        long long p = i / c;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        int y0, y1, x0, x1; float ty, tx;
+        up2_src(oy, h, align, y0, y1, ty);
+        up2_src(ox, wd, align, x0, x1, tx);
+        const float* b = x + (long long)nn * h * wd * ldx + ch;
+        const float v00 = b[((long long)y0 * wd + x0) * ldx], v01 = b[((long long)y0 * wd + x1) * ldx];
+        const float v10 = b[((long long)y1 * wd + x0) * ldx], v11 = b[((long long)y1 * wd + x1) * ldx];
+        const float v = (1.f - ty) * ((1.f - tx) * v00 + tx * v01) + ty * ((1.f - tx) * v10 + tx * v11);
+        y[((long long)(nn * oh + oy) * ow + ox) * ldy + ch] = v;
+    }
+}
+
+// gather form of the transpose: each input pixel collects from the <=3x3... output pixels that read it.
+// Output o reads inputs (i0,i1); the outputs that can touch input i lie in [2i-2, 2i+2] (align=False) or a
+// comparable window (align=True); we scan a conservative window and test membership exactly.
+__global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
+                                     int accumulate, int n, int h, int wd, int c, int align) {
+    const int oh = h * 2, ow = wd * 2;
+    const long long total = (long long)n * h * wd * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        long long p = i / c;
+        const int xx = (int)(p % wd); p /= wd;
+        const int yy = (int)(p % h);
+        const int nn = (int)(p / h);
+        float wy[6]; int oy_[6]; int ny = 0;
+        for (int o = max(0, 2 * yy - 3); o <= min(oh - 1, 2 * yy + 3); ++o) {
+            int a, b; float t; up2_src(o, h, align, a, b, t);
+            float wgt = 0.f;
+            if (a == yy) wgt += 1.f - t;
+            if (b == yy) wgt += t;
+            if (wgt != 0.f && ny < 6) { wy[ny] = wgt; oy_[ny] = o; ++ny; }
+        }
+        float wx[6]; int ox_[6]; int nx = 0;
+        for (int o = max(0, 2 * xx - 3); o <= min(ow - 1, 2 * xx + 3); ++o) {
+            int a, b; float t; up2_src(o, wd, align, a, b, t);
+            float wgt = 0.f;
+            if (a == xx) wgt += 1.f - t;
+            if (b == xx) wgt += t;
+            if (wgt != 0.f && nx < 6) { wx[nx] = wgt; ox_[nx] = o; ++nx; }
+        }
+        float acc = 0.f;
+        for (int a = 0; a < ny; ++a)
+            for (int b = 0; b < nx; ++b)
+                acc += wy[a] * wx[b] * dy[((long long)(nn * oh + oy_[a]) * ow + ox_[b]) * lddy + ch];
+        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + ch;
+        *d = accumulate ? *d + acc : acc;
+    }
+}
+
+// ----------------------------------------------------------------------------- simple pointwise
+__global__ void add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                           float* __restrict__ y, int ldy, long long pixels, int c) {
+    const long long total = pixels * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        const long long p = i / c;
+        y[p * ldy + ch] = a[p * lda + ch] + b[p * ldb + ch];
+    }
+}
+
+__global__ void copy_kernel(const float* __restrict__ s, int lds, float* __restrict__ d, int ldd, int accumulate,
+                            long long pixels, int c) {
+    const long long total = pixels * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        const long long p = i / c;
+        const float v = s[p * lds + ch];
+        float* q = d + p * ldd + ch;
+        *q = accumulate ? *q + v : v;
+    }
+}
+
+__global__ void act_bwd_kernel(float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
+                               float slope, long long pixels, int c) {
+    const long long total = pixels * c;
+    GRID_STRIDE(i, total) {
+        const int ch = (int)(i % c);
+        const long long p = i / c;
+        dy[p * lddy + ch] *= mi_act_grad(y[p * ldy + ch], act, slope);
+    }
+}
+
+__global__ void fill_kernel(float* __restrict__ p, float v, long long count) {
+    GRID_STRIDE(i, count) p[i] = v;
+}
+
+__global__ void axpby_kernel(const float* __restrict__ x, float a, float* __restrict__ y, float b, long long count) {
+    GRID_STRIDE(i, count) y[i] = a * x[i] + (b == 0.f ? 0.f : b * y[i]);
+}
+
+__global__ void addcmul_kernel(float* __restrict__ y, float a, const float* __restrict__ x1,
+                               const float* __restrict__ x2, long long count) {
+    GRID_STRIDE(i, count) y[i] = fmaf(a * x1[i], x2[i], y[i]);
+}
+
+// ----------------------------------------------------------------------------- frames <-> NHWC
+__device__ __forceinline__ int reflect_idx(int i, int nsz) {
+    if (nsz == 1) return 0;
+    while (i < 0 || i >= nsz) {
+        if (i < 0) i = -i;
+        if (i >= nsz) i = 2 * (nsz - 1) - i;
+    }
+    return i;
+}
+
+__global__ void frames_to_canvas_kernel(const float* __restrict__ f0, const float* __restrict__ f1,
+                                        float* __restrict__ canvas, int ldc, int n, int h, int wd, int ch, int cw,
+                                        int pad_top, int pad_left, int mode) {
+    const long long total = (long long)n * ch * cw;
+    GRID_STRIDE(i, total) {
+        long long p = i;
+        const int x = (int)(p % cw); p /= cw;
+        const int y = (int)(p % ch);
+        const int nn = (int)(p / ch);
+        int sy = y - pad_top, sx = x - pad_left;
+        if (mode == 0) {
+            sy = min(max(sy, 0), h - 1);
+            sx = min(max(sx, 0), wd - 1);
+        } else {
+            sy = reflect_idx(sy, h);
+            sx = reflect_idx(sx, wd);
+        }
+        const long long plane = (long long)h * wd;
+        const long long src = (long long)nn * 3 * plane + (long long)sy * wd + sx;
+        float* d = canvas + i * ldc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            d[c] = f0[src + c * plane];
+            d[3 + c] = f1[src + c * plane];
+        }
+        for (int c = 6; c < ldc; ++c) d[c] = 0.f;
+    }
+}
+
+__global__ void nhwc_window_to_nchw_kernel(const float* __restrict__ s, int lds, float* __restrict__ d, int n, int hs,
+                                           int ws, int y0, int x0, int h, int wd, int c) {
+    const long long total = (long long)n * c * h * wd;
+    GRID_STRIDE(i, total) {
+        long long p = i;
+        const int x = (int)(p % wd); p /= wd;
+        const int y = (int)(p % h); p /= h;
+        const int cc = (int)(p % c);
+        const int nn = (int)(p / c);
+        d[i] = s[((long long)(nn * hs + y0 + y) * ws + x0 + x) * lds + cc];
+    }
+}
+
+__global__ void nchw_to_nhwc_window_kernel(const float* __restrict__ s, float* __restrict__ d, int ldd, int n, int hs,
+                                           int ws, int y0, int x0, int h, int wd, int c) {
+    const long long total = (long long)n * c * h * wd;
+    GRID_STRIDE(i, total) {
+        long long p = i;
+        const int x = (int)(p % wd); p /= wd;
+        const int y = (int)(p % h); p /= h;
+        const int cc = (int)(p % c);
+        const int nn = (int)(p / c);
+        d[((long long)(nn * hs + y0 + y) * ws + x0 + x) * ldd + cc] = s[i];
+    }
+}
+
+// ----------------------------------------------------------------------------- loss / metrics
+__global__ void loss_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                    float* __restrict__ grad, float* __restrict__ loss_out, long long count, int kind,
+                                    float weight) {
+    const float inv = 1.f / (float)count;
+    float local = 0.f;
+    GRID_STRIDE(i, count) {
+        const float d = pred[i] - target[i];
+        if (kind == 0) {
+            local += fabsf(d);
+            if (grad) grad[i] = weight * inv * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        } else {
+            local += d * d;
+            if (grad) grad[i] = weight * inv * 2.f * d;
+        }
+    }
+    __shared__ float red[TPB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < TPB / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(loss_out, weight * inv * v);
+    }
+}
+
+__global__ void psnr_accumulate_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                       double* __restrict__ sq_out, long long count) {
+    double local = 0.0;
+    GRID_STRIDE(i, count) {
+        const float qp = rintf(fminf(fmaxf(pred[i] * 255.f, 0.f), 255.f));
+        const float qt = rintf(fminf(fmaxf(target[i] * 255.f, 0.f), 255.f));
+        const float d = (qp - qt) / 255.f;
+        local += (double)(d * d);
+    }
+    __shared__ double red[TPB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int q = 0; q < TPB / 32; ++q) v += red[q];
+        atomicAdd(sq_out, v);
+    }
+}
+
+// ----------------------------------------------------------------------------- inner-loop rules (flat arena)
+__global__ void inner_update_kernel(const float* __restrict__ w_in, const float* __restrict__ g,
+                                    float* __restrict__ w_out, float* __restrict__ exp_avg,
+                                    float* __restrict__ exp_avg_sq, const float* __restrict__ lr, int lr_per_element,
+                                    int lr_stride, int num_step, const int32_t* __restrict__ seg,
+                                    const uint8_t* __restrict__ skip, long long count, int rule, float bc1,
+                                    float bc2_sqrt) {
+    const float b1 = 0.9f, b2 = 0.99f, eps = 1e-8f;
+    GRID_STRIDE(i, count) {
+        const int t = seg[i >> 10];
+        const float w = w_in[i];
+        if (t < 0 || (skip && skip[t])) { w_out[i] = w; continue; }
+        const float l = lr_per_element ? lr[i] : lr[(long long)t * lr_stride + num_step];
+        const float gi = g[i];
+        float o;
+        if (rule == 0) {
+            o = w - l * gi;
+        } else if (rule == 1) {
+            const float m = b1 * exp_avg[i] + (1.f - b1) * gi;
+            const float v = b2 * exp_avg_sq[i] + (1.f - b2) * gi * gi;
+            exp_avg[i] = m;
+            exp_avg_sq[i] = v;
+            const float denom = sqrtf(v) / bc2_sqrt + eps;
+            o = w - (l / bc1) * m / denom;
+        } else if (rule == 2) {
+            const float m = b1 * exp_avg[i] + (1.f - b1) * gi;
+            exp_avg[i] = m;
+            o = w - (l / bc1) * m / (fabsf(gi) + eps);
+        } else {
+            const float m = (1.f - b1) * gi;
+            o = w - (l / bc1) * m / (fabsf(gi) + eps);
+        }
+        w_out[i] = o;
+    }
+}
+
+__global__ void outer_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, long long count, int kind, float lr, float b1, float b2,
+                                  float eps, float wd, float step_size, float bc2_sqrt) {
+    GRID_STRIDE(i, count) {
+        float gi = g[i];
+        float pi = p[i];
+        if (wd != 0.f) gi += wd * pi;
+        if (kind == 0) {
+            pi -= lr * gi;
+        } else if (kind == 1) {  // torch.optim.Adam (amsgrad off)
+            const float mi = b1 * m[i] + (1.f - b1) * gi;
+            const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+            m[i] = mi; v[i] = vi;
+            const float denom = sqrtf(vi) / bc2_sqrt + eps;
+            pi -= step_size * (mi / denom);
+        } else {                 // torch.optim.Adamax
+            const float mi = b1 * m[i] + (1.f - b1) * gi;
+            const float ui = fmaxf(b2 * v[i], fabsf(gi) + eps);
+            m[i] = mi; v[i] = ui;
+            pi -= step_size * (mi / ui);
+        }
+        p[i] = pi;
+    }
+}
+
+__global__ void segment_dot_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                   const int32_t* __restrict__ seg, float* __restrict__ out, long long count) {
+    // one block per 1024-float chunk (chunks never straddle tensors)
+    const long long chunk = blockIdx.x;
+    const long long base = chunk << 10;
+    const int t = seg[chunk];
+    if (t < 0) return;
+    float local = 0.f;
+    for (int q = threadIdx.x; q < 1024; q += blockDim.x) {
+        const long long i = base + q;
+        if (i < count) local += a[i] * b[i];
+    }
+    __shared__ float red[TPB / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int q = 0; q < TPB / 32; ++q) v += red[q];
+        atomicAdd(out + t, v);
+    }
+}
+
+}  // namespace
+
+#define LAUNCH(kernel, work, stream, ...)                                      \
+    do {                                                                       \
+        kernel<<<grid_for(work), TPB, 0, mi_cs(stream)>>>(__VA_ARGS__);        \
+        MI_LAUNCHED();                                                         \
+        MI_RETURN_LAST();                                                      \
+    } while (0)
+
+extern "C" {
+
+int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t s) {
+    if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
+    LAUNCH(avgpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * c, s, x, ldx, y, ldy, n, h, wd, c);
+}
+int mi_avgpool2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
+                    mi_stream_t s) {
+    if (!dy || !dx || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
+    LAUNCH(avgpool2_bwd_kernel, (long long)n * h * wd * c, s, dy, lddy, dx, lddx, accumulate, n, h, wd, c);
+}
+int mi_maxpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t s) {
+    if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
+    LAUNCH(maxpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * c, s, x, ldx, y, ldy, n, h, wd, c);
+}
+int mi_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx, int accumulate, int n,
+                    int h, int wd, int c, mi_stream_t s) {
+    if (!x || !dy || !dx || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
+    LAUNCH(maxpool2_bwd_kernel, (long long)n * (h / 2) * (wd / 2) * c, s, x, ldx, dy, lddy, dx, lddx, accumulate, n, h,
+           wd, c);
+}
+int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align,
+                     mi_stream_t s) {
+    if (!x || !y) return MI_ERR_BAD_ARG;
+    LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * c, s, x, ldx, y, ldy, n, h, wd, c, align);
+}
+int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
+                     int align, mi_stream_t s) {
+    if (!dy || !dx) return MI_ERR_BAD_ARG;
+    LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * c, s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align);
+}
+int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t s) {
+    if (!a || !b || !y) return MI_ERR_BAD_ARG;
+    LAUNCH(add_kernel, (long long)pixels * c, s, a, lda, b, ldb, y, ldy, (long long)pixels, c);
+}
+int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size_t pixels, int c, mi_stream_t s) {
+    if (!src || !dst) return MI_ERR_BAD_ARG;
+    LAUNCH(copy_kernel, (long long)pixels * c, s, src, lds, dst, ldd, accumulate, (long long)pixels, c);
+}
+int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c,
+               mi_stream_t s) {
+    if (!dy || !y) return MI_ERR_BAD_ARG;
+    if (act == MI_ACT_NONE) return MI_OK;
+    LAUNCH(act_bwd_kernel, (long long)pixels * c, s, dy, lddy, y, ldy, act, slope, (long long)pixels, c);
+}
+int mi_fill(float* p, float v, size_t count, mi_stream_t s) {
+    if (!p) return MI_ERR_BAD_ARG;
+    if (count == 0) return MI_OK;
+    LAUNCH(fill_kernel, (long long)count, s, p, v, (long long)count);
+}
+int mi_axpby(const float* x, float a, float* y, float b, size_t count, mi_stream_t s) {
+    if (!x || !y) return MI_ERR_BAD_ARG;
+    if (count == 0) return MI_OK;
+    LAUNCH(axpby_kernel, (long long)count, s, x, a, y, b, (long long)count);
+}
+int mi_addcmul(float* y, float a, const float* x1, const float* x2, size_t count, mi_stream_t s) {
+    if (!y || !x1 || !x2) return MI_ERR_BAD_ARG;
+    if (count == 0) return MI_OK;
+    LAUNCH(addcmul_kernel, (long long)count, s, y, a, x1, x2, (long long)count);
+}
+int mi_frames_to_canvas(const float* f0, const float* f1, float* canvas, int ldc, int n, int h, int wd, int ch, int cw,
+                        int pad_top, int pad_left, int mode, mi_stream_t s) {
+    if (!f0 || !f1 || !canvas || ldc < 6) return MI_ERR_BAD_ARG;
+    LAUNCH(frames_to_canvas_kernel, (long long)n * ch * cw, s, f0, f1, canvas, ldc, n, h, wd, ch, cw, pad_top,
+           pad_left, mode);
+}
+int mi_nhwc_window_to_nchw(const float* src, int lds, float* dst, int n, int hs, int ws, int y0, int x0, int h, int wd,
+                           int c, mi_stream_t s) {
+    if (!src || !dst || y0 < 0 || x0 < 0 || y0 + h > hs || x0 + wd > ws) return MI_ERR_BAD_ARG;
+    LAUNCH(nhwc_window_to_nchw_kernel, (long long)n * c * h * wd, s, src, lds, dst, n, hs, ws, y0, x0, h, wd, c);
+}
+int mi_nchw_to_nhwc_window(const float* src, float* dst, int ldd, int n, int hs, int ws, int y0, int x0, int h, int wd,
+                           int c, mi_stream_t s) {
+    if (!src || !dst || y0 < 0 || x0 < 0 || y0 + h > hs || x0 + wd > ws) return MI_ERR_BAD_ARG;
+    LAUNCH(nchw_to_nhwc_window_kernel, (long long)n * c * h * wd, s, src, dst, ldd, n, hs, ws, y0, x0, h, wd, c);
+}
+int mi_loss_fwd_bwd(const float* pred, const float* target, float* grad, float* loss_out, size_t count, int kind,
+                    float weight, mi_stream_t s) {
+    if (!pred || !target || !loss_out || count == 0 || (kind != 0 && kind != 1)) return MI_ERR_BAD_ARG;
+    LAUNCH(loss_fwd_bwd_kernel, (long long)count, s, pred, target, grad, loss_out, (long long)count, kind, weight);
+}
+int mi_psnr_accumulate(const float* pred, const float* target, double* sq_out, size_t count, mi_stream_t s) {
+    if (!pred || !target || !sq_out) return MI_ERR_BAD_ARG;
+    LAUNCH(psnr_accumulate_kernel, (long long)count, s, pred, target, sq_out, (long long)count);
+}
+int mi_inner_update(const float* w_in, const float* g, float* w_out, float* exp_avg, float* exp_avg_sq,
+                    const float* lr, int lr_per_element, int lr_stride, int num_step, const int32_t* seg,
+                    const uint8_t* skip, size_t count, int rule, int step_count, mi_stream_t s) {
+    if (!w_in || !g || !w_out || !lr || !seg || rule < 0 || rule > 3) return MI_ERR_BAD_ARG;
+    if ((rule == 1 && (!exp_avg || !exp_avg_sq)) || (rule == 2 && !exp_avg)) return MI_ERR_BAD_ARG;
+    // bias corrections in double on the host, as the reference computes them in Python floats
+    const float bc1 = (float)(1.0 - pow(0.9, (double)step_count));
+    const float bc2s = (float)sqrt(1.0 - pow(0.99, (double)step_count));
+    LAUNCH(inner_update_kernel, (long long)count, s, w_in, g, w_out, exp_avg, exp_avg_sq, lr, lr_per_element,
+           lr_stride, num_step, seg, skip, (long long)count, rule, bc1, bc2s);
+}
+int mi_outer_step(float* p, const float* g, float* m, float* v, size_t count, int kind, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int step, mi_stream_t s) {
+    if (!p || !g || kind < 0 || kind > 2 || (kind > 0 && (!m || !v))) return MI_ERR_BAD_ARG;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const float step_size = (float)((double)lr / bc1);
+    const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    LAUNCH(outer_step_kernel, (long long)count, s, p, g, m, v, (long long)count, kind, lr, beta1, beta2, eps,
+           weight_decay, step_size, bc2s);
+}
+int mi_segment_dot(const float* a, const float* b, const int32_t* seg, float* out, size_t count, mi_stream_t s) {
+    if (!a || !b || !seg || !out) return MI_ERR_BAD_ARG;
+    const int chunks = (int)((count + 1023) >> 10);
+    segment_dot_kernel<<<chunks, TPB, 0, mi_cs(s)>>>(a, b, seg, out, (long long)count);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+}  // extern "C"

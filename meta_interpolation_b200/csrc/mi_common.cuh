@@ -1,0 +1,58 @@
+// Shared helpers for libmi_b200 (sm_100a).  Host-side launch bookkeeping and
+// small device utilities used by every translation unit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include "../../include/mi_b200.h"
+
+extern std::atomic<unsigned long long> g_mi_launches;
+
+#define MI_LAUNCHED() (g_mi_launches.fetch_add(1, std::memory_order_relaxed))
+#define MI_RETURN_LAST()                         \
+    do {                                         \
+        cudaError_t e__ = cudaPeekAtLastError(); \
+        return (int)e__;                         \
+    } while (0)
+
+static inline cudaStream_t mi_cs(mi_stream_t s) { return (cudaStream_t)s; }
+static inline int mi_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline bool mi_al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+__device__ __forceinline__ float mi_act_apply(float v, int act, float slope) {
+    switch (act) {
+        case MI_ACT_RELU: return v > 0.f ? v : 0.f;
+        case MI_ACT_LEAKY: return v > 0.f ? v : v * slope;
+        case MI_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+        case MI_ACT_TANH: return tanhf(v);
+        default: return v;
+    }
+}
+// derivative expressed through the POST-activation value y
+__device__ __forceinline__ float mi_act_grad(float y, int act, float slope) {
+    switch (act) {
+        case MI_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+        case MI_ACT_LEAKY: return y > 0.f ? 1.f : slope;
+        case MI_ACT_SIGMOID: return y * (1.f - y);
+        case MI_ACT_TANH: return 1.f - y * y;
+        default: return 1.f;
+    }
+}
+
+// shared by the SIMT and tcgen05 weight-gradient paths (conv_simt.cu)
+int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int cin, int cout, int k, int ldw,
+                           int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
+                           float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
+                           float* gsum_b, cudaStream_t stream);
+int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k);
+
+// tcgen05 entry points (conv_tc.cu); return MI_ERR_UNSUPPORTED when the shape is not eligible
+int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+                const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate,
+                int n, int h, int wd, int cin, int cout, int k, int act, float slope, cudaStream_t stream);
+int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
+                         int k, int ldw, float* ws_w, float* ws_b, int splits, cudaStream_t stream);
+bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, const float* y, int ldy, int n, int h,
+                          int wd, int cin, int cout, int k);
+bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
+                          int k);

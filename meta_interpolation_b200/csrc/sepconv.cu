@@ -1,0 +1,266 @@
+// Adaptive separable convolution (SepConv local filtering), forward and the
+// fused gradVertical/gradHorizontal backward.
+//
+// Replaces the reference's cupy-JIT kernels (sepconv/sepconv_op/sepconv.py:5-30,
+// 138-190).  Those run one thread per output with 2601 taps x 3 global loads;
+// here the 51x51 window of a 32x8 pixel tile is staged once in shared memory
+// (replicate border folded into the staging, so the doubly padded frame of
+// sepconv/model.py:244-245,261-263 is never materialised), the per-pixel
+// horizontal filter lives in registers and the sum is factorised as
+//   out = sum_fy v[fy] * (sum_fx in[y+fy][x+fx] * h[fx])          (SURVEY Appx E1)
+// The op has no GEMM structure (filters differ per pixel) and is bound by the
+// FP32 FMA pipe / shared-memory bandwidth, not HBM.
+#include "mi_common.cuh"
+
+namespace {
+
+constexpr int TX = 32;
+constexpr int TY = 8;
+
+template <int F>
+struct Geo {
+    static constexpr int WIN_W = TX + F - 1;
+    static constexpr int WIN_H = TY + F - 1;
+    static constexpr int PITCH = WIN_W + 1;  // odd pitch
+};
+
+template <int F>
+__device__ __forceinline__ void stage_window(float* smem, const float* __restrict__ frame, int c, int fh, int fw,
+                                             int n_idx, int y_base, int x_base) {
+    constexpr int WW = Geo<F>::WIN_W, WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    const long long plane = (long long)fh * fw;
+    const float* fb = frame + (long long)n_idx * c * plane;
+    for (int i = threadIdx.x; i < c * WH * WW; i += blockDim.x) {
+        const int col = i % WW;
+        const int r = (i / WW) % WH;
+        const int cc = i / (WW * WH);
+        int sy = y_base + r, sx = x_base + col;
+        sy = min(max(sy, 0), fh - 1);
+        sx = min(max(sx, 0), fw - 1);
+        smem[(cc * WH + r) * P + col] = fb[cc * plane + (long long)sy * fw + sx];
+    }
+}
+
+template <int F, int C>
+__global__ void __launch_bounds__(TX* TY)
+sepconv_fwd_kernel(const float* __restrict__ frame, const float* __restrict__ vert, const float* __restrict__ horiz,
+                   int ldf, float* __restrict__ out, int fh, int fw, int gh, int gw, int oh, int ow, int gy0, int gx0,
+                   int iy0, int ix0) {
+    extern __shared__ float smem[];
+    constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    const int n_idx = blockIdx.z;
+    const int ty = threadIdx.x / TX, tx = threadIdx.x % TX;
+    const int oy_base = blockIdx.y * TY, ox_base = blockIdx.x * TX;
+    stage_window<F>(smem, frame, C, fh, fw, n_idx, oy_base + iy0, ox_base + ix0);
+    __syncthreads();
+    const int oy = oy_base + ty, ox = ox_base + tx;
+    if (oy >= oh || ox >= ow) return;
+    const long long gpix = ((long long)n_idx * gh + gy0 + oy) * gw + gx0 + ox;
+    const float* hp = horiz + gpix * ldf;
+    const float* vp = vert + gpix * ldf;
+    float hreg[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) hreg[f] = __ldg(hp + f);
+    float acc[C];
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) acc[cc] = 0.f;
+    for (int fy = 0; fy < F; ++fy) {
+        const float vv = __ldg(vp + fy);
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            const float* row = smem + (cc * WH + ty + fy) * P + tx;
+            float t = 0.f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) t = fmaf(row[f], hreg[f], t);
+            acc[cc] = fmaf(vv, t, acc[cc]);
+        }
+    }
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) out[(((long long)n_idx * C + cc) * oh + oy) * ow + ox] = acc[cc];
+}
+
+template <int F, int C>
+__global__ void __launch_bounds__(TX* TY)
+sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ vert, const float* __restrict__ horiz,
+                   int ldf, const float* __restrict__ grad_out, float* __restrict__ g_vert,
+                   float* __restrict__ g_horiz, int ldg, int fh, int fw, int gh, int gw, int oh, int ow, int gy0,
+                   int gx0, int iy0, int ix0) {
+    extern __shared__ float smem[];
+    constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    const int n_idx = blockIdx.z;
+    const int ty = threadIdx.x / TX, tx = threadIdx.x % TX;
+    const int oy_base = blockIdx.y * TY, ox_base = blockIdx.x * TX;
+    stage_window<F>(smem, frame, C, fh, fw, n_idx, oy_base + iy0, ox_base + ix0);
+    __syncthreads();
+    const int oy = oy_base + ty, ox = ox_base + tx;
+    if (oy >= oh || ox >= ow) return;
+    const long long gpix = ((long long)n_idx * gh + gy0 + oy) * gw + gx0 + ox;
+    const float* hp = horiz + gpix * ldf;
+    const float* vp = vert + gpix * ldf;
+    float hreg[F], gh_acc[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) { hreg[f] = __ldg(hp + f); gh_acc[f] = 0.f; }
+    float go[C];
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) go[cc] = grad_out[(((long long)n_idx * C + cc) * oh + oy) * ow + ox];
+    float* gvp = g_vert + gpix * ldg;
+    for (int fy = 0; fy < F; ++fy) {
+        const float vv = __ldg(vp + fy);
+        float gv = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            const float* row = smem + (cc * WH + ty + fy) * P + tx;
+            const float gvc = go[cc] * vv;
+            float t = 0.f;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const float in = row[f];
+                t = fmaf(in, hreg[f], t);
+                gh_acc[f] = fmaf(gvc, in, gh_acc[f]);
+            }
+            gv = fmaf(go[cc], t, gv);
+        }
+        gvp[fy] = gv;
+    }
+    float* ghp = g_horiz + gpix * ldg;
+#pragma unroll
+    for (int f = 0; f < F; ++f) ghp[f] = gh_acc[f];
+}
+
+// any filter size / channel count: one thread per output pixel straight from global memory
+__global__ void sepconv_fwd_generic_kernel(const float* __restrict__ frame, const float* __restrict__ vert,
+                                           const float* __restrict__ horiz, int ldf, float* __restrict__ out, int n,
+                                           int c, int fh, int fw, int gh, int gw, int oh, int ow, int gy0, int gx0,
+                                           int iy0, int ix0, int taps) {
+    const long long total = (long long)n * c * oh * ow;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh); p /= oh;
+        const int cc = (int)(p % c);
+        const int nn = (int)(p / c);
+        const long long gpix = ((long long)nn * gh + gy0 + oy) * gw + gx0 + ox;
+        const float* fb = frame + ((long long)nn * c + cc) * fh * fw;
+        float acc = 0.f;
+        for (int fy = 0; fy < taps; ++fy) {
+            const int sy = min(max(oy + iy0 + fy, 0), fh - 1);
+            float t = 0.f;
+            for (int fx = 0; fx < taps; ++fx) {
+                const int sx = min(max(ox + ix0 + fx, 0), fw - 1);
+                t = fmaf(fb[(long long)sy * fw + sx], horiz[gpix * ldf + fx], t);
+            }
+            acc = fmaf(vert[gpix * ldf + fy], t, acc);
+        }
+        out[i] = acc;
+    }
+}
+
+__global__ void sepconv_bwd_generic_kernel(const float* __restrict__ frame, const float* __restrict__ vert,
+                                           const float* __restrict__ horiz, int ldf,
+                                           const float* __restrict__ grad_out, float* __restrict__ g_vert,
+                                           float* __restrict__ g_horiz, int ldg, int n, int c, int fh, int fw, int gh,
+                                           int gw, int oh, int ow, int gy0, int gx0, int iy0, int ix0, int taps) {
+    // one thread per (pixel, tap index k): computes g_vert[k] and g_horiz[k]
+    const long long total = (long long)n * oh * ow * taps;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long p = i;
+        const int kidx = (int)(p % taps); p /= taps;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        const long long gpix = ((long long)nn * gh + gy0 + oy) * gw + gx0 + ox;
+        float av = 0.f, ah = 0.f;
+        for (int cc = 0; cc < c; ++cc) {
+            const float* fb = frame + ((long long)nn * c + cc) * fh * fw;
+            const float go = grad_out[(((long long)nn * c + cc) * oh + oy) * ow + ox];
+            const int syk = min(max(oy + iy0 + kidx, 0), fh - 1);
+            const int sxk = min(max(ox + ix0 + kidx, 0), fw - 1);
+            float tv = 0.f, th = 0.f;
+            for (int j = 0; j < taps; ++j) {
+                const int sxj = min(max(ox + ix0 + j, 0), fw - 1);
+                const int syj = min(max(oy + iy0 + j, 0), fh - 1);
+                tv = fmaf(fb[(long long)syk * fw + sxj], horiz[gpix * ldf + j], tv);
+                th = fmaf(fb[(long long)syj * fw + sxk], vert[gpix * ldf + j], th);
+            }
+            av = fmaf(go, tv, av);
+            ah = fmaf(go, th, ah);
+        }
+        g_vert[gpix * ldg + kidx] = av;
+        g_horiz[gpix * ldg + kidx] = ah;
+    }
+}
+
+template <int F>
+size_t smem_bytes(int c) { return (size_t)c * Geo<F>::WIN_H * Geo<F>::PITCH * sizeof(float); }
+
+bool args_ok(const void* a, const void* b, const void* c, int n, int ch, int fh, int fw, int gh, int gw, int oh,
+             int ow, int gy0, int gx0, int taps, int ld) {
+    return a && b && c && n > 0 && ch > 0 && fh > 0 && fw > 0 && oh > 0 && ow > 0 && taps > 0 && ld >= taps &&
+           gy0 >= 0 && gx0 >= 0 && gy0 + oh <= gh && gx0 + ow <= gw;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, int ldf, float* out, int n, int c,
+                   int fh, int fw, int gh, int gw, int oh, int ow, int gy0, int gx0, int iy0, int ix0, int taps,
+                   mi_stream_t stream) {
+    if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !out) return MI_ERR_BAD_ARG;
+    cudaStream_t st = mi_cs(stream);
+    if (taps == 51 && c == 3) {
+        static bool attr_set = false;
+        const size_t sm = smem_bytes<51>(3);
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(sepconv_fwd_kernel<51, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sm);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY), n);
+        sepconv_fwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, out, fh, fw, gh, gw, oh, ow, gy0,
+                                                             gx0, iy0, ix0);
+    } else {
+        const long long total = (long long)n * c * oh * ow;
+        int blocks = mi_cdiv(total, 128);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        sepconv_fwd_generic_kernel<<<blocks, 128, 0, st>>>(frame, vert, horiz, ldf, out, n, c, fh, fw, gh, gw, oh, ow,
+                                                           gy0, gx0, iy0, ix0, taps);
+    }
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
+                   float* g_vert, float* g_horiz, int ldg, int n, int c, int fh, int fw, int gh, int gw, int oh,
+                   int ow, int gy0, int gx0, int iy0, int ix0, int taps, mi_stream_t stream) {
+    if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !grad_out || !g_vert ||
+        !g_horiz || ldg < taps)
+        return MI_ERR_BAD_ARG;
+    cudaStream_t st = mi_cs(stream);
+    if (taps == 51 && c == 3) {
+        static bool attr_set = false;
+        const size_t sm = smem_bytes<51>(3);
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(sepconv_bwd_kernel<51, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sm);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY), n);
+        sepconv_bwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz, ldg,
+                                                             fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
+    } else {
+        const long long total = (long long)n * oh * ow * taps;
+        int blocks = mi_cdiv(total, 128);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        sepconv_bwd_generic_kernel<<<blocks, 128, 0, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz, ldg, n,
+                                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps);
+    }
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+"""Graph-captured executor of the MAML inner loop (the hot path proper).
+
+For one task (reference meta_learning_system.py:366-461) it runs
+
+    K x [ support step: both support triplets batched as N=2 ->
+            forward, L1/MSE value+gradient, backward, and the inner update fused into the
+            weight-gradient finishing kernel (w <- w - lr*g written straight into the
+            fast-weight arena; no elementwise launch between inner steps) ]
+    (+ per-step query passes when the MAML++ multi-step loss is active)
+    1 x [ query pass: forward, loss, backward; outer gradients accumulated with scale
+            1/B into the flat meta-gradient buffer ]
+
+Each bracket is one CUDA graph, captured the second time it is needed and replayed
+afterwards; frames are copied into static input buffers before a replay.  Fast
+weights live in ONE arena updated in place after step 0 (step 0 reads the
+meta-parameters and writes the arena), so three support graphs/two query graphs cover
+any K.  Un-routed tensors read the meta arena and skip
+their dead inner-loop weight gradients; the query pass differentiates everything.
+
+First-order outer gradients follow SURVEY Appendix E4:
+  LSLR fixed lr      dL/dtheta = G
+  LSLR learnable lr  + dL/dlr[t][k] = -<g_k[t], G[t]>
+  Meta-SGD (SGD)     + dL/dalpha    = -(sum_k g_k) (.) G
+  multi-step loss    the above per step with weight w_k.
+"""
+import torch
+
+from . import utils
+from .arena import Arena
+from .ops import WG_ACCUM, WG_SGD_SCALAR, WG_SGD_TENSOR, WG_STORE, WgradSpec
+from .tape import ConvParam, Tape
+
+LOSS_KIND = {'L1': 0, 'MSE': 1}
+
+
+class _Sink:
+    """Weight-gradient policy handed to the tape."""
+
+    def __init__(self, fp, mode, step=0, scale=1.0, src=None):
+        self.fp, self.mode, self.step, self.scale, self.src = fp, mode, step, scale, src
+
+    def weight_grad(self, p, x, dy, k):
+        fp = self.fp
+        net = fp.net
+        wn, bn = p.name + ".weight", p.name + ".bias"
+        has_b = p.b is not None
+        ldw = p.w.stride(2)
+        if self.mode == 'inner':
+            if not net.is_routed(wn):
+                return                       # dead work in support passes (Q1/Q2/Q2b)
+            fast = fp.fast
+            spec = WgradSpec(w_in=p.w, b_in=p.b, w_out=fast.kernel_view(wn),
+                             b_out=fast.kernel_view(bn) if has_b else None)
+            if fp.metasgd:
+                spec.mode = WG_SGD_TENSOR
+                spec.lr_w = fp.sys.alpha.kernel_view(wn)
+                spec.lr_b = fp.sys.alpha.kernel_view(bn) if has_b else None
+                spec.gsum_w = fp.gsum.kernel_view(wn)
+                spec.gsum_b = fp.gsum.kernel_view(bn) if has_b else None
+            else:
+                spec.mode = WG_SGD_SCALAR
+                iw = net.layout.index(wn)
+                spec.lr_w = fp.cur_lr[iw:iw + 1]
+                if has_b:
+                    ib = net.layout.index(bn)
+                    spec.lr_b = fp.cur_lr[ib:ib + 1]
+                if fp.learnable_lr:
+                    garena = fp.gsteps[self.step]
+                    spec.grad_w = garena.kernel_view(wn)
+                    spec.grad_b = garena.kernel_view(bn) if has_b else None
+            fp.ops.conv_wgrad(x, dy, k, ldw, spec)
+        elif self.mode == 'accum':
+            garena = fp.sys.net_grad
+            spec = WgradSpec(WG_ACCUM, scale=self.scale, grad_w=garena.kernel_view(wn),
+                             grad_b=garena.kernel_view(bn) if has_b else None)
+            fp.ops.conv_wgrad(x, dy, k, ldw, spec)
+        else:   # 'store': per-task query gradient G (needed for lr / alpha outer gradients)
+            garena = fp.gquery
+            spec = WgradSpec(WG_STORE, grad_w=garena.kernel_view(wn), grad_b=garena.kernel_view(bn) if has_b else None)
+            fp.ops.conv_wgrad(x, dy, k, ldw, spec)
+
+
+class _Program:
+    """One capturable unit: static inputs, a body, static outputs."""
+
+    def __init__(self, fp, body, n, h, w):
+        dev = fp.ops.device
+        self.f0 = torch.zeros(n, 3, h, w, device=dev)
+        self.f1 = torch.zeros(n, 3, h, w, device=dev)
+        self.tgt = torch.zeros(n, 3, h, w, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.pred = None
+        self.body = body
+        self.graph = None
+        self.calls = 0
+        self.fp = fp
+
+    def run(self):
+        fp = self.fp
+        self.calls += 1
+        if not fp.use_graphs or self.calls == 1:
+            self.body(self)                      # eager (also sizes workspaces before a capture)
+            return
+        if self.graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.body(self)
+            self.graph = g
+        self.graph.replay()
+
+
+class FastPath:
+    @staticmethod
+    def supports(system):
+        a = system.args
+        if a.second_order and system.current_epoch > a.first_order_to_second_order_epoch:
+            return False
+        if a.optimizer != 'SGD' or a.attenuate:
+            return False
+        if not all(t.split('*')[1] in LOSS_KIND for t in a.loss.split('+')):
+            return False
+        if a.metasgd and any(not system.net.is_routed(n) for n in system.net.param_names):
+            return False   # the reference itself fails here for K>=2
+        return hasattr(system.net, 'build_graph')
+
+    def __init__(self, system):
+        self.sys = system
+        self.net = system.net
+        self.ops = system.ops
+        a = system.args
+        self.metasgd = bool(a.metasgd)
+        self.learnable_lr = (not self.metasgd) and bool(a.learnable_per_layer_per_step_inner_loop_learning_rate)
+        self.K = a.number_of_training_steps_per_iter
+        self.use_graphs = bool(system.use_cuda_graphs) and self.ops.name == 'cuda'
+        dev = self.ops.device
+        lay = self.net.layout
+        self.fast = Arena(lay, dev)
+        self.seg = lay.segment_table().to(dev)
+        self.routed = [n for n in self.net.param_names if self.net.is_routed(n)]
+        self.routed_mask = torch.tensor([1.0 if self.net.is_routed(n) else 0.0 for n in self.net.param_names],
+                                        device=dev)
+        self.cur_lr = torch.zeros(len(self.net.param_names), device=dev)
+        self.gsum = Arena(lay, dev) if self.metasgd else None
+        self.gquery = Arena(lay, dev) if (self.metasgd or self.learnable_lr) else None
+        self.gsteps = []
+        self.dots = torch.zeros(len(self.net.param_names), device=dev)
+        self.loss_terms = [(LOSS_KIND[t.split('*')[1]], float(t.split('*')[0])) for t in a.loss.split('+')]
+        self.programs = {}
+
+    # ------------------------------------------------------------------ graph bodies
+    def _provider(self, src):
+        net, fast = self.net, self.fast
+        cache = {}
+
+        def provider(name):
+            p = cache.get(name)
+            if p is None:
+                if src == 'fast' and net.is_routed(name + ".weight"):
+                    w = fast.kernel_view(name + ".weight")
+                    b = fast.kernel_view(name + ".bias") if net._spec[name][4] else None
+                    p = ConvParam(name, w, b)
+                else:
+                    p = net.meta_param(name)
+                cache[name] = p
+            return p
+
+        return provider
+
+    def _loss(self, prog, pred, n_pairs):
+        self.ops.fill(prog.loss, 0.0)
+        grad = torch.empty_like(pred)
+        first = True
+        for kind, weight in self.loss_terms:
+            if first:
+                self.ops.loss_fwd_bwd(pred, prog.tgt, kind, weight * n_pairs, prog.loss, grad)
+                first = False
+            else:
+                g2 = torch.empty_like(pred)
+                self.ops.loss_fwd_bwd(pred, prog.tgt, kind, weight * n_pairs, prog.loss, g2)
+                self.ops.axpby(g2, 1.0, grad, 1.0)
+        return grad
+
+    def _support_body(self, src, step_slot):
+        def body(prog):
+            sink = _Sink(self, 'inner', step=step_slot)
+            tape = Tape(self.ops, self._provider(src), sink)
+            out = self.net.build_graph(tape, prog.f0, prog.f1)
+            out.grad = self._loss(prog, out.data, prog.f0.shape[0])
+            tape.backward()
+        return body
+
+    def _query_body(self, src, mode, backward=True):
+        def body(prog):
+            sink = _Sink(self, mode, scale=1.0) if backward else None
+            if mode == 'accum' and backward:
+                sink.scale = prog.scale
+            tape = Tape(self.ops, self._provider(src), sink)
+            out = self.net.build_graph(tape, prog.f0, prog.f1)
+            prog.pred = out.data
+            g = self._loss(prog, out.data, 1)
+            if backward:
+                out.grad = g
+                tape.backward()
+        return body
+
+    def _program(self, key, body, n, h, w):
+        p = self.programs.get(key)
+        if p is None:
+            p = _Program(self, body, n, h, w)
+            self.programs[key] = p
+        return p
+
+    # ------------------------------------------------------------------ one task
+    def _set_lr(self, step):
+        if not self.metasgd:
+            self.cur_lr.copy_(self.sys.lr_table[:, step])
+
+    def _support_step(self, frames, task, step, h, w, support_idxs):
+        src = 'meta' if step == 0 else 'fast'
+        slot = step if self.learnable_lr else 0
+        prog = self._program(('support', src, slot, h, w), self._support_body(src, slot), len(support_idxs), h, w)
+        for i, (a, b, c) in enumerate(support_idxs):
+            prog.f0[i].copy_(frames[a][task])
+            prog.f1[i].copy_(frames[c][task])
+            prog.tgt[i].copy_(frames[b][task])
+        self._set_lr(step)
+        if step == 0:
+            # un-routed tensors and (for K=0) everything are read from the meta arena; routed tensors are
+            # written by the fused update, nothing to initialise
+            if self.metasgd:
+                self.ops.fill(self.gsum.flat, 0.0)
+        prog.run()
+
+    def _query(self, frames, task, src, h, w, mode, scale, backward=True):
+        ti = self.sys.target_idxs
+        key = ('query', src, mode, backward, h, w, scale if mode == 'accum' else 0)
+        prog = self._program(key, self._query_body(src, mode, backward), 1, h, w)
+        prog.scale = scale
+        prog.f0[0].copy_(frames[ti[0]][task])
+        prog.f1[0].copy_(frames[ti[2]][task])
+        prog.tgt[0].copy_(frames[ti[1]][task])
+        prog.run()
+        return prog
+
+    def _outer_extras(self, scale, steps_done):
+        """alpha / lr outer gradients from the stored per-task query gradient G (Appx E4)."""
+        sysm, ops = self.sys, self.ops
+        G = self.gquery.flat
+        ops.axpby(G, scale, sysm.net_grad.flat, 1.0)                     # dL/dtheta += scale * G
+        if self.metasgd:
+            ops.addcmul(sysm.alpha_grad.flat, -scale, self.gsum.flat, G)  # dL/dalpha -= scale * gsum (.) G
+        elif self.learnable_lr:
+            for j in range(steps_done):
+                ops.fill(self.dots, 0.0)
+                ops.segment_dot(self.gsteps[j].flat, G, self.seg, self.dots)
+                # only routed tensors are adapted; un-routed rows keep a zero gradient
+                sysm.lr_table_grad[:, j].add_(self.dots * self.routed_mask, alpha=-scale)
+
+    def adapt_and_query(self, frames, task, num_steps, epoch, training, scale, msl, msl_w):
+        """Inner loop + query for one task.  Returns (task_loss tensor[1], pred [1,3,H,W])."""
+        h, w = frames[0].shape[2], frames[0].shape[3]
+        sysm = self.sys
+        support_idxs = sysm.support_idxs
+        if self.learnable_lr and training:
+            while len(self.gsteps) < num_steps:
+                self.gsteps.append(Arena(self.net.layout, self.ops.device))
+        extras = training and (self.metasgd or self.learnable_lr)
+        task_loss = torch.zeros(1, device=self.ops.device)
+        prog = None
+        for step in range(num_steps):
+            self._support_step(frames, task, step, h, w, support_idxs)
+            if msl:
+                wk = float(msl_w[step])
+                if extras:
+                    prog = self._query(frames, task, 'fast', h, w, 'store', 1.0)
+                    self._outer_extras(scale * wk, step + 1)
+                else:
+                    prog = self._query(frames, task, 'fast', h, w, 'accum', scale * wk)
+                task_loss += wk * prog.loss
+        if not msl:
+            src = 'fast' if num_steps > 0 else 'meta'
+            if not training:
+                prog = self._query(frames, task, src, h, w, 'none', 0.0, backward=False)
+            elif extras:
+                prog = self._query(frames, task, src, h, w, 'store', 1.0)
+                self._outer_extras(scale, num_steps)
+            else:
+                prog = self._query(frames, task, src, h, w, 'accum', scale)
+            task_loss += prog.loss
+        return task_loss, prog.pred.clone()
+
+    # ------------------------------------------------------------------ meta-batch drivers
+    def _finish(self, frames, task_ids, losses_dev, preds, do_evaluation, msl_w, loss_name_terms):
+        sysm = self.sys
+        n_tasks = len(frames[0])
+        metrics = {'psnr': utils.AverageMeter(), 'ssim': utils.AverageMeter()}
+        per_task = [[] for _ in range(n_tasks)]
+        ti = sysm.target_idxs
+        for t, p in zip(task_ids, preds):
+            per_task[t] = sysm._denorm(p)
+            if do_evaluation:
+                psnr, ssim = utils.calc_metrics(sysm._denorm(p).squeeze(0), sysm._denorm(frames[ti[1]][t]),
+                                                ops=self.ops)
+                metrics['psnr'].update(psnr)
+                metrics['ssim'].update(ssim)
+        stacked = torch.cat(losses_dev)
+        losses = {'loss': stacked.mean()}
+        total = stacked.mean().detach().cpu().numpy()
+        losses['total'] = total
+        if len(self.loss_terms) == 1:
+            losses[loss_name_terms[0]] = total
+        for idx, item in enumerate(msl_w):
+            losses['loss_importance_vector_{}'.format(idx)] = item.detach().cpu().numpy()
+        return losses, per_task, metrics
+
+    def train_iter(self, frames, epoch, task_ids, world, do_evaluation):
+        sysm, a = self.sys, self.sys.args
+        msl_w = sysm.get_per_step_loss_importance_vector()
+        msl = a.use_multi_step_loss_optimization and epoch < a.multi_step_loss_num_epochs
+        n_global = len(task_ids) * world
+        scale = 1.0 / n_global
+        sysm.optimizer.zero_grad()
+        for g in sysm._groups:
+            g.dirty = True
+        losses_dev, preds = [], []
+        for t in task_ids:
+            l, p = self.adapt_and_query(frames, t, self.K, epoch, True, scale, msl, msl_w)
+            losses_dev.append(l)
+            preds.append(p)
+        names = [t.split('*')[1] for t in a.loss.split('+')]
+        return self._finish(frames, task_ids, losses_dev, preds, do_evaluation, msl_w, names)
+
+    def eval_iter(self, frames, epoch):
+        sysm, a = self.sys, self.sys.args
+        msl_w = sysm.get_per_step_loss_importance_vector()
+        task_ids = list(range(len(frames[0])))
+        losses_dev, preds = [], []
+        for t in task_ids:
+            l, p = self.adapt_and_query(frames, t, a.number_of_evaluation_steps_per_iter, epoch, False, 0.0, False,
+                                        msl_w)
+            losses_dev.append(l)
+            preds.append(p)
+        names = [t.split('*')[1] for t in a.loss.split('+')]
+        return self._finish(frames, task_ids, losses_dev, preds, True, msl_w, names)

@@ -1,0 +1,428 @@
+"""Scene-adaptive interpolation meta-learner (drop-in for the reference's
+``meta_learning_system.py:SceneAdaptiveInterpolation``).
+
+Same constructor (an ``argparse.Namespace`` with the reference's flags), attributes
+and methods as reference meta_learning_system.py:29-697; ``run_train_iter`` /
+``run_validation_iter`` / ``run_test_iter`` return what the reference returns.
+
+Two execution paths, selected per configuration:
+
+* fast path (``fastpath.FastPath``): first-order MAML with an SGD inner rule (LSLR
+  fixed/learnable or Meta-SGD), with or without the MAML++ multi-step loss.  Each
+  inner step (2 support pairs batched as N=2: forward, loss, backward, fused
+  ``w -= lr*g`` in the weight-gradient epilogue) and each query pass is one CUDA
+  graph; per-task outer gradients are accumulated straight into the flat
+  meta-gradient buffer (mathematically the reference's single ``loss.backward()``
+  over B retained graphs, SURVEY section 7 decision 4).
+* compat path: the reference's own control flow (dict of fast weights,
+  ``torch.autograd.grad`` with ``allow_unused=True``, ``update_params``) running on
+  the same kernels through ``torch.autograd.Function`` wrappers; used for the
+  Adam/Adamax inner rules, L2F attenuation and by anything calling the pieces
+  (``net_forward``, ``apply_inner_loop_update`` ...) individually.
+
+Multi-GPU: one process per GPU; rank r adapts tasks [r*B/R, (r+1)*B/R) of the
+meta-batch and the flat meta-gradient buffers are summed with one NCCL
+all-reduce each before the (identical) outer step.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.distributed as dist
+
+from . import utils
+from .backbone import default_ops
+from .inner_loop_optimizers import LSLRGradientDescentLearningRule, MetaSGDLearningRule
+from .loss import Loss
+from .outer_optim import FlatGroup, FusedOuterOptimizer
+
+
+def set_torch_seed(seed):
+    """reference meta_learning_system.py:16-26."""
+    rng = np.random.RandomState(seed=seed)
+    torch_seed = rng.randint(0, 999999)
+    torch.manual_seed(seed=torch_seed)
+    return rng
+
+
+def _build_backbone(args, ops):
+    resume = False if args.resume else True   # reference :52 (inverted flag kept)
+    if args.model == 'sepconv':
+        from .sepconv.model import MetaNetwork as MetaSepConv
+        return MetaSepConv(resume=resume, strModel='l1', ops=ops)
+    raise NotImplementedError('Model not implemented yet!')
+
+
+class SceneAdaptiveInterpolation(nn.Module):
+    def __init__(self, args, ops=None):
+        super(SceneAdaptiveInterpolation, self).__init__()
+        self.args = args
+        self.ops = ops if ops is not None else default_ops()
+        self.device = self.ops.device
+        self.batch_size = args.batch_size
+        self.use_cuda = args.cuda
+        self.current_epoch = 0
+
+        # frame indices of a septuplet: support triplets and the query triplet (reference :42-46)
+        self.support_idxs = [[0, 2, 4], [2, 4, 6]]
+        if args.mode == 'test':
+            self.support_idxs = [[0, 1, 2], [1, 2, 3]]
+        self.target_idxs = [2, 3, 4]
+
+        self.rng = set_torch_seed(seed=args.random_seed)
+        self.net = _build_backbone(args, self.ops)
+
+        self.inner_learning_rate = args.inner_lr
+        if self.args.metasgd:
+            self.inner_loop_optimizer = MetaSGDLearningRule(device=self.device, optimizer=self.args.optimizer,
+                                                            init_learning_rate=self.inner_learning_rate)
+        else:
+            self.inner_loop_optimizer = LSLRGradientDescentLearningRule(
+                device=self.device, optimizer=self.args.optimizer, init_learning_rate=self.inner_learning_rate,
+                total_num_inner_loop_steps=self.args.number_of_training_steps_per_iter,
+                use_learnable_learning_rates=self.args.learnable_per_layer_per_step_inner_loop_learning_rate)
+        self.inner_loop_optimizer._ops = self.ops
+
+        names_weights_dict = self.get_inner_loop_parameter_dict(params=self.net.named_parameters())
+        self.inner_loop_optimizer.initialize(names_weights_dict=names_weights_dict)
+
+        if self.args.attenuate:   # L2F attenuator (reference :107-117)
+            num_layers = len(names_weights_dict.keys())
+            self.attenuator = nn.Sequential(
+                nn.Linear(num_layers, num_layers), nn.ReLU(inplace=True),
+                nn.Linear(num_layers, num_layers), nn.Sigmoid()).to(device=self.device)
+            self.gamma_mult = nn.Parameter(torch.zeros(1, device=self.device))
+
+        self._build_flat_groups()
+        kind = self.args.optimizer if self.args.optimizer in ('Adam', 'Adamax') else 'SGD'
+        betas = (0.9, 0.999) if kind == 'Adamax' else (0.9, 0.99)
+        self.optimizer = FusedOuterOptimizer(self._groups, self.ops, kind, lr=args.outer_lr, betas=betas)
+        self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer=self.optimizer, mode='min', factor=0.2,
+                                                                    patience=5)
+        self.criterion = Loss(args, ops=self.ops)
+        self._fast = None
+        self.use_fast_path = getattr(args, 'fast_path', True)
+        self.use_cuda_graphs = getattr(args, 'cuda_graphs', True)
+
+    # ------------------------------------------------------------------ flat buffers
+    def _build_flat_groups(self):
+        net = self.net
+        own = dict(net.named_parameters())
+        g_net = FlatGroup('net', net.arena.flat, [])
+        from .arena import Arena
+        self.net_grad = Arena(net.layout, self.device, data=g_net.grad)
+        for n in net.param_names:
+            g_net.members.append((own[n], self.net_grad.reference_view(n)))
+        groups = [g_net]
+        lr_params = list(self.inner_loop_optimizer.names_learning_rates_dict.values())
+        if self.args.metasgd:
+            self.alpha = Arena(net.layout, self.device)
+            g_lr = FlatGroup('alpha', self.alpha.flat, [])
+            self.alpha_grad = Arena(net.layout, self.device, data=g_lr.grad)
+            for n in net.param_names:
+                p = self.inner_loop_optimizer.names_learning_rates_dict[n.replace('.', '-')]
+                view = self.alpha.reference_view(n)
+                view.copy_(p.data)
+                p.data = view
+                g_lr.members.append((p, self.alpha_grad.reference_view(n)))
+            groups.append(g_lr)
+        else:
+            g_lr = FlatGroup.pack('lslr', lr_params, self.device)
+            k1 = self.args.number_of_training_steps_per_iter + 1
+            self.lr_table = g_lr.flat[:len(lr_params) * k1].view(len(lr_params), k1)
+            self.lr_table_grad = g_lr.grad[:len(lr_params) * k1].view(len(lr_params), k1)
+            if self.args.learnable_per_layer_per_step_inner_loop_learning_rate:
+                groups.append(g_lr)
+        if self.args.attenuate:
+            groups.append(FlatGroup.pack('l2f', list(self.attenuator.parameters()) + [self.gamma_mult], self.device))
+        self._groups = groups
+
+    # ------------------------------------------------------------------ reference helpers
+    def get_per_step_loss_importance_vector(self):
+        """MSL importance weights (reference :186-210; closed form SURVEY Appx E6)."""
+        k = self.args.number_of_training_steps_per_iter
+        if k == 0:
+            return torch.ones(1, device=self.device)
+        w = np.ones(shape=(k)) * (1.0 / k)
+        decay = 1.0 / k / self.args.multi_step_loss_num_epochs
+        floor = 0.03 / k
+        for i in range(k - 1):
+            w[i] = np.maximum(w[i] - (self.current_epoch * decay), floor)
+        w[-1] = np.minimum(w[-1] + (self.current_epoch * (k - 1) * decay), 1.0 - ((k - 1) * floor))
+        return torch.Tensor(w).to(device=self.device)
+
+    def get_inner_loop_parameter_dict(self, params):
+        """reference :213-228."""
+        out = dict()
+        for name, param in params:
+            if param.requires_grad:
+                if self.args.enable_inner_loop_optimizable_bn_params or "norm_layer" not in name:
+                    out[name] = param
+        return out
+
+    def get_task_embeddings(self, frames, task_id, names_weights_copy):
+        """L2F task embedding = per-tensor mean of the support gradient (reference :231-255)."""
+        support_loss = 0
+        for ind in self.support_idxs:
+            _loss, _ = self.net_forward(frame0=frames[ind[0]][task_id].unsqueeze(0),
+                                        frame1=frames[ind[2]][task_id].unsqueeze(0),
+                                        target=frames[ind[1]][task_id].unsqueeze(0),
+                                        weights=names_weights_copy, backup_running_statistics=True, training=True,
+                                        num_step=0)
+            support_loss = support_loss + _loss['total']
+        self.net.zero_grad(names_weights_copy)
+        grads = torch.autograd.grad(support_loss, names_weights_copy.values(), create_graph=False, allow_unused=True)
+        return torch.stack([g.mean() for g in grads])
+
+    def attenuate_init(self, task_embeddings, names_weights_copy):
+        """gamma = clamp(1 - gamma_mult * attenuator(emb), 0, 1); theta_i <- gamma_i * theta_i (reference :258-272)."""
+        gamma = 1 - self.gamma_mult * self.attenuator(task_embeddings)
+        gamma = gamma.clamp(0, 1)
+        return {k: gamma[i] * v for i, (k, v) in enumerate(names_weights_copy.items())}
+
+    def apply_inner_loop_update(self, loss, names_weights_copy, use_second_order, current_step_idx):
+        """reference :275-321 (first-order: SURVEY F10)."""
+        if use_second_order:
+            raise NotImplementedError('second-order MAML cannot work for these backbones even in the reference '
+                                      '(grid_sampler / raw-kernel backward, SURVEY F10)')
+        self.net.zero_grad(params=names_weights_copy)
+        grads = torch.autograd.grad(loss, names_weights_copy.values(), create_graph=False, allow_unused=True)
+        names_grads_copy = dict(zip(names_weights_copy.keys(), grads))
+        return self.inner_loop_optimizer.update_params(names_weights_dict=names_weights_copy,
+                                                       names_grads_wrt_params_dict=names_grads_copy,
+                                                       num_step=current_step_idx)
+
+    def update_loss_metrics(self, task_losses, target_loss):
+        for key, value in target_loss.items():
+            if key not in task_losses:
+                task_losses[key] = utils.AverageMeter()
+            task_losses[key].update(value.detach())     # kept on device; read once per meta-batch
+
+    def get_across_task_loss_metrics(self, total_losses, specific_losses):
+        losses = dict()
+        losses['loss'] = torch.mean(torch.stack(total_losses))
+        for key, meter in specific_losses.items():
+            avg = meter.avg
+            losses[key] = avg.cpu().numpy() if torch.is_tensor(avg) else avg
+        return losses
+
+    def net_forward(self, frame0, frame1, target, weights, backup_running_statistics, training, num_step):
+        """reference :475-509."""
+        kwargs = {'backup_running_statistics': backup_running_statistics, 'num_step': num_step}
+        output = self.net.forward(frame0, frame1, params=weights, **kwargs)
+        if self.args.model == 'superslomo':
+            output[1]['I0'], output[1]['I1'] = frame0, frame1
+            losses = self.criterion(output[0], target, **output[1])
+            output = output[0]
+        else:
+            losses = self.criterion(output, target)
+        return losses, output
+
+    def trainable_parameters(self):
+        for param in self.parameters():
+            if param.requires_grad:
+                yield param
+
+    # ------------------------------------------------------------------ task sharding
+    def _world(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _local_tasks(self, n_tasks):
+        rank, world = self._world()
+        if world == 1 or n_tasks % world != 0:
+            return list(range(n_tasks)), 1
+        per = n_tasks // world
+        return list(range(rank * per, (rank + 1) * per)), world
+
+    # ------------------------------------------------------------------ forward (compat control flow)
+    def _denorm(self, pred):
+        return pred
+
+    def forward(self, data_batch, epoch, use_second_order, use_multi_step_loss_optimization, num_steps,
+                training_phase, do_evaluation=False, task_ids=None):
+        """reference :346-472 (one meta-batch, serial over tasks)."""
+        frames = data_batch
+        n_tasks = len(frames[0])
+        task_ids = list(range(n_tasks)) if task_ids is None else task_ids
+        total_losses = []
+        loss_accumulator = {'total': utils.AverageMeter()}
+        metrics = {'psnr': utils.AverageMeter(), 'ssim': utils.AverageMeter()}
+        per_task_target_preds = [[] for _ in range(n_tasks)]
+        self.net.zero_grad()
+        msl = use_multi_step_loss_optimization and training_phase and epoch < self.args.multi_step_loss_num_epochs
+        ti = self.target_idxs
+        per_step_loss_importance_vectors = self.get_per_step_loss_importance_vector()
+
+        for task_id in task_ids:
+            task_losses = []
+            names_weights_copy = self.get_inner_loop_parameter_dict(self.net.named_parameters())
+            self.inner_loop_optimizer.initialize_state()
+            if self.args.attenuate:
+                emb = self.get_task_embeddings(frames, task_id, names_weights_copy)
+                names_weights_copy = self.attenuate_init(task_embeddings=emb, names_weights_copy=names_weights_copy)
+
+            def query(step_kw):
+                return self.net_forward(frame0=frames[ti[0]][task_id].unsqueeze(0),
+                                        frame1=frames[ti[2]][task_id].unsqueeze(0),
+                                        target=frames[ti[1]][task_id].unsqueeze(0), weights=names_weights_copy,
+                                        backup_running_statistics=False, training=True, num_step=step_kw)
+
+            for num_step in range(num_steps):
+                support_loss = 0
+                for ind in self.support_idxs:
+                    _loss, _ = self.net_forward(frame0=frames[ind[0]][task_id].unsqueeze(0),
+                                                frame1=frames[ind[2]][task_id].unsqueeze(0),
+                                                target=frames[ind[1]][task_id].unsqueeze(0),
+                                                weights=names_weights_copy,
+                                                backup_running_statistics=(num_step == 0), training=True,
+                                                num_step=num_step)
+                    support_loss = support_loss + _loss['total']
+                names_weights_copy = self.apply_inner_loop_update(loss=support_loss,
+                                                                  names_weights_copy=names_weights_copy,
+                                                                  use_second_order=use_second_order,
+                                                                  current_step_idx=num_step)
+                if msl:
+                    target_loss, target_preds = query(num_step)
+                    task_losses.append(per_step_loss_importance_vectors[num_step] * target_loss['total'])
+                    self.update_loss_metrics(loss_accumulator, target_loss)
+
+            if not training_phase:
+                with torch.no_grad():
+                    target_loss, target_preds = query(num_steps)
+                task_losses.append(target_loss['total'])
+                self.update_loss_metrics(loss_accumulator, target_loss)
+            elif not msl:
+                target_loss, target_preds = query(num_steps)
+                task_losses.append(target_loss['total'])
+                self.update_loss_metrics(loss_accumulator, target_loss)
+
+            per_task_target_preds[task_id] = self._denorm(target_preds.detach())
+            if do_evaluation:
+                psnr, ssim = utils.calc_metrics(self._denorm(target_preds.detach()).squeeze(0),
+                                                self._denorm(frames[ti[1]][task_id]), ops=self.ops)
+                metrics['psnr'].update(psnr)
+                metrics['ssim'].update(ssim)
+            total_losses.append(torch.sum(torch.stack(task_losses)))
+            if not training_phase:
+                self.net.restore_backup_stats()
+
+        losses = self.get_across_task_loss_metrics(total_losses=total_losses, specific_losses=loss_accumulator)
+        for idx, item in enumerate(per_step_loss_importance_vectors):
+            losses['loss_importance_vector_{}'.format(idx)] = item.detach().cpu().numpy()
+        return losses, per_task_target_preds, metrics
+
+    def train_forward_prop(self, data_batch, epoch, do_evaluation=False, task_ids=None):
+        return self.forward(data_batch=data_batch, epoch=epoch,
+                            use_second_order=self.args.second_order and epoch > self.args.first_order_to_second_order_epoch,
+                            use_multi_step_loss_optimization=self.args.use_multi_step_loss_optimization,
+                            num_steps=self.args.number_of_training_steps_per_iter, training_phase=True,
+                            do_evaluation=do_evaluation, task_ids=task_ids)
+
+    def evaluation_forward_prop(self, data_batch, epoch, task_ids=None):
+        return self.forward(data_batch=data_batch, epoch=epoch, use_second_order=False,
+                            use_multi_step_loss_optimization=True,
+                            num_steps=self.args.number_of_evaluation_steps_per_iter, training_phase=False,
+                            do_evaluation=True, task_ids=task_ids)
+
+    def meta_update(self, loss):
+        """reference :551-574: zero_grad; backward; step (gradients land in the flat buffers)."""
+        self.optimizer.zero_grad()
+        loss.backward()
+        self.optimizer.gather_grads()
+        self._allreduce_grads()
+        self.optimizer.step()
+
+    def _allreduce_grads(self):
+        rank, world = self._world()
+        if world == 1:
+            return
+        for g in self._groups:
+            dist.all_reduce(g.grad, op=dist.ReduceOp.SUM)
+
+    # ------------------------------------------------------------------ fast path
+    def fast_path(self):
+        if self._fast is None:
+            from .fastpath import FastPath
+            self._fast = FastPath(self)
+        return self._fast
+
+    def fast_path_supported(self):
+        from .fastpath import FastPath
+        return self.use_fast_path and FastPath.supports(self)
+
+    # ------------------------------------------------------------------ iterations
+    def run_train_iter(self, data_batch, epoch, do_evaluation=False):
+        """reference :584-606."""
+        epoch = int(epoch)
+        if self.current_epoch != epoch:
+            self.current_epoch = epoch
+        if not self.training:
+            self.train()
+        data_batch = [frame.to(device=self.device) for frame in data_batch]
+        task_ids, world = self._local_tasks(len(data_batch[0]))
+
+        if self.fast_path_supported():
+            losses, preds, metrics = self.fast_path().train_iter(data_batch, epoch, task_ids, world, do_evaluation)
+            self._allreduce_grads()
+            self.optimizer.step()
+        else:
+            losses, preds, metrics = self.train_forward_prop(data_batch=data_batch, epoch=epoch,
+                                                             do_evaluation=do_evaluation, task_ids=task_ids)
+            self.meta_update(loss=losses['loss'] / world)
+        self.optimizer.zero_grad()
+        self.zero_grad()
+        return losses, preds, metrics
+
+    def run_validation_iter(self, data_batch):
+        """reference :608-627."""
+        data_batch = [frame.to(device=self.device) for frame in data_batch]
+        if self.fast_path_supported():
+            return self.fast_path().eval_iter(data_batch, self.current_epoch)
+        return self.evaluation_forward_prop(data_batch=data_batch, epoch=self.current_epoch)
+
+    def run_test_iter(self, data_batch):
+        """reference :630-697: 4-frame clips, support [[0,1,2],[1,2,3]], query (1,2) -> list of [3,H,W]."""
+        if self.training:
+            self.eval()
+        frames = [frame.to(device=self.device) for frame in data_batch]
+        preds = [[] for _ in range(len(frames[0]))]
+        self.net.zero_grad()
+        support_idxs = [[0, 1, 2], [1, 2, 3]]
+        for task_id in range(len(frames[0])):
+            names_weights_copy = self.get_inner_loop_parameter_dict(self.net.named_parameters())
+            self.inner_loop_optimizer.initialize_state()
+            saved, self.support_idxs = self.support_idxs, support_idxs
+            try:
+                if self.args.attenuate:
+                    emb = self.get_task_embeddings(frames, task_id, names_weights_copy)
+                    names_weights_copy = self.attenuate_init(task_embeddings=emb,
+                                                             names_weights_copy=names_weights_copy)
+            finally:
+                self.support_idxs = saved
+            num_step = 0
+            for num_step in range(self.args.number_of_evaluation_steps_per_iter):
+                support_loss = 0
+                for ind in support_idxs:
+                    _loss, _ = self.net_forward(frame0=frames[ind[0]][task_id].unsqueeze(0),
+                                                frame1=frames[ind[2]][task_id].unsqueeze(0),
+                                                target=frames[ind[1]][task_id].unsqueeze(0),
+                                                weights=names_weights_copy,
+                                                backup_running_statistics=(num_step == 0), training=True,
+                                                num_step=num_step)
+                    support_loss = support_loss + _loss['total']
+                names_weights_copy = self.apply_inner_loop_update(loss=support_loss,
+                                                                  names_weights_copy=names_weights_copy,
+                                                                  use_second_order=self.args.second_order,
+                                                                  current_step_idx=num_step)
+            with torch.no_grad():
+                output = self.net.forward(frames[1][task_id].unsqueeze(0), frames[2][task_id].unsqueeze(0),
+                                          params=names_weights_copy, backup_running_statistics=False, training=True,
+                                          num_step=num_step)
+            if self.args.model == 'superslomo':
+                output = output[0]
+            preds[task_id] = self._denorm(output.detach()).squeeze(0)
+            self.net.restore_backup_stats()
+        return preds

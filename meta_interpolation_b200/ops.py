@@ -1,0 +1,310 @@
+"""Operator table of the hot path: thin tensor-level wrappers over the C ABI.
+
+Tensors are torch CUDA tensors used purely as device-memory handles:
+
+* activation: view of shape [N,H,W,C] with strides (H*W*ld, W*ld, ld, 1); ``ld``
+  (= ``t.stride(2)``) may exceed C (channel padding to 4, or a channel slice of a
+  concat buffer);
+* conv weight: "KRSC" view of shape [Cout,k,k,Cin] with ``stride(2) == ldw``;
+  the reference's OIHW parameter is ``w.permute(0,3,1,2)`` of the same storage.
+
+``CudaOps`` is the only operator table the product ships.  Host-side logic
+(tape, backbones, meta system) is written against this interface so the CPU
+test-suite can inject the oracle's table (oracle/ops_ref.py) to check the host
+logic without a GPU; nothing in this package imports the oracle.
+"""
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+WG_STORE, WG_ACCUM, WG_SGD_SCALAR, WG_SGD_TENSOR = 0, 1, 2, 3
+
+
+def pad4(c):
+    return (c + 3) & ~3
+
+
+def _ld(t):
+    """pixel stride of an NHWC activation view (floats)."""
+    assert t.dim() == 4 and t.stride(3) == 1, "NHWC view with unit channel stride expected"
+    n, h, w, _ = t.shape
+    ld = t.stride(2)
+    assert h == 1 or t.stride(1) == w * ld, "rows must be contiguous in NHWC"
+    assert n == 1 or t.stride(0) == h * w * ld, "images must be contiguous in NHWC"
+    return ld
+
+
+def _ldw(w):
+    assert w.dim() == 4 and w.stride(3) == 1
+    co, k, k2, ci = w.shape
+    ld = w.stride(2)
+    assert k == k2 and (k == 1 or w.stride(1) == k * ld) and w.stride(0) == k * k * ld, "KRSC weight view expected"
+    return ld
+
+
+class WgradSpec:
+    """What the weight-gradient finishing stage does (include/mi_b200.h MI_WG_*)."""
+    __slots__ = ("mode", "scale", "grad_w", "grad_b", "w_in", "b_in", "w_out", "b_out", "lr_w", "lr_b", "gsum_w",
+                 "gsum_b")
+
+    def __init__(self, mode=WG_STORE, scale=1.0, grad_w=None, grad_b=None, w_in=None, b_in=None, w_out=None,
+                 b_out=None, lr_w=None, lr_b=None, gsum_w=None, gsum_b=None):
+        self.mode, self.scale = mode, scale
+        self.grad_w, self.grad_b = grad_w, grad_b
+        self.w_in, self.b_in, self.w_out, self.b_out = w_in, b_in, w_out, b_out
+        self.lr_w, self.lr_b, self.gsum_w, self.gsum_b = lr_w, lr_b, gsum_w, gsum_b
+
+
+class CudaOps:
+    """sm_100a operator table (libmi_b200.so).  Raises if the library is absent."""
+
+    name = "cuda"
+
+    def __init__(self, device=None, engine=ENGINE_AUTO):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MiB200Error("CudaOps needs a CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.engine = engine
+        self._ws = None
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def empty_act(self, n, h, w, c, zero_pad=False):
+        ld = pad4(c)
+        buf = torch.empty(n, h, w, ld, device=self.device, dtype=torch.float32)
+        if zero_pad and ld != c:
+            buf[..., c:].zero_()
+        return buf[..., :c] if ld != c else buf
+
+    def zeros_act(self, n, h, w, c):
+        ld = pad4(c)
+        buf = torch.zeros(n, h, w, ld, device=self.device, dtype=torch.float32)
+        return buf[..., :c] if ld != c else buf
+
+    def empty_like_act(self, t):
+        n, h, w, c = t.shape
+        return self.empty_act(n, h, w, c)
+
+    def empty_weight(self, cout, cin, k):
+        ld = pad4(cin)
+        buf = torch.zeros(cout, k, k, ld, device=self.device, dtype=torch.float32)
+        return buf[..., :cin] if ld != cin else buf
+
+    def workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
+        return self._ws
+
+    def launch_count(self):
+        return int(self.lib.mi_launch_count())
+
+    # ------------------------------------------------------------------ convolution
+    def conv_fprop(self, x, w, b, act=ACT_NONE, slope=0.0, out=None, engine=None):
+        n, h, wd, cin = x.shape
+        cout, k = w.shape[0], w.shape[1]
+        assert w.shape[3] == cin
+        y = out if out is not None else self.empty_act(n, h, wd, cout)
+        _lib.check(self.lib.mi_conv2d_fprop(x.data_ptr(), _ld(x), w.data_ptr(), _ldw(w), self._p(b), y.data_ptr(),
+                                            _ld(y), n, h, wd, cin, cout, k, act, float(slope),
+                                            self.engine if engine is None else engine, self._stream()),
+                   "mi_conv2d_fprop")
+        return y
+
+    def weight_to_dgrad(self, w):
+        cout, k, _, cin = w.shape
+        wt = self.empty_weight(cin, cout, k)
+        _lib.check(self.lib.mi_weight_to_dgrad(w.data_ptr(), _ldw(w), wt.data_ptr(), _ldw(wt), cin, cout, k,
+                                               self._stream()), "mi_weight_to_dgrad")
+        return wt
+
+    def conv_dgrad(self, dy, w, wt=None, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0, out=None, accumulate=False,
+                   engine=None):
+        n, h, wd, cout = dy.shape
+        k, cin = w.shape[1], w.shape[3]
+        if wt is None:
+            wt = self.weight_to_dgrad(w)
+        dx = out if out is not None else self.empty_act(n, h, wd, cin)
+        _lib.check(self.lib.mi_conv2d_dgrad(dy.data_ptr(), _ld(dy), wt.data_ptr(), _ldw(wt), dx.data_ptr(), _ld(dx),
+                                            self._p(mask_y), 0 if mask_y is None else _ld(mask_y), mask_act,
+                                            float(mask_slope), 1 if accumulate else 0, n, h, wd, cin, cout, k,
+                                            self.engine if engine is None else engine, self._stream()),
+                   "mi_conv2d_dgrad")
+        return dx
+
+    def conv_wgrad(self, x, dy, k, ldw, spec, engine=None):
+        n, h, wd, cin = x.shape
+        cout = dy.shape[3]
+        eng = self.engine if engine is None else engine
+        need = self.lib.mi_conv2d_wgrad_workspace(n, h, wd, cin, cout, k, eng)
+        ws = self.workspace(need)
+        p = self._p
+        _lib.check(self.lib.mi_conv2d_wgrad(x.data_ptr(), _ld(x), dy.data_ptr(), _ld(dy), n, h, wd, cin, cout, k, ldw,
+                                            spec.mode, float(spec.scale), p(spec.grad_w), p(spec.grad_b), p(spec.w_in),
+                                            p(spec.b_in), p(spec.w_out), p(spec.b_out), p(spec.lr_w), p(spec.lr_b),
+                                            p(spec.gsum_w), p(spec.gsum_b), ws.data_ptr(), ws.numel(), eng,
+                                            self._stream()), "mi_conv2d_wgrad")
+
+    # ------------------------------------------------------------------ resampling / pointwise
+    def avgpool_fwd(self, x):
+        n, h, w, c = x.shape
+        y = self.empty_act(n, h // 2, w // 2, c)
+        _lib.check(self.lib.mi_avgpool2_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c, self._stream()),
+                   "mi_avgpool2_fwd")
+        return y
+
+    def avgpool_bwd(self, dy, dx, accumulate):
+        n, h, w, c = dx.shape
+        _lib.check(self.lib.mi_avgpool2_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n, h, w,
+                                            c, self._stream()), "mi_avgpool2_bwd")
+
+    def maxpool_fwd(self, x):
+        n, h, w, c = x.shape
+        y = self.empty_act(n, h // 2, w // 2, c)
+        _lib.check(self.lib.mi_maxpool2_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c, self._stream()),
+                   "mi_maxpool2_fwd")
+        return y
+
+    def maxpool_bwd(self, x, dy, dx, accumulate):
+        n, h, w, c = x.shape
+        _lib.check(self.lib.mi_maxpool2_bwd(x.data_ptr(), _ld(x), dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx),
+                                            int(accumulate), n, h, w, c, self._stream()), "mi_maxpool2_bwd")
+
+    def upsample_fwd(self, x, align_corners, out=None):
+        n, h, w, c = x.shape
+        y = out if out is not None else self.empty_act(n, 2 * h, 2 * w, c)
+        _lib.check(self.lib.mi_upsample2_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c,
+                                             int(align_corners), self._stream()), "mi_upsample2_fwd")
+        return y
+
+    def upsample_bwd(self, dy, dx, align_corners, accumulate):
+        n, h, w, c = dx.shape
+        _lib.check(self.lib.mi_upsample2_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n, h, w,
+                                             c, int(align_corners), self._stream()), "mi_upsample2_bwd")
+
+    def add(self, a, b, out=None):
+        n, h, w, c = a.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_add(a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), y.data_ptr(), _ld(y), n * h * w, c,
+                                   self._stream()), "mi_add")
+        return y
+
+    def copy(self, src, dst, accumulate=False):
+        n, h, w, c = src.shape
+        _lib.check(self.lib.mi_copy(src.data_ptr(), _ld(src), dst.data_ptr(), _ld(dst), int(accumulate), n * h * w, c,
+                                    self._stream()), "mi_copy")
+
+    def act_bwd(self, dy, y, act, slope=0.0):
+        n, h, w, c = y.shape
+        _lib.check(self.lib.mi_act_bwd(dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), act, float(slope), n * h * w, c,
+                                       self._stream()), "mi_act_bwd")
+
+    def fill(self, t, value):
+        assert t.is_contiguous()
+        _lib.check(self.lib.mi_fill(t.data_ptr(), float(value), t.numel(), self._stream()), "mi_fill")
+
+    def axpby(self, x, a, y, b):
+        assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+        _lib.check(self.lib.mi_axpby(x.data_ptr(), float(a), y.data_ptr(), float(b), x.numel(), self._stream()),
+                   "mi_axpby")
+
+    # ------------------------------------------------------------------ frames in / prediction out
+    def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
+        """f0, f1: NCHW [n,3,h,w] contiguous -> NHWC canvas [n,ch,cw,6] (ld 8)."""
+        n, c, h, w = f0.shape
+        assert c == 3 and f0.is_contiguous() and f1.is_contiguous()
+        y = self.empty_act(n, ch, cw, 6)
+        _lib.check(self.lib.mi_frames_to_canvas(f0.data_ptr(), f1.data_ptr(), y.data_ptr(), _ld(y), n, h, w, ch, cw,
+                                                pad_top, pad_left, mode, self._stream()), "mi_frames_to_canvas")
+        return y
+
+    def nhwc_window_to_nchw(self, src, y0, x0, h, w):
+        n, hs, ws, c = src.shape
+        dst = torch.empty(n, c, h, w, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.mi_nhwc_window_to_nchw(src.data_ptr(), _ld(src), dst.data_ptr(), n, hs, ws, y0, x0, h, w,
+                                                   c, self._stream()), "mi_nhwc_window_to_nchw")
+        return dst
+
+    def nchw_to_nhwc_window(self, src, dst, y0, x0):
+        n, c, h, w = src.shape
+        _, hs, ws, _ = dst.shape
+        assert src.is_contiguous()
+        _lib.check(self.lib.mi_nchw_to_nhwc_window(src.data_ptr(), dst.data_ptr(), _ld(dst), n, hs, ws, y0, x0, h, w,
+                                                   c, self._stream()), "mi_nchw_to_nhwc_window")
+
+    # ------------------------------------------------------------------ adaptive separable convolution
+    def sepconv_fwd(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0):
+        """frame NCHW [n,c,fh,fw]; vert/horiz NHWC [n,gh,gw,F]; -> NCHW [n,c,oh,ow]."""
+        n, c, fh, fw = frame.shape
+        _, gh, gw, taps = vert.shape
+        assert frame.is_contiguous() and _ld(vert) == _ld(horiz)
+        out = torch.empty(n, c, oh, ow, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.mi_sepconv_fwd(frame.data_ptr(), vert.data_ptr(), horiz.data_ptr(), _ld(vert),
+                                           out.data_ptr(), n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps,
+                                           self._stream()), "mi_sepconv_fwd")
+        return out
+
+    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0):
+        n, c, fh, fw = frame.shape
+        _, gh, gw, taps = vert.shape
+        oh, ow = grad_out.shape[2], grad_out.shape[3]
+        assert grad_out.is_contiguous() and _ld(g_vert) == _ld(g_horiz) and _ld(vert) == _ld(horiz)
+        _lib.check(self.lib.mi_sepconv_bwd(frame.data_ptr(), vert.data_ptr(), horiz.data_ptr(), _ld(vert),
+                                           grad_out.data_ptr(), g_vert.data_ptr(), g_horiz.data_ptr(), _ld(g_vert), n,
+                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps, self._stream()),
+                   "mi_sepconv_bwd")
+
+    # ------------------------------------------------------------------ warp
+    def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0):
+        n, h, w, c = img.shape
+        out = self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_warp_fwd(img.data_ptr(), _ld(img), flow.data_ptr(), _ld(flow), out.data_ptr(), _ld(out),
+                                        n, h, w, c, variant, float(sx), float(sy), self._stream()), "mi_warp_fwd")
+        return out
+
+    def warp_bwd(self, img, flow, grad_out, grad_flow, variant, sx=1.0, sy=1.0, accumulate=False):
+        n, h, w, c = img.shape
+        _lib.check(self.lib.mi_warp_bwd(img.data_ptr(), _ld(img), flow.data_ptr(), _ld(flow), grad_out.data_ptr(),
+                                        _ld(grad_out), grad_flow.data_ptr(), _ld(grad_flow), None, 0, int(accumulate),
+                                        n, h, w, c, variant, float(sx), float(sy), self._stream()), "mi_warp_bwd")
+
+    # ------------------------------------------------------------------ loss / metrics / optimizers
+    def loss_fwd_bwd(self, pred, target, kind, weight, loss_out, grad=None):
+        """loss_out[0] += weight*mean(f(pred-target)); grad (optional) = d/dpred."""
+        assert pred.is_contiguous() and target.is_contiguous() and pred.numel() == target.numel()
+        _lib.check(self.lib.mi_loss_fwd_bwd(pred.data_ptr(), target.data_ptr(), self._p(grad), loss_out.data_ptr(),
+                                            pred.numel(), kind, float(weight), self._stream()), "mi_loss_fwd_bwd")
+
+    def psnr_accumulate(self, pred, target, sq_out):
+        assert pred.is_contiguous() and target.is_contiguous() and sq_out.dtype == torch.float64
+        _lib.check(self.lib.mi_psnr_accumulate(pred.data_ptr(), target.data_ptr(), sq_out.data_ptr(), pred.numel(),
+                                               self._stream()), "mi_psnr_accumulate")
+
+    def inner_update(self, w_in, g, w_out, exp_avg, exp_avg_sq, lr, lr_per_element, lr_stride, num_step, seg, skip,
+                     rule, step_count):
+        _lib.check(self.lib.mi_inner_update(w_in.data_ptr(), g.data_ptr(), w_out.data_ptr(), self._p(exp_avg),
+                                            self._p(exp_avg_sq), lr.data_ptr(), int(lr_per_element), int(lr_stride),
+                                            int(num_step), seg.data_ptr(), self._p(skip), w_in.numel(), rule,
+                                            int(step_count), self._stream()), "mi_inner_update")
+
+    def outer_step(self, p, g, m, v, kind, lr, beta1, beta2, eps, weight_decay, step):
+        _lib.check(self.lib.mi_outer_step(p.data_ptr(), g.data_ptr(), self._p(m), self._p(v), p.numel(), kind,
+                                          float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
+                                          int(step), self._stream()), "mi_outer_step")
+
+    def addcmul(self, y, a, x1, x2):
+        assert y.is_contiguous() and x1.is_contiguous() and x2.is_contiguous()
+        _lib.check(self.lib.mi_addcmul(y.data_ptr(), float(a), x1.data_ptr(), x2.data_ptr(), y.numel(),
+                                       self._stream()), "mi_addcmul")
+
+    def segment_dot(self, a, b, seg, out):
+        _lib.check(self.lib.mi_segment_dot(a.data_ptr(), b.data_ptr(), seg.data_ptr(), out.data_ptr(), a.numel(),
+                                           self._stream()), "mi_segment_dot")

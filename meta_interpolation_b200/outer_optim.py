@@ -1,0 +1,81 @@
+"""Outer (meta) optimizer: one fused multi-tensor step per flat buffer.
+
+Stands where the reference builds ``optim.Adam(betas=(0.9,0.99))`` / ``optim.Adamax``
+/ ``optim.SGD`` over ``trainable_parameters()`` (meta_learning_system.py:132-143).
+It IS a ``torch.optim.Optimizer`` (``ReduceLROnPlateau``, ``param_groups[...]['lr']``
+and ``zero_grad`` keep working) but every parameter is a view into a flat buffer
+with a matching flat gradient buffer, so ``step()`` is one ``mi_outer_step`` launch
+per buffer and the NCCL all-reduce of the meta-gradient is one call per buffer.
+"""
+import torch
+
+KIND = {"SGD": 0, "Adam": 1, "Adamax": 2}
+
+
+class FlatGroup:
+    """A flat parameter buffer, its flat gradient buffer and the Parameters viewing it."""
+
+    def __init__(self, name, flat, members):
+        """members: list of (Parameter, grad_view) where grad_view is the view of ``self.grad`` shaped like
+        the Parameter (OIHW permuted view for conv weights)."""
+        self.name = name
+        self.flat = flat
+        self.grad = torch.zeros_like(flat)
+        self.members = members
+        self.m = None
+        self.v = None
+        self.dirty = False     # fast path wrote gradients straight into ``self.grad``
+
+    @staticmethod
+    def pack(name, params, device):
+        """Re-home arbitrary contiguous Parameters into one flat buffer (values preserved)."""
+        total = sum(p.numel() for p in params)
+        flat = torch.zeros(max(total, 1), device=device, dtype=torch.float32)
+        group = FlatGroup(name, flat, [])
+        off = 0
+        for p in params:
+            n = p.numel()
+            view = flat[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            p.data = view
+            group.members.append((p, group.grad[off:off + n].view(p.shape)))
+            off += n
+        return group
+
+
+class FusedOuterOptimizer(torch.optim.Optimizer):
+    def __init__(self, groups, ops, kind, lr, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.0):
+        self.flat_groups = groups
+        self.ops = ops
+        self.kind = KIND[kind]
+        params = [p for g in groups for p, _ in g.members]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._step = 0
+
+    def gather_grads(self):
+        """Move autograd ``.grad`` tensors (compat path) into the flat gradient buffers."""
+        for g in self.flat_groups:
+            for p, gv in g.members:
+                if p.grad is not None:
+                    gv.add_(p.grad) if g.dirty else gv.copy_(p.grad)
+                    p.grad = None
+
+    def zero_grad(self, set_to_none=True):
+        for g in self.flat_groups:
+            self.ops.fill(g.grad, 0.0)
+            g.dirty = False
+            for p, _ in g.members:
+                p.grad = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        self.gather_grads()
+        self._step += 1
+        hp = self.param_groups[0]
+        b1, b2 = hp["betas"]
+        for g in self.flat_groups:
+            if self.kind != 0 and g.m is None:
+                g.m = torch.zeros_like(g.flat)
+                g.v = torch.zeros_like(g.flat)
+            self.ops.outer_step(g.flat, g.grad, g.m, g.v, self.kind, hp["lr"], b1, b2, hp["eps"],
+                                hp["weight_decay"], self._step)

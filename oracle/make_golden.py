@@ -1,0 +1,131 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference on CPU (container only).
+
+    python -m oracle.make_golden            # needs /root/reference
+
+For every case below the reference's ``SceneAdaptiveInterpolation`` (under the shims
+of ``oracle/reference_shims.py``) runs one ``run_train_iter`` on seeded synthetic
+frames; the oracle (``oracle/maml.py``) runs the same case and must agree with the
+reference before anything is written (that is the pin of the oracle).  The fixture
+stores the inputs, the reference's outputs and compact per-tensor digests of the
+meta-gradients / post-step parameters (full tensors would be ~90 MB per case).
+"""
+import argparse
+import os
+import sys
+import warnings
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (reference args overrides, frame size, batch)
+    "sepconv_lslr_sgd_k2": (dict(model="sepconv", loss="1*L1", optimizer="SGD", number_of_training_steps_per_iter=2), 64, 1),
+    "sepconv_lslr_sgd_k1_b2_mse": (dict(model="sepconv", loss="1*MSE", optimizer="SGD",
+                                        number_of_training_steps_per_iter=1), 48, 2),
+    "sepconv_lslr_learnable_msl_k2": (dict(model="sepconv", loss="1*L1", optimizer="SGD",
+                                           number_of_training_steps_per_iter=2,
+                                           learnable_per_layer_per_step_inner_loop_learning_rate=True,
+                                           use_multi_step_loss_optimization=True), 48, 1),
+    "sepconv_lslr_adam_k2": (dict(model="sepconv", loss="1*L1", optimizer="Adam",
+                                  number_of_training_steps_per_iter=2), 48, 1),
+    "sepconv_metasgd_adamax_k2": (dict(model="sepconv", loss="1*L1", optimizer="Adamax", metasgd=True,
+                                       number_of_training_steps_per_iter=2), 48, 1),
+    "sepconv_l2f_sgd_k1": (dict(model="sepconv", loss="1*L1", optimizer="SGD", attenuate=True,
+                                number_of_training_steps_per_iter=1), 48, 1),
+}
+
+
+def digest(t):
+    t = t.detach().double().reshape(-1)
+    return torch.tensor([t.sum(), t.abs().sum(), (t * t).sum()], dtype=torch.float64), t[:8].clone().float()
+
+
+def synthetic_frames(seed, batch, size):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(batch, 3, size, size, generator=g) for _ in range(7)]
+
+
+def run_case(name, over, size, batch):
+    from oracle import reference_shims as rs
+    from oracle import maml
+    system, args = rs.build_system(batch_size=batch, **over)
+    frames = synthetic_frames(0, batch, size)
+    init = {k: v.detach().clone() for k, v in system.net.named_parameters()}
+    att_state = {k: v.detach().clone() for k, v in system.attenuator.state_dict().items()} if args.attenuate else None
+
+    # the oracle on the same case (before the reference mutates its parameters)
+    ora = maml.OracleSystem(args.model, init, optimizer=args.optimizer, metasgd=args.metasgd,
+                            num_steps=args.number_of_training_steps_per_iter, inner_lr=args.inner_lr,
+                            outer_lr=args.outer_lr,
+                            learnable_lr=args.learnable_per_layer_per_step_inner_loop_learning_rate, loss=args.loss,
+                            attenuate=args.attenuate, use_msl=args.use_multi_step_loss_optimization,
+                            msl_epochs=args.multi_step_loss_num_epochs, attenuator_state=att_state)
+    record = {}
+    o_loss, o_preds, o_psnrs, o_grads = ora.run_train_iter(frames, 0, record=record)
+
+    # capture the reference's meta-gradients by wrapping its optimizer step
+    grads_ref = {}
+    orig_step = system.optimizer.step
+
+    def step_and_capture(*a, **k):
+        for n, p in system.named_parameters():
+            grads_ref[n] = None if p.grad is None else p.grad.detach().clone()
+        return orig_step(*a, **k)
+
+    system.optimizer.step = step_and_capture
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
+    post = {k: v.detach().clone() for k, v in system.net.named_parameters()}
+
+    # ---- pin: oracle == reference
+    assert abs(float(losses["loss"]) - float(o_loss)) <= 1e-6 * max(1.0, abs(float(o_loss))), (name, losses["loss"], o_loss)
+    for a, b in zip(preds, o_preds):
+        assert (a - b).abs().max().item() <= 1e-6, name
+    for k, g in o_grads["theta"].items():
+        r = grads_ref["net." + k]
+        assert (g - r).abs().max().item() <= 1e-6 * max(1.0, r.abs().max().item()), (name, k)
+    pin = max((post[k] - ora.params[k].detach()).abs().max().item() for k in post)
+
+    fixture = dict(
+        name=name, args={k: getattr(args, k) for k in (
+            "model", "loss", "optimizer", "metasgd", "attenuate", "inner_lr", "outer_lr", "batch_size", "random_seed",
+            "number_of_training_steps_per_iter", "number_of_evaluation_steps_per_iter",
+            "learnable_per_layer_per_step_inner_loop_learning_rate", "use_multi_step_loss_optimization",
+            "multi_step_loss_num_epochs", "second_order", "first_order_to_second_order_epoch",
+            "enable_inner_loop_optimizable_bn_params")},
+        frames=torch.stack(frames),
+        loss=float(losses["loss"]), psnr=float(metrics["psnr"].avg), ssim=float(metrics["ssim"].avg),
+        preds=torch.cat([p.detach() for p in preds]),
+        support_losses=record.get("support_loss"),
+        init_digest={k: digest(v)[0] for k, v in init.items()},
+        grad_digest={k[4:]: digest(v) for k, v in grads_ref.items() if k.startswith("net.") and v is not None},
+        post_digest={k: digest(v) for k, v in post.items()},
+        lr_grads={k: (None if v is None else v.clone()) for k, v in grads_ref.items()
+                  if k.startswith("inner_loop_optimizer.") and v is not None and v.numel() <= 64},
+        oracle_vs_reference_post_step_maxabs=pin,
+        attenuator_state=att_state,
+    )
+    os.makedirs(GOLDEN, exist_ok=True)
+    path = os.path.join(GOLDEN, name + ".pt")
+    torch.save(fixture, path)
+    print("%-32s loss %.8f psnr %.6f  oracle-vs-reference post-step max|d| %.2e  -> %s (%.0f KB)" % (
+        name, fixture["loss"], fixture["psnr"], pin, os.path.relpath(path, ROOT), os.path.getsize(path) / 1024))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    sys.path.insert(0, ROOT)
+    for name, (over, size, batch) in CASES.items():
+        if a.only and a.only != name:
+            continue
+        run_case(name, over, size, batch)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,351 @@
+"""Oracle: per-operator CPU references mirroring ``meta_interpolation_b200.ops.CudaOps``
+method for method (test infrastructure, not product).
+
+Every method has the same name, argument meaning and layouts (NHWC activation
+views, KRSC weight views) as the CUDA table, implemented with plain ATen CPU ops,
+so that (a) ``tests/`` can compare each CUDA kernel with its reference on the
+same inputs and (b) the host-side executor can be exercised on CPU by injecting
+this table.  The product never imports this module.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .sepconv_op import sepconv_forward, sepconv_backward
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+WG_STORE, WG_ACCUM, WG_SGD_SCALAR, WG_SGD_TENSOR = 0, 1, 2, 3
+
+
+def pad4(c):
+    return (c + 3) & ~3
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1)
+
+
+def _oihw(w):
+    return w.permute(0, 3, 1, 2)
+
+
+def act_apply(v, act, slope):
+    if act == ACT_RELU:
+        return F.relu(v)
+    if act == ACT_LEAKY:
+        return F.leaky_relu(v, slope)
+    if act == ACT_SIGMOID:
+        return torch.sigmoid(v)
+    if act == ACT_TANH:
+        return torch.tanh(v)
+    return v
+
+
+def act_grad(y, act, slope):
+    if act == ACT_RELU:
+        return (y > 0).to(y.dtype)
+    if act == ACT_LEAKY:
+        return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, slope))
+    if act == ACT_SIGMOID:
+        return y * (1 - y)
+    if act == ACT_TANH:
+        return 1 - y * y
+    return torch.ones_like(y)
+
+
+class RefOps:
+    name = "ref"
+
+    def __init__(self, device="cpu", dtype=torch.float32):
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self._launches = 0
+
+    def launch_count(self):
+        return self._launches
+
+    # ------------------------------------------------------------------ allocation (same layouts as CudaOps)
+    def empty_act(self, n, h, w, c, zero_pad=False):
+        ld = pad4(c)
+        buf = torch.zeros(n, h, w, ld, device=self.device, dtype=self.dtype)
+        return buf[..., :c] if ld != c else buf
+
+    zeros_act = empty_act
+
+    def empty_like_act(self, t):
+        n, h, w, c = t.shape
+        return self.empty_act(n, h, w, c)
+
+    def empty_weight(self, cout, cin, k):
+        ld = pad4(cin)
+        buf = torch.zeros(cout, k, k, ld, device=self.device, dtype=self.dtype)
+        return buf[..., :cin] if ld != cin else buf
+
+    # ------------------------------------------------------------------ convolution
+    def conv_fprop(self, x, w, b, act=ACT_NONE, slope=0.0, out=None, engine=None):
+        k = w.shape[1]
+        y = F.conv2d(_nchw(x), _oihw(w), b, stride=1, padding=k // 2)
+        y = _nhwc(act_apply(y, act, slope))
+        if out is None:
+            out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    def weight_to_dgrad(self, w):
+        cout, k, _, cin = w.shape
+        wt = self.empty_weight(cin, cout, k)
+        wt.copy_(torch.flip(w, dims=(1, 2)).permute(3, 1, 2, 0))
+        return wt
+
+    def conv_dgrad(self, dy, w, wt=None, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0, out=None, accumulate=False,
+                   engine=None):
+        k = w.shape[1]
+        dx = _nhwc(F.conv_transpose2d(_nchw(dy), _oihw(w), None, stride=1, padding=k // 2))
+        if mask_y is not None:
+            dx = dx * act_grad(mask_y, mask_act, mask_slope)
+        if out is None:
+            out = self.empty_act(*dx.shape)
+            accumulate = False
+        if accumulate:
+            out.add_(dx)
+        else:
+            out.copy_(dx)
+        return out
+
+    def conv_wgrad(self, x, dy, k, ldw, spec, engine=None):
+        cin, cout = x.shape[3], dy.shape[3]
+        gw = torch.nn.grad.conv2d_weight(_nchw(x), (cout, cin, k, k), _nchw(dy), stride=1, padding=k // 2)
+        gw = gw.permute(0, 2, 3, 1)  # KRSC
+        gb = dy.sum(dim=(0, 1, 2))
+        has_b = (spec.grad_b is not None) if spec.mode <= WG_ACCUM else (spec.b_in is not None)
+        if spec.mode == WG_STORE:
+            spec.grad_w.copy_(gw)
+            if has_b:
+                spec.grad_b.copy_(gb)
+        elif spec.mode == WG_ACCUM:
+            spec.grad_w.add_(spec.scale * gw)
+            if has_b:
+                spec.grad_b.add_(spec.scale * gb)
+        else:
+            lr_w = spec.lr_w.reshape(-1)[0] if spec.mode == WG_SGD_SCALAR else spec.lr_w
+            new_w = spec.w_in - lr_w * gw
+            spec.w_out.copy_(new_w)
+            if spec.grad_w is not None:
+                spec.grad_w.copy_(gw)
+            if has_b:
+                lr_b = spec.lr_b.reshape(-1)[0] if spec.mode == WG_SGD_SCALAR else spec.lr_b
+                new_b = spec.b_in - lr_b * gb
+                spec.b_out.copy_(new_b)
+                if spec.grad_b is not None:
+                    spec.grad_b.copy_(gb)
+        if spec.gsum_w is not None:
+            spec.gsum_w.add_(gw)
+        if spec.gsum_b is not None:
+            spec.gsum_b.add_(gb)
+
+    # ------------------------------------------------------------------ resampling / pointwise
+    def avgpool_fwd(self, x):
+        y = _nhwc(F.avg_pool2d(_nchw(x), 2, 2))
+        out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    def avgpool_bwd(self, dy, dx, accumulate):
+        g = 0.25 * dy.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+        dx.add_(g) if accumulate else dx.copy_(g)
+
+    def maxpool_fwd(self, x):
+        y = _nhwc(F.max_pool2d(_nchw(x), 2, 2))
+        out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    @torch.enable_grad()
+    def maxpool_bwd(self, x, dy, dx, accumulate):
+        xx = _nchw(x).detach().clone().requires_grad_(True)
+        y = F.max_pool2d(xx, 2, 2)
+        (g,) = torch.autograd.grad(y, xx, _nchw(dy))
+        g = _nhwc(g)
+        dx.add_(g) if accumulate else dx.copy_(g)
+
+    def upsample_fwd(self, x, align_corners, out=None):
+        y = _nhwc(F.interpolate(_nchw(x), scale_factor=2, mode="bilinear", align_corners=bool(align_corners)))
+        if out is None:
+            out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    @torch.enable_grad()
+    def upsample_bwd(self, dy, dx, align_corners, accumulate):
+        n, h, w, c = dx.shape
+        xx = torch.zeros(n, c, h, w, dtype=dy.dtype, requires_grad=True)
+        y = F.interpolate(xx, scale_factor=2, mode="bilinear", align_corners=bool(align_corners))
+        (g,) = torch.autograd.grad(y, xx, _nchw(dy))
+        g = _nhwc(g)
+        dx.add_(g) if accumulate else dx.copy_(g)
+
+    def add(self, a, b, out=None):
+        if out is None:
+            out = self.empty_act(*a.shape)
+        out.copy_(a + b)
+        return out
+
+    def copy(self, src, dst, accumulate=False):
+        dst.add_(src) if accumulate else dst.copy_(src)
+
+    def act_bwd(self, dy, y, act, slope=0.0):
+        dy.mul_(act_grad(y, act, slope))
+
+    def fill(self, t, value):
+        t.fill_(value)
+
+    def axpby(self, x, a, y, b):
+        y.copy_(a * x + (b * y if b != 0 else 0))
+
+    # ------------------------------------------------------------------ frames in / prediction out
+    def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
+        n, c, h, w = f0.shape
+        pad = [pad_left, cw - pad_left - w, pad_top, ch - pad_top - h]
+        m = "replicate" if mode == 0 else "reflect"
+        x = torch.cat([F.pad(f0, pad, mode=m), F.pad(f1, pad, mode=m)], 1)
+        out = self.empty_act(n, ch, cw, 6)
+        out.copy_(_nhwc(x))
+        return out
+
+    def nhwc_window_to_nchw(self, src, y0, x0, h, w):
+        return _nchw(src[:, y0:y0 + h, x0:x0 + w, :]).contiguous()
+
+    def nchw_to_nhwc_window(self, src, dst, y0, x0):
+        n, c, h, w = src.shape
+        dst[:, y0:y0 + h, x0:x0 + w, :].copy_(_nhwc(src))
+
+    # ------------------------------------------------------------------ adaptive separable convolution
+    @staticmethod
+    def _sep_input(frame, oh, ow, iy0, ix0, taps):
+        n, c, fh, fw = frame.shape
+        ys = (torch.arange(oh + taps - 1) + iy0).clamp(0, fh - 1)
+        xs = (torch.arange(ow + taps - 1) + ix0).clamp(0, fw - 1)
+        return frame[:, :, ys][:, :, :, xs]
+
+    def sepconv_fwd(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0):
+        taps = vert.shape[3]
+        inp = self._sep_input(frame, oh, ow, iy0, ix0, taps)
+        v = _nchw(vert[:, gy0:gy0 + oh, gx0:gx0 + ow, :])
+        h = _nchw(horiz[:, gy0:gy0 + oh, gx0:gx0 + ow, :])
+        return sepconv_forward(inp, v, h)
+
+    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0):
+        taps = vert.shape[3]
+        oh, ow = grad_out.shape[2], grad_out.shape[3]
+        inp = self._sep_input(frame, oh, ow, iy0, ix0, taps)
+        v = _nchw(vert[:, gy0:gy0 + oh, gx0:gx0 + ow, :]).contiguous()
+        h = _nchw(horiz[:, gy0:gy0 + oh, gx0:gx0 + ow, :]).contiguous()
+        gv, gh = sepconv_backward(inp, v, h, grad_out)
+        g_vert[:, gy0:gy0 + oh, gx0:gx0 + ow, :].copy_(_nhwc(gv))
+        g_horiz[:, gy0:gy0 + oh, gx0:gx0 + ow, :].copy_(_nhwc(gh))
+
+    # ------------------------------------------------------------------ warp
+    @staticmethod
+    def _warp_grid(flow, variant, sx, sy):
+        n, h, w, _ = flow.shape
+        u, v = flow[..., 0], flow[..., 1]
+        if variant == 0:   # superslomo/model.py:292-302, rrin/model.py:8-21
+            gx = torch.arange(w, dtype=flow.dtype).view(1, 1, w).expand(n, h, w)
+            gy = torch.arange(h, dtype=flow.dtype).view(1, h, 1).expand(n, h, w)
+            x = 2 * ((gx + sx * u) / w - 0.5)
+            y = 2 * ((gy + sy * v) / h - 0.5)
+            return torch.stack((x, y), dim=3), dict(mode="bilinear", padding_mode="zeros", align_corners=False)
+        gx = torch.linspace(-1.0, 1.0, w).view(1, 1, w).expand(n, h, w)
+        gy = torch.linspace(-1.0, 1.0, h).view(1, h, 1).expand(n, h, w)
+        return torch.stack((gx + sx * u, gy + sy * v), dim=3), dict(mode="bilinear", padding_mode="border",
+                                                                    align_corners=True)
+
+    def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0):
+        grid, kw = self._warp_grid(flow, variant, sx, sy)
+        y = _nhwc(F.grid_sample(_nchw(img), grid, **kw))
+        out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    @torch.enable_grad()
+    def warp_bwd(self, img, flow, grad_out, grad_flow, variant, sx=1.0, sy=1.0, accumulate=False):
+        fl = flow.detach().clone().contiguous().requires_grad_(True)
+        grid, kw = self._warp_grid(fl, variant, sx, sy)
+        y = F.grid_sample(_nchw(img), grid, **kw)
+        (g,) = torch.autograd.grad(y, fl, _nchw(grad_out))
+        grad_flow.add_(g) if accumulate else grad_flow.copy_(g)
+
+    # ------------------------------------------------------------------ loss / metrics / optimizers
+    def loss_fwd_bwd(self, pred, target, kind, weight, loss_out, grad=None):
+        d = pred - target
+        cnt = pred.numel()
+        if kind == 0:
+            loss_out.add_(weight * d.abs().mean())
+            if grad is not None:
+                grad.copy_(weight * torch.sign(d) / cnt)
+        else:
+            loss_out.add_(weight * (d * d).mean())
+            if grad is not None:
+                grad.copy_(weight * 2 * d / cnt)
+
+    def psnr_accumulate(self, pred, target, sq_out):
+        q = lambda t: t.mul(255).clamp(0, 255).round()
+        d = (q(pred) - q(target)).div(255)
+        sq_out.add_(d.pow(2).double().sum())
+
+    def inner_update(self, w_in, g, w_out, exp_avg, exp_avg_sq, lr, lr_per_element, lr_stride, num_step, seg, skip,
+                     rule, step_count):
+        n = w_in.numel()
+        t = seg.long().repeat_interleave(1024)[:n]
+        valid = t >= 0
+        if skip is not None:
+            valid = valid & ~(skip.bool()[t.clamp(min=0)])
+        l = lr.reshape(-1) if lr_per_element else lr.reshape(-1)[(t.clamp(min=0) * lr_stride + num_step)]
+        b1, b2, eps = 0.9, 0.99, 1e-8
+        bc1 = 1 - b1 ** step_count
+        bc2 = 1 - b2 ** step_count
+        wi, gi = w_in.reshape(-1), g.reshape(-1)
+        if rule == 0:
+            o = wi - l * gi
+        elif rule == 1:
+            m = b1 * exp_avg.reshape(-1) + (1 - b1) * gi
+            v = b2 * exp_avg_sq.reshape(-1) + (1 - b2) * gi * gi
+            exp_avg.reshape(-1)[valid] = m[valid]
+            exp_avg_sq.reshape(-1)[valid] = v[valid]
+            o = wi - (l / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps)
+        elif rule == 2:
+            m = b1 * exp_avg.reshape(-1) + (1 - b1) * gi
+            exp_avg.reshape(-1)[valid] = m[valid]
+            o = wi - (l / bc1) * m / (gi.abs() + eps)
+        else:
+            o = wi - (l / bc1) * ((1 - b1) * gi) / (gi.abs() + eps)
+        w_out.reshape(-1).copy_(torch.where(valid, o, wi))
+
+    def outer_step(self, p, g, m, v, kind, lr, beta1, beta2, eps, weight_decay, step):
+        gi = g + weight_decay * p if weight_decay != 0 else g
+        if kind == 0:
+            p.sub_(lr * gi)
+        elif kind == 1:
+            m.mul_(beta1).add_(gi, alpha=1 - beta1)
+            v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
+            denom = (v.sqrt() / math.sqrt(1 - beta2 ** step)).add_(eps)
+            p.addcdiv_(m, denom, value=-(lr / (1 - beta1 ** step)))
+        else:
+            m.mul_(beta1).add_(gi, alpha=1 - beta1)
+            torch.maximum(v * beta2, gi.abs() + eps, out=v)
+            p.addcdiv_(m, v, value=-(lr / (1 - beta1 ** step)))
+
+    def addcmul(self, y, a, x1, x2):
+        y.add_(a * x1 * x2)
+
+    def segment_dot(self, a, b, seg, out):
+        n = a.numel()
+        t = seg.long().repeat_interleave(1024)[:n]
+        prod = (a.reshape(-1) * b.reshape(-1))
+        valid = t >= 0
+        out.index_add_(0, t[valid], prod[valid])

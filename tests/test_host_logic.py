@@ -1,0 +1,106 @@
+"""Host-side logic (tape, plugin, inner rules, meta system, fast path) on CPU with the oracle's
+operator table injected in place of the CUDA one."""
+import pytest
+import torch
+
+from helpers import digest, load_golden, make_args, oracle_from_fixture, system_from_fixture
+from oracle import backbones as bb
+
+
+def test_plugin_parameter_names_shapes_and_seeded_init(ref_ops):
+    from meta_interpolation_b200.sepconv.model import MetaNetwork
+    bb.set_torch_seed(12345)
+    net = MetaNetwork(ops=ref_ops)
+    ref = bb.seeded_params("sepconv", 12345)
+    own = dict(net.named_parameters())
+    assert list(own) == list(ref)
+    for k in ref:
+        assert own[k].shape == ref[k].shape and torch.equal(own[k].detach(), ref[k]), k
+    # checkpoint round trip keeps the reference's keys
+    sd = net.state_dict()
+    assert set(sd) == set(ref)
+    net2 = MetaNetwork(ops=ref_ops)
+    net2.load_state_dict(sd)
+    assert torch.equal(net2.arena.flat, net.arena.flat)
+
+
+def test_plugin_forward_and_unrouted_grads_are_none_after_step0(ref_ops):
+    from meta_interpolation_b200.sepconv.model import MetaNetwork
+    bb.set_torch_seed(12345)
+    net = MetaNetwork(ops=ref_ops)
+    own = dict(net.named_parameters())
+    g = torch.Generator().manual_seed(0)
+    f0, f1, tgt = (torch.rand(1, 3, 32, 32, generator=g) for _ in range(3))
+    fast = {k: v.detach().clone().requires_grad_(True) for k, v in own.items()}
+    out = net.forward(f0, f1, params=fast)
+    assert out.shape == (1, 3, 32, 32)
+    grads = torch.autograd.grad((out - tgt).abs().mean(), list(fast.values()), allow_unused=True)
+    for (k, _), gr in zip(fast.items(), grads):
+        assert (gr is not None) == net.is_routed(k), k
+    ref = {k: v.detach().clone().requires_grad_(True) for k, v in own.items()}
+    o2 = bb.sepconv_forward(f0, f1, ref, ref)
+    assert (out - o2).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("name,fast", [("sepconv_lslr_sgd_k2", True), ("sepconv_lslr_sgd_k2", False),
+                                       ("sepconv_lslr_sgd_k1_b2_mse", True),
+                                       ("sepconv_lslr_learnable_msl_k2", True),
+                                       ("sepconv_lslr_learnable_msl_k2", False),
+                                       ("sepconv_lslr_adam_k2", False), ("sepconv_metasgd_adamax_k2", False),
+                                       ("sepconv_l2f_sgd_k1", False)])
+def test_system_against_reference_golden(ref_ops, name, fast):
+    fx = load_golden(name)
+    system = system_from_fixture(fx, ref_ops, fast_path=fast)
+    assert system.fast_path_supported() == fast
+    frames = list(fx["frames"])
+    losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
+    assert abs(float(losses["loss"]) - fx["loss"]) <= 2e-6
+    assert (torch.cat(preds) - fx["preds"]).abs().max().item() <= 2e-6
+    assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01          # north_star tolerance: |dPSNR| < 0.01 dB
+    if fx["args"]["optimizer"] == "SGD":                          # Adam/Adamax steps are sign-like: digest only for SGD
+        own = dict(system.net.named_parameters())
+        for k, (d, head) in fx["post_digest"].items():
+            assert torch.allclose(digest(own[k])[0], d, rtol=1e-5, atol=1e-8), k
+
+
+def test_state_dict_keys_match_reference_schema(ref_ops):
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    s = SceneAdaptiveInterpolation(make_args(attenuate=True, number_of_training_steps_per_iter=2), ops=ref_ops)
+    keys = list(s.state_dict().keys())
+    assert "net.moduleConv1.0.weight" in keys and "gamma_mult" in keys
+    assert "inner_loop_optimizer.names_learning_rates_dict.moduleConv1-0-weight" in keys
+    assert s.state_dict()["inner_loop_optimizer.names_learning_rates_dict.moduleConv1-0-weight"].shape == (3,)
+    assert {"attenuator.0.weight", "attenuator.0.bias", "attenuator.2.weight", "attenuator.2.bias"} <= set(keys)
+    assert len(keys) == 94 + 94 + 4 + 1     # 193 keys for sepconv+L2F
+
+
+def test_metasgd_sgd_reproduces_reference_failure(ref_ops):
+    # Meta-SGD + SGD with K>=2 on a backbone with un-routed tensors raises in the reference
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    s = SceneAdaptiveInterpolation(make_args(metasgd=True, number_of_training_steps_per_iter=2), ops=ref_ops)
+    g = torch.Generator().manual_seed(0)
+    frames = [torch.rand(1, 3, 32, 32, generator=g) for _ in range(7)]
+    with pytest.raises(TypeError):
+        s.run_train_iter(frames, epoch=0)
+
+
+def test_validation_and_test_iters(ref_ops):
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    from oracle import maml
+    s = SceneAdaptiveInterpolation(make_args(number_of_evaluation_steps_per_iter=1), ops=ref_ops)
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.rand(1, 3, 32, 32, generator=g) for _ in range(7)]
+    losses, preds, metrics = s.run_validation_iter(frames)
+    ora = maml.OracleSystem("sepconv", bb.seeded_params("sepconv", 12345), num_steps=1)
+    loss, opreds, psnrs = ora.run_validation_iter(frames, num_steps=1)
+    assert abs(float(losses["loss"]) - float(loss)) < 2e-6
+    assert (preds[0] - opreds[0]).abs().max().item() < 2e-6
+    out = s.run_test_iter(frames[:4])
+    assert out[0].shape == (3, 32, 32)
+
+
+def test_extract_top_level_dict():
+    from meta_interpolation_b200.model_utils import extract_top_level_dict
+    d = {"a.0.weight": 1, "a.0.bias": 2, "b.weight": 3, "c": 4, "layer_dict.e.f": 5}
+    out = extract_top_level_dict(d)
+    assert out == {"a": {"0.weight": 1, "0.bias": 2}, "b": {"weight": 3}, "c": 4, "e": {"f": 5}}

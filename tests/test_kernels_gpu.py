@@ -1,0 +1,327 @@
+"""Every CUDA kernel of libmi_b200 against its CPU reference (oracle/ops_ref.py) on the same inputs."""
+import pytest
+import torch
+
+from oracle.ops_ref import RefOps
+from meta_interpolation_b200.ops import (ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ENGINE_SIMT, ENGINE_TC,
+                                         WG_ACCUM, WG_SGD_SCALAR, WG_SGD_TENSOR, WG_STORE, WgradSpec, pad4)
+
+pytestmark = pytest.mark.gpu
+REF = RefOps()
+
+
+def act_pair(ops, n, h, w, c, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    cpu = REF.empty_act(n, h, w, c)
+    cpu.copy_((torch.rand(n, h, w, c, generator=g) - 0.5) * 2 * scale)
+    dev = ops.empty_act(n, h, w, c)
+    dev.copy_(cpu.cuda())
+    return cpu, dev
+
+
+def weight_pair(ops, cout, cin, k, seed):
+    g = torch.Generator().manual_seed(seed)
+    cpu = REF.empty_weight(cout, cin, k)
+    cpu.copy_((torch.rand(cout, k, k, cin, generator=g) - 0.5) * (2.0 / (cin * k * k) ** 0.5))
+    dev = ops.empty_weight(cout, cin, k)
+    dev.copy_(cpu.cuda())
+    return cpu, dev
+
+
+def close(dev, cpu, tol, what=""):
+    d = (dev.detach().cpu() - cpu).abs().max().item()
+    s = cpu.abs().max().item()
+    assert d <= tol * max(s, 1e-6), "%s: max|diff| %.3e vs scale %.3e" % (what, d, s)
+
+
+CONV_SHAPES = [
+    # n, h, w, cin, cout, k
+    (1, 8, 8, 6, 32, 3), (2, 16, 24, 32, 32, 3), (1, 12, 16, 64, 51, 3), (1, 16, 16, 51, 51, 3),
+    (2, 6, 8, 128, 64, 3), (1, 9, 7, 5, 3, 5), (1, 10, 12, 20, 32, 7), (1, 4, 4, 192, 12, 1), (1, 3, 5, 7, 130, 3),
+]
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+@pytest.mark.parametrize("act", [ACT_NONE, ACT_RELU, ACT_LEAKY])
+def test_conv_fprop_simt(cuda_ops, shape, act):
+    n, h, w, cin, cout, k = shape
+    xc, xd = act_pair(cuda_ops, n, h, w, cin, 1)
+    wc, wd = weight_pair(cuda_ops, cout, cin, k, 2)
+    bc = torch.rand(cout) - 0.5
+    yc = REF.conv_fprop(xc, wc, bc, act, 0.1)
+    yd = cuda_ops.conv_fprop(xd, wd, bc.cuda(), act, 0.1, engine=ENGINE_SIMT)
+    close(yd, yc, 2e-5, "fprop")
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_dgrad_simt(cuda_ops, shape):
+    n, h, w, cin, cout, k = shape
+    dyc, dyd = act_pair(cuda_ops, n, h, w, cout, 3)
+    wc, wd = weight_pair(cuda_ops, cout, cin, k, 4)
+    mc, md = act_pair(cuda_ops, n, h, w, cin, 5)
+    dxc = REF.conv_dgrad(dyc, wc, mask_y=mc, mask_act=ACT_RELU)
+    dxd = cuda_ops.conv_dgrad(dyd, wd, mask_y=md, mask_act=ACT_RELU, engine=ENGINE_SIMT)
+    close(dxd, dxc, 2e-5, "dgrad")
+    # accumulate
+    acc_c, acc_d = act_pair(cuda_ops, n, h, w, cin, 6)
+    REF.conv_dgrad(dyc, wc, out=acc_c, accumulate=True)
+    cuda_ops.conv_dgrad(dyd, wd, out=acc_d, accumulate=True, engine=ENGINE_SIMT)
+    close(acc_d, acc_c, 2e-5, "dgrad accumulate")
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv_wgrad_simt_modes(cuda_ops, shape):
+    n, h, w, cin, cout, k = shape
+    xc, xd = act_pair(cuda_ops, n, h, w, cin, 7)
+    dyc, dyd = act_pair(cuda_ops, n, h, w, cout, 8)
+    wc, wd = weight_pair(cuda_ops, cout, cin, k, 9)
+    bc = torch.rand(cout)
+    bd = bc.cuda()
+    ld = pad4(cin)
+    # STORE
+    gwc, gwd = REF.empty_weight(cout, cin, k), cuda_ops.empty_weight(cout, cin, k)
+    gbc, gbd = torch.zeros(cout), torch.zeros(cout, device="cuda")
+    REF.conv_wgrad(xc, dyc, k, ld, WgradSpec(WG_STORE, grad_w=gwc, grad_b=gbc))
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_STORE, grad_w=gwd, grad_b=gbd), engine=ENGINE_SIMT)
+    close(gwd, gwc, 3e-5, "wgrad store w")
+    close(gbd, gbc, 3e-5, "wgrad store b")
+    # ACCUM with scale on top of the stored gradient
+    REF.conv_wgrad(xc, dyc, k, ld, WgradSpec(WG_ACCUM, scale=0.25, grad_w=gwc, grad_b=gbc))
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_ACCUM, scale=0.25, grad_w=gwd, grad_b=gbd), engine=ENGINE_SIMT)
+    close(gwd, gwc, 3e-5, "wgrad accum w")
+    # fused LSLR SGD update, in place, with gsum
+    lr = torch.tensor([0.05])
+    sc = WgradSpec(WG_SGD_SCALAR, w_in=wc, b_in=bc, w_out=wc, b_out=bc, lr_w=lr, lr_b=lr,
+                   gsum_w=REF.empty_weight(cout, cin, k), gsum_b=torch.zeros(cout))
+    sd = WgradSpec(WG_SGD_SCALAR, w_in=wd, b_in=bd, w_out=wd, b_out=bd, lr_w=lr.cuda(), lr_b=lr.cuda(),
+                   gsum_w=cuda_ops.empty_weight(cout, cin, k), gsum_b=torch.zeros(cout, device="cuda"))
+    REF.conv_wgrad(xc, dyc, k, ld, sc)
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, sd, engine=ENGINE_SIMT)
+    close(wd, wc, 3e-5, "fused sgd w")
+    close(bd, bc, 3e-5, "fused sgd b")
+    close(sd.gsum_w, sc.gsum_w, 3e-5, "gsum")
+    # Meta-SGD (per-element alpha)
+    ac, ad = weight_pair(cuda_ops, cout, cin, k, 10)
+    ab = torch.rand(cout)
+    w2c, w2d = REF.empty_weight(cout, cin, k), cuda_ops.empty_weight(cout, cin, k)
+    b2c, b2d = torch.zeros(cout), torch.zeros(cout, device="cuda")
+    REF.conv_wgrad(xc, dyc, k, ld, WgradSpec(WG_SGD_TENSOR, w_in=wc, b_in=bc, w_out=w2c, b_out=b2c, lr_w=ac, lr_b=ab))
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_SGD_TENSOR, w_in=wd, b_in=bd, w_out=w2d, b_out=b2d, lr_w=ad,
+                                                  lr_b=ab.cuda()), engine=ENGINE_SIMT)
+    close(w2d, w2c, 3e-5, "metasgd w")
+    # pad lanes of the KRSC storage stay zero
+    if ld != cin:
+        full = w2d.as_strided((cout, k, k, ld), (k * k * ld, k * ld, ld, 1), w2d.storage_offset())
+        assert float(full[..., cin:].abs().max()) == 0.0
+
+
+def test_weight_to_dgrad(cuda_ops):
+    wc, wd = weight_pair(cuda_ops, 7, 5, 3, 11)
+    close(cuda_ops.weight_to_dgrad(wd), REF.weight_to_dgrad(wc), 0.0, "weight_to_dgrad")
+
+
+@pytest.mark.parametrize("c", [3, 32, 51])
+def test_pool_upsample_add_copy_act(cuda_ops, c):
+    n, h, w = 2, 8, 12
+    xc, xd = act_pair(cuda_ops, n, h, w, c, 12)
+    close(cuda_ops.avgpool_fwd(xd), REF.avgpool_fwd(xc), 1e-6, "avgpool")
+    close(cuda_ops.maxpool_fwd(xd), REF.maxpool_fwd(xc), 0.0, "maxpool")
+    gyc, gyd = act_pair(cuda_ops, n, h // 2, w // 2, c, 13)
+    for acc in (False, True):
+        dc, dd = act_pair(cuda_ops, n, h, w, c, 14)
+        REF.avgpool_bwd(gyc, dc, acc)
+        cuda_ops.avgpool_bwd(gyd, dd, acc)
+        close(dd, dc, 1e-6, "avgpool bwd")
+        dc, dd = act_pair(cuda_ops, n, h, w, c, 15)
+        REF.maxpool_bwd(xc, gyc, dc, acc)
+        cuda_ops.maxpool_bwd(xd, gyd, dd, acc)
+        close(dd, dc, 1e-6, "maxpool bwd")
+    for align in (True, False):
+        close(cuda_ops.upsample_fwd(xd, align), REF.upsample_fwd(xc, align), 2e-6, "upsample")
+        guc, gud = act_pair(cuda_ops, n, 2 * h, 2 * w, c, 16)
+        for acc in (False, True):
+            dc, dd = act_pair(cuda_ops, n, h, w, c, 17)
+            REF.upsample_bwd(guc, dc, align, acc)
+            cuda_ops.upsample_bwd(gud, dd, align, acc)
+            close(dd, dc, 2e-6, "upsample bwd align=%s" % align)
+    yc, yd = act_pair(cuda_ops, n, h, w, c, 18)
+    close(cuda_ops.add(xd, yd), REF.add(xc, yc), 1e-7, "add")
+    for act in (ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH):
+        gc, gd = act_pair(cuda_ops, n, h, w, c, 19)
+        REF.act_bwd(gc, xc, act, 0.1)
+        cuda_ops.act_bwd(gd, xd, act, 0.1)
+        close(gd, gc, 1e-6, "act_bwd")
+    # channel-slice copy into a wider concat buffer
+    bufc, bufd = act_pair(cuda_ops, n, h, w, c + 8, 20)
+    REF.copy(xc, bufc[..., 4:4 + c])
+    cuda_ops.copy(xd, bufd[..., 4:4 + c])
+    close(bufd, bufc, 0.0, "slice copy")
+
+
+@pytest.mark.parametrize("mode,hw", [(0, (20, 28)), (1, (20, 28)), (0, (5, 3))])
+def test_frames_to_canvas_and_windows(cuda_ops, mode, hw):
+    h, w = hw
+    g = torch.Generator().manual_seed(21)
+    f0, f1 = torch.rand(2, 3, h, w, generator=g), torch.rand(2, 3, h, w, generator=g)
+    pt, pl = (3, 2) if mode == 1 else (25, 25)
+    ch, cw = (h + 8, w + 6) if mode == 1 else (128, 128)
+    cc = REF.frames_to_canvas(f0, f1, ch, cw, pt, pl, mode)
+    cd = cuda_ops.frames_to_canvas(f0.cuda(), f1.cuda(), ch, cw, pt, pl, mode)
+    close(cd, cc, 0.0, "canvas")
+    close(cuda_ops.nhwc_window_to_nchw(cd, pt, pl, h, w), REF.nhwc_window_to_nchw(cc, pt, pl, h, w), 0.0, "window")
+
+
+@pytest.mark.parametrize("geom", [dict(taps=51, c=3, h=40, w=70), dict(taps=51, c=3, h=9, w=33),
+                                  dict(taps=5, c=2, h=6, w=7)])
+def test_sepconv_fused_geometry(cuda_ops, geom):
+    taps, c, h, w = geom["taps"], geom["c"], geom["h"], geom["w"]
+    pad = taps // 2
+    gh, gw = h + 2 * pad + 3, w + 2 * pad + 5
+    g = torch.Generator().manual_seed(22)
+    frame = torch.rand(2, c, h, w, generator=g)
+    vc, vd = act_pair(cuda_ops, 2, gh, gw, taps, 23, 0.2)
+    hc, hd = act_pair(cuda_ops, 2, gh, gw, taps, 24, 0.2)
+    oc = REF.sepconv_fwd(frame, vc, hc, h, w, pad, pad, -pad, -pad)
+    od = cuda_ops.sepconv_fwd(frame.cuda(), vd, hd, h, w, pad, pad, -pad, -pad)
+    close(od, oc, 2e-5, "sepconv fwd")
+    go = torch.rand(2, c, h, w, generator=g) - 0.5
+    gvc, ghc = REF.zeros_act(2, gh, gw, taps), REF.zeros_act(2, gh, gw, taps)
+    gvd, ghd = cuda_ops.zeros_act(2, gh, gw, taps), cuda_ops.zeros_act(2, gh, gw, taps)
+    REF.sepconv_bwd(frame, vc, hc, go, gvc, ghc, pad, pad, -pad, -pad)
+    cuda_ops.sepconv_bwd(frame.cuda(), vd, hd, go.cuda(), gvd, ghd, pad, pad, -pad, -pad)
+    close(gvd, gvc, 3e-5, "sepconv gV")
+    close(ghd, ghc, 3e-5, "sepconv gH")
+
+
+def test_function_sepconv_dropin_matches_reference_op(cuda_ops):
+    """The reference's own calling convention (pre-padded NCHW input, [N,F,H,W] filters)."""
+    from meta_interpolation_b200.sepconv.sepconv_op.sepconv import FunctionSepconv
+    from oracle.sepconv_op import FunctionSepconvCPU
+    g = torch.Generator().manual_seed(25)
+    inp = torch.rand(1, 3, 16 + 50, 20 + 50, generator=g)
+    v = (torch.rand(1, 51, 16, 20, generator=g) * 0.1).requires_grad_(True)
+    h = (torch.rand(1, 51, 16, 20, generator=g) * 0.1).requires_grad_(True)
+    vd, hd = v.detach().cuda().requires_grad_(True), h.detach().cuda().requires_grad_(True)
+    out_c = FunctionSepconvCPU.apply(inp, v, h)
+    out_d = FunctionSepconv.apply(inp.cuda(), vd, hd)
+    close(out_d, out_c.detach(), 2e-5, "FunctionSepconv fwd")
+    go = torch.rand(1, 3, 16, 20, generator=g)
+    out_c.backward(go)
+    out_d.backward(go.cuda())
+    close(vd.grad, v.grad, 3e-5, "FunctionSepconv gV")
+    close(hd.grad, h.grad, 3e-5, "FunctionSepconv gH")
+    with pytest.raises(NotImplementedError):
+        FunctionSepconv.apply(inp, v, h)   # CPU tensors: same error as the reference (sepconv.py:293-294)
+
+
+@pytest.mark.parametrize("variant,sx,sy", [(0, 1.0, 1.0), (1, -0.5, -0.5), (1, 0.5, 0.5)])
+def test_warp(cuda_ops, variant, sx, sy):
+    n, h, w, c = 2, 12, 17, 3
+    ic, idv = act_pair(cuda_ops, n, h, w, c, 26)
+    fc, fd = act_pair(cuda_ops, n, h, w, 2, 27, 3.0 if variant == 0 else 0.6)
+    close(cuda_ops.warp_fwd(idv, fd, variant, sx, sy), REF.warp_fwd(ic, fc, variant, sx, sy), 1e-5, "warp fwd")
+    goc, god = act_pair(cuda_ops, n, h, w, c, 28)
+    gfc, gfd = REF.zeros_act(n, h, w, 2), cuda_ops.zeros_act(n, h, w, 2)
+    REF.warp_bwd(ic, fc, goc, gfc, variant, sx, sy)
+    cuda_ops.warp_bwd(idv, fd, god, gfd, variant, sx, sy)
+    close(gfd, gfc, 2e-4, "warp flow grad")
+
+
+def test_identity_flow_is_half_pixel_shift(cuda_ops):
+    # KAT: zero flow samples at x-0.5 -> average of the pixel and its upper-left neighbours, zeros outside
+    img = cuda_ops.zeros_act(1, 4, 4, 1)
+    img.fill_(1.0)
+    out = cuda_ops.warp_fwd(img, cuda_ops.zeros_act(1, 4, 4, 2), 0)
+    exp = torch.ones(4, 4)
+    exp[0, :] = 0.5
+    exp[:, 0] = 0.5
+    exp[0, 0] = 0.25
+    assert torch.allclose(out[0, :, :, 0].cpu(), exp, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_loss_and_psnr(cuda_ops, kind):
+    g = torch.Generator().manual_seed(29)
+    p, t = torch.rand(2, 3, 9, 11, generator=g), torch.rand(2, 3, 9, 11, generator=g)
+    lc, ld = torch.zeros(1), torch.zeros(1, device="cuda")
+    gc, gd = torch.zeros_like(p), torch.zeros_like(p).cuda()
+    REF.loss_fwd_bwd(p, t, kind, 2.0, lc, gc)
+    cuda_ops.loss_fwd_bwd(p.cuda(), t.cuda(), kind, 2.0, ld, gd)
+    close(ld, lc, 1e-5, "loss")
+    close(gd, gc, 1e-6, "loss grad")
+    sc, sd = torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64, device="cuda")
+    REF.psnr_accumulate(p, t, sc)
+    cuda_ops.psnr_accumulate(p.cuda(), t.cuda(), sd)
+    assert abs(float(sd) - float(sc)) <= 1e-9 * float(sc)
+
+
+@pytest.mark.parametrize("rule", [0, 1, 2, 3])
+def test_inner_update_rules(cuda_ops, rule):
+    n = 3000
+    g = torch.Generator().manual_seed(30)
+    w, gr = torch.rand(n, generator=g), torch.rand(n, generator=g) - 0.5
+    seg = torch.tensor([0, 1, -1], dtype=torch.int32)
+    skip = torch.tensor([0, 1], dtype=torch.uint8)
+    lr = torch.rand(2, 4, generator=g) * 0.1
+    mc, vc = torch.rand(n, generator=g) * 0.1, torch.rand(n, generator=g) * 0.1
+    md, vd = mc.cuda(), vc.cuda()
+    for use_skip in (None, skip):
+        oc, od = torch.zeros(n), torch.zeros(n, device="cuda")
+        REF.inner_update(w, gr, oc, mc, vc, lr, False, 4, 2, seg, use_skip, rule, 2)
+        cuda_ops.inner_update(w.cuda(), gr.cuda(), od, md, vd, lr.cuda(), False, 4, 2, seg.cuda(),
+                              None if use_skip is None else use_skip.cuda(), rule, 2)
+        close(od, oc, 2e-6, "inner rule %d" % rule)
+        close(md, mc, 2e-6, "exp_avg")
+    alpha = torch.rand(n, generator=g) * 0.1
+    oc, od = torch.zeros(n), torch.zeros(n, device="cuda")
+    REF.inner_update(w, gr, oc, mc, vc, alpha, True, 0, 0, seg, None, rule, 1)
+    cuda_ops.inner_update(w.cuda(), gr.cuda(), od, md, vd, alpha.cuda(), True, 0, 0, seg.cuda(), None, rule, 1)
+    close(od, oc, 2e-6, "per-element lr")
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_outer_step_matches_torch_optim(cuda_ops, kind):
+    n = 5000
+    g = torch.Generator().manual_seed(31)
+    p0 = torch.rand(n, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = [torch.optim.SGD([ref], lr=1e-2), torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.99)),
+           torch.optim.Adamax([ref], lr=1e-2, betas=(0.9, 0.999))][kind]
+    pd = p0.cuda()
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in (1, 2, 3):
+        gr = torch.rand(n, generator=g) - 0.5
+        ref.grad = gr.clone()
+        opt.step()
+        cuda_ops.outer_step(pd, gr.cuda(), m, v, kind, 1e-2, 0.9, 0.999 if kind == 2 else 0.99, 1e-8, 0.0, step)
+    close(pd, ref.detach(), 2e-6, "outer step")
+
+
+def test_axpby_addcmul_segment_dot_fill(cuda_ops):
+    n = 2500
+    g = torch.Generator().manual_seed(32)
+    a, b, c = (torch.rand(n, generator=g) for _ in range(3))
+    yd = b.cuda()
+    cuda_ops.axpby(a.cuda(), 0.5, yd, -2.0)
+    close(yd, 0.5 * a - 2.0 * b, 1e-6, "axpby")
+    yd = c.cuda()
+    cuda_ops.addcmul(yd, -0.3, a.cuda(), b.cuda())
+    close(yd, c - 0.3 * a * b, 1e-6, "addcmul")
+    seg = torch.tensor([0, 2, -1], dtype=torch.int32)
+    out = torch.zeros(3, device="cuda")
+    cuda_ops.segment_dot(a.cuda(), b.cuda(), seg.cuda(), out)
+    exp = torch.zeros(3)
+    REF.segment_dot(a, b, seg, exp)
+    close(out, exp, 1e-5, "segment_dot")
+    cuda_ops.fill(yd, 3.0)
+    assert float(yd.min()) == 3.0 == float(yd.max())
+
+
+def test_bad_arguments_raise(cuda_ops):
+    from meta_interpolation_b200._lib import MiB200Error
+    x = cuda_ops.empty_act(1, 5, 5, 4)     # odd size cannot be pooled
+    with pytest.raises(MiB200Error):
+        cuda_ops.avgpool_fwd(x)
+    w = cuda_ops.empty_weight(4, 4, 3)
+    with pytest.raises(MiB200Error):
+        cuda_ops.conv_fprop(cuda_ops.empty_act(1, 4, 4, 3), w, None, engine=ENGINE_TC)   # ineligible shape for tcgen05

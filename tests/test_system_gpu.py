@@ -1,0 +1,80 @@
+"""The CUDA path of the meta system against the reference's golden vectors and the CPU oracle."""
+import pytest
+import torch
+
+from helpers import digest, load_golden, make_args, oracle_from_fixture, system_from_fixture
+
+pytestmark = pytest.mark.gpu
+
+# fp32 tolerance of the path: the conv stacks run TF32 on the tensor cores when eligible (fp32 storage and
+# accumulation).  north_star bar: |dPSNR| < 0.01 dB against the reference on identical inputs.
+PRED_TOL = 5e-3
+LOSS_TOL = 5e-4
+
+
+@pytest.mark.parametrize("name,fast,graphs", [
+    ("sepconv_lslr_sgd_k2", True, True), ("sepconv_lslr_sgd_k2", True, False), ("sepconv_lslr_sgd_k2", False, False),
+    ("sepconv_lslr_sgd_k1_b2_mse", True, True), ("sepconv_lslr_learnable_msl_k2", True, True),
+    ("sepconv_lslr_learnable_msl_k2", False, False), ("sepconv_lslr_adam_k2", False, False),
+    ("sepconv_metasgd_adamax_k2", False, False), ("sepconv_l2f_sgd_k1", False, False)])
+def test_train_iter_against_reference_golden(cuda_ops, name, fast, graphs):
+    fx = load_golden(name)
+    system = system_from_fixture(fx, cuda_ops, fast_path=fast, cuda_graphs=graphs)
+    assert system.fast_path_supported() == fast
+    frames = [f.cuda() for f in fx["frames"]]
+    n0 = cuda_ops.launch_count()
+    losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
+    torch.cuda.synchronize()
+    assert cuda_ops.launch_count() > n0
+    assert abs(float(losses["loss"]) - fx["loss"]) <= LOSS_TOL
+    assert (torch.cat(preds).cpu() - fx["preds"]).abs().max().item() <= PRED_TOL
+    assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+    if fx["args"]["optimizer"] == "SGD":
+        own = dict(system.net.named_parameters())
+        for k, (d, head) in fx["post_digest"].items():
+            mine = digest(own[k])[0]
+            assert torch.allclose(mine[1:], d[1:], rtol=2e-3, atol=1e-7), k
+
+
+def test_graph_replay_is_stable_over_iterations(cuda_ops):
+    """Three meta-iterations: eager / capture+replay / replay must track the CPU oracle step for step."""
+    fx = load_golden("sepconv_lslr_sgd_k2")
+    system = system_from_fixture(fx, cuda_ops, fast_path=True, cuda_graphs=True)
+    ora = oracle_from_fixture(fx)
+    g = torch.Generator().manual_seed(5)
+    for it in range(3):
+        frames = [torch.rand(2, 3, 64, 64, generator=g) for _ in range(7)]
+        losses, preds, metrics = system.run_train_iter([f.cuda() for f in frames], epoch=0, do_evaluation=True)
+        loss, opreds, psnrs, _ = ora.run_train_iter(frames, 0)
+        assert abs(float(losses["loss"]) - float(loss)) <= LOSS_TOL, it
+        assert (torch.cat(preds).cpu() - torch.cat(opreds)).abs().max().item() <= PRED_TOL, it
+        assert abs(metrics["psnr"].avg - sum(psnrs) / len(psnrs)) < 0.01, it
+
+
+def test_eval_and_test_iters(cuda_ops):
+    from oracle import backbones as bb, maml
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    args = make_args(cuda=True, number_of_evaluation_steps_per_iter=2, number_of_training_steps_per_iter=2)
+    s = SceneAdaptiveInterpolation(args, ops=cuda_ops)
+    g = torch.Generator().manual_seed(3)
+    frames = [torch.rand(1, 3, 40, 56, generator=g) for _ in range(7)]
+    losses, preds, metrics = s.run_validation_iter([f.cuda() for f in frames])
+    ora = maml.OracleSystem("sepconv", bb.seeded_params("sepconv", 12345), num_steps=2)
+    loss, opreds, psnrs = ora.run_validation_iter(frames, num_steps=2)
+    assert abs(float(losses["loss"]) - float(loss)) < LOSS_TOL
+    assert (preds[0].cpu() - opreds[0]).abs().max().item() < PRED_TOL
+    assert abs(metrics["psnr"].avg - psnrs[0]) < 0.01
+    out = s.run_test_iter([f.cuda() for f in frames[:4]])
+    assert out[0].shape == (3, 40, 56) and out[0].is_cuda
+
+
+def test_linearity_property_full_size_conv(cuda_ops):
+    """Size-independent property at the BASELINE canvas (384x512): conv is linear in its input."""
+    ops = cuda_ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = ops.empty_act(1, 384, 512, 32); a.copy_(torch.rand(1, 384, 512, 32, device="cuda", generator=g))
+    b = ops.empty_act(1, 384, 512, 32); b.copy_(torch.rand(1, 384, 512, 32, device="cuda", generator=g))
+    w = ops.empty_weight(32, 32, 3); w.copy_(torch.rand(32, 3, 3, 32, device="cuda", generator=g) - 0.5)
+    ya, yb = ops.conv_fprop(a, w, None), ops.conv_fprop(b, w, None)
+    yab = ops.conv_fprop(ops.add(a, b), w, None)
+    assert (yab - (ya + yb)).abs().max().item() <= 2e-2 * yab.abs().max().item()
