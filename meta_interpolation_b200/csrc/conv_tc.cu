@@ -1,7 +1,568 @@
-// placeholder, replaced below
+// tcgen05 (5th-gen tensor core) implicit-GEMM convolution for sm_100a: fprop (and dgrad through the
+// rotated filter) and the split-K weight-gradient partials.  TF32 operands, fp32 accumulation in TMEM,
+// operands staged by TMA with the 128-byte swizzle the UMMA shared-memory descriptors expect.
+//
+// fprop  : D[128 pixels][BN couts] += A[128 pixels][32 cin] * B[BN couts][32 cin]^T per (tap, cin chunk).
+//          A is one TMA box {32 ch, TW, TH, 1} of the NHWC activation shifted by the tap; out-of-image
+//          pixels and channel tails are zero-filled by TMA (that IS the conv padding).  Both operands K-major.
+// wgrad  : D[128 couts][BN cins] += dY[P pixels][128 couts]^T * X_tap[P pixels][BN cins] per pixel chunk:
+//          the reduction (pixels) is the slow dimension of both NHWC tensors, so both operands are MN-major.
+//
+// Warp roles per CTA (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> bias/activation/mask -> global).
+// Replaces cuDNN's F.conv2d kernels used by the reference (model_utils.py:360).
+#include <cuda.h>
+
 #include "mi_common.cuh"
-bool mi_tc_fprop_eligible(const float*, int, const float*, int, const float*, int, int, int, int, int, int, int) { return false; }
-bool mi_tc_wgrad_eligible(const float*, int, const float*, int, int, int, int, int, int, int) { return false; }
-int mi_tc_fprop(const float*, int, const float*, int, const float*, float*, int, const float*, int, int, float, int, int, int, int, int, int, int, int, float, cudaStream_t) { return MI_ERR_UNSUPPORTED; }
-int mi_tc_wgrad_partials(const float*, int, const float*, int, int, int, int, int, int, int, int, float*, float*, int, cudaStream_t) { return MI_ERR_UNSUPPORTED; }
-extern "C" int mi_tc_available(void) { return 0; }
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int KCH = 32;          // fp32 channels per 128-byte swizzle row
+constexpr int NTHREADS = 192;
+constexpr uint32_t ROW_BYTES = 128;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;                                  // descriptor version (Blackwell)
+    d |= (uint64_t)((addr >> 7) & 7u) << 49;          // base offset: swizzle phase of the start row
+    d |= 2ull << 61;                                  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
+__device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct FpropParams {
+    int n, h, w, cin, cout, k, tw, th, tiles_x, tiles_y, bn, stages, act, accumulate, mask_act, ldy, ldmask;
+    float slope, mask_slope;
+    const float* bias;
+    const float* mask_y;
+    float* y;
+};
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad
+__global__ void __launch_bounds__(NTHREADS)
+conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                     const FpropParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t a_bytes = BM * ROW_BYTES;
+    const uint32_t b_bytes = (uint32_t)p.bn * ROW_BYTES;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    // bars[0..stages) = full, [stages..2*stages) = empty, [2*stages] = accumulator ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tile = blockIdx.x;
+    const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+    const int img = tile;
+    const int x0 = tx_i * p.tw, y0 = ty_i * p.th;
+    const int co0 = blockIdx.y * p.bn;
+    const int pad = p.k >> 1;
+    const int chunks = (p.cin + KCH - 1) / KCH;
+    const int iters = p.k * p.k * chunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[p.stages + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * p.stages]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.bn);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[p.stages + s]), ph ^ 1u);
+                const int tap = it / chunks, ch = it - tap * chunks;
+                const int ky = tap / p.k, kx = tap - ky * p.k;
+                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t a_dst = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(full, stage_bytes);
+                tma_load_4d(a_dst, &map_x, full, ch * KCH, x0 + kx - pad, y0 + ky - pad, img);
+                tma_load_3d(a_dst + a_bytes, &map_w, full, ch * KCH, tap, co0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(BM, p.bn, 0, 0);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t ad = smem_desc(a_addr + kk * 32, 16, 1024);
+                    const uint64_t bd = smem_desc(b_addr + kk * 32, 16, 1024);
+                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bars[p.stages + s]));   // frees this smem stage when the MMAs retire
+            }
+            umma_commit(smem_u32(&bars[2 * p.stages]));       // accumulator complete
+        }
+    } else {
+        // epilogue: warp q owns TMEM lanes [32q, 32q+32) == output pixels of the tile
+        const int q = warp & 3;
+        mbar_wait(smem_u32(&bars[2 * p.stages]), 0);
+        tc_fence_after();
+        const int r = q * 32 + lane;
+        const int th_i = r / p.tw, tw_i = r - th_i * p.tw;
+        const int oy = y0 + th_i, ox = x0 + tw_i;
+        const bool pix_ok = (oy < p.h) && (ox < p.w);
+        const long long pix = ((long long)img * p.h + oy) * p.w + ox;
+        float* yrow = p.y + pix * p.ldy;
+        const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
+        const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!pix_ok) continue;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int co = co0 + c0 + j;
+                if (co >= p.cout) break;
+                float o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = co + e;
+                    float val = __uint_as_float(v[j + e]);
+                    if (c < p.cout) {
+                        if (p.bias) val += __ldg(p.bias + c);
+                        val = mi_act_apply(val, p.act, p.slope);
+                        if (mrow) val *= mi_act_grad(__ldg(mrow + c), p.mask_act, p.mask_slope);
+                        if (p.accumulate) val += yrow[c];
+                    }
+                    o[e] = val;
+                }
+                if (vec && co + 3 < p.cout) {
+                    *reinterpret_cast<float4*>(yrow + co) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (co + e < p.cout) yrow[co + e] = o[e];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.bn);
+}
+
+// ------------------------------------------------------------------------------------------ wgrad partials
+struct WgradParams {
+    int n, h, w, cin, cout, k, ldw, pw, ph, tiles_x, tiles_y, bn, stages, co_tiles, ci_tiles, tiles_per_split,
+        total_tiles;
+    float* ws_w;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                     const WgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int P = p.pw * p.ph;                          // pixels per stage (multiple of 8)
+    const uint32_t box_bytes = (uint32_t)P * ROW_BYTES;  // one {32 ch x P pixels} box
+    const int a_boxes = BM / KCH;                        // 4 boxes of 32 couts
+    const int b_boxes = p.bn / KCH;
+    const uint32_t a_bytes = a_boxes * box_bytes, b_bytes = b_boxes * box_bytes;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int bid = blockIdx.x;
+    const int ci_tile = bid % p.ci_tiles; bid /= p.ci_tiles;
+    const int co_tile = bid % p.co_tiles; bid /= p.co_tiles;
+    const int tap = bid;
+    const int ky = tap / p.k, kx = tap - ky * p.k, pad = p.k >> 1;
+    const int split = blockIdx.y;
+    const int t_begin = split * p.tiles_per_split;
+    const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
+    const int iters = max(t_end - t_begin, 0);
+    const int co0 = co_tile * BM, ci0 = ci_tile * p.bn;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[p.stages + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * p.stages]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.bn);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[p.stages + s]), ph ^ 1u);
+                int t = t_begin + it;
+                const int tx_i = t % p.tiles_x; t /= p.tiles_x;
+                const int ty_i = t % p.tiles_y; t /= p.tiles_y;
+                const int img = t;
+                const int x0 = tx_i * p.pw, y0 = ty_i * p.ph;
+                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(full, stage_bytes);
+                for (int j = 0; j < a_boxes; ++j)
+                    tma_load_4d(base + j * box_bytes, &map_dy, full, co0 + j * KCH, x0, y0, img);
+                for (int j = 0; j < b_boxes; ++j)
+                    tma_load_4d(base + a_bytes + j * box_bytes, &map_x, full, ci0 + j * KCH, x0 + kx - pad,
+                                y0 + ky - pad, img);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(BM, p.bn, 1, 1);   // both operands MN-major
+            const int ksteps = P / 8;
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    // 8 pixels (K) x 32 channels (MN) atoms of 1024 B; MN blocks of 32 channels are box_bytes apart
+                    const uint64_t ad = smem_desc(a_addr + kk * 1024, box_bytes, 1024);
+                    const uint64_t bd = smem_desc(b_addr + kk * 1024, box_bytes, 1024);
+                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bars[p.stages + s]));
+            }
+            umma_commit(smem_u32(&bars[2 * p.stages]));
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = co0 + q * 32 + lane;
+        float* dst = p.ws_w + (long long)split * p.cout * p.k * p.k * p.ldw + ((long long)co * p.k * p.k + tap) * p.ldw;
+        if (iters > 0) {
+            mbar_wait(smem_u32(&bars[2 * p.stages]), 0);
+            tc_fence_after();
+        }
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            uint32_t v[32];
+            if (iters > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (co >= p.cout) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int ci = ci0 + c0 + j;
+                if (ci < p.cin) dst[ci] = __uint_as_float(v[j]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.bn);
+}
+
+// per-split column sums of dy for the bias gradient
+__global__ void bias_partial_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ ws_b, int cout,
+                                    long long m_total, long long chunk) {
+    const int split = blockIdx.x;
+    const long long m0 = (long long)split * chunk;
+    long long m1 = m0 + chunk;
+    if (m1 > m_total) m1 = m_total;
+    // blockDim = (32 channels, 8 pixel lanes)
+    __shared__ float red[8][33];
+    for (int cb = 0; cb < cout; cb += 32) {
+        const int c = cb + threadIdx.x;
+        float acc = 0.f;
+        if (c < cout)
+            for (long long m = m0 + threadIdx.y; m < m1; m += 8) acc += dy[m * lddy + c];
+        red[threadIdx.y][threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.y == 0 && c < cout) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+            ws_b[(long long)split * cout + c] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// NHWC activation view [n][h][w][c] (pixel stride ld floats) with box {32, bw, bh, 1}
+bool make_act_map(CUtensorMap* map, const float* base, int ld, int n, int h, int w, int c, int bw, int bh) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)w * ld * 4, (cuuint64_t)h * w * ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// KRSC weights [cout][k*k][cin] (row stride ldw floats) with box {32, 1, bn}
+bool make_weight_map(CUtensorMap* map, const float* base, int ldw, int cout, int taps, int cin, int bn) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)cout};
+    cuuint64_t strides[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)taps * ldw * 4};
+    cuuint32_t box[3] = {(cuuint32_t)KCH, 1, (cuuint32_t)bn};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int device_is_sm100() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        cached = (major == 10) ? 1 : 0;
+    }
+    return cached;
+}
+
+// spatial tile of `pixels` pixels: widest power-of-two row segment that fits the image width
+void pick_tile(int w, int pixels, int* tw, int* th) {
+    int t = 1;
+    while (t * 2 <= pixels && t * 2 <= w) t *= 2;
+    // prefer an exact divisor of w when one exists among the powers of two (no wasted columns)
+    int best = t;
+    for (int c = t; c >= 8; c >>= 1)
+        if (w % c == 0) { best = c; break; }
+    *tw = best;
+    *th = pixels / best;
+}
+
+int pick_bn(int cout) {
+    if (cout <= 32) return 32;
+    if (cout <= 64) return 64;
+    if (cout <= 128) return 128;
+    return (cout % 256 == 0 || cout > 384) ? 256 : 128;
+}
+
+bool aligned_view(const float* p, int ld) { return mi_al16(p) && (ld % 4 == 0); }
+
+}  // namespace
+
+bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, const float* y, int ldy, int n, int h,
+                          int wd, int cin, int cout, int k) {
+    (void)y; (void)ldy; (void)n;
+    if (!device_is_sm100() || !encode_fn()) return false;
+    if (!aligned_view(x, ldx) || !aligned_view(w, ldw)) return false;
+    if (k > 7 || wd < 8 || h < 1) return false;
+    if (cout < 16) return false;   // tiny heads stay on the exact fp32 SIMT engine
+    if (cin < 8) return false;
+    return true;
+}
+
+int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+                const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd,
+                int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
+    FpropParams p;
+    p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.k = k;
+    pick_tile(wd, BM, &p.tw, &p.th);
+    p.tiles_x = mi_cdiv(wd, p.tw);
+    p.tiles_y = mi_cdiv(h, p.th);
+    p.bn = pick_bn(cout);
+    p.act = act; p.slope = slope; p.accumulate = accumulate; p.mask_act = mask_act; p.mask_slope = mask_slope;
+    p.ldy = ldy; p.ldmask = ldmask; p.bias = bias; p.mask_y = mask_y; p.y = y;
+    const size_t stage_bytes = (size_t)(BM + p.bn) * ROW_BYTES;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (p.bn <= 128 && stages > 3) stages = 3;   // leave room for 2 CTAs per SM so epilogues overlap mainloops
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + (2 * stages + 2) * 8 + 1024;
+    CUtensorMap map_x, map_w;
+    if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, p.tw, p.th)) return MI_ERR_UNSUPPORTED;
+    if (!make_weight_map(&map_w, w, ldw, cout, k * k, cin, p.bn)) return MI_ERR_UNSUPPORTED;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(220 * 1024));
+        if (e != cudaSuccess) return (int)e;
+        smem_set = 220 * 1024;
+    }
+    dim3 grid(p.tiles_x * p.tiles_y * n, mi_cdiv(cout, p.bn));
+    conv_fprop_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, p);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
+                          int k) {
+    (void)n;
+    if (!device_is_sm100() || !encode_fn()) return false;
+    if (!aligned_view(x, ldx) || !aligned_view(dy, lddy)) return false;
+    if (k > 7 || wd < 8 || h < 1) return false;
+    if (cout < 16 || cin < 8) return false;
+    return true;
+}
+
+int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
+                         int k, int ldw, float* ws_w, float* ws_b, int splits, cudaStream_t stream) {
+    WgradParams p;
+    p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.k = k; p.ldw = ldw;
+    pick_tile(wd, 64, &p.pw, &p.ph);
+    p.tiles_x = mi_cdiv(wd, p.pw);
+    p.tiles_y = mi_cdiv(h, p.ph);
+    p.total_tiles = p.tiles_x * p.tiles_y * n;
+    p.bn = cin <= 32 ? 32 : (cin <= 64 ? 64 : 128);
+    p.co_tiles = mi_cdiv(cout, BM);
+    p.ci_tiles = mi_cdiv(cin, p.bn);
+    p.tiles_per_split = mi_cdiv(p.total_tiles, splits);
+    p.ws_w = ws_w;
+    const size_t stage_bytes = (size_t)(BM / KCH + p.bn / KCH) * 64 * ROW_BYTES;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 4) stages = 4;
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + (2 * stages + 2) * 8 + 1024;
+    CUtensorMap map_dy, map_x;
+    if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, p.pw, p.ph)) return MI_ERR_UNSUPPORTED;
+    if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, p.pw, p.ph)) return MI_ERR_UNSUPPORTED;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(220 * 1024));
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    dim3 grid(k * k * p.co_tiles * p.ci_tiles, splits);
+    conv_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, p);
+    MI_LAUNCHED();
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) return (int)e;
+    const long long m_total = (long long)n * h * wd;
+    const long long chunk = (m_total + splits - 1) / splits;
+    bias_partial_kernel<<<splits, dim3(32, 8), 0, stream>>>(dy, lddy, ws_b, cout, m_total, chunk);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
+extern "C" int mi_tc_available(void) { return (device_is_sm100() && encode_fn()) ? 1 : 0; }

@@ -104,10 +104,14 @@ class _Program:
         if self.graph is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = int(fp.ops.lib.mi_launch_count())
             with torch.cuda.graph(g):
                 self.body(self)
+            self.kernels = int(fp.ops.lib.mi_launch_count()) - n0   # recorded, not executed, during capture
+            fp.ops.replayed_launches -= self.kernels
             self.graph = g
         self.graph.replay()
+        fp.ops.replayed_launches += self.kernels
 
 
 class FastPath:

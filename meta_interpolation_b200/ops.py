@@ -13,6 +13,8 @@ Tensors are torch CUDA tensors used purely as device-memory handles:
 test-suite can inject the oracle's table (oracle/ops_ref.py) to check the host
 logic without a GPU; nothing in this package imports the oracle.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -67,8 +69,10 @@ class CudaOps:
         if not torch.cuda.is_available():
             raise _lib.MiB200Error("CudaOps needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.engine = engine
+        env = os.environ.get("MI_B200_ENGINE", "").lower()   # debugging aid: force one conv engine everywhere
+        self.engine = {"simt": ENGINE_SIMT, "tc": ENGINE_TC}.get(env, engine)
         self._ws = None
+        self.replayed_launches = 0   # kernels executed through CUDA-graph replays (counted at capture time)
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -105,7 +109,8 @@ class CudaOps:
         return self._ws
 
     def launch_count(self):
-        return int(self.lib.mi_launch_count())
+        """libmi_b200 kernels executed so far: eager launches + kernels inside replayed CUDA graphs."""
+        return int(self.lib.mi_launch_count()) + self.replayed_launches
 
     # ------------------------------------------------------------------ convolution
     def conv_fprop(self, x, w, b, act=ACT_NONE, slope=0.0, out=None, engine=None):

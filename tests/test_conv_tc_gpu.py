@@ -1,0 +1,89 @@
+"""tcgen05 (TF32) convolution engine against the fp32 CPU reference and the on-device SIMT engine.
+
+Tolerance: TF32 operands carry a 10-bit mantissa (2^-11 relative rounding per operand); with fp32
+accumulation the result differs from fp32 by ~1e-3 of the output scale.  Stated bar: 4e-3 * max|ref|."""
+import pytest
+import torch
+
+from oracle.ops_ref import RefOps
+from meta_interpolation_b200.ops import ACT_NONE, ACT_RELU, ENGINE_SIMT, ENGINE_TC, WG_STORE, WgradSpec, pad4
+from test_kernels_gpu import act_pair, weight_pair, close
+
+pytestmark = pytest.mark.gpu
+REF = RefOps()
+TF32_TOL = 4e-3
+
+TC_SHAPES = [
+    # n, h, w, cin, cout, k
+    (2, 16, 24, 32, 32, 3), (1, 12, 16, 64, 51, 3), (1, 16, 16, 51, 51, 3), (2, 6, 8, 128, 64, 3),
+    (1, 24, 32, 256, 512, 3), (1, 9, 14, 64, 64, 3), (1, 10, 12, 20, 32, 7), (2, 8, 16, 64, 64, 5),
+    (1, 48, 64, 64, 64, 3), (1, 8, 8, 192, 16, 1),
+]
+
+
+def _require_tc(ops):
+    if not ops.lib.mi_tc_available():
+        pytest.skip("tcgen05 path not available on this device")
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_fprop_tc(cuda_ops, shape):
+    _require_tc(cuda_ops)
+    n, h, w, cin, cout, k = shape
+    xc, xd = act_pair(cuda_ops, n, h, w, cin, 41)
+    wc, wd = weight_pair(cuda_ops, cout, cin, k, 42)
+    bc = torch.rand(cout) - 0.5
+    yc = REF.conv_fprop(xc, wc, bc, ACT_RELU)
+    yd = cuda_ops.conv_fprop(xd, wd, bc.cuda(), ACT_RELU, engine=ENGINE_TC)
+    close(yd, yc, TF32_TOL, "tc fprop")
+    ys = cuda_ops.conv_fprop(xd, wd, bc.cuda(), ACT_RELU, engine=ENGINE_SIMT)
+    close(yd, ys.cpu(), TF32_TOL, "tc vs simt")
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_dgrad_tc(cuda_ops, shape):
+    _require_tc(cuda_ops)
+    n, h, w, cin, cout, k = shape
+    if cin < 16:
+        pytest.skip("dgrad output channels below the tensor-core threshold")
+    dyc, dyd = act_pair(cuda_ops, n, h, w, cout, 43)
+    wc, wd = weight_pair(cuda_ops, cout, cin, k, 44)
+    mc, md = act_pair(cuda_ops, n, h, w, cin, 45)
+    dxc = REF.conv_dgrad(dyc, wc, mask_y=mc, mask_act=ACT_RELU)
+    dxd = cuda_ops.conv_dgrad(dyd, wd, mask_y=md, mask_act=ACT_RELU, engine=ENGINE_TC)
+    close(dxd, dxc, TF32_TOL, "tc dgrad")
+    acc_c, acc_d = act_pair(cuda_ops, n, h, w, cin, 46)
+    REF.conv_dgrad(dyc, wc, out=acc_c, accumulate=True)
+    cuda_ops.conv_dgrad(dyd, wd, out=acc_d, accumulate=True, engine=ENGINE_TC)
+    close(acc_d, acc_c, TF32_TOL, "tc dgrad accumulate")
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_wgrad_tc(cuda_ops, shape):
+    _require_tc(cuda_ops)
+    n, h, w, cin, cout, k = shape
+    xc, xd = act_pair(cuda_ops, n, h, w, cin, 47)
+    dyc, dyd = act_pair(cuda_ops, n, h, w, cout, 48)
+    ld = pad4(cin)
+    gwc, gwd = REF.empty_weight(cout, cin, k), cuda_ops.empty_weight(cout, cin, k)
+    gbc, gbd = torch.zeros(cout), torch.zeros(cout, device="cuda")
+    REF.conv_wgrad(xc, dyc, k, ld, WgradSpec(WG_STORE, grad_w=gwc, grad_b=gbc))
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_STORE, grad_w=gwd, grad_b=gbd), engine=ENGINE_TC)
+    close(gwd, gwc, TF32_TOL, "tc wgrad w")
+    close(gbd, gbc, 1e-4, "tc wgrad b")
+
+
+def test_large_canvas_tc_vs_simt(cuda_ops):
+    """BASELINE canvas (384x512): the two engines agree on the 51->51 full-resolution layer."""
+    _require_tc(cuda_ops)
+    ops = cuda_ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = ops.empty_act(1, 384, 512, 51)
+    x.copy_(torch.rand(1, 384, 512, 51, device="cuda", generator=g) - 0.5)
+    w = ops.empty_weight(51, 51, 3)
+    w.copy_((torch.rand(51, 3, 3, 51, device="cuda", generator=g) - 0.5) * 0.1)
+    b = torch.rand(51, device="cuda", generator=g)
+    yt = ops.conv_fprop(x, w, b, engine=ENGINE_TC)
+    ys = ops.conv_fprop(x, w, b, engine=ENGINE_SIMT)
+    d = (yt - ys).abs().max().item()
+    assert d <= TF32_TOL * ys.abs().max().item(), d

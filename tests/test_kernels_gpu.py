@@ -324,4 +324,4 @@ def test_bad_arguments_raise(cuda_ops):
         cuda_ops.avgpool_fwd(x)
     w = cuda_ops.empty_weight(4, 4, 3)
     with pytest.raises(MiB200Error):
-        cuda_ops.conv_fprop(cuda_ops.empty_act(1, 4, 4, 3), w, None, engine=ENGINE_TC)   # ineligible shape for tcgen05
+        cuda_ops.conv_fprop(cuda_ops.empty_act(1, 4, 4, 4), w, None, engine=ENGINE_TC)   # ineligible shape for tcgen05
