@@ -53,6 +53,12 @@ unsigned long long mi_launch_count(void);
 /* 1 if the tcgen05 path was compiled in and the current device is sm_100 */
 int mi_tc_available(void);
 
+/* per-launch CUDA-event timing of the hot kernels (bench.py roofline section).  tag: 0 fprop/dgrad tcgen05,
+ * 1 wgrad tcgen05, 2 fprop/dgrad SIMT, 3 wgrad SIMT, 4 sepconv fwd, 5 sepconv bwd, 6 wgrad finish.
+ * out[4] = {launches, total ms, algorithmic flops, algorithmic bytes}.  Not usable under graph capture. */
+int mi_prof_enable(int on);
+int mi_prof_summary(int tag, double* out);
+
 /* ------------------------------------------------------------------ convolution
  * Replaces F.conv2d in MetaConv2dLayer.forward (model_utils.py:360) and its
  * autograd backward; stride 1, padding k/2, dilation 1, groups 1 (the only

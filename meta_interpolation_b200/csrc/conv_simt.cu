@@ -300,8 +300,10 @@ int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int
     const long long total = (long long)cout * k * k * ldw + cout;
     int blocks = mi_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
+    mi_prof_begin(MI_TAG_WGRAD_FINISH, 0.0, 4.0 * (double)total * (splits + 2), stream);
     wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, cin, cout, k * k, ldw, mode, scale, grad_w,
                                                     grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b);
+    mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }
@@ -312,9 +314,12 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
     const long long m_total = (long long)n * h * wd;
     dim3 grid(mi_cdiv(m_total, BM), mi_cdiv(cout, BN));
     const int vec_ok = (ldx % 4 == 0) && (ldw % 4 == 0) && mi_al16(x) && mi_al16(w);
+    mi_prof_begin(MI_TAG_FPROP_SIMT, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+                  stream);
     conv_fprop_simt_kernel<<<grid, 256, 0, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask, mask_act,
                                                      mask_slope, accumulate, n, h, wd, cin, cout, k, act, slope,
                                                      vec_ok);
+    mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }
@@ -395,8 +400,11 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
         dim3 grid(k * k * co_tiles * ci_tiles, splits);
         const int vec_x = (ldx % 4 == 0) && mi_al16(x);
         const int vec_dy = (lddy % 4 == 0) && mi_al16(dy);
+        mi_prof_begin(MI_TAG_WGRAD_SIMT, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+                      st);
         conv_wgrad_simt_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, lddy, ws_w, ws_b, n, h, wd, cin, cout, k, ldw,
                                                      co_tiles, ci_tiles, chunk, vec_x, vec_dy);
+        mi_prof_end(st);
         MI_LAUNCHED();
         rc = (int)cudaPeekAtLastError();
     }

@@ -97,14 +97,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte chunks; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks;
+// the only layout the hardware accepts for MN-major TF32 operands)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= 1ull << 46;                                  // descriptor version (Blackwell)
     d |= (uint64_t)((addr >> 7) & 7u) << 49;          // base offset: swizzle phase of the start row
-    d |= 2ull << 61;                                  // SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 // instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
@@ -323,9 +326,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
                 for (int kk = 0; kk < ksteps; ++kk) {
-                    // 8 pixels (K) x 32 channels (MN) atoms of 1024 B; MN blocks of 32 channels are box_bytes apart
-                    const uint64_t ad = smem_desc(a_addr + kk * 1024, box_bytes, 1024);
-                    const uint64_t bd = smem_desc(b_addr + kk * 1024, box_bytes, 1024);
+                    // MN-major TF32: swizzle atoms are 4 pixels (K) x 32 channels (MN) = 512 B, so one K=8 MMA
+                    // spans two atoms SBO=512 B apart; MN blocks of 32 channels are box_bytes apart (LBO)
+                    const uint64_t ad = smem_desc(a_addr + kk * 1024, box_bytes, 512, 1);
+                    const uint64_t bd = smem_desc(b_addr + kk * 1024, box_bytes, 512, 1);
                     umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
                 }
                 umma_commit(smem_u32(&bars[p.stages + s]));
@@ -407,7 +411,8 @@ EncodeTiledFn encode_fn() {
 }
 
 // NHWC activation view [n][h][w][c] (pixel stride ld floats) with box {32, bw, bh, 1}
-bool make_act_map(CUtensorMap* map, const float* base, int ld, int n, int h, int w, int c, int bw, int bh) {
+bool make_act_map(CUtensorMap* map, const float* base, int ld, int n, int h, int w, int c, int bw, int bh,
+                  CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -415,7 +420,7 @@ bool make_act_map(CUtensorMap* map, const float* base, int ld, int n, int h, int
     cuuint32_t box[4] = {(cuuint32_t)KCH, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -509,7 +514,9 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         smem_set = 220 * 1024;
     }
     dim3 grid(p.tiles_x * p.tiles_y * n, mi_cdiv(cout, p.bn));
+    mi_prof_begin(MI_TAG_FPROP_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
     conv_fprop_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, p);
+    mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }
@@ -544,8 +551,10 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
     p.stages = stages;
     const size_t smem = stages * stage_bytes + (2 * stages + 2) * 8 + 1024;
     CUtensorMap map_dy, map_x;
-    if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, p.pw, p.ph)) return MI_ERR_UNSUPPORTED;
-    if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, p.pw, p.ph)) return MI_ERR_UNSUPPORTED;
+    if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, p.pw, p.ph, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return MI_ERR_UNSUPPORTED;
+    if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, p.pw, p.ph, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        return MI_ERR_UNSUPPORTED;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -554,7 +563,9 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         attr = true;
     }
     dim3 grid(k * k * p.co_tiles * p.ci_tiles, splits);
+    mi_prof_begin(MI_TAG_WGRAD_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
     conv_wgrad_tc_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, p);
+    mi_prof_end(stream);
     MI_LAUNCHED();
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return (int)e;

@@ -15,6 +15,18 @@ extern std::atomic<unsigned long long> g_mi_launches;
         return (int)e__;                         \
     } while (0)
 
+// per-launch profiling hooks (profile.cu); no-ops unless mi_prof_enable(1)
+enum { MI_TAG_FPROP_TC = 0, MI_TAG_WGRAD_TC = 1, MI_TAG_FPROP_SIMT = 2, MI_TAG_WGRAD_SIMT = 3, MI_TAG_SEPCONV_FWD = 4,
+       MI_TAG_SEPCONV_BWD = 5, MI_TAG_WGRAD_FINISH = 6 };
+void mi_prof_begin(int tag, double flops, double bytes, cudaStream_t s);
+void mi_prof_end(cudaStream_t s);
+static inline double mi_conv_flops(int n, int h, int w, int cin, int cout, int k) {
+    return 2.0 * n * h * w * (double)cin * cout * k * k;
+}
+static inline double mi_conv_bytes(int n, int h, int w, int cin, int cout, int k) {
+    return 4.0 * ((double)n * h * w * (cin + cout) + (double)cout * k * k * cin);
+}
+
 static inline cudaStream_t mi_cs(mi_stream_t s) { return (cudaStream_t)s; }
 static inline int mi_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline bool mi_al16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }

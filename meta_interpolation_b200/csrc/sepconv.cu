@@ -220,8 +220,11 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
             attr_set = true;
         }
         dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY), n);
+        const double px = (double)n * oh * ow;
+        mi_prof_begin(MI_TAG_SEPCONV_FWD, 2.0 * px * (3 * 51 * 51 + 3 * 51), 4.0 * px * (2 * 51 + 3 + 3), st);
         sepconv_fwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, out, fh, fw, gh, gw, oh, ow, gy0,
                                                              gx0, iy0, ix0);
+        mi_prof_end(st);
     } else {
         const long long total = (long long)n * c * oh * ow;
         int blocks = mi_cdiv(total, 128);
@@ -250,8 +253,11 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
             attr_set = true;
         }
         dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY), n);
+        const double px = (double)n * oh * ow;
+        mi_prof_begin(MI_TAG_SEPCONV_BWD, 2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51), 4.0 * px * (4 * 51 + 3 + 3), st);
         sepconv_bwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz, ldg,
                                                              fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
+        mi_prof_end(st);
     } else {
         const long long total = (long long)n * oh * ow * taps;
         int blocks = mi_cdiv(total, 128);

@@ -112,6 +112,23 @@ class CudaOps:
         """libmi_b200 kernels executed so far: eager launches + kernels inside replayed CUDA graphs."""
         return int(self.lib.mi_launch_count()) + self.replayed_launches
 
+    # ------------------------------------------------------------------ per-launch profiling (bench roofline)
+    PROF_TAGS = {"fprop_tc": 0, "wgrad_tc": 1, "fprop_simt": 2, "wgrad_simt": 3, "sepconv_fwd": 4, "sepconv_bwd": 5,
+                 "wgrad_finish": 6}
+
+    def prof_enable(self, on):
+        _lib.check(self.lib.mi_prof_enable(1 if on else 0), "mi_prof_enable")
+
+    def prof_summary(self):
+        """{tag: dict(launches, ms, flops, bytes)} since prof_enable(True) (synchronises the device)."""
+        import ctypes
+        out = {}
+        buf = (ctypes.c_double * 4)()
+        for name, tag in self.PROF_TAGS.items():
+            _lib.check(self.lib.mi_prof_summary(tag, ctypes.cast(buf, ctypes.c_void_p)), "mi_prof_summary")
+            out[name] = dict(launches=int(buf[0]), ms=buf[1], flops=buf[2], bytes=buf[3])
+        return out
+
     # ------------------------------------------------------------------ convolution
     def conv_fprop(self, x, w, b, act=ACT_NONE, slope=0.0, out=None, engine=None):
         n, h, wd, cin = x.shape
