@@ -331,9 +331,12 @@ int mi_conv2d_fprop(const float* x, int ldx, const float* w, int ldw, const floa
     if (!x || !w || !y || n <= 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || (k & 1) == 0 || ldx < cin ||
         ldw < cin || ldy < cout)
         return MI_ERR_BAD_ARG;
-    if (engine != MI_ENGINE_SIMT && mi_tc_fprop_eligible(x, ldx, w, ldw, y, ldy, n, h, wd, cin, cout, k))
-        return mi_tc_fprop(x, ldx, w, ldw, bias, y, ldy, nullptr, 0, 0, 0.f, 0, n, h, wd, cin, cout, k, act, slope,
-                           mi_cs(stream));
+    if (engine != MI_ENGINE_SIMT && mi_tc_fprop_eligible(x, ldx, w, ldw, y, ldy, n, h, wd, cin, cout, k)) {
+        const int rc = mi_tc_fprop(x, ldx, w, ldw, bias, y, ldy, nullptr, 0, 0, 0.f, 0, n, h, wd, cin, cout, k, act,
+                                   slope, mi_cs(stream));
+        // a tensor map the driver refuses is a shape limit, not an error: AUTO moves on to the other CUDA engine
+        if (rc != MI_ERR_UNSUPPORTED || engine == MI_ENGINE_TC) return rc;
+    }
     if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
     return fprop_simt_launch(x, ldx, w, ldw, bias, y, ldy, nullptr, 0, 0, 0.f, 0, n, h, wd, cin, cout, k, act, slope,
                              mi_cs(stream));
@@ -346,9 +349,11 @@ int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt, float*
         ldwt < cout || lddx < cin)
         return MI_ERR_BAD_ARG;
     // dgrad == fprop over dy with the rotated/transposed filter: roles of cin/cout swap
-    if (engine != MI_ENGINE_SIMT && mi_tc_fprop_eligible(dy, lddy, wt, ldwt, dx, lddx, n, h, wd, cout, cin, k))
-        return mi_tc_fprop(dy, lddy, wt, ldwt, nullptr, dx, lddx, mask_y, ldmask, mask_act, mask_slope, accumulate, n,
-                           h, wd, cout, cin, k, MI_ACT_NONE, 0.f, mi_cs(stream));
+    if (engine != MI_ENGINE_SIMT && mi_tc_fprop_eligible(dy, lddy, wt, ldwt, dx, lddx, n, h, wd, cout, cin, k)) {
+        const int rc = mi_tc_fprop(dy, lddy, wt, ldwt, nullptr, dx, lddx, mask_y, ldmask, mask_act, mask_slope,
+                                   accumulate, n, h, wd, cout, cin, k, MI_ACT_NONE, 0.f, mi_cs(stream));
+        if (rc != MI_ERR_UNSUPPORTED || engine == MI_ENGINE_TC) return rc;
+    }
     if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
     return fprop_simt_launch(dy, lddy, wt, ldwt, nullptr, dx, lddx, mask_y, ldmask, mask_act, mask_slope, accumulate,
                              n, h, wd, cout, cin, k, MI_ACT_NONE, 0.f, mi_cs(stream));

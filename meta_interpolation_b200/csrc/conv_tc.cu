@@ -12,6 +12,7 @@
 // (one lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> bias/activation/mask -> global).
 // Replaces cuDNN's F.conv2d kernels used by the reference (model_utils.py:360).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "mi_common.cuh"
 
@@ -110,10 +111,112 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     d |= (uint64_t)layout_type << 61;
     return d;
 }
+// The MMA-issuing thread is a single lane: building a descriptor from scratch per instruction (a dozen dependent
+// integer ops) costs more issue cycles than a 128xN MMA with small N takes to execute.  So descriptors are built
+// once per stage and advanced with one 64-bit add: the start-address field counts 16-byte units in bits [0,14).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+__device__ __forceinline__ uint64_t desc_with_base_offset(uint64_t desc, uint32_t phase) {
+    return (desc & ~(7ull << 49)) | ((uint64_t)(phase & 7u) << 49);
+}
 // instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
 __device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Epilogue for one 32-channel chunk of one output pixel (one thread == one TMEM lane).
+// ncu showed the first version (per-element `if`s, __ldg of the bias inside them) serialising ~64 dependent
+// global loads per tile; here the bias comes from shared memory, the activation switch is hoisted out of
+// the element loop, and mask / accumulate operands are fetched as independent float4 loads.
+struct EpiArgs {
+    int cout, cout_store, act, mask_act, accumulate;   // cout_store = cout rounded up to 4 when the row stride allows
+    float slope, mask_slope;
+};
+
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* __restrict__ sbias, int co,
+                                               const EpiArgs& e, const float* __restrict__ mrow, float* yrow, bool vec) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + sbias[j];
+    if (e.act == MI_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if (e.act == MI_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * e.slope;
+    } else if (e.act != MI_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = mi_act_apply(o[j], e.act, e.slope);
+    }
+    if (vec && co + 32 <= e.cout) {
+        if (mrow) {
+            float4 m[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) m[g] = __ldg(reinterpret_cast<const float4*>(mrow + co) + g);
+            if (e.mask_act == MI_ACT_RELU) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    o[4 * g + 0] = m[g].x > 0.f ? o[4 * g + 0] : 0.f;
+                    o[4 * g + 1] = m[g].y > 0.f ? o[4 * g + 1] : 0.f;
+                    o[4 * g + 2] = m[g].z > 0.f ? o[4 * g + 2] : 0.f;
+                    o[4 * g + 3] = m[g].w > 0.f ? o[4 * g + 3] : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    o[4 * g + 0] *= mi_act_grad(m[g].x, e.mask_act, e.mask_slope);
+                    o[4 * g + 1] *= mi_act_grad(m[g].y, e.mask_act, e.mask_slope);
+                    o[4 * g + 2] *= mi_act_grad(m[g].z, e.mask_act, e.mask_slope);
+                    o[4 * g + 3] *= mi_act_grad(m[g].w, e.mask_act, e.mask_slope);
+                }
+            }
+        }
+        if (e.accumulate) {
+            float4 a[8];
+#pragma unroll
+            for (int g = 0; g < 8; ++g) a[g] = *(reinterpret_cast<const float4*>(yrow + co) + g);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                o[4 * g + 0] += a[g].x; o[4 * g + 1] += a[g].y; o[4 * g + 2] += a[g].z; o[4 * g + 3] += a[g].w;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+            *(reinterpret_cast<float4*>(yrow + co) + g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    } else {
+        // ragged tail (e.g. 51 channels): float4 groups while they fit in the padded row (the pad lane of a
+        // 4-padded NHWC row is never read as data), guarded scalars for the rest
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int c = co + 4 * g;
+            if (c >= e.cout) break;
+            if (vec && c + 4 <= e.cout_store) {
+                float4 r = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+                if (mrow) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(mrow + c));
+                    r.x *= mi_act_grad(m.x, e.mask_act, e.mask_slope);
+                    r.y *= mi_act_grad(m.y, e.mask_act, e.mask_slope);
+                    r.z *= mi_act_grad(m.z, e.mask_act, e.mask_slope);
+                    r.w *= mi_act_grad(m.w, e.mask_act, e.mask_slope);
+                }
+                if (e.accumulate) {
+                    const float4 a = *reinterpret_cast<const float4*>(yrow + c);
+                    r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+                }
+                *reinterpret_cast<float4*>(yrow + c) = r;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (c + q < e.cout) {
+                        float val = o[4 * g + q];
+                        if (mrow) val *= mi_act_grad(__ldg(mrow + c + q), e.mask_act, e.mask_slope);
+                        if (e.accumulate) val += yrow[c + q];
+                        yrow[c + q] = val;
+                    }
+                }
+            }
+        }
+    }
 }
 
 struct FpropParams {
@@ -148,6 +251,11 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int chunks = (p.cin + KCH - 1) / KCH;
     const int iters = p.k * p.k * chunks;
 
+    __shared__ float sbias[256];
+    for (int i = threadIdx.x; i < p.bn; i += NTHREADS) {
+        const int c = co0 + i;
+        sbias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
@@ -187,12 +295,11 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
+                const uint64_t ad0 = smem_desc(a_addr, 16, 1024), bd0 = smem_desc(b_addr, 16, 1024);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t ad = smem_desc(a_addr + kk * 32, 16, 1024);
-                    const uint64_t bd = smem_desc(b_addr + kk * 32, 16, 1024);
-                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                }
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_tf32(tmem_base, desc_advance(ad0, kk * 32), desc_advance(bd0, kk * 32), idesc,
+                              (it > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(smem_u32(&bars[p.stages + s]));   // frees this smem stage when the MMAs retire
             }
             umma_commit(smem_u32(&bars[2 * p.stages]));       // accumulator complete
@@ -209,41 +316,183 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const long long pix = ((long long)img * p.h + oy) * p.w + ox;
         float* yrow = p.y + pix * p.ldy;
         const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
-        const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+        const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                         (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
+        EpiArgs ea;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.slope = p.slope; ea.mask_slope = p.mask_slope;
+        ea.cout_store = min(min((p.cout + 3) & ~3, p.ldy), p.mask_y ? p.ldmask : (1 << 30));
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            if (co0 + c0 >= p.cout) break;             // warp-uniform
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (!pix_ok) continue;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const int co = co0 + c0 + j;
-                if (co >= p.cout) break;
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = co + e;
-                    float val = __uint_as_float(v[j + e]);
-                    if (c < p.cout) {
-                        if (p.bias) val += __ldg(p.bias + c);
-                        val = mi_act_apply(val, p.act, p.slope);
-                        if (mrow) val *= mi_act_grad(__ldg(mrow + c), p.mask_act, p.mask_slope);
-                        if (p.accumulate) val += yrow[c];
-                    }
-                    o[e] = val;
-                }
-                if (vec && co + 3 < p.cout) {
-                    *reinterpret_cast<float4*>(yrow + co) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (co + e < p.cout) yrow[co + e] = o[e];
-                }
-            }
+            if (pix_ok) epilogue_chunk(v, sbias + c0, co0 + c0, ea, mrow, yrow, vec);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.bn);
+}
+
+// ------------------------------------------------------------------------------------------ fprop, small channels
+// 3x3 layers with Cin <= 64 and Cout <= 64 (two thirds of SepConv's conv FLOPs, all at high resolution) are bound
+// by L2->SM operand traffic in the per-tap kernel above (each tap re-reads the activation tile and every CTA
+// re-reads the weights).  This persistent variant
+//   * keeps ALL weights of the layer resident in shared memory (<= 144 KB), loaded once per CTA;
+//   * stages one HALO tile of the activation per 32-channel chunk -- an 18x16-pixel box for an 8(w)x16(h)
+//     output tile -- and issues the 9 taps' MMAs from that single copy by offsetting the UMMA descriptor
+//     start address ((ky*16 + kx) rows of 128 B; the row pitch of 16 pixels keeps every 8-row core group at the
+//     same swizzle phase kx, carried in the descriptor's base-offset field);
+//   * double-buffers the accumulator in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+constexpr int HALO_W = 16, HALO_H = 18, HT_W = 8, HT_H = 16;
+constexpr uint32_t HALO_BYTES = HALO_W * HALO_H * ROW_BYTES;   // 36864
+
+struct HaloParams {
+    int n, h, w, cin, cout, chunks, bn, stages, tiles_x, tiles_y, total_tiles, act, accumulate, mask_act, ldy, ldmask,
+        base_offset_mode;
+    float slope, mask_slope;
+    const float* bias;
+    const float* mask_y;
+    float* y;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                          const HaloParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t b_tile = (uint32_t)p.bn * ROW_BYTES;            // one (tap, chunk) weight tile
+    const uint32_t b_total = 9u * p.chunks * b_tile;
+    uint8_t* smem_a = smem + b_total;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * HALO_BYTES);
+    // bars: [0,S) full, [S,2S) empty, 2S = weights loaded, 2S+1..2 = tmem full[2], 2S+3..4 = tmem empty[2]
+    const int S = p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    __shared__ float sbias[64];
+    if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[S + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * S]), 1);
+        mbar_init(smem_u32(&bars[2 * S + 1]), 1);
+        mbar_init(smem_u32(&bars[2 * S + 2]), 1);
+        mbar_init(smem_u32(&bars[2 * S + 3]), 128);
+        mbar_init(smem_u32(&bars[2 * S + 4]), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * p.bn));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t wbar = smem_u32(&bars[2 * S]);
+            mbar_expect_tx(wbar, b_total);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int ch = 0; ch < p.chunks; ++ch)
+                    tma_load_3d(smem_u32(smem) + (uint32_t)(tap * p.chunks + ch) * b_tile, &map_w, wbar, ch * KCH, tap, 0);
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                int tile = (int)blockIdx.x + t * (int)gridDim.x;
+                const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+                const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+                const int img = tile;
+                for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (uint32_t)(it / S) & 1u;
+                    mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&bars[s]);
+                    mbar_expect_tx(full, HALO_BYTES);
+                    tma_load_4d(smem_u32(smem_a + (size_t)s * HALO_BYTES), &map_x, full, ch * KCH, tx_i * HT_W - 1,
+                                ty_i * HT_H - 1, img);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(BM, p.bn, 0, 0);
+            mbar_wait(smem_u32(&bars[2 * S]), 0);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(smem);
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int buf = t & 1;
+                const uint32_t use = (uint32_t)(t >> 1);
+                mbar_wait(smem_u32(&bars[2 * S + 3 + buf]), (use & 1u) ^ 1u);   // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+                for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                    const int s = it % S;
+                    const uint32_t ph = (uint32_t)(it / S) & 1u;
+                    mbar_wait(smem_u32(&bars[s]), ph);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem_a + (size_t)s * HALO_BYTES);
+                    const uint64_t ad0 = smem_desc(a_base, 16, HALO_W * ROW_BYTES);     // 1024-aligned: base offset 0
+                    const uint64_t bd0 = smem_desc(b_base + (uint32_t)ch * b_tile, 16, 1024);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        // shift the view by (ky rows of 16 pixels + kx pixels).  Measured on B200 (tools/diag_halo.py):
+                        // the 128B swizzle XOR is taken from the ABSOLUTE smem address bits [7,10), so a
+                        // row-shifted start needs base offset 0; setting it to the start row's phase (kx) as the
+                        // PTX text suggests double-counts the phase and corrupts the kx != 0 taps.
+                        uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * HALO_W + kx) * ROW_BYTES);
+                        if (p.base_offset_mode) a_tap = desc_with_base_offset(a_tap, (uint32_t)kx);
+                        const uint64_t b_tap = desc_advance(bd0, (uint32_t)(tap * p.chunks) * b_tile);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                      (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&bars[S + s]));
+                }
+                umma_commit(smem_u32(&bars[2 * S + 1 + buf]));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int th_i = r >> 3, tw_i = r & 7;
+        const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                         (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
+        EpiArgs ea;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.slope = p.slope; ea.mask_slope = p.mask_slope;
+        ea.cout_store = min(min((p.cout + 3) & ~3, p.ldy), p.mask_y ? p.ldmask : (1 << 30));
+        for (int t = 0; t < my_tiles; ++t) {
+            const int buf = t & 1;
+            const uint32_t use = (uint32_t)(t >> 1);
+            int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            const int img = tile;
+            const int oy = ty_i * HT_H + th_i, ox = tx_i * HT_W + tw_i;
+            const bool pix_ok = (oy < p.h) && (ox < p.w);
+            const long long pix = ((long long)img * p.h + oy) * p.w + ox;
+            float* yrow = p.y + pix * p.ldy;
+            const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
+            mbar_wait(smem_u32(&bars[2 * S + 1 + buf]), use & 1u);
+            tc_fence_after();
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                if (c0 >= p.cout) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn + c0), v);
+                if (pix_ok) epilogue_chunk(v, sbias + c0, c0, ea, mrow, yrow, vec);
+            }
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[2 * S + 3 + buf])) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * p.bn));
 }
 
 // ------------------------------------------------------------------------------------------ wgrad partials
@@ -325,13 +574,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    // MN-major TF32: swizzle atoms are 4 pixels (K) x 32 channels (MN) = 512 B, so one K=8 MMA
-                    // spans two atoms SBO=512 B apart; MN blocks of 32 channels are box_bytes apart (LBO)
-                    const uint64_t ad = smem_desc(a_addr + kk * 1024, box_bytes, 512, 1);
-                    const uint64_t bd = smem_desc(b_addr + kk * 1024, box_bytes, 512, 1);
-                    umma_tf32(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-                }
+                // MN-major TF32: swizzle atoms are 4 pixels (K) x 32 channels (MN) = 512 B, so one K=8 MMA
+                // spans two atoms SBO=512 B apart; MN blocks of 32 channels are box_bytes apart (LBO)
+                const uint64_t ad0 = smem_desc(a_addr, box_bytes, 512, 1), bd0 = smem_desc(b_addr, box_bytes, 512, 1);
+                for (int kk = 0; kk < ksteps; ++kk)
+                    umma_tf32(tmem_base, desc_advance(ad0, kk * 1024), desc_advance(bd0, kk * 1024), idesc,
+                              (it > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(smem_u32(&bars[p.stages + s]));
             }
             umma_commit(smem_u32(&bars[2 * p.stages]));
@@ -353,10 +601,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
             if (co >= p.cout) continue;
+            const int cb = ci0 + c0;
+            if (cb >= p.cin) continue;
+            if (cb + 32 <= p.ldw) {
+                // whole chunk inside the padded row: 8 float4 stores (columns >= cin are exact zeros: TMA zero-fill)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int ci = ci0 + c0 + j;
-                if (ci < p.cin) dst[ci] = __uint_as_float(v[j]);
+                for (int g = 0; g < 8; ++g)
+                    *(reinterpret_cast<float4*>(dst + cb) + g) =
+                        make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                    __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (cb + j < p.cin) dst[cb + j] = __uint_as_float(v[j]);
             }
         }
     }
@@ -472,6 +729,37 @@ int pick_bn(int cout) {
 
 bool aligned_view(const float* p, int ld) { return mi_al16(p) && (ld % 4 == 0); }
 
+// MI_B200_HALO=0 falls back to the per-tap kernel for the small-channel layers (A/B switch for profiling)
+bool halo_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MI_B200_HALO");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// MI_B200_HALO_BO=0: leave the descriptor base-offset field 0 for row-shifted views (experiment switch)
+int halo_base_offset_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MI_B200_HALO_BO");
+        v = (e && e[0] == '1') ? 1 : 0;   // 1 reproduces the (wrong) phase-in-base-offset experiment
+    }
+    return v;
+}
+
+int num_sms() {
+    static int v = 0;
+    if (!v) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+    }
+    return v;
+}
+
 }  // namespace
 
 bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, const float* y, int ldy, int n, int h,
@@ -488,6 +776,43 @@ bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, cons
 int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                 const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd,
                 int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
+    if (k == 3 && cin <= 64 && cout <= 64 && halo_enabled()) {
+        HaloParams hp;
+        hp.n = n; hp.h = h; hp.w = wd; hp.cin = cin; hp.cout = cout;
+        hp.chunks = mi_cdiv(cin, KCH);
+        hp.bn = cout <= 32 ? 32 : 64;
+        hp.tiles_x = mi_cdiv(wd, HT_W);
+        hp.tiles_y = mi_cdiv(h, HT_H);
+        hp.total_tiles = hp.tiles_x * hp.tiles_y * n;
+        hp.base_offset_mode = halo_base_offset_mode();
+        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
+        hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
+        const size_t b_total = (size_t)9 * hp.chunks * hp.bn * ROW_BYTES;
+        const size_t budget = 226 * 1024 - 2048;   // 227 KB per CTA minus the kernel's static shared memory
+        int stages = (int)((budget - b_total) / HALO_BYTES);
+        if (stages > 4) stages = 4;
+        if (stages >= 2) {
+            hp.stages = stages;
+            const size_t smem = b_total + (size_t)stages * HALO_BYTES + (2 * stages + 6) * 8 + 1024;
+            CUtensorMap map_x, map_w;
+            if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, HALO_W, HALO_H)) return MI_ERR_UNSUPPORTED;
+            if (!make_weight_map(&map_w, w, ldw, cout, 9, cin, hp.bn)) return MI_ERR_UNSUPPORTED;
+            static bool attr = false;
+            if (!attr) {
+                cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_halo_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+                if (e != cudaSuccess) return (int)e;
+                attr = true;
+            }
+            int grid = hp.total_tiles < num_sms() ? hp.total_tiles : num_sms();
+            mi_prof_begin(MI_TAG_FPROP_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+                          stream);
+            conv_fprop_tc_halo_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, hp);
+            mi_prof_end(stream);
+            MI_LAUNCHED();
+            MI_RETURN_LAST();
+        }
+    }
     FpropParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.k = k;
     pick_tile(wd, BM, &p.tw, &p.th);

@@ -14,12 +14,16 @@ from .ops import ACT_NONE
 
 class Var:
     """An NHWC activation (or NCHW image for frames/predictions) plus its gradient slot."""
-    __slots__ = ("data", "grad", "requires_grad")
+    __slots__ = ("data", "grad", "requires_grad", "act", "slope", "consumers", "grad_masked")
 
     def __init__(self, data, requires_grad=True):
         self.data = data
         self.grad = None
         self.requires_grad = requires_grad
+        self.act = ACT_NONE        # activation fused into the producing conv's epilogue
+        self.slope = 0.0
+        self.consumers = 0         # ops reading this Var (decides whether the act mask can be fused)
+        self.grad_masked = False   # True once .grad already is the gradient w.r.t. the PRE-activation
 
 
 class ConvParam:
@@ -64,18 +68,27 @@ class Tape:
         ops = self.ops
         p = self.params(name)
         k = p.w.shape[1]
+        x.consumers += 1
         y = Var(ops.conv_fprop(x.data, p.w, p.b, act, slope, out=out))
+        y.act, y.slope = act, slope
 
         def bwd():
             dy = y.grad
             if dy is None:
                 return
-            if act != ACT_NONE:
+            if act != ACT_NONE and not y.grad_masked:
                 ops.act_bwd(dy, y.data, act, slope)
             # dgrad first: a fused-update sink may overwrite p.w in place, and the rotated copy
             # p.wt must come from the weights this forward pass actually used
             if x.requires_grad:
-                self._give(x, lambda o, acc: ops.conv_dgrad(dy, p.w, wt=p.wt(ops), out=o, accumulate=acc))
+                if x.consumers == 1 and x.act != ACT_NONE and x.grad is None:
+                    # sole consumer of an activated conv output: fold that activation's derivative into
+                    # this dgrad's epilogue, so x.grad is born as the pre-activation gradient
+                    x.grad = ops.conv_dgrad(dy, p.w, wt=p.wt(ops), mask_y=x.data, mask_act=x.act,
+                                            mask_slope=x.slope)
+                    x.grad_masked = True
+                else:
+                    self._give(x, lambda o, acc: ops.conv_dgrad(dy, p.w, wt=p.wt(ops), out=o, accumulate=acc))
             if self.sink is not None:
                 self.sink.weight_grad(p, x.data, dy, k)
             y.grad = None
@@ -85,6 +98,7 @@ class Tape:
 
     def avgpool(self, x):
         ops = self.ops
+        x.consumers += 1
         y = Var(ops.avgpool_fwd(x.data))
 
         def bwd():
@@ -102,6 +116,7 @@ class Tape:
 
     def maxpool(self, x):
         ops = self.ops
+        x.consumers += 1
         y = Var(ops.maxpool_fwd(x.data))
 
         def bwd():
@@ -119,6 +134,7 @@ class Tape:
 
     def upsample(self, x, align_corners, out=None):
         ops = self.ops
+        x.consumers += 1
         y = Var(ops.upsample_fwd(x.data, align_corners, out=out))
 
         def bwd():
@@ -136,6 +152,8 @@ class Tape:
 
     def add(self, a, b):
         ops = self.ops
+        a.consumers += 1
+        b.consumers += 1
         y = Var(ops.add(a.data, b.data))
 
         def bwd():
@@ -163,6 +181,8 @@ class Tape:
         """Var over a concat buffer whose channel slices were produced by ``parts`` (list of (Var, c0, c1))."""
         ops = self.ops
         y = Var(buf)
+        for v, _, _ in parts:
+            v.consumers += 1
 
         def bwd():
             g = y.grad
@@ -185,6 +205,8 @@ class Tape:
     def sepconv(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0):
         """Adaptive separable convolution; ``frame`` is NCHW data, result is an NCHW Var."""
         ops = self.ops
+        vert.consumers += 1
+        horiz.consumers += 1
         y = Var(ops.sepconv_fwd(frame, vert.data, horiz.data, oh, ow, gy0, gx0, iy0, ix0))
 
         def bwd():
@@ -204,6 +226,8 @@ class Tape:
     def add_nchw(self, a, b):
         """a += b on contiguous NCHW outputs (sepconv/model.py:349 ``tensorDot1 + tensorDot2``); shares the gradient."""
         ops = self.ops
+        a.consumers += 1
+        b.consumers += 1
         ops.axpby(b.data, 1.0, a.data, 1.0)
         y = Var(a.data)
 

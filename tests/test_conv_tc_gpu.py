@@ -18,6 +18,8 @@ TC_SHAPES = [
     (2, 16, 24, 32, 32, 3), (1, 12, 16, 64, 51, 3), (1, 16, 16, 51, 51, 3), (2, 6, 8, 128, 64, 3),
     (1, 24, 32, 256, 512, 3), (1, 9, 14, 64, 64, 3), (1, 10, 12, 20, 32, 7), (2, 8, 16, 64, 64, 5),
     (1, 48, 64, 64, 64, 3), (1, 8, 8, 192, 16, 1),
+    # persistent halo kernel: ragged tiles, and more tiles than SMs (TMEM double buffering, stage wrap-around)
+    (1, 17, 13, 40, 64, 3), (2, 200, 208, 64, 64, 3), (1, 130, 300, 32, 32, 3),
 ]
 
 
