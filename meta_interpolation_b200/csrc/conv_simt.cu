@@ -244,7 +244,7 @@ conv_wgrad_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
 
 // reduce the split-K partials and apply the requested epilogue (store / accumulate / fused inner update)
 __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float* __restrict__ ws_b, int splits,
-                                    int cin, int cout, int kk, int ldw, int mode, float scale,
+                                    int bias_splits, int cin, int cout, int kk, int ldw, int mode, float scale,
                                     float* __restrict__ grad_w, float* __restrict__ grad_b,
                                     const float* __restrict__ w_in, const float* __restrict__ b_in,
                                     float* __restrict__ w_out, float* __restrict__ b_out,
@@ -260,7 +260,8 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
         const float* src = is_b ? ws_b : ws_w;
         const long long stride = is_b ? cout : wsz;
         float g = 0.f;
-        for (int s = 0; s < splits; ++s) g += src[(long long)s * stride + e];
+        const int ns = is_b ? bias_splits : splits;
+        for (int s = 0; s < ns; ++s) g += src[(long long)s * stride + e];
         float* gout = is_b ? grad_b : grad_w;
         const float* pin = is_b ? b_in : w_in;
         float* pout = is_b ? b_out : w_out;
@@ -293,15 +294,22 @@ int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
     return (int)splits;
 }
 
-int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int cin, int cout, int k, int ldw,
-                           int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
+int mi_bias_splits(long long m_total) {
+    long long s = m_total / 1024;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    return (int)s;
+}
+
+int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int bias_splits, int cin, int cout, int k,
+                           int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
                            float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
                            float* gsum_b, cudaStream_t stream) {
     const long long total = (long long)cout * k * k * ldw + cout;
     int blocks = mi_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     mi_prof_begin(MI_TAG_WGRAD_FINISH, 0.0, 4.0 * (double)total * (splits + 2), stream);
-    wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, cin, cout, k * k, ldw, mode, scale, grad_w,
+    wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, bias_splits, cin, cout, k * k, ldw, mode, scale, grad_w,
                                                     grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b);
     mi_prof_end(stream);
     MI_LAUNCHED();
@@ -373,7 +381,8 @@ size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k,
     (void)engine;
     const int ldw = (cin + 3) & ~3;
     const size_t splits = (size_t)mi_wgrad_splits(n, h, wd, cin, cout, k);
-    return splits * ((size_t)cout * k * k * ldw + (size_t)cout) * sizeof(float) + 256;
+    const size_t bsplits = splits > 64 ? splits : 64;
+    return (splits * (size_t)cout * k * k * ldw + bsplits * (size_t)cout) * sizeof(float) + 256;
 }
 
 int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
@@ -388,14 +397,16 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
     if ((mode == MI_WG_SGD_SCALAR || mode == MI_WG_SGD_TENSOR) && (!w_in || !w_out || !lr_w)) return MI_ERR_BAD_ARG;
     const int splits = mi_wgrad_splits(n, h, wd, cin, cout, k);
     const size_t wsz = (size_t)cout * k * k * ldw;
-    const size_t need = (size_t)splits * (wsz + cout) * sizeof(float);
+    const size_t need = ((size_t)splits * wsz + (size_t)(splits > 64 ? splits : 64) * cout) * sizeof(float);
     if (workspace_bytes < need) return MI_ERR_WORKSPACE;
     float* ws_w = reinterpret_cast<float*>(workspace);
     float* ws_b = ws_w + (size_t)splits * wsz;
     cudaStream_t st = mi_cs(stream);
     int rc = MI_ERR_UNSUPPORTED;
+    int bias_splits = splits;   // the SIMT kernel emits one bias partial per split-K slice
     if (engine != MI_ENGINE_SIMT && mi_tc_wgrad_eligible(x, ldx, dy, lddy, n, h, wd, cin, cout, k))
         rc = mi_tc_wgrad_partials(x, ldx, dy, lddy, n, h, wd, cin, cout, k, ldw, ws_w, ws_b, splits, st);
+    if (rc == 0) bias_splits = mi_bias_splits((long long)n * h * wd);
     if (rc == MI_ERR_UNSUPPORTED) {
         if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
         const long long m_total = (long long)n * h * wd;
@@ -414,7 +425,7 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
         rc = (int)cudaPeekAtLastError();
     }
     if (rc != 0) return rc;
-    return mi_wgrad_finish_launch(ws_w, ws_b, splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
+    return mi_wgrad_finish_launch(ws_w, ws_b, splits, bias_splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
                                   w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, st);
 }
 

@@ -321,7 +321,9 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         EpiArgs ea;
         ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
-        ea.cout_store = min(min((p.cout + 3) & ~3, p.ldy), p.mask_y ? p.ldmask : (1 << 30));
+        // the pad lane may be written only when the row is exactly the 4-padded width (not a concat slice)
+        const int c4 = (p.cout + 3) & ~3;
+        ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
             if (co0 + c0 >= p.cout) break;             // warp-uniform
             uint32_t v[32];
@@ -465,7 +467,9 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         EpiArgs ea;
         ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
-        ea.cout_store = min(min((p.cout + 3) & ~3, p.ldy), p.mask_y ? p.ldmask : (1 << 30));
+        // the pad lane may be written only when the row is exactly the 4-padded width (not a concat slice)
+        const int c4 = (p.cout + 3) & ~3;
+        ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
         for (int t = 0; t < my_tiles; ++t) {
             const int buf = t & 1;
             const uint32_t use = (uint32_t)(t >> 1);
@@ -622,29 +626,34 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.bn);
 }
 
-// per-split column sums of dy for the bias gradient
+// column sums of dy for the bias gradient: grid (pixel slices, 32-channel groups), 32x8 threads; every block
+// streams its slice with 8 pixel lanes in flight per channel and writes one partial per (slice, channel)
 __global__ void bias_partial_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ ws_b, int cout,
                                     long long m_total, long long chunk) {
     const int split = blockIdx.x;
     const long long m0 = (long long)split * chunk;
     long long m1 = m0 + chunk;
     if (m1 > m_total) m1 = m_total;
-    // blockDim = (32 channels, 8 pixel lanes)
     __shared__ float red[8][33];
-    for (int cb = 0; cb < cout; cb += 32) {
-        const int c = cb + threadIdx.x;
-        float acc = 0.f;
-        if (c < cout)
-            for (long long m = m0 + threadIdx.y; m < m1; m += 8) acc += dy[m * lddy + c];
-        red[threadIdx.y][threadIdx.x] = acc;
-        __syncthreads();
-        if (threadIdx.y == 0 && c < cout) {
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
-            ws_b[(long long)split * cout + c] = s;
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    if (c < cout) {
+        long long m = m0 + threadIdx.y;
+        for (; m + 24 < m1; m += 32) {
+            acc0 += dy[m * lddy + c];
+            acc1 += dy[(m + 8) * lddy + c];
+            acc2 += dy[(m + 16) * lddy + c];
+            acc3 += dy[(m + 24) * lddy + c];
         }
-        __syncthreads();
+        for (; m < m1; m += 8) acc0 += dy[m * lddy + c];
+    }
+    red[threadIdx.y][threadIdx.x] = (acc0 + acc1) + (acc2 + acc3);
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cout) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
+        ws_b[(long long)split * cout + c] = s;
     }
 }
 
@@ -769,7 +778,7 @@ bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, cons
     if (!aligned_view(x, ldx) || !aligned_view(w, ldw)) return false;
     if (k > 7 || wd < 8 || h < 1) return false;
     if (cout < 16) return false;   // tiny heads stay on the exact fp32 SIMT engine
-    if (cin < 8) return false;
+    if (cin < 4) return false;     // (a 32-channel TMA box over a 6-channel tensor is legal: the tail is zero-filled)
     return true;
 }
 
@@ -852,7 +861,7 @@ bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, in
     if (!device_is_sm100() || !encode_fn()) return false;
     if (!aligned_view(x, ldx) || !aligned_view(dy, lddy)) return false;
     if (k > 7 || wd < 8 || h < 1) return false;
-    if (cout < 16 || cin < 8) return false;
+    if (cout < 16 || cin < 4) return false;
     return true;
 }
 
@@ -895,8 +904,10 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) return (int)e;
     const long long m_total = (long long)n * h * wd;
-    const long long chunk = (m_total + splits - 1) / splits;
-    bias_partial_kernel<<<splits, dim3(32, 8), 0, stream>>>(dy, lddy, ws_b, cout, m_total, chunk);
+    const int bsplits = mi_bias_splits(m_total);
+    const long long chunk = (m_total + bsplits - 1) / bsplits;
+    bias_partial_kernel<<<dim3(bsplits, mi_cdiv(cout, 32)), dim3(32, 8), 0, stream>>>(dy, lddy, ws_b, cout, m_total,
+                                                                                       chunk);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }

@@ -17,38 +17,74 @@ inline int grid_for(long long work) {
 #define GRID_STRIDE(i, total) \
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (total); i += (long long)gridDim.x * blockDim.x)
 
+// All NHWC kernels below work on groups of 4 channels: one thread = (pixel, channel group).  With 16-byte
+// aligned rows (`vec`) a group is one float4 access (pad lanes of a 4-padded row are never read as data, so
+// touching them is harmless); otherwise the group is handled with guarded scalars.
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* p, int valid, bool vec) {
+    F4 r;
+    if (vec) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r.v[q] = q < valid ? p[q] : 0.f;
+    }
+    return r;
+}
+__device__ __forceinline__ void st4(float* p, const F4& r, int valid, bool vec) {
+    if (vec) {
+        *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (q < valid) p[q] = r.v[q];
+    }
+}
+
 // ----------------------------------------------------------------------------- pooling
 __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
-                                    int wd, int c) {
-    const int oh = h >> 1, ow = wd >> 1;
-    const long long total = (long long)n * oh * ow * c;
+                                    int wd, int c, int vec) {
+    const int oh = h >> 1, ow = wd >> 1, cg = (c + 3) >> 2;
+    const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        long long p = i / c;
+        const int g = (int)(i % cg);
+        long long p = i / cg;
         const int ox = (int)(p % ow); p /= ow;
         const int oy = (int)(p % oh);
         const int nn = (int)(p / oh);
-        const float* s = x + ((long long)(nn * h + 2 * oy) * wd + 2 * ox) * ldx + ch;
-        const float v = (s[0] + s[ldx]) + (s[(long long)wd * ldx] + s[(long long)wd * ldx + ldx]);
-        y[((long long)(nn * oh + oy) * ow + ox) * ldy + ch] = 0.25f * v;
+        const int valid = min(4, c - 4 * g);
+        const float* s = x + ((long long)(nn * h + 2 * oy) * wd + 2 * ox) * ldx + 4 * g;
+        const F4 a = ld4(s, valid, vec), b = ld4(s + ldx, valid, vec);
+        const F4 cc = ld4(s + (long long)wd * ldx, valid, vec), d = ld4(s + (long long)wd * ldx + ldx, valid, vec);
+        F4 o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o.v[q] = 0.25f * ((a.v[q] + b.v[q]) + (cc.v[q] + d.v[q]));
+        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * g, o, valid, vec);
     }
 }
 
 __global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
-                                    int accumulate, int n, int h, int wd, int c) {
-    const int oh = h >> 1, ow = wd >> 1;
-    const long long total = (long long)n * h * wd * c;
+                                    int accumulate, int n, int h, int wd, int c, int vec) {
+    const int oh = h >> 1, ow = wd >> 1, cg = (c + 3) >> 2;
+    const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        long long p = i / c;
+        const int g = (int)(i % cg);
+        long long p = i / cg;
         const int xx = (int)(p % wd); p /= wd;
         const int yy = (int)(p % h);
         const int nn = (int)(p / h);
-        float v = 0.f;
-        if ((yy >> 1) < oh && (xx >> 1) < ow)
-            v = 0.25f * dy[((long long)(nn * oh + (yy >> 1)) * ow + (xx >> 1)) * lddy + ch];
-        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + ch;
-        *d = accumulate ? *d + v : v;
+        const int valid = min(4, c - 4 * g);
+        F4 v = ld4(dy + ((long long)(nn * oh + (yy >> 1)) * ow + (xx >> 1)) * lddy + 4 * g, valid, vec);
+        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + 4 * g;
+        if (accumulate) {
+            const F4 o = ld4(d, valid, vec);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v.v[q] = o.v[q] + 0.25f * v.v[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v.v[q] *= 0.25f;
+        }
+        st4(d, v, valid, vec);
     }
 }
 
@@ -119,39 +155,43 @@ __device__ __forceinline__ void up2_src(int o, int in_size, int align, int& i0, 
 }
 
 __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
-                                     int wd, int c, int align) {
-    const int oh = h * 2, ow = wd * 2;
-    const long long total = (long long)n * oh * ow * c;
+                                     int wd, int c, int align, int vec) {
+    const int oh = h * 2, ow = wd * 2, cg = (c + 3) >> 2;
+    const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        long long p = i / c;
+        const int g = (int)(i % cg);
+        long long p = i / cg;
         const int ox = (int)(p % ow); p /= ow;
         const int oy = (int)(p % oh);
         const int nn = (int)(p / oh);
+        const int valid = min(4, c - 4 * g);
         int y0, y1, x0, x1; float ty, tx;
         up2_src(oy, h, align, y0, y1, ty);
         up2_src(ox, wd, align, x0, x1, tx);
-        const float* b = x + (long long)nn * h * wd * ldx + ch;
-        const float v00 = b[((long long)y0 * wd + x0) * ldx], v01 = b[((long long)y0 * wd + x1) * ldx];
-        const float v10 = b[((long long)y1 * wd + x0) * ldx], v11 = b[((long long)y1 * wd + x1) * ldx];
-        const float v = (1.f - ty) * ((1.f - tx) * v00 + tx * v01) + ty * ((1.f - tx) * v10 + tx * v11);
-        y[((long long)(nn * oh + oy) * ow + ox) * ldy + ch] = v;
+        const float* b = x + (long long)nn * h * wd * ldx + 4 * g;
+        const F4 v00 = ld4(b + ((long long)y0 * wd + x0) * ldx, valid, vec), v01 = ld4(b + ((long long)y0 * wd + x1) * ldx, valid, vec);
+        const F4 v10 = ld4(b + ((long long)y1 * wd + x0) * ldx, valid, vec), v11 = ld4(b + ((long long)y1 * wd + x1) * ldx, valid, vec);
+        F4 o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            o.v[q] = (1.f - ty) * ((1.f - tx) * v00.v[q] + tx * v01.v[q]) + ty * ((1.f - tx) * v10.v[q] + tx * v11.v[q]);
+        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * g, o, valid, vec);
     }
 }
 
-// gather form of the transpose: each input pixel collects from the <=3x3... output pixels that read it.
-// Output o reads inputs (i0,i1); the outputs that can touch input i lie in [2i-2, 2i+2] (align=False) or a
-// comparable window (align=True); we scan a conservative window and test membership exactly.
+// gather form of the transpose: each input pixel collects from the output pixels that read it.  Output o reads
+// inputs (i0,i1); the outputs that can touch input i lie within [2i-3, 2i+3]; membership is tested exactly.
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
-                                     int accumulate, int n, int h, int wd, int c, int align) {
-    const int oh = h * 2, ow = wd * 2;
-    const long long total = (long long)n * h * wd * c;
+                                     int accumulate, int n, int h, int wd, int c, int align, int vec) {
+    const int oh = h * 2, ow = wd * 2, cg = (c + 3) >> 2;
+    const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        long long p = i / c;
+        const int g = (int)(i % cg);
+        long long p = i / cg;
         const int xx = (int)(p % wd); p /= wd;
         const int yy = (int)(p % h);
         const int nn = (int)(p / h);
+        const int valid = min(4, c - 4 * g);
         float wy[6]; int oy_[6]; int ny = 0;
         for (int o = max(0, 2 * yy - 3); o <= min(oh - 1, 2 * yy + 3); ++o) {
             int a, b; float t; up2_src(o, h, align, a, b, t);
@@ -168,45 +208,75 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
             if (b == xx) wgt += t;
             if (wgt != 0.f && nx < 6) { wx[nx] = wgt; ox_[nx] = o; ++nx; }
         }
-        float acc = 0.f;
+        F4 acc;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc.v[q] = 0.f;
         for (int a = 0; a < ny; ++a)
-            for (int b = 0; b < nx; ++b)
-                acc += wy[a] * wx[b] * dy[((long long)(nn * oh + oy_[a]) * ow + ox_[b]) * lddy + ch];
-        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + ch;
-        *d = accumulate ? *d + acc : acc;
+            for (int b = 0; b < nx; ++b) {
+                const F4 v = ld4(dy + ((long long)(nn * oh + oy_[a]) * ow + ox_[b]) * lddy + 4 * g, valid, vec);
+                const float wgt = wy[a] * wx[b];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc.v[q] += wgt * v.v[q];
+            }
+        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + 4 * g;
+        if (accumulate) {
+            const F4 o = ld4(d, valid, vec);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc.v[q] += o.v[q];
+        }
+        st4(d, acc, valid, vec);
     }
 }
 
 // ----------------------------------------------------------------------------- simple pointwise
 __global__ void add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
-                           float* __restrict__ y, int ldy, long long pixels, int c) {
-    const long long total = pixels * c;
+                           float* __restrict__ y, int ldy, long long pixels, int c, int vec) {
+    const int cg = (c + 3) >> 2;
+    const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        const long long p = i / c;
-        y[p * ldy + ch] = a[p * lda + ch] + b[p * ldb + ch];
+        const int g = (int)(i % cg);
+        const long long p = i / cg;
+        const int valid = min(4, c - 4 * g);
+        const F4 u = ld4(a + p * lda + 4 * g, valid, vec), v = ld4(b + p * ldb + 4 * g, valid, vec);
+        F4 o;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o.v[q] = u.v[q] + v.v[q];
+        st4(y + p * ldy + 4 * g, o, valid, vec);
     }
 }
 
 __global__ void copy_kernel(const float* __restrict__ s, int lds, float* __restrict__ d, int ldd, int accumulate,
-                            long long pixels, int c) {
-    const long long total = pixels * c;
+                            long long pixels, int c, int vec) {
+    const int cg = (c + 3) >> 2;
+    const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        const long long p = i / c;
-        const float v = s[p * lds + ch];
-        float* q = d + p * ldd + ch;
-        *q = accumulate ? *q + v : v;
+        const int g = (int)(i % cg);
+        const long long p = i / cg;
+        const int valid = min(4, c - 4 * g);
+        F4 v = ld4(s + p * lds + 4 * g, valid, vec);
+        float* q4 = d + p * ldd + 4 * g;
+        if (accumulate) {
+            const F4 o = ld4(q4, valid, vec);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v.v[q] += o.v[q];
+        }
+        st4(q4, v, valid, vec);
     }
 }
 
 __global__ void act_bwd_kernel(float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
-                               float slope, long long pixels, int c) {
-    const long long total = pixels * c;
+                               float slope, long long pixels, int c, int vec) {
+    const int cg = (c + 3) >> 2;
+    const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
-        const int ch = (int)(i % c);
-        const long long p = i / c;
-        dy[p * lddy + ch] *= mi_act_grad(y[p * ldy + ch], act, slope);
+        const int g = (int)(i % cg);
+        const long long p = i / cg;
+        const int valid = min(4, c - 4 * g);
+        F4 d = ld4(dy + p * lddy + 4 * g, valid, vec);
+        const F4 v = ld4(y + p * ldy + 4 * g, valid, vec);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d.v[q] *= mi_act_grad(v.v[q], act, slope);
+        st4(dy + p * lddy + 4 * g, d, valid, vec);
     }
 }
 
@@ -425,6 +495,13 @@ __global__ void segment_dot_kernel(const float* __restrict__ a, const float* __r
 
 }  // namespace
 
+// float4 groups are legal when the row is 16-byte aligned and the 4-padded channel count fits in the row
+// (a ragged channel count may only use its pad lane when the row is exactly the padded width, i.e. the view is
+// not a channel slice of a wider concat buffer whose next slice starts in that lane)
+static inline bool mi_vec_ok(const void* p, int ld, int c) {
+    return mi_al16(p) && (ld % 4 == 0) && ((c % 4 == 0 && c <= ld) || ld == ((c + 3) & ~3));
+}
+
 #define LAUNCH(kernel, work, stream, ...)                                      \
     do {                                                                       \
         kernel<<<grid_for(work), TPB, 0, mi_cs(stream)>>>(__VA_ARGS__);        \
@@ -436,12 +513,14 @@ extern "C" {
 
 int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t s) {
     if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
-    LAUNCH(avgpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * c, s, x, ldx, y, ldy, n, h, wd, c);
+    const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
+    LAUNCH(avgpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, vec);
 }
 int mi_avgpool2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                     mi_stream_t s) {
     if (!dy || !dx || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
-    LAUNCH(avgpool2_bwd_kernel, (long long)n * h * wd * c, s, dy, lddy, dx, lddx, accumulate, n, h, wd, c);
+    const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
+    LAUNCH(avgpool2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, vec);
 }
 int mi_maxpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t s) {
     if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
@@ -456,26 +535,32 @@ int mi_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* d
 int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align,
                      mi_stream_t s) {
     if (!x || !y) return MI_ERR_BAD_ARG;
-    LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * c, s, x, ldx, y, ldy, n, h, wd, c, align);
+    const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
+    LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec);
 }
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                      int align, mi_stream_t s) {
     if (!dy || !dx) return MI_ERR_BAD_ARG;
-    LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * c, s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align);
+    const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
+    LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
+           vec);
 }
 int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t s) {
     if (!a || !b || !y) return MI_ERR_BAD_ARG;
-    LAUNCH(add_kernel, (long long)pixels * c, s, a, lda, b, ldb, y, ldy, (long long)pixels, c);
+    const int vec = mi_vec_ok(a, lda, c) && mi_vec_ok(b, ldb, c) && mi_vec_ok(y, ldy, c);
+    LAUNCH(add_kernel, (long long)pixels * ((c + 3) / 4), s, a, lda, b, ldb, y, ldy, (long long)pixels, c, vec);
 }
 int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size_t pixels, int c, mi_stream_t s) {
     if (!src || !dst) return MI_ERR_BAD_ARG;
-    LAUNCH(copy_kernel, (long long)pixels * c, s, src, lds, dst, ldd, accumulate, (long long)pixels, c);
+    const int vec = mi_vec_ok(src, lds, c) && mi_vec_ok(dst, ldd, c);
+    LAUNCH(copy_kernel, (long long)pixels * ((c + 3) / 4), s, src, lds, dst, ldd, accumulate, (long long)pixels, c, vec);
 }
 int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c,
                mi_stream_t s) {
     if (!dy || !y) return MI_ERR_BAD_ARG;
     if (act == MI_ACT_NONE) return MI_OK;
-    LAUNCH(act_bwd_kernel, (long long)pixels * c, s, dy, lddy, y, ldy, act, slope, (long long)pixels, c);
+    const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(y, ldy, c);
+    LAUNCH(act_bwd_kernel, (long long)pixels * ((c + 3) / 4), s, dy, lddy, y, ldy, act, slope, (long long)pixels, c, vec);
 }
 int mi_fill(float* p, float v, size_t count, mi_stream_t s) {
     if (!p) return MI_ERR_BAD_ARG;

@@ -151,6 +151,20 @@ class FastPath:
         self.dots = torch.zeros(len(self.net.param_names), device=dev)
         self.loss_terms = [(LOSS_KIND[t.split('*')[1]], float(t.split('*')[0])) for t in a.loss.split('+')]
         self.programs = {}
+        self.meta_wt = {}
+
+    def refresh_meta_wt(self):
+        """dgrad needs the rotated/transposed filter; for meta-parameters (un-routed tensors in support passes,
+        everything at step 0 and in K=0 query passes) it only changes with the outer step, so it is rebuilt once
+        per meta-batch into persistent buffers instead of once per pass."""
+        for name in self.net.conv_names:
+            w = self.net.arena.kernel_view(name + ".weight")
+            buf = self.meta_wt.get(name)
+            if buf is None:
+                cout, k, _, cin = w.shape
+                buf = self.ops.empty_weight(cin, cout, k)
+                self.meta_wt[name] = buf
+            self.ops.weight_to_dgrad(w, out=buf)
 
     # ------------------------------------------------------------------ graph bodies
     def _provider(self, src):
@@ -166,6 +180,7 @@ class FastPath:
                     p = ConvParam(name, w, b)
                 else:
                     p = net.meta_param(name)
+                    p._wt = self.meta_wt.get(name)   # rotated copy refreshed once per meta-batch
                 cache[name] = p
             return p
 
@@ -327,6 +342,7 @@ class FastPath:
         sysm.optimizer.zero_grad()
         for g in sysm._groups:
             g.dirty = True
+        self.refresh_meta_wt()
         losses_dev, preds = [], []
         for t in task_ids:
             l, p = self.adapt_and_query(frames, t, self.K, epoch, True, scale, msl, msl_w)
@@ -340,6 +356,7 @@ class FastPath:
         msl_w = sysm.get_per_step_loss_importance_vector()
         task_ids = list(range(len(frames[0])))
         losses_dev, preds = [], []
+        self.refresh_meta_wt()
         for t in task_ids:
             l, p = self.adapt_and_query(frames, t, a.number_of_evaluation_steps_per_iter, epoch, False, 0.0, False,
                                         msl_w)

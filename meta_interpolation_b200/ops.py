@@ -141,9 +141,9 @@ class CudaOps:
                    "mi_conv2d_fprop")
         return y
 
-    def weight_to_dgrad(self, w):
+    def weight_to_dgrad(self, w, out=None):
         cout, k, _, cin = w.shape
-        wt = self.empty_weight(cin, cout, k)
+        wt = out if out is not None else self.empty_weight(cin, cout, k)
         _lib.check(self.lib.mi_weight_to_dgrad(w.data_ptr(), _ldw(w), wt.data_ptr(), _ldw(wt), cin, cout, k,
                                                self._stream()), "mi_weight_to_dgrad")
         return wt

@@ -96,9 +96,9 @@ class RefOps:
         out.copy_(y)
         return out
 
-    def weight_to_dgrad(self, w):
+    def weight_to_dgrad(self, w, out=None):
         cout, k, _, cin = w.shape
-        wt = self.empty_weight(cin, cout, k)
+        wt = out if out is not None else self.empty_weight(cin, cout, k)
         wt.copy_(torch.flip(w, dims=(1, 2)).permute(3, 1, 2, 0))
         return wt
 

@@ -20,6 +20,8 @@ TC_SHAPES = [
     (1, 48, 64, 64, 64, 3), (1, 8, 8, 192, 16, 1),
     # persistent halo kernel: ragged tiles, and more tiles than SMs (TMEM double buffering, stage wrap-around)
     (1, 17, 13, 40, 64, 3), (2, 200, 208, 64, 64, 3), (1, 130, 300, 32, 32, 3),
+    # stem: 6 input channels (32-channel TMA box over a 6-channel tensor, zero-filled tail)
+    (1, 8, 8, 6, 32, 3), (2, 40, 48, 6, 32, 3),
 ]
 
 
