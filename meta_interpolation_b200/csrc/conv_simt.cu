@@ -295,9 +295,9 @@ int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
 }
 
 int mi_bias_splits(long long m_total) {
-    long long s = m_total / 1024;
+    long long s = m_total / 512;
     if (s < 1) s = 1;
-    if (s > 64) s = 64;
+    if (s > 256) s = 256;
     return (int)s;
 }
 
@@ -381,7 +381,7 @@ size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k,
     (void)engine;
     const int ldw = (cin + 3) & ~3;
     const size_t splits = (size_t)mi_wgrad_splits(n, h, wd, cin, cout, k);
-    const size_t bsplits = splits > 64 ? splits : 64;
+    const size_t bsplits = splits > 256 ? splits : 256;
     return (splits * (size_t)cout * k * k * ldw + bsplits * (size_t)cout) * sizeof(float) + 256;
 }
 
@@ -397,7 +397,7 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
     if ((mode == MI_WG_SGD_SCALAR || mode == MI_WG_SGD_TENSOR) && (!w_in || !w_out || !lr_w)) return MI_ERR_BAD_ARG;
     const int splits = mi_wgrad_splits(n, h, wd, cin, cout, k);
     const size_t wsz = (size_t)cout * k * k * ldw;
-    const size_t need = ((size_t)splits * wsz + (size_t)(splits > 64 ? splits : 64) * cout) * sizeof(float);
+    const size_t need = ((size_t)splits * wsz + (size_t)(splits > 256 ? splits : 256) * cout) * sizeof(float);
     if (workspace_bytes < need) return MI_ERR_WORKSPACE;
     float* ws_w = reinterpret_cast<float*>(workspace);
     float* ws_b = ws_w + (size_t)splits * wsz;

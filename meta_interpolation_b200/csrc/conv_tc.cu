@@ -626,34 +626,58 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.bn);
 }
 
-// column sums of dy for the bias gradient: grid (pixel slices, 32-channel groups), 32x8 threads; every block
-// streams its slice with 8 pixel lanes in flight per channel and writes one partial per (slice, channel)
-__global__ void bias_partial_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ ws_b, int cout,
-                                    long long m_total, long long chunk) {
+// column sums of dy for the bias gradient.  grid = (pixel slices, 32-channel groups); a block is 8 float4 channel
+// lanes x 32 pixel lanes with 4 independent loads in flight per thread (16 KB per block), so a few hundred blocks
+// keep enough bytes in flight to stream dy near HBM rate; one deterministic partial per (slice, channel).
+__global__ void __launch_bounds__(256)
+bias_partial_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ ws_b, int cout, long long m_total,
+                    long long chunk, int vec) {
     const int split = blockIdx.x;
     const long long m0 = (long long)split * chunk;
     long long m1 = m0 + chunk;
     if (m1 > m_total) m1 = m_total;
-    __shared__ float red[8][33];
-    const int c = blockIdx.y * 32 + threadIdx.x;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    __shared__ float red[32][33];
+    const int lane_c = threadIdx.x & 7, lane_p = threadIdx.x >> 3;
+    const int c = blockIdx.y * 32 + lane_c * 4;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < cout) {
-        long long m = m0 + threadIdx.y;
-        for (; m + 24 < m1; m += 32) {
-            acc0 += dy[m * lddy + c];
-            acc1 += dy[(m + 8) * lddy + c];
-            acc2 += dy[(m + 16) * lddy + c];
-            acc3 += dy[(m + 24) * lddy + c];
-        }
-        for (; m < m1; m += 8) acc0 += dy[m * lddy + c];
-    }
-    red[threadIdx.y][threadIdx.x] = (acc0 + acc1) + (acc2 + acc3);
-    __syncthreads();
-    if (threadIdx.y == 0 && c < cout) {
-        float s = 0.f;
+        if (vec) {
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            long long m = m0 + lane_p;
+            for (; m + 96 < m1; m += 128) {
+                const float4 v0 = *reinterpret_cast<const float4*>(dy + m * lddy + c);
+                const float4 v1 = *reinterpret_cast<const float4*>(dy + (m + 32) * lddy + c);
+                const float4 v2 = *reinterpret_cast<const float4*>(dy + (m + 64) * lddy + c);
+                const float4 v3 = *reinterpret_cast<const float4*>(dy + (m + 96) * lddy + c);
+                s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+                s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+                s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
+                s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
+            }
+            for (; m < m1; m += 32) {
+                const float4 v0 = *reinterpret_cast<const float4*>(dy + m * lddy + c);
+                s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+            }
+            a[0] = (s0.x + s1.x) + (s2.x + s3.x); a[1] = (s0.y + s1.y) + (s2.y + s3.y);
+            a[2] = (s0.z + s1.z) + (s2.z + s3.z); a[3] = (s0.w + s1.w) + (s2.w + s3.w);
+        } else {
+            for (long long m = m0 + lane_p; m < m1; m += 32)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += red[j][threadIdx.x];
-        ws_b[(long long)split * cout + c] = s;
+                for (int q = 0; q < 4; ++q)
+                    if (c + q < cout) a[q] += dy[m * lddy + c + q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) red[lane_p][lane_c * 4 + q] = a[q];
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int cc = blockIdx.y * 32 + threadIdx.x;
+        if (cc < cout) {
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += red[j][threadIdx.x];
+            ws_b[(long long)split * cout + cc] = s;
+        }
     }
 }
 
@@ -828,6 +852,9 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
     p.tiles_x = mi_cdiv(wd, p.tw);
     p.tiles_y = mi_cdiv(h, p.th);
     p.bn = pick_bn(cout);
+    // Each SM fills its shared memory from L2 at a fixed rate (~130 GB/s measured), so a deep layer with few
+    // 128-pixel tiles is bound by how many SMs take part: shrink the channel tile until the grid covers the chip.
+    while (p.bn > 64 && (long long)p.tiles_x * p.tiles_y * n * mi_cdiv(cout, p.bn) < num_sms()) p.bn >>= 1;
     p.act = act; p.slope = slope; p.accumulate = accumulate; p.mask_act = mask_act; p.mask_slope = mask_slope;
     p.ldy = ldy; p.ldmask = ldmask; p.bias = bias; p.mask_y = mask_y; p.y = y;
     const size_t stage_bytes = (size_t)(BM + p.bn) * ROW_BYTES;
@@ -906,8 +933,9 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
     const long long m_total = (long long)n * h * wd;
     const int bsplits = mi_bias_splits(m_total);
     const long long chunk = (m_total + bsplits - 1) / bsplits;
-    bias_partial_kernel<<<dim3(bsplits, mi_cdiv(cout, 32)), dim3(32, 8), 0, stream>>>(dy, lddy, ws_b, cout, m_total,
-                                                                                       chunk);
+    // float4 lanes may read the pad lane of a 4-padded row (never a neighbouring concat slice)
+    const int vec = mi_al16(dy) && (lddy % 4 == 0) && ((cout % 4 == 0) || lddy == ((cout + 3) & ~3));
+    bias_partial_kernel<<<dim3(bsplits, mi_cdiv(cout, 32)), 256, 0, stream>>>(dy, lddy, ws_b, cout, m_total, chunk, vec);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }

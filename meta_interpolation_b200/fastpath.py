@@ -8,7 +8,7 @@ For one task (reference meta_learning_system.py:366-461) it runs
             fast-weight arena; no elementwise launch between inner steps) ]
     (+ per-step query passes when the MAML++ multi-step loss is active)
     1 x [ query pass: forward, loss, backward; outer gradients accumulated with scale
-            1/B into the flat meta-gradient buffer ]
+            1/B into a flat meta-gradient buffer ]
 
 Each bracket is one CUDA graph, captured the second time it is needed and replayed
 afterwards; frames are copied into static input buffers before a replay.  Fast
@@ -16,6 +16,13 @@ weights live in ONE arena updated in place after step 0 (step 0 reads the
 meta-parameters and writes the arena), so three support graphs/two query graphs cover
 any K.  Un-routed tensors read the meta arena and skip
 their dead inner-loop weight gradients; the query pass differentiates everything.
+
+Task-level concurrency (decision 3): the deep layers of a single task
+launch only 24-96 CTAs on 148 SMs, and fast weights differ per task so tasks cannot be
+batched into N.  Tasks are therefore dealt round-robin to ``task_streams`` LANES; a lane
+owns a CUDA stream, its fast-weight arena, its graphs, its split-K workspace and its own
+meta-gradient accumulators, so two tasks' graphs run concurrently with no shared mutable
+state; the lanes' accumulators are summed once per meta-batch.
 
 First-order outer gradients follow SURVEY Appendix E4:
   LSLR fixed lr      dL/dtheta = G
@@ -36,11 +43,12 @@ LOSS_KIND = {'L1': 0, 'MSE': 1}
 class _Sink:
     """Weight-gradient policy handed to the tape."""
 
-    def __init__(self, fp, mode, step=0, scale=1.0, src=None):
-        self.fp, self.mode, self.step, self.scale, self.src = fp, mode, step, scale, src
+    def __init__(self, lane, mode, step=0, scale=1.0):
+        self.lane, self.mode, self.step, self.scale = lane, mode, step, scale
 
     def weight_grad(self, p, x, dy, k):
-        fp = self.fp
+        lane = self.lane
+        fp = lane.fp
         net = fp.net
         wn, bn = p.name + ".weight", p.name + ".bias"
         has_b = p.b is not None
@@ -48,34 +56,34 @@ class _Sink:
         if self.mode == 'inner':
             if not net.is_routed(wn):
                 return                       # dead work in support passes (Q1/Q2/Q2b)
-            fast = fp.fast
+            fast = lane.fast
             spec = WgradSpec(w_in=p.w, b_in=p.b, w_out=fast.kernel_view(wn),
                              b_out=fast.kernel_view(bn) if has_b else None)
             if fp.metasgd:
                 spec.mode = WG_SGD_TENSOR
                 spec.lr_w = fp.sys.alpha.kernel_view(wn)
                 spec.lr_b = fp.sys.alpha.kernel_view(bn) if has_b else None
-                spec.gsum_w = fp.gsum.kernel_view(wn)
-                spec.gsum_b = fp.gsum.kernel_view(bn) if has_b else None
+                spec.gsum_w = lane.gsum.kernel_view(wn)
+                spec.gsum_b = lane.gsum.kernel_view(bn) if has_b else None
             else:
                 spec.mode = WG_SGD_SCALAR
                 iw = net.layout.index(wn)
-                spec.lr_w = fp.cur_lr[iw:iw + 1]
+                spec.lr_w = lane.cur_lr[iw:iw + 1]
                 if has_b:
                     ib = net.layout.index(bn)
-                    spec.lr_b = fp.cur_lr[ib:ib + 1]
+                    spec.lr_b = lane.cur_lr[ib:ib + 1]
                 if fp.learnable_lr:
-                    garena = fp.gsteps[self.step]
+                    garena = lane.gsteps[self.step]
                     spec.grad_w = garena.kernel_view(wn)
                     spec.grad_b = garena.kernel_view(bn) if has_b else None
             fp.ops.conv_wgrad(x, dy, k, ldw, spec)
         elif self.mode == 'accum':
-            garena = fp.sys.net_grad
+            garena = lane.acc_theta
             spec = WgradSpec(WG_ACCUM, scale=self.scale, grad_w=garena.kernel_view(wn),
                              grad_b=garena.kernel_view(bn) if has_b else None)
             fp.ops.conv_wgrad(x, dy, k, ldw, spec)
         else:   # 'store': per-task query gradient G (needed for lr / alpha outer gradients)
-            garena = fp.gquery
+            garena = lane.gquery
             spec = WgradSpec(WG_STORE, grad_w=garena.kernel_view(wn), grad_b=garena.kernel_view(bn) if has_b else None)
             fp.ops.conv_wgrad(x, dy, k, ldw, spec)
 
@@ -83,8 +91,8 @@ class _Sink:
 class _Program:
     """One capturable unit: static inputs, a body, static outputs."""
 
-    def __init__(self, fp, body, n, h, w):
-        dev = fp.ops.device
+    def __init__(self, lane, body, n, h, w):
+        dev = lane.fp.ops.device
         self.f0 = torch.zeros(n, 3, h, w, device=dev)
         self.f1 = torch.zeros(n, 3, h, w, device=dev)
         self.tgt = torch.zeros(n, 3, h, w, device=dev)
@@ -93,10 +101,12 @@ class _Program:
         self.body = body
         self.graph = None
         self.calls = 0
-        self.fp = fp
+        self.kernels = 0
+        self.lane = lane
 
     def run(self):
-        fp = self.fp
+        fp = self.lane.fp
+        ops = fp.ops
         self.calls += 1
         if not fp.use_graphs or self.calls == 1:
             self.body(self)                      # eager (also sizes workspaces before a capture)
@@ -104,14 +114,65 @@ class _Program:
         if self.graph is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            n0 = int(fp.ops.lib.mi_launch_count())
-            with torch.cuda.graph(g):
+            n0 = int(ops.lib.mi_launch_count())
+            with torch.cuda.graph(g, stream=self.lane.capture_stream):
                 self.body(self)
-            self.kernels = int(fp.ops.lib.mi_launch_count()) - n0   # recorded, not executed, during capture
-            fp.ops.replayed_launches -= self.kernels
+            self.kernels = int(ops.lib.mi_launch_count()) - n0   # recorded, not executed, during capture
+            ops.replayed_launches -= self.kernels
             self.graph = g
         self.graph.replay()
-        fp.ops.replayed_launches += self.kernels
+        ops.replayed_launches += self.kernels
+
+
+class _Lane:
+    """Everything one in-flight task mutates: stream, fast weights, graphs, workspace slot, accumulators."""
+
+    def __init__(self, fp, index):
+        self.fp = fp
+        self.index = index
+        ops, net, sysm = fp.ops, fp.net, fp.sys
+        dev = ops.device
+        lay = net.layout
+        cuda = ops.name == 'cuda'
+        self.stream = torch.cuda.Stream(device=dev) if (cuda and fp.n_lanes > 1) else None
+        self.capture_stream = torch.cuda.Stream(device=dev) if cuda else None
+        self.fast = Arena(lay, dev)
+        self.cur_lr = torch.zeros(len(net.param_names), device=dev)
+        self.gsum = Arena(lay, dev) if fp.metasgd else None
+        self.gquery = Arena(lay, dev) if (fp.metasgd or fp.learnable_lr) else None
+        self.gsteps = []
+        self.dots = torch.zeros(len(net.param_names), device=dev)
+        self.programs = {}
+        # lane 0 accumulates straight into the optimizer's flat gradient buffers; the others into private
+        # buffers that are added once per meta-batch
+        if index == 0:
+            self.acc_theta = sysm.net_grad
+            self.acc_alpha = sysm.alpha_grad if fp.metasgd else None
+            self.acc_lr = sysm.lr_table_grad if fp.learnable_lr else None
+        else:
+            self.acc_theta = Arena(lay, dev)
+            self.acc_alpha = Arena(lay, dev) if fp.metasgd else None
+            self.acc_lr = torch.zeros_like(sysm.lr_table_grad) if fp.learnable_lr else None
+
+    def zero_accumulators(self):
+        if self.index == 0:
+            return
+        ops = self.fp.ops
+        ops.fill(self.acc_theta.flat, 0.0)
+        if self.acc_alpha is not None:
+            ops.fill(self.acc_alpha.flat, 0.0)
+        if self.acc_lr is not None:
+            self.acc_lr.zero_()
+
+    def reduce_into_system(self):
+        if self.index == 0:
+            return
+        ops, sysm = self.fp.ops, self.fp.sys
+        ops.axpby(self.acc_theta.flat, 1.0, sysm.net_grad.flat, 1.0)
+        if self.acc_alpha is not None:
+            ops.axpby(self.acc_alpha.flat, 1.0, sysm.alpha_grad.flat, 1.0)
+        if self.acc_lr is not None:
+            sysm.lr_table_grad.add_(self.acc_lr)
 
 
 class FastPath:
@@ -139,19 +200,13 @@ class FastPath:
         self.use_graphs = bool(system.use_cuda_graphs) and self.ops.name == 'cuda'
         dev = self.ops.device
         lay = self.net.layout
-        self.fast = Arena(lay, dev)
         self.seg = lay.segment_table().to(dev)
-        self.routed = [n for n in self.net.param_names if self.net.is_routed(n)]
         self.routed_mask = torch.tensor([1.0 if self.net.is_routed(n) else 0.0 for n in self.net.param_names],
                                         device=dev)
-        self.cur_lr = torch.zeros(len(self.net.param_names), device=dev)
-        self.gsum = Arena(lay, dev) if self.metasgd else None
-        self.gquery = Arena(lay, dev) if (self.metasgd or self.learnable_lr) else None
-        self.gsteps = []
-        self.dots = torch.zeros(len(self.net.param_names), device=dev)
         self.loss_terms = [(LOSS_KIND[t.split('*')[1]], float(t.split('*')[0])) for t in a.loss.split('+')]
-        self.programs = {}
         self.meta_wt = {}
+        self.n_lanes = max(1, int(getattr(a, 'task_streams', 2))) if self.ops.name == 'cuda' else 1
+        self.lanes = [_Lane(self, i) for i in range(self.n_lanes)]
 
     def refresh_meta_wt(self):
         """dgrad needs the rotated/transposed filter; for meta-parameters (un-routed tensors in support passes,
@@ -167,8 +222,8 @@ class FastPath:
             self.ops.weight_to_dgrad(w, out=buf)
 
     # ------------------------------------------------------------------ graph bodies
-    def _provider(self, src):
-        net, fast = self.net, self.fast
+    def _provider(self, lane, src):
+        net, fast = self.net, lane.fast
         cache = {}
 
         def provider(name):
@@ -200,21 +255,23 @@ class FastPath:
                 self.ops.axpby(g2, 1.0, grad, 1.0)
         return grad
 
-    def _support_body(self, src, step_slot):
+    def _support_body(self, lane, src, step_slot):
         def body(prog):
-            sink = _Sink(self, 'inner', step=step_slot)
-            tape = Tape(self.ops, self._provider(src), sink)
+            self.ops.set_workspace_slot(lane.index)
+            sink = _Sink(lane, 'inner', step=step_slot)
+            tape = Tape(self.ops, self._provider(lane, src), sink)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             out.grad = self._loss(prog, out.data, prog.f0.shape[0])
             tape.backward()
         return body
 
-    def _query_body(self, src, mode, backward=True):
+    def _query_body(self, lane, src, mode, backward=True):
         def body(prog):
-            sink = _Sink(self, mode, scale=1.0) if backward else None
+            self.ops.set_workspace_slot(lane.index)
+            sink = _Sink(lane, mode, scale=1.0) if backward else None
             if mode == 'accum' and backward:
                 sink.scale = prog.scale
-            tape = Tape(self.ops, self._provider(src), sink)
+            tape = Tape(self.ops, self._provider(lane, src), sink)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             prog.pred = out.data
             g = self._loss(prog, out.data, 1)
@@ -223,38 +280,33 @@ class FastPath:
                 tape.backward()
         return body
 
-    def _program(self, key, body, n, h, w):
-        p = self.programs.get(key)
+    def _program(self, lane, key, body, n, h, w):
+        p = lane.programs.get(key)
         if p is None:
-            p = _Program(self, body, n, h, w)
-            self.programs[key] = p
+            p = _Program(lane, body, n, h, w)
+            lane.programs[key] = p
         return p
 
     # ------------------------------------------------------------------ one task
-    def _set_lr(self, step):
-        if not self.metasgd:
-            self.cur_lr.copy_(self.sys.lr_table[:, step])
-
-    def _support_step(self, frames, task, step, h, w, support_idxs):
+    def _support_step(self, lane, frames, task, step, h, w, support_idxs):
         src = 'meta' if step == 0 else 'fast'
         slot = step if self.learnable_lr else 0
-        prog = self._program(('support', src, slot, h, w), self._support_body(src, slot), len(support_idxs), h, w)
+        prog = self._program(lane, ('support', src, slot, h, w), self._support_body(lane, src, slot),
+                             len(support_idxs), h, w)
         for i, (a, b, c) in enumerate(support_idxs):
             prog.f0[i].copy_(frames[a][task])
             prog.f1[i].copy_(frames[c][task])
             prog.tgt[i].copy_(frames[b][task])
-        self._set_lr(step)
-        if step == 0:
-            # un-routed tensors and (for K=0) everything are read from the meta arena; routed tensors are
-            # written by the fused update, nothing to initialise
-            if self.metasgd:
-                self.ops.fill(self.gsum.flat, 0.0)
+        if not self.metasgd:
+            lane.cur_lr.copy_(self.sys.lr_table[:, step])
+        elif step == 0:
+            self.ops.fill(lane.gsum.flat, 0.0)
         prog.run()
 
-    def _query(self, frames, task, src, h, w, mode, scale, backward=True):
+    def _query(self, lane, frames, task, src, h, w, mode, scale, backward=True):
         ti = self.sys.target_idxs
         key = ('query', src, mode, backward, h, w, scale if mode == 'accum' else 0)
-        prog = self._program(key, self._query_body(src, mode, backward), 1, h, w)
+        prog = self._program(lane, key, self._query_body(lane, src, mode, backward), 1, h, w)
         prog.scale = scale
         prog.f0[0].copy_(frames[ti[0]][task])
         prog.f1[0].copy_(frames[ti[2]][task])
@@ -262,54 +314,76 @@ class FastPath:
         prog.run()
         return prog
 
-    def _outer_extras(self, scale, steps_done):
+    def _outer_extras(self, lane, scale, steps_done):
         """alpha / lr outer gradients from the stored per-task query gradient G (Appx E4)."""
-        sysm, ops = self.sys, self.ops
-        G = self.gquery.flat
-        ops.axpby(G, scale, sysm.net_grad.flat, 1.0)                     # dL/dtheta += scale * G
+        ops = self.ops
+        G = lane.gquery.flat
+        ops.axpby(G, scale, lane.acc_theta.flat, 1.0)                     # dL/dtheta += scale * G
         if self.metasgd:
-            ops.addcmul(sysm.alpha_grad.flat, -scale, self.gsum.flat, G)  # dL/dalpha -= scale * gsum (.) G
+            ops.addcmul(lane.acc_alpha.flat, -scale, lane.gsum.flat, G)    # dL/dalpha -= scale * gsum (.) G
         elif self.learnable_lr:
             for j in range(steps_done):
-                ops.fill(self.dots, 0.0)
-                ops.segment_dot(self.gsteps[j].flat, G, self.seg, self.dots)
+                ops.fill(lane.dots, 0.0)
+                ops.segment_dot(lane.gsteps[j].flat, G, self.seg, lane.dots)
                 # only routed tensors are adapted; un-routed rows keep a zero gradient
-                sysm.lr_table_grad[:, j].add_(self.dots * self.routed_mask, alpha=-scale)
+                lane.acc_lr[:, j].add_(lane.dots * self.routed_mask, alpha=-scale)
 
-    def adapt_and_query(self, frames, task, num_steps, epoch, training, scale, msl, msl_w):
-        """Inner loop + query for one task.  Returns (task_loss tensor[1], pred [1,3,H,W])."""
+    def adapt_and_query(self, lane, frames, task, num_steps, epoch, training, scale, msl, msl_w):
+        """Inner loop + query for one task on ``lane``.  Returns (task_loss tensor[1], pred [1,3,H,W])."""
         h, w = frames[0].shape[2], frames[0].shape[3]
         sysm = self.sys
         support_idxs = sysm.support_idxs
         if self.learnable_lr and training:
-            while len(self.gsteps) < num_steps:
-                self.gsteps.append(Arena(self.net.layout, self.ops.device))
+            while len(lane.gsteps) < num_steps:
+                lane.gsteps.append(Arena(self.net.layout, self.ops.device))
         extras = training and (self.metasgd or self.learnable_lr)
         task_loss = torch.zeros(1, device=self.ops.device)
         prog = None
         for step in range(num_steps):
-            self._support_step(frames, task, step, h, w, support_idxs)
+            self._support_step(lane, frames, task, step, h, w, support_idxs)
             if msl:
                 wk = float(msl_w[step])
                 if extras:
-                    prog = self._query(frames, task, 'fast', h, w, 'store', 1.0)
-                    self._outer_extras(scale * wk, step + 1)
+                    prog = self._query(lane, frames, task, 'fast', h, w, 'store', 1.0)
+                    self._outer_extras(lane, scale * wk, step + 1)
                 else:
-                    prog = self._query(frames, task, 'fast', h, w, 'accum', scale * wk)
+                    prog = self._query(lane, frames, task, 'fast', h, w, 'accum', scale * wk)
                 task_loss += wk * prog.loss
         if not msl:
             src = 'fast' if num_steps > 0 else 'meta'
             if not training:
-                prog = self._query(frames, task, src, h, w, 'none', 0.0, backward=False)
+                prog = self._query(lane, frames, task, src, h, w, 'none', 0.0, backward=False)
             elif extras:
-                prog = self._query(frames, task, src, h, w, 'store', 1.0)
-                self._outer_extras(scale, num_steps)
+                prog = self._query(lane, frames, task, src, h, w, 'store', 1.0)
+                self._outer_extras(lane, scale, num_steps)
             else:
-                prog = self._query(frames, task, src, h, w, 'accum', scale)
+                prog = self._query(lane, frames, task, src, h, w, 'accum', scale)
             task_loss += prog.loss
         return task_loss, prog.pred.clone()
 
     # ------------------------------------------------------------------ meta-batch drivers
+    def _run_tasks(self, frames, task_ids, num_steps, epoch, training, scale, msl, msl_w):
+        """Deal the tasks round-robin to the lanes; lanes run concurrently on their own streams."""
+        losses_dev, preds = [None] * len(task_ids), [None] * len(task_ids)
+        multi = self.n_lanes > 1
+        main = torch.cuda.current_stream(self.ops.device) if multi else None
+        if multi:
+            for lane in self.lanes:
+                lane.stream.wait_stream(main)      # inputs, zeroed gradients and rotated weights are ready
+        for i, t in enumerate(task_ids):
+            lane = self.lanes[i % self.n_lanes]
+            if multi:
+                with torch.cuda.stream(lane.stream):
+                    losses_dev[i], preds[i] = self.adapt_and_query(lane, frames, t, num_steps, epoch, training, scale,
+                                                                   msl, msl_w)
+            else:
+                losses_dev[i], preds[i] = self.adapt_and_query(lane, frames, t, num_steps, epoch, training, scale, msl,
+                                                               msl_w)
+        if multi:
+            for lane in self.lanes:
+                main.wait_stream(lane.stream)
+        return losses_dev, preds
+
     def _finish(self, frames, task_ids, losses_dev, preds, do_evaluation, msl_w, loss_name_terms):
         sysm = self.sys
         n_tasks = len(frames[0])
@@ -342,12 +416,12 @@ class FastPath:
         sysm.optimizer.zero_grad()
         for g in sysm._groups:
             g.dirty = True
+        for lane in self.lanes:
+            lane.zero_accumulators()
         self.refresh_meta_wt()
-        losses_dev, preds = [], []
-        for t in task_ids:
-            l, p = self.adapt_and_query(frames, t, self.K, epoch, True, scale, msl, msl_w)
-            losses_dev.append(l)
-            preds.append(p)
+        losses_dev, preds = self._run_tasks(frames, task_ids, self.K, epoch, True, scale, msl, msl_w)
+        for lane in self.lanes:
+            lane.reduce_into_system()
         names = [t.split('*')[1] for t in a.loss.split('+')]
         return self._finish(frames, task_ids, losses_dev, preds, do_evaluation, msl_w, names)
 
@@ -355,12 +429,8 @@ class FastPath:
         sysm, a = self.sys, self.sys.args
         msl_w = sysm.get_per_step_loss_importance_vector()
         task_ids = list(range(len(frames[0])))
-        losses_dev, preds = [], []
         self.refresh_meta_wt()
-        for t in task_ids:
-            l, p = self.adapt_and_query(frames, t, a.number_of_evaluation_steps_per_iter, epoch, False, 0.0, False,
-                                        msl_w)
-            losses_dev.append(l)
-            preds.append(p)
+        losses_dev, preds = self._run_tasks(frames, task_ids, a.number_of_evaluation_steps_per_iter, epoch, False, 0.0,
+                                            False, msl_w)
         names = [t.split('*')[1] for t in a.loss.split('+')]
         return self._finish(frames, task_ids, losses_dev, preds, True, msl_w, names)

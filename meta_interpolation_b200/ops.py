@@ -103,10 +103,22 @@ class CudaOps:
         buf = torch.zeros(cout, k, k, ld, device=self.device, dtype=torch.float32)
         return buf[..., :cin] if ld != cin else buf
 
+    def set_workspace_slot(self, slot):
+        """Split-K scratch is per execution lane: two tasks running on two streams must not share it."""
+        self._ws_slot = slot
+
     def workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
-        return self._ws
+        if self._ws is None:
+            self._ws = {}
+        slot = getattr(self, "_ws_slot", 0)
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                # a captured CUDA graph may hold the old address: outgrown buffers are retired, never freed
+                self._ws.setdefault("retired", []).append(ws)
+            ws = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
+            self._ws[slot] = ws
+        return ws
 
     def launch_count(self):
         """libmi_b200 kernels executed so far: eager launches + kernels inside replayed CUDA graphs."""

@@ -69,6 +69,9 @@ class RefOps:
     def launch_count(self):
         return self._launches
 
+    def set_workspace_slot(self, slot):
+        pass
+
     # ------------------------------------------------------------------ allocation (same layouts as CudaOps)
     def empty_act(self, n, h, w, c, zero_pad=False):
         ld = pad4(c)
