@@ -12,6 +12,7 @@
 // (one lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> bias/activation/mask -> global).
 // Replaces cuDNN's F.conv2d kernels used by the reference (model_utils.py:360).
 #include <cuda.h>
+#include <cstdio>
 #include <cstdlib>
 
 #include "mi_common.cuh"
@@ -66,6 +67,20 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// One lane of a fully converged warp.  Issuing tcgen05/TMA under `if (lane == 0)` makes the compiler treat the
+// region as divergent and wrap every uniform-datapath instruction in an ELECT/BRA.U.ANY loop (seen in SASS, ~2x
+// the issue cost per MMA); with elect.sync on warp-uniform control flow it emits straight-line code.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -219,6 +234,86 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
     }
 }
 
+// Warp-cooperative variant used whenever rows are 16-byte aligned.  After tcgen05.ld each lane holds 32 channels
+// of ITS pixel, so a per-lane store touches 32 different 128-byte lines per instruction (ncu: the epilogue warps
+// sat in the LSU queue for ~70% of a tile's period).  Here the 32x32 block is bounced through a padded per-warp
+// shared-memory tile and read back transposed: 8 consecutive lanes then cover the 128 contiguous bytes of one
+// pixel, i.e. 4 full lines per STG.128 instead of 32 partial ones; mask / accumulate operands are loaded with the
+// same coalesced pattern.
+struct RowMap {
+    int tw, y0, x0, h, w, img, q;   // tile width in pixels, tile origin, image size, image index, warp quarter
+    __device__ __forceinline__ bool pixel(int row, long long& pix) const {
+        const int r = q * 32 + row;
+        const int th_i = r / tw, tw_i = r - th_i * tw;
+        const int oy = y0 + th_i, ox = x0 + tw_i;
+        pix = ((long long)img * h + oy) * w + ox;
+        return oy < h && ox < w;
+    }
+};
+constexpr int EPI_PITCH = 36;   // floats per staged row (32 + 4): conflict-free for both access patterns
+
+__device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t (&v)[32], const float* __restrict__ sbias,
+                                                         int co, const EpiArgs& e, float* stage, int lane,
+                                                         const RowMap& rm, const float* __restrict__ mask_y, int ldmask,
+                                                         float* __restrict__ y, int ldy) {
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) + sbias[j];
+    if (e.act == MI_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if (e.act == MI_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * e.slope;
+    } else if (e.act != MI_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = mi_act_apply(o[j], e.act, e.slope);
+    }
+    float* mine = stage + lane * EPI_PITCH;
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(mine + 4 * g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    __syncwarp();
+    const int c4 = (lane & 7) * 4;          // channel offset of this lane's float4 inside the chunk
+    const int c = co + c4;
+    const bool full = c + 4 <= e.cout_store;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3);
+        long long pix;
+        const bool ok = rm.pixel(row, pix);
+        if (!ok || c >= e.cout) continue;
+        float4 r = *reinterpret_cast<const float4*>(stage + row * EPI_PITCH + c4);
+        float* dst = y + pix * ldy + c;
+        if (full) {
+            if (mask_y) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mask_y + pix * ldmask + c));
+                r.x *= mi_act_grad(m.x, e.mask_act, e.mask_slope);
+                r.y *= mi_act_grad(m.y, e.mask_act, e.mask_slope);
+                r.z *= mi_act_grad(m.z, e.mask_act, e.mask_slope);
+                r.w *= mi_act_grad(m.w, e.mask_act, e.mask_slope);
+            }
+            if (e.accumulate) {
+                const float4 a = *reinterpret_cast<const float4*>(dst);
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+            }
+            *reinterpret_cast<float4*>(dst) = r;
+        } else {
+            const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c + q < e.cout) {
+                    float val = rv[q];
+                    if (mask_y) val *= mi_act_grad(__ldg(mask_y + pix * ldmask + c + q), e.mask_act, e.mask_slope);
+                    if (e.accumulate) val += dst[q];
+                    dst[q] = val;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 struct FpropParams {
     int n, h, w, cin, cout, k, tw, th, tiles_x, tiles_y, bn, stages, act, accumulate, mask_act, ldy, ldmask;
     float slope, mask_slope;
@@ -250,8 +345,10 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const int pad = p.k >> 1;
     const int chunks = (p.cin + KCH - 1) / KCH;
     const int iters = p.k * p.k * chunks;
+    const int last_ksteps = (p.cin - (chunks - 1) * KCH + 7) / 8;
 
     __shared__ float sbias[256];
+    // (the epilogue staging tile aliases pipeline stage 0: every MMA has retired before the epilogue starts)
     for (int i = threadIdx.x; i < p.bn; i += NTHREADS) {
         const int c = co0 + i;
         sbias[i] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
@@ -270,6 +367,9 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Non-persistent kernel with 2-3 co-resident CTAs per SM: only ONE lane of the producer / MMA warps spins on the
+    // pipeline barriers (the other 31 park at the final __syncthreads); polling with the whole warp was measured
+    // 15-40% slower on the deep layers because the pollers steal issue slots from the other CTAs' epilogues.
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < iters; ++it) {
@@ -296,10 +396,18 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
                 const uint64_t ad0 = smem_desc(a_addr, 16, 1024), bd0 = smem_desc(b_addr, 16, 1024);
+                const bool last_chunk = (it % chunks) == chunks - 1;
+                if (!last_chunk || last_ksteps == 4) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_tf32(tmem_base, desc_advance(ad0, kk * 32), desc_advance(bd0, kk * 32), idesc,
-                              (it > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_tf32(tmem_base, desc_advance(ad0, kk * 32), desc_advance(bd0, kk * 32), idesc,
+                                  (it > 0 || kk > 0) ? 1u : 0u);
+                } else {
+                    // the last channel chunk holds fewer than 32 real channels: its all-zero K=8 steps are skipped
+                    for (int kk = 0; kk < last_ksteps; ++kk)
+                        umma_tf32(tmem_base, desc_advance(ad0, kk * 32), desc_advance(bd0, kk * 32), idesc,
+                                  (it > 0 || kk > 0) ? 1u : 0u);
+                }
                 umma_commit(smem_u32(&bars[p.stages + s]));   // frees this smem stage when the MMAs retire
             }
             umma_commit(smem_u32(&bars[2 * p.stages]));       // accumulator complete
@@ -324,11 +432,15 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         // the pad lane may be written only when the row is exactly the 4-padded width (not a concat slice)
         const int c4 = (p.cout + 3) & ~3;
         ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
+        RowMap rm;
+        rm.tw = p.tw; rm.y0 = y0; rm.x0 = x0; rm.h = p.h; rm.w = p.w; rm.img = img; rm.q = q;
+        float* stage = reinterpret_cast<float*>(smem) + q * 32 * EPI_PITCH;
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
             if (co0 + c0 >= p.cout) break;             // warp-uniform
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (pix_ok) epilogue_chunk(v, sbias + c0, co0 + c0, ea, mrow, yrow, vec);
+            if (vec) epilogue_chunk_coalesced(v, sbias + c0, co0 + c0, ea, stage, lane, rm, p.mask_y, p.ldmask, p.y, p.ldy);
+            else if (pix_ok) epilogue_chunk(v, sbias + c0, co0 + c0, ea, mrow, yrow, vec);
         }
     }
     tc_fence_before();
@@ -346,12 +458,16 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 //     start address ((ky*16 + kx) rows of 128 B; the row pitch of 16 pixels keeps every 8-row core group at the
 //     same swizzle phase kx, carried in the descriptor's base-offset field);
 //   * double-buffers the accumulator in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-constexpr int HALO_W = 16, HALO_H = 18, HT_W = 8, HT_H = 16;
-constexpr uint32_t HALO_BYTES = HALO_W * HALO_H * ROW_BYTES;   // 36864
+// The halo row pitch is 10 pixels (8 + 2): because the swizzle follows absolute shared-memory address bits, the
+// 8-row core groups may sit at any 16-byte-aligned offset, so the stride between them (SBO) is simply the pitch
+// (1280 B) and no padding rows are staged.  MI_B200_HALO_PITCH=16 restores the padded 16-pixel pitch (SBO 2048).
+constexpr int HALO_H = 18, HT_W = 8, HT_H = 16;
 
 struct HaloParams {
     int n, h, w, cin, cout, chunks, bn, stages, tiles_x, tiles_y, total_tiles, act, accumulate, mask_act, ldy, ldmask,
-        base_offset_mode;
+        base_offset_mode, halo_w;
+    uint32_t halo_bytes, halo_stride;   // bytes one TMA box delivers / 1024-aligned distance between stages
+    unsigned long long* dbg;            // optional per-role cycle counters of CTA 0 (MI_B200_DEBUG_TIMING=1)
     float slope, mask_slope;
     const float* bias;
     const float* mask_y;
@@ -366,13 +482,14 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const uint32_t b_tile = (uint32_t)p.bn * ROW_BYTES;            // one (tap, chunk) weight tile
     const uint32_t b_total = 9u * p.chunks * b_tile;
     uint8_t* smem_a = smem + b_total;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * HALO_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * p.halo_stride);
     // bars: [0,S) full, [S,2S) empty, 2S = weights loaded, 2S+1..2 = tmem full[2], 2S+3..4 = tmem empty[2]
     const int S = p.stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     __shared__ float sbias[64];
+    __shared__ __align__(16) float epi_stage[4 * 32 * EPI_PITCH];
     if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -394,74 +511,111 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t wbar = smem_u32(&bars[2 * S]);
             mbar_expect_tx(wbar, b_total);
             for (int tap = 0; tap < 9; ++tap)
                 for (int ch = 0; ch < p.chunks; ++ch)
                     tma_load_3d(smem_u32(smem) + (uint32_t)(tap * p.chunks + ch) * b_tile, &map_w, wbar, ch * KCH, tap, 0);
-            int it = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                int tile = (int)blockIdx.x + t * (int)gridDim.x;
-                const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
-                const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
-                const int img = tile;
-                for (int ch = 0; ch < p.chunks; ++ch, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (uint32_t)(it / S) & 1u;
-                    mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
+        }
+        __syncwarp();
+        int it = 0;
+        long long t_empty = 0;
+        const long long t_begin = clock64();
+        for (int t = 0; t < my_tiles; ++t) {
+            int tile = (int)blockIdx.x + t * (int)gridDim.x;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            const int img = tile;
+            for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                const long long c0 = clock64();
+                mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);
+                t_empty += clock64() - c0;
+                if (elect_one()) {
                     const uint32_t full = smem_u32(&bars[s]);
-                    mbar_expect_tx(full, HALO_BYTES);
-                    tma_load_4d(smem_u32(smem_a + (size_t)s * HALO_BYTES), &map_x, full, ch * KCH, tx_i * HT_W - 1,
+                    mbar_expect_tx(full, p.halo_bytes);
+                    tma_load_4d(smem_u32(smem_a + (size_t)s * p.halo_stride), &map_x, full, ch * KCH, tx_i * HT_W - 1,
                                 ty_i * HT_H - 1, img);
                 }
+                __syncwarp();
             }
         }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+            p.dbg[0] = (unsigned long long)t_empty; p.dbg[1] = (unsigned long long)(clock64() - t_begin);
+        }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc(BM, p.bn, 0, 0);
-            mbar_wait(smem_u32(&bars[2 * S]), 0);
+        const uint32_t idesc = instr_desc(BM, p.bn, 0, 0);
+        const long long t_begin = clock64();
+        long long t_w = 0, t_full = 0, t_tmem = 0;
+        mbar_wait(smem_u32(&bars[2 * S]), 0);
+        t_w = clock64() - t_begin;
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(smem);
+        const int last_ksteps = (p.cin - (p.chunks - 1) * KCH + 7) / 8;
+        int it = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int buf = t & 1;
+            const uint32_t use = (uint32_t)(t >> 1);
+            long long c0 = clock64();
+            mbar_wait(smem_u32(&bars[2 * S + 3 + buf]), (use & 1u) ^ 1u);   // epilogue drained this buffer
+            t_tmem += clock64() - c0;
             tc_fence_after();
-            const uint32_t b_base = smem_u32(smem);
-            int it = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const int buf = t & 1;
-                const uint32_t use = (uint32_t)(t >> 1);
-                mbar_wait(smem_u32(&bars[2 * S + 3 + buf]), (use & 1u) ^ 1u);   // epilogue drained this buffer
+            const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+            for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (uint32_t)(it / S) & 1u;
+                c0 = clock64();
+                mbar_wait(smem_u32(&bars[s]), ph);
+                t_full += clock64() - c0;
                 tc_fence_after();
-                const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
-                for (int ch = 0; ch < p.chunks; ++ch, ++it) {
-                    const int s = it % S;
-                    const uint32_t ph = (uint32_t)(it / S) & 1u;
-                    mbar_wait(smem_u32(&bars[s]), ph);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem_a + (size_t)s * HALO_BYTES);
-                    const uint64_t ad0 = smem_desc(a_base, 16, HALO_W * ROW_BYTES);     // 1024-aligned: base offset 0
+                if (elect_one()) {
+                    const uint32_t a_base = smem_u32(smem_a + (size_t)s * p.halo_stride);
+                    const uint64_t ad0 = smem_desc(a_base, 16, (uint32_t)p.halo_w * ROW_BYTES);   // 1024-aligned base
                     const uint64_t bd0 = smem_desc(b_base + (uint32_t)ch * b_tile, 16, 1024);
+                    const uint32_t tap_b = (uint32_t)p.chunks * b_tile;
+                    // Views shifted by (ky halo rows + kx pixels).  Measured on B200 (tools/diag_halo.py): the 128B
+                    // swizzle XOR is taken from the ABSOLUTE smem address bits [7,10), so a row-shifted start keeps
+                    // base offset 0; putting the start row's phase there (as the PTX text suggests) corrupts kx != 0.
+                    if (ch < p.chunks - 1 || last_ksteps == 4) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int ky = tap / 3, kx = tap - ky * 3;
-                        // shift the view by (ky rows of 16 pixels + kx pixels).  Measured on B200 (tools/diag_halo.py):
-                        // the 128B swizzle XOR is taken from the ABSOLUTE smem address bits [7,10), so a
-                        // row-shifted start needs base offset 0; setting it to the start row's phase (kx) as the
-                        // PTX text suggests double-counts the phase and corrupts the kx != 0 taps.
-                        uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * HALO_W + kx) * ROW_BYTES);
-                        if (p.base_offset_mode) a_tap = desc_with_base_offset(a_tap, (uint32_t)kx);
-                        const uint64_t b_tap = desc_advance(bd0, (uint32_t)(tap * p.chunks) * b_tile);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
+                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * tap_b);
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
-                                      (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                          (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    } else {
+                        // ragged last chunk (e.g. 51 = 32 + 19 channels): skip its all-zero K=8 steps
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
+                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * tap_b);
+                            for (int kk = 0; kk < last_ksteps; ++kk)
+                                umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                          (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(smem_u32(&bars[S + s]));
+                    if (ch == p.chunks - 1) umma_commit(smem_u32(&bars[2 * S + 1 + buf]));
                 }
-                umma_commit(smem_u32(&bars[2 * S + 1 + buf]));
+                __syncwarp();
             }
+        }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+            p.dbg[2] = (unsigned long long)t_w; p.dbg[3] = (unsigned long long)t_full;
+            p.dbg[4] = (unsigned long long)t_tmem; p.dbg[5] = (unsigned long long)(clock64() - t_begin);
         }
     } else {
         const int q = warp & 3;
         const int r = q * 32 + lane;
         const int th_i = r >> 3, tw_i = r & 7;
+        long long e_wait = 0, e_ld = 0, e_st = 0;
+        const long long e_begin = clock64();
         const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
         EpiArgs ea;
@@ -482,16 +636,31 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
             const long long pix = ((long long)img * p.h + oy) * p.w + ox;
             float* yrow = p.y + pix * p.ldy;
             const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
+            long long c0 = clock64();
             mbar_wait(smem_u32(&bars[2 * S + 1 + buf]), use & 1u);
+            e_wait += clock64() - c0;
             tc_fence_after();
+            RowMap rm;
+            rm.tw = HT_W; rm.y0 = ty_i * HT_H; rm.x0 = tx_i * HT_W; rm.h = p.h; rm.w = p.w; rm.img = img; rm.q = q;
+            float* stage = epi_stage + q * 32 * EPI_PITCH;
             for (int c0 = 0; c0 < p.bn; c0 += 32) {
                 if (c0 >= p.cout) break;
                 uint32_t v[32];
+                long long c1 = clock64();
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn + c0), v);
-                if (pix_ok) epilogue_chunk(v, sbias + c0, c0, ea, mrow, yrow, vec);
+                e_ld += clock64() - c1;
+                c1 = clock64();
+                if (vec) epilogue_chunk_coalesced(v, sbias + c0, c0, ea, stage, lane, rm, p.mask_y, p.ldmask, p.y, p.ldy);
+                else if (pix_ok) epilogue_chunk(v, sbias + c0, c0, ea, mrow, yrow, vec);
+                e_st += clock64() - c1;
             }
             tc_fence_before();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[2 * S + 3 + buf])) : "memory");
+        }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+            p.dbg[6] = (unsigned long long)e_wait; p.dbg[7] = (unsigned long long)e_ld;
+            p.dbg[8] = (unsigned long long)e_st; p.dbg[9] = (unsigned long long)(clock64() - e_begin);
+            p.dbg[10] = (unsigned long long)my_tiles;
         }
     }
     tc_fence_before();
@@ -782,6 +951,15 @@ int halo_base_offset_mode() {
     return v;
 }
 
+int halo_pitch() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MI_B200_HALO_PITCH");
+        v = (e && atoi(e) == 16) ? 16 : 10;
+    }
+    return v;
+}
+
 int num_sms() {
     static int v = 0;
     if (!v) {
@@ -821,26 +999,47 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
         hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
         const size_t b_total = (size_t)9 * hp.chunks * hp.bn * ROW_BYTES;
-        const size_t budget = 226 * 1024 - 2048;   // 227 KB per CTA minus the kernel's static shared memory
-        int stages = (int)((budget - b_total) / HALO_BYTES);
-        if (stages > 4) stages = 4;
+        const size_t budget = 227 * 1024 - 20 * 1024 - 2048;   // 227 KB per CTA minus static smem (epilogue tile, bias)
+        hp.halo_w = halo_pitch();
+        hp.halo_bytes = (uint32_t)hp.halo_w * HALO_H * ROW_BYTES;
+        hp.halo_stride = (hp.halo_bytes + 1023u) & ~1023u;
+        int stages = (int)((budget - b_total) / hp.halo_stride);
+        if (stages > 6) stages = 6;
         if (stages >= 2) {
             hp.stages = stages;
-            const size_t smem = b_total + (size_t)stages * HALO_BYTES + (2 * stages + 6) * 8 + 1024;
+            const size_t smem = b_total + (size_t)stages * hp.halo_stride + (2 * stages + 6) * 8 + 1024;
             CUtensorMap map_x, map_w;
-            if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, HALO_W, HALO_H)) return MI_ERR_UNSUPPORTED;
+            if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, hp.halo_w, HALO_H)) return MI_ERR_UNSUPPORTED;
             if (!make_weight_map(&map_w, w, ldw, cout, 9, cin, hp.bn)) return MI_ERR_UNSUPPORTED;
             static bool attr = false;
             if (!attr) {
                 cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_halo_kernel,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(206 * 1024));
                 if (e != cudaSuccess) return (int)e;
                 attr = true;
             }
             int grid = hp.total_tiles < num_sms() ? hp.total_tiles : num_sms();
             mi_prof_begin(MI_TAG_FPROP_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
                           stream);
+            static unsigned long long* dbg_buf = nullptr;
+            static int dbg_on = -1;
+            if (dbg_on < 0) { const char* e = getenv("MI_B200_DEBUG_TIMING"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+            hp.dbg = nullptr;
+            if (dbg_on) {
+                if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+                cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), stream);
+                hp.dbg = dbg_buf;
+            }
             conv_fprop_tc_halo_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, hp);
+            if (dbg_on) {
+                unsigned long long h[16];
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[halo cta0] tiles=%llu producer: wait_empty=%llu total=%llu | mma: wait_weights=%llu "
+                        "wait_full=%llu wait_tmem_empty=%llu total=%llu | epilogue: wait_acc=%llu tmem_ld=%llu "
+                        "math+store=%llu total=%llu cycles (stages=%d bn=%d chunks=%d)\n", h[10], h[0], h[1], h[2], h[3],
+                        h[4], h[5], h[6], h[7], h[8], h[9], hp.stages, hp.bn, hp.chunks);
+            }
             mi_prof_end(stream);
             MI_LAUNCHED();
             MI_RETURN_LAST();
