@@ -96,7 +96,9 @@ def dist_setup(n_gpus):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     else:
         torch.cuda.set_device(0)
     return rank, world, local
@@ -168,6 +170,8 @@ def run_ours(a):
     ms_e2e = timed(step_e2e, a.steps)
     e2e = batch * a.steps / (ms_e2e / 1e3)
 
+    # the instrumented roofline iteration contains the meta-gradient all-reduce: every rank must take part
+    extra = extra_sections(system, a, rank)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": "tasks/s", "n_gpus": world, "steps": a.steps,
@@ -180,7 +184,7 @@ def run_ours(a):
                     "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
         }
-        line.update(extra_sections(system, a, rank))
+        line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -191,7 +195,7 @@ def extra_sections(system, a, rank):
     try:
         from bench_sections import roofline_section, cpu_baseline_section
         out["roofline"] = roofline_section(system)
-        if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not a.no_cpu_baseline:
+        if rank == 0 and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not a.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_section()
     except ImportError:
         pass

@@ -1,0 +1,78 @@
+"""Task sharding + meta-gradient all-reduce: a 2-rank gloo run on CPU must reproduce the 1-rank run
+of the same meta-batch (sum of per-rank mean gradients scaled by 1/R == global mean)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, fast, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helpers import make_args
+    from oracle.ops_ref import RefOps
+    from meta_interpolation_b200 import backbone
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    ops = RefOps()
+    backbone.set_default_ops(ops)
+    args = make_args(batch_size=2, number_of_training_steps_per_iter=1, fast_path=fast)
+    system = SceneAdaptiveInterpolation(args, ops=ops)
+    g = torch.Generator().manual_seed(11)
+    frames = [torch.rand(2, 3, 32, 32, generator=g) for _ in range(7)]
+    losses, preds, _ = system.run_train_iter(frames, epoch=0)
+    mine = [i for i, p in enumerate(preds) if torch.is_tensor(p)]
+    torch.save({"flat": system.net.arena.flat.clone(), "tasks": mine, "loss": float(losses["loss"])},
+               os.path.join(out_dir, "rank%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def _single(fast):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import make_args
+    from oracle.ops_ref import RefOps
+    from meta_interpolation_b200 import backbone
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    ops = RefOps()
+    saved = backbone._default_ops
+    backbone.set_default_ops(ops)
+    try:
+        args = make_args(batch_size=2, number_of_training_steps_per_iter=1, fast_path=fast)
+        system = SceneAdaptiveInterpolation(args, ops=ops)
+        g = torch.Generator().manual_seed(11)
+        frames = [torch.rand(2, 3, 32, 32, generator=g) for _ in range(7)]
+        losses, _, _ = system.run_train_iter(frames, epoch=0)
+        return system.net.arena.flat.clone(), float(losses["loss"])
+    finally:
+        backbone.set_default_ops(saved)
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_two_ranks_equal_one_rank(tmp_path, fast):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, fast, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
+    r1 = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
+    assert r0["tasks"] == [0] and r1["tasks"] == [1]           # each rank adapted its own shard
+    assert torch.equal(r0["flat"], r1["flat"])                   # identical outer step on every rank
+    single, loss = _single(fast)
+    # outer SGD step: theta - lr * mean-gradient; the two summation orders agree to fp32 rounding
+    assert (r0["flat"] - single).abs().max().item() <= 1e-9
+    assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6
