@@ -122,6 +122,31 @@ int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size
 int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c, mi_stream_t stream);
 int mi_fill(float* p, float v, size_t count, mi_stream_t stream);
 
+/* ------------------------------------------------------------------ glue of the flow-based backbones
+ * Frozen batch norm + activation (nn.BatchNorm2d in eval mode, voxel_flow.py:241-263,352-355):
+ *   y = act((x - mean[c]) * rsqrt(var[c] + eps) * gamma[c] + beta[c]).
+ * Backward: dx (+)= dz * gamma * inv_std with dz = dy * act'(y); dgamma = sum dz * xhat, dbeta = sum dz
+ * (mode MI_WG_STORE or MI_WG_ACCUM with `scale`); dx / dgamma / dbeta may be NULL. */
+int mi_bn_eval_fwd(const float* x, int ldx, float* y, int ldy, const float* gamma, const float* beta,
+                   const float* mean, const float* var, float eps, int act, float slope, size_t pixels, int c,
+                   mi_stream_t stream);
+size_t mi_bn_eval_bwd_workspace(size_t pixels, int c);
+int mi_bn_eval_bwd(const float* dy, int lddy, const float* y, int ldy, const float* x, int ldx, float* dx, int lddx,
+                   int accumulate_dx, const float* gamma, const float* mean, const float* var, float eps, int act,
+                   float slope, float* dgamma, float* dbeta, int mode, float scale, void* workspace,
+                   size_t workspace_bytes, size_t pixels, int c, mi_stream_t stream);
+/* y = a (op) b, op 0 add / 1 sub / 2 mul / 3 div; b has c channels or 1 (broadcast over channels).
+ * Replaces the blend / flow arithmetic of voxel_flow.py:480-507, superslomo/model.py:600-640, rrin/model.py:88-120.
+ * Backward writes (acc=0) or accumulates (acc=1) ga / gb; either may be NULL. */
+int mi_binary_fwd(int op, const float* a, int lda, const float* b, int ldb, int cb, float* y, int ldy, size_t pixels,
+                  int c, mi_stream_t stream);
+int mi_binary_bwd(int op, const float* a, int lda, const float* b, int ldb, int cb, const float* go, int ldgo,
+                  float* ga, int ldga, int acc_a, float* gb, int ldgb, int acc_b, size_t pixels, int c,
+                  mi_stream_t stream);
+/* y (+)= alpha * x + beta over [pixels][c] */
+int mi_affine(const float* x, int ldx, float* y, int ldy, float alpha, float beta, int accumulate, size_t pixels,
+              int c, mi_stream_t stream);
+
 /* ------------------------------------------------------------------ frames in / prediction out
  * Builds the NHWC network input from two NCHW frames with the reference's
  * padding folded in: canvas[n,y,x,0:3]=f0, [3:6]=f1 sampled at

@@ -39,6 +39,13 @@ SIGNATURES = {
     "mi_copy": (_i, [_f, _i, _f, _i, _i, _sz, _i, _st]),
     "mi_act_bwd": (_i, [_f, _i, _f, _i, _i, _fl, _sz, _i, _st]),
     "mi_fill": (_i, [_f, _fl, _sz, _st]),
+    "mi_bn_eval_fwd": (_i, [_f, _i, _f, _i, _f, _f, _f, _f, _fl, _i, _fl, _sz, _i, _st]),
+    "mi_bn_eval_bwd_workspace": (_sz, [_sz, _i]),
+    "mi_bn_eval_bwd": (_i, [_f, _i, _f, _i, _f, _i, _f, _i, _i, _f, _f, _f, _fl, _i, _fl, _f, _f, _i, _fl, _f, _sz,
+                            _sz, _i, _st]),
+    "mi_binary_fwd": (_i, [_i, _f, _i, _f, _i, _i, _f, _i, _sz, _i, _st]),
+    "mi_binary_bwd": (_i, [_i, _f, _i, _f, _i, _i, _f, _i, _f, _i, _i, _f, _i, _i, _sz, _i, _st]),
+    "mi_affine": (_i, [_f, _i, _f, _i, _fl, _fl, _i, _sz, _i, _st]),
     "mi_frames_to_canvas": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nhwc_window_to_nchw": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nchw_to_nhwc_window": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),

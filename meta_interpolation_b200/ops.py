@@ -250,6 +250,47 @@ class CudaOps:
         _lib.check(self.lib.mi_axpby(x.data_ptr(), float(a), y.data_ptr(), float(b), x.numel(), self._stream()),
                    "mi_axpby")
 
+    # ------------------------------------------------------------------ glue ops of the flow-based backbones
+    BIN_ADD, BIN_SUB, BIN_MUL, BIN_DIV = 0, 1, 2, 3
+
+    def bn_eval_fwd(self, x, gamma, beta, mean, var, eps, act=ACT_NONE, slope=0.0, out=None):
+        n, h, w, c = x.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_bn_eval_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), gamma.data_ptr(),
+                                           beta.data_ptr(), mean.data_ptr(), var.data_ptr(), float(eps), act,
+                                           float(slope), n * h * w, c, self._stream()), "mi_bn_eval_fwd")
+        return y
+
+    def bn_eval_bwd(self, dy, y, x, gamma, mean, var, eps, act, slope, dx, accumulate_dx, dgamma, dbeta, mode, scale):
+        n, h, w, c = x.shape
+        ws = self.workspace(self.lib.mi_bn_eval_bwd_workspace(n * h * w, c))
+        _lib.check(self.lib.mi_bn_eval_bwd(dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), x.data_ptr(), _ld(x),
+                                           self._p(dx), 0 if dx is None else _ld(dx), int(accumulate_dx),
+                                           gamma.data_ptr(), mean.data_ptr(), var.data_ptr(), float(eps), act,
+                                           float(slope), self._p(dgamma), self._p(dbeta), mode, float(scale),
+                                           ws.data_ptr(), ws.numel(), n * h * w, c, self._stream()), "mi_bn_eval_bwd")
+
+    def binary_fwd(self, op, a, b, out=None):
+        n, h, w, c = a.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_binary_fwd(op, a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), b.shape[3], y.data_ptr(),
+                                          _ld(y), n * h * w, c, self._stream()), "mi_binary_fwd")
+        return y
+
+    def binary_bwd(self, op, a, b, go, ga, acc_a, gb, acc_b):
+        n, h, w, c = a.shape
+        _lib.check(self.lib.mi_binary_bwd(op, a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), b.shape[3], go.data_ptr(),
+                                          _ld(go), self._p(ga), 0 if ga is None else _ld(ga), int(acc_a), self._p(gb),
+                                          0 if gb is None else _ld(gb), int(acc_b), n * h * w, c, self._stream()),
+                   "mi_binary_bwd")
+
+    def affine(self, x, alpha, beta, out=None, accumulate=False):
+        n, h, w, c = x.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_affine(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), float(alpha), float(beta),
+                                      int(accumulate), n * h * w, c, self._stream()), "mi_affine")
+        return y
+
     # ------------------------------------------------------------------ frames in / prediction out
     def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
         """f0, f1: NCHW [n,3,h,w] contiguous -> NHWC canvas [n,ch,cw,6] (ld 8)."""

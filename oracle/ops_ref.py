@@ -210,6 +210,63 @@ class RefOps:
     def axpby(self, x, a, y, b):
         y.copy_(a * x + (b * y if b != 0 else 0))
 
+    # ------------------------------------------------------------------ glue ops of the flow-based backbones
+    BIN_ADD, BIN_SUB, BIN_MUL, BIN_DIV = 0, 1, 2, 3
+
+    def bn_eval_fwd(self, x, gamma, beta, mean, var, eps, act=ACT_NONE, slope=0.0, out=None):
+        y = act_apply((x - mean) * torch.rsqrt(var + eps) * gamma + beta, act, slope)
+        if out is None:
+            out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    def bn_eval_bwd(self, dy, y, x, gamma, mean, var, eps, act, slope, dx, accumulate_dx, dgamma, dbeta, mode, scale):
+        dz = dy * act_grad(y, act, slope)
+        inv = torch.rsqrt(var + eps)
+        if dx is not None:
+            g = dz * gamma * inv
+            dx.add_(g) if accumulate_dx else dx.copy_(g)
+        dg = (dz * (x - mean) * inv).sum(dim=(0, 1, 2))
+        db = dz.sum(dim=(0, 1, 2))
+        for tgt, val in ((dgamma, dg), (dbeta, db)):
+            if tgt is not None:
+                tgt.add_(scale * val) if mode == WG_ACCUM else tgt.copy_(val)
+
+    @staticmethod
+    def _bin(op, a, b):
+        return (a + b, a - b, a * b, a / b)[op]
+
+    def binary_fwd(self, op, a, b, out=None):
+        y = self._bin(op, a, b)
+        if out is None:
+            out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    def binary_bwd(self, op, a, b, go, ga, acc_a, gb, acc_b):
+        if op == 0:
+            da, db = go, go
+        elif op == 1:
+            da, db = go, -go
+        elif op == 2:
+            da, db = go * b, go * a
+        else:
+            da, db = go / b, -go * a / (b * b)
+        if b.shape[3] == 1 and a.shape[3] != 1:
+            db = db.sum(dim=3, keepdim=True)
+        if ga is not None:
+            ga.add_(da) if acc_a else ga.copy_(da)
+        if gb is not None:
+            gb.add_(db) if acc_b else gb.copy_(db)
+
+    def affine(self, x, alpha, beta, out=None, accumulate=False):
+        y = alpha * x + beta
+        if out is None:
+            out = self.empty_act(*y.shape)
+            accumulate = False
+        out.add_(y) if accumulate else out.copy_(y)
+        return out
+
     # ------------------------------------------------------------------ frames in / prediction out
     def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
         n, c, h, w = f0.shape
