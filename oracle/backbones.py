@@ -137,9 +137,28 @@ def sepconv_param_shapes():
     return out
 
 
+from . import backbones_flow as _bf  # noqa: E402
+
 BACKBONES = {
     "sepconv": dict(forward=sepconv_forward, is_routed=sepconv_is_routed, shapes=sepconv_param_shapes),
+    "voxelflow": dict(forward=_bf.voxelflow_forward, is_routed=_bf.voxelflow_is_routed,
+                      shapes=_bf.voxelflow_param_shapes),
+    "superslomo": dict(forward=_bf.superslomo_forward, is_routed=_bf.superslomo_is_routed,
+                       shapes=_bf.superslomo_param_shapes),
+    "rrin": dict(forward=_bf.rrin_forward, is_routed=_bf.rrin_is_routed, shapes=_bf.rrin_param_shapes),
+    "cain": dict(forward=_bf.cain_forward, is_routed=_bf.cain_is_routed, shapes=_bf.cain_param_shapes),
 }
+
+SUPERSLOMO_MEAN = (0.429, 0.431, 0.397)
+
+
+def denormalise(model, x):
+    """Prediction / target back to [0,1] (meta_learning_system.py:70-73,78-79,434-447)."""
+    if model == "superslomo":
+        return x + torch.tensor(SUPERSLOMO_MEAN, dtype=x.dtype).view(-1, 1, 1)
+    if model == "voxelflow":
+        return (x * 127.5 + 127.5) / 255.0
+    return x
 
 
 def set_torch_seed(seed):
@@ -157,6 +176,8 @@ def seeded_params(model, seed=12345):
     tensors as ``SceneAdaptiveInterpolation(args).net`` without the reference."""
     from collections import OrderedDict
     set_torch_seed(seed)
+    if model == "voxelflow":
+        return _bf.voxelflow_seeded_params()
     out = OrderedDict()
     for name, shape in BACKBONES[model]["shapes"]():
         if name.endswith(".weight") and len(shape) == 4:

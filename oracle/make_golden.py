@@ -35,6 +35,27 @@ CASES = {
                                        number_of_training_steps_per_iter=2), 48, 1),
     "sepconv_l2f_sgd_k1": (dict(model="sepconv", loss="1*L1", optimizer="SGD", attenuate=True,
                                 number_of_training_steps_per_iter=1), 48, 1),
+    # BASELINE configs[0]: voxelflow, batch 1, 128x128, 1 inner step, CPU-runnable
+    "voxelflow_lslr_sgd_k1_mse": (dict(model="voxelflow", loss="1*MSE", optimizer="SGD",
+                                       number_of_training_steps_per_iter=1), 128, 1),
+    "voxelflow_lslr_sgd_k2_ragged": (dict(model="voxelflow", loss="1*L1", optimizer="SGD",
+                                          number_of_training_steps_per_iter=2), (72, 88), 1),
+    # configs[2] in miniature: superslomo Meta-SGD (SGD rule), K=2
+    "superslomo_metasgd_sgd_k2": (dict(model="superslomo", loss="1*L1", optimizer="SGD", metasgd=True,
+                                       number_of_training_steps_per_iter=2), 64, 2),
+    "superslomo_lslr_sgd_k1_ragged": (dict(model="superslomo", loss="1*L1", optimizer="SGD",
+                                           number_of_training_steps_per_iter=1), (72, 80), 1),
+    # configs[4] in miniature: rrin MAML++ (multi-step loss + learnable per-step lr), K=2
+    "rrin_msl_learnable_k2": (dict(model="rrin", loss="1*L1", optimizer="SGD", number_of_training_steps_per_iter=2,
+                                   learnable_per_layer_per_step_inner_loop_learning_rate=True,
+                                   use_multi_step_loss_optimization=True), (64, 128), 1),
+    "rrin_lslr_sgd_k1_ragged": (dict(model="rrin", loss="1*L1", optimizer="SGD",
+                                     number_of_training_steps_per_iter=1), (72, 136), 1),
+    # configs[3] in miniature: cain L2F (--attenuate)
+    "cain_l2f_sgd_k1": (dict(model="cain", loss="1*L1", optimizer="SGD", attenuate=True,
+                             number_of_training_steps_per_iter=1), 128, 1),
+    "cain_lslr_sgd_k2_ragged": (dict(model="cain", loss="1*L1", optimizer="SGD",
+                                     number_of_training_steps_per_iter=2), (120, 136), 1),
 }
 
 
@@ -43,16 +64,24 @@ def digest(t):
     return torch.tensor([t.sum(), t.abs().sum(), (t * t).sum()], dtype=torch.float64), t[:8].clone().float()
 
 
-def synthetic_frames(seed, batch, size):
+def synthetic_frames(seed, batch, size, model="sepconv"):
+    """Seeded [0,1] frames, then the model's dataset normalisation (data/vimeo_septuplet.py:31-40,73-76)."""
     g = torch.Generator().manual_seed(seed)
-    return [torch.rand(batch, 3, size, size, generator=g) for _ in range(7)]
+    h, w = (size, size) if isinstance(size, int) else size
+    frames = [torch.rand(batch, 3, h, w, generator=g) for _ in range(7)]
+    if model == "superslomo":
+        mean = torch.tensor([0.429, 0.431, 0.397]).view(1, 3, 1, 1)
+        frames = [f - mean for f in frames]
+    elif model == "voxelflow":
+        frames = [(f * 255 - 127.5) / 127.5 for f in frames]
+    return frames
 
 
 def run_case(name, over, size, batch):
     from oracle import reference_shims as rs
     from oracle import maml
     system, args = rs.build_system(batch_size=batch, **over)
-    frames = synthetic_frames(0, batch, size)
+    frames = synthetic_frames(0, batch, size, over.get("model", "sepconv"))
     init = {k: v.detach().clone() for k, v in system.net.named_parameters()}
     att_state = {k: v.detach().clone() for k, v in system.attenuator.state_dict().items()} if args.attenuate else None
 

@@ -165,8 +165,9 @@ class OracleSystem:
                 task_losses.append(tl["total"])
             if record is not None and task == 0:
                 record["fast_final"] = {k: v.detach().clone() for k, v in fast.items()}
-            preds.append(out.detach())
-            psnrs.append(psnr(out.detach()[0], frames[target_idx[1]][task]))
+            preds.append(bb.denormalise(self.model, out.detach()[0]).unsqueeze(0))
+            psnrs.append(psnr(bb.denormalise(self.model, out.detach()[0]),
+                              bb.denormalise(self.model, frames[target_idx[1]][task])))
             total_losses.append(torch.sum(torch.stack(task_losses)))
         loss = torch.mean(torch.stack(total_losses))
         return loss, preds, psnrs
