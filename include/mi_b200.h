@@ -147,6 +147,53 @@ int mi_binary_bwd(int op, const float* a, int lda, const float* b, int ldb, int 
 int mi_affine(const float* x, int ldx, float* y, int ldy, float alpha, float beta, int accumulate, size_t pixels,
               int c, mi_stream_t stream);
 
+/* ------------------------------------------------------------------ heads of the flow / attention backbones
+ * y = act(x) standalone (superslomo/model.py:617 sigmoid of one channel, voxel_flow.py:449 tanh) */
+int mi_act_fwd(const float* x, int ldx, float* y, int ldy, int act, float slope, size_t pixels, int c, mi_stream_t stream);
+/* y = clamp(x, lo, hi) and its gradient (passes where lo <= x <= hi), rrin/model.py:119 */
+int mi_clamp_fwd(const float* x, int ldx, float* y, int ldy, float lo, float hi, size_t pixels, int c, mi_stream_t stream);
+int mi_clamp_bwd(const float* dy, int lddy, const float* x, int ldx, float* dx, int lddx, int accumulate, float lo,
+                 float hi, size_t pixels, int c, mi_stream_t stream);
+/* visibility-weighted blend of two warped frames a, b (c channels) with one-channel maps m0, m1:
+ *   mode 0: (w0*m0*a + w1*m1*b) / (w0*m0 + w1*m1 + eps)     rrin/model.py:102-103
+ *   mode 1: the same with m1 = 1 - m0 (m1 ignored)           superslomo/model.py:621-630
+ *   mode 2: m0*a + (1-m0)*b                                  voxel_flow.py:505-507
+ * Backward writes / accumulates ga, gb, gm0, gm1 (any may be NULL). */
+int mi_blend_fwd(const float* a, int lda, const float* b, int ldb, const float* m0, int ldm0, const float* m1,
+                 int ldm1, float* out, int ldo, float w0, float w1, float eps, int mode, size_t pixels, int c,
+                 mi_stream_t stream);
+int mi_blend_bwd(const float* a, int lda, const float* b, int ldb, const float* m0, int ldm0, const float* m1,
+                 int ldm1, const float* go, int ldgo, float* ga, int ldga, float* gb, int ldgb, float* gm0, int ldgm0,
+                 float* gm1, int ldgm1, int accumulate, float w0, float w1, float eps, int mode, size_t pixels, int c,
+                 mi_stream_t stream);
+/* Reflection-padded convolution (MetaConvNorm, model_utils.py:821-849) on the zero-padding conv engine: the
+ * activation lives in the interior of an h x wd buffer whose one-pixel ring mi_ring_fix fills in place with zeros
+ * (mode 0) or the reflection of the interior (mode 1); mi_ring_fold is the transpose (ring gradient folded onto the
+ * mirrored interior pixel for mode 1, ring cleared in both modes). */
+int mi_ring_fix(float* x, int ld, int n, int h, int wd, int c, int mode, mi_stream_t stream);
+int mi_ring_fold(float* g, int ld, int n, int h, int wd, int c, int mode, mi_stream_t stream);
+/* CAIN input/output (cain/model.py:70-94, model_utils.py:11-28,202-217): per-plane mean of an NCHW tensor;
+ * space-to-depth by r of the two reflect-padded, mean-shifted frames into one ringed NHWC buffer
+ * [n, oh+2, ow+2, 6*r*r] (ring = 0); depth-to-space of a ringed NHWC buffer [n, ih+2, iw+2, 3*r*r] into the cropped
+ * NCHW image plus (mean0+mean1)/2, and its transpose. */
+int mi_channel_mean_nchw(const float* f, float* out, int planes, int hw, mi_stream_t stream);
+int mi_space_to_depth(const float* f0, const float* f1, const float* mean0, const float* mean1, float* out, int ldo,
+                      int n, int h, int wd, int pad_top, int pad_left, int oh, int ow, int r, mi_stream_t stream);
+int mi_depth_to_space(const float* in, int ldi, const float* mean0, const float* mean1, float* out, int n, int h,
+                      int wd, int pad_top, int pad_left, int ih, int iw, int r, mi_stream_t stream);
+int mi_depth_to_space_bwd(const float* gout, float* gin, int ldi, int n, int h, int wd, int pad_top, int pad_left,
+                          int ih, int iw, int r, mi_stream_t stream);
+/* Channel attention (MetaCALayer, model_utils.py:931-955) on a buffer with `ring` border pixels excluded:
+ * out[n,c] = scale * sum_interior x (* mul);  out = o*s[n,c] + res;  dx (+)= g*s[n,c];  dx[interior] += dy[n,c]*scale */
+int mi_interior_reduce(const float* x, int ldx, const float* mul, int ldm, float* out, int n, int h, int wd, int c,
+                       int ring, float scale, mi_stream_t stream);
+int mi_scale_add(const float* o, int ldo, const float* s, const float* res, int ldr, float* out, int ldout, int n,
+                 size_t pixels_per_image, int c, mi_stream_t stream);
+int mi_scale_bwd(const float* g, int ldg, const float* s, float* dx, int lddx, int accumulate, int n,
+                 size_t pixels_per_image, int c, mi_stream_t stream);
+int mi_interior_bcast_add(const float* dy, float* dx, int lddx, int n, int h, int wd, int c, int ring, float scale,
+                          mi_stream_t stream);
+
 /* ------------------------------------------------------------------ frames in / prediction out
  * Builds the NHWC network input from two NCHW frames with the reference's
  * padding folded in: canvas[n,y,x,0:3]=f0, [3:6]=f1 sampled at

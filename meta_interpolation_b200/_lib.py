@@ -46,6 +46,22 @@ SIGNATURES = {
     "mi_binary_fwd": (_i, [_i, _f, _i, _f, _i, _i, _f, _i, _sz, _i, _st]),
     "mi_binary_bwd": (_i, [_i, _f, _i, _f, _i, _i, _f, _i, _f, _i, _i, _f, _i, _i, _sz, _i, _st]),
     "mi_affine": (_i, [_f, _i, _f, _i, _fl, _fl, _i, _sz, _i, _st]),
+    "mi_act_fwd": (_i, [_f, _i, _f, _i, _i, _fl, _sz, _i, _st]),
+    "mi_clamp_fwd": (_i, [_f, _i, _f, _i, _fl, _fl, _sz, _i, _st]),
+    "mi_clamp_bwd": (_i, [_f, _i, _f, _i, _f, _i, _i, _fl, _fl, _sz, _i, _st]),
+    "mi_blend_fwd": (_i, [_f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _fl, _fl, _fl, _i, _sz, _i, _st]),
+    "mi_blend_bwd": (_i, [_f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _i, _fl, _fl, _fl,
+                          _i, _sz, _i, _st]),
+    "mi_ring_fix": (_i, [_f, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_ring_fold": (_i, [_f, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_channel_mean_nchw": (_i, [_f, _f, _i, _i, _st]),
+    "mi_space_to_depth": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_depth_to_space": (_i, [_f, _i, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_depth_to_space_bwd": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_interior_reduce": (_i, [_f, _i, _f, _i, _f, _i, _i, _i, _i, _i, _fl, _st]),
+    "mi_scale_add": (_i, [_f, _i, _f, _f, _i, _f, _i, _i, _sz, _i, _st]),
+    "mi_scale_bwd": (_i, [_f, _i, _f, _f, _i, _i, _i, _sz, _i, _st]),
+    "mi_interior_bcast_add": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _fl, _st]),
     "mi_frames_to_canvas": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nhwc_window_to_nchw": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nchw_to_nhwc_window": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),

@@ -37,6 +37,19 @@ def set_default_ops(ops):
     _default_ops = ops
 
 
+class _BnSlot(nn.Module):
+    """Reference-visible parameters / buffers of one frozen BatchNorm2d (voxel_flow.py:241-263)."""
+
+    def __init__(self, weight, bias, channels, device, eps=1e-5):
+        super().__init__()
+        self.weight = weight
+        self.bias = bias
+        self.eps = eps
+        self.register_buffer("running_mean", torch.zeros(channels, device=device))
+        self.register_buffer("running_var", torch.ones(channels, device=device))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long, device=device))
+
+
 class _ConvSlot(nn.Module):
     """Holds the reference-visible ``weight`` / ``bias`` Parameters of one conv (views into the arena)."""
 
@@ -64,10 +77,20 @@ def kernel_weight_view(ops, t):
 class StoreSink:
     """Weight-gradient sink of the compat path: plain gradients, only where autograd asks for them."""
 
-    def __init__(self, ops, wanted):
+    def __init__(self, ops, wanted, vec_like=None):
         self.ops = ops
         self.wanted = wanted          # set of parameter names whose gradient is needed
         self.grads = {}
+        self.vec_like = vec_like      # name -> tensor shaped like a batch-norm scale
+
+    def bn_targets(self, name):
+        wn, bn = name + ".weight", name + ".bias"
+        if wn not in self.wanted and bn not in self.wanted:
+            return None
+        ref = self.vec_like(name)
+        gw, gb = torch.zeros_like(ref), torch.zeros_like(ref)
+        self.grads[wn], self.grads[bn] = gw, gb
+        return gw, gb, WG_STORE, 1.0
 
     def weight_grad(self, p, x, dy, k):
         wn, bn = p.name + ".weight", p.name + ".bias"
@@ -100,7 +123,12 @@ class _BackboneFunction(torch.autograd.Function):
                 cache[name] = p
             return p
 
-        tape = Tape(ops, provider, sink=None)
+        def vectors(name):
+            slot = net.bn_slot(name)
+            return (table[name + ".weight"].detach(), table[name + ".bias"].detach(), slot.running_mean,
+                    slot.running_var, slot.eps)
+
+        tape = Tape(ops, provider, sink=None, vectors=vectors)
         out = net.build_graph(tape, frame0.detach().contiguous(), frame1.detach().contiguous())
         ctx.tape, ctx.out_var, ctx.names, ctx.net = tape, out, names, net
         ctx.shapes = [tuple(t.shape) for t in tensors]
@@ -111,7 +139,7 @@ class _BackboneFunction(torch.autograd.Function):
         net, tape = ctx.net, ctx.tape
         needs = ctx.needs_input_grad[4:]
         wanted = {n for n, need in zip(ctx.names, needs) if need}
-        sink = StoreSink(net.ops, wanted)
+        sink = StoreSink(net.ops, wanted, vec_like=lambda name: net.bn_slot(name).weight.detach())
         tape.sink = sink
         ctx.out_var.grad = grad_out.contiguous()
         tape.backward()
@@ -147,30 +175,62 @@ class MetaBackbone(nn.Module):
         raise NotImplementedError
 
     # -- construction ---------------------------------------------------------------------------
+    def param_entries(self):
+        """Ordered entries in the reference's registration order: ("conv", name, cin, cout, k, has_bias) or
+        ("bn", name, channels).  Default: the convs of ``conv_specs``."""
+        return [("conv",) + tuple(spec) for spec in self.conv_specs()]
+
     def _build_parameters(self, init_fn):
         """Create the arena and the reference-named Parameters; ``init_fn(name, shape) -> CPU tensor`` is
         called in registration order so the CPU RNG stream matches the reference's constructors."""
-        specs = self.conv_specs()
+        entries = self.param_entries()
         named_shapes = []
-        for name, cin, cout, k, has_bias in specs:
-            named_shapes.append((name + ".weight", (cout, cin, k, k)))
-            if has_bias:
-                named_shapes.append((name + ".bias", (cout,)))
+        for e in entries:
+            if e[0] == "conv":
+                _, name, cin, cout, k, has_bias = e
+                named_shapes.append((name + ".weight", (cout, cin, k, k)))
+                if has_bias:
+                    named_shapes.append((name + ".bias", (cout,)))
+            else:
+                _, name, c = e
+                named_shapes.append((name + ".weight", (c,)))
+                named_shapes.append((name + ".bias", (c,)))
         self.layout = Layout(named_shapes)
         self.arena = Arena(self.layout, self.ops.device)
         self.param_names = [n for n, _ in named_shapes]
-        self.conv_names = [s[0] for s in specs]
-        self._spec = {s[0]: s for s in specs}
-        for name, cin, cout, k, has_bias in specs:
-            wv = self.arena.reference_view(name + ".weight")
-            wv.copy_(init_fn(name + ".weight", (cout, cin, k, k)))
-            weight = nn.Parameter(wv)
-            bias = None
-            if has_bias:
+        self.conv_names = [e[1] for e in entries if e[0] == "conv"]
+        self.bn_names = [e[1] for e in entries if e[0] == "bn"]
+        self._spec = {e[1]: e[1:] for e in entries if e[0] == "conv"}
+        self._bn_slots = {}
+        for e in entries:
+            if e[0] == "conv":
+                _, name, cin, cout, k, has_bias = e
+                wv = self.arena.reference_view(name + ".weight")
+                wv.copy_(init_fn(name + ".weight", (cout, cin, k, k)))
+                weight = nn.Parameter(wv)
+                bias = None
+                if has_bias:
+                    bv = self.arena.reference_view(name + ".bias")
+                    bv.copy_(init_fn(name + ".bias", (cout,)))
+                    bias = nn.Parameter(bv)
+                self._register(name, _ConvSlot(weight, bias))
+            else:
+                _, name, c = e
+                wv = self.arena.reference_view(name + ".weight")
+                wv.copy_(init_fn(name + ".weight", (c,)))
                 bv = self.arena.reference_view(name + ".bias")
-                bv.copy_(init_fn(name + ".bias", (cout,)))
-                bias = nn.Parameter(bv)
-            self._register(name, _ConvSlot(weight, bias))
+                bv.copy_(init_fn(name + ".bias", (c,)))
+                slot = _BnSlot(nn.Parameter(wv), nn.Parameter(bv), c, self.ops.device)
+                self._bn_slots[name] = slot
+                self._register(name, slot)
+
+    def bn_slot(self, name):
+        return self._bn_slots[name]
+
+    def meta_bn(self, name):
+        slot = self._bn_slots[name]
+        return (self.arena.kernel_view(name + ".weight"), self.arena.kernel_view(name + ".bias"), slot.running_mean,
+                slot.running_var, slot.eps)
 
     def _register(self, dotted, slot):
         parts = dotted.split(".")

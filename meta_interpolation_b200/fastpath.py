@@ -89,6 +89,20 @@ class _Sink:
             spec = WgradSpec(WG_STORE, grad_w=garena.kernel_view(wn), grad_b=garena.kernel_view(bn) if has_b else None)
             fp.ops.conv_wgrad(x, dy, k, ldw, spec)
 
+    def bn_targets(self, name):
+        """(dgamma, dbeta, mode, scale) for a frozen batch norm, or None when its gradient is dead work
+        (never routed from the fast weights: support passes skip it)."""
+        lane = self.lane
+        wn, bn = name + ".weight", name + ".bias"
+        if self.mode == 'inner':
+            assert not lane.fp.net.is_routed(wn)
+            return None
+        if self.mode == 'accum':
+            g = lane.acc_theta
+            return g.kernel_view(wn), g.kernel_view(bn), WG_ACCUM, self.scale
+        g = lane.gquery
+        return g.kernel_view(wn), g.kernel_view(bn), WG_STORE, 1.0
+
 
 class _Program:
     """One capturable unit: static inputs, a body, static outputs."""
@@ -263,7 +277,7 @@ class FastPath:
         def body(prog):
             self.ops.set_workspace_slot(lane.index)
             sink = _Sink(lane, 'inner', step=step_slot)
-            tape = Tape(self.ops, self._provider(lane, src), sink)
+            tape = Tape(self.ops, self._provider(lane, src), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             out.grad = self._loss(prog, out.data, prog.f0.shape[0])
             tape.backward()
@@ -275,7 +289,7 @@ class FastPath:
             sink = _Sink(lane, mode, scale=1.0) if backward else None
             if mode == 'accum' and backward:
                 sink.scale = prog.scale
-            tape = Tape(self.ops, self._provider(lane, src), sink)
+            tape = Tape(self.ops, self._provider(lane, src), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             prog.pred = out.data
             g = self._loss(prog, out.data, 1)

@@ -51,6 +51,19 @@ def _build_backbone(args, ops):
     if args.model == 'sepconv':
         from .sepconv.model import MetaNetwork as MetaSepConv
         return MetaSepConv(resume=resume, strModel='l1', ops=ops)
+    if args.model == 'cain':
+        from .cain.model import MetaCAIN
+        return MetaCAIN(depth=3, resume=resume, ops=ops)
+    if args.model == 'rrin':
+        from .rrin.model import MetaRRIN
+        return MetaRRIN(level=3, resume=resume, ops=ops)
+    if args.model == 'superslomo':
+        from .superslomo.model import MetaSuperSloMo
+        return MetaSuperSloMo(ops.device, resume=resume, ops=ops)
+    if args.model == 'voxelflow':
+        from .voxelflow.core.models.voxel_flow import MetaVoxelFlow
+        return MetaVoxelFlow(args, resume=resume, ops=ops)
+    # 'dain' needs its eight native extensions and is outside the hot path
     raise NotImplementedError('Model not implemented yet!')
 
 
@@ -72,6 +85,15 @@ class SceneAdaptiveInterpolation(nn.Module):
 
         self.rng = set_torch_seed(seed=args.random_seed)
         self.net = _build_backbone(args, self.ops)
+        if args.model == 'superslomo':   # reference :70-73: outputs back to the 0~1 scale
+            self._shift = torch.tensor([0.429, 0.431, 0.397], device=self.device).view(3, 1, 1)
+            self.revNormalize = lambda img: img + self._shift
+        elif args.model == 'voxelflow':  # reference :78-79
+            self.mean = torch.FloatTensor([0.5 * 255] * 3).to(self.device).unsqueeze(1).unsqueeze(2)
+            self.std = torch.FloatTensor([0.5 * 255] * 3).to(self.device).unsqueeze(1).unsqueeze(2)
+            if args.optimizer == 'Adam':
+                raise NotImplementedError('voxelflow + Adam uses per-group lr/decay policies (reference :134-136) '
+                                          'that the flat outer optimizer does not implement')
 
         self.inner_learning_rate = args.inner_lr
         if self.args.metasgd:
@@ -239,6 +261,11 @@ class SceneAdaptiveInterpolation(nn.Module):
 
     # ------------------------------------------------------------------ forward (compat control flow)
     def _denorm(self, pred):
+        """Prediction / target back to [0,1] (reference :434-447).  Accepts [3,H,W] or [1,3,H,W]."""
+        if self.args.model == 'superslomo':
+            return pred + self._shift
+        if self.args.model == 'voxelflow':
+            return (pred * self.std + self.mean) / 255.0
         return pred
 
     def forward(self, data_batch, epoch, use_second_order, use_multi_step_loss_optimization, num_steps,
@@ -423,6 +450,9 @@ class SceneAdaptiveInterpolation(nn.Module):
                                           num_step=num_step)
             if self.args.model == 'superslomo':
                 output = output[0]
-            preds[task_id] = self._denorm(output.detach()).squeeze(0)
+            output = output.detach()
+            if self.args.model == 'superslomo':   # reference :686-690 de-normalises superslomo only
+                output = self._denorm(output)
+            preds[task_id] = output.squeeze(0)
             self.net.restore_backup_stats()
         return preds

@@ -291,6 +291,122 @@ class CudaOps:
                                       int(accumulate), n * h * w, c, self._stream()), "mi_affine")
         return y
 
+    # ------------------------------------------------------------------ heads of the flow / attention backbones
+    BLEND_RATIO, BLEND_RATIO_COMPLEMENT, BLEND_LERP = 0, 1, 2
+    RING_ZERO, RING_REFLECT = 0, 1
+
+    def act_fwd(self, x, act, slope=0.0, out=None):
+        n, h, w, c = x.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_act_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), act, float(slope), n * h * w, c,
+                                       self._stream()), "mi_act_fwd")
+        return y
+
+    def clamp_fwd(self, x, lo, hi, out=None):
+        n, h, w, c = x.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_clamp_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), float(lo), float(hi), n * h * w,
+                                         c, self._stream()), "mi_clamp_fwd")
+        return y
+
+    def clamp_bwd(self, dy, x, dx, lo, hi, accumulate):
+        n, h, w, c = x.shape
+        _lib.check(self.lib.mi_clamp_bwd(dy.data_ptr(), _ld(dy), x.data_ptr(), _ld(x), dx.data_ptr(), _ld(dx),
+                                         int(accumulate), float(lo), float(hi), n * h * w, c, self._stream()),
+                   "mi_clamp_bwd")
+
+    def blend_fwd(self, a, b, m0, m1, w0, w1, eps, mode, out=None):
+        n, h, w, c = a.shape
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_blend_fwd(a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), m0.data_ptr(), _ld(m0),
+                                         self._p(m1), 0 if m1 is None else _ld(m1), y.data_ptr(), _ld(y), float(w0),
+                                         float(w1), float(eps), mode, n * h * w, c, self._stream()), "mi_blend_fwd")
+        return y
+
+    def blend_bwd(self, a, b, m0, m1, go, ga, gb, gm0, gm1, accumulate, w0, w1, eps, mode):
+        n, h, w, c = a.shape
+        ld = lambda t: 0 if t is None else _ld(t)
+        _lib.check(self.lib.mi_blend_bwd(a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), m0.data_ptr(), _ld(m0),
+                                         self._p(m1), ld(m1), go.data_ptr(), _ld(go), self._p(ga), ld(ga), self._p(gb),
+                                         ld(gb), self._p(gm0), ld(gm0), self._p(gm1), ld(gm1), int(accumulate),
+                                         float(w0), float(w1), float(eps), mode, n * h * w, c, self._stream()),
+                   "mi_blend_bwd")
+
+    def ring_fix(self, x, mode):
+        n, h, w, c = x.shape
+        _lib.check(self.lib.mi_ring_fix(x.data_ptr(), _ld(x), n, h, w, c, mode, self._stream()), "mi_ring_fix")
+
+    def ring_fold(self, g, mode):
+        n, h, w, c = g.shape
+        _lib.check(self.lib.mi_ring_fold(g.data_ptr(), _ld(g), n, h, w, c, mode, self._stream()), "mi_ring_fold")
+
+    def channel_mean_nchw(self, f):
+        n, c, h, w = f.shape
+        assert f.is_contiguous()
+        out = torch.empty(n * c, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.mi_channel_mean_nchw(f.data_ptr(), out.data_ptr(), n * c, h * w, self._stream()),
+                   "mi_channel_mean_nchw")
+        return out
+
+    def space_to_depth(self, f0, f1, mean0, mean1, pad_top, pad_left, oh, ow, r):
+        """Two NCHW frames -> one ringed NHWC buffer [n, oh+2, ow+2, 6*r*r] (reflect pad, mean shift, ring 0)."""
+        n, c, h, w = f0.shape
+        assert c == 3 and f0.is_contiguous() and f1.is_contiguous()
+        out = self.empty_act(n, oh + 2, ow + 2, 6 * r * r)
+        _lib.check(self.lib.mi_space_to_depth(f0.data_ptr(), f1.data_ptr(), mean0.data_ptr(), mean1.data_ptr(),
+                                              out.data_ptr(), _ld(out), n, h, w, pad_top, pad_left, oh, ow, r,
+                                              self._stream()), "mi_space_to_depth")
+        return out
+
+    def depth_to_space(self, x, mean0, mean1, h, w, pad_top, pad_left, r):
+        """Ringed NHWC [n, ih+2, iw+2, 3*r*r] -> cropped NCHW [n,3,h,w] + (mean0+mean1)/2."""
+        n, hh, ww, c = x.shape
+        assert c == 3 * r * r
+        out = torch.empty(n, 3, h, w, device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.mi_depth_to_space(x.data_ptr(), _ld(x), mean0.data_ptr(), mean1.data_ptr(), out.data_ptr(),
+                                              n, h, w, pad_top, pad_left, hh - 2, ww - 2, r, self._stream()),
+                   "mi_depth_to_space")
+        return out
+
+    def depth_to_space_bwd(self, gout, gin, pad_top, pad_left, r):
+        n, _, h, w = gout.shape
+        _, hh, ww, c = gin.shape
+        assert gout.is_contiguous()
+        _lib.check(self.lib.mi_depth_to_space_bwd(gout.data_ptr(), gin.data_ptr(), _ld(gin), n, h, w, pad_top,
+                                                  pad_left, hh - 2, ww - 2, r, self._stream()),
+                   "mi_depth_to_space_bwd")
+
+    def interior_reduce(self, x, mul, ring, scale):
+        """[n,h,w,c] -> [n,1,1,c]: scale * sum over the interior (ring excluded) of x (* mul)."""
+        n, h, w, c = x.shape
+        out = self.empty_act(n, 1, 1, c)
+        assert _ld(out) == c
+        _lib.check(self.lib.mi_interior_reduce(x.data_ptr(), _ld(x), self._p(mul), 0 if mul is None else _ld(mul),
+                                               out.data_ptr(), n, h, w, c, ring, float(scale), self._stream()),
+                   "mi_interior_reduce")
+        return out
+
+    def scale_add(self, o, s, res, out=None):
+        n, h, w, c = o.shape
+        assert s.shape == (n, 1, 1, c) and _ld(s) == c
+        y = out if out is not None else self.empty_act(n, h, w, c)
+        _lib.check(self.lib.mi_scale_add(o.data_ptr(), _ld(o), s.data_ptr(), self._p(res),
+                                         0 if res is None else _ld(res), y.data_ptr(), _ld(y), n, h * w, c,
+                                         self._stream()), "mi_scale_add")
+        return y
+
+    def scale_bwd(self, g, s, dx, accumulate):
+        n, h, w, c = g.shape
+        assert _ld(s) == c
+        _lib.check(self.lib.mi_scale_bwd(g.data_ptr(), _ld(g), s.data_ptr(), dx.data_ptr(), _ld(dx), int(accumulate),
+                                         n, h * w, c, self._stream()), "mi_scale_bwd")
+
+    def interior_bcast_add(self, dy, dx, ring, scale):
+        n, h, w, c = dx.shape
+        assert _ld(dy) == c
+        _lib.check(self.lib.mi_interior_bcast_add(dy.data_ptr(), dx.data_ptr(), _ld(dx), n, h, w, c, ring,
+                                                  float(scale), self._stream()), "mi_interior_bcast_add")
+
     # ------------------------------------------------------------------ frames in / prediction out
     def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
         """f0, f1: NCHW [n,3,h,w] contiguous -> NHWC canvas [n,ch,cw,6] (ld 8)."""
@@ -338,9 +454,9 @@ class CudaOps:
                    "mi_sepconv_bwd")
 
     # ------------------------------------------------------------------ warp
-    def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0):
+    def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0, out=None):
         n, h, w, c = img.shape
-        out = self.empty_act(n, h, w, c)
+        out = out if out is not None else self.empty_act(n, h, w, c)
         _lib.check(self.lib.mi_warp_fwd(img.data_ptr(), _ld(img), flow.data_ptr(), _ld(flow), out.data_ptr(), _ld(out),
                                         n, h, w, c, variant, float(sx), float(sy), self._stream()), "mi_warp_fwd")
         return out

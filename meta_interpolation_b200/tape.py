@@ -41,10 +41,12 @@ class ConvParam:
 
 
 class Tape:
-    def __init__(self, ops, params, sink=None):
-        """params: callable name -> ConvParam; sink: object with weight_grad(param, x, dy, k) or None (no wgrad)."""
+    def __init__(self, ops, params, sink=None, vectors=None):
+        """params: callable name -> ConvParam; vectors: callable name -> (gamma, beta, mean, var, eps) of a frozen
+        batch norm; sink: object with weight_grad(param, x, dy, k) [and bn_targets(name)] or None (no wgrad)."""
         self.ops = ops
         self.params = params
+        self.vectors = vectors
         self.sink = sink
         self.nodes = []
 
@@ -236,6 +238,291 @@ class Tape:
                 return
             a.grad = y.grad
             b.grad = y.grad
+
+        self.nodes.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ ops of the flow / attention backbones
+    def _own_or_add(self, var, g):
+        """Hand the freshly built gradient tensor ``g`` to ``var`` (ownership moves when it is the first one)."""
+        if not var.requires_grad:
+            return
+        if var.grad is None:
+            var.grad = g
+        else:
+            self.ops.copy(g, var.grad, True)
+
+    def _grad_slot(self, var, zero=False):
+        """(buffer, accumulate) to write ``var``'s gradient into; a fresh buffer is zeroed when ``zero``."""
+        if var.grad is None:
+            n, h, w, c = var.data.shape
+            var.grad = self.ops.zeros_act(n, h, w, c) if zero else self.ops.empty_act(n, h, w, c)
+            return var.grad, zero
+        return var.grad, True
+
+    def data(self, tensor):
+        """A constant (frames, warped inputs): no gradient flows into it."""
+        return Var(tensor, requires_grad=False)
+
+    def slice(self, x, c0, c1):
+        """Channel slice ``x[:, c0:c1]`` as a view (superslomo/model.py:597-598, rrin/model.py:83 ...)."""
+        ops = self.ops
+        x.consumers += 1
+        y = Var(x.data[..., c0:c1], requires_grad=x.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            if x.grad is None:
+                n, h, w, c = x.data.shape
+                x.grad = ops.zeros_act(n, h, w, c)
+            ops.copy(g, x.grad[..., c0:c1], True)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def lincomb(self, terms, const=0.0, out=None):
+        """y = sum_i coef_i * x_i + const (flow interpolation coefficients, mask affine maps)."""
+        ops = self.ops
+        y_data = out
+        for i, (coef, v) in enumerate(terms):
+            v.consumers += 1
+            y_data = ops.affine(v.data, coef, const if i == 0 else 0.0, out=y_data, accumulate=i > 0)
+        y = Var(y_data, requires_grad=any(v.requires_grad for _, v in terms))
+
+        def bwd():
+            g = y.grad
+            if g is None:
+                return
+            for coef, v in terms:
+                if not v.requires_grad:
+                    continue
+                buf, acc = self._grad_slot(v)
+                ops.affine(g, coef, 0.0, out=buf, accumulate=acc)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def warp(self, img, flow, variant, sx=1.0, sy=1.0, out=None):
+        """Bilinear backward warp of the constant image ``img`` (NHWC data) by the Var ``flow``."""
+        ops = self.ops
+        flow.consumers += 1
+        y = Var(ops.warp_fwd(img, flow.data, variant, sx, sy, out=out), requires_grad=flow.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not flow.requires_grad:
+                return
+            buf, acc = self._grad_slot(flow)
+            ops.warp_bwd(img, flow.data, g, buf, variant, sx, sy, accumulate=acc)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def act(self, x, kind, slope=0.0):
+        ops = self.ops
+        x.consumers += 1
+        y = Var(ops.act_fwd(x.data, kind, slope), requires_grad=x.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            ops.act_bwd(g, y.data, kind, slope)
+            self._own_or_add(x, g)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def clamp(self, x, lo, hi):
+        ops = self.ops
+        x.consumers += 1
+        y = Var(ops.clamp_fwd(x.data, lo, hi), requires_grad=x.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            buf, acc = self._grad_slot(x)
+            ops.clamp_bwd(g, x.data, buf, lo, hi, acc)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def blend(self, a, b, m0, m1, w0, w1, eps, mode, out=None):
+        """Visibility-weighted blend of two warped frames (include/mi_b200.h mi_blend_fwd)."""
+        ops = self.ops
+        parts = [v for v in (a, b, m0, m1) if v is not None]
+        for v in parts:
+            v.consumers += 1
+        y = Var(ops.blend_fwd(a.data, b.data, m0.data, None if m1 is None else m1.data, w0, w1, eps, mode, out=out))
+
+        def bwd():
+            g = y.grad
+            if g is None:
+                return
+            tg = []
+            for v in (a, b, m0, m1):
+                if v is None or not v.requires_grad:
+                    tg.append(None)
+                else:
+                    tg.append(self._grad_slot(v, zero=True)[0])
+            ops.blend_bwd(a.data, b.data, m0.data, None if m1 is None else m1.data, g, tg[0], tg[1], tg[2], tg[3],
+                          True, w0, w1, eps, mode)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def to_nchw(self, x, y0, x0, h, w):
+        """Crop window of an NHWC Var as the NCHW prediction (the paddingOutput of every backbone)."""
+        ops = self.ops
+        x.consumers += 1
+        y = Var(ops.nhwc_window_to_nchw(x.data, y0, x0, h, w))
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            assert x.grad is None, "the cropped tensor has a single consumer"
+            n, hh, ww, c = x.data.shape
+            full = (y0 == 0 and x0 == 0 and hh == h and ww == w)
+            x.grad = ops.empty_act(n, hh, ww, c) if full else ops.zeros_act(n, hh, ww, c)
+            ops.nchw_to_nhwc_window(g.contiguous(), x.grad, y0, x0)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def concat(self, buf, parts, consts=()):
+        """Var over the concat buffer ``buf``: ``parts`` = [(Var, c0, c1)] were produced in place (``out=`` slices),
+        ``consts`` = [(tensor, c0, c1)] are constants copied in now."""
+        for tsr, c0, c1 in consts:
+            self.ops.copy(tsr, buf[..., c0:c1], False)
+        return self.as_var_of_slices(buf, parts)
+
+    def bn(self, x, name, act=ACT_NONE, slope=0.0, out=None):
+        """Frozen batch norm + activation (voxel_flow.py:352-355: BN layers always run in eval mode)."""
+        ops = self.ops
+        gamma, beta, mean, var, eps = self.vectors(name)
+        x.consumers += 1
+        y = Var(ops.bn_eval_fwd(x.data, gamma, beta, mean, var, eps, act, slope, out=out))
+
+        def bwd():
+            dy = y.grad
+            if dy is None:
+                return
+            tg = self.sink.bn_targets(name) if self.sink is not None else None
+            dgamma, dbeta, mode, scale = tg if tg is not None else (None, None, 0, 1.0)
+            dx, acc = (None, False)
+            if x.requires_grad:
+                dx, acc = self._grad_slot(x)
+            if dx is not None or dgamma is not None:
+                ops.bn_eval_bwd(dy, y.data, x.data, gamma, mean, var, eps, act, slope, dx, acc, dgamma, dbeta, mode,
+                                scale)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def ring_conv(self, x, name, act=ACT_NONE, slope=0.0, ring_mode=1):
+        """Convolution over a ringed buffer: the ring of ``x`` is filled in place (zeros or reflection), the
+        zero-padding engine runs over the whole buffer and only the interior of the result is meaningful
+        (MetaConvNorm = ReflectionPad2d(1) + conv, model_utils.py:821-849)."""
+        ops = self.ops
+        p = self.params(name)
+        k = p.w.shape[1]
+        x.consumers += 1
+        ops.ring_fix(x.data, ring_mode)
+        y = Var(ops.conv_fprop(x.data, p.w, p.b, act, slope))
+        y.act, y.slope = act, slope
+
+        def bwd():
+            dy = y.grad
+            if dy is None:
+                return
+            ops.ring_fix(dy, ops.RING_ZERO)      # ring outputs are never consumed
+            if act != ACT_NONE and not y.grad_masked:
+                ops.act_bwd(dy, y.data, act, slope)
+            if x.requires_grad:
+                if x.consumers == 1 and x.act != ACT_NONE and x.grad is None:
+                    g = ops.conv_dgrad(dy, p.w, wt=p.wt(ops), mask_y=x.data, mask_act=x.act, mask_slope=x.slope)
+                    ops.ring_fold(g, ring_mode)
+                    x.grad = g
+                    x.grad_masked = True
+                else:
+                    g = ops.conv_dgrad(dy, p.w, wt=p.wt(ops))
+                    ops.ring_fold(g, ring_mode)
+                    self._own_or_add(x, g)
+            if self.sink is not None:
+                self.sink.weight_grad(p, x.data, dy, k)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def interior_mean(self, x, ring):
+        """Global average pool over the interior of a ringed buffer -> [n,1,1,c] (MetaCALayer, model_utils.py:947)."""
+        ops = self.ops
+        n, h, w, c = x.data.shape
+        scale = 1.0 / ((h - 2 * ring) * (w - 2 * ring))
+        x.consumers += 1
+        y = Var(ops.interior_reduce(x.data, None, ring, scale))
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            if x.grad is None:
+                x.grad = ops.zeros_act(n, h, w, c)
+            ops.interior_bcast_add(g, x.grad, ring, scale)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def scale_add(self, o, s, res, ring):
+        """out = o * s[n,c] + res (channel attention rescale + residual, model_utils.py:955,985)."""
+        ops = self.ops
+        for v in (o, s, res):
+            v.consumers += 1
+        y = Var(ops.scale_add(o.data, s.data, res.data))
+
+        def bwd():
+            g = y.grad
+            if g is None:
+                return
+            assert s.grad is None
+            s.grad = ops.interior_reduce(g, o.data, ring, 1.0)
+            if o.requires_grad:
+                buf, acc = self._grad_slot(o)
+                ops.scale_bwd(g, s.data, buf, acc)
+            self._own_or_add(res, g)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def depth_to_space(self, x, mean0, mean1, h, w, pad_top, pad_left, r):
+        """Ringed NHWC features -> cropped NCHW image + mean shift (cain/model.py:84-94, model_utils.py:202-217)."""
+        ops = self.ops
+        x.consumers += 1
+        y = Var(ops.depth_to_space(x.data, mean0, mean1, h, w, pad_top, pad_left, r))
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            assert x.grad is None, "the shuffled tensor has a single consumer"
+            x.grad = ops.empty_like_act(x.data)
+            ops.depth_to_space_bwd(g.contiguous(), x.grad, pad_top, pad_left, r)
+            y.grad = None
 
         self.nodes.append(bwd)
         return y

@@ -267,6 +267,123 @@ class RefOps:
         out.add_(y) if accumulate else out.copy_(y)
         return out
 
+    # ------------------------------------------------------------------ heads of the flow / attention backbones
+    BLEND_RATIO, BLEND_RATIO_COMPLEMENT, BLEND_LERP = 0, 1, 2
+    RING_ZERO, RING_REFLECT = 0, 1
+
+    def _out(self, y, out):
+        if out is None:
+            out = self.empty_act(*y.shape)
+        out.copy_(y)
+        return out
+
+    def act_fwd(self, x, act, slope=0.0, out=None):
+        return self._out(act_apply(x, act, slope), out)
+
+    def clamp_fwd(self, x, lo, hi, out=None):
+        return self._out(x.clamp(lo, hi), out)
+
+    def clamp_bwd(self, dy, x, dx, lo, hi, accumulate):
+        g = dy * ((x >= lo) & (x <= hi)).to(dy.dtype)
+        dx.add_(g) if accumulate else dx.copy_(g)
+
+    @staticmethod
+    def _blend(a, b, m0, m1, w0, w1, eps, mode):
+        if mode == 2:
+            return m0 * a + (1 - m0) * b
+        if mode == 1:
+            m1 = 1 - m0
+        return (w0 * m0 * a + w1 * m1 * b) / (w0 * m0 + w1 * m1 + eps)
+
+    def blend_fwd(self, a, b, m0, m1, w0, w1, eps, mode, out=None):
+        return self._out(self._blend(a, b, m0, m1, w0, w1, eps, mode), out)
+
+    @torch.enable_grad()
+    def blend_bwd(self, a, b, m0, m1, go, ga, gb, gm0, gm1, accumulate, w0, w1, eps, mode):
+        ins = [t.detach().clone().requires_grad_(True) for t in (a, b, m0)]
+        m1v = m1.detach().clone().requires_grad_(True) if (mode == 0) else None
+        y = self._blend(ins[0], ins[1], ins[2], m1v, w0, w1, eps, mode)
+        wrt = ins + ([m1v] if m1v is not None else [])
+        grads = torch.autograd.grad(y, wrt, go)
+        for tgt, g in zip((ga, gb, gm0, gm1), list(grads) + [None] * (4 - len(grads))):
+            if tgt is not None and g is not None:
+                tgt.add_(g) if accumulate else tgt.copy_(g)
+
+    def ring_fix(self, x, mode):
+        inner = _nchw(x[:, 1:-1, 1:-1, :])
+        y = F.pad(inner, [1, 1, 1, 1], mode="reflect") if mode == 1 else F.pad(inner, [1, 1, 1, 1])
+        x.copy_(_nhwc(y))
+
+    @torch.enable_grad()
+    def ring_fold(self, g, mode):
+        n, h, w, c = g.shape
+        if mode == 1:
+            inner = torch.zeros(n, c, h - 2, w - 2, dtype=g.dtype, requires_grad=True)
+            y = F.pad(inner, [1, 1, 1, 1], mode="reflect")
+            (gi,) = torch.autograd.grad(y, inner, _nchw(g))
+        else:
+            gi = _nchw(g[:, 1:-1, 1:-1, :])
+        g.copy_(_nhwc(F.pad(gi.detach(), [1, 1, 1, 1])))
+
+    def channel_mean_nchw(self, f):
+        return f.mean(2).mean(2).reshape(-1)
+
+    def space_to_depth(self, f0, f1, mean0, mean1, pad_top, pad_left, oh, ow, r):
+        n, c, h, w = f0.shape
+        pads = [pad_left, ow * r - w - pad_left, pad_top, oh * r - h - pad_top]
+        outs = []
+        for f, m in ((f0, mean0), (f1, mean1)):
+            x = f - m.view(n, c, 1, 1)
+            if any(pads):
+                x = F.pad(x, pads, mode="reflect")
+            v = x.contiguous().view(n, c, oh, r, ow, r).permute(0, 1, 3, 5, 2, 4).contiguous()
+            outs.append(v.view(n, c * r * r, oh, ow))
+        y = F.pad(torch.cat(outs, 1), [1, 1, 1, 1])
+        out = self.empty_act(n, oh + 2, ow + 2, 2 * c * r * r)
+        out.copy_(_nhwc(y))
+        return out
+
+    def depth_to_space(self, x, mean0, mean1, h, w, pad_top, pad_left, r):
+        n, hh, ww, c = x.shape
+        ih, iw = hh - 2, ww - 2
+        inner = _nchw(x[:, 1:-1, 1:-1, :]).contiguous()
+        oc = c // (r * r)
+        y = inner.view(n, oc, r, r, ih, iw).permute(0, 1, 4, 2, 5, 3).contiguous().view(n, oc, ih * r, iw * r)
+        y = y[:, :, pad_top:pad_top + h, pad_left:pad_left + w]
+        return (y + 0.5 * (mean0 + mean1).view(n, oc, 1, 1)).contiguous()
+
+    def depth_to_space_bwd(self, gout, gin, pad_top, pad_left, r):
+        n, oc, h, w = gout.shape
+        _, hh, ww, c = gin.shape
+        ih, iw = hh - 2, ww - 2
+        full = torch.zeros(n, oc, ih * r, iw * r, dtype=gout.dtype)
+        full[:, :, pad_top:pad_top + h, pad_left:pad_left + w] = gout
+        v = full.view(n, oc, ih, r, iw, r).permute(0, 1, 3, 5, 2, 4).contiguous().view(n, c, ih, iw)
+        gin.copy_(_nhwc(F.pad(v, [1, 1, 1, 1])))
+
+    def interior_reduce(self, x, mul, ring, scale):
+        n, h, w, c = x.shape
+        v = x if mul is None else x * mul
+        if ring:
+            v = v[:, ring:h - ring, ring:w - ring, :]
+        out = self.empty_act(n, 1, 1, c)
+        out.copy_(scale * v.sum(dim=(1, 2), keepdim=True))
+        return out
+
+    def scale_add(self, o, s, res, out=None):
+        y = o * s
+        if res is not None:
+            y = y + res
+        return self._out(y, out)
+
+    def scale_bwd(self, g, s, dx, accumulate):
+        v = g * s
+        dx.add_(v) if accumulate else dx.copy_(v)
+
+    def interior_bcast_add(self, dy, dx, ring, scale):
+        n, h, w, c = dx.shape
+        dx[:, ring:h - ring, ring:w - ring, :].add_(dy * scale)
+
     # ------------------------------------------------------------------ frames in / prediction out
     def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
         n, c, h, w = f0.shape
@@ -325,10 +442,11 @@ class RefOps:
         return torch.stack((gx + sx * u, gy + sy * v), dim=3), dict(mode="bilinear", padding_mode="border",
                                                                     align_corners=True)
 
-    def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0):
+    def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0, out=None):
         grid, kw = self._warp_grid(flow, variant, sx, sy)
         y = _nhwc(F.grid_sample(_nchw(img), grid, **kw))
-        out = self.empty_act(*y.shape)
+        if out is None:
+            out = self.empty_act(*y.shape)
         out.copy_(y)
         return out
 

@@ -96,7 +96,8 @@ def test_seeded_init_digest_matches_reference_fixture():
 
 
 @pytest.mark.parametrize("name", ["sepconv_lslr_sgd_k2", "sepconv_lslr_learnable_msl_k2", "sepconv_metasgd_adamax_k2",
-                                  "sepconv_l2f_sgd_k1"])
+                                  "sepconv_l2f_sgd_k1", "voxelflow_lslr_sgd_k1_mse", "superslomo_metasgd_sgd_k2",
+                                  "rrin_msl_learnable_k2", "rrin_lslr_sgd_k1_ragged", "cain_l2f_sgd_k1"])
 def test_oracle_reproduces_reference_golden(name):
     """Outputs of the UNMODIFIED reference (tests/golden, made by oracle/make_golden.py) vs the oracle."""
     fx = load_golden(name)
@@ -111,6 +112,28 @@ def test_oracle_reproduces_reference_golden(name):
         assert torch.allclose(mine[0], d, rtol=1e-5, atol=1e-9), k
     for k, (d, head) in fx["post_digest"].items():
         assert torch.allclose(digest(ora.params[k])[0], d, rtol=1e-6, atol=1e-9), k
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("model,size", [("voxelflow", (40, 72)), ("superslomo", (72, 64)), ("rrin", (64, 136)),
+                                        ("cain", (128, 120))])
+def test_flow_oracles_equal_live_reference(model, size):
+    """The UNMODIFIED reference (ragged sizes: its reflection paddings are exercised) vs the restatement."""
+    from oracle import reference_shims as rs
+    system, args = rs.build_system(model=model, loss="1*L1", optimizer="SGD", number_of_training_steps_per_iter=1)
+    seeded = bb.seeded_params(model, args.random_seed)
+    init = {k: v.detach().clone() for k, v in system.net.named_parameters()}
+    assert list(init) == list(seeded) and all(torch.equal(init[k], seeded[k]) for k in init)
+    g = torch.Generator().manual_seed(7)
+    frames = [torch.rand(1, 3, *size, generator=g) - 0.4 for _ in range(7)]
+    ora = maml.OracleSystem(model, init, optimizer="SGD", num_steps=1)
+    loss, preds, _, _ = ora.run_train_iter(frames, 0)
+    losses, rpreds, _ = system.run_train_iter(frames, epoch=0, do_evaluation=False)
+    assert float(losses["loss"]) == pytest.approx(float(loss), abs=1e-7 * max(1.0, abs(float(loss))))
+    assert (rpreds[0] - preds[0]).abs().max().item() <= 1e-7 * max(1.0, preds[0].abs().max().item())
+    post = {k: v.detach() for k, v in system.net.named_parameters()}
+    assert max((post[k] - ora.params[k].detach()).abs().max().item() for k in post) <= 1e-9
 
 
 @pytest.mark.reference
