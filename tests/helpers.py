@@ -34,7 +34,10 @@ def digest(t):
 def oracle_from_fixture(fx):
     from oracle import backbones as bb, maml
     a = fx["args"]
-    return maml.OracleSystem(a["model"], bb.seeded_params(a["model"], a["random_seed"]), optimizer=a["optimizer"],
+    init = bb.seeded_params(a["model"], a["random_seed"])
+    if fx.get("weight_gain") is not None:
+        init = {k: (v * fx["weight_gain"] if v.dim() == 4 else v) for k, v in init.items()}
+    return maml.OracleSystem(a["model"], init, optimizer=a["optimizer"],
                              metasgd=a["metasgd"], num_steps=a["number_of_training_steps_per_iter"],
                              inner_lr=a["inner_lr"], outer_lr=a["outer_lr"],
                              learnable_lr=a["learnable_per_layer_per_step_inner_loop_learning_rate"], loss=a["loss"],
@@ -49,4 +52,9 @@ def system_from_fixture(fx, ops, **extra):
     system = SceneAdaptiveInterpolation(args, ops=ops)
     if fx.get("attenuator_state") is not None:
         system.attenuator.load_state_dict(fx["attenuator_state"])
+    if fx.get("weight_gain") is not None:      # fixture generated from a rescaled seeded init (oracle/make_golden.py)
+        with torch.no_grad():
+            for p in system.net.parameters():
+                if p.dim() == 4:
+                    p.mul_(fx["weight_gain"])
     return system

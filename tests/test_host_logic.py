@@ -108,7 +108,7 @@ def test_flow_plugins_names_init_forward_and_routing(ref_ops, model):
 
 FLOW_GOLDEN = ["voxelflow_lslr_sgd_k1_mse", "voxelflow_lslr_sgd_k2_ragged", "superslomo_metasgd_sgd_k2",
                "superslomo_lslr_sgd_k1_ragged", "rrin_msl_learnable_k2", "rrin_lslr_sgd_k1_ragged",
-               "cain_l2f_sgd_k1", "cain_lslr_sgd_k2_ragged"]
+               "cain_l2f_sgd_k1", "cain_lslr_sgd_k2_ragged", "cain_lslr_sgd_k2_gain04", "cain_l2f_sgd_k1_gain04"]
 
 
 @pytest.mark.parametrize("name", FLOW_GOLDEN)

@@ -81,3 +81,69 @@ def test_linearity_property_full_size_conv(cuda_ops):
     ya, yb = ops.conv_fprop(a, w, None), ops.conv_fprop(b, w, None)
     yab = ops.conv_fprop(ops.add(a, b), w, None)
     assert (yab - (ya + yb)).abs().max().item() <= 2e-2 * yab.abs().max().item()
+
+
+FLOW_GOLDEN = ["voxelflow_lslr_sgd_k1_mse", "voxelflow_lslr_sgd_k2_ragged", "superslomo_metasgd_sgd_k2",
+               "superslomo_lslr_sgd_k1_ragged", "rrin_msl_learnable_k2", "rrin_lslr_sgd_k1_ragged",
+               "cain_l2f_sgd_k1_gain04", "cain_lslr_sgd_k2_gain04"]
+
+
+def _run_flow_case(ops, name, fast, graphs, loss_tol, pred_tol):
+    fx = load_golden(name)
+    system = system_from_fixture(fx, ops, fast_path=fast, cuda_graphs=graphs)
+    if fast and not system.fast_path_supported():
+        assert fx["args"]["attenuate"]
+        pytest.skip("L2F runs on the compat path only")
+    frames = [f.cuda() for f in fx["frames"]]
+    n0 = ops.launch_count()
+    losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
+    torch.cuda.synchronize()
+    assert ops.launch_count() > n0
+    scale = max(1.0, fx["preds"].abs().max().item())
+    assert abs(float(losses["loss"].detach()) - fx["loss"]) <= loss_tol * max(1.0, abs(fx["loss"]))
+    assert (torch.cat(preds).cpu() - fx["preds"]).abs().max().item() <= pred_tol * scale
+    assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+    return system, fx
+
+
+@pytest.mark.parametrize("name", FLOW_GOLDEN)
+@pytest.mark.parametrize("fast,graphs", [(True, True), (False, False)])
+def test_flow_train_iter_against_reference_golden(cuda_ops, name, fast, graphs):
+    """BASELINE configs[0] (voxelflow K=1) and configs[2..4] in miniature: the CUDA path of the VoxelFlow /
+    SuperSloMo / RRIN / CAIN plugins against outputs of the unmodified reference (tests/golden, oracle/make_golden.py).
+    """
+    _run_flow_case(cuda_ops, name, fast, graphs, LOSS_TOL, PRED_TOL)
+
+
+@pytest.mark.parametrize("name", ["cain_l2f_sgd_k1", "cain_lslr_sgd_k2_ragged"])
+@pytest.mark.parametrize("engine", ["simt", "tc"])
+def test_cain_default_init_goldens(name, engine):
+    """CAIN at the reference's default init: 125 stacked xavier convs blow the activations up to |pred| ~ 1e2 (loss
+    ~ 20, PSNR < 0), so rounding differences are amplified a hundredfold.  The exact-fp32 SIMT engine must still
+    meet the standard tolerance; the TF32 tensor-core engine is held to 3 % of the (exploded) output scale here and
+    to the standard tolerance on the well-conditioned gain-0.4 fixtures above."""
+    from meta_interpolation_b200.ops import CudaOps, ENGINE_SIMT, ENGINE_AUTO
+    ops = CudaOps(engine=ENGINE_SIMT if engine == "simt" else ENGINE_AUTO)
+    if engine == "simt":
+        _run_flow_case(ops, name, False, False, LOSS_TOL, PRED_TOL)
+    else:
+        _run_flow_case(ops, name, False, False, 3e-2, 3e-2)
+
+
+@pytest.mark.parametrize("model,hw", [("superslomo", (256, 448)), ("rrin", (256, 448)), ("voxelflow", (128, 128))])
+def test_flow_full_size_second_iteration_is_finite_and_replays(cuda_ops, model, hw):
+    """BASELINE frame sizes through the graph path twice (capture, then replay): losses finite and the replay of
+    an identical batch from identical weights gives the identical loss (determinism of the captured step)."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    args = make_args(model=model, cuda=True, number_of_training_steps_per_iter=2, outer_lr=0.0, weight_decay=0.0,
+                     loss="1*L1")
+    s = SceneAdaptiveInterpolation(args, ops=cuda_ops)
+    g = torch.Generator().manual_seed(9)
+    frames = [torch.rand(1, 3, *hw, generator=g).cuda() for _ in range(7)]
+    vals = []
+    for it in range(3):
+        losses, preds, _ = s.run_train_iter(frames, epoch=0)
+        vals.append(float(losses["loss"]))
+        assert torch.isfinite(preds[0]).all()
+    assert all(v == v and abs(v) < 1e4 for v in vals)
+    assert abs(vals[1] - vals[2]) <= 1e-6 * max(1.0, abs(vals[1]))
