@@ -114,6 +114,22 @@ int mi_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* d
 int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners, mi_stream_t stream);
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                      int align_corners, mi_stream_t stream);
+/* Region-of-interest forms.  SepConv crops its prediction to the frame (modulePaddingOutput, sepconv/model.py:264-266,
+ * 350), so the four filter Subnets (:313-347) are only needed on the part of the padded canvas whose receptive field
+ * reaches the surviving window; the Subnet chain is evaluated on that crop.
+ *   mi_upsample2_window_*: x holds rows [ly0,ly0+h) x cols [lx0,lx0+wd) of a full_h x full_w grid, y holds rows
+ *   [hy0,hy0+oh) x cols [hx0,hx0+ow) of its x2 bilinear upsampling; weights are those of the FULL grid
+ *   (nn.Upsample(scale_factor=2, align_corners=True), sepconv/model.py:213-234), so results equal the full
+ *   evaluation wherever the sources lie inside x.
+ *   mi_window_copy: dst[dy0:dy0+h, dx0:dx0+wd] (+)= src[sy0:sy0+h, sx0:sx0+wd] (crop, and its adjoint). */
+int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners,
+                            int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
+                            mi_stream_t stream);
+int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
+                            int align_corners, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0,
+                            int hx0, mi_stream_t stream);
+int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, float* dst, int ldd, int dh, int dw,
+                   int dy0, int dx0, int n, int h, int wd, int c, int accumulate, mi_stream_t stream);
 /* y = a + b  (skip adds, sepconv/model.py:294-309) ; a,b,y may alias */
 int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t stream);
 /* dst (+)= src over a channel slice; used for concat/split and gradient fan-in */

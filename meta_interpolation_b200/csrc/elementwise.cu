@@ -154,77 +154,111 @@ __device__ __forceinline__ void up2_src(int o, int in_size, int align, int& i0, 
     t = s - (float)i0;
 }
 
+// Windowed form: the low-resolution buffer x holds rows [ly0, ly0+h) x cols [lx0, lx0+wd) of a full_h x full_w grid and
+// the output buffer y holds rows [hy0, hy0+oh) x cols [hx0, hx0+ow) of its x2 upsampling; interpolation weights are
+// those of the FULL grid (align_corners=True depends on the full size), so a cropped evaluation reproduces the
+// full one bit for bit wherever the sources lie inside the low-resolution window (the host checks that they do).
+// The plain x2 upsample is the window that covers everything.
+struct UpWin { int full_h, full_w, ly0, lx0, hy0, hx0, oh, ow; };
+
 __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
-                                     int wd, int c, int align, int vec) {
-    const int oh = h * 2, ow = wd * 2, cg = (c + 3) >> 2;
+                                     int wd, int c, int align, int vec, UpWin g) {
+    const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
+        const int gi = (int)(i % cg);
         long long p = i / cg;
         const int ox = (int)(p % ow); p /= ow;
         const int oy = (int)(p % oh);
         const int nn = (int)(p / oh);
-        const int valid = min(4, c - 4 * g);
+        const int valid = min(4, c - 4 * gi);
         int y0, y1, x0, x1; float ty, tx;
-        up2_src(oy, h, align, y0, y1, ty);
-        up2_src(ox, wd, align, x0, x1, tx);
-        const float* b = x + (long long)nn * h * wd * ldx + 4 * g;
+        up2_src(oy + g.hy0, g.full_h, align, y0, y1, ty);
+        up2_src(ox + g.hx0, g.full_w, align, x0, x1, tx);
+        y0 = min(max(y0 - g.ly0, 0), h - 1); y1 = min(max(y1 - g.ly0, 0), h - 1);
+        x0 = min(max(x0 - g.lx0, 0), wd - 1); x1 = min(max(x1 - g.lx0, 0), wd - 1);
+        const float* b = x + (long long)nn * h * wd * ldx + 4 * gi;
         const F4 v00 = ld4(b + ((long long)y0 * wd + x0) * ldx, valid, vec), v01 = ld4(b + ((long long)y0 * wd + x1) * ldx, valid, vec);
         const F4 v10 = ld4(b + ((long long)y1 * wd + x0) * ldx, valid, vec), v11 = ld4(b + ((long long)y1 * wd + x1) * ldx, valid, vec);
         F4 o;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             o.v[q] = (1.f - ty) * ((1.f - tx) * v00.v[q] + tx * v01.v[q]) + ty * ((1.f - tx) * v10.v[q] + tx * v11.v[q]);
-        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * g, o, valid, vec);
+        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * gi, o, valid, vec);
     }
 }
 
 // gather form of the transpose: each input pixel collects from the output pixels that read it.  Output o reads
 // inputs (i0,i1); the outputs that can touch input i lie within [2i-3, 2i+3]; membership is tested exactly.
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
-                                     int accumulate, int n, int h, int wd, int c, int align, int vec) {
-    const int oh = h * 2, ow = wd * 2, cg = (c + 3) >> 2;
+                                     int accumulate, int n, int h, int wd, int c, int align, int vec, UpWin g) {
+    const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
+        const int gi = (int)(i % cg);
         long long p = i / cg;
         const int xx = (int)(p % wd); p /= wd;
         const int yy = (int)(p % h);
         const int nn = (int)(p / h);
-        const int valid = min(4, c - 4 * g);
+        const int valid = min(4, c - 4 * gi);
+        const int gy = yy + g.ly0, gx = xx + g.lx0;          // position on the full low-resolution grid
         float wy[6]; int oy_[6]; int ny = 0;
-        for (int o = max(0, 2 * yy - 3); o <= min(oh - 1, 2 * yy + 3); ++o) {
-            int a, b; float t; up2_src(o, h, align, a, b, t);
+        for (int o = max(g.hy0, 2 * gy - 3); o <= min(g.hy0 + oh - 1, 2 * gy + 3); ++o) {
+            int a, b; float t; up2_src(o, g.full_h, align, a, b, t);
             float wgt = 0.f;
-            if (a == yy) wgt += 1.f - t;
-            if (b == yy) wgt += t;
-            if (wgt != 0.f && ny < 6) { wy[ny] = wgt; oy_[ny] = o; ++ny; }
+            if (a == gy) wgt += 1.f - t;
+            if (b == gy) wgt += t;
+            if (wgt != 0.f && ny < 6) { wy[ny] = wgt; oy_[ny] = o - g.hy0; ++ny; }
         }
         float wx[6]; int ox_[6]; int nx = 0;
-        for (int o = max(0, 2 * xx - 3); o <= min(ow - 1, 2 * xx + 3); ++o) {
-            int a, b; float t; up2_src(o, wd, align, a, b, t);
+        for (int o = max(g.hx0, 2 * gx - 3); o <= min(g.hx0 + ow - 1, 2 * gx + 3); ++o) {
+            int a, b; float t; up2_src(o, g.full_w, align, a, b, t);
             float wgt = 0.f;
-            if (a == xx) wgt += 1.f - t;
-            if (b == xx) wgt += t;
-            if (wgt != 0.f && nx < 6) { wx[nx] = wgt; ox_[nx] = o; ++nx; }
+            if (a == gx) wgt += 1.f - t;
+            if (b == gx) wgt += t;
+            if (wgt != 0.f && nx < 6) { wx[nx] = wgt; ox_[nx] = o - g.hx0; ++nx; }
         }
         F4 acc;
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc.v[q] = 0.f;
         for (int a = 0; a < ny; ++a)
             for (int b = 0; b < nx; ++b) {
-                const F4 v = ld4(dy + ((long long)(nn * oh + oy_[a]) * ow + ox_[b]) * lddy + 4 * g, valid, vec);
+                const F4 v = ld4(dy + ((long long)(nn * oh + oy_[a]) * ow + ox_[b]) * lddy + 4 * gi, valid, vec);
                 const float wgt = wy[a] * wx[b];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) acc.v[q] += wgt * v.v[q];
             }
-        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + 4 * g;
+        float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + 4 * gi;
         if (accumulate) {
             const F4 o = ld4(d, valid, vec);
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc.v[q] += o.v[q];
         }
         st4(d, acc, valid, vec);
+    }
+}
+
+// dst window (+)= src window, both NHWC buffers with their own extents (crop of a region of interest and its adjoint)
+__global__ void window_copy_kernel(const float* __restrict__ s, int lds, int sh, int sw, int sy0, int sx0,
+                                   float* __restrict__ d, int ldd, int dh, int dw, int dy0, int dx0, int n, int h,
+                                   int w, int c, int accumulate, int vec) {
+    const int cg = (c + 3) >> 2;
+    const long long total = (long long)n * h * w * cg;
+    GRID_STRIDE(i, total) {
+        const int gi = (int)(i % cg);
+        long long p = i / cg;
+        const int xx = (int)(p % w); p /= w;
+        const int yy = (int)(p % h);
+        const int nn = (int)(p / h);
+        const int valid = min(4, c - 4 * gi);
+        F4 v = ld4(s + (((long long)nn * sh + sy0 + yy) * sw + sx0 + xx) * lds + 4 * gi, valid, vec);
+        float* q4 = d + (((long long)nn * dh + dy0 + yy) * dw + dx0 + xx) * ldd + 4 * gi;
+        if (accumulate) {
+            const F4 o = ld4(q4, valid, vec);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v.v[q] += o.v[q];
+        }
+        st4(q4, v, valid, vec);
     }
 }
 
@@ -536,14 +570,45 @@ int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, i
                      mi_stream_t s) {
     if (!x || !y) return MI_ERR_BAD_ARG;
     const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
-    LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec);
+    const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
+    LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                      int align, mi_stream_t s) {
     if (!dy || !dx) return MI_ERR_BAD_ARG;
     const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
+    const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
     LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
-           vec);
+           vec, g);
+}
+static bool up_window_ok(int h, int wd, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0) {
+    return h >= 1 && wd >= 1 && oh >= 1 && ow >= 1 && ly0 >= 0 && lx0 >= 0 && hy0 >= 0 && hx0 >= 0 &&
+           ly0 + h <= full_h && lx0 + wd <= full_w && hy0 + oh <= 2 * full_h && hx0 + ow <= 2 * full_w;
+}
+int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align,
+                            int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0, mi_stream_t s) {
+    if (!x || !y || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0)) return MI_ERR_BAD_ARG;
+    const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
+    const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
+    LAUNCH(upsample2_fwd_kernel, (long long)n * oh * ow * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
+}
+int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
+                            int align, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
+                            mi_stream_t s) {
+    if (!dy || !dx || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0)) return MI_ERR_BAD_ARG;
+    const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
+    const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
+    LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
+           vec, g);
+}
+int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, float* dst, int ldd, int dh, int dw,
+                   int dy0, int dx0, int n, int h, int wd, int c, int accumulate, mi_stream_t s) {
+    if (!src || !dst || n < 1 || h < 1 || wd < 1 || c < 1 || sy0 < 0 || sx0 < 0 || dy0 < 0 || dx0 < 0 ||
+        sy0 + h > sh || sx0 + wd > sw || dy0 + h > dh || dx0 + wd > dw)
+        return MI_ERR_BAD_ARG;
+    const int vec = mi_vec_ok(src, lds, c) && mi_vec_ok(dst, ldd, c);
+    LAUNCH(window_copy_kernel, (long long)n * h * wd * ((c + 3) / 4), s, src, lds, sh, sw, sy0, sx0, dst, ldd, dh, dw, dy0,
+           dx0, n, h, wd, c, accumulate, vec);
 }
 int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t s) {
     if (!a || !b || !y) return MI_ERR_BAD_ARG;

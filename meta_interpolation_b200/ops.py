@@ -224,6 +224,31 @@ class CudaOps:
         _lib.check(self.lib.mi_upsample2_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n, h, w,
                                              c, int(align_corners), self._stream()), "mi_upsample2_bwd")
 
+    def upsample_window_fwd(self, x, align_corners, full_hw, lo_origin, hi_origin, hi_hw):
+        """x = rows/cols [lo_origin, +x.shape) of a full_hw grid -> rows/cols [hi_origin, +hi_hw) of its x2 upsampling."""
+        n, h, w, c = x.shape
+        y = self.empty_act(n, hi_hw[0], hi_hw[1], c)
+        _lib.check(self.lib.mi_upsample2_window_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c,
+                                                    int(align_corners), full_hw[0], full_hw[1], lo_origin[0],
+                                                    lo_origin[1], hi_hw[0], hi_hw[1], hi_origin[0], hi_origin[1],
+                                                    self._stream()), "mi_upsample2_window_fwd")
+        return y
+
+    def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin):
+        n, h, w, c = dx.shape
+        _lib.check(self.lib.mi_upsample2_window_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n,
+                                                    h, w, c, int(align_corners), full_hw[0], full_hw[1], lo_origin[0],
+                                                    lo_origin[1], dy.shape[1], dy.shape[2], hi_origin[0], hi_origin[1],
+                                                    self._stream()), "mi_upsample2_window_bwd")
+
+    def window_copy(self, src, src_origin, dst, dst_origin, hw, accumulate=False):
+        """dst[:, dy0:dy0+h, dx0:dx0+w] (+)= src[:, sy0:sy0+h, sx0:sx0+w] between two NHWC buffers."""
+        n, sh, sw, c = src.shape
+        _, dh, dw, _ = dst.shape
+        _lib.check(self.lib.mi_window_copy(src.data_ptr(), _ld(src), sh, sw, src_origin[0], src_origin[1],
+                                           dst.data_ptr(), _ld(dst), dh, dw, dst_origin[0], dst_origin[1], n, hw[0],
+                                           hw[1], c, int(accumulate), self._stream()), "mi_window_copy")
+
     def add(self, a, b, out=None):
         n, h, w, c = a.shape
         y = out if out is not None else self.empty_act(n, h, w, c)

@@ -32,8 +32,34 @@ def canvas_size(height, width, border=25):
     return ph, pw
 
 
+def _up2_sources(o, in_size):
+    """(i0, i1) read by output index ``o`` of the x2 align_corners=True upsample (fp32 arithmetic of the kernel)."""
+    import numpy as np
+    out_size = 2 * in_size
+    scale = np.float32(in_size - 1) / np.float32(out_size - 1) if out_size > 1 else np.float32(0)
+    i0 = min(int(scale * np.float32(o)), in_size - 1)
+    return i0, i0 + (1 if i0 < in_size - 1 else 0)
+
+
+def _axis_roi(win0, win_len, full_hi, convs_low=3):
+    """One axis of the Subnet region of interest.  The separable convolution reads its filters on canvas positions
+    [win0, win0+win_len) only (the crop of sepconv/model.py:350).  Walking the Subnet backwards: the final 3x3 conv
+    needs one more position on each side (hi window); its x2 upsample reads low-resolution sources i0..i1 of that
+    window; the three 3x3 convs below need ``convs_low`` more on each side (low window).  Windows are clipped at the
+    canvas, where the zero padding of the full evaluation applies unchanged.  Returns (hi0, hi_len, lo0, lo_len)."""
+    full_lo = full_hi // 2
+    hi0, hi1 = max(win0 - 1, 0), min(win0 + win_len + 1, full_hi)            # [hi0, hi1)
+    src0, src1 = _up2_sources(hi0, full_lo)[0], _up2_sources(hi1 - 1, full_lo)[1]
+    lo0, lo1 = max(src0 - convs_low, 0), min(src1 + convs_low + 1, full_lo)
+    for o in range(hi0, hi1):       # every source of the hi window lies inside the low window (no clamping)
+        a, b = _up2_sources(o, full_lo)
+        assert lo0 <= a and b < lo1
+    return hi0, hi1 - hi0, lo0, lo1 - lo0
+
+
 class MetaNetwork(MetaBackbone):
     FILTER = 51
+    SUBNET_ROI = True   # evaluate the four Subnets only where the cropped prediction can see them
 
     def __init__(self, resume=False, strModel='lf', ops=None):
         super().__init__(ops)
@@ -92,11 +118,14 @@ class MetaNetwork(MetaBackbone):
     def _up(self, t, x, name):
         return t.conv(t.upsample(x, True), name + ".1", ACT_RELU)
 
-    def _subnet(self, t, x, name):
+    def _subnet(self, t, x, name, roi=None):
         x = t.conv(x, name + ".0", ACT_RELU)
         x = t.conv(x, name + ".2", ACT_RELU)
         x = t.conv(x, name + ".4", ACT_RELU)
-        x = t.upsample(x, True)
+        if roi is None:
+            x = t.upsample(x, True)
+        else:
+            x = t.upsample_window(x, True, roi["full_lo"], roi["lo_origin"], roi["hi_origin"], roi["hi_hw"])
         return t.conv(x, name + ".7", ACT_NONE)
 
     def build_graph(self, t, frame0, frame1):
@@ -120,11 +149,24 @@ class MetaNetwork(MetaBackbone):
         d2 = self._basic(t, comb, "moduleDeconv2")
         comb = t.add(self._up(t, d2, "moduleUpsample2"), c2)
 
-        v1 = self._subnet(t, comb, "moduleVertical1")
-        h1 = self._subnet(t, comb, "moduleHorizontal1")
-        v2 = self._subnet(t, comb, "moduleVertical2")
-        h2 = self._subnet(t, comb, "moduleHorizontal2")
+        # Region of interest: the prediction is cropped to canvas rows [25, 25+H) x cols [25, 25+W)
+        # (modulePaddingOutput, reference :264-266, :350), so the filters outside that window are dead values.  The
+        # Subnets (52 % of the backbone's FLOPs) run on the crop of `comb` whose receptive field covers the window;
+        # inside the window every value equals the full-canvas evaluation (3 pixels of slack absorb the wrong zero
+        # padding at the crop edges), and gradients vanish identically outside it.
+        roi, gy0, gx0 = None, 25, 25
+        if self.SUBNET_ROI:
+            hy0, hh, ly0, lh = _axis_roi(25, height, ch)
+            hx0, hw, lx0, lw = _axis_roi(25, width, cw)
+            if lh * lw < (ch // 2) * (cw // 2):
+                roi = dict(full_lo=(ch // 2, cw // 2), lo_origin=(ly0, lx0), hi_origin=(hy0, hx0), hi_hw=(hh, hw))
+                comb = t.crop(comb, ly0, lx0, lh, lw)
+                gy0, gx0 = 25 - hy0, 25 - hx0
+        v1 = self._subnet(t, comb, "moduleVertical1", roi)
+        h1 = self._subnet(t, comb, "moduleHorizontal1", roi)
+        v2 = self._subnet(t, comb, "moduleVertical2", roi)
+        h2 = self._subnet(t, comb, "moduleHorizontal2", roi)
         # output pixel (i,j) = canvas pixel (i+25, j+25); its 51x51 window starts at frame (i-25, j-25)
-        dot1 = t.sepconv(frame0, v1, h1, height, width, 25, 25, -25, -25)
-        dot2 = t.sepconv(frame1, v2, h2, height, width, 25, 25, -25, -25)
+        dot1 = t.sepconv(frame0, v1, h1, height, width, gy0, gx0, -25, -25)
+        dot2 = t.sepconv(frame1, v2, h2, height, width, gy0, gx0, -25, -25)
         return t.add_nchw(dot1, dot2)

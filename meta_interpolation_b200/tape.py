@@ -152,6 +152,46 @@ class Tape:
         self.nodes.append(bwd)
         return y
 
+    def crop(self, x, y0, x0, h, w):
+        """Contiguous copy of the window x[:, y0:y0+h, x0:x0+w]; its gradient is zero outside the window."""
+        ops = self.ops
+        x.consumers += 1
+        n, _, _, c = x.data.shape
+        buf = ops.empty_act(n, h, w, c)
+        ops.window_copy(x.data, (y0, x0), buf, (0, 0), (h, w))
+        y = Var(buf, requires_grad=x.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            if x.grad is None:
+                x.grad = ops.zeros_act(*x.data.shape)
+            ops.window_copy(g, (0, 0), x.grad, (y0, x0), (h, w), accumulate=True)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def upsample_window(self, x, align_corners, full_hw, lo_origin, hi_origin, hi_hw):
+        """x2 bilinear upsample of a window of a larger grid, evaluated only on a window of the result."""
+        ops = self.ops
+        x.consumers += 1
+        y = Var(ops.upsample_window_fwd(x.data, align_corners, full_hw, lo_origin, hi_origin, hi_hw))
+
+        def bwd():
+            if y.grad is None or not x.requires_grad:
+                return
+            if x.grad is None:
+                x.grad = ops.empty_like_act(x.data)
+                ops.upsample_window_bwd(y.grad, x.grad, align_corners, False, full_hw, lo_origin, hi_origin)
+            else:
+                ops.upsample_window_bwd(y.grad, x.grad, align_corners, True, full_hw, lo_origin, hi_origin)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
     def add(self, a, b):
         ops = self.ops
         a.consumers += 1

@@ -192,6 +192,32 @@ class RefOps:
         g = _nhwc(g)
         dx.add_(g) if accumulate else dx.copy_(g)
 
+    def upsample_window_fwd(self, x, align_corners, full_hw, lo_origin, hi_origin, hi_hw):
+        """Reference = the FULL x2 upsampling of the window embedded in a zero grid, then cropped."""
+        n, h, w, c = x.shape
+        full = torch.zeros(n, full_hw[0], full_hw[1], c, dtype=x.dtype)
+        full[:, lo_origin[0]:lo_origin[0] + h, lo_origin[1]:lo_origin[1] + w, :] = x
+        up = _nhwc(F.interpolate(_nchw(full), scale_factor=2, mode="bilinear", align_corners=bool(align_corners)))
+        y = self.empty_act(n, hi_hw[0], hi_hw[1], c)
+        y.copy_(up[:, hi_origin[0]:hi_origin[0] + hi_hw[0], hi_origin[1]:hi_origin[1] + hi_hw[1], :])
+        return y
+
+    @torch.enable_grad()
+    def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin):
+        n, h, w, c = dx.shape
+        xin = torch.zeros(n, h, w, c, dtype=dx.dtype, requires_grad=True)
+        full = F.pad(_nchw(xin), [lo_origin[1], full_hw[1] - lo_origin[1] - w, lo_origin[0],
+                                  full_hw[0] - lo_origin[0] - h])
+        up = F.interpolate(full, scale_factor=2, mode="bilinear", align_corners=bool(align_corners))
+        win = up[:, :, hi_origin[0]:hi_origin[0] + dy.shape[1], hi_origin[1]:hi_origin[1] + dy.shape[2]]
+        (g,) = torch.autograd.grad(win, xin, _nchw(dy))
+        dx.add_(g) if accumulate else dx.copy_(g)
+
+    def window_copy(self, src, src_origin, dst, dst_origin, hw, accumulate=False):
+        s = src[:, src_origin[0]:src_origin[0] + hw[0], src_origin[1]:src_origin[1] + hw[1], :]
+        d = dst[:, dst_origin[0]:dst_origin[0] + hw[0], dst_origin[1]:dst_origin[1] + hw[1], :]
+        d.add_(s) if accumulate else d.copy_(s)
+
     def add(self, a, b, out=None):
         if out is None:
             out = self.empty_act(*a.shape)

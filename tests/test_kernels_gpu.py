@@ -325,3 +325,68 @@ def test_bad_arguments_raise(cuda_ops):
     w = cuda_ops.empty_weight(4, 4, 3)
     with pytest.raises(MiB200Error):
         cuda_ops.conv_fprop(cuda_ops.empty_act(1, 4, 4, 4), w, None, engine=ENGINE_TC)   # ineligible shape for tcgen05
+
+
+@pytest.mark.parametrize("frame_hw", [(32, 32), (40, 56), (64, 64)])
+@pytest.mark.parametrize("c", [51, 64])
+def test_region_of_interest_upsample_and_crop(cuda_ops, frame_hw, c):
+    """Windowed x2 upsample (weights of the full grid) and window copy used by the SepConv Subnet region of interest:
+    equal to the full-canvas evaluation restricted to the window, and the backward is its exact adjoint."""
+    from meta_interpolation_b200.sepconv.model import _axis_roi, canvas_size
+    ch, cw = canvas_size(*frame_hw)
+    hy0, hh, ly0, lh = _axis_roi(25, frame_hw[0], ch)
+    hx0, hw, lx0, lw = _axis_roi(25, frame_hw[1], cw)
+    n = 2
+    fullc, fulld = act_pair(cuda_ops, n, ch // 2, cw // 2, c, 80)
+    # crop
+    cropc, cropd = REF.empty_act(n, lh, lw, c), cuda_ops.empty_act(n, lh, lw, c)
+    REF.window_copy(fullc, (ly0, lx0), cropc, (0, 0), (lh, lw))
+    cuda_ops.window_copy(fulld, (ly0, lx0), cropd, (0, 0), (lh, lw))
+    close(cropd, cropc, 0.0, "window_copy")
+    close(cropd, fullc[:, ly0:ly0 + lh, lx0:lx0 + lw, :], 0.0, "window_copy vs slice")
+    # windowed upsample == window of the full upsample
+    geo = dict(full_hw=(ch // 2, cw // 2), lo_origin=(ly0, lx0), hi_origin=(hy0, hx0))
+    upd = cuda_ops.upsample_window_fwd(cropd, True, hi_hw=(hh, hw), **geo)
+    full_up = cuda_ops.upsample_fwd(fulld, True)
+    close(upd, full_up[:, hy0:hy0 + hh, hx0:hx0 + hw, :].cpu(), 0.0, "windowed upsample vs full upsample (bit exact)")
+    close(upd, REF.upsample_window_fwd(cropc, True, hi_hw=(hh, hw), **geo), 2e-6, "windowed upsample vs reference")
+    # adjoint
+    gc, gd = act_pair(cuda_ops, n, hh, hw, c, 81)
+    for acc in (False, True):
+        dc, dd = act_pair(cuda_ops, n, lh, lw, c, 82)
+        REF.upsample_window_bwd(gc, dc, True, acc, **geo)
+        cuda_ops.upsample_window_bwd(gd, dd, True, acc, **geo)
+        close(dd, dc, 3e-6, "windowed upsample bwd")
+    # scatter back (adjoint of the crop) accumulates into the window only
+    bigc, bigd = act_pair(cuda_ops, n, ch // 2, cw // 2, c, 83)
+    REF.window_copy(cropc, (0, 0), bigc, (ly0, lx0), (lh, lw), accumulate=True)
+    cuda_ops.window_copy(cropd, (0, 0), bigd, (ly0, lx0), (lh, lw), accumulate=True)
+    close(bigd, bigc, 1e-6, "window accumulate")
+    with pytest.raises(Exception):
+        cuda_ops.window_copy(cropd, (0, 0), bigd, (ch // 2 - 1, 0), (lh, lw))
+
+
+def test_subnet_region_of_interest_equals_full_canvas(cuda_ops):
+    """SepConv forward + support-gradient with the Subnets on the region of interest vs on the full canvas: the
+    prediction is bit-identical (same kernels, same values inside the window) and the gradients agree to rounding
+    (split-K partitions differ with the buffer size)."""
+    from meta_interpolation_b200.sepconv.model import MetaNetwork
+    from oracle import backbones as bb
+    bb.set_torch_seed(12345)
+    net = MetaNetwork(ops=cuda_ops)
+    g = torch.Generator().manual_seed(4)
+    f0, f1, tgt = (torch.rand(1, 3, 72, 104, generator=g).cuda() for _ in range(3))
+    outs, grads = [], []
+    for roi in (True, False):
+        net.SUBNET_ROI = roi
+        fast = {k: v.detach().clone().requires_grad_(True) for k, v in net.named_parameters()}
+        out = net.forward(f0, f1, params=fast)
+        gr = torch.autograd.grad((out - tgt).abs().mean(), list(fast.values()), allow_unused=True)
+        outs.append(out.detach())
+        grads.append(gr)
+    net.SUBNET_ROI = True
+    assert (outs[0] - outs[1]).abs().max().item() <= 1e-6
+    for a, b in zip(*grads):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert (a - b).abs().max().item() <= 2e-3 * max(b.abs().max().item(), 1e-8)
