@@ -259,9 +259,18 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
         if (!is_b && (int)(e % ldw) >= cin) continue;  // pad lanes stay zero
         const float* src = is_b ? ws_b : ws_w;
         const long long stride = is_b ? cout : wsz;
-        float g = 0.f;
         const int ns = is_b ? bias_splits : splits;
-        for (int s = 0; s < ns; ++s) g += src[(long long)s * stride + e];
+        // four independent partial sums: the loads of a slice do not wait for the previous slice's add
+        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+        int s = 0;
+        for (; s + 3 < ns; s += 4) {
+            g0 += src[(long long)s * stride + e];
+            g1 += src[(long long)(s + 1) * stride + e];
+            g2 += src[(long long)(s + 2) * stride + e];
+            g3 += src[(long long)(s + 3) * stride + e];
+        }
+        for (; s < ns; ++s) g0 += src[(long long)s * stride + e];
+        const float g = (g0 + g1) + (g2 + g3);
         float* gout = is_b ? grad_b : grad_w;
         const float* pin = is_b ? b_in : w_in;
         float* pout = is_b ? b_out : w_out;
@@ -285,6 +294,15 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
 
 int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
     const long long m_total = (long long)n * h * wd;
+    if (mi_tc_wgrad_kx_shape(cin, cout, k)) {
+        // filter-column kernel: grid = (3, splits) persistent CTAs over 8x8-pixel tiles; one wave of the 148 SMs,
+        // at least four tiles per CTA so the pipeline fills
+        const long long tiles = (long long)n * mi_cdiv(h, 8) * mi_cdiv(wd, 8);
+        long long s = tiles / 4;
+        if (s > 49) s = 49;
+        if (s < 1) s = 1;
+        return (int)s;
+    }
     const long long base = (long long)k * k * mi_cdiv(cout, BN) * mi_cdiv(cin, BM);
     long long splits = (148 * 4 + base - 1) / base;
     const long long max_splits = (m_total + 255) / 256;

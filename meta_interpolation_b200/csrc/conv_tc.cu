@@ -795,6 +795,147 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.bn);
 }
 
+// ------------------------------------------------------------------------------------------ wgrad, small channels
+// The per-tap kernel above re-reads dY and X from L2 once per tap: 18 activation passes per layer, which is what
+// bounds it on the full-resolution 32/64-channel layers (ncu: ~10 TB/s of L2->SM traffic, M=128 MMAs with 32-64 real
+// rows).  For 3x3 layers with Cin <= 64 and Cout <= 128 a CTA owns one filter COLUMN kx and all three rows ky:
+//   * per 8(w) x R(h) pixel tile it loads dY once and ONE X box of R+2 rows shifted by kx-1 columns;
+//   * the three ky taps are the same box seen from a start address ky tile-rows (ky * 1024 B) further down -- a whole
+//     number of swizzle periods, so no descriptor trickery is involved -- and they are stacked along the MMA N
+//     dimension by setting the descriptor's MN-block stride (LBO) to one tile row: one 128 x 96 x 8 MMA per
+//     32-channel block and tile row computes D[cout][(ky, cin)] for all three ky at once.
+// L2 traffic drops from 18 to ~6.4 activation passes and the MMA count per pixel by 3x.
+struct WgradKxParams {
+    int n, h, w, cin, cout, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb;
+    float* ws_w;
+};
+
+__global__ void __launch_bounds__(NTHREADS)
+conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                        const WgradKxParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t row_bytes = 8u * ROW_BYTES;                       // one tile row: 8 pixels x 32 channels
+    const uint32_t a_box = (uint32_t)p.rows * row_bytes;             // dY box {32 ch, 8 px, R rows}
+    const uint32_t b_box = (uint32_t)(p.rows + 2) * row_bytes;       // X box  {32 ch, 8 px, R+2 rows}
+    const uint32_t a_bytes = (uint32_t)p.na * a_box, b_bytes = (uint32_t)p.nb * b_box;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    // the M=128 A descriptor always spans four 32-channel blocks; blocks past `na` alias whatever follows (the X
+    // boxes, the next stage, or the zeroed tail pad after the last stage) and only feed accumulator rows >= cout,
+    // which are never read back
+    const uint32_t tail_pad = 4u * a_box;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + tail_pad);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    const uint32_t tmem_cols = p.nb == 1 ? 128u : 256u;              // nb * 96 accumulator columns
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kx = blockIdx.x;
+    const int split = blockIdx.y;
+    const int t_begin = split * p.tiles_per_split;
+    const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
+    const int iters = max(t_end - t_begin, 0);
+
+    // finite contents for the aliased A blocks of the last stage
+    for (uint32_t i = threadIdx.x; i < tail_pad / 16; i += NTHREADS)
+        reinterpret_cast<float4*>(smem + (size_t)p.stages * stage_bytes)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[p.stages + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * p.stages]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // tail-pad stores visible to the MMA's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[p.stages + s]), ph ^ 1u);
+                int t = t_begin + it;
+                const int tx_i = t % p.tiles_x; t /= p.tiles_x;
+                const int ty_i = t % p.tiles_y; t /= p.tiles_y;
+                const int img = t;
+                const int x0 = tx_i * 8, y0 = ty_i * p.rows;
+                const uint32_t full = smem_u32(&bars[s]);
+                const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(full, stage_bytes);
+                for (int j = 0; j < p.na; ++j)
+                    tma_load_4d(base + j * a_box, &map_dy, full, j * KCH, x0, y0, img);
+                for (int j = 0; j < p.nb; ++j)
+                    tma_load_4d(base + a_bytes + j * b_box, &map_x, full, j * KCH, x0 + kx - 1, y0 - 1, img);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc(BM, 96, 1, 1);   // both operands MN-major, N = 3 taps x 32 channels
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(smem_u32(&bars[s]), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+                // A: 4 MN blocks (32 couts each) one dY box apart; B: 3 MN blocks (ky = 0,1,2) one tile row apart.
+                // K = 8 pixels = one tile row = two 4-pixel swizzle atoms 512 B apart (SBO).
+                const uint64_t ad0 = smem_desc(a_addr, a_box, 512, 1);
+                for (int j = 0; j < p.nb; ++j) {
+                    const uint64_t bd0 = smem_desc(b_addr + (uint32_t)j * b_box, row_bytes, 512, 1);
+                    const uint32_t d_addr = tmem_base + (uint32_t)(j * 96);
+                    for (int r = 0; r < p.rows; ++r)
+                        umma_tf32(d_addr, desc_advance(ad0, (uint32_t)r * row_bytes),
+                                  desc_advance(bd0, (uint32_t)r * row_bytes), idesc, (it > 0 || r > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bars[p.stages + s]));
+            }
+            umma_commit(smem_u32(&bars[2 * p.stages]));
+        }
+    } else {
+        const int q = warp & 3;
+        const int co = q * 32 + lane;
+        float* dst0 = p.ws_w + (long long)split * p.cout * 9 * p.ldw + (long long)co * 9 * p.ldw;
+        if (iters > 0) {
+            mbar_wait(smem_u32(&bars[2 * p.stages]), 0);
+            tc_fence_after();
+        }
+        for (int j = 0; j < p.nb; ++j) {
+            for (int ky = 0; ky < 3; ++ky) {
+                uint32_t v[32];
+                if (iters > 0) {
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 96 + ky * 32), v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0u;
+                }
+                if (co >= p.cout) continue;
+                const int cb = j * KCH;
+                float* dst = dst0 + (ky * 3 + kx) * p.ldw;
+                if (cb + 32 <= p.ldw) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        *(reinterpret_cast<float4*>(dst + cb) + g) =
+                            make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                        __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (cb + i < p.cin) dst[cb + i] = __uint_as_float(v[i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // column sums of dy for the bias gradient.  grid = (pixel slices, 32-channel groups); a block is 8 float4 channel
 // lanes x 32 pixel lanes with 4 independent loads in flight per thread (16 KB per block), so a few hundred blocks
 // keep enough bytes in flight to stream dy near HBM rate; one deterministic partial per (slice, channel).
@@ -1059,7 +1200,11 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
     const size_t stage_bytes = (size_t)(BM + p.bn) * ROW_BYTES;
     int stages = (int)((200 * 1024) / stage_bytes);
     if (stages > 6) stages = 6;
-    if (p.bn <= 128 && stages > 3) stages = 3;   // leave room for 2 CTAs per SM so epilogues overlap mainloops
+    // leave room for 2 CTAs per SM so epilogues overlap mainloops -- unless the grid cannot put two CTAs on an SM
+    // anyway (deep layers: 32-96 CTAs with 144-iteration K loops): there the pipeline depth is what hides the
+    // L2 latency (3 stages x 24 KB in flight measured ~50 GB/s per SM), so those take every stage that fits
+    const long long ctas = (long long)p.tiles_x * p.tiles_y * n * mi_cdiv(cout, p.bn);
+    if (p.bn <= 128 && stages > 3 && ctas > num_sms()) stages = 3;
     if (stages < 2) stages = 2;
     p.stages = stages;
     const size_t smem = stages * stage_bytes + (2 * stages + 2) * 8 + 1024;
@@ -1081,6 +1226,16 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
     MI_RETURN_LAST();
 }
 
+// 3x3, Cin <= 64, Cout <= 128: the filter-column kernel (MI_B200_WGRAD_KX=0 keeps the per-tap kernel: A/B switch)
+bool mi_tc_wgrad_kx_shape(int cin, int cout, int k) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MI_B200_WGRAD_KX");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on && k == 3 && cin <= 64 && cout <= 128 && device_is_sm100() && encode_fn();
+}
+
 bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
                           int k) {
     (void)n;
@@ -1093,6 +1248,52 @@ bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, in
 
 int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
                          int k, int ldw, float* ws_w, float* ws_b, int splits, cudaStream_t stream) {
+    if (mi_tc_wgrad_kx_shape(cin, cout, k)) {
+        WgradKxParams q;
+        q.n = n; q.h = h; q.w = wd; q.cin = cin; q.cout = cout; q.ldw = ldw;
+        q.rows = 8;
+        q.tiles_x = mi_cdiv(wd, 8);
+        q.tiles_y = mi_cdiv(h, q.rows);
+        q.total_tiles = q.tiles_x * q.tiles_y * n;
+        q.tiles_per_split = mi_cdiv(q.total_tiles, splits);
+        q.na = mi_cdiv(cout, KCH);
+        q.nb = mi_cdiv(cin, KCH);
+        q.ws_w = ws_w;
+        const size_t row_bytes = 8 * ROW_BYTES;
+        const size_t stage_bytes = (size_t)q.na * q.rows * row_bytes + (size_t)q.nb * (q.rows + 2) * row_bytes;
+        const size_t tail = 4 * (size_t)q.rows * row_bytes;
+        int stages = (int)((200 * 1024 - tail) / stage_bytes);
+        if (stages > 6) stages = 6;
+        if (stages < 2) return MI_ERR_UNSUPPORTED;
+        q.stages = stages;
+        const size_t smem = stages * stage_bytes + tail + (2 * stages + 2) * 8 + 1024;
+        CUtensorMap map_dy, map_x;
+        if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, 8, q.rows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return MI_ERR_UNSUPPORTED;
+        if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, 8, q.rows + 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return MI_ERR_UNSUPPORTED;
+        static bool attr_kx = false;
+        if (!attr_kx) {
+            cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(220 * 1024));
+            if (e != cudaSuccess) return (int)e;
+            attr_kx = true;
+        }
+        dim3 grid(3, splits);
+        mi_prof_begin(MI_TAG_WGRAD_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
+        conv_wgrad_tc_kx_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, q);
+        mi_prof_end(stream);
+        MI_LAUNCHED();
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) return (int)e;
+        const long long m_total = (long long)n * h * wd;
+        const int bsplits = mi_bias_splits(m_total);
+        const long long chunk = (m_total + bsplits - 1) / bsplits;
+        const int vec = mi_al16(dy) && (lddy % 4 == 0) && ((cout % 4 == 0) || lddy == ((cout + 3) & ~3));
+        bias_partial_kernel<<<dim3(bsplits, mi_cdiv(cout, 32)), 256, 0, stream>>>(dy, lddy, ws_b, cout, m_total, chunk, vec);
+        MI_LAUNCHED();
+        MI_RETURN_LAST();
+    }
     WgradParams p;
     p.n = n; p.h = h; p.w = wd; p.cin = cin; p.cout = cout; p.k = k; p.ldw = ldw;
     pick_tile(wd, 64, &p.pw, &p.ph);

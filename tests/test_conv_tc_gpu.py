@@ -22,6 +22,10 @@ TC_SHAPES = [
     (1, 17, 13, 40, 64, 3), (2, 200, 208, 64, 64, 3), (1, 130, 300, 32, 32, 3),
     # stem: 6 input channels (32-channel TMA box over a 6-channel tensor, zero-filled tail)
     (1, 8, 8, 6, 32, 3), (2, 40, 48, 6, 32, 3),
+    # filter-column weight-gradient kernel: Cout = 128 (four dY boxes), ragged Cout / Cin, one-tile layer,
+    # many tiles per CTA (stage wrap-around), width not a multiple of the 8-pixel tile
+    (2, 64, 72, 32, 128, 3), (1, 30, 50, 64, 100, 3), (1, 8, 8, 64, 64, 3), (2, 137, 233, 64, 64, 3),
+    (2, 96, 128, 51, 51, 3),
 ]
 
 
