@@ -41,42 +41,83 @@ __device__ __forceinline__ void stage_window(float* smem, const float* __restric
     }
 }
 
+// Forward.  The inner sum reads one staged value per FMA, so with one pixel per thread the kernel is bound by the
+// shared-memory pipe (one 32-lane LDS per cycle per SM against four FMA issue slots; ncu: LSU wavefronts 53 %, FMA 32 %).
+// Each thread therefore owns TWO vertically adjacent pixels (y, y+1): their windows share 50 of 51 rows, so every
+// staged value feeds two FMAs (one per pixel, each against its own register-resident horizontal filter), halving
+// the shared-memory traffic per output.  A block of 32 x 8 threads covers a 32 x 16 pixel tile.
+constexpr int FWD_PY = 2;
+
+template <int F>
+struct GeoF {
+    static constexpr int WIN_W = TX + F - 1;
+    static constexpr int WIN_H = TY * FWD_PY + F - 1;
+    static constexpr int PITCH = WIN_W + 1;
+};
+
 template <int F, int C>
-__global__ void __launch_bounds__(TX* TY)
+__global__ void __launch_bounds__(TX* TY, 2)
 sepconv_fwd_kernel(const float* __restrict__ frame, const float* __restrict__ vert, const float* __restrict__ horiz,
                    int ldf, float* __restrict__ out, int fh, int fw, int gh, int gw, int oh, int ow, int gy0, int gx0,
                    int iy0, int ix0) {
     extern __shared__ float smem[];
-    constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    constexpr int WW = GeoF<F>::WIN_W, WH = GeoF<F>::WIN_H, P = GeoF<F>::PITCH;
     const int n_idx = blockIdx.z;
     const int ty = threadIdx.x / TX, tx = threadIdx.x % TX;
-    const int oy_base = blockIdx.y * TY, ox_base = blockIdx.x * TX;
-    stage_window<F>(smem, frame, C, fh, fw, n_idx, oy_base + iy0, ox_base + ix0);
+    const int oy_base = blockIdx.y * (TY * FWD_PY), ox_base = blockIdx.x * TX;
+    {   // stage the (16+50) x (32+50) window of every channel; replicate border folded in
+        const long long plane = (long long)fh * fw;
+        const float* fb = frame + (long long)n_idx * C * plane;
+        for (int i = threadIdx.x; i < C * WH * WW; i += blockDim.x) {
+            const int col = i % WW;
+            const int r = (i / WW) % WH;
+            const int cc = i / (WW * WH);
+            const int sy = min(max(oy_base + iy0 + r, 0), fh - 1);
+            const int sx = min(max(ox_base + ix0 + col, 0), fw - 1);
+            smem[(cc * WH + r) * P + col] = fb[cc * plane + (long long)sy * fw + sx];
+        }
+    }
     __syncthreads();
-    const int oy = oy_base + ty, ox = ox_base + tx;
+    const int oy = oy_base + FWD_PY * ty, ox = ox_base + tx;
     if (oy >= oh || ox >= ow) return;
-    const long long gpix = ((long long)n_idx * gh + gy0 + oy) * gw + gx0 + ox;
-    const float* hp = horiz + gpix * ldf;
-    const float* vp = vert + gpix * ldf;
-    float hreg[F];
+    const bool two = oy + 1 < oh;                          // the second pixel of the pair exists
+    const long long gpix0 = ((long long)n_idx * gh + gy0 + oy) * gw + gx0 + ox;
+    const long long gpix1 = two ? gpix0 + gw : gpix0;      // (a missing partner re-reads pixel 0; result discarded)
+    const float* hp0 = horiz + gpix0 * ldf;
+    const float* hp1 = horiz + gpix1 * ldf;
+    const float* vp0 = vert + gpix0 * ldf;
+    const float* vp1 = vert + gpix1 * ldf;
+    float h0[F], h1[F];
 #pragma unroll
-    for (int f = 0; f < F; ++f) hreg[f] = __ldg(hp + f);
-    float acc[C];
+    for (int f = 0; f < F; ++f) { h0[f] = __ldg(hp0 + f); h1[f] = __ldg(hp1 + f); }
+    float acc0[C], acc1[C];
 #pragma unroll
-    for (int cc = 0; cc < C; ++cc) acc[cc] = 0.f;
-    for (int fy = 0; fy < F; ++fy) {
-        const float vv = __ldg(vp + fy);
+    for (int cc = 0; cc < C; ++cc) { acc0[cc] = 0.f; acc1[cc] = 0.f; }
+    // window row r (relative to pixel 0) is tap fy = r of pixel 0 and tap fy = r - 1 of pixel 1
+#pragma unroll 1
+    for (int r = 0; r <= F; ++r) {
+        const float v0 = r < F ? __ldg(vp0 + r) : 0.f;
+        const float v1 = r > 0 ? __ldg(vp1 + r - 1) : 0.f;
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) {
-            const float* row = smem + (cc * WH + ty + fy) * P + tx;
-            float t = 0.f;
+            const float* row = smem + (cc * WH + FWD_PY * ty + r) * P + tx;
+            float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-            for (int f = 0; f < F; ++f) t = fmaf(row[f], hreg[f], t);
-            acc[cc] = fmaf(vv, t, acc[cc]);
+            for (int f = 0; f < F; ++f) {
+                const float in = row[f];
+                t0 = fmaf(in, h0[f], t0);
+                t1 = fmaf(in, h1[f], t1);
+            }
+            acc0[cc] = fmaf(v0, t0, acc0[cc]);
+            acc1[cc] = fmaf(v1, t1, acc1[cc]);
         }
     }
 #pragma unroll
-    for (int cc = 0; cc < C; ++cc) out[(((long long)n_idx * C + cc) * oh + oy) * ow + ox] = acc[cc];
+    for (int cc = 0; cc < C; ++cc) {
+        float* o = out + (((long long)n_idx * C + cc) * oh + oy) * ow + ox;
+        o[0] = acc0[cc];
+        if (two) o[ow] = acc1[cc];
+    }
 }
 
 template <int F, int C>
@@ -212,14 +253,14 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
     cudaStream_t st = mi_cs(stream);
     if (taps == 51 && c == 3) {
         static bool attr_set = false;
-        const size_t sm = smem_bytes<51>(3);
+        const size_t sm = (size_t)3 * GeoF<51>::WIN_H * GeoF<51>::PITCH * sizeof(float);
         if (!attr_set) {
             cudaError_t e = cudaFuncSetAttribute(sepconv_fwd_kernel<51, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)sm);
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
-        dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY), n);
+        dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY * FWD_PY), n);
         const double px = (double)n * oh * ow;
         mi_prof_begin(MI_TAG_SEPCONV_FWD, 2.0 * px * (3 * 51 * 51 + 3 * 51), 4.0 * px * (2 * 51 + 3 + 3), st);
         sepconv_fwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, out, fh, fw, gh, gw, oh, ow, gy0,
