@@ -668,6 +668,203 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * p.bn));
 }
 
+// ------------------------------------------------------------------------------------------ fprop, mid/deep channels
+// 3x3 layers with more than 64 channels: the weights no longer fit in shared memory next to the halo ring, so they
+// are streamed -- but at the SAME granularity as the halo tile: one pipeline stage = the 18x10-pixel halo box of a
+// 32-channel chunk PLUS the nine {64 couts x 32 cin} weight tiles of that chunk, behind ONE mbarrier.  Measured on
+// B200 (per-role cycle counters): the MMA lane pays ~450 cycles of fixed cost per barrier wait (try_wait, fence,
+// elect, descriptor set-up, commit), so the per-tap kernel (4 MMAs per wait) and a per-tap weight ring (4-8 MMAs per
+// wait) both leave the tensor pipe idle 70 % of the time, while 36 MMAs per wait amortise it (this is why the
+// small-channel halo kernel is the fastest of the family).  Persistent CTAs walk (pixel tile, 64-cout tile) work
+// items; accumulators are double buffered in TMEM so the epilogue of one item overlaps the MMAs of the next.
+struct HaloStreamParams {
+    int n, h, w, cin, cout, chunks, n_tiles, tiles_x, tiles_y, total_tiles, items, act, accumulate, mask_act, ldy,
+        ldmask, halo_w;
+    uint32_t halo_bytes, halo_stride;
+    unsigned long long* dbg;            // optional per-role cycle counters of CTA 0 (MI_B200_DEBUG_TIMING=1)
+    float slope, mask_slope;
+    const float* bias;
+    const float* mask_y;
+    float* y;
+};
+constexpr int HS_BN = 64;        // cout tile of the streamed kernel
+constexpr int HS_STAGES = 2;
+
+__global__ void __launch_bounds__(NTHREADS)
+conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                                 const HaloStreamParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int S = HS_STAGES;
+    constexpr uint32_t b_tile = HS_BN * ROW_BYTES;                 // one (tap, chunk) weight tile: 8 KB
+    const uint32_t stage_bytes = p.halo_stride + 9u * b_tile;      // halo box + nine weight tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+    // bars: [0,S) full, [S,2S) empty, 2S..2S+1 tmem full[2], 2S+2..2S+3 tmem empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_start = clock64();
+
+    __shared__ float sbias[512];
+    __shared__ __align__(16) float epi_stage[4 * 32 * EPI_PITCH];
+    for (int i = threadIdx.x; i < 512; i += NTHREADS) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&bars[s]), 1);
+            mbar_init(smem_u32(&bars[S + s]), 1);
+        }
+        mbar_init(smem_u32(&bars[2 * S]), 1);
+        mbar_init(smem_u32(&bars[2 * S + 1]), 1);
+        mbar_init(smem_u32(&bars[2 * S + 2]), 128);
+        mbar_init(smem_u32(&bars[2 * S + 3]), 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * HS_BN));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        int it = 0;
+        long long w_e = 0;
+        for (int t = 0; t < my_items; ++t) {
+            const int item = (int)blockIdx.x + t * (int)gridDim.x;
+            const int nt = item % p.n_tiles;
+            int tile = item / p.n_tiles;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            const int img = tile;
+            for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                const int s = it % S;
+                const long long c0 = clock64();
+                mbar_wait(smem_u32(&bars[S + s]), (((uint32_t)(it / S)) & 1u) ^ 1u);
+                w_e += clock64() - c0;
+                if (elect_one()) {
+                    const uint32_t full = smem_u32(&bars[s]);
+                    const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
+                    mbar_expect_tx(full, p.halo_bytes + 9u * b_tile);
+                    tma_load_4d(base, &map_x, full, ch * KCH, tx_i * HT_W - 1, ty_i * HT_H - 1, img);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_3d(base + p.halo_stride + (uint32_t)tap * b_tile, &map_w, full, ch * KCH, tap,
+                                    nt * HS_BN);
+                }
+                __syncwarp();
+            }
+        }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+            p.dbg[0] = (unsigned long long)w_e; p.dbg[2] = (unsigned long long)(clock64() - t_start);
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = instr_desc(BM, HS_BN, 0, 0);
+        const int last_ksteps = (p.cin - (p.chunks - 1) * KCH + 7) / 8;
+        int it = 0;
+        long long w_f = 0, w_te = 0, t_first = 0;
+        for (int t = 0; t < my_items; ++t) {
+            const int buf = t & 1;
+            long long c0 = clock64();
+            mbar_wait(smem_u32(&bars[2 * S + 2 + buf]), (((uint32_t)(t >> 1)) & 1u) ^ 1u);   // epilogue drained it
+            w_te += clock64() - c0;
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + (uint32_t)(buf * HS_BN);
+            for (int ch = 0; ch < p.chunks; ++ch, ++it) {
+                const int s = it % S;
+                c0 = clock64();
+                mbar_wait(smem_u32(&bars[s]), ((uint32_t)(it / S)) & 1u);
+                w_f += clock64() - c0;
+                if (it == 0) t_first = clock64() - t_start;
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t ad0 = smem_desc(a_base, 16, (uint32_t)p.halo_w * ROW_BYTES);
+                    const uint64_t bd0 = smem_desc(a_base + p.halo_stride, 16, 1024);
+                    if (ch < p.chunks - 1 || last_ksteps == 4) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
+                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * b_tile);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+                                umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                          (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    } else {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int ky = tap / 3, kx = tap - ky * 3;
+                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
+                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * b_tile);
+                            for (int kk = 0; kk < last_ksteps; ++kk)
+                                umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                          (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(smem_u32(&bars[S + s]));
+                    if (ch == p.chunks - 1) umma_commit(smem_u32(&bars[2 * S + buf]));
+                }
+                __syncwarp();
+            }
+        }
+        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+            p.dbg[3] = (unsigned long long)w_f; p.dbg[5] = (unsigned long long)w_te;
+            p.dbg[6] = (unsigned long long)t_first; p.dbg[7] = (unsigned long long)(clock64() - t_start);
+        }
+    } else {
+        const int q = warp & 3;
+        const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                         (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
+        EpiArgs ea;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.slope = p.slope; ea.mask_slope = p.mask_slope;
+        const int c4 = (p.cout + 3) & ~3;
+        ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
+        const int r = q * 32 + lane;
+        const int th_i = r >> 3, tw_i = r & 7;
+        float* stage = epi_stage + q * 32 * EPI_PITCH;
+        long long e_wait = 0;
+        for (int t = 0; t < my_items; ++t) {
+            const int buf = t & 1;
+            const int item = (int)blockIdx.x + t * (int)gridDim.x;
+            const int nt = item % p.n_tiles;
+            const int co0 = nt * HS_BN;
+            int tile = item / p.n_tiles;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            const int img = tile;
+            const int oy = ty_i * HT_H + th_i, ox = tx_i * HT_W + tw_i;
+            const bool pix_ok = (oy < p.h) && (ox < p.w);
+            const long long pix = ((long long)img * p.h + oy) * p.w + ox;
+            float* yrow = p.y + pix * p.ldy;
+            const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
+            const long long c0 = clock64();
+            mbar_wait(smem_u32(&bars[2 * S + buf]), ((uint32_t)(t >> 1)) & 1u);
+            e_wait += clock64() - c0;
+            tc_fence_after();
+            RowMap rm;
+            rm.tw = HT_W; rm.y0 = ty_i * HT_H; rm.x0 = tx_i * HT_W; rm.h = p.h; rm.w = p.w; rm.img = img; rm.q = q;
+#pragma unroll
+            for (int c0i = 0; c0i < HS_BN; c0i += 32) {
+                if (co0 + c0i >= p.cout) break;                    // warp-uniform
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * HS_BN + c0i), v);
+                if (vec) epilogue_chunk_coalesced(v, sbias + co0 + c0i, co0 + c0i, ea, stage, lane, rm, p.mask_y, p.ldmask,
+                                                  p.y, p.ldy);
+                else if (pix_ok) epilogue_chunk(v, sbias + co0 + c0i, co0 + c0i, ea, mrow, yrow, vec);
+            }
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[2 * S + 2 + buf])) : "memory");
+        }
+        if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
+            p.dbg[8] = (unsigned long long)e_wait; p.dbg[9] = (unsigned long long)(clock64() - t_start);
+            p.dbg[10] = (unsigned long long)my_items;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * HS_BN));
+}
+
 // ------------------------------------------------------------------------------------------ wgrad partials
 struct WgradParams {
     int n, h, w, cin, cout, k, ldw, pw, ph, tiles_x, tiles_y, bn, stages, co_tiles, ci_tiles, tiles_per_split,
@@ -1092,6 +1289,16 @@ int halo_base_offset_mode() {
     return v;
 }
 
+// MI_B200_HALO_STREAM=0 keeps the per-tap kernel for the >64-channel 3x3 layers (A/B switch for profiling)
+bool halo_stream_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MI_B200_HALO_STREAM");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int halo_pitch() {
     static int v = -1;
     if (v < 0) {
@@ -1182,6 +1389,60 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
                         h[4], h[5], h[6], h[7], h[8], h[9], hp.stages, hp.bn, hp.chunks);
             }
             mi_prof_end(stream);
+            MI_LAUNCHED();
+            MI_RETURN_LAST();
+        }
+    }
+    if (k == 3 && (cin > 64 || cout > 64) && cout <= 512 && halo_stream_enabled()) {
+        HaloStreamParams hp;
+        hp.n = n; hp.h = h; hp.w = wd; hp.cin = cin; hp.cout = cout;
+        hp.chunks = mi_cdiv(cin, KCH);
+        hp.tiles_x = mi_cdiv(wd, HT_W);
+        hp.tiles_y = mi_cdiv(h, HT_H);
+        hp.total_tiles = hp.tiles_x * hp.tiles_y * n;
+        hp.n_tiles = mi_cdiv(cout, HS_BN);
+        hp.items = hp.total_tiles * hp.n_tiles;
+        hp.halo_w = halo_pitch();
+        hp.halo_bytes = (uint32_t)hp.halo_w * HALO_H * ROW_BYTES;
+        hp.halo_stride = (hp.halo_bytes + 1023u) & ~1023u;
+        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
+        hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
+        const size_t stage_bytes = (size_t)hp.halo_stride + 9 * (size_t)HS_BN * ROW_BYTES;
+        const size_t smem = HS_STAGES * stage_bytes + (2 * HS_STAGES + 5) * 8 + 1024;
+        if (smem <= 205 * 1024) {
+            CUtensorMap map_x, map_w;
+            if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, hp.halo_w, HALO_H)) return MI_ERR_UNSUPPORTED;
+            if (!make_weight_map(&map_w, w, ldw, cout, 9, cin, HS_BN)) return MI_ERR_UNSUPPORTED;
+            static bool attr = false;
+            if (!attr) {
+                cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_halo_stream_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(205 * 1024));
+                if (e != cudaSuccess) return (int)e;
+                attr = true;
+            }
+            const int grid = hp.items < num_sms() ? hp.items : num_sms();
+            static unsigned long long* dbg_buf = nullptr;
+            static int dbg_on = -1;
+            if (dbg_on < 0) { const char* e = getenv("MI_B200_DEBUG_TIMING"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+            hp.dbg = nullptr;
+            if (dbg_on) {
+                if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+                cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), stream);
+                hp.dbg = dbg_buf;
+            }
+            mi_prof_begin(MI_TAG_FPROP_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+                          stream);
+            conv_fprop_tc_halo_stream_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, hp);
+            mi_prof_end(stream);
+            if (dbg_on) {
+                unsigned long long d[16];
+                cudaStreamSynchronize(stream);
+                cudaMemcpy(d, dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[stream cta0] items=%llu n_tiles=%d chunks=%d grid=%d | producer: wait_empty=%llu total=%llu | "
+                        "mma: wait_full=%llu wait_tmem_empty=%llu first_data_at=%llu total=%llu | epilogue: wait_acc=%llu "
+                        "total=%llu cycles\n", d[10], hp.n_tiles, hp.chunks, grid, d[0], d[2], d[3], d[5], d[6], d[7], d[8],
+                        d[9]);
+            }
             MI_LAUNCHED();
             MI_RETURN_LAST();
         }

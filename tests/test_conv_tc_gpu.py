@@ -26,6 +26,10 @@ TC_SHAPES = [
     # many tiles per CTA (stage wrap-around), width not a multiple of the 8-pixel tile
     (2, 64, 72, 32, 128, 3), (1, 30, 50, 64, 100, 3), (1, 8, 8, 64, 64, 3), (2, 137, 233, 64, 64, 3),
     (2, 96, 128, 51, 51, 3),
+    # streamed-weights halo kernel (> 64 channels): two tiles per item, one tile per item with 128- and 64-wide cout
+    # tiles, odd tile counts (the last group re-reads a tile), ragged channels, the deepest SepConv layers
+    (2, 96, 128, 128, 128, 3), (2, 48, 64, 256, 256, 3), (2, 24, 32, 512, 512, 3), (2, 12, 16, 512, 512, 3),
+    (1, 40, 72, 128, 64, 3), (3, 33, 41, 96, 160, 3), (2, 96, 136, 64, 128, 3), (1, 50, 70, 200, 300, 3),
 ]
 
 

@@ -9,7 +9,11 @@ from meta_interpolation_b200.backbone import default_ops  # noqa: E402
 from meta_interpolation_b200.ops import ENGINE_TC, WG_STORE, WgradSpec, pad4  # noqa: E402
 
 SHAPES = [(2, 384, 512, 32, 32), (2, 384, 512, 51, 51), (2, 192, 256, 64, 64), (2, 192, 256, 64, 51),
-          (2, 96, 128, 128, 128), (2, 48, 64, 256, 256), (2, 24, 32, 512, 512), (2, 12, 16, 512, 512)]
+          (2, 96, 128, 128, 128), (2, 48, 64, 256, 256), (2, 24, 32, 512, 512), (2, 12, 16, 512, 512),
+          # region-of-interest Subnet shapes and the channel-changing mid layers
+          (2, 258, 450, 51, 51), (2, 137, 233, 64, 64), (2, 96, 128, 64, 128), (2, 96, 128, 128, 64),
+          (2, 48, 64, 128, 256), (2, 48, 64, 256, 128), (2, 48, 64, 128, 128), (2, 24, 32, 256, 512),
+          (2, 24, 32, 512, 256), (2, 24, 32, 256, 256)]
 
 
 def timeit(fn, iters=20):
@@ -28,7 +32,9 @@ def timeit(fn, iters=20):
 def main():
     ops = default_ops()
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    print("env HALO=%s" % os.environ.get("MI_B200_HALO"))
+    print("env HALO=%s HALO_STREAM=%s WGRAD_KX=%s" % (os.environ.get("MI_B200_HALO"),
+                                                      os.environ.get("MI_B200_HALO_STREAM"),
+                                                      os.environ.get("MI_B200_WGRAD_KX")))
     for (n, h, w, cin, cout) in SHAPES:
         x = ops.empty_act(n, h, w, cin); x.copy_(torch.rand(n, h, w, cin, device="cuda") - 0.5)
         dy = ops.empty_act(n, h, w, cout); dy.copy_(torch.rand(n, h, w, cout, device="cuda") - 0.5)
