@@ -93,13 +93,16 @@ size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k,
  *   w_in,b_in -> w_out,b_out : SGD modes (may alias)
  *   lr_w, lr_b : device pointers; scalar (mode 2) or same shape as w / b (mode 3)
  *   gsum_w,gsum_b : optional running sum of g over inner steps (Meta-SGD outer grad of alpha, SURVEY Appx E4)
- *   scale : multiplies g in ACCUM mode. */
+ *   scale : multiplies g in ACCUM mode.
+ *   wt_out, ldwt : optional (SGD modes only): the updated weight is also written in the dgrad layout of
+ *                  mi_weight_to_dgrad, so the next inner step needs no rotation launch. */
 int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy,
                     int n, int h, int wd, int cin, int cout, int k, int ldw,
                     int mode, float scale,
                     float* grad_w, float* grad_b,
                     const float* w_in, const float* b_in, float* w_out, float* b_out,
                     const float* lr_w, const float* lr_b, float* gsum_w, float* gsum_b,
+                    float* wt_out, int ldwt,
                     void* workspace, size_t workspace_bytes, int engine, mi_stream_t stream);
 
 /* ------------------------------------------------------------------ pointwise / resampling

@@ -28,7 +28,7 @@ SIGNATURES = {
     "mi_weight_to_dgrad": (_i, [_f, _i, _f, _i, _i, _i, _i, _st]),
     "mi_conv2d_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mi_conv2d_wgrad": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _f, _f, _f, _f, _f, _f, _f, _f, _f,
-                             _f, _f, _sz, _i, _st]),
+                             _f, _f, _i, _f, _sz, _i, _st]),
     "mi_avgpool2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _st]),
     "mi_avgpool2_bwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _st]),
     "mi_maxpool2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _st]),

@@ -242,51 +242,79 @@ conv_wgrad_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
     }
 }
 
-// reduce the split-K partials and apply the requested epilogue (store / accumulate / fused inner update)
+// reduce the split-K partials and apply the requested epilogue (store / accumulate / fused inner update).
+// Index space: [0, wsz) one thread per weight element; then, from the next multiple of 32, one WARP per bias
+// element (its 32 lanes stride over the up-to-256 bias partials and combine with shuffles: a single thread walking
+// 256 partials was a 46 us serial tail on the small layers).  In the SGD modes the updated weight can also be
+// written in the rotated layout dgrad reads (wt_out[ci][kk-1-tap][co]), which removes the per-step
+// weight_to_dgrad launch of every adapted layer.
 __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float* __restrict__ ws_b, int splits,
                                     int bias_splits, int cin, int cout, int kk, int ldw, int mode, float scale,
                                     float* __restrict__ grad_w, float* __restrict__ grad_b,
                                     const float* __restrict__ w_in, const float* __restrict__ b_in,
                                     float* __restrict__ w_out, float* __restrict__ b_out,
                                     const float* __restrict__ lr_w, const float* __restrict__ lr_b,
-                                    float* __restrict__ gsum_w, float* __restrict__ gsum_b) {
+                                    float* __restrict__ gsum_w, float* __restrict__ gsum_b,
+                                    float* __restrict__ wt_out, int ldwt) {
     const long long wsz = (long long)cout * kk * ldw;
-    const long long total = wsz + cout;
+    const long long wsz32 = (wsz + 31) & ~31LL;
+    const long long total = wsz32 + (long long)cout * 32;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const bool is_b = i >= wsz;
-        const long long e = is_b ? i - wsz : i;
-        if (!is_b && (int)(e % ldw) >= cin) continue;  // pad lanes stay zero
-        const float* src = is_b ? ws_b : ws_w;
-        const long long stride = is_b ? cout : wsz;
-        const int ns = is_b ? bias_splits : splits;
-        // four independent partial sums: the loads of a slice do not wait for the previous slice's add
-        float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
-        int s = 0;
-        for (; s + 3 < ns; s += 4) {
-            g0 += src[(long long)s * stride + e];
-            g1 += src[(long long)(s + 1) * stride + e];
-            g2 += src[(long long)(s + 2) * stride + e];
-            g3 += src[(long long)(s + 3) * stride + e];
-        }
-        for (; s < ns; ++s) g0 += src[(long long)s * stride + e];
-        const float g = (g0 + g1) + (g2 + g3);
-        float* gout = is_b ? grad_b : grad_w;
-        const float* pin = is_b ? b_in : w_in;
-        float* pout = is_b ? b_out : w_out;
-        const float* lr = is_b ? lr_b : lr_w;
-        float* gs = is_b ? gsum_b : gsum_w;
-        if (is_b && ((mode <= MI_WG_ACCUM && !gout) || (mode > MI_WG_ACCUM && (!pin || !pout || !lr)))) continue;
-        if (mode == MI_WG_STORE) {
-            gout[e] = g;
-        } else if (mode == MI_WG_ACCUM) {
-            gout[e] += scale * g;
+        if (i < wsz32) {
+            if (i >= wsz) continue;
+            const long long e = i;
+            const int ci = (int)(e % ldw);
+            if (ci >= cin) continue;  // pad lanes stay zero
+            // four independent partial sums: the loads of a slice do not wait for the previous slice's add
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+            int s = 0;
+            for (; s + 3 < splits; s += 4) {
+                g0 += ws_w[(long long)s * wsz + e];
+                g1 += ws_w[(long long)(s + 1) * wsz + e];
+                g2 += ws_w[(long long)(s + 2) * wsz + e];
+                g3 += ws_w[(long long)(s + 3) * wsz + e];
+            }
+            for (; s < splits; ++s) g0 += ws_w[(long long)s * wsz + e];
+            const float g = (g0 + g1) + (g2 + g3);
+            if (mode == MI_WG_STORE) {
+                grad_w[e] = g;
+            } else if (mode == MI_WG_ACCUM) {
+                grad_w[e] += scale * g;
+            } else {
+                const float l = (mode == MI_WG_SGD_SCALAR) ? lr_w[0] : lr_w[e];
+                const float wn = w_in[e] - l * g;
+                w_out[e] = wn;
+                if (grad_w) grad_w[e] = g;
+                if (wt_out) {
+                    const long long r = e / ldw;
+                    const int tap = (int)(r % kk);
+                    const int co = (int)(r / kk);
+                    wt_out[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = wn;
+                }
+            }
+            if (gsum_w) gsum_w[e] += g;
         } else {
-            const float l = (mode == MI_WG_SGD_SCALAR) ? lr[0] : lr[e];
-            pout[e] = pin[e] - l * g;
-            if (gout) gout[e] = g;
+            // whole warps land here (wsz32 and the grid stride are multiples of 32)
+            const long long j = i - wsz32;
+            const int c = (int)(j >> 5), lane = (int)(j & 31);
+            float g = 0.f;
+            for (int s = lane; s < bias_splits; s += 32) g += ws_b[(long long)s * cout + c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+            if (lane != 0) continue;
+            if ((mode <= MI_WG_ACCUM && !grad_b) || (mode > MI_WG_ACCUM && (!b_in || !b_out || !lr_b))) continue;
+            if (mode == MI_WG_STORE) {
+                grad_b[c] = g;
+            } else if (mode == MI_WG_ACCUM) {
+                grad_b[c] += scale * g;
+            } else {
+                const float l = (mode == MI_WG_SGD_SCALAR) ? lr_b[0] : lr_b[c];
+                b_out[c] = b_in[c] - l * g;
+                if (grad_b) grad_b[c] = g;
+            }
+            if (gsum_b) gsum_b[c] += g;
         }
-        if (gs) gs[e] += g;
     }
 }
 
@@ -322,13 +350,13 @@ int mi_bias_splits(long long m_total) {
 int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int bias_splits, int cin, int cout, int k,
                            int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
                            float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
-                           float* gsum_b, cudaStream_t stream) {
-    const long long total = (long long)cout * k * k * ldw + cout;
+                           float* gsum_b, float* wt_out, int ldwt, cudaStream_t stream) {
+    const long long total = (((long long)cout * k * k * ldw + 31) & ~31LL) + (long long)cout * 32;
     int blocks = mi_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     mi_prof_begin(MI_TAG_WGRAD_FINISH, 0.0, 4.0 * (double)total * (splits + 2), stream);
     wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, bias_splits, cin, cout, k * k, ldw, mode, scale, grad_w,
-                                                    grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b);
+                                                    grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, wt_out, ldwt);
     mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
@@ -406,13 +434,14 @@ size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k,
 int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
                     int k, int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in,
                     const float* b_in, float* w_out, float* b_out, const float* lr_w, const float* lr_b,
-                    float* gsum_w, float* gsum_b, void* workspace, size_t workspace_bytes, int engine,
-                    mi_stream_t stream) {
+                    float* gsum_w, float* gsum_b, float* wt_out, int ldwt, void* workspace, size_t workspace_bytes,
+                    int engine, mi_stream_t stream) {
     if (!x || !dy || !workspace || n <= 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || (k & 1) == 0 ||
         ldx < cin || lddy < cout || ldw < cin)
         return MI_ERR_BAD_ARG;
     if ((mode == MI_WG_STORE || mode == MI_WG_ACCUM) && (!grad_w)) return MI_ERR_BAD_ARG;
     if ((mode == MI_WG_SGD_SCALAR || mode == MI_WG_SGD_TENSOR) && (!w_in || !w_out || !lr_w)) return MI_ERR_BAD_ARG;
+    if (wt_out && (ldwt < cout || (mode != MI_WG_SGD_SCALAR && mode != MI_WG_SGD_TENSOR))) return MI_ERR_BAD_ARG;
     const int splits = mi_wgrad_splits(n, h, wd, cin, cout, k);
     const size_t wsz = (size_t)cout * k * k * ldw;
     const size_t need = ((size_t)splits * wsz + (size_t)(splits > 256 ? splits : 256) * cout) * sizeof(float);
@@ -444,7 +473,7 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
     }
     if (rc != 0) return rc;
     return mi_wgrad_finish_launch(ws_w, ws_b, splits, bias_splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
-                                  w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, st);
+                                  w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, wt_out, ldwt, st);
 }
 
 int mi_version(void) { return 100; }

@@ -56,7 +56,7 @@ int mi_bias_splits(long long m_total);
 int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int bias_splits, int cin, int cout, int k,
                            int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
                            float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
-                           float* gsum_b, cudaStream_t stream);
+                           float* gsum_b, float* wt_out, int ldwt, cudaStream_t stream);
 int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k);
 
 // tcgen05 entry points (conv_tc.cu); return MI_ERR_UNSUPPORTED when the shape is not eligible

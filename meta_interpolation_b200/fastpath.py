@@ -60,7 +60,7 @@ class _Sink:
                 return                       # dead work in support passes (Q1/Q2/Q2b)
             fast = lane.fast
             spec = WgradSpec(w_in=p.w, b_in=p.b, w_out=fast.kernel_view(wn),
-                             b_out=fast.kernel_view(bn) if has_b else None)
+                             b_out=fast.kernel_view(bn) if has_b else None, wt_out=lane.wt_buffer(p.name))
             if fp.metasgd:
                 spec.mode = WG_SGD_TENSOR
                 spec.lr_w = fp.sys.alpha.kernel_view(wn)
@@ -159,6 +159,7 @@ class _Lane:
         self.gsteps = []
         self.dots = torch.zeros(len(net.param_names), device=dev)
         self.programs = {}
+        self.fast_wt = {}    # rotated (dgrad-layout) copies of the fast weights, written by the fused update
         # lane 0 accumulates straight into the optimizer's flat gradient buffers; the others into private
         # buffers that are added once per meta-batch
         if index == 0:
@@ -169,6 +170,17 @@ class _Lane:
             self.acc_theta = Arena(lay, dev)
             self.acc_alpha = Arena(lay, dev) if fp.metasgd else None
             self.acc_lr = torch.zeros_like(sysm.lr_table_grad) if fp.learnable_lr else None
+
+    def wt_buffer(self, name):
+        """Persistent dgrad-layout buffer of the routed conv ``name``: the weight-gradient finishing kernel of inner
+        step k writes the rotated updated weight here, inner step k+1 (and the query pass) read it."""
+        buf = self.fast_wt.get(name)
+        if buf is None:
+            w = self.fast.kernel_view(name + ".weight")
+            cout, k, _, cin = w.shape
+            buf = self.fp.ops.empty_weight(cin, cout, k)
+            self.fast_wt[name] = buf
+        return buf
 
     def zero_accumulators(self):
         if self.index == 0:
@@ -251,6 +263,7 @@ class FastPath:
                     w = fast.kernel_view(name + ".weight")
                     b = fast.kernel_view(name + ".bias") if net._spec[name][4] else None
                     p = ConvParam(name, w, b)
+                    p._wt = lane.wt_buffer(name)     # kept current by the fused update of the previous step
                 else:
                     p = net.meta_param(name)
                     p._wt = self.meta_wt.get(name)   # rotated copy refreshed once per meta-batch

@@ -49,10 +49,11 @@ def _ldw(w):
 class WgradSpec:
     """What the weight-gradient finishing stage does (include/mi_b200.h MI_WG_*)."""
     __slots__ = ("mode", "scale", "grad_w", "grad_b", "w_in", "b_in", "w_out", "b_out", "lr_w", "lr_b", "gsum_w",
-                 "gsum_b")
+                 "gsum_b", "wt_out")
 
     def __init__(self, mode=WG_STORE, scale=1.0, grad_w=None, grad_b=None, w_in=None, b_in=None, w_out=None,
-                 b_out=None, lr_w=None, lr_b=None, gsum_w=None, gsum_b=None):
+                 b_out=None, lr_w=None, lr_b=None, gsum_w=None, gsum_b=None, wt_out=None):
+        self.wt_out = wt_out        # SGD modes: also emit the updated weight in the dgrad (rotated) layout
         self.mode, self.scale = mode, scale
         self.grad_w, self.grad_b = grad_w, grad_b
         self.w_in, self.b_in, self.w_out, self.b_out = w_in, b_in, w_out, b_out
@@ -184,8 +185,9 @@ class CudaOps:
         _lib.check(self.lib.mi_conv2d_wgrad(x.data_ptr(), _ld(x), dy.data_ptr(), _ld(dy), n, h, wd, cin, cout, k, ldw,
                                             spec.mode, float(spec.scale), p(spec.grad_w), p(spec.grad_b), p(spec.w_in),
                                             p(spec.b_in), p(spec.w_out), p(spec.b_out), p(spec.lr_w), p(spec.lr_b),
-                                            p(spec.gsum_w), p(spec.gsum_b), ws.data_ptr(), ws.numel(), eng,
-                                            self._stream()), "mi_conv2d_wgrad")
+                                            p(spec.gsum_w), p(spec.gsum_b), p(spec.wt_out),
+                                            0 if spec.wt_out is None else _ldw(spec.wt_out), ws.data_ptr(),
+                                            ws.numel(), eng, self._stream()), "mi_conv2d_wgrad")
 
     # ------------------------------------------------------------------ resampling / pointwise
     def avgpool_fwd(self, x):

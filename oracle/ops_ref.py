@@ -138,6 +138,8 @@ class RefOps:
             lr_w = spec.lr_w.reshape(-1)[0] if spec.mode == WG_SGD_SCALAR else spec.lr_w
             new_w = spec.w_in - lr_w * gw
             spec.w_out.copy_(new_w)
+            if getattr(spec, "wt_out", None) is not None:
+                self.weight_to_dgrad(new_w, out=spec.wt_out)
             if spec.grad_w is not None:
                 spec.grad_w.copy_(gw)
             if has_b:

@@ -109,6 +109,13 @@ def test_conv_wgrad_simt_modes(cuda_ops, shape):
     cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_SGD_TENSOR, w_in=wd, b_in=bd, w_out=w2d, b_out=b2d, lr_w=ad,
                                                   lr_b=ab.cuda()), engine=ENGINE_SIMT)
     close(w2d, w2c, 3e-5, "metasgd w")
+    # the fused update can also emit the updated weight in the rotated layout dgrad reads
+    w3d, wt3 = cuda_ops.empty_weight(cout, cin, k), cuda_ops.empty_weight(cin, cout, k)
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_SGD_SCALAR, w_in=wd, b_in=bd, w_out=w3d, b_out=b2d,
+                                                  lr_w=lr.cuda(), lr_b=lr.cuda(), wt_out=wt3), engine=ENGINE_SIMT)
+    close(wt3, cuda_ops.weight_to_dgrad(w3d).cpu(), 0.0, "fused rotated weight == weight_to_dgrad(updated weight)")
+    with pytest.raises(Exception):      # only the SGD modes own an updated weight to rotate
+        cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_STORE, grad_w=gwd, grad_b=gbd, wt_out=wt3), engine=ENGINE_SIMT)
     # pad lanes of the KRSC storage stay zero
     if ld != cin:
         full = w2d.as_strided((cout, k, k, ld), (k * k * ld, k * ld, ld, 1), w2d.storage_offset())
