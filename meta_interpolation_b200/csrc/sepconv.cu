@@ -87,29 +87,57 @@ sepconv_fwd_kernel(const float* __restrict__ frame, const float* __restrict__ ve
     const float* hp1 = horiz + gpix1 * ldf;
     const float* vp0 = vert + gpix0 * ldf;
     const float* vp1 = vert + gpix1 * ldf;
-    float h0[F], h1[F];
+    // Per-pixel filters are rows of an NHWC tensor (one pixel = 51 taps = 208 B), so a warp-wide scalar load touches
+    // 32 different lines and costs the LSU pipe as much as 32 staged-window loads.  Rows are 16-byte aligned
+    // (ldf % 4 == 0 checked by the host), so taps are fetched four at a time: 13 + 13 LDG.128 instead of 102 LDG.32
+    // for the horizontal filters, one LDG.128 per pixel per four window rows for the vertical ones.
+    float h0[F + 1], h1[F + 1];          // tap 51 is the pad lane of the 52-float row: loaded, never used
 #pragma unroll
-    for (int f = 0; f < F; ++f) { h0[f] = __ldg(hp0 + f); h1[f] = __ldg(hp1 + f); }
+    for (int g = 0; g < (F + 3) / 4; ++g) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(hp0) + g);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(hp1) + g);
+        h0[4 * g] = a.x; h1[4 * g] = b.x;
+        if (4 * g + 1 <= F) { h0[4 * g + 1] = a.y; h1[4 * g + 1] = b.y; }
+        if (4 * g + 2 <= F) { h0[4 * g + 2] = a.z; h1[4 * g + 2] = b.z; }
+        if (4 * g + 3 <= F) { h0[4 * g + 3] = a.w; h1[4 * g + 3] = b.w; }
+    }
     float acc0[C], acc1[C];
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) { acc0[cc] = 0.f; acc1[cc] = 0.f; }
     // window row r (relative to pixel 0) is tap fy = r of pixel 0 and tap fy = r - 1 of pixel 1
+    float v1_prev = 0.f;                 // tap 4q-1 of pixel 1, carried from the previous group
 #pragma unroll 1
-    for (int r = 0; r <= F; ++r) {
-        const float v0 = r < F ? __ldg(vp0 + r) : 0.f;
-        const float v1 = r > 0 ? __ldg(vp1 + r - 1) : 0.f;
+    for (int q = 0; q < (F + 1 + 3) / 4; ++q) {
+        const float4 va = __ldg(reinterpret_cast<const float4*>(vp0) + q);   // taps 4q..4q+3 of pixel 0
+        const float4 vb = __ldg(reinterpret_cast<const float4*>(vp1) + q);   // taps 4q..4q+3 of pixel 1
+        const float v0s[4] = {va.x, va.y, va.z, va.w};
+        const float v1s[4] = {v1_prev, vb.x, vb.y, vb.z};
+        v1_prev = vb.w;
 #pragma unroll
-        for (int cc = 0; cc < C; ++cc) {
-            const float* row = smem + (cc * WH + FWD_PY * ty + r) * P + tx;
-            float t0 = 0.f, t1 = 0.f;
+        for (int i = 0; i < 4; ++i) {
+            const int r = 4 * q + i;
+            if (r > F) break;
+            const float v0 = r < F ? v0s[i] : 0.f;       // (tap 51 of the row is the pad lane)
+            const float v1 = r > 0 ? v1s[i] : 0.f;
+            // channels innermost: 2*C independent accumulation chains and C independent loads per tap
+            const float* row = smem + (FWD_PY * ty + r) * P + tx;
+            float t0[C], t1[C];
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) { t0[cc] = 0.f; t1[cc] = 0.f; }
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                const float in = row[f];
-                t0 = fmaf(in, h0[f], t0);
-                t1 = fmaf(in, h1[f], t1);
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) {
+                    const float in = row[cc * WH * P + f];
+                    t0[cc] = fmaf(in, h0[f], t0[cc]);
+                    t1[cc] = fmaf(in, h1[f], t1[cc]);
+                }
             }
-            acc0[cc] = fmaf(v0, t0, acc0[cc]);
-            acc1[cc] = fmaf(v1, t1, acc1[cc]);
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) {
+                acc0[cc] = fmaf(v0, t0[cc], acc0[cc]);
+                acc1[cc] = fmaf(v1, t1[cc], acc1[cc]);
+            }
         }
     }
 #pragma unroll
@@ -138,34 +166,63 @@ sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ ve
     const long long gpix = ((long long)n_idx * gh + gy0 + oy) * gw + gx0 + ox;
     const float* hp = horiz + gpix * ldf;
     const float* vp = vert + gpix * ldf;
-    float hreg[F], gh_acc[F];
+    // filters and their gradients move four taps at a time (rows are 16-byte aligned, see the forward kernel); the
+    // fourth lane of the last group is the pad lane of the 52-float row
+    float hreg[F + 1], gh_acc[F + 1];
 #pragma unroll
-    for (int f = 0; f < F; ++f) { hreg[f] = __ldg(hp + f); gh_acc[f] = 0.f; }
+    for (int g = 0; g < (F + 3) / 4; ++g) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(hp) + g);
+        hreg[4 * g] = a.x;
+        if (4 * g + 1 <= F) hreg[4 * g + 1] = a.y;
+        if (4 * g + 2 <= F) hreg[4 * g + 2] = a.z;
+        if (4 * g + 3 <= F) hreg[4 * g + 3] = a.w;
+    }
+#pragma unroll
+    for (int f = 0; f <= F; ++f) gh_acc[f] = 0.f;
     float go[C];
 #pragma unroll
     for (int cc = 0; cc < C; ++cc) go[cc] = grad_out[(((long long)n_idx * C + cc) * oh + oy) * ow + ox];
     float* gvp = g_vert + gpix * ldg;
-    for (int fy = 0; fy < F; ++fy) {
-        const float vv = __ldg(vp + fy);
-        float gv = 0.f;
+#pragma unroll 1
+    for (int q = 0; q < (F + 3) / 4; ++q) {
+        const float4 va = __ldg(reinterpret_cast<const float4*>(vp) + q);
+        const float vs[4] = {va.x, va.y, va.z, va.w};
+        float gvs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int cc = 0; cc < C; ++cc) {
-            const float* row = smem + (cc * WH + ty + fy) * P + tx;
-            const float gvc = go[cc] * vv;
-            float t = 0.f;
+        for (int i = 0; i < 4; ++i) {
+            const int fy = 4 * q + i;
+            if (fy >= F) break;
+            const float vv = vs[i];
+            // channels innermost: C independent loads and C independent `t` chains per tap (see the forward kernel)
+            const float* row = smem + (ty + fy) * P + tx;
+            float gvc[C], t[C];
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) { gvc[cc] = go[cc] * vv; t[cc] = 0.f; }
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                const float in = row[f];
-                t = fmaf(in, hreg[f], t);
-                gh_acc[f] = fmaf(gvc, in, gh_acc[f]);
+                float in[C];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) in[cc] = row[cc * WH * P + f];
+                float gh = gh_acc[f];
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) {
+                    t[cc] = fmaf(in[cc], hreg[f], t[cc]);
+                    gh = fmaf(gvc[cc], in[cc], gh);
+                }
+                gh_acc[f] = gh;
             }
-            gv = fmaf(go[cc], t, gv);
+            float gv = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) gv = fmaf(go[cc], t[cc], gv);
+            gvs[i] = gv;
         }
-        gvp[fy] = gv;
+        reinterpret_cast<float4*>(gvp)[q] = make_float4(gvs[0], gvs[1], gvs[2], gvs[3]);   // pad lane gets 0
     }
     float* ghp = g_horiz + gpix * ldg;
 #pragma unroll
-    for (int f = 0; f < F; ++f) ghp[f] = gh_acc[f];
+    for (int g = 0; g < (F + 3) / 4; ++g)
+        reinterpret_cast<float4*>(ghp)[g] =
+            make_float4(gh_acc[4 * g], gh_acc[4 * g + 1], gh_acc[4 * g + 2], gh_acc[4 * g + 3]);
 }
 
 // any filter size / channel count: one thread per output pixel straight from global memory
@@ -251,7 +308,7 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
                    mi_stream_t stream) {
     if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !out) return MI_ERR_BAD_ARG;
     cudaStream_t st = mi_cs(stream);
-    if (taps == 51 && c == 3) {
+    if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && mi_al16(vert) && mi_al16(horiz)) {
         static bool attr_set = false;
         const size_t sm = (size_t)3 * GeoF<51>::WIN_H * GeoF<51>::PITCH * sizeof(float);
         if (!attr_set) {
@@ -284,7 +341,8 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
         !g_horiz || ldg < taps)
         return MI_ERR_BAD_ARG;
     cudaStream_t st = mi_cs(stream);
-    if (taps == 51 && c == 3) {
+    if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && ldg >= 52 && (ldg & 3) == 0 && mi_al16(vert) &&
+        mi_al16(horiz) && mi_al16(g_vert) && mi_al16(g_horiz)) {
         static bool attr_set = false;
         const size_t sm = smem_bytes<51>(3);
         if (!attr_set) {
