@@ -47,7 +47,8 @@ def roofline_section(system):
         fast.use_graphs = fast_saved
     peaks = measured_peaks()
     total_ms = sum(v["ms"] for v in summ.values())
-    conv_tags = ("fprop_tc", "wgrad_tc", "fprop_simt", "wgrad_simt")
+    conv_tags = ("fprop_tc_halo", "fprop_tc_halo_stream", "fprop_tc", "wgrad_tc_kx", "wgrad_tc", "fprop_simt",
+                 "wgrad_simt")
     dom = max(conv_tags, key=lambda t: summ[t]["ms"])
     d = summ[dom]
     achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
@@ -57,14 +58,26 @@ def roofline_section(system):
                      "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0}
                  for k, v in summ.items() if v["launches"]}
     return {
-        "bound": "tensor", "kernel": dom, "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s",
-        "frac": round(achieved / peak, 4), "traffic": None,
+        "bound": "tensor", "kernel": KERNEL_NAMES.get(dom, dom), "achieved": round(achieved, 2), "peak": peak,
+        "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on its heaviest
+        # layer (51->51 on the 258x450 region of interest, N=2): see profiles/README.md
+        "traffic": NCU_TRAFFIC_BYTES.get(dom),
         "peak_source": peaks["source"] + "; dense bf16 sustained (kernel timed inside a long step); the kernel "
-                       "computes in TF32 whose tensor-pipe ceiling is half the bf16 one",
+                       "computes in TF32, whose tensor-pipe ceiling is half the bf16 one (frac 0.5 = TF32 peak)",
         "share_of_instrumented_step": round(d["ms"] / total_ms, 3) if total_ms > 0 else None,
         "avg_launch_us": round(d["ms"] * 1e3 / max(d["launches"], 1), 2),
+        "algorithmic_gflop_per_launch": round(d["flops"] / max(d["launches"], 1) / 1e9, 3),
         "instrumented_step_ms": round(wall_ms, 2), "per_kernel": breakdown,
     }
+
+
+KERNEL_NAMES = {"fprop_tc_halo": "conv_fprop_tc_halo_kernel", "fprop_tc_halo_stream": "conv_fprop_tc_halo_stream_kernel",
+                "fprop_tc": "conv_fprop_tc_kernel", "wgrad_tc_kx": "conv_wgrad_tc_kx_kernel",
+                "wgrad_tc": "conv_wgrad_tc_kernel", "fprop_simt": "conv_fprop_simt_kernel",
+                "wgrad_simt": "conv_wgrad_simt_kernel"}
+# filled from the committed ncu captures (profiles/); None = not captured this round
+NCU_TRAFFIC_BYTES = {"fprop_tc_halo": 48484608 + 5084416}   # profiles/r01b_ncu_conv_fprop_halo_51x51_258x450.txt
 
 
 # --------------------------------------------------------------------------------------------- CPU legs

@@ -53,8 +53,10 @@ unsigned long long mi_launch_count(void);
 /* 1 if the tcgen05 path was compiled in and the current device is sm_100 */
 int mi_tc_available(void);
 
-/* per-launch CUDA-event timing of the hot kernels (bench.py roofline section).  tag: 0 fprop/dgrad tcgen05,
- * 1 wgrad tcgen05, 2 fprop/dgrad SIMT, 3 wgrad SIMT, 4 sepconv fwd, 5 sepconv bwd, 6 wgrad finish.
+/* per-launch CUDA-event timing of the hot kernels (bench.py roofline section).  tag: 0 fprop/dgrad tcgen05 per-tap,
+ * 1 wgrad tcgen05 per-tap, 2 fprop/dgrad SIMT, 3 wgrad SIMT, 4 sepconv fwd, 5 sepconv bwd, 6 wgrad finish,
+ * 7 fprop/dgrad tcgen05 halo (resident weights), 8 fprop/dgrad tcgen05 halo (streamed weights), 9 wgrad tcgen05
+ * filter-column.
  * out[4] = {launches, total ms, algorithmic flops, algorithmic bytes}.  Not usable under graph capture. */
 int mi_prof_enable(int on);
 int mi_prof_summary(int tag, double* out);

@@ -1367,7 +1367,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
                 attr = true;
             }
             int grid = hp.total_tiles < num_sms() ? hp.total_tiles : num_sms();
-            mi_prof_begin(MI_TAG_FPROP_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+            mi_prof_begin(MI_TAG_FPROP_HALO, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
                           stream);
             static unsigned long long* dbg_buf = nullptr;
             static int dbg_on = -1;
@@ -1430,7 +1430,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
                 cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), stream);
                 hp.dbg = dbg_buf;
             }
-            mi_prof_begin(MI_TAG_FPROP_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+            mi_prof_begin(MI_TAG_FPROP_STREAM, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
                           stream);
             conv_fprop_tc_halo_stream_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, hp);
             mi_prof_end(stream);
@@ -1541,7 +1541,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
             attr_kx = true;
         }
         dim3 grid(3, splits);
-        mi_prof_begin(MI_TAG_WGRAD_TC, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
+        mi_prof_begin(MI_TAG_WGRAD_KX, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
         conv_wgrad_tc_kx_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, q);
         mi_prof_end(stream);
         MI_LAUNCHED();

@@ -17,7 +17,8 @@ extern std::atomic<unsigned long long> g_mi_launches;
 
 // per-launch profiling hooks (profile.cu); no-ops unless mi_prof_enable(1)
 enum { MI_TAG_FPROP_TC = 0, MI_TAG_WGRAD_TC = 1, MI_TAG_FPROP_SIMT = 2, MI_TAG_WGRAD_SIMT = 3, MI_TAG_SEPCONV_FWD = 4,
-       MI_TAG_SEPCONV_BWD = 5, MI_TAG_WGRAD_FINISH = 6 };
+       MI_TAG_SEPCONV_BWD = 5, MI_TAG_WGRAD_FINISH = 6, MI_TAG_FPROP_HALO = 7, MI_TAG_FPROP_STREAM = 8,
+       MI_TAG_WGRAD_KX = 9 };
 void mi_prof_begin(int tag, double flops, double bytes, cudaStream_t s);
 void mi_prof_end(cudaStream_t s);
 static inline double mi_conv_flops(int n, int h, int w, int cin, int cout, int k) {

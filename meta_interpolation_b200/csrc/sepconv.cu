@@ -10,6 +10,8 @@
 //   out = sum_fy v[fy] * (sum_fx in[y+fy][x+fx] * h[fx])          (SURVEY Appx E1)
 // The op has no GEMM structure (filters differ per pixel) and is bound by the
 // FP32 FMA pipe / shared-memory bandwidth, not HBM.
+#include <cstdlib>
+
 #include "mi_common.cuh"
 
 namespace {
@@ -55,8 +57,8 @@ struct GeoF {
     static constexpr int PITCH = WIN_W + 1;
 };
 
-template <int F, int C>
-__global__ void __launch_bounds__(TX* TY, 2)
+template <int F, int C, int MINB>
+__global__ void __launch_bounds__(TX* TY, MINB)
 sepconv_fwd_kernel(const float* __restrict__ frame, const float* __restrict__ vert, const float* __restrict__ horiz,
                    int ldf, float* __restrict__ out, int fh, int fw, int gh, int gw, int oh, int ow, int gy0, int gx0,
                    int iy0, int ix0) {
@@ -148,8 +150,8 @@ sepconv_fwd_kernel(const float* __restrict__ frame, const float* __restrict__ ve
     }
 }
 
-template <int F, int C>
-__global__ void __launch_bounds__(TX* TY)
+template <int F, int C, int MINB>
+__global__ void __launch_bounds__(TX* TY, MINB)
 sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ vert, const float* __restrict__ horiz,
                    int ldf, const float* __restrict__ grad_out, float* __restrict__ g_vert,
                    float* __restrict__ g_horiz, int ldg, int fh, int fw, int gh, int gw, int oh, int ow, int gy0,
@@ -299,6 +301,19 @@ bool args_ok(const void* a, const void* b, const void* c, int n, int ch, int fh,
            gy0 >= 0 && gx0 >= 0 && gy0 + oh <= gh && gx0 + ow <= gw;
 }
 
+// Register budget of the two kernels: MINB = 2 caps them at 128 registers (two 256-thread blocks per SM), MINB = 1
+// lets ptxas keep more staged-window loads in flight at one block per SM.  MI_B200_SEPCONV_MINB="<fwd><bwd>" (e.g.
+// "21") overrides the measured defaults.
+int variant_minb(int which) {
+    static int v[2] = {0, 0};
+    if (!v[0]) {
+        v[0] = 1; v[1] = 1;   // measured on B200 (tools/bench_sepconv.py): fwd 201 vs 221 us, bwd 333 vs 460 us
+        const char* e = getenv("MI_B200_SEPCONV_MINB");
+        if (e && (e[0] == '1' || e[0] == '2') && (e[1] == '1' || e[1] == '2')) { v[0] = e[0] - '0'; v[1] = e[1] - '0'; }
+    }
+    return v[which];
+}
+
 }  // namespace
 
 extern "C" {
@@ -312,16 +327,22 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
         static bool attr_set = false;
         const size_t sm = (size_t)3 * GeoF<51>::WIN_H * GeoF<51>::PITCH * sizeof(float);
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(sepconv_fwd_kernel<51, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(sepconv_fwd_kernel<51, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)sm);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(sepconv_fwd_kernel<51, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
         dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY * FWD_PY), n);
         const double px = (double)n * oh * ow;
         mi_prof_begin(MI_TAG_SEPCONV_FWD, 2.0 * px * (3 * 51 * 51 + 3 * 51), 4.0 * px * (2 * 51 + 3 + 3), st);
-        sepconv_fwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, out, fh, fw, gh, gw, oh, ow, gy0,
-                                                             gx0, iy0, ix0);
+        if (variant_minb(0) == 1)
+            sepconv_fwd_kernel<51, 3, 1><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, out, fh, fw, gh, gw, oh, ow,
+                                                                    gy0, gx0, iy0, ix0);
+        else
+            sepconv_fwd_kernel<51, 3, 2><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, out, fh, fw, gh, gw, oh, ow,
+                                                                    gy0, gx0, iy0, ix0);
         mi_prof_end(st);
     } else {
         const long long total = (long long)n * c * oh * ow;
@@ -346,16 +367,22 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
         static bool attr_set = false;
         const size_t sm = smem_bytes<51>(3);
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(sepconv_bwd_kernel<51, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(sepconv_bwd_kernel<51, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)sm);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(sepconv_bwd_kernel<51, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
             if (e != cudaSuccess) return (int)e;
             attr_set = true;
         }
         dim3 grid(mi_cdiv(ow, TX), mi_cdiv(oh, TY), n);
         const double px = (double)n * oh * ow;
         mi_prof_begin(MI_TAG_SEPCONV_BWD, 2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51), 4.0 * px * (4 * 51 + 3 + 3), st);
-        sepconv_bwd_kernel<51, 3><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz, ldg,
-                                                             fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
+        if (variant_minb(1) == 1)
+            sepconv_bwd_kernel<51, 3, 1><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz,
+                                                                    ldg, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
+        else
+            sepconv_bwd_kernel<51, 3, 2><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz,
+                                                                    ldg, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
         mi_prof_end(st);
     } else {
         const long long total = (long long)n * oh * ow * taps;

@@ -127,7 +127,7 @@ class CudaOps:
 
     # ------------------------------------------------------------------ per-launch profiling (bench roofline)
     PROF_TAGS = {"fprop_tc": 0, "wgrad_tc": 1, "fprop_simt": 2, "wgrad_simt": 3, "sepconv_fwd": 4, "sepconv_bwd": 5,
-                 "wgrad_finish": 6}
+                 "wgrad_finish": 6, "fprop_tc_halo": 7, "fprop_tc_halo_stream": 8, "wgrad_tc_kx": 9}
 
     def prof_enable(self, on):
         _lib.check(self.lib.mi_prof_enable(1 if on else 0), "mi_prof_enable")
