@@ -112,6 +112,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), 128-byte swizzle
 // layout_type: 2 = SWIZZLE_128B (16-byte chunks; K-major operands), 1 = SWIZZLE_128B_BASE32B (32-byte chunks;
 // the only layout the hardware accepts for MN-major TF32 operands)
@@ -241,13 +252,21 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
 // pixel, i.e. 4 full lines per STG.128 instead of 32 partial ones; mask / accumulate operands are loaded with the
 // same coalesced pattern.
 struct RowMap {
-    int tw, y0, x0, h, w, img, q;   // tile width in pixels, tile origin, image size, image index, warp quarter
-    __device__ __forceinline__ bool pixel(int row, long long& pix) const {
-        const int r = q * 32 + row;
-        const int th_i = r / tw, tw_i = r - th_i * tw;
-        const int oy = y0 + th_i, ox = x0 + tw_i;
-        pix = ((long long)img * h + oy) * w + ox;
-        return oy < h && ox < w;
+    // The epilogue thread `lane` of TMEM-lane quarter q stores the staged rows i*4 + (lane>>3), i = 0..7.  Their global
+    // pixel indices are the same for every 32-channel chunk of a tile, so they are resolved once per tile (the
+    // per-chunk division by the tile width was a third of the epilogue's instructions).
+    long long pix[8];
+    uint32_t ok;          // bit i: row i lies inside the image
+    __device__ __forceinline__ void init(int tw, int y0, int x0, int h, int w, int img, int q, int lane) {
+        ok = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = q * 32 + i * 4 + (lane >> 3);
+            const int th_i = r / tw, tw_i = r - th_i * tw;
+            const int oy = y0 + th_i, ox = x0 + tw_i;
+            pix[i] = ((long long)img * h + oy) * w + ox;
+            if (oy < h && ox < w) ok |= 1u << i;
+        }
     }
 };
 constexpr int EPI_PITCH = 36;   // floats per staged row (32 + 4): conflict-free for both access patterns
@@ -280,9 +299,8 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t (&v)[32]
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = i * 4 + (lane >> 3);
-        long long pix;
-        const bool ok = rm.pixel(row, pix);
-        if (!ok || c >= e.cout) continue;
+        const long long pix = rm.pix[i];
+        if (!((rm.ok >> i) & 1u) || c >= e.cout) continue;
         float4 r = *reinterpret_cast<const float4*>(stage + row * EPI_PITCH + c4);
         float* dst = y + pix * ldy + c;
         if (full) {
@@ -312,6 +330,103 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t (&v)[32]
         }
     }
     __syncwarp();
+}
+
+// 16-column pieces for the persistent halo kernels.  Per-role cycle counters showed their epilogue (one warp per
+// TMEM lane quarter, ~1.8k cycles per 32x32 block of dependent shared/global round trips) pacing the MMA lane, so
+// those kernels run EIGHT epilogue warps: the two warps that share a lane quarter each take one 16-column half of
+// every 32-column chunk.  A staged row is 16 + 4 floats; 4 lanes cover the 64 contiguous bytes of one pixel.
+constexpr int EPI16_PITCH = 20;
+constexpr int HALO_THREADS = 320;   // warp 0 producer, warp 1 MMA, warps 2-9 epilogue
+
+struct RowMap16 {
+    long long pix[4];     // staged rows i*8 + (lane>>2), i = 0..3
+    uint32_t ok;
+    __device__ __forceinline__ void init(int tw, int y0, int x0, int h, int w, int img, int q, int lane) {
+        ok = 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = q * 32 + i * 8 + (lane >> 2);
+            const int th_i = r / tw, tw_i = r - th_i * tw;
+            const int oy = y0 + th_i, ox = x0 + tw_i;
+            pix[i] = ((long long)img * h + oy) * w + ox;
+            if (oy < h && ox < w) ok |= 1u << i;
+        }
+    }
+};
+
+__device__ __forceinline__ void epilogue_half_coalesced(const uint32_t (&v)[16], const float* __restrict__ sbias, int co,
+                                                        const EpiArgs& e, float* stage, int lane, const RowMap16& rm,
+                                                        const float* __restrict__ mask_y, int ldmask,
+                                                        float* __restrict__ y, int ldy) {
+    float o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(v[j]) + sbias[j];
+    if (e.act == MI_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if (e.act == MI_ACT_LEAKY) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * e.slope;
+    } else if (e.act != MI_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = mi_act_apply(o[j], e.act, e.slope);
+    }
+    float* mine = stage + lane * EPI16_PITCH;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<float4*>(mine + 4 * g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
+    __syncwarp();
+    const int c4 = (lane & 3) * 4;
+    const int c = co + c4;
+    const bool full = c + 4 <= e.cout_store;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = i * 8 + (lane >> 2);
+        const long long pix = rm.pix[i];
+        if (!((rm.ok >> i) & 1u) || c >= e.cout) continue;
+        float4 r = *reinterpret_cast<const float4*>(stage + row * EPI16_PITCH + c4);
+        float* dst = y + pix * ldy + c;
+        if (full) {
+            if (mask_y) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(mask_y + pix * ldmask + c));
+                r.x *= mi_act_grad(m.x, e.mask_act, e.mask_slope);
+                r.y *= mi_act_grad(m.y, e.mask_act, e.mask_slope);
+                r.z *= mi_act_grad(m.z, e.mask_act, e.mask_slope);
+                r.w *= mi_act_grad(m.w, e.mask_act, e.mask_slope);
+            }
+            if (e.accumulate) {
+                const float4 a = *reinterpret_cast<const float4*>(dst);
+                r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
+            }
+            *reinterpret_cast<float4*>(dst) = r;
+        } else {
+            const float rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (c + q < e.cout) {
+                    float val = rv[q];
+                    if (mask_y) val *= mi_act_grad(__ldg(mask_y + pix * ldmask + c + q), e.mask_act, e.mask_slope);
+                    if (e.accumulate) val += dst[q];
+                    dst[q] = val;
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+// unaligned rows (channel slices of a concat buffer that do not start on a 16-byte boundary): plain per-lane stores
+__device__ __forceinline__ void epilogue_half_scalar(const uint32_t (&v)[16], const float* __restrict__ sbias, int co,
+                                                     const EpiArgs& e, const float* __restrict__ mrow, float* yrow) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (co + j >= e.cout) break;
+        float val = mi_act_apply(__uint_as_float(v[j]) + sbias[j], e.act, e.slope);
+        if (mrow) val *= mi_act_grad(__ldg(mrow + co + j), e.mask_act, e.mask_slope);
+        if (e.accumulate) val += yrow[co + j];
+        yrow[co + j] = val;
+    }
 }
 
 struct FpropParams {
@@ -433,7 +548,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const int c4 = (p.cout + 3) & ~3;
         ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
         RowMap rm;
-        rm.tw = p.tw; rm.y0 = y0; rm.x0 = x0; rm.h = p.h; rm.w = p.w; rm.img = img; rm.q = q;
+        rm.init(p.tw, y0, x0, p.h, p.w, img, q, lane);
         float* stage = reinterpret_cast<float*>(smem) + q * 32 * EPI_PITCH;
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
             if (co0 + c0 >= p.cout) break;             // warp-uniform
@@ -474,7 +589,7 @@ struct HaloParams {
     float* y;
 };
 
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(HALO_THREADS)
 conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                           const HaloParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -489,7 +604,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     __shared__ float sbias[64];
-    __shared__ __align__(16) float epi_stage[4 * 32 * EPI_PITCH];
+    __shared__ __align__(16) float epi_stage[8 * 32 * EPI16_PITCH];
     if (threadIdx.x < 64) sbias[threadIdx.x] = (p.bias && (int)threadIdx.x < p.cout) ? p.bias[threadIdx.x] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -499,8 +614,8 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         mbar_init(smem_u32(&bars[2 * S]), 1);
         mbar_init(smem_u32(&bars[2 * S + 1]), 1);
         mbar_init(smem_u32(&bars[2 * S + 2]), 1);
-        mbar_init(smem_u32(&bars[2 * S + 3]), 128);
-        mbar_init(smem_u32(&bars[2 * S + 4]), 128);
+        mbar_init(smem_u32(&bars[2 * S + 3]), 256);     // all eight epilogue warps release an accumulator buffer
+        mbar_init(smem_u32(&bars[2 * S + 4]), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * p.bn));
@@ -590,15 +705,21 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
                                           (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
                         }
                     } else {
-                        // ragged last chunk (e.g. 51 = 32 + 19 channels): skip its all-zero K=8 steps
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
-                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * tap_b);
-                            for (int kk = 0; kk < last_ksteps; ++kk)
-                                umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
-                                          (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
-                        }
+                        // ragged last chunk (e.g. 51 = 32 + 19 channels): skip its all-zero K=8 steps.  Unrolled per
+                        // step count: the rolled form cost ~100 cycles per MMA against ~57 for the unrolled one
+                        // (per-role cycle counters), i.e. the single issuing lane, not the tensor pipe, set the pace
+#define MI_HALO_RAGGED(KS)                                                                                          \
+    _Pragma("unroll") for (int tap = 0; tap < 9; ++tap) {                                                           \
+        const int ky = tap / 3, kx = tap - ky * 3;                                                                  \
+        const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);                       \
+        const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * tap_b);                                            \
+        _Pragma("unroll") for (int kk = 0; kk < KS; ++kk)                                                           \
+            umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,                    \
+                      (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);                                                     \
+    }
+                        if (last_ksteps == 3) { MI_HALO_RAGGED(3) }
+                        else if (last_ksteps == 2) { MI_HALO_RAGGED(2) }
+                        else { MI_HALO_RAGGED(1) }
                     }
                     umma_commit(smem_u32(&bars[S + s]));
                     if (ch == p.chunks - 1) umma_commit(smem_u32(&bars[2 * S + 1 + buf]));
@@ -611,7 +732,8 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
             p.dbg[4] = (unsigned long long)t_tmem; p.dbg[5] = (unsigned long long)(clock64() - t_begin);
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;               // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;     // which 16-column half of every 32-column chunk it owns
         const int r = q * 32 + lane;
         const int th_i = r >> 3, tw_i = r & 7;
         long long e_wait = 0, e_ld = 0, e_st = 0;
@@ -624,6 +746,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         // the pad lane may be written only when the row is exactly the 4-padded width (not a concat slice)
         const int c4 = (p.cout + 3) & ~3;
         ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
+        float* stage = epi_stage + (warp - 2) * 32 * EPI16_PITCH;
         for (int t = 0; t < my_tiles; ++t) {
             const int buf = t & 1;
             const uint32_t use = (uint32_t)(t >> 1);
@@ -636,22 +759,21 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
             const long long pix = ((long long)img * p.h + oy) * p.w + ox;
             float* yrow = p.y + pix * p.ldy;
             const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
+            RowMap16 rm;
+            rm.init(HT_W, ty_i * HT_H, tx_i * HT_W, p.h, p.w, img, q, lane);
             long long c0 = clock64();
             mbar_wait(smem_u32(&bars[2 * S + 1 + buf]), use & 1u);
             e_wait += clock64() - c0;
             tc_fence_after();
-            RowMap rm;
-            rm.tw = HT_W; rm.y0 = ty_i * HT_H; rm.x0 = tx_i * HT_W; rm.h = p.h; rm.w = p.w; rm.img = img; rm.q = q;
-            float* stage = epi_stage + q * 32 * EPI_PITCH;
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
-                if (c0 >= p.cout) break;
-                uint32_t v[32];
+            for (int c0 = 16 * half; c0 < p.bn; c0 += 32) {
+                if (c0 >= p.cout) break;            // warp-uniform
+                uint32_t v[16];
                 long long c1 = clock64();
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn + c0), v);
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn + c0), v);
                 e_ld += clock64() - c1;
                 c1 = clock64();
-                if (vec) epilogue_chunk_coalesced(v, sbias + c0, c0, ea, stage, lane, rm, p.mask_y, p.ldmask, p.y, p.ldy);
-                else if (pix_ok) epilogue_chunk(v, sbias + c0, c0, ea, mrow, yrow, vec);
+                if (vec) epilogue_half_coalesced(v, sbias + c0, c0, ea, stage, lane, rm, p.mask_y, p.ldmask, p.y, p.ldy);
+                else if (pix_ok) epilogue_half_scalar(v, sbias + c0, c0, ea, mrow, yrow);
                 e_st += clock64() - c1;
             }
             tc_fence_before();
@@ -690,7 +812,7 @@ struct HaloStreamParams {
 constexpr int HS_BN = 64;        // cout tile of the streamed kernel
 constexpr int HS_STAGES = 2;
 
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(HALO_THREADS)
 conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                                  const HaloStreamParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -705,8 +827,8 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
     const long long t_start = clock64();
 
     __shared__ float sbias[512];
-    __shared__ __align__(16) float epi_stage[4 * 32 * EPI_PITCH];
-    for (int i = threadIdx.x; i < 512; i += NTHREADS) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+    __shared__ __align__(16) float epi_stage[8 * 32 * EPI16_PITCH];
+    for (int i = threadIdx.x; i < 512; i += HALO_THREADS) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
@@ -714,8 +836,8 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
         }
         mbar_init(smem_u32(&bars[2 * S]), 1);
         mbar_init(smem_u32(&bars[2 * S + 1]), 1);
-        mbar_init(smem_u32(&bars[2 * S + 2]), 128);
-        mbar_init(smem_u32(&bars[2 * S + 3]), 128);
+        mbar_init(smem_u32(&bars[2 * S + 2]), 256);     // all eight epilogue warps release an accumulator buffer
+        mbar_init(smem_u32(&bars[2 * S + 3]), 256);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * HS_BN));
@@ -791,14 +913,10 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
                                           (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
                         }
                     } else {
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
-                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)tap * b_tile);
-                            for (int kk = 0; kk < last_ksteps; ++kk)
-                                umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
-                                          (ch > 0 || tap > 0 || kk > 0) ? 1u : 0u);
-                        }
+                        const uint32_t tap_b = b_tile;
+                        if (last_ksteps == 3) { MI_HALO_RAGGED(3) }
+                        else if (last_ksteps == 2) { MI_HALO_RAGGED(2) }
+                        else { MI_HALO_RAGGED(1) }
                     }
                     umma_commit(smem_u32(&bars[S + s]));
                     if (ch == p.chunks - 1) umma_commit(smem_u32(&bars[2 * S + buf]));
@@ -811,7 +929,8 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
             p.dbg[6] = (unsigned long long)t_first; p.dbg[7] = (unsigned long long)(clock64() - t_start);
         }
     } else {
-        const int q = warp & 3;
+        const int q = warp & 3;               // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;     // which 16-column half of every 32-column chunk it owns
         const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
         EpiArgs ea;
@@ -821,7 +940,7 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
         ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
         const int r = q * 32 + lane;
         const int th_i = r >> 3, tw_i = r & 7;
-        float* stage = epi_stage + q * 32 * EPI_PITCH;
+        float* stage = epi_stage + (warp - 2) * 32 * EPI16_PITCH;
         long long e_wait = 0;
         for (int t = 0; t < my_items; ++t) {
             const int buf = t & 1;
@@ -841,16 +960,16 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
             mbar_wait(smem_u32(&bars[2 * S + buf]), ((uint32_t)(t >> 1)) & 1u);
             e_wait += clock64() - c0;
             tc_fence_after();
-            RowMap rm;
-            rm.tw = HT_W; rm.y0 = ty_i * HT_H; rm.x0 = tx_i * HT_W; rm.h = p.h; rm.w = p.w; rm.img = img; rm.q = q;
+            RowMap16 rm;
+            rm.init(HT_W, ty_i * HT_H, tx_i * HT_W, p.h, p.w, img, q, lane);
 #pragma unroll
-            for (int c0i = 0; c0i < HS_BN; c0i += 32) {
+            for (int c0i = 16 * half; c0i < HS_BN; c0i += 32) {
                 if (co0 + c0i >= p.cout) break;                    // warp-uniform
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * HS_BN + c0i), v);
-                if (vec) epilogue_chunk_coalesced(v, sbias + co0 + c0i, co0 + c0i, ea, stage, lane, rm, p.mask_y, p.ldmask,
-                                                  p.y, p.ldy);
-                else if (pix_ok) epilogue_chunk(v, sbias + co0 + c0i, co0 + c0i, ea, mrow, yrow, vec);
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * HS_BN + c0i), v);
+                if (vec) epilogue_half_coalesced(v, sbias + co0 + c0i, co0 + c0i, ea, stage, lane, rm, p.mask_y, p.ldmask,
+                                                 p.y, p.ldy);
+                else if (pix_ok) epilogue_half_scalar(v, sbias + co0 + c0i, co0 + c0i, ea, mrow, yrow);
             }
             tc_fence_before();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[2 * S + 2 + buf])) : "memory");
@@ -1347,7 +1466,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
         hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
         const size_t b_total = (size_t)9 * hp.chunks * hp.bn * ROW_BYTES;
-        const size_t budget = 227 * 1024 - 20 * 1024 - 2048;   // 227 KB per CTA minus static smem (epilogue tile, bias)
+        const size_t budget = 227 * 1024 - 22 * 1024 - 2048;   // 227 KB per CTA minus static smem (epilogue tiles, bias)
         hp.halo_w = halo_pitch();
         hp.halo_bytes = (uint32_t)hp.halo_w * HALO_H * ROW_BYTES;
         hp.halo_stride = (hp.halo_bytes + 1023u) & ~1023u;
@@ -1378,7 +1497,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
                 cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), stream);
                 hp.dbg = dbg_buf;
             }
-            conv_fprop_tc_halo_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, hp);
+            conv_fprop_tc_halo_kernel<<<grid, HALO_THREADS, smem, stream>>>(map_x, map_w, hp);
             if (dbg_on) {
                 unsigned long long h[16];
                 cudaStreamSynchronize(stream);
@@ -1432,7 +1551,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
             }
             mi_prof_begin(MI_TAG_FPROP_STREAM, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
                           stream);
-            conv_fprop_tc_halo_stream_kernel<<<grid, NTHREADS, smem, stream>>>(map_x, map_w, hp);
+            conv_fprop_tc_halo_stream_kernel<<<grid, HALO_THREADS, smem, stream>>>(map_x, map_w, hp);
             mi_prof_end(stream);
             if (dbg_on) {
                 unsigned long long d[16];
