@@ -266,17 +266,22 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
             const long long e = i;
             const int ci = (int)(e % ldw);
             if (ci >= cin) continue;  // pad lanes stay zero
-            // four independent partial sums: the loads of a slice do not wait for the previous slice's add
-            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+            // eight independent partial sums: the loads of a slice do not wait for the previous slice's add
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f, g4 = 0.f, g5 = 0.f, g6 = 0.f, g7 = 0.f;
             int s = 0;
-            for (; s + 3 < splits; s += 4) {
-                g0 += ws_w[(long long)s * wsz + e];
-                g1 += ws_w[(long long)(s + 1) * wsz + e];
-                g2 += ws_w[(long long)(s + 2) * wsz + e];
-                g3 += ws_w[(long long)(s + 3) * wsz + e];
+            for (; s + 7 < splits; s += 8) {
+                const float* q = ws_w + (long long)s * wsz + e;
+                g0 += q[0];
+                g1 += q[wsz];
+                g2 += q[2 * wsz];
+                g3 += q[3 * wsz];
+                g4 += q[4 * wsz];
+                g5 += q[5 * wsz];
+                g6 += q[6 * wsz];
+                g7 += q[7 * wsz];
             }
             for (; s < splits; ++s) g0 += ws_w[(long long)s * wsz + e];
-            const float g = (g0 + g1) + (g2 + g3);
+            const float g = ((g0 + g1) + (g2 + g3)) + ((g4 + g5) + (g6 + g7));
             if (mode == MI_WG_STORE) {
                 grad_w[e] = g;
             } else if (mode == MI_WG_ACCUM) {
@@ -326,8 +331,10 @@ int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
         // filter-column kernel: grid = (3, splits) persistent CTAs over 8x8-pixel tiles; one wave of the 148 SMs,
         // at least four tiles per CTA so the pipeline fills
         const long long tiles = (long long)n * mi_cdiv(h, 8) * mi_cdiv(wd, 8);
+        const long long per_split = 3LL * mi_cdiv(cin, 64) * mi_cdiv(cout, 128);   // CTAs of one split-K slice
         long long s = tiles / 4;
-        if (s > 49) s = 49;
+        const long long cap = 148 / per_split;
+        if (s > cap) s = cap;
         if (s < 1) s = 1;
         return (int)s;
     }

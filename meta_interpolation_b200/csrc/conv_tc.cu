@@ -1122,7 +1122,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 //     32-channel block and tile row computes D[cout][(ky, cin)] for all three ky at once.
 // L2 traffic drops from 18 to ~6.4 activation passes and the MMA count per pixel by 3x.
 struct WgradKxParams {
-    int n, h, w, cin, cout, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb;
+    int n, h, w, cin, cout, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb, ci_tiles;
     float* ws_w;
 };
 
@@ -1145,7 +1145,11 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const uint32_t tmem_cols = p.nb == 1 ? 128u : 256u;              // nb * 96 accumulator columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kx = blockIdx.x;
+    // blockIdx.x = kx + 3 * (cin tile of 64 + ci_tiles * cout tile of 128): wider layers are cut into channel blocks,
+    // each block re-reading its dY / X boxes (3 * ci_tiles and 3 * co_tiles passes instead of 9 * tiles of the per-tap form)
+    const int kx = (int)blockIdx.x % 3;
+    const int ct = (int)blockIdx.x / 3;
+    const int ci0 = (ct % p.ci_tiles) * 64, co0 = (ct / p.ci_tiles) * BM;
     const int split = blockIdx.y;
     const int t_begin = split * p.tiles_per_split;
     const int t_end = min(t_begin + p.tiles_per_split, p.total_tiles);
@@ -1184,9 +1188,9 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
                 mbar_expect_tx(full, stage_bytes);
                 for (int j = 0; j < p.na; ++j)
-                    tma_load_4d(base + j * a_box, &map_dy, full, j * KCH, x0, y0, img);
+                    tma_load_4d(base + j * a_box, &map_dy, full, co0 + j * KCH, x0, y0, img);
                 for (int j = 0; j < p.nb; ++j)
-                    tma_load_4d(base + a_bytes + j * b_box, &map_x, full, j * KCH, x0 + kx - 1, y0 - 1, img);
+                    tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - 1, y0 - 1, img);
             }
         }
     } else if (warp == 1) {
@@ -1215,7 +1219,7 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         }
     } else {
         const int q = warp & 3;
-        const int co = q * 32 + lane;
+        const int co = co0 + q * 32 + lane;
         float* dst0 = p.ws_w + (long long)split * p.cout * 9 * p.ldw + (long long)co * 9 * p.ldw;
         if (iters > 0) {
             mbar_wait(smem_u32(&bars[2 * p.stages]), 0);
@@ -1231,7 +1235,8 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
                 }
                 if (co >= p.cout) continue;
-                const int cb = j * KCH;
+                const int cb = ci0 + j * KCH;
+                if (cb >= p.cin) continue;
                 float* dst = dst0 + (ky * 3 + kx) * p.ldw;
                 if (cb + 32 <= p.ldw) {
 #pragma unroll
@@ -1606,14 +1611,15 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
     MI_RETURN_LAST();
 }
 
-// 3x3, Cin <= 64, Cout <= 128: the filter-column kernel (MI_B200_WGRAD_KX=0 keeps the per-tap kernel: A/B switch)
+// every 3x3 layer takes the filter-column kernel (MI_B200_WGRAD_KX=0 keeps the per-tap kernel: A/B switch)
 bool mi_tc_wgrad_kx_shape(int cin, int cout, int k) {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("MI_B200_WGRAD_KX");
         on = (e && e[0] == '0') ? 0 : 1;
     }
-    return on && k == 3 && cin <= 64 && cout <= 128 && device_is_sm100() && encode_fn();
+    (void)cin; (void)cout;
+    return on && k == 3 && device_is_sm100() && encode_fn();
 }
 
 bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
@@ -1636,8 +1642,10 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         q.tiles_y = mi_cdiv(h, q.rows);
         q.total_tiles = q.tiles_x * q.tiles_y * n;
         q.tiles_per_split = mi_cdiv(q.total_tiles, splits);
-        q.na = mi_cdiv(cout, KCH);
-        q.nb = mi_cdiv(cin, KCH);
+        q.na = cout >= BM ? 4 : mi_cdiv(cout, KCH);      // dY boxes per CTA (a partial last cout tile is zero-filled)
+        q.nb = cin >= 64 ? 2 : mi_cdiv(cin, KCH);        // X boxes per CTA
+        q.ci_tiles = mi_cdiv(cin, 64);
+        const int co_tiles = mi_cdiv(cout, BM);
         q.ws_w = ws_w;
         const size_t row_bytes = 8 * ROW_BYTES;
         const size_t stage_bytes = (size_t)q.na * q.rows * row_bytes + (size_t)q.nb * (q.rows + 2) * row_bytes;
@@ -1659,7 +1667,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
             if (e != cudaSuccess) return (int)e;
             attr_kx = true;
         }
-        dim3 grid(3, splits);
+        dim3 grid(3 * q.ci_tiles * co_tiles, splits);
         mi_prof_begin(MI_TAG_WGRAD_KX, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
         conv_wgrad_tc_kx_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, q);
         mi_prof_end(stream);
