@@ -1139,7 +1139,7 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     // the M=128 A descriptor always spans four 32-channel blocks; blocks past `na` alias whatever follows (the X
     // boxes, the next stage, or the zeroed tail pad after the last stage) and only feed accumulator rows >= cout,
     // which are never read back
-    const uint32_t tail_pad = 4u * a_box;
+    const uint32_t tail_pad = (uint32_t)(4 - p.na) * a_box;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + tail_pad);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
     const uint32_t tmem_cols = p.nb == 1 ? 128u : 256u;              // nb * 96 accumulator columns
@@ -1637,23 +1637,31 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
     if (mi_tc_wgrad_kx_shape(cin, cout, k)) {
         WgradKxParams q;
         q.n = n; q.h = h; q.w = wd; q.cin = cin; q.cout = cout; q.ldw = ldw;
-        q.rows = 8;
-        q.tiles_x = mi_cdiv(wd, 8);
-        q.tiles_y = mi_cdiv(h, q.rows);
-        q.total_tiles = q.tiles_x * q.tiles_y * n;
-        q.tiles_per_split = mi_cdiv(q.total_tiles, splits);
         q.na = cout >= BM ? 4 : mi_cdiv(cout, KCH);      // dY boxes per CTA (a partial last cout tile is zero-filled)
         q.nb = cin >= 64 ? 2 : mi_cdiv(cin, KCH);        // X boxes per CTA
         q.ci_tiles = mi_cdiv(cin, 64);
         const int co_tiles = mi_cdiv(cout, BM);
         q.ws_w = ws_w;
         const size_t row_bytes = 8 * ROW_BYTES;
-        const size_t stage_bytes = (size_t)q.na * q.rows * row_bytes + (size_t)q.nb * (q.rows + 2) * row_bytes;
-        const size_t tail = 4 * (size_t)q.rows * row_bytes;
-        int stages = (int)((200 * 1024 - tail) / stage_bytes);
-        if (stages > 6) stages = 6;
+        // Tile height: every pipeline stage costs the MMA lane one barrier wait (~450 cycles), so the narrow layers
+        // (one or two boxes per operand: 8-16 MMAs per 8-row stage) take 16-row tiles when three stages still fit.
+        // (the split count was sized on 8x8 tiles; with 16 rows a CTA simply walks half as many, twice as large)
+        int rows = 16, stages = 0;
+        size_t stage_bytes = 0, tail = 0;
+        for (;; rows = 8) {
+            stage_bytes = (size_t)q.na * rows * row_bytes + (size_t)q.nb * (rows + 2) * row_bytes;
+            tail = (size_t)(4 - q.na) * rows * row_bytes;
+            stages = (int)((200 * 1024 - tail) / stage_bytes);
+            if (stages > 6) stages = 6;
+            if (rows == 8 || (stages >= 3 && h >= 16)) break;
+        }
         if (stages < 2) return MI_ERR_UNSUPPORTED;
+        q.rows = rows;
         q.stages = stages;
+        q.tiles_x = mi_cdiv(wd, 8);
+        q.tiles_y = mi_cdiv(h, q.rows);
+        q.total_tiles = q.tiles_x * q.tiles_y * n;
+        q.tiles_per_split = mi_cdiv(q.total_tiles, splits);
         const size_t smem = stages * stage_bytes + tail + (2 * stages + 2) * 8 + 1024;
         CUtensorMap map_dy, map_x;
         if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, 8, q.rows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
