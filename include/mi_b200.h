@@ -278,8 +278,15 @@ int mi_outer_step(float* p, const float* g, float* m, float* v, size_t count, in
 int mi_axpby(const float* x, float a, float* y, float b, size_t count, mi_stream_t stream);
 /* y[i] += a * x1[i] * x2[i]  (Meta-SGD alpha gradient  -gsum (.) G, SURVEY Appx E4) */
 int mi_addcmul(float* y, float a, const float* x1, const float* x2, size_t count, mi_stream_t stream);
-/* out[t] = sum over tensor t of a[i]*b[i]  (lr / gamma outer gradients, SURVEY Appx E4); segs as above; out zeroed by caller */
+/* out[t] = sum over tensor t of a[i]*b[i]  (lr / gamma outer gradients, SURVEY Appx E4); segs as above; out zeroed by
+ * caller.  b == NULL sums a alone (per-tensor mean of the support gradient = the L2F task embedding,
+ * meta_learning_system.py:231-255). */
 int mi_segment_dot(const float* a, const float* b, const int32_t* seg, float* out, size_t count, mi_stream_t stream);
+/* y[i] (+)= alpha * s(t) * x[i] with s(t) = scale[t] where mask[t] != 0 (mask == NULL: everywhere), else 1.
+ * L2F attenuation theta_i <- gamma_i * theta_i (meta_learning_system.py:258-272) and its outer gradient
+ * dL/dtheta_i += gamma_i * G_i on the flat arena. */
+int mi_segment_scale(const float* x, const float* scale, const int32_t* seg, const float* mask, float* y, float alpha,
+                     int accumulate, size_t count, mi_stream_t stream);
 
 #ifdef __cplusplus
 }

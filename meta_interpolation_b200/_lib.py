@@ -79,6 +79,7 @@ SIGNATURES = {
     "mi_axpby": (_i, [_f, _fl, _f, _fl, _sz, _st]),
     "mi_addcmul": (_i, [_f, _fl, _f, _f, _sz, _st]),
     "mi_segment_dot": (_i, [_f, _f, _f, _f, _sz, _st]),
+    "mi_segment_scale": (_i, [_f, _f, _f, _f, _f, _fl, _i, _sz, _st]),
 }
 
 

@@ -513,7 +513,7 @@ __global__ void segment_dot_kernel(const float* __restrict__ a, const float* __r
     float local = 0.f;
     for (int q = threadIdx.x; q < 1024; q += blockDim.x) {
         const long long i = base + q;
-        if (i < count) local += a[i] * b[i];
+        if (i < count) local += b ? a[i] * b[i] : a[i];
     }
     __shared__ float red[TPB / 32];
 #pragma unroll
@@ -524,6 +524,20 @@ __global__ void segment_dot_kernel(const float* __restrict__ a, const float* __r
         float v = 0.f;
         for (int q = 0; q < TPB / 32; ++q) v += red[q];
         atomicAdd(out + t, v);
+    }
+}
+
+// y (+)= alpha * s(t) * x over a flat arena, with s(t) = scale[t] for the tensors selected by `mask` (all when NULL)
+// and 1 otherwise; padding chunks are left untouched.  L2F: theta' = gamma (.) theta and dL/dtheta += gamma (.) G.
+__global__ void segment_scale_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                     const int32_t* __restrict__ seg, const float* __restrict__ mask,
+                                     float* __restrict__ y, float alpha, int accumulate, long long count) {
+    GRID_STRIDE(i, count) {
+        const int t = seg[i >> 10];
+        if (t < 0) continue;
+        const float sc = (!mask || mask[t] != 0.f) ? scale[t] : 1.f;
+        const float v = alpha * sc * x[i];
+        y[i] = accumulate ? y[i] + v : v;
     }
 }
 
@@ -687,8 +701,13 @@ int mi_outer_step(float* p, const float* g, float* m, float* v, size_t count, in
     LAUNCH(outer_step_kernel, (long long)count, s, p, g, m, v, (long long)count, kind, lr, beta1, beta2, eps,
            weight_decay, step_size, bc2s);
 }
+int mi_segment_scale(const float* x, const float* scale, const int32_t* seg, const float* mask, float* y, float alpha,
+                     int accumulate, size_t count, mi_stream_t s) {
+    if (!x || !scale || !seg || !y) return MI_ERR_BAD_ARG;
+    LAUNCH(segment_scale_kernel, (long long)count, s, x, scale, seg, mask, y, alpha, accumulate, (long long)count);
+}
 int mi_segment_dot(const float* a, const float* b, const int32_t* seg, float* out, size_t count, mi_stream_t s) {
-    if (!a || !b || !seg || !out) return MI_ERR_BAD_ARG;
+    if (!a || !seg || !out) return MI_ERR_BAD_ARG;
     const int chunks = (int)((count + 1023) >> 10);
     segment_dot_kernel<<<chunks, TPB, 0, mi_cs(s)>>>(a, b, seg, out, (long long)count);
     MI_LAUNCHED();

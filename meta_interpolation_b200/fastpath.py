@@ -155,7 +155,9 @@ class _Lane:
         self.fast = Arena(lay, dev)
         self.cur_lr = torch.zeros(len(net.param_names), device=dev)
         self.gsum = Arena(lay, dev) if fp.metasgd else None
-        self.gquery = Arena(lay, dev) if (fp.metasgd or fp.learnable_lr) else None
+        self.gquery = Arena(lay, dev) if (fp.metasgd or fp.learnable_lr or fp.l2f) else None
+        self.gamma = None        # L2F attenuation of the task in flight
+        self.l2f_records = []    # (task embedding, dL/dgamma) per adapted task, consumed once per meta-batch
         self.gsteps = []
         self.dots = torch.zeros(len(net.param_names), device=dev)
         self.programs = {}
@@ -209,8 +211,16 @@ class FastPath:
         a = system.args
         if a.second_order and system.current_epoch > a.first_order_to_second_order_epoch:
             return False
-        if a.optimizer != 'SGD' or a.attenuate:
+        if a.optimizer != 'SGD':
             return False
+        if a.attenuate:
+            # L2F (reference :231-272) is graph-captured for the plain fixed-lr LSLR rule; its combinations with
+            # Meta-SGD / learnable lr / the multi-step loss stay on the compat path
+            if a.metasgd or a.learnable_per_layer_per_step_inner_loop_learning_rate or \
+                    a.use_multi_step_loss_optimization:
+                return False
+            if len(system.get_inner_loop_parameter_dict(system.net.named_parameters())) != len(system.net.param_names):
+                return False
         if not all(t.split('*')[1] in LOSS_KIND for t in a.loss.split('+')):
             return False
         if a.metasgd and any(not system.net.is_routed(n) for n in system.net.param_names):
@@ -224,6 +234,7 @@ class FastPath:
         a = system.args
         self.metasgd = bool(a.metasgd)
         self.learnable_lr = (not self.metasgd) and bool(a.learnable_per_layer_per_step_inner_loop_learning_rate)
+        self.l2f = bool(a.attenuate)
         self.K = a.number_of_training_steps_per_iter
         self.use_graphs = bool(system.use_cuda_graphs) and self.ops.name == 'cuda'
         dev = self.ops.device
@@ -231,6 +242,7 @@ class FastPath:
         self.seg = lay.segment_table().to(dev)
         self.routed_mask = torch.tensor([1.0 if self.net.is_routed(n) else 0.0 for n in self.net.param_names],
                                         device=dev)
+        self.numel = torch.tensor([float(lay.logical_numel(n)) for n in self.net.param_names], device=dev)
         self.loss_terms = [(LOSS_KIND[t.split('*')[1]], float(t.split('*')[0])) for t in a.loss.split('+')]
         self.meta_wt = {}
         # measured on B200, SepConv 256x448 K=5: 1 lane 22.7, 2 lanes 27.9, 3 lanes 29.2, 4 lanes 30.1 tasks/s
@@ -296,6 +308,50 @@ class FastPath:
             tape.backward()
         return body
 
+    def _embed_body(self, lane):
+        """L2F task embedding (reference :231-255): both support triplets through the META weights, gradient of the
+        summed support loss w.r.t. every tensor stored into the lane's gradient arena."""
+        def body(prog):
+            self.ops.set_workspace_slot(lane.index)
+            sink = _Sink(lane, 'store')
+            tape = Tape(self.ops, self._provider(lane, 'meta'), sink, vectors=self.net.meta_bn)
+            out = self.net.build_graph(tape, prog.f0, prog.f1)
+            out.grad = self._loss(prog, out.data, prog.f0.shape[0])
+            tape.backward()
+        return body
+
+    def _attenuate(self, lane, frames, task, h, w, support_idxs):
+        """gamma = clamp(1 - gamma_mult * attenuator(emb), 0, 1); fast <- gamma (.) theta (reference :258-272)."""
+        ops, sysm = self.ops, self.sys
+        prog = self._program(lane, ('embed', h, w), self._embed_body(lane), len(support_idxs), h, w)
+        for i, (a, b, c) in enumerate(support_idxs):
+            prog.f0[i].copy_(frames[a][task])
+            prog.f1[i].copy_(frames[c][task])
+            prog.tgt[i].copy_(frames[b][task])
+        prog.run()
+        ops.fill(lane.dots, 0.0)
+        ops.segment_dot(lane.gquery.flat, None, self.seg, lane.dots)
+        emb = lane.dots / self.numel                       # per-tensor mean of the support gradient
+        with torch.no_grad():
+            gamma = (1 - sysm.gamma_mult * sysm.attenuator(emb)).clamp(0, 1).contiguous()
+        lane.gamma = gamma
+        ops.segment_scale(self.net.arena.flat, gamma, self.seg, None, lane.fast.flat, 1.0, False)
+        for name in self.net.conv_names:                   # rotated copies of the attenuated weights for step 0
+            if self.net.is_routed(name + ".weight"):
+                ops.weight_to_dgrad(lane.fast.kernel_view(name + ".weight"), out=lane.wt_buffer(name))
+        return emb
+
+    def _l2f_outer(self, lane, emb, scale):
+        """First-order outer gradients through the attenuation: dL/dtheta_i += gamma_i G_i on the adapted tensors
+        (G_i itself elsewhere) and dL/dgamma_i = <G_i, theta_i>; the attenuator / gamma_mult gradients follow from
+        dL/dgamma by autograd over the small MLP once per meta-batch."""
+        ops = self.ops
+        G = lane.gquery.flat
+        ops.segment_scale(G, lane.gamma, self.seg, self.routed_mask, lane.acc_theta.flat, scale, True)
+        ops.fill(lane.dots, 0.0)
+        ops.segment_dot(G, self.net.arena.flat, self.seg, lane.dots)
+        lane.l2f_records.append((emb.clone(), (lane.dots * self.routed_mask * scale).clone()))
+
     def _query_body(self, lane, src, mode, backward=True):
         def body(prog):
             self.ops.set_workspace_slot(lane.index)
@@ -320,7 +376,7 @@ class FastPath:
 
     # ------------------------------------------------------------------ one task
     def _support_step(self, lane, frames, task, step, h, w, support_idxs):
-        src = 'meta' if step == 0 else 'fast'
+        src = 'meta' if (step == 0 and not self.l2f) else 'fast'     # L2F: step 0 starts from gamma (.) theta
         slot = step if self.learnable_lr else 0
         prog = self._program(lane, ('support', src, slot, h, w), self._support_body(lane, src, slot),
                              len(support_idxs), h, w)
@@ -370,6 +426,7 @@ class FastPath:
         extras = training and (self.metasgd or self.learnable_lr)
         task_loss = torch.zeros(1, device=self.ops.device)
         prog = None
+        emb = self._attenuate(lane, frames, task, h, w, support_idxs) if self.l2f else None
         for step in range(num_steps):
             self._support_step(lane, frames, task, step, h, w, support_idxs)
             if msl:
@@ -381,9 +438,12 @@ class FastPath:
                     prog = self._query(lane, frames, task, 'fast', h, w, 'accum', scale * wk)
                 task_loss += wk * prog.loss
         if not msl:
-            src = 'fast' if num_steps > 0 else 'meta'
+            src = 'fast' if (num_steps > 0 or self.l2f) else 'meta'
             if not training:
                 prog = self._query(lane, frames, task, src, h, w, 'none', 0.0, backward=False)
+            elif self.l2f:
+                prog = self._query(lane, frames, task, src, h, w, 'store', 1.0)
+                self._l2f_outer(lane, emb, scale)
             elif extras:
                 prog = self._query(lane, frames, task, src, h, w, 'store', 1.0)
                 self._outer_extras(lane, scale, num_steps)
@@ -453,6 +513,15 @@ class FastPath:
         losses_dev, preds = self._run_tasks(frames, task_ids, self.K, epoch, True, scale, msl, msl_w)
         for lane in self.lanes:
             lane.reduce_into_system()
+        if self.l2f:
+            # attenuator / gamma_mult gradients: gamma_t = f(emb_t) re-evaluated under autograd with the embedding
+            # as a constant (the reference's embedding carries no graph either: create_graph=False, :246-247)
+            for lane in self.lanes:
+                for emb, dldg in lane.l2f_records:
+                    gamma = (1 - sysm.gamma_mult * sysm.attenuator(emb)).clamp(0, 1)
+                    gamma.backward(dldg)
+                lane.l2f_records = []
+            sysm.optimizer.gather_grads()
         names = [t.split('*')[1] for t in a.loss.split('+')]
         return self._finish(frames, task_ids, losses_dev, preds, do_evaluation, msl_w, names)
 

@@ -524,5 +524,13 @@ class CudaOps:
                                        self._stream()), "mi_addcmul")
 
     def segment_dot(self, a, b, seg, out):
-        _lib.check(self.lib.mi_segment_dot(a.data_ptr(), b.data_ptr(), seg.data_ptr(), out.data_ptr(), a.numel(),
+        """out[t] += <a_t, b_t> per arena tensor; b=None sums a alone."""
+        _lib.check(self.lib.mi_segment_dot(a.data_ptr(), self._p(b), seg.data_ptr(), out.data_ptr(), a.numel(),
                                            self._stream()), "mi_segment_dot")
+
+    def segment_scale(self, x, scale, seg, mask, y, alpha=1.0, accumulate=False):
+        """y (+)= alpha * s(t) * x with s(t) = scale[t] on the tensors selected by mask (None: all), 1 elsewhere."""
+        assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+        _lib.check(self.lib.mi_segment_scale(x.data_ptr(), scale.data_ptr(), seg.data_ptr(), self._p(mask),
+                                             y.data_ptr(), float(alpha), int(accumulate), x.numel(), self._stream()),
+                   "mi_segment_scale")

@@ -552,6 +552,18 @@ class RefOps:
     def segment_dot(self, a, b, seg, out):
         n = a.numel()
         t = seg.long().repeat_interleave(1024)[:n]
-        prod = (a.reshape(-1) * b.reshape(-1))
+        prod = a.reshape(-1) if b is None else (a.reshape(-1) * b.reshape(-1))
         valid = t >= 0
         out.index_add_(0, t[valid], prod[valid])
+
+    def segment_scale(self, x, scale, seg, mask, y, alpha=1.0, accumulate=False):
+        n = x.numel()
+        t = seg.long().repeat_interleave(1024)[:n]
+        valid = t >= 0
+        tc = t.clamp(min=0)
+        sc = scale.reshape(-1)[tc]
+        if mask is not None:
+            sc = torch.where(mask.reshape(-1)[tc] != 0, sc, torch.ones_like(sc))
+        v = alpha * sc * x.reshape(-1)
+        yy = y.reshape(-1)
+        yy[valid] = (yy[valid] + v[valid]) if accumulate else v[valid]

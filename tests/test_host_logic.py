@@ -47,7 +47,7 @@ def test_plugin_forward_and_unrouted_grads_are_none_after_step0(ref_ops):
                                        ("sepconv_lslr_learnable_msl_k2", True),
                                        ("sepconv_lslr_learnable_msl_k2", False),
                                        ("sepconv_lslr_adam_k2", False), ("sepconv_metasgd_adamax_k2", False),
-                                       ("sepconv_l2f_sgd_k1", False)])
+                                       ("sepconv_l2f_sgd_k1", False), ("sepconv_l2f_sgd_k1", True)])
 def test_system_against_reference_golden(ref_ops, name, fast):
     fx = load_golden(name)
     system = system_from_fixture(fx, ref_ops, fast_path=fast)
@@ -117,9 +117,7 @@ def test_flow_systems_against_reference_golden(ref_ops, name, fast):
     """BASELINE configs[0] (voxelflow 128x128 K=1) and configs[2..4] in miniature against the reference's outputs."""
     fx = load_golden(name)
     system = system_from_fixture(fx, ref_ops, fast_path=fast)
-    if fast and not system.fast_path_supported():
-        assert fx["args"]["attenuate"]      # L2F is the only configuration here the graph path does not cover
-        pytest.skip("compat path only")
+    assert system.fast_path_supported() == fast     # every configuration here, L2F included, has a graph path
     frames = list(fx["frames"])
     losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
     scale = max(1.0, fx["preds"].abs().max().item())           # cain's default init explodes (|pred| ~ 1e2)
@@ -174,3 +172,28 @@ def test_extract_top_level_dict():
     d = {"a.0.weight": 1, "a.0.bias": 2, "b.weight": 3, "c": 4, "layer_dict.e.f": 5}
     out = extract_top_level_dict(d)
     assert out == {"a": {"0.weight": 1, "0.bias": 2}, "b": {"weight": 3}, "c": 4, "e": {"f": 5}}
+
+
+@pytest.mark.parametrize("name", ["sepconv_l2f_sgd_k1"])
+def test_l2f_graph_path_matches_compat_path_on_attenuator_gradients(ref_ops, name):
+    """The goldens digest only the backbone parameters; the L2F-specific outer gradients (gamma_mult, attenuator
+    MLP; reference meta_learning_system.py:107-117, 258-272) are checked path against path: the graph path derives
+    them from dL/dgamma_i = <G_i, theta_i>, the compat path from autograd through the whole inner loop."""
+    fx = load_golden(name)
+    delta = {}
+    for fast in (False, True):
+        system = system_from_fixture(fx, ref_ops, fast_path=fast)
+        with torch.no_grad():
+            system.gamma_mult.fill_(0.3)      # away from the init (0), where the attenuator gradients vanish
+        system.optimizer.param_groups[0]["lr"] = 1.0    # SGD outer step: the parameter change IS minus the gradient
+        pick = lambda: {k: v.detach().clone() for k, v in system.state_dict().items()
+                        if k.startswith("attenuator") or k == "gamma_mult"}
+        before = pick()
+        system.run_train_iter(list(fx["frames"]), epoch=0)
+        after = pick()
+        delta[fast] = {k: after[k] - before[k] for k in before}
+    assert delta[True]["gamma_mult"].abs().item() > 0
+    for k in delta[False]:
+        a, b = delta[True][k], delta[False][k]
+        assert b.abs().max().item() > 0, k                         # every L2F tensor receives a gradient
+        assert (a - b).abs().max().item() <= 1e-3 * b.abs().max().item(), (k, (a - b).abs().max().item())

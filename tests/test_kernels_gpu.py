@@ -324,6 +324,25 @@ def test_axpby_addcmul_segment_dot_fill(cuda_ops):
     assert float(yd.min()) == 3.0 == float(yd.max())
 
 
+def test_segment_scale_and_segment_sum(cuda_ops):
+    """L2F arena ops: theta' = gamma (.) theta, dL/dtheta += a * gamma' (.) G, per-tensor sums (embedding)."""
+    n = 5 * 1024
+    g = torch.Generator().manual_seed(40)
+    x, y0 = torch.rand(n, generator=g) - 0.5, torch.rand(n, generator=g)
+    seg = torch.tensor([0, 0, 1, -1, 2], dtype=torch.int32)
+    gamma, mask = torch.rand(3, generator=g), torch.tensor([1.0, 0.0, 1.0])
+    for m, acc, alpha in ((None, False, 1.0), (mask, True, 0.25)):
+        yc, yd = y0.clone(), y0.clone().cuda()
+        REF.segment_scale(x, gamma, seg, m, yc, alpha, acc)
+        cuda_ops.segment_scale(x.cuda(), gamma.cuda(), seg.cuda(), None if m is None else m.cuda(), yd, alpha, acc)
+        close(yd, yc, 1e-6, "segment_scale")
+        assert torch.equal(yd[3 * 1024:4 * 1024].cpu(), y0[3 * 1024:4 * 1024])      # padding chunk untouched
+    oc, od = torch.zeros(3), torch.zeros(3, device="cuda")
+    REF.segment_dot(x, None, seg, oc)
+    cuda_ops.segment_dot(x.cuda(), None, seg.cuda(), od)
+    close(od, oc, 1e-5, "segment sum")
+
+
 def test_bad_arguments_raise(cuda_ops):
     from meta_interpolation_b200._lib import MiB200Error
     x = cuda_ops.empty_act(1, 5, 5, 4)     # odd size cannot be pooled

@@ -16,7 +16,8 @@ LOSS_TOL = 5e-4
     ("sepconv_lslr_sgd_k2", True, True), ("sepconv_lslr_sgd_k2", True, False), ("sepconv_lslr_sgd_k2", False, False),
     ("sepconv_lslr_sgd_k1_b2_mse", True, True), ("sepconv_lslr_learnable_msl_k2", True, True),
     ("sepconv_lslr_learnable_msl_k2", False, False), ("sepconv_lslr_adam_k2", False, False),
-    ("sepconv_metasgd_adamax_k2", False, False), ("sepconv_l2f_sgd_k1", False, False)])
+    ("sepconv_metasgd_adamax_k2", False, False), ("sepconv_l2f_sgd_k1", False, False),
+    ("sepconv_l2f_sgd_k1", True, True), ("sepconv_l2f_sgd_k1", True, False)])
 def test_train_iter_against_reference_golden(cuda_ops, name, fast, graphs):
     fx = load_golden(name)
     system = system_from_fixture(fx, cuda_ops, fast_path=fast, cuda_graphs=graphs)
@@ -91,9 +92,7 @@ FLOW_GOLDEN = ["voxelflow_lslr_sgd_k1_mse", "voxelflow_lslr_sgd_k2_ragged", "sup
 def _run_flow_case(ops, name, fast, graphs, loss_tol, pred_tol):
     fx = load_golden(name)
     system = system_from_fixture(fx, ops, fast_path=fast, cuda_graphs=graphs)
-    if fast and not system.fast_path_supported():
-        assert fx["args"]["attenuate"]
-        pytest.skip("L2F runs on the compat path only")
+    assert system.fast_path_supported() == fast
     frames = [f.cuda() for f in fx["frames"]]
     n0 = ops.launch_count()
     losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
