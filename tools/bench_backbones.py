@@ -21,7 +21,7 @@ CONFIGS = {
                         number_of_training_steps_per_iter=5), (256, 448), 4,
                    "C3: superslomo Meta-SGD K=5 256x448, 4 tasks per GPU (32 over 8)"),
     "cain": (dict(model="cain", loss="1*L1", optimizer="SGD", attenuate=True, number_of_training_steps_per_iter=3),
-             (512, 512), 4, "C4: cain L2F K=3 512x512, 4 tasks per GPU (16 over 4); L2F runs on the compat path"),
+             (512, 512), 4, "C4: cain L2F K=3 512x512, 4 tasks per GPU (16 over 4)"),
     "rrin": (dict(model="rrin", loss="1*L1", optimizer="SGD", number_of_training_steps_per_iter=5,
                   learnable_per_layer_per_step_inner_loop_learning_rate=True, use_multi_step_loss_optimization=True,
                   multi_step_loss_num_epochs=1), (256, 448), 8,
