@@ -598,9 +598,10 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const uint32_t b_total = 9u * p.chunks * b_tile;
     uint8_t* smem_a = smem + b_total;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + (size_t)p.stages * p.halo_stride);
-    // bars: [0,S) full, [S,2S) empty, 2S = weights loaded, 2S+1..2 = tmem full[2], 2S+3..4 = tmem empty[2]
+    // bars: [0,S) full, [S,2S) empty, 2S = weights of chunk 0 loaded, 2S+1..2 = tmem full[2], 2S+3..4 = tmem empty[2],
+    // 2S+5 = weights of chunk 1 loaded
     const int S = p.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     __shared__ float sbias[64];
@@ -616,6 +617,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         mbar_init(smem_u32(&bars[2 * S + 2]), 1);
         mbar_init(smem_u32(&bars[2 * S + 3]), 256);     // all eight epilogue warps release an accumulator buffer
         mbar_init(smem_u32(&bars[2 * S + 4]), 256);
+        mbar_init(smem_u32(&bars[2 * S + 5]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * p.bn));
@@ -626,12 +628,14 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
     const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
+        // The resident weights arrive per 32-channel chunk, each behind its own barrier, with the first halo box in
+        // between: the MMAs of chunk 0 start as soon as its nine weight tiles (half of the 147 KB of a 64-channel
+        // layer) and the first halo are in, instead of after the whole filter bank (the wait was ~4.5 us per launch)
         if (elect_one()) {
             const uint32_t wbar = smem_u32(&bars[2 * S]);
-            mbar_expect_tx(wbar, b_total);
+            mbar_expect_tx(wbar, 9u * b_tile);
             for (int tap = 0; tap < 9; ++tap)
-                for (int ch = 0; ch < p.chunks; ++ch)
-                    tma_load_3d(smem_u32(smem) + (uint32_t)(tap * p.chunks + ch) * b_tile, &map_w, wbar, ch * KCH, tap, 0);
+                tma_load_3d(smem_u32(smem) + (uint32_t)(tap * p.chunks) * b_tile, &map_w, wbar, 0, tap, 0);
         }
         __syncwarp();
         int it = 0;
@@ -653,9 +657,22 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
                     mbar_expect_tx(full, p.halo_bytes);
                     tma_load_4d(smem_u32(smem_a + (size_t)s * p.halo_stride), &map_x, full, ch * KCH, tx_i * HT_W - 1,
                                 ty_i * HT_H - 1, img);
+                    if (it == 0 && p.chunks > 1) {
+                        const uint32_t wbar = smem_u32(&bars[2 * S + 5]);
+                        mbar_expect_tx(wbar, 9u * b_tile);
+                        for (int tap = 0; tap < 9; ++tap)
+                            tma_load_3d(smem_u32(smem) + (uint32_t)(tap * p.chunks + 1) * b_tile, &map_w, wbar, KCH, tap, 0);
+                    }
                 }
                 __syncwarp();
             }
+        }
+        if (my_tiles == 0 && p.chunks > 1 && elect_one()) {
+            // (a CTA without tiles still owes the second barrier its bytes before the block may retire)
+            const uint32_t wbar = smem_u32(&bars[2 * S + 5]);
+            mbar_expect_tx(wbar, 9u * b_tile);
+            for (int tap = 0; tap < 9; ++tap)
+                tma_load_3d(smem_u32(smem) + (uint32_t)(tap * p.chunks + 1) * b_tile, &map_w, wbar, KCH, tap, 0);
         }
         if (p.dbg && blockIdx.x == 0 && lane == 0) {
             p.dbg[0] = (unsigned long long)t_empty; p.dbg[1] = (unsigned long long)(clock64() - t_begin);
@@ -667,6 +684,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         mbar_wait(smem_u32(&bars[2 * S]), 0);
         t_w = clock64() - t_begin;
         tc_fence_after();
+        if (my_tiles == 0 && p.chunks > 1) mbar_wait(smem_u32(&bars[2 * S + 5]), 0);   // in-flight TMA must land
         const uint32_t b_base = smem_u32(smem);
         const int last_ksteps = (p.cin - (p.chunks - 1) * KCH + 7) / 8;
         int it = 0;
@@ -684,6 +702,11 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
                 c0 = clock64();
                 mbar_wait(smem_u32(&bars[s]), ph);
                 t_full += clock64() - c0;
+                if (t == 0 && ch == 1) {
+                    c0 = clock64();
+                    mbar_wait(smem_u32(&bars[2 * S + 5]), 0);      // second half of the filter bank
+                    t_w += clock64() - c0;
+                }
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_base = smem_u32(smem_a + (size_t)s * p.halo_stride);
@@ -1479,7 +1502,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         if (stages > 6) stages = 6;
         if (stages >= 2) {
             hp.stages = stages;
-            const size_t smem = b_total + (size_t)stages * hp.halo_stride + (2 * stages + 6) * 8 + 1024;
+            const size_t smem = b_total + (size_t)stages * hp.halo_stride + (2 * stages + 7) * 8 + 1024;
             CUtensorMap map_x, map_w;
             if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, hp.halo_w, HALO_H)) return MI_ERR_UNSUPPORTED;
             if (!make_weight_map(&map_w, w, ldw, cout, 9, cin, hp.bn)) return MI_ERR_UNSUPPORTED;
