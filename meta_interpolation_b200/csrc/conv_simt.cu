@@ -125,6 +125,29 @@ conv_fprop_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
     }
 }
 
+// Tiled form of the rotation for layers wide enough to fill 32x32 tiles: per tap it is a (cout x cin) transpose, done
+// through shared memory so both the read (along cin) and the write (along cout) are 128-byte rows.  Pad lanes of wt
+// (co >= cout) are not touched: weight buffers are allocated zeroed and nothing ever writes those lanes.
+__global__ void __launch_bounds__(256)
+weight_to_dgrad_tiled_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt, int cin, int cout,
+                             int kk) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z;
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int co = co0 + ty + 8 * r, ci = ci0 + tx;
+        tile[ty + 8 * r][tx] = (co < cout && ci < cin) ? w[((long long)co * kk + tap) * ldw + ci] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int ci = ci0 + ty + 8 * r, co = co0 + tx;
+        if (ci < cin && co < cout) wt[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = tile[tx][ty + 8 * r];
+    }
+}
+
 // wt[ci][k-1-ky][k-1-kx][co] = w[co][ky][kx][ci]
 __global__ void weight_to_dgrad_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt,
                                        int cin, int cout, int k) {
@@ -325,6 +348,20 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
 
 }  // namespace
 
+int mi_weight_to_dgrad_launch(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, cudaStream_t st) {
+    if (cin >= 32 && cout >= 32) {
+        weight_to_dgrad_tiled_kernel<<<dim3(mi_cdiv(cin, 32), mi_cdiv(cout, 32), k * k), 256, 0, st>>>(w, ldw, wt, ldwt, cin,
+                                                                                                    cout, k * k);
+    } else {
+        const long long total = (long long)cin * k * k * ldwt;
+        int blocks = mi_cdiv(total, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        weight_to_dgrad_kernel<<<blocks, 256, 0, st>>>(w, ldw, wt, ldwt, cin, cout, k);
+    }
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
 int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
     const long long m_total = (long long)n * h * wd;
     if (mi_tc_wgrad_kx_shape(cin, cout, k)) {
@@ -422,13 +459,9 @@ int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt, float*
 
 int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, mi_stream_t stream) {
     if (!w || !wt || ldw < cin || ldwt < cout) return MI_ERR_BAD_ARG;
-    const long long total = (long long)cin * k * k * ldwt;
-    int blocks = mi_cdiv(total, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    weight_to_dgrad_kernel<<<blocks, 256, 0, mi_cs(stream)>>>(w, ldw, wt, ldwt, cin, cout, k);
-    MI_LAUNCHED();
-    MI_RETURN_LAST();
+    return mi_weight_to_dgrad_launch(w, ldw, wt, ldwt, cin, cout, k, mi_cs(stream));
 }
+
 
 size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k, int engine) {
     (void)engine;
@@ -479,8 +512,13 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
         rc = (int)cudaPeekAtLastError();
     }
     if (rc != 0) return rc;
-    return mi_wgrad_finish_launch(ws_w, ws_b, splits, bias_splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
-                                  w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, wt_out, ldwt, st);
+    // wide layers: the finishing kernel's rotated store would be one 4-byte write per 18 KB stride (measured 17 us on
+    // 512x512x9); there the updated weight is rotated by the tiled transpose right after instead
+    const bool rotate_after = wt_out && (long long)cin * cout >= 128LL * 128;
+    rc = mi_wgrad_finish_launch(ws_w, ws_b, splits, bias_splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
+                                w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, rotate_after ? nullptr : wt_out, ldwt, st);
+    if (rc != 0 || !rotate_after) return rc;
+    return mi_weight_to_dgrad_launch(w_out, ldw, wt_out, ldwt, cin, cout, k, st);
 }
 
 int mi_version(void) { return 100; }
