@@ -525,6 +525,22 @@ class FastPath:
         names = [t.split('*')[1] for t in a.loss.split('+')]
         return self._finish(frames, task_ids, losses_dev, preds, do_evaluation, msl_w, names)
 
+    def test_iter(self, frames):
+        """Test-time adaptation of 4-frame clips (reference run_test_iter, :630-697): support triplets (0,1,2) and
+        (1,2,3), query frames (1,2) with no ground truth; returns the raw predictions [1,3,H,W] per clip."""
+        sysm, a = self.sys, self.sys.args
+        msl_w = sysm.get_per_step_loss_importance_vector()
+        task_ids = list(range(len(frames[0])))
+        self.refresh_meta_wt()
+        saved = (sysm.support_idxs, sysm.target_idxs)
+        sysm.support_idxs, sysm.target_idxs = [[0, 1, 2], [1, 2, 3]], [1, 1, 2]    # (the query "target" is a dummy)
+        try:
+            _, preds = self._run_tasks(frames, task_ids, a.number_of_evaluation_steps_per_iter, 0, False, 0.0, False,
+                                       msl_w)
+        finally:
+            sysm.support_idxs, sysm.target_idxs = saved
+        return preds
+
     def eval_iter(self, frames, epoch):
         sysm, a = self.sys, self.sys.args
         msl_w = sysm.get_per_step_loss_importance_vector()

@@ -410,11 +410,57 @@ class SceneAdaptiveInterpolation(nn.Module):
             return self.fast_path().eval_iter(data_batch, self.current_epoch)
         return self.evaluation_forward_prop(data_batch=data_batch, epoch=self.current_epoch)
 
+    # ------------------------------------------------------------------ large frames
+    @staticmethod
+    def _halves(frames):
+        h, w = frames[0].shape[-2:]
+        if h > w:
+            return [im[..., :h // 2, :] for im in frames], [im[..., h // 2:, :] for im in frames], -2
+        return [im[..., :w // 2] for im in frames], [im[..., w // 2:] for im in frames], -1
+
+    def _needs_tiling(self, frames):
+        h, w = frames[0].shape[-2:]
+        return h * w > 5e5 or (self.args.model == 'rrin' and h * w > 3e5)
+
+    def run_validation_iter_tiled(self, data_batch):
+        """``ExperimentBuilder.evaluation_iteration``'s frame splitting (experiment_builder.py:101-128): frames above
+        5e5 pixels (3e5 for rrin) are halved along their longer side, recursively, each half adapted and predicted on
+        its own, predictions concatenated and losses averaged.  Returns (losses, preds) like the reference's
+        ``_eval_iter`` (its metrics are recomputed by the caller on the stitched frame)."""
+        frames = [f.to(device=self.device) for f in data_batch]
+        if not self._needs_tiling(frames):
+            losses, outputs, _ = self.run_validation_iter(frames)
+            losses['loss'] = losses['loss'].detach()
+            return losses, outputs
+        f0, f1, dim = self._halves(frames)
+        l0, o0 = self.run_validation_iter_tiled(f0)
+        l1, o1 = self.run_validation_iter_tiled(f1)
+        outputs = [torch.cat([a, b], dim=dim) for a, b in zip(o0, o1)]
+        losses = l0
+        for k, v in l1.items():
+            losses[k] = (v + losses[k]) / 2
+        losses['loss'] = losses['loss'].detach()
+        return losses, outputs
+
+    def run_test_iter_tiled(self, data_batch):
+        """``ExperimentBuilder.test_iteration`` (experiment_builder.py:153-172): ONE level of halving above 5e5 px."""
+        frames = [f.to(device=self.device) for f in data_batch]
+        h, w = frames[0].shape[-2:]
+        if h * w <= 5e5:
+            return self.run_test_iter(frames)
+        f0, f1, dim = self._halves(frames)
+        o0, o1 = self.run_test_iter(f0), self.run_test_iter(f1)
+        return [torch.cat([a, b], dim=dim) for a, b in zip(o0, o1)]
+
     def run_test_iter(self, data_batch):
         """reference :630-697: 4-frame clips, support [[0,1,2],[1,2,3]], query (1,2) -> list of [3,H,W]."""
         if self.training:
             self.eval()
         frames = [frame.to(device=self.device) for frame in data_batch]
+        if self.fast_path_supported():
+            outs = self.fast_path().test_iter(frames)
+            # reference :686-690 de-normalises superslomo only
+            return [(self._denorm(o) if self.args.model == 'superslomo' else o).squeeze(0) for o in outs]
         preds = [[] for _ in range(len(frames[0]))]
         self.net.zero_grad()
         support_idxs = [[0, 1, 2], [1, 2, 3]]

@@ -197,3 +197,40 @@ def test_l2f_graph_path_matches_compat_path_on_attenuator_gradients(ref_ops, nam
         a, b = delta[True][k], delta[False][k]
         assert b.abs().max().item() > 0, k                         # every L2F tensor receives a gradient
         assert (a - b).abs().max().item() <= 1e-3 * b.abs().max().item(), (k, (a - b).abs().max().item())
+
+
+@pytest.mark.parametrize("model,hw", [("sepconv", (32, 40)), ("superslomo", (64, 64))])
+def test_test_time_adaptation_graph_path_matches_compat_path(ref_ops, model, hw):
+    """run_test_iter (reference :630-697: 4-frame clips, support (0,1,2),(1,2,3), query (1,2)) through the captured
+    fast path equals the compat transcription of the reference's control flow."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    g = torch.Generator().manual_seed(11)
+    frames = [torch.rand(2, 3, *hw, generator=g) - (0.4 if model == "superslomo" else 0.0) for _ in range(4)]
+    outs = {}
+    for fast in (True, False):
+        s = SceneAdaptiveInterpolation(make_args(model=model, number_of_evaluation_steps_per_iter=2, fast_path=fast),
+                                       ops=ref_ops)
+        assert s.fast_path_supported() == fast
+        outs[fast] = s.run_test_iter(frames)
+    for a, b in zip(outs[True], outs[False]):
+        assert a.shape == (3,) + hw and (a - b).abs().max().item() <= 2e-6
+
+
+def test_tiled_evaluation_follows_experiment_builder_splitting(ref_ops, monkeypatch):
+    """Frames above 5e5 pixels are halved along the longer side (experiment_builder.py:101-128, 153-172)."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    s = SceneAdaptiveInterpolation(make_args(), ops=ref_ops)
+    calls = []
+
+    def fake_val(frames):
+        calls.append(tuple(frames[0].shape[-2:]))
+        return {"loss": torch.tensor(float(len(calls)))}, [f.clone() for f in frames[3]], None
+
+    monkeypatch.setattr(s, "run_validation_iter", fake_val)
+    frames = [torch.arange(2 * 3 * 8 * 6, dtype=torch.float32).view(2, 3, 8, 6) + i for i in range(7)]
+    monkeypatch.setattr(s, "_needs_tiling", lambda fr: fr[0].shape[-2] * fr[0].shape[-1] > 20)
+    losses, outs = s.run_validation_iter_tiled(frames)
+    # 8x6=48 > 20 -> halve rows (H > W): 4x6=24 > 20 -> halve columns (W > H): 4x3 = 12
+    assert calls == [(4, 3)] * 4
+    assert torch.equal(torch.stack(outs), frames[3])             # stitched back in place
+    assert float(losses["loss"]) == ((1 + 2) / 2 + (3 + 4) / 2) / 2

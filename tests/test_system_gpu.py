@@ -146,3 +146,20 @@ def test_flow_full_size_second_iteration_is_finite_and_replays(cuda_ops, model, 
         assert torch.isfinite(preds[0]).all()
     assert all(v == v and abs(v) < 1e4 for v in vals)
     assert abs(vals[1] - vals[2]) <= 1e-6 * max(1.0, abs(vals[1]))
+
+
+@pytest.mark.parametrize("model,hw", [("sepconv", (40, 56)), ("rrin", (64, 72))])
+def test_test_time_adaptation_graph_vs_compat(cuda_ops, model, hw):
+    """run_test_iter on the GPU: captured fast path (eager pass, then capture, then replay) vs the compat control flow."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    g = torch.Generator().manual_seed(21)
+    frames = [torch.rand(2, 3, *hw, generator=g).cuda() for _ in range(4)]
+    ref = SceneAdaptiveInterpolation(make_args(model=model, cuda=True, number_of_evaluation_steps_per_iter=2,
+                                               fast_path=False), ops=cuda_ops).run_test_iter(frames)
+    s = SceneAdaptiveInterpolation(make_args(model=model, cuda=True, number_of_evaluation_steps_per_iter=2),
+                                   ops=cuda_ops)
+    for it in range(3):
+        outs = s.run_test_iter(frames)
+        for a, b in zip(outs, ref):
+            assert a.shape == (3,) + hw
+            assert (a - b).abs().max().item() <= PRED_TOL, it
