@@ -544,9 +544,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         EpiArgs ea;
         ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
-        // the pad lane may be written only when the row is exactly the 4-padded width (not a concat slice)
-        const int c4 = (p.cout + 3) & ~3;
-        ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
+        ea.cout_store = p.cout;   // lanes past cout are never written: they may belong to the next concat slice
         RowMap rm;
         rm.init(p.tw, y0, x0, p.h, p.w, img, q, lane);
         float* stage = reinterpret_cast<float*>(smem) + q * 32 * EPI_PITCH;
@@ -766,9 +764,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         EpiArgs ea;
         ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
-        // the pad lane may be written only when the row is exactly the 4-padded width (not a concat slice)
-        const int c4 = (p.cout + 3) & ~3;
-        ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
+        ea.cout_store = p.cout;   // lanes past cout are never written: they may belong to the next concat slice
         float* stage = epi_stage + (warp - 2) * 32 * EPI16_PITCH;
         for (int t = 0; t < my_tiles; ++t) {
             const int buf = t & 1;
@@ -959,8 +955,7 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
         EpiArgs ea;
         ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
-        const int c4 = (p.cout + 3) & ~3;
-        ea.cout_store = (p.ldy == c4 && (!p.mask_y || p.ldmask == c4)) ? c4 : p.cout;
+        ea.cout_store = p.cout;   // lanes past cout are never written: they may belong to the next concat slice
         const int r = q * 32 + lane;
         const int th_i = r >> 3, tw_i = r & 7;
         float* stage = epi_stage + (warp - 2) * 32 * EPI16_PITCH;

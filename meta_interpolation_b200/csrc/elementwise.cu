@@ -33,7 +33,10 @@ __device__ __forceinline__ F4 ld4(const float* p, int valid, bool vec) {
     return r;
 }
 __device__ __forceinline__ void st4(float* p, const F4& r, int valid, bool vec) {
-    if (vec) {
+    // A ragged last group is stored lane by lane: whether the lanes past the channel count are padding or the first
+    // channels of the NEXT slice of a concat buffer cannot be told from (pointer, stride, count) -- a [0:2] slice of a
+    // 4-channel tensor looks exactly like a 2-channel tensor padded to 4 -- so they are never written.
+    if (vec && valid == 4) {
         *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
     } else {
 #pragma unroll
@@ -543,11 +546,10 @@ __global__ void segment_scale_kernel(const float* __restrict__ x, const float* _
 
 }  // namespace
 
-// float4 groups are legal when the row is 16-byte aligned and the 4-padded channel count fits in the row
-// (a ragged channel count may only use its pad lane when the row is exactly the padded width, i.e. the view is
-// not a channel slice of a wider concat buffer whose next slice starts in that lane)
+// float4 groups are legal when the row is 16-byte aligned and the 4-padded channel count fits in the row: lanes past
+// the channel count may be READ (padding or a neighbouring slice, never used as data) but are never written (st4)
 static inline bool mi_vec_ok(const void* p, int ld, int c) {
-    return mi_al16(p) && (ld % 4 == 0) && ((c % 4 == 0 && c <= ld) || ld == ((c + 3) & ~3));
+    return mi_al16(p) && (ld % 4 == 0) && (((c + 3) & ~3) <= ld);
 }
 
 #define LAUNCH(kernel, work, stream, ...)                                      \

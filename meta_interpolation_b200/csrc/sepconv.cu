@@ -218,13 +218,21 @@ sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ ve
             for (int cc = 0; cc < C; ++cc) gv = fmaf(go[cc], t[cc], gv);
             gvs[i] = gv;
         }
-        reinterpret_cast<float4*>(gvp)[q] = make_float4(gvs[0], gvs[1], gvs[2], gvs[3]);   // pad lane gets 0
+        if (4 * q + 4 <= F) {
+            reinterpret_cast<float4*>(gvp)[q] = make_float4(gvs[0], gvs[1], gvs[2], gvs[3]);
+        } else {                             // last group: the lane past tap 50 is not ours to write
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * q + i < F) gvp[4 * q + i] = gvs[i];
+        }
     }
     float* ghp = g_horiz + gpix * ldg;
 #pragma unroll
-    for (int g = 0; g < (F + 3) / 4; ++g)
+    for (int g = 0; g < F / 4; ++g)
         reinterpret_cast<float4*>(ghp)[g] =
             make_float4(gh_acc[4 * g], gh_acc[4 * g + 1], gh_acc[4 * g + 2], gh_acc[4 * g + 3]);
+#pragma unroll
+    for (int f = (F / 4) * 4; f < F; ++f) ghp[f] = gh_acc[f];
 }
 
 // any filter size / channel count: one thread per output pixel straight from global memory

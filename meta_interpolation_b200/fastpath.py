@@ -30,6 +30,7 @@ First-order outer gradients follow SURVEY Appendix E4:
   Meta-SGD (SGD)     + dL/dalpha    = -(sum_k g_k) (.) G
   multi-step loss    the above per step with weight w_k.
 """
+import gc
 import os
 
 import torch
@@ -131,8 +132,16 @@ class _Program:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = int(ops.lib.mi_launch_count())
-            with torch.cuda.graph(g, stream=self.lane.capture_stream):
-                self.body(self)
+            # no cyclic-GC pass while the stream is capturing: collecting an unreachable system of an earlier
+            # meta-batch would destroy its CUDA graphs / free their pools in the middle of this capture
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, stream=self.lane.capture_stream):
+                    self.body(self)
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self.kernels = int(ops.lib.mi_launch_count()) - n0   # recorded, not executed, during capture
             ops.replayed_launches -= self.kernels
             self.graph = g

@@ -20,6 +20,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+_POISON = os.environ.get("MI_B200_POISON", "") == "1"   # fill fresh activation / workspace buffers with NaN
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
 WG_STORE, WG_ACCUM, WG_SGD_SCALAR, WG_SGD_TENSOR = 0, 1, 2, 3
 
@@ -86,6 +87,8 @@ class CudaOps:
     def empty_act(self, n, h, w, c, zero_pad=False):
         ld = pad4(c)
         buf = torch.empty(n, h, w, ld, device=self.device, dtype=torch.float32)
+        if _POISON:      # debugging aid: a kernel that reads what nobody wrote turns the result into NaN
+            buf.fill_(float("nan"))
         if zero_pad and ld != c:
             buf[..., c:].zero_()
         return buf[..., :c] if ld != c else buf
@@ -118,6 +121,8 @@ class CudaOps:
                 # a captured CUDA graph may hold the old address: outgrown buffers are retired, never freed
                 self._ws.setdefault("retired", []).append(ws)
             ws = torch.empty(int(nbytes), device=self.device, dtype=torch.uint8)
+            if _POISON:
+                ws.fill_(255)          # 0xFFFFFFFF is a NaN pattern
             self._ws[slot] = ws
         return ws
 

@@ -99,3 +99,42 @@ def test_large_canvas_tc_vs_simt(cuda_ops):
     ys = ops.conv_fprop(x, w, b, engine=ENGINE_SIMT)
     d = (yt - ys).abs().max().item()
     assert d <= TF32_TOL * ys.abs().max().item(), d
+
+
+POISON_SHAPES = [
+    # n, h, w, cin, cout  (3x3): U-Net pyramids at miniature sizes -- few tiles, many channel blocks, concat inputs
+    (1, 64, 128, 6, 32), (1, 64, 128, 32, 32), (1, 32, 64, 32, 64), (1, 16, 32, 64, 128), (1, 8, 16, 128, 256),
+    (1, 4, 8, 256, 512), (1, 4, 8, 512, 512), (1, 8, 16, 1024, 512), (1, 16, 32, 512, 256), (1, 32, 64, 256, 128),
+    (1, 64, 128, 128, 64), (1, 64, 128, 64, 32), (2, 8, 8, 96, 160), (1, 16, 16, 200, 300), (1, 24, 40, 51, 51),
+    (1, 64, 128, 16, 32), (1, 64, 128, 10, 32), (1, 20, 24, 48, 48),
+    # the RRIN pyramid on a 128x128 canvas (batch 1), including its 9- and 10-channel inputs (row stride 12)
+    (1, 8, 8, 256, 512), (1, 8, 8, 512, 512), (1, 16, 16, 128, 256), (1, 16, 16, 512, 256), (1, 32, 32, 256, 128),
+    (1, 64, 64, 128, 64), (1, 128, 128, 9, 32), (1, 128, 128, 10, 32), (1, 128, 128, 64, 32), (1, 128, 128, 32, 32),
+]
+
+
+@pytest.mark.parametrize("shape", POISON_SHAPES)
+def test_wgrad_never_reads_stale_workspace(cuda_ops, shape):
+    """Every split-K partial the finishing kernel reads must have been written by the launch itself: the workspace is
+    poisoned with NaN before the call (a hole shows up as NaN / garbage only when the allocator hands back dirty
+    memory, i.e. depending on what ran before)."""
+    _require_tc(cuda_ops)
+    n, h, w, cin, cout = shape
+    k = 3
+    xc, xd = act_pair(cuda_ops, n, h, w, cin, 61)
+    dyc, dyd = act_pair(cuda_ops, n, h, w, cout, 62)
+    ld = pad4(cin)
+    for t, c in ((xd, cin), (dyd, cout)):        # pad lanes of the 4-padded rows are poisoned too
+        if pad4(c) != c:
+            t.as_strided((n, h, w, pad4(c)), (h * w * pad4(c), w * pad4(c), pad4(c), 1),
+                         t.storage_offset())[..., c:].fill_(float("nan"))
+    need = cuda_ops.lib.mi_conv2d_wgrad_workspace(n, h, w, cin, cout, k, 0)
+    ws = cuda_ops.workspace(need)
+    ws.view(torch.float32)[: ws.numel() // 4].fill_(float("nan"))
+    gwc, gwd = REF.empty_weight(cout, cin, k), cuda_ops.empty_weight(cout, cin, k)
+    gbc, gbd = torch.zeros(cout), torch.zeros(cout, device="cuda")
+    REF.conv_wgrad(xc, dyc, k, ld, WgradSpec(WG_STORE, grad_w=gwc, grad_b=gbc))
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_STORE, grad_w=gwd, grad_b=gbd))
+    assert torch.isfinite(gwd).all() and torch.isfinite(gbd).all()
+    close(gwd, gwc, TF32_TOL, "wgrad w")
+    close(gbd, gbc, 1e-4, "wgrad b")

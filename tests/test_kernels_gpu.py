@@ -416,3 +416,61 @@ def test_subnet_region_of_interest_equals_full_canvas(cuda_ops):
         assert (a is None) == (b is None)
         if a is not None:
             assert (a - b).abs().max().item() <= 2e-3 * max(b.abs().max().item(), 1e-8)
+
+
+def _poisoned(ops, n, h, w, c, seed):
+    """Activation whose pad lanes hold NaN (what a dirty allocator block looks like)."""
+    cpu, dev = act_pair(ops, n, h, w, c, seed)
+    if pad4(c) != c:
+        dev.as_strided((n, h, w, pad4(c)), (h * w * pad4(c), w * pad4(c), pad4(c), 1),
+                       dev.storage_offset())[..., c:].fill_(float("nan"))
+    return cpu, dev
+
+
+@pytest.mark.parametrize("c,width", [(2, 4), (6, 8), (3, 4), (18, 20), (51, 52)])
+def test_ragged_slice_never_writes_neighbouring_channels(cuda_ops, c, width):
+    """A [0:c] channel slice of a tensor whose width equals c rounded up to 4 is indistinguishable, by pointer and
+    stride, from a c-channel tensor padded to 4: no kernel may store into the lanes past c (they are the next slice's
+    channels), whatever the source's own pad lanes contain.  (Regression: a float4 tail store in the slice-gradient
+    fan-in corrupted flow channels 2:4 of RRIN whenever the allocator returned dirty memory.)"""
+    ops = cuda_ops
+    n, h, w = 2, 6, 8
+    srcc, srcd = _poisoned(ops, n, h, w, c, 90)
+    othc, othd = _poisoned(ops, n, h, w, c, 91)
+
+    def fresh():
+        full = ops.zeros_act(n, h, w, width)
+        full.fill_(7.0)
+        return full
+
+    def check(full, expect, what):
+        assert torch.equal(full[..., c:].cpu(), torch.full((n, h, w, width - c), 7.0)), what + ": neighbours touched"
+        close(full[..., :c], expect, 1e-6, what)
+
+    full = fresh()
+    ops.copy(srcd, full[..., :c], accumulate=True)
+    check(full, 7.0 + srcc, "copy accumulate")
+    full = fresh()
+    ops.copy(srcd, full[..., :c], accumulate=False)
+    check(full, srcc, "copy")
+    full = fresh()
+    ops.add(srcd, othd, out=full[..., :c])
+    check(full, srcc + othc, "add")
+    full = fresh()
+    ops.affine(srcd, 0.5, 0.25, out=full[..., :c])
+    check(full, 0.5 * srcc + 0.25, "affine")
+    full = fresh()
+    ops.act_fwd(srcd, ACT_TANH, 0.0, out=full[..., :c])
+    check(full, torch.tanh(srcc), "act_fwd")
+    big = ops.zeros_act(n, 2 * h, 2 * w, width)
+    big.fill_(7.0)
+    ops.upsample_fwd(srcd, False, out=big[..., :c])
+    assert torch.equal(big[..., c:].cpu(), torch.full((n, 2 * h, 2 * w, width - c), 7.0)), "upsample: neighbours touched"
+    close(big[..., :c], REF.upsample_fwd(srcc, False), 2e-6, "upsample into slice")
+    if c >= 16:      # tensor-core convolution writing a ragged slice
+        xc, xd = _poisoned(ops, n, h, w, 32, 92)
+        wc, wd = weight_pair(ops, c, 32, 3, 93)
+        full = fresh()
+        ops.conv_fprop(xd, wd, None, ACT_NONE, 0.0, out=full[..., :c])
+        assert torch.equal(full[..., c:].cpu(), torch.full((n, h, w, width - c), 7.0)), "conv: neighbours touched"
+        close(full[..., :c], REF.conv_fprop(xc, wc, None), 4e-3, "conv into slice")
