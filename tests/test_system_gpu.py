@@ -163,3 +163,24 @@ def test_test_time_adaptation_graph_vs_compat(cuda_ops, model, hw):
         for a, b in zip(outs, ref):
             assert a.shape == (3,) + hw
             assert (a - b).abs().max().item() <= PRED_TOL, it
+
+
+def test_full_size_sepconv_graph_path_equals_compat_path(cuda_ops):
+    """BASELINE configs[1] geometry (256x448 frames, 384x512 canvas, K=2 here): the graph-captured fast path (N=2
+    batched support triplets, fused updates, region-of-interest Subnets) and the eager compat path (the reference's
+    control flow, one triplet at a time through torch.autograd, full-canvas Subnets) are two independent executions
+    of the same mathematics; their losses, predictions and PSNR must agree within the TF32 tolerance."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    from bench import synthetic_septuplets
+    frames = [f.cuda() for f in synthetic_septuplets(1, 77)]
+    res = {}
+    for fast in (True, False):
+        s = SceneAdaptiveInterpolation(make_args(cuda=True, number_of_training_steps_per_iter=2, fast_path=fast),
+                                       ops=cuda_ops)
+        if not fast:
+            s.net.SUBNET_ROI = False
+        losses, preds, metrics = s.run_train_iter(frames, epoch=0, do_evaluation=True)
+        res[fast] = (float(losses["loss"].detach()), preds[0].detach().clone(), metrics["psnr"].avg)
+    assert abs(res[True][0] - res[False][0]) <= LOSS_TOL
+    assert (res[True][1] - res[False][1]).abs().max().item() <= PRED_TOL
+    assert abs(res[True][2] - res[False][2]) < 0.01
