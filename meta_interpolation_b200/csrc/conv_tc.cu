@@ -1140,7 +1140,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 //     32-channel block and tile row computes D[cout][(ky, cin)] for all three ky at once.
 // L2 traffic drops from 18 to ~6.4 activation passes and the MMA count per pixel by 3x.
 struct WgradKxParams {
-    int n, h, w, cin, cout, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb, ci_tiles;
+    int n, h, w, cin, cout, k, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb, ci_tiles;
     float* ws_w;
 };
 
@@ -1151,7 +1151,9 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const uint32_t row_bytes = 8u * ROW_BYTES;                       // one tile row: 8 pixels x 32 channels
     const uint32_t a_box = (uint32_t)p.rows * row_bytes;             // dY box {32 ch, 8 px, R rows}
-    const uint32_t b_box = (uint32_t)(p.rows + 2) * row_bytes;       // X box  {32 ch, 8 px, R+2 rows}
+    const uint32_t b_box = (uint32_t)(p.rows + p.k - 1) * row_bytes; // X box  {32 ch, 8 px, R+k-1 rows}
+    const int pad = p.k >> 1;
+    const uint32_t ncols = 32u * (uint32_t)p.k;                      // accumulator columns per X box: k taps x 32 cin
     const uint32_t a_bytes = (uint32_t)p.na * a_box, b_bytes = (uint32_t)p.nb * b_box;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     // the M=128 A descriptor always spans four 32-channel blocks; blocks past `na` alias whatever follows (the X
@@ -1160,13 +1162,14 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const uint32_t tail_pad = (uint32_t)(4 - p.na) * a_box;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + tail_pad);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
-    const uint32_t tmem_cols = p.nb == 1 ? 128u : 256u;              // nb * 96 accumulator columns
+    uint32_t tmem_cols = 32;                                         // nb * k * 32 accumulator columns -> power of two
+    while (tmem_cols < (uint32_t)p.nb * ncols) tmem_cols <<= 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // blockIdx.x = kx + 3 * (cin tile of 64 + ci_tiles * cout tile of 128): wider layers are cut into channel blocks,
     // each block re-reading its dY / X boxes (3 * ci_tiles and 3 * co_tiles passes instead of 9 * tiles of the per-tap form)
-    const int kx = (int)blockIdx.x % 3;
-    const int ct = (int)blockIdx.x / 3;
+    const int kx = (int)blockIdx.x % p.k;
+    const int ct = (int)blockIdx.x / p.k;
     const int ci0 = (ct % p.ci_tiles) * 64, co0 = (ct / p.ci_tiles) * BM;
     const int split = blockIdx.y;
     const int t_begin = split * p.tiles_per_split;
@@ -1208,12 +1211,12 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 for (int j = 0; j < p.na; ++j)
                     tma_load_4d(base + j * a_box, &map_dy, full, co0 + j * KCH, x0, y0, img);
                 for (int j = 0; j < p.nb; ++j)
-                    tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - 1, y0 - 1, img);
+                    tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - pad, y0 - pad, img);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = instr_desc(BM, 96, 1, 1);   // both operands MN-major, N = 3 taps x 32 channels
+            const uint32_t idesc = instr_desc(BM, (int)ncols, 1, 1);   // both operands MN-major, N = k taps x 32 channels
             for (int it = 0; it < iters; ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -1226,7 +1229,7 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 const uint64_t ad0 = smem_desc(a_addr, a_box, 512, 1);
                 for (int j = 0; j < p.nb; ++j) {
                     const uint64_t bd0 = smem_desc(b_addr + (uint32_t)j * b_box, row_bytes, 512, 1);
-                    const uint32_t d_addr = tmem_base + (uint32_t)(j * 96);
+                    const uint32_t d_addr = tmem_base + (uint32_t)j * ncols;
                     for (int r = 0; r < p.rows; ++r)
                         umma_tf32(d_addr, desc_advance(ad0, (uint32_t)r * row_bytes),
                                   desc_advance(bd0, (uint32_t)r * row_bytes), idesc, (it > 0 || r > 0) ? 1u : 0u);
@@ -1238,16 +1241,17 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     } else {
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;
-        float* dst0 = p.ws_w + (long long)split * p.cout * 9 * p.ldw + (long long)co * 9 * p.ldw;
+        const int kk2 = p.k * p.k;
+        float* dst0 = p.ws_w + (long long)split * p.cout * kk2 * p.ldw + (long long)co * kk2 * p.ldw;
         if (iters > 0) {
             mbar_wait(smem_u32(&bars[2 * p.stages]), 0);
             tc_fence_after();
         }
         for (int j = 0; j < p.nb; ++j) {
-            for (int ky = 0; ky < 3; ++ky) {
+            for (int ky = 0; ky < p.k; ++ky) {
                 uint32_t v[32];
                 if (iters > 0) {
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 96 + ky * 32), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j * ncols + (uint32_t)(ky * 32), v);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -1255,7 +1259,7 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 if (co >= p.cout) continue;
                 const int cb = ci0 + j * KCH;
                 if (cb >= p.cin) continue;
-                float* dst = dst0 + (ky * 3 + kx) * p.ldw;
+                float* dst = dst0 + (ky * p.k + kx) * p.ldw;
                 if (cb + 32 <= p.ldw) {
 #pragma unroll
                     for (int g = 0; g < 8; ++g)
@@ -1629,15 +1633,18 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
     MI_RETURN_LAST();
 }
 
-// every 3x3 layer takes the filter-column kernel (MI_B200_WGRAD_KX=0 keeps the per-tap kernel: A/B switch)
+// every 3x3 / 5x5 / 7x7 layer takes the filter-column kernel (MI_B200_WGRAD_KX=0 keeps the per-tap kernel: A/B switch)
 bool mi_tc_wgrad_kx_shape(int cin, int cout, int k) {
     static int on = -1;
     if (on < 0) {
         const char* e = getenv("MI_B200_WGRAD_KX");
         on = (e && e[0] == '0') ? 0 : 1;
     }
-    (void)cin; (void)cout;
-    return on && k == 3 && device_is_sm100() && encode_fn();
+    (void)cout;
+    // 5x5 / 7x7: k filter rows stacked along N (k * 32 columns per 32-channel X box); the two boxes of a 64-cin block
+    // need 2 * k * 32 <= 512 TMEM columns
+    return on && (k == 3 || k == 5 || k == 7) && (long long)(cin >= 64 ? 2 : 1) * k * 32 <= 512 && device_is_sm100() &&
+           encode_fn();
 }
 
 bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
@@ -1654,7 +1661,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
                          int k, int ldw, float* ws_w, float* ws_b, int splits, cudaStream_t stream) {
     if (mi_tc_wgrad_kx_shape(cin, cout, k)) {
         WgradKxParams q;
-        q.n = n; q.h = h; q.w = wd; q.cin = cin; q.cout = cout; q.ldw = ldw;
+        q.n = n; q.h = h; q.w = wd; q.cin = cin; q.cout = cout; q.k = k; q.ldw = ldw;
         q.na = cout >= BM ? 4 : mi_cdiv(cout, KCH);      // dY boxes per CTA (a partial last cout tile is zero-filled)
         q.nb = cin >= 64 ? 2 : mi_cdiv(cin, KCH);        // X boxes per CTA
         q.ci_tiles = mi_cdiv(cin, 64);
@@ -1667,7 +1674,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         int rows = 16, stages = 0;
         size_t stage_bytes = 0, tail = 0;
         for (;; rows = 8) {
-            stage_bytes = (size_t)q.na * rows * row_bytes + (size_t)q.nb * (rows + 2) * row_bytes;
+            stage_bytes = (size_t)q.na * rows * row_bytes + (size_t)q.nb * (rows + k - 1) * row_bytes;
             tail = (size_t)(4 - q.na) * rows * row_bytes;
             stages = (int)((200 * 1024 - tail) / stage_bytes);
             if (stages > 6) stages = 6;
@@ -1684,7 +1691,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         CUtensorMap map_dy, map_x;
         if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, 8, q.rows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return MI_ERR_UNSUPPORTED;
-        if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, 8, q.rows + 2, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, 8, q.rows + k - 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return MI_ERR_UNSUPPORTED;
         static bool attr_kx = false;
         if (!attr_kx) {
@@ -1693,7 +1700,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
             if (e != cudaSuccess) return (int)e;
             attr_kx = true;
         }
-        dim3 grid(3 * q.ci_tiles * co_tiles, splits);
+        dim3 grid(k * q.ci_tiles * co_tiles, splits);
         mi_prof_begin(MI_TAG_WGRAD_KX, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
         conv_wgrad_tc_kx_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, q);
         mi_prof_end(stream);

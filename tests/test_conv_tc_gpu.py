@@ -30,6 +30,8 @@ TC_SHAPES = [
     # tiles, odd tile counts (the last group re-reads a tile), ragged channels, the deepest SepConv layers
     (2, 96, 128, 128, 128, 3), (2, 48, 64, 256, 256, 3), (2, 24, 32, 512, 512, 3), (2, 12, 16, 512, 512, 3),
     (1, 40, 72, 128, 64, 3), (3, 33, 41, 96, 160, 3), (2, 96, 136, 64, 128, 3), (1, 50, 70, 200, 300, 3),
+    # 5x5 / 7x7 layers (superslomo, voxelflow): filter-column weight gradient with 5 / 7 rows stacked along N
+    (2, 40, 56, 32, 32, 7), (1, 33, 47, 64, 64, 5), (1, 32, 40, 6, 32, 7), (1, 24, 24, 128, 64, 5), (2, 16, 24, 20, 32, 7),
 ]
 
 
