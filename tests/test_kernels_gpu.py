@@ -38,6 +38,9 @@ CONV_SHAPES = [
     # n, h, w, cin, cout, k
     (1, 8, 8, 6, 32, 3), (2, 16, 24, 32, 32, 3), (1, 12, 16, 64, 51, 3), (1, 16, 16, 51, 51, 3),
     (2, 6, 8, 128, 64, 3), (1, 9, 7, 5, 3, 5), (1, 10, 12, 20, 32, 7), (1, 4, 4, 192, 12, 1), (1, 3, 5, 7, 130, 3),
+    # few-output-channel heads (flow / mask / RGB): the per-pixel forward and per-(tap,cin) weight-gradient kernels
+    (2, 16, 24, 32, 5, 3), (1, 20, 28, 32, 4, 3), (1, 12, 12, 64, 3, 5), (2, 9, 11, 32, 2, 3), (1, 40, 33, 33, 8, 3),
+    (1, 70, 90, 32, 4, 3),
 ]
 
 
