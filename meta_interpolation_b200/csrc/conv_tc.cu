@@ -141,9 +141,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 // integer ops) costs more issue cycles than a 128xN MMA with small N takes to execute.  So descriptors are built
 // once per stage and advanced with one 64-bit add: the start-address field counts 16-byte units in bits [0,14).
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
-__device__ __forceinline__ uint64_t desc_with_base_offset(uint64_t desc, uint32_t phase) {
-    return (desc & ~(7ull << 49)) | ((uint64_t)(phase & 7u) << 49);
-}
 // instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout)
 __device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -578,7 +575,7 @@ constexpr int HALO_H = 18, HT_W = 8, HT_H = 16;
 
 struct HaloParams {
     int n, h, w, cin, cout, chunks, bn, stages, tiles_x, tiles_y, total_tiles, act, accumulate, mask_act, ldy, ldmask,
-        base_offset_mode, halo_w;
+        halo_w;
     uint32_t halo_bytes, halo_stride;   // bytes one TMA box delivers / 1024-aligned distance between stages
     unsigned long long* dbg;            // optional per-role cycle counters of CTA 0 (MI_B200_DEBUG_TIMING=1)
     float slope, mask_slope;
@@ -1425,16 +1422,6 @@ bool halo_enabled() {
     return v == 1;
 }
 
-// MI_B200_HALO_BO=0: leave the descriptor base-offset field 0 for row-shifted views (experiment switch)
-int halo_base_offset_mode() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("MI_B200_HALO_BO");
-        v = (e && e[0] == '1') ? 1 : 0;   // 1 reproduces the (wrong) phase-in-base-offset experiment
-    }
-    return v;
-}
-
 // MI_B200_HALO_STREAM=0 keeps the per-tap kernel for the >64-channel 3x3 layers (A/B switch for profiling)
 bool halo_stream_enabled() {
     static int v = -1;
@@ -1489,7 +1476,6 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         hp.tiles_x = mi_cdiv(wd, HT_W);
         hp.tiles_y = mi_cdiv(h, HT_H);
         hp.total_tiles = hp.tiles_x * hp.tiles_y * n;
-        hp.base_offset_mode = halo_base_offset_mode();
         hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
         hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
         const size_t b_total = (size_t)9 * hp.chunks * hp.bn * ROW_BYTES;
