@@ -999,6 +999,188 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * HS_BN));
 }
 
+// ------------------------------------------------------------------------------------------ fprop, 5x5 / 7x7
+// The 5x5 / 7x7 layers of superslomo and voxelflow.  Their filter bank is too large for a pipeline stage (49 taps x 32
+// couts x 128 B = 196 KB per 32-channel chunk), so it streams one FILTER ROW at a time: the halo box of a chunk
+// ((16+k-1) x (8+k-1) pixels, one TMA box, ring of two) stays put while k rows of k weight tiles pass through their
+// own ring (three stages); the MMA lane waits once per row, i.e. once per 4k = 20-28 MMAs.  Tap (ky, kx) is again a
+// descriptor view of the halo box shifted by ky rows and kx pixels.  Persistent CTAs over (pixel tile, cout tile) items,
+// double-buffered TMEM accumulators, the eight-warp epilogue of the 3x3 halo kernels.
+struct HaloRowsParams {
+    int n, h, w, cin, cout, k, chunks, bn, n_tiles, tiles_x, tiles_y, total_tiles, items, act, accumulate, mask_act,
+        ldy, ldmask, halo_w, sa, sb;
+    uint32_t halo_bytes, halo_stride;
+    float slope, mask_slope;
+    const float* bias;
+    const float* mask_y;
+    float* y;
+};
+
+__global__ void __launch_bounds__(HALO_THREADS)
+conv_fprop_tc_halo_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                               const HaloRowsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int SA = p.sa, SB = p.sb, K = p.k, pad = p.k >> 1;
+    const uint32_t b_tile = (uint32_t)p.bn * ROW_BYTES;            // one (tap, chunk) weight tile
+    const uint32_t b_stage = (uint32_t)K * b_tile;                 // one filter row of a chunk
+    uint8_t* smem_b = smem + (size_t)SA * p.halo_stride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (size_t)SB * b_stage);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + SA;
+    uint64_t* b_full = bars + 2 * SA;
+    uint64_t* b_empty = bars + 2 * SA + SB;
+    uint64_t* t_full = bars + 2 * SA + 2 * SB;
+    uint64_t* t_empty = t_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_cols = (uint32_t)(2 * p.bn);               // 64 or 128
+
+    __shared__ float sbias[512];
+    __shared__ __align__(16) float epi_stage[8 * 32 * EPI16_PITCH];
+    for (int i = threadIdx.x; i < 512; i += HALO_THREADS) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SA; ++s) { mbar_init(smem_u32(&a_full[s]), 1); mbar_init(smem_u32(&a_empty[s]), 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+        mbar_init(smem_u32(&t_full[0]), 1);
+        mbar_init(smem_u32(&t_full[1]), 1);
+        mbar_init(smem_u32(&t_empty[0]), 256);
+        mbar_init(smem_u32(&t_empty[1]), 256);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int my_items = (p.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 0) {
+        int ia = 0, ib = 0;
+        for (int t = 0; t < my_items; ++t) {
+            const int item = (int)blockIdx.x + t * (int)gridDim.x;
+            const int nt = item % p.n_tiles;
+            int tile = item / p.n_tiles;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            const int img = tile;
+            for (int ch = 0; ch < p.chunks; ++ch, ++ia) {
+                const int s = ia % SA;
+                mbar_wait(smem_u32(&a_empty[s]), (((uint32_t)(ia / SA)) & 1u) ^ 1u);
+                if (elect_one()) {
+                    const uint32_t full = smem_u32(&a_full[s]);
+                    mbar_expect_tx(full, p.halo_bytes);
+                    tma_load_4d(smem_u32(smem + (size_t)s * p.halo_stride), &map_x, full, ch * KCH, tx_i * HT_W - pad,
+                                ty_i * HT_H - pad, img);
+                }
+                __syncwarp();
+                for (int ky = 0; ky < K; ++ky, ++ib) {
+                    const int sb = ib % SB;
+                    mbar_wait(smem_u32(&b_empty[sb]), (((uint32_t)(ib / SB)) & 1u) ^ 1u);
+                    if (elect_one()) {
+                        const uint32_t full = smem_u32(&b_full[sb]);
+                        mbar_expect_tx(full, b_stage);
+                        for (int kx = 0; kx < K; ++kx)
+                            tma_load_3d(smem_u32(smem_b + (size_t)sb * b_stage) + (uint32_t)kx * b_tile, &map_w, full,
+                                        ch * KCH, ky * K + kx, nt * p.bn);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = instr_desc(BM, p.bn, 0, 0);
+        const int last_ksteps = (p.cin - (p.chunks - 1) * KCH + 7) / 8;
+        int ia = 0, ib = 0;
+        for (int t = 0; t < my_items; ++t) {
+            const int buf = t & 1;
+            mbar_wait(smem_u32(&t_empty[buf]), (((uint32_t)(t >> 1)) & 1u) ^ 1u);   // epilogue drained this buffer
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+            for (int ch = 0; ch < p.chunks; ++ch, ++ia) {
+                const int s = ia % SA;
+                mbar_wait(smem_u32(&a_full[s]), ((uint32_t)(ia / SA)) & 1u);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + (size_t)s * p.halo_stride);
+                const int ksteps = (ch == p.chunks - 1) ? last_ksteps : 4;
+                for (int ky = 0; ky < K; ++ky, ++ib) {
+                    const int sb = ib % SB;
+                    mbar_wait(smem_u32(&b_full[sb]), ((uint32_t)(ib / SB)) & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t ad0 = smem_desc(a_base, 16, (uint32_t)p.halo_w * ROW_BYTES);
+                        const uint64_t bd0 = smem_desc(smem_u32(smem_b + (size_t)sb * b_stage), 16, 1024);
+                        for (int kx = 0; kx < K; ++kx) {
+                            const uint64_t a_tap = desc_advance(ad0, (uint32_t)(ky * p.halo_w + kx) * ROW_BYTES);
+                            const uint64_t b_tap = desc_advance(bd0, (uint32_t)kx * b_tile);
+                            if (ksteps == 4) {
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)
+                                    umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                              (ch > 0 || ky > 0 || kx > 0 || kk > 0) ? 1u : 0u);
+                            } else {
+                                for (int kk = 0; kk < ksteps; ++kk)
+                                    umma_tf32(d_addr, desc_advance(a_tap, kk * 32), desc_advance(b_tap, kk * 32), idesc,
+                                              (ch > 0 || ky > 0 || kx > 0 || kk > 0) ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(smem_u32(&b_empty[sb]));
+                        if (ky == K - 1) {
+                            umma_commit(smem_u32(&a_empty[s]));
+                            if (ch == p.chunks - 1) umma_commit(smem_u32(&t_full[buf]));
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;               // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;     // which 16-column half of every 32-column chunk it owns
+        const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                         (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
+        EpiArgs ea;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.slope = p.slope; ea.mask_slope = p.mask_slope;
+        ea.cout_store = p.cout;
+        const int r = q * 32 + lane;
+        const int th_i = r >> 3, tw_i = r & 7;
+        float* stage = epi_stage + (warp - 2) * 32 * EPI16_PITCH;
+        for (int t = 0; t < my_items; ++t) {
+            const int buf = t & 1;
+            const int item = (int)blockIdx.x + t * (int)gridDim.x;
+            const int nt = item % p.n_tiles;
+            const int co0 = nt * p.bn;
+            int tile = item / p.n_tiles;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            const int img = tile;
+            const int oy = ty_i * HT_H + th_i, ox = tx_i * HT_W + tw_i;
+            const bool pix_ok = (oy < p.h) && (ox < p.w);
+            const long long pix = ((long long)img * p.h + oy) * p.w + ox;
+            float* yrow = p.y + pix * p.ldy;
+            const float* mrow = p.mask_y ? p.mask_y + pix * p.ldmask : nullptr;
+            mbar_wait(smem_u32(&t_full[buf]), ((uint32_t)(t >> 1)) & 1u);
+            tc_fence_after();
+            RowMap16 rm;
+            rm.init(HT_W, ty_i * HT_H, tx_i * HT_W, p.h, p.w, img, q, lane);
+            for (int c0i = 16 * half; c0i < p.bn; c0i += 32) {
+                if (co0 + c0i >= p.cout) break;                    // warp-uniform
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn + c0i), v);
+                if (vec) epilogue_half_coalesced(v, sbias + co0 + c0i, co0 + c0i, ea, stage, lane, rm, p.mask_y, p.ldmask,
+                                                 p.y, p.ldy);
+                else if (pix_ok) epilogue_half_scalar(v, sbias + co0 + c0i, co0 + c0i, ea, mrow, yrow);
+            }
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&t_empty[buf])) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 // ------------------------------------------------------------------------------------------ wgrad partials
 struct WgradParams {
     int n, h, w, cin, cout, k, ldw, pw, ph, tiles_x, tiles_y, bn, stages, co_tiles, ci_tiles, tiles_per_split,
@@ -1575,6 +1757,47 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
                         "total=%llu cycles\n", d[10], hp.n_tiles, hp.chunks, grid, d[0], d[2], d[3], d[5], d[6], d[7], d[8],
                         d[9]);
             }
+            MI_LAUNCHED();
+            MI_RETURN_LAST();
+        }
+    }
+    if ((k == 5 || k == 7) && cout <= 512 && halo_stream_enabled()) {
+        HaloRowsParams hp;
+        hp.n = n; hp.h = h; hp.w = wd; hp.cin = cin; hp.cout = cout; hp.k = k;
+        hp.chunks = mi_cdiv(cin, KCH);
+        hp.bn = cout <= 32 ? 32 : 64;
+        hp.tiles_x = mi_cdiv(wd, HT_W);
+        hp.tiles_y = mi_cdiv(h, HT_H);
+        hp.total_tiles = hp.tiles_x * hp.tiles_y * n;
+        hp.n_tiles = mi_cdiv(cout, hp.bn);
+        hp.items = hp.total_tiles * hp.n_tiles;
+        hp.halo_w = HT_W + k - 1;
+        hp.halo_bytes = (uint32_t)hp.halo_w * (HT_H + k - 1) * ROW_BYTES;
+        hp.halo_stride = (hp.halo_bytes + 1023u) & ~1023u;
+        hp.sa = 2;
+        const size_t b_stage = (size_t)k * hp.bn * ROW_BYTES;
+        int sb = (int)((200 * 1024 - (size_t)hp.sa * hp.halo_stride) / b_stage);
+        if (sb > 4) sb = 4;
+        hp.sb = sb;
+        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
+        hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
+        if (sb >= 2) {
+            const size_t smem = (size_t)hp.sa * hp.halo_stride + (size_t)sb * b_stage + (2 * hp.sa + 2 * sb + 5) * 8 + 1024;
+            CUtensorMap map_x, map_w;
+            if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, hp.halo_w, HT_H + k - 1)) return MI_ERR_UNSUPPORTED;
+            if (!make_weight_map(&map_w, w, ldw, cout, k * k, cin, hp.bn)) return MI_ERR_UNSUPPORTED;
+            static bool attr = false;
+            if (!attr) {
+                cudaError_t e = cudaFuncSetAttribute(conv_fprop_tc_halo_rows_kernel,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(205 * 1024));
+                if (e != cudaSuccess) return (int)e;
+                attr = true;
+            }
+            const int grid = hp.items < num_sms() ? hp.items : num_sms();
+            mi_prof_begin(MI_TAG_FPROP_STREAM, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+                          stream);
+            conv_fprop_tc_halo_rows_kernel<<<grid, HALO_THREADS, smem, stream>>>(map_x, map_w, hp);
+            mi_prof_end(stream);
             MI_LAUNCHED();
             MI_RETURN_LAST();
         }
