@@ -269,25 +269,26 @@ conv_wgrad_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
 // Few-output-channel layers (flow / mask / RGB heads: Cout = 2..5 at full resolution; the dgrad into a 9/10-channel
 // concat input).  They stay on exact fp32 (flows are measured in pixels), but the 64x64-tile kernels above waste
 // 59 of 64 output columns on them (271 us forward / 579 us weight gradient per superslomo head at 256x448).
-//   forward : one thread per pixel, all Cout (<= SC_MAX) accumulators in registers, the whole filter bank in shared
-//             memory transposed to [tap][cin][SC_MAX] so every weight read is a broadcast;
-//   wgrad   : one thread per (tap, cin) pair (up to SC_PAIRS per thread), Cout accumulators each; a block walks a
+//   forward : one thread per pixel, all Cout (<= 8 or <= 16) accumulators in registers, the whole filter bank in shared
+//             memory transposed to [tap][cin][SC] so every weight read is a broadcast (also the data gradient into the
+//             9/10-channel concat inputs of RRIN);
+//   wgrad   : one thread per (tap, cin) pair (two past 1024 pairs), Cout accumulators each; a block walks a
 //             strip of pixels with dY staged in shared memory (broadcast reads) and X read coalesced along cin; one
 //             partial per block, reduced by the common finishing kernel.
 // ---------------------------------------------------------------------------------------------
 constexpr int SC_MAX = 8;       // output channels handled by the small-Cout kernels
-constexpr int SC_PAIRS = 8;     // (tap, cin) pairs per thread in the weight-gradient kernel (256 threads -> 2048 pairs)
 constexpr int SC_STRIP = 64;    // pixels of dY staged per iteration
 
+template <int SC>
 __global__ void __launch_bounds__(256)
 conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, int ldw,
                         const float* __restrict__ bias, float* __restrict__ y, int ldy,
                         const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope, int accumulate,
                         int n, int h, int wd, int cin, int cout, int k, int act, float slope, int vec_x) {
-    extern __shared__ __align__(16) float sw[];      // [k*k][cin][SC_MAX]
+    extern __shared__ __align__(16) float sw[];      // [k*k][cin][SC]
     const int kk = k * k, pad = k >> 1;
-    for (int i = threadIdx.x; i < kk * cin * SC_MAX; i += blockDim.x) {
-        const int co = i % SC_MAX, ci = (i / SC_MAX) % cin, tap = i / (SC_MAX * cin);
+    for (int i = threadIdx.x; i < kk * cin * SC; i += blockDim.x) {
+        const int co = i % SC, ci = (i / SC) % cin, tap = i / (SC * cin);
         sw[i] = co < cout ? w[((long long)co * kk + tap) * ldw + ci] : 0.f;
     }
     __syncthreads();
@@ -297,14 +298,14 @@ conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __res
         const int ox = (int)(m % wd);
         const int oy = (int)((m / wd) % h);
         const long long img = m / ((long long)wd * h);
-        float acc[SC_MAX];
+        float acc[SC];
 #pragma unroll
-        for (int co = 0; co < SC_MAX; ++co) acc[co] = (bias && co < cout) ? bias[co] : 0.f;
+        for (int co = 0; co < SC; ++co) acc[co] = (bias && co < cout) ? bias[co] : 0.f;
         for (int tap = 0; tap < kk; ++tap) {
             const int iy = oy + tap / k - pad, ix = ox + tap % k - pad;
             if (iy < 0 || iy >= h || ix < 0 || ix >= wd) continue;
             const float* xp = x + ((img * h + iy) * wd + ix) * ldx;
-            const float4* wp = reinterpret_cast<const float4*>(sw + (long long)tap * cin * SC_MAX);
+            const float4* wp = reinterpret_cast<const float4*>(sw + (long long)tap * cin * SC);
             int ci = 0;
             if (vec_x) {
                 for (; ci + 3 < cin; ci += 4) {
@@ -313,8 +314,8 @@ conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __res
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
 #pragma unroll
-                        for (int g = 0; g < SC_MAX / 4; ++g) {
-                            const float4 wv = wp[(ci + q) * (SC_MAX / 4) + g];
+                        for (int g = 0; g < SC / 4; ++g) {
+                            const float4 wv = wp[(ci + q) * (SC / 4) + g];
                             acc[4 * g + 0] = fmaf(xs[q], wv.x, acc[4 * g + 0]);
                             acc[4 * g + 1] = fmaf(xs[q], wv.y, acc[4 * g + 1]);
                             acc[4 * g + 2] = fmaf(xs[q], wv.z, acc[4 * g + 2]);
@@ -326,8 +327,8 @@ conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __res
             for (; ci < cin; ++ci) {
                 const float xv = xp[ci];
 #pragma unroll
-                for (int g = 0; g < SC_MAX / 4; ++g) {
-                    const float4 wv = wp[ci * (SC_MAX / 4) + g];
+                for (int g = 0; g < SC / 4; ++g) {
+                    const float4 wv = wp[ci * (SC / 4) + g];
                     acc[4 * g + 0] = fmaf(xv, wv.x, acc[4 * g + 0]);
                     acc[4 * g + 1] = fmaf(xv, wv.y, acc[4 * g + 1]);
                     acc[4 * g + 2] = fmaf(xv, wv.z, acc[4 * g + 2]);
@@ -338,7 +339,7 @@ conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __res
         float* yp = y + m * ldy;
         const float* mp = mask_y ? mask_y + m * ldmask : nullptr;
 #pragma unroll
-        for (int co = 0; co < SC_MAX; ++co) {
+        for (int co = 0; co < SC; ++co) {
             if (co >= cout) break;
             float v = mi_act_apply(acc[co], act, slope);
             if (mp) v *= mi_act_grad(mp[co], mask_act, mask_slope);
@@ -348,22 +349,26 @@ conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __res
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <int J>
+__global__ void __launch_bounds__(1024)
 conv_wgrad_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int lddy,
                         float* __restrict__ ws_w, float* __restrict__ ws_b, int n, int h, int wd, int cin, int cout,
                         int k, int ldw, long long chunk) {
-    __shared__ float sdy[SC_STRIP][SC_MAX];
+    __shared__ __align__(16) float sdy[SC_STRIP][SC_MAX];
+    __shared__ int s_oy[SC_STRIP], s_ox[SC_STRIP];
+    __shared__ long long s_base[SC_STRIP];            // pixel index (img*h + oy)*wd + ox
     const int kk = k * k, pad = k >> 1;
     const int pairs = kk * cin;
     const int split = blockIdx.x;
+    const int nthr = blockDim.x;
     const long long m_total = (long long)n * h * wd;
     const long long m0 = (long long)split * chunk;
     const long long m1 = min(m0 + chunk, m_total);
-    float acc[SC_PAIRS][SC_MAX];
-    int p_ky[SC_PAIRS], p_kx[SC_PAIRS], p_ci[SC_PAIRS];
+    float acc[J][SC_MAX];
+    int p_ky[J], p_kx[J], p_ci[J];
 #pragma unroll
-    for (int j = 0; j < SC_PAIRS; ++j) {
-        const int idx = (int)threadIdx.x + j * 256;
+    for (int j = 0; j < J; ++j) {
+        const int idx = (int)threadIdx.x + j * nthr;
         const int tap = idx < pairs ? idx / cin : 0;
         p_ci[j] = idx < pairs ? idx % cin : -1;
         p_ky[j] = tap / k - pad; p_kx[j] = tap % k - pad;
@@ -374,41 +379,50 @@ conv_wgrad_small_kernel(const float* __restrict__ x, int ldx, const float* __res
     for (long long mb = m0; mb < m1; mb += SC_STRIP) {
         const int cnt = (int)min((long long)SC_STRIP, m1 - mb);
         __syncthreads();
-        for (int i = threadIdx.x; i < SC_STRIP * SC_MAX; i += 256) {
+        for (int i = threadIdx.x; i < SC_STRIP * SC_MAX; i += nthr) {
             const int pp = i / SC_MAX, co = i % SC_MAX;
-            sdy[pp][co] = (pp < cnt && co < cout) ? dy[(mb + pp) * lddy + co] : 0.f;
+            sdy[pp][co] = (pp < cnt && co < cout) ? dy[(mb + pp) * lddy + co] : 0.f;   // rows past cnt: zero weight
+        }
+        for (int pp = threadIdx.x; pp < SC_STRIP; pp += nthr) {
+            const long long m = min(mb + pp, m_total - 1);
+            s_ox[pp] = (int)(m % wd);
+            s_oy[pp] = (int)((m / wd) % h);
+            s_base[pp] = m;
         }
         __syncthreads();
         if ((int)threadIdx.x < cout)
             for (int pp = 0; pp < cnt; ++pp) bsum += sdy[pp][threadIdx.x];
-        int ox = (int)(mb % wd);
-        int oy = (int)((mb / wd) % h);
-        long long img = mb / ((long long)wd * h);
-        for (int pp = 0; pp < cnt; ++pp) {
-            float4 d4[SC_MAX / 4];
+        // four pixels per iteration: their X loads are independent, so the FMAs of one hide the latency of the next
+        for (int pp = 0; pp < SC_STRIP; pp += 4) {
+            if (pp >= cnt) break;
 #pragma unroll
-            for (int g = 0; g < SC_MAX / 4; ++g) d4[g] = *reinterpret_cast<const float4*>(&sdy[pp][4 * g]);
-#pragma unroll
-            for (int j = 0; j < SC_PAIRS; ++j) {
+            for (int j = 0; j < J; ++j) {
                 if (p_ci[j] < 0) continue;
-                const int iy = oy + p_ky[j], ix = ox + p_kx[j];
-                if (iy < 0 || iy >= h || ix < 0 || ix >= wd) continue;
-                const float xv = x[((img * h + iy) * wd + ix) * ldx + p_ci[j]];
+                float xv[4];
 #pragma unroll
-                for (int g = 0; g < SC_MAX / 4; ++g) {
-                    acc[j][4 * g + 0] = fmaf(xv, d4[g].x, acc[j][4 * g + 0]);
-                    acc[j][4 * g + 1] = fmaf(xv, d4[g].y, acc[j][4 * g + 1]);
-                    acc[j][4 * g + 2] = fmaf(xv, d4[g].z, acc[j][4 * g + 2]);
-                    acc[j][4 * g + 3] = fmaf(xv, d4[g].w, acc[j][4 * g + 3]);
+                for (int u = 0; u < 4; ++u) {
+                    const int iy = s_oy[pp + u] + p_ky[j], ix = s_ox[pp + u] + p_kx[j];
+                    const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < wd;
+                    xv[u] = ok ? x[(s_base[pp + u] + (long long)p_ky[j] * wd + p_kx[j]) * ldx + p_ci[j]] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int g = 0; g < SC_MAX / 4; ++g) {
+                        const float4 d = *reinterpret_cast<const float4*>(&sdy[pp + u][4 * g]);
+                        acc[j][4 * g + 0] = fmaf(xv[u], d.x, acc[j][4 * g + 0]);
+                        acc[j][4 * g + 1] = fmaf(xv[u], d.y, acc[j][4 * g + 1]);
+                        acc[j][4 * g + 2] = fmaf(xv[u], d.z, acc[j][4 * g + 2]);
+                        acc[j][4 * g + 3] = fmaf(xv[u], d.w, acc[j][4 * g + 3]);
+                    }
                 }
             }
-            if (++ox == wd) { ox = 0; if (++oy == h) { oy = 0; ++img; } }
         }
     }
     float* wsp = ws_w + (long long)split * cout * kk * ldw;
 #pragma unroll
-    for (int j = 0; j < SC_PAIRS; ++j) {
-        const int idx = (int)threadIdx.x + j * 256;
+    for (int j = 0; j < J; ++j) {
+        const int idx = (int)threadIdx.x + j * nthr;
         if (idx >= pairs) continue;
         const int tap = idx / cin, ci = idx % cin;
 #pragma unroll
@@ -420,9 +434,9 @@ conv_wgrad_small_kernel(const float* __restrict__ x, int ldx, const float* __res
 
 // eligibility of the small-Cout kernels (exact fp32; used by both engines)
 static bool small_cout_fprop_ok(int cin, int cout, int k) {
-    return cout <= 8 && (size_t)k * k * cin * SC_MAX * sizeof(float) <= 96 * 1024;
+    return cout <= 16 && (size_t)k * k * cin * (cout <= 8 ? 8 : 16) * sizeof(float) <= 96 * 1024;
 }
-static bool small_cout_wgrad_ok(int cin, int cout, int k) { return cout <= 8 && k * k * cin <= 256 * SC_PAIRS; }
+static bool small_cout_wgrad_ok(int cin, int cout, int k) { return cout <= SC_MAX && k * k * cin <= 2048; }
 
 // reduce the split-K partials and apply the requested epilogue (store / accumulate / fused inner update).
 // Index space: [0, wsz) one thread per weight element; then, from the next multiple of 32, one WARP per bias
@@ -576,11 +590,15 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
                              int h, int wd, int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
     const long long m_total = (long long)n * h * wd;
     if (small_cout_fprop_ok(cin, cout, k)) {
-        const size_t sm = (size_t)k * k * cin * SC_MAX * sizeof(float);
+        const int sc = cout <= 8 ? 8 : 16;
+        const size_t sm = (size_t)k * k * cin * sc * sizeof(float);
         static bool attr = false;
         if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(conv_fprop_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(conv_fprop_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  96 * 1024);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(conv_fprop_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         96 * 1024);
             if (e != cudaSuccess) return (int)e;
             attr = true;
         }
@@ -589,9 +607,14 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
         const int vx = (ldx % 4 == 0) && mi_al16(x);
         mi_prof_begin(MI_TAG_FPROP_SIMT, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
                       stream);
-        conv_fprop_small_kernel<<<(int)blocks, 256, sm, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask, mask_act,
-                                                                 mask_slope, accumulate, n, h, wd, cin, cout, k, act,
-                                                                 slope, vx);
+        if (sc == 8)
+            conv_fprop_small_kernel<8><<<(int)blocks, 256, sm, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask,
+                                                                        mask_act, mask_slope, accumulate, n, h, wd, cin,
+                                                                        cout, k, act, slope, vx);
+        else
+            conv_fprop_small_kernel<16><<<(int)blocks, 256, sm, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask,
+                                                                         mask_act, mask_slope, accumulate, n, h, wd, cin,
+                                                                         cout, k, act, slope, vx);
         mi_prof_end(stream);
         MI_LAUNCHED();
         MI_RETURN_LAST();
@@ -685,7 +708,14 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
         const long long chunk = (m_total + splits - 1) / splits;
         mi_prof_begin(MI_TAG_WGRAD_SIMT, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
                       st);
-        conv_wgrad_small_kernel<<<splits, 256, 0, st>>>(x, ldx, dy, lddy, ws_w, ws_b, n, h, wd, cin, cout, k, ldw, chunk);
+        const int pairs = k * k * cin;
+        const int nthr = pairs >= 1024 ? 1024 : ((pairs + 31) / 32) * 32;     // one (tap, cin) pair per thread, two past 1024
+        if (pairs > nthr)
+            conv_wgrad_small_kernel<2><<<splits, nthr, 0, st>>>(x, ldx, dy, lddy, ws_w, ws_b, n, h, wd, cin, cout, k, ldw,
+                                                             chunk);
+        else
+            conv_wgrad_small_kernel<1><<<splits, nthr, 0, st>>>(x, ldx, dy, lddy, ws_w, ws_b, n, h, wd, cin, cout, k, ldw,
+                                                             chunk);
         mi_prof_end(st);
         MI_LAUNCHED();
         rc = (int)cudaPeekAtLastError();

@@ -40,7 +40,7 @@ CONV_SHAPES = [
     (2, 6, 8, 128, 64, 3), (1, 9, 7, 5, 3, 5), (1, 10, 12, 20, 32, 7), (1, 4, 4, 192, 12, 1), (1, 3, 5, 7, 130, 3),
     # few-output-channel heads (flow / mask / RGB): the per-pixel forward and per-(tap,cin) weight-gradient kernels
     (2, 16, 24, 32, 5, 3), (1, 20, 28, 32, 4, 3), (1, 12, 12, 64, 3, 5), (2, 9, 11, 32, 2, 3), (1, 40, 33, 33, 8, 3),
-    (1, 70, 90, 32, 4, 3),
+    (1, 70, 90, 32, 4, 3), (2, 12, 20, 32, 10, 3), (1, 16, 16, 32, 9, 3), (1, 10, 14, 64, 3, 5), (1, 6, 6, 250, 2, 3),
 ]
 
 
