@@ -63,6 +63,7 @@ def roofline_section(system):
         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on its heaviest
         # layer (51->51 on the 258x450 region of interest, N=2): see profiles/README.md
         "traffic": NCU_TRAFFIC_BYTES.get(dom),
+        "traffic_launch": NCU_TRAFFIC_LAUNCH.get(dom),
         "peak_source": peaks["source"] + "; dense bf16 sustained (kernel timed inside a long step); the kernel "
                        "computes in TF32, whose tensor-pipe ceiling is half the bf16 one (frac 0.5 = TF32 peak)",
         "share_of_instrumented_step": round(d["ms"] / total_ms, 3) if total_ms > 0 else None,
@@ -76,8 +77,11 @@ KERNEL_NAMES = {"fprop_tc_halo": "conv_fprop_tc_halo_kernel", "fprop_tc_halo_str
                 "fprop_tc": "conv_fprop_tc_kernel", "wgrad_tc_kx": "conv_wgrad_tc_kx_kernel",
                 "wgrad_tc": "conv_wgrad_tc_kernel", "fprop_simt": "conv_fprop_simt_kernel",
                 "wgrad_simt": "conv_wgrad_simt_kernel"}
-# filled from the committed ncu captures (profiles/); None = not captured this round
-NCU_TRAFFIC_BYTES = {"fprop_tc_halo": 48484608 + 5084416}   # profiles/r01b_ncu_conv_fprop_halo_51x51_258x450.txt
+# filled from the committed ncu captures (profiles/); None = not captured this round.  The capture is of ONE launch
+# (named in NCU_TRAFFIC_LAUNCH, with its algorithmic bytes), while `achieved` averages all launches of the kernel.
+NCU_TRAFFIC_LAUNCH = {"fprop_tc_halo": "51->51 3x3 on the 258x450 region of interest, N=2: 10.9 GFLOP, 94.7 MB "
+                                       "algorithmic (profiles/r01c_ncu_conv_fprop_halo_51x51_258x450.txt)"}
+NCU_TRAFFIC_BYTES = {"fprop_tc_halo": 48479488 + 6179072}   # dram read + write of that launch
 
 
 # --------------------------------------------------------------------------------------------- CPU legs
