@@ -130,9 +130,12 @@ int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumul
 int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners,
                             int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
                             mi_stream_t stream);
+/* mask_y (optional, shaped like dx): the post-activation tensor that was upsampled; dx is then the gradient w.r.t.
+ * its pre-activation (dx *= act'(mask_y)), saving the separate mi_act_bwd pass. */
 int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                             int align_corners, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0,
-                            int hx0, mi_stream_t stream);
+                            int hx0, const float* mask_y, int ldmask, int mask_act, float mask_slope,
+                            mi_stream_t stream);
 int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, float* dst, int ldd, int dh, int dw,
                    int dy0, int dx0, int n, int h, int wd, int c, int accumulate, mi_stream_t stream);
 /* y = a + b  (skip adds, sepconv/model.py:294-309) ; a,b,y may alias */

@@ -36,7 +36,7 @@ SIGNATURES = {
     "mi_upsample2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _st]),
     "mi_upsample2_bwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_upsample2_window_fwd": (_i, [_f, _i, _f, _i] + [_i] * 13 + [_st]),
-    "mi_upsample2_window_bwd": (_i, [_f, _i, _f, _i] + [_i] * 14 + [_st]),
+    "mi_upsample2_window_bwd": (_i, [_f, _i, _f, _i] + [_i] * 14 + [_f, _i, _i, _fl, _st]),
     "mi_window_copy": (_i, [_f, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_add": (_i, [_f, _i, _f, _i, _f, _i, _sz, _i, _st]),
     "mi_copy": (_i, [_f, _i, _f, _i, _i, _sz, _i, _st]),

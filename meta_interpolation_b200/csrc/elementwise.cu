@@ -193,8 +193,11 @@ __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float
 
 // gather form of the transpose: each input pixel collects from the output pixels that read it.  Output o reads
 // inputs (i0,i1); the outputs that can touch input i lie within [2i-3, 2i+3]; membership is tested exactly.
+// Optional mask: `mask_y` is the post-activation tensor whose x2 upsampling is being differentiated (same shape as
+// dx); the result is then the gradient w.r.t. its PRE-activation, which saves the separate act_bwd pass.
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
-                                     int accumulate, int n, int h, int wd, int c, int align, int vec, UpWin g) {
+                                     int accumulate, int n, int h, int wd, int c, int align, int vec, UpWin g,
+                                     const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope) {
     const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
@@ -236,6 +239,12 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
             const F4 o = ld4(d, valid, vec);
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc.v[q] += o.v[q];
+        }
+        if (mask_y) {
+            const float* mp = mask_y + ((long long)(nn * h + yy) * wd + xx) * ldmask + 4 * gi;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < valid) acc.v[q] *= mi_act_grad(mp[q], mask_act, mask_slope);
         }
         st4(d, acc, valid, vec);
     }
@@ -595,7 +604,7 @@ int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumul
     const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
     LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
-           vec, g);
+           vec, g, nullptr, 0, 0, 0.f);
 }
 static bool up_window_ok(int h, int wd, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0) {
     return h >= 1 && wd >= 1 && oh >= 1 && ow >= 1 && ly0 >= 0 && lx0 >= 0 && hy0 >= 0 && hx0 >= 0 &&
@@ -610,12 +619,13 @@ int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, i
 }
 int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                             int align, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
-                            mi_stream_t s) {
-    if (!dy || !dx || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0)) return MI_ERR_BAD_ARG;
+                            const float* mask_y, int ldmask, int mask_act, float mask_slope, mi_stream_t s) {
+    if (!dy || !dx || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0) || (mask_y && ldmask < c))
+        return MI_ERR_BAD_ARG;
     const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
     LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
-           vec, g);
+           vec, g, mask_y, ldmask, mask_act, mask_slope);
 }
 int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, float* dst, int ldd, int dh, int dw,
                    int dy0, int dx0, int n, int h, int wd, int c, int accumulate, mi_stream_t s) {

@@ -226,8 +226,11 @@ class CudaOps:
                                              int(align_corners), self._stream()), "mi_upsample2_fwd")
         return y
 
-    def upsample_bwd(self, dy, dx, align_corners, accumulate):
+    def upsample_bwd(self, dy, dx, align_corners, accumulate, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0):
         n, h, w, c = dx.shape
+        if mask_y is not None:   # fused activation derivative: the plain upsample is the window that covers everything
+            return self.upsample_window_bwd(dy, dx, align_corners, accumulate, (h, w), (0, 0), (0, 0), mask_y,
+                                            mask_act, mask_slope)
         _lib.check(self.lib.mi_upsample2_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n, h, w,
                                              c, int(align_corners), self._stream()), "mi_upsample2_bwd")
 
@@ -241,12 +244,14 @@ class CudaOps:
                                                     self._stream()), "mi_upsample2_window_fwd")
         return y
 
-    def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin):
+    def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin, mask_y=None,
+                            mask_act=ACT_NONE, mask_slope=0.0):
         n, h, w, c = dx.shape
         _lib.check(self.lib.mi_upsample2_window_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n,
                                                     h, w, c, int(align_corners), full_hw[0], full_hw[1], lo_origin[0],
                                                     lo_origin[1], dy.shape[1], dy.shape[2], hi_origin[0], hi_origin[1],
-                                                    self._stream()), "mi_upsample2_window_bwd")
+                                                    self._p(mask_y), 0 if mask_y is None else _ld(mask_y), mask_act,
+                                                    float(mask_slope), self._stream()), "mi_upsample2_window_bwd")
 
     def window_copy(self, src, src_origin, dst, dst_origin, hw, accumulate=False):
         """dst[:, dy0:dy0+h, dx0:dx0+w] (+)= src[:, sy0:sy0+h, sx0:sx0+w] between two NHWC buffers."""

@@ -144,7 +144,13 @@ class Tape:
                 return
             if x.grad is None:
                 x.grad = ops.empty_like_act(x.data)
-                ops.upsample_bwd(y.grad, x.grad, align_corners, False)
+                if x.consumers == 1 and x.act != ACT_NONE:
+                    # sole consumer of an activated conv output: its activation derivative is applied here, so
+                    # x.grad is born as the pre-activation gradient and the conv skips its act_bwd pass
+                    ops.upsample_bwd(y.grad, x.grad, align_corners, False, x.data, x.act, x.slope)
+                    x.grad_masked = True
+                else:
+                    ops.upsample_bwd(y.grad, x.grad, align_corners, False)
             else:
                 ops.upsample_bwd(y.grad, x.grad, align_corners, True)
             y.grad = None
@@ -184,7 +190,12 @@ class Tape:
                 return
             if x.grad is None:
                 x.grad = ops.empty_like_act(x.data)
-                ops.upsample_window_bwd(y.grad, x.grad, align_corners, False, full_hw, lo_origin, hi_origin)
+                if x.consumers == 1 and x.act != ACT_NONE:
+                    ops.upsample_window_bwd(y.grad, x.grad, align_corners, False, full_hw, lo_origin, hi_origin, x.data,
+                                            x.act, x.slope)
+                    x.grad_masked = True
+                else:
+                    ops.upsample_window_bwd(y.grad, x.grad, align_corners, False, full_hw, lo_origin, hi_origin)
             else:
                 ops.upsample_window_bwd(y.grad, x.grad, align_corners, True, full_hw, lo_origin, hi_origin)
             y.grad = None

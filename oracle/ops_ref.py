@@ -186,8 +186,11 @@ class RefOps:
         return out
 
     @torch.enable_grad()
-    def upsample_bwd(self, dy, dx, align_corners, accumulate):
+    def upsample_bwd(self, dy, dx, align_corners, accumulate, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0):
         n, h, w, c = dx.shape
+        if mask_y is not None:
+            return self.upsample_window_bwd(dy, dx, align_corners, accumulate, (h, w), (0, 0), (0, 0), mask_y,
+                                            mask_act, mask_slope)
         xx = torch.zeros(n, c, h, w, dtype=dy.dtype, requires_grad=True)
         y = F.interpolate(xx, scale_factor=2, mode="bilinear", align_corners=bool(align_corners))
         (g,) = torch.autograd.grad(y, xx, _nchw(dy))
@@ -205,7 +208,8 @@ class RefOps:
         return y
 
     @torch.enable_grad()
-    def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin):
+    def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin, mask_y=None,
+                            mask_act=ACT_NONE, mask_slope=0.0):
         n, h, w, c = dx.shape
         xin = torch.zeros(n, h, w, c, dtype=dx.dtype, requires_grad=True)
         full = F.pad(_nchw(xin), [lo_origin[1], full_hw[1] - lo_origin[1] - w, lo_origin[0],
@@ -214,6 +218,8 @@ class RefOps:
         win = up[:, :, hi_origin[0]:hi_origin[0] + dy.shape[1], hi_origin[1]:hi_origin[1] + dy.shape[2]]
         (g,) = torch.autograd.grad(win, xin, _nchw(dy))
         dx.add_(g) if accumulate else dx.copy_(g)
+        if mask_y is not None:
+            dx.mul_(act_grad(mask_y, mask_act, mask_slope))
 
     def window_copy(self, src, src_origin, dst, dst_origin, hw, accumulate=False):
         s = src[:, src_origin[0]:src_origin[0] + hw[0], src_origin[1]:src_origin[1] + hw[1], :]

@@ -154,6 +154,14 @@ def test_pool_upsample_add_copy_act(cuda_ops, c):
             REF.upsample_bwd(guc, dc, align, acc)
             cuda_ops.upsample_bwd(gud, dd, align, acc)
             close(dd, dc, 2e-6, "upsample bwd align=%s" % align)
+    # activation derivative of the upsampled tensor fused into the upsample backward
+    for act in (ACT_RELU, ACT_LEAKY):
+        for align in (True, False):
+            guc, gud = act_pair(cuda_ops, n, 2 * h, 2 * w, c, 24)
+            dc, dd = act_pair(cuda_ops, n, h, w, c, 25)
+            REF.upsample_bwd(guc, dc, align, False, xc, act, 0.1)
+            cuda_ops.upsample_bwd(gud, dd, align, False, xd, act, 0.1)
+            close(dd, dc, 2e-6, "upsample bwd with fused act mask")
     yc, yd = act_pair(cuda_ops, n, h, w, c, 18)
     close(cuda_ops.add(xd, yd), REF.add(xc, yc), 1e-7, "add")
     for act in (ACT_RELU, ACT_LEAKY, ACT_SIGMOID, ACT_TANH):
