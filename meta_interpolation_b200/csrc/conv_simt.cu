@@ -589,7 +589,7 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
                              const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n,
                              int h, int wd, int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
     const long long m_total = (long long)n * h * wd;
-    if (small_cout_fprop_ok(cin, cout, k)) {
+    if (small_cout_fprop_ok(cin, cout, k) && m_total >= 4096) {   // (one thread per pixel: pointless on 1x1 maps)
         const int sc = cout <= 8 ? 8 : 16;
         const size_t sm = (size_t)k * k * cin * sc * sizeof(float);
         static bool attr = false;

@@ -3,7 +3,11 @@
 // the zero-padding conv engine into a reflection-padding one, CAIN's space-to-depth / depth-to-space image
 // transforms with the mean shift folded in, and the channel-attention pooling / rescaling.
 // All NHWC fp32, HBM-bound, one thread per element or per pixel; reductions are deterministic (no atomics).
+#include <cooperative_groups.h>
+
 #include "mi_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -285,47 +289,60 @@ __global__ void depth_to_space_bwd_kernel(const float* __restrict__ gout, float*
 }
 
 // ----------------------------------------------------------------------------- channel attention
-// mean over the interior (ring excluded) of each channel: grid (n, ceil(c/32)), block 32 channel lanes x 32 pixel
-// lanes, coalesced 128-byte rows, deterministic tree reduction.  `mul` (optional) turns it into sum(x*mul), the
-// gradient of the per-channel scale (model_utils.py:931-955: x * y).
-__global__ void __launch_bounds__(1024)
+// mean over the interior (ring excluded) of each channel.  One thread-block CLUSTER of eight CTAs per (image, 32-channel
+// group): every CTA (32 channel lanes x 32 pixel lanes, coalesced 128-byte rows, four loads in flight per thread)
+// reduces one eighth of the pixels, then CTA 0 collects the eight partial rows through distributed shared memory in
+// rank order -- deterministic, no workspace, no second launch.  (The single-CTA form put 12 blocks on 148 SMs and was
+// a quarter of a CAIN task.)  `mul` (optional) turns it into sum(x*mul), the gradient of the per-channel scale
+// (model_utils.py:931-955: x * y).
+constexpr int IR_CLUSTER = 8;
+
+__global__ void __cluster_dims__(1, 1, IR_CLUSTER) __launch_bounds__(1024)
 interior_reduce_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mul, int ldm,
                        float* __restrict__ out, int h, int w, int c, int ring, float scale) {
     __shared__ float red[32][33];
+    __shared__ float part[32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
     const int img = blockIdx.x;
     const int ch = blockIdx.y * 32 + threadIdx.x;
     const int ih = h - 2 * ring, iw = w - 2 * ring;
     const long long npix = (long long)ih * iw;
-    float s0 = 0.f, s1 = 0.f;
+    const long long per = (npix + IR_CLUSTER - 1) / IR_CLUSTER;
+    const long long q_end = min(npix, (long long)(rank + 1) * per);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
     if (ch < c) {
         const float* bx = x + (long long)img * h * w * ldx + ch;
         const float* bm = mul ? mul + (long long)img * h * w * ldm + ch : nullptr;
-        long long q = threadIdx.y;
-        for (; q + 32 < npix; q += 64) {
-            const int y0 = (int)(q / iw), x0 = (int)(q - (long long)y0 * iw);
-            const long long q1 = q + 32;
-            const int y1 = (int)(q1 / iw), x1 = (int)(q1 - (long long)y1 * iw);
-            const long long o0 = (long long)(y0 + ring) * w + x0 + ring, o1 = (long long)(y1 + ring) * w + x1 + ring;
-            float a0 = bx[o0 * ldx], a1 = bx[o1 * ldx];
-            if (bm) { a0 *= bm[o0 * ldm]; a1 *= bm[o1 * ldm]; }
-            s0 += a0; s1 += a1;
-        }
-        for (; q < npix; q += 32) {
-            const int y0 = (int)(q / iw), x0 = (int)(q - (long long)y0 * iw);
-            const long long o0 = (long long)(y0 + ring) * w + x0 + ring;
-            float a0 = bx[o0 * ldx];
-            if (bm) a0 *= bm[o0 * ldm];
-            s0 += a0;
-        }
-    }
-    red[threadIdx.y][threadIdx.x] = s0 + s1;
-    __syncthreads();
-    if (threadIdx.y == 0 && ch < c) {
-        float s = 0.f;
+        for (long long q = (long long)rank * per + threadIdx.y; q < q_end; q += 128) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s += red[j][threadIdx.x];
-        out[(long long)img * c + ch] = s * scale;
+            for (int u = 0; u < 4; ++u) {
+                const long long qq = q + 32 * u;
+                if (qq < q_end) {
+                    const int y0 = (int)(qq / iw), x0 = (int)(qq - (long long)y0 * iw);
+                    const long long o0 = (long long)(y0 + ring) * w + x0 + ring;
+                    float a0 = bx[o0 * ldx];
+                    if (bm) a0 *= bm[o0 * ldm];
+                    s[u] += a0;
+                }
+            }
+        }
     }
+    red[threadIdx.y][threadIdx.x] = (s[0] + s[1]) + (s[2] + s[3]);
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) t += red[j][threadIdx.x];
+        part[threadIdx.x] = t;
+    }
+    cluster.sync();                                   // every CTA's partial row is in its shared memory
+    if (rank == 0 && threadIdx.y == 0 && ch < c) {
+        float t = 0.f;
+        for (int r = 0; r < IR_CLUSTER; ++r) t += cluster.map_shared_rank(part, r)[threadIdx.x];
+        out[(long long)img * c + ch] = t * scale;
+    }
+    cluster.sync();                                   // remote shared memory stays alive until CTA 0 has read it
 }
 
 // out = o * s[n,c] + res   (RCAB: x * y then out += res, model_utils.py:955,985)
@@ -490,8 +507,8 @@ int mi_depth_to_space_bwd(const float* gout, float* gin, int ldi, int n, int h, 
 int mi_interior_reduce(const float* x, int ldx, const float* mul, int ldm, float* out, int n, int h, int wd, int c,
                        int ring, float scale, mi_stream_t stream) {
     if (!x || !out || ring < 0 || h <= 2 * ring || wd <= 2 * ring) return MI_ERR_BAD_ARG;
-    interior_reduce_kernel<<<dim3(n, mi_cdiv(c, 32)), dim3(32, 32), 0, mi_cs(stream)>>>(x, ldx, mul, ldm, out, h, wd, c,
-                                                                                       ring, scale);
+    interior_reduce_kernel<<<dim3(n, mi_cdiv(c, 32), IR_CLUSTER), dim3(32, 32), 0, mi_cs(stream)>>>(x, ldx, mul, ldm, out,
+                                                                                                   h, wd, c, ring, scale);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }
