@@ -120,6 +120,8 @@ class SceneAdaptiveInterpolation(nn.Module):
         kind = self.args.optimizer if self.args.optimizer in ('Adam', 'Adamax') else 'SGD'
         betas = (0.9, 0.999) if kind == 'Adamax' else (0.9, 0.99)
         self.optimizer = FusedOuterOptimizer(self._groups, self.ops, kind, lr=args.outer_lr, betas=betas)
+        # checkpoints exchange optimizer state in the order of the reference's Adam(self.trainable_parameters())
+        self.optimizer.set_reference_order(list(self.trainable_parameters()))
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer=self.optimizer, mode='min', factor=0.2,
                                                                     patience=5)
         self.criterion = Loss(args, ops=self.ops)

@@ -52,6 +52,74 @@ class FusedOuterOptimizer(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._step = 0
 
+    # ------------------------------------------------------------------ checkpoint interchange
+    # The reference saves ``optimizer.state_dict()`` of a stock ``torch.optim.Adam / Adamax / SGD`` built over
+    # ``trainable_parameters()`` (utils.py:34-75, experiment_builder.py save/load).  The moments here live in flat
+    # buffers, so ``state_dict`` / ``load_state_dict`` translate to and from the stock per-parameter layout
+    # (``state[i] = {step, exp_avg, exp_avg_sq | exp_inf}`` in the order of ``ref_order``).
+    def set_reference_order(self, params):
+        """Parameter order of the reference's optimizer (``nn.Module.parameters()`` order of its system)."""
+        own = {id(p) for g in self.flat_groups for p, _ in g.members}
+        assert {id(p) for p in params} == own, "reference order must list exactly the optimised parameters"
+        self._ref_order = list(params)
+
+    def _moment_views(self):
+        """{id(param): (exp_avg view, second-moment view)} shaped like the parameter (views of the flat buffers)."""
+        out = {}
+        for g in self.flat_groups:
+            for p, gv in g.members:
+                off = gv.storage_offset() - g.grad.storage_offset()
+                out[id(p)] = tuple(None if b is None else torch.as_strided(b, gv.size(), gv.stride(), off)
+                                   for b in (g.m, g.v))
+        return out
+
+    def state_dict(self):
+        order = getattr(self, "_ref_order", None) or [p for g in self.flat_groups for p, _ in g.members]
+        views = self._moment_views()
+        second = "exp_avg_sq" if self.kind == 1 else "exp_inf"
+        state = {}
+        if self.kind != 0 and self._step > 0:
+            for i, p in enumerate(order):
+                m, v = views[id(p)]
+                state[i] = {"step": torch.tensor(float(self._step)), "exp_avg": m.detach().clone().contiguous(),
+                            second: v.detach().clone().contiguous()}
+        hp = dict(self.param_groups[0])
+        hp["params"] = list(range(len(order)))
+        return {"state": state, "param_groups": [hp], "fused_step": self._step}
+
+    def load_state_dict(self, state_dict):
+        order = getattr(self, "_ref_order", None) or [p for g in self.flat_groups for p, _ in g.members]
+        hp_in = state_dict["param_groups"][0]
+        for key in ("lr", "betas", "eps", "weight_decay"):
+            if key in hp_in:
+                self.param_groups[0][key] = hp_in[key]
+        st = state_dict.get("state", {})
+        if self.kind == 0 or not st:
+            self._step = int(state_dict.get("fused_step", 0))
+            return
+        if len(st) != len(order):
+            raise ValueError("optimizer state has %d entries for %d parameters" % (len(st), len(order)))
+        for g in self.flat_groups:
+            if g.m is None:
+                g.m = torch.zeros_like(g.flat)
+                g.v = torch.zeros_like(g.flat)
+        views = self._moment_views()
+        second = "exp_avg_sq" if self.kind == 1 else "exp_inf"
+        steps = set()
+        with torch.no_grad():
+            for i, p in enumerate(order):
+                e = st[i] if i in st else st[str(i)]
+                m, v = views[id(p)]
+                if tuple(e["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError("optimizer state %d has shape %s, parameter has %s"
+                                     % (i, tuple(e["exp_avg"].shape), tuple(p.shape)))
+                m.copy_(e["exp_avg"])
+                v.copy_(e[second])
+                steps.add(int(float(e["step"])))
+        if len(steps) != 1:
+            raise ValueError("per-parameter step counts differ: %s" % sorted(steps))
+        self._step = steps.pop()
+
     def gather_grads(self):
         """Move autograd ``.grad`` tensors (compat path) into the flat gradient buffers."""
         for g in self.flat_groups:

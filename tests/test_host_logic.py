@@ -234,3 +234,34 @@ def test_tiled_evaluation_follows_experiment_builder_splitting(ref_ops, monkeypa
     assert calls == [(4, 3)] * 4
     assert torch.equal(torch.stack(outs), frames[3])             # stitched back in place
     assert float(losses["loss"]) == ((1 + 2) / 2 + (3 + 4) / 2) / 2
+
+
+@pytest.mark.parametrize("opt", ["Adam", "Adamax", "SGD"])
+def test_outer_optimizer_state_dict_round_trip(ref_ops, opt):
+    """The fused outer optimizer writes / reads the stock per-parameter ``torch.optim`` state layout: a fresh system
+    restored from (model state_dict, optimizer state_dict) continues bit-identically to the one that kept running."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    kw = dict(optimizer=opt, outer_lr=1e-3, number_of_training_steps_per_iter=1, metasgd=(opt == "Adamax"))
+    g = torch.Generator().manual_seed(2)
+    batches = [[torch.rand(1, 3, 32, 32, generator=g) for _ in range(7)] for _ in range(2)]
+    a = SceneAdaptiveInterpolation(make_args(**kw), ops=ref_ops)
+    a.run_train_iter(batches[0], epoch=0)
+    sd_model = {k: v.detach().clone() for k, v in a.state_dict().items()}
+    sd_opt = a.optimizer.state_dict()
+    n_params = len(list(a.trainable_parameters()))
+    assert sd_opt["param_groups"][0]["params"] == list(range(n_params))
+    if opt == "SGD":
+        assert sd_opt["state"] == {}
+    else:
+        second = "exp_avg_sq" if opt == "Adam" else "exp_inf"
+        assert len(sd_opt["state"]) == n_params
+        for i, p in enumerate(a.trainable_parameters()):
+            assert sd_opt["state"][i]["exp_avg"].shape == p.shape and sd_opt["state"][i][second].shape == p.shape
+            assert sd_opt["state"][i]["exp_avg"].is_contiguous()
+    b = SceneAdaptiveInterpolation(make_args(**kw), ops=ref_ops)
+    b.load_state_dict(sd_model)
+    b.optimizer.load_state_dict(sd_opt)
+    a.run_train_iter(batches[1], epoch=0)
+    b.run_train_iter(batches[1], epoch=0)
+    for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(x, y), k

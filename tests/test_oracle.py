@@ -149,3 +149,66 @@ def test_oracle_equals_live_reference():
     losses, rpreds, _ = system.run_train_iter(frames, epoch=0, do_evaluation=False)
     assert float(losses["loss"]) == pytest.approx(float(loss), abs=1e-7)
     assert (rpreds[0] - preds[0]).abs().max().item() <= 1e-7
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_outer_optimizer_state_interchanges_with_reference_checkpoints():
+    """the fused flat-buffer outer optimizer speaks the stock ``torch.optim.Adam.state_dict()``
+    layout the reference checkpoints carry (utils.py:34-118): after one meta-iteration both hold the same per-parameter
+    moments; a fresh system restored from the REFERENCE's model + optimizer state continues exactly like the
+    reference; and the reference's Adam accepts the state this repo writes."""
+    import copy
+    import warnings
+    from oracle import reference_shims as rs
+    from oracle.ops_ref import RefOps
+    from oracle.make_golden import synthetic_frames
+    from meta_interpolation_b200 import backbone
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    from helpers import make_args
+
+    over = dict(model="sepconv", loss="1*L1", optimizer="Adam", number_of_training_steps_per_iter=1, outer_lr=1e-3)
+    ref, rargs = rs.build_system(batch_size=1, **over)
+    ops = RefOps()
+    saved = backbone._default_ops
+    backbone.set_default_ops(ops)
+    try:
+        mine = SceneAdaptiveInterpolation(make_args(batch_size=1, **over), ops=ops)
+        frames = synthetic_frames(3, 1, 32)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref.run_train_iter(frames, epoch=0)
+        mine.run_train_iter(frames, epoch=0)
+        rsd, msd = ref.optimizer.state_dict(), mine.optimizer.state_dict()
+        assert sorted(rsd["state"]) == sorted(msd["state"]) and len(msd["state"]) == len(list(mine.trainable_parameters()))
+        for i, e in rsd["state"].items():
+            assert int(float(e["step"])) == int(float(msd["state"][i]["step"])) == 1
+            for key in ("exp_avg", "exp_avg_sq"):
+                a, b = msd["state"][i][key], e[key]
+                assert a.shape == b.shape
+                assert (a - b).abs().max().item() <= 2e-5 * max(b.abs().max().item(), 1e-12), (i, key)
+
+        # reference checkpoint -> this repo: model + optimizer state, then one more iteration on both
+        fresh = SceneAdaptiveInterpolation(make_args(batch_size=1, **over), ops=ops)
+        fresh.load_state_dict(copy.deepcopy(ref.state_dict()))
+        fresh.optimizer.load_state_dict(copy.deepcopy(rsd))
+        frames2 = synthetic_frames(4, 1, 32)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref.run_train_iter(frames2, epoch=0)
+        fresh.run_train_iter(frames2, epoch=0)
+        rp, fp = dict(ref.net.named_parameters()), dict(fresh.net.named_parameters())
+        for k in rp:
+            d = (rp[k].detach() - fp[k].detach()).abs().max().item()
+            # an Adam step is lr * m / sqrt(v): elements whose gradient is ~0 amplify rounding, so the bar is a small
+            # fraction of the step size (lr = 1e-3), not of the parameter scale
+            mean = (rp[k].detach() - fp[k].detach()).abs().mean().item()
+            assert d <= 0.1 * over["outer_lr"] and mean <= 1e-3 * over["outer_lr"], (k, d, mean)
+
+        # this repo -> the reference's stock Adam
+        ref2, _ = rs.build_system(batch_size=1, **over)
+        ref2.optimizer.load_state_dict(copy.deepcopy(mine.optimizer.state_dict()))
+        st = ref2.optimizer.state_dict()["state"]
+        assert len(st) == len(msd["state"]) and torch.equal(st[1]["exp_avg"], msd["state"][1]["exp_avg"])
+    finally:
+        backbone.set_default_ops(saved)
