@@ -21,6 +21,12 @@ def cuda_ops():
         pytest.skip("no CUDA device")
     from meta_interpolation_b200 import backbone
     ops = backbone.default_ops()   # raises if libmi_b200.so is missing: no silent fallback
+    # Dirty the caching allocator once: a 1 GiB block of NaN is released back to it, so the `torch.empty` buffers of
+    # the tests that follow are carved out of NaN-filled memory.  A kernel that reads what nobody wrote (or writes
+    # into a neighbouring channel slice) then fails here too, not only under MI_B200_POISON=1 or after some unlucky
+    # sequence of earlier tests (see profiles/README.md for the bug this caught).
+    dirty = torch.full((256 * 1024 * 1024,), float("nan"), device="cuda")
+    del dirty
     return ops
 
 
