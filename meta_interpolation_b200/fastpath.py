@@ -28,7 +28,14 @@ First-order outer gradients follow SURVEY Appendix E4:
   LSLR fixed lr      dL/dtheta = G
   LSLR learnable lr  + dL/dlr[t][k] = -<g_k[t], G[t]>
   Meta-SGD (SGD)     + dL/dalpha    = -(sum_k g_k) (.) G
+  Meta-SGD (Adamax)  + dL/dalpha    = -((theta - w_K) / alpha) (.) G      (sum of the K update directions)
   multi-step loss    the above per step with weight w_k.
+
+The Adam / Adamax inner rules (reference inner_loop_optimizers.py:150-244, :335-426) cannot be folded into the
+weight-gradient epilogue (they need the whole gradient tensor's moments first), so their support graphs store the
+step's gradients into a lane arena and apply ONE flat ``mi_inner_update`` launch over the whole fast-weight arena,
+followed by the rotation of the routed filters; bias corrections and the lr column are baked per step, so these
+rules capture one support graph per inner step.
 """
 import gc
 import os
@@ -37,6 +44,7 @@ import torch
 
 from . import utils
 from .arena import Arena
+from .inner_loop_optimizers import RULE_ADAM, RULE_ADAMAX_LSLR, RULE_ADAMAX_METASGD, RULE_SGD
 from .ops import WG_ACCUM, WG_SGD_SCALAR, WG_SGD_TENSOR, WG_STORE, WgradSpec
 from .tape import ConvParam, Tape
 
@@ -59,6 +67,12 @@ class _Sink:
         if self.mode == 'inner':
             if not net.is_routed(wn):
                 return                       # dead work in support passes (Q1/Q2/Q2b)
+            if fp.rule != RULE_SGD:          # moment rules: store g, the flat update follows the backward pass
+                garena = lane.gstep
+                spec = WgradSpec(WG_STORE, grad_w=garena.kernel_view(wn),
+                                 grad_b=garena.kernel_view(bn) if has_b else None)
+                fp.ops.conv_wgrad(x, dy, k, ldw, spec)
+                return
             fast = lane.fast
             spec = WgradSpec(w_in=p.w, b_in=p.b, w_out=fast.kernel_view(wn),
                              b_out=fast.kernel_view(bn) if has_b else None, wt_out=lane.wt_buffer(p.name))
@@ -163,7 +177,11 @@ class _Lane:
         self.capture_stream = torch.cuda.Stream(device=dev) if cuda else None
         self.fast = Arena(lay, dev)
         self.cur_lr = torch.zeros(len(net.param_names), device=dev)
-        self.gsum = Arena(lay, dev) if fp.metasgd else None
+        self.gsum = Arena(lay, dev) if (fp.metasgd and fp.rule == RULE_SGD) else None
+        # Adam / Adamax inner rules: gradient of the step in flight and the per-task moments
+        self.gstep = Arena(lay, dev) if fp.rule != RULE_SGD else None
+        self.exp_avg = Arena(lay, dev) if fp.rule in (RULE_ADAM, RULE_ADAMAX_LSLR) else None
+        self.exp_avg_sq = Arena(lay, dev) if fp.rule == RULE_ADAM else None
         self.gquery = Arena(lay, dev) if (fp.metasgd or fp.learnable_lr or fp.l2f) else None
         self.gamma = None        # L2F attenuation of the task in flight
         self.l2f_records = []    # (task embedding, dL/dgamma) per adapted task, consumed once per meta-batch
@@ -220,8 +238,15 @@ class FastPath:
         a = system.args
         if a.second_order and system.current_epoch > a.first_order_to_second_order_epoch:
             return False
-        if a.optimizer != 'SGD':
+        if a.optimizer not in ('SGD', 'Adam', 'Adamax'):
             return False
+        if a.optimizer != 'SGD':
+            # moment rules are graph-captured with a fixed LSLR table, and as Meta-SGD + Adamax (the authors'
+            # scripts/run_sepconv.sh operating point); Meta-SGD + Adam fails in the reference for K >= 2 (F11)
+            if a.attenuate or (a.metasgd and a.optimizer != 'Adamax'):
+                return False
+            if not a.metasgd and a.learnable_per_layer_per_step_inner_loop_learning_rate:
+                return False
         if a.attenuate:
             # L2F (reference :231-272) is graph-captured for the plain fixed-lr LSLR rule; its combinations with
             # Meta-SGD / learnable lr / the multi-step loss stay on the compat path
@@ -232,7 +257,7 @@ class FastPath:
                 return False
         if not all(t.split('*')[1] in LOSS_KIND for t in a.loss.split('+')):
             return False
-        if a.metasgd and any(not system.net.is_routed(n) for n in system.net.param_names):
+        if a.metasgd and a.optimizer == 'SGD' and any(not system.net.is_routed(n) for n in system.net.param_names):
             return False   # the reference itself fails here for K>=2
         return hasattr(system.net, 'build_graph')
 
@@ -244,6 +269,12 @@ class FastPath:
         self.metasgd = bool(a.metasgd)
         self.learnable_lr = (not self.metasgd) and bool(a.learnable_per_layer_per_step_inner_loop_learning_rate)
         self.l2f = bool(a.attenuate)
+        if a.optimizer == 'SGD':
+            self.rule = RULE_SGD
+        elif a.optimizer == 'Adam':
+            self.rule = RULE_ADAM
+        else:
+            self.rule = RULE_ADAMAX_METASGD if self.metasgd else RULE_ADAMAX_LSLR
         self.K = a.number_of_training_steps_per_iter
         self.use_graphs = bool(system.use_cuda_graphs) and self.ops.name == 'cuda'
         dev = self.ops.device
@@ -251,6 +282,8 @@ class FastPath:
         self.seg = lay.segment_table().to(dev)
         self.routed_mask = torch.tensor([1.0 if self.net.is_routed(n) else 0.0 for n in self.net.param_names],
                                         device=dev)
+        self.skip = torch.tensor([0 if self.net.is_routed(n) else 1 for n in self.net.param_names], dtype=torch.uint8,
+                                 device=dev)
         self.numel = torch.tensor([float(lay.logical_numel(n)) for n in self.net.param_names], device=dev)
         self.loss_terms = [(LOSS_KIND[t.split('*')[1]], float(t.split('*')[0])) for t in a.loss.split('+')]
         self.meta_wt = {}
@@ -315,7 +348,26 @@ class FastPath:
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             out.grad = self._loss(prog, out.data, prog.f0.shape[0])
             tape.backward()
+            if self.rule != RULE_SGD:
+                self._moment_update(lane, src, step_slot)
         return body
+
+    def _moment_update(self, lane, src, step):
+        """Adam / Adamax inner step ``step`` over the whole arena (un-routed tensors skipped: their gradient is
+        None in the reference, inner_loop_optimizers.py:209 / :393), then the rotated copies of the new filters."""
+        ops, net = self.ops, self.net
+        w_in = net.arena.flat if src == 'meta' else lane.fast.flat
+        if self.metasgd:
+            lr, per_element, stride = self.sys.alpha.flat, True, 0
+        else:
+            lr, per_element, stride = self.sys.lr_table, False, self.sys.lr_table.shape[1]
+        ops.inner_update(w_in, lane.gstep.flat, lane.fast.flat,
+                         lane.exp_avg.flat if lane.exp_avg is not None else None,
+                         lane.exp_avg_sq.flat if lane.exp_avg_sq is not None else None,
+                         lr, per_element, stride, 0 if self.metasgd else step, self.seg, self.skip, self.rule, step + 1)
+        for name in net.conv_names:
+            if net.is_routed(name + ".weight"):
+                ops.weight_to_dgrad(lane.fast.kernel_view(name + ".weight"), out=lane.wt_buffer(name))
 
     def _embed_body(self, lane):
         """L2F task embedding (reference :231-255): both support triplets through the META weights, gradient of the
@@ -386,14 +438,19 @@ class FastPath:
     # ------------------------------------------------------------------ one task
     def _support_step(self, lane, frames, task, step, h, w, support_idxs):
         src = 'meta' if (step == 0 and not self.l2f) else 'fast'     # L2F: step 0 starts from gamma (.) theta
-        slot = step if self.learnable_lr else 0
+        slot = step if (self.learnable_lr or self.rule != RULE_SGD) else 0
         prog = self._program(lane, ('support', src, slot, h, w), self._support_body(lane, src, slot),
                              len(support_idxs), h, w)
         for i, (a, b, c) in enumerate(support_idxs):
             prog.f0[i].copy_(frames[a][task])
             prog.f1[i].copy_(frames[c][task])
             prog.tgt[i].copy_(frames[b][task])
-        if not self.metasgd:
+        if self.rule != RULE_SGD:
+            if step == 0:      # moments live for the K steps of one task (initialize_state per task, Q5)
+                for arena in (lane.exp_avg, lane.exp_avg_sq):
+                    if arena is not None:
+                        self.ops.fill(arena.flat, 0.0)
+        elif not self.metasgd:
             lane.cur_lr.copy_(self.sys.lr_table[:, step])
         elif step == 0:
             self.ops.fill(lane.gsum.flat, 0.0)
@@ -415,7 +472,12 @@ class FastPath:
         ops = self.ops
         G = lane.gquery.flat
         ops.axpby(G, scale, lane.acc_theta.flat, 1.0)                     # dL/dtheta += scale * G
-        if self.metasgd:
+        if self.metasgd and self.rule != RULE_SGD:
+            # alpha is constant over the K steps, so the update directions sum to (theta - w_K) / alpha
+            alpha = self.sys.alpha.flat
+            dirs = torch.where(alpha != 0, (self.net.arena.flat - lane.fast.flat) / alpha, torch.zeros_like(alpha))
+            ops.addcmul(lane.acc_alpha.flat, -scale, dirs, G)
+        elif self.metasgd:
             ops.addcmul(lane.acc_alpha.flat, -scale, lane.gsum.flat, G)    # dL/dalpha -= scale * gsum (.) G
         elif self.learnable_lr:
             for j in range(steps_done):

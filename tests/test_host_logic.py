@@ -47,6 +47,7 @@ def test_plugin_forward_and_unrouted_grads_are_none_after_step0(ref_ops):
                                        ("sepconv_lslr_learnable_msl_k2", True),
                                        ("sepconv_lslr_learnable_msl_k2", False),
                                        ("sepconv_lslr_adam_k2", False), ("sepconv_metasgd_adamax_k2", False),
+                                       ("sepconv_lslr_adam_k2", True), ("sepconv_metasgd_adamax_k2", True),
                                        ("sepconv_l2f_sgd_k1", False), ("sepconv_l2f_sgd_k1", True)])
 def test_system_against_reference_golden(ref_ops, name, fast):
     fx = load_golden(name)
@@ -197,6 +198,73 @@ def test_l2f_graph_path_matches_compat_path_on_attenuator_gradients(ref_ops, nam
         a, b = delta[True][k], delta[False][k]
         assert b.abs().max().item() > 0, k                         # every L2F tensor receives a gradient
         assert (a - b).abs().max().item() <= 1e-3 * b.abs().max().item(), (k, (a - b).abs().max().item())
+
+
+@pytest.mark.parametrize("name", ["sepconv_lslr_adam_k2", "sepconv_metasgd_adamax_k2"])
+def test_moment_rules_graph_path_matches_compat_path_on_outer_gradients(ref_ops, name):
+    """Adam / Adamax inner rules (reference inner_loop_optimizers.py:150-244, :335-426): the goldens pin loss and
+    predictions; the outer gradients (theta, and Meta-SGD's alpha = -((theta - w_K)/alpha) (.) G on the graph path)
+    are checked path against path on the flat gradient buffers handed to the outer step."""
+    fx = load_golden(name)
+    grads = {}
+    for fast in (False, True):
+        system = system_from_fixture(fx, ref_ops, fast_path=fast)
+        assert system.fast_path_supported() == fast
+        opt, seen = system.optimizer, {}
+        orig = opt.step
+
+        def step(opt=opt, seen=seen, orig=orig):
+            opt.gather_grads()
+            for g in opt.flat_groups:
+                seen[g.name] = g.grad.detach().clone()
+            orig()
+        opt.step = step
+        system.run_train_iter(list(fx["frames"]), epoch=0)
+        grads[fast] = seen
+    assert set(grads[True]) == set(grads[False]) and len(grads[True]) == (2 if fx["args"]["metasgd"] else 1)
+    for k, b in grads[False].items():
+        a = grads[True][k]
+        assert b.abs().max().item() > 0, k
+        tol = 1e-4 * b.abs().max().item() + 1e-12
+        assert (a - b).abs().max().item() <= tol, (k, (a - b).abs().max().item(), b.abs().max().item())
+
+
+@pytest.mark.parametrize("kw", [
+    dict(optimizer="Adamax", metasgd=True, use_multi_step_loss_optimization=True, multi_step_loss_num_epochs=5,
+         inner_lr=1e-4, number_of_training_steps_per_iter=2),
+    dict(optimizer="Adamax", inner_lr=1e-7, number_of_training_steps_per_iter=3)],
+    ids=["metasgd_adamax_msl", "lslr_adamax_k3"])
+def test_moment_rule_combinations_graph_path_matches_compat_path(ref_ops, kw):
+    """Meta-SGD-Adamax under the multi-step loss (alpha gradient per step from (theta - w_k)/alpha) and the
+    LSLR-Adamax quirk over three steps (exp_avg persists, exp_inf does not; inner_loop_optimizers.py:229-236; tiny lr:
+    that rule is chaotic at practical rates in the reference too); train and validation iterations."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    g = torch.Generator().manual_seed(4)
+    frames = [torch.rand(2, 3, 32, 40, generator=g) for _ in range(7)]
+    res = {}
+    for fast in (True, False):
+        s = SceneAdaptiveInterpolation(make_args(number_of_evaluation_steps_per_iter=2, fast_path=fast, **kw),
+                                       ops=ref_ops)
+        assert s.fast_path_supported() == fast
+        opt, seen = s.optimizer, {}
+        orig = opt.step
+
+        def step(opt=opt, seen=seen, orig=orig):
+            opt.gather_grads()
+            for gr in opt.flat_groups:
+                seen[gr.name] = gr.grad.detach().clone()
+            orig()
+        opt.step = step
+        lt, pt, _ = s.run_train_iter(frames, epoch=0)
+        lv, pv, _ = s.run_validation_iter(frames)
+        res[fast] = (float(lt["loss"].detach()), torch.cat(pt), seen, float(lv["loss"].detach()), torch.cat(pv))
+    a, b = res[True], res[False]
+    assert abs(a[0] - b[0]) <= 2e-6 and abs(a[3] - b[3]) <= 2e-6
+    assert (a[1] - b[1]).abs().max().item() <= 5e-6
+    assert (a[4] - b[4]).abs().max().item() <= 5e-5      # after a sign-like Adamax OUTER step on both paths
+    for k, gb in b[2].items():
+        # (the LSLR-Adamax direction m/(|g|+eps) magnifies fp32 summation-order noise wherever |g| ~ eps)
+        assert (a[2][k] - gb).abs().max().item() <= 1e-3 * gb.abs().max().item() + 1e-12, k
 
 
 @pytest.mark.parametrize("model,hw", [("sepconv", (32, 40)), ("superslomo", (64, 64))])

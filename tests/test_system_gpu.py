@@ -17,6 +17,8 @@ LOSS_TOL = 5e-4
     ("sepconv_lslr_sgd_k1_b2_mse", True, True), ("sepconv_lslr_learnable_msl_k2", True, True),
     ("sepconv_lslr_learnable_msl_k2", False, False), ("sepconv_lslr_adam_k2", False, False),
     ("sepconv_metasgd_adamax_k2", False, False), ("sepconv_l2f_sgd_k1", False, False),
+    ("sepconv_lslr_adam_k2", True, True), ("sepconv_metasgd_adamax_k2", True, True),
+    ("sepconv_metasgd_adamax_k2", True, False),
     ("sepconv_l2f_sgd_k1", True, True), ("sepconv_l2f_sgd_k1", True, False)])
 def test_train_iter_against_reference_golden(cuda_ops, name, fast, graphs):
     fx = load_golden(name)
@@ -40,19 +42,31 @@ def test_train_iter_against_reference_golden(cuda_ops, name, fast, graphs):
             assert torch.allclose(mine[1:], d[1:], rtol=rtol, atol=1e-7), k
 
 
-def test_graph_replay_is_stable_over_iterations(cuda_ops):
-    """Three meta-iterations: eager / capture+replay / replay must track the CPU oracle step for step."""
-    fx = load_golden("sepconv_lslr_sgd_k2")
+@pytest.mark.parametrize("name", ["sepconv_lslr_sgd_k2", "sepconv_lslr_adam_k2", "sepconv_metasgd_adamax_k2"])
+def test_graph_replay_is_stable_over_iterations(cuda_ops, name):
+    """Three meta-iterations: eager / capture+replay / replay must track the CPU oracle step for step (the Adam /
+    Adamax inner rules capture one support graph per inner step).  The moment rules take sign-like steps, which
+    amplify TF32 rounding from iteration to iteration, so after the first iteration they are held against the SAME
+    kernels launched eagerly instead of the fp32 oracle."""
+    fx = load_golden(name)
     system = system_from_fixture(fx, cuda_ops, fast_path=True, cuda_graphs=True)
+    sgd = fx["args"]["optimizer"] == "SGD"
+    eager = None if sgd else system_from_fixture(fx, cuda_ops, fast_path=True, cuda_graphs=False)
     ora = oracle_from_fixture(fx)
     g = torch.Generator().manual_seed(5)
     for it in range(3):
         frames = [torch.rand(2, 3, 64, 64, generator=g) for _ in range(7)]
         losses, preds, metrics = system.run_train_iter([f.cuda() for f in frames], epoch=0, do_evaluation=True)
-        loss, opreds, psnrs, _ = ora.run_train_iter(frames, 0)
-        assert abs(float(losses["loss"]) - float(loss)) <= LOSS_TOL, it
-        assert (torch.cat(preds).cpu() - torch.cat(opreds)).abs().max().item() <= PRED_TOL, it
-        assert abs(metrics["psnr"].avg - sum(psnrs) / len(psnrs)) < 0.01, it
+        if sgd or it == 0:
+            loss, opreds, psnrs, _ = ora.run_train_iter(frames, 0)
+            assert abs(float(losses["loss"]) - float(loss)) <= LOSS_TOL, it
+            assert (torch.cat(preds).cpu() - torch.cat(opreds)).abs().max().item() <= PRED_TOL, it
+            assert abs(metrics["psnr"].avg - sum(psnrs) / len(psnrs)) < 0.01, it
+        if eager is not None:
+            l2, p2, m2 = eager.run_train_iter([f.cuda() for f in frames], epoch=0, do_evaluation=True)
+            assert abs(float(losses["loss"]) - float(l2["loss"])) <= LOSS_TOL, it
+            assert (torch.cat(preds) - torch.cat(p2)).abs().max().item() <= PRED_TOL, it
+            assert abs(metrics["psnr"].avg - m2["psnr"].avg) < 0.01, it
 
 
 def test_eval_and_test_iters(cuda_ops):

@@ -26,6 +26,13 @@ CONFIGS = {
                   learnable_per_layer_per_step_inner_loop_learning_rate=True, use_multi_step_loss_optimization=True,
                   multi_step_loss_num_epochs=1), (256, 448), 8,
              "C5: rrin MAML++ (MSL + learnable per-step lr) K=5 256x448, 8 tasks per GPU (64 over 8)"),
+    # the operating point of the authors' scripts/run_sepconv.sh: Meta-SGD with the Adamax inner rule, K=3, batch 3
+    "sepconv_adamax": (dict(model="sepconv", loss="1*L1", optimizer="Adamax", metasgd=True, inner_lr=1e-5,
+                            outer_lr=1e-5, number_of_training_steps_per_iter=3), (256, 448), 3,
+                       "scripts/run_sepconv.sh: sepconv Meta-SGD + Adamax K=3 256x448 batch 3, graph path"),
+    "sepconv_adamax_compat": (dict(model="sepconv", loss="1*L1", optimizer="Adamax", metasgd=True, inner_lr=1e-5,
+                                   outer_lr=1e-5, number_of_training_steps_per_iter=3, fast_path=False), (256, 448), 3,
+                              "scripts/run_sepconv.sh: same, compat (autograd) path"),
 }
 
 
