@@ -35,7 +35,8 @@ def make_args(batch, cuda=True):
         metasgd=False, attenuate=False, learnable_per_layer_per_step_inner_loop_learning_rate=False,
         enable_inner_loop_optimizable_bn_params=False, second_order=False, first_order_to_second_order_epoch=-1,
         use_multi_step_loss_optimization=False, multi_step_loss_num_epochs=1, random_seed=12345, cuda=cuda,
-        num_gpu=1 if cuda else 0, pretrained_model=None, weight_decay=1e-4)
+        num_gpu=1 if cuda else 0, pretrained_model=None, weight_decay=1e-4,
+        load_checkpoint=False)   # seeded random init: no checkpoint files on the box
 
 
 def synthetic_septuplets(batch, seed, h=H, w=W):

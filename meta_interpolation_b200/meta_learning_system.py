@@ -125,9 +125,31 @@ class SceneAdaptiveInterpolation(nn.Module):
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer=self.optimizer, mode='min', factor=0.2,
                                                                     patience=5)
         self.criterion = Loss(args, ops=self.ops)
+        self._load_weights()
         self._fast = None
         self.use_fast_path = getattr(args, 'fast_path', True)
         self.use_cuda_graphs = getattr(args, 'cuda_graphs', True)
+
+    def _load_weights(self):
+        """reference :154-170: ``--resume`` restores checkpoint/<exp>/checkpoint.pth (model_best.pth in val / test
+        mode); ``--pretrained_model`` then overlays a backbone file with the lossy matching rules.  Harnesses that run
+        from the seeded random init with no files on disk (tests, bench.py, smoke) set ``args.load_checkpoint=False``."""
+        args = self.args
+        if args.resume and getattr(args, 'load_checkpoint', True):
+            print('Resume training')
+            utils.load_checkpoint(args, self, None)
+        if getattr(args, 'pretrained_model', None) is not None:
+            print('Loading pretrained model: %s' % args.pretrained_model)
+            checkpoint = torch.load(args.pretrained_model, map_location=self.device, weights_only=False)
+            if args.model == 'superslomo' and 'state_dictFC' in checkpoint.keys():
+                # the original SuperSloMo release keeps its two U-Nets in separate dicts
+                merged = {'flowComp.' + k: v for k, v in checkpoint['state_dictFC'].items()}
+                merged.update({'arbTimeFlowIntrp.' + k: v for k, v in checkpoint['state_dictAT'].items()})
+                utils.lossy_load_state_dict(self.net, merged)
+            elif args.model == 'superslomo':
+                utils.lossy_load_state_dict(self, checkpoint['state_dict'])
+            else:
+                utils.lossy_load_state_dict(self.net, checkpoint['state_dict'])
 
     # ------------------------------------------------------------------ flat buffers
     def _build_flat_groups(self):

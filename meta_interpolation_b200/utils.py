@@ -4,8 +4,15 @@ PSNR is computed on 8-bit-quantised tensors with ``mse + 1e-8`` exactly as
 utils.py:171-186,195-204; the squared-error reduction runs in one sm_100a kernel
 (``mi_psnr_accumulate``).  SSIM follows pytorch_msssim/__init__.py:19-75 (11x11
 gaussian, valid convolution) and is a logging-only metric.
+
+Checkpoint helpers (reference utils.py:34-118, 253-255) keep the reference's file layout
+(``checkpoint/<exp_name>/checkpoint.pth`` + ``model_best.pth``; a dict with ``epoch``, ``arch``, ``state_dict``,
+``best_PSNR`` and optionally ``optimizer``) and its lossy matching rules, so files written by either code base load in
+the other: the state-dict keys and shapes of this package's modules are the reference's.
 """
 import math
+import os
+import shutil
 
 import torch
 import torch.nn.functional as F
@@ -74,3 +81,79 @@ def calc_metrics(im_pred, im_gt, ops=None):
         psnr = -10 * math.log10(float(d.pow(2).mean()) + 1e-8)
     s = ssim(quantize(im_pred.detach(), 1.).unsqueeze(0), quantize(im_gt.detach(), 1.).unsqueeze(0), val_range=255)
     return psnr, s
+
+
+# ---------------------------------------------------------------------- checkpoints (reference utils.py:34-118)
+def _matching_entries(own_state, ckpt_state, report_missing_keys):
+    """Entries of ``ckpt_state`` whose key exists in ``own_state`` with the same shape; second value is True when
+    anything was left out (a shape differs, or -- load_checkpoint only, :47-58 -- a key is unknown / absent)."""
+    picked, partial = {}, False
+    for key, value in ckpt_state.items():
+        if key not in own_state:
+            partial = partial or report_missing_keys
+            continue
+        if own_state[key].size() != value.size():
+            print('Size mismatch while loading!   %s != %s   Skipping %s...'
+                  % (str(own_state[key].size()), str(value.size()), key))
+            partial = True
+            continue
+        picked[key] = value
+    if report_missing_keys and len(own_state) > len(picked):
+        partial = True
+    return picked, partial
+
+
+def _read(path, device=None):
+    # the reference's files pickle the argparse Namespace under 'arch' (experiment_builder.py:308-314)
+    return torch.load(path, map_location=device, weights_only=False)
+
+
+def update_lr(optimizer, lr):
+    """reference utils.py:253-255."""
+    for group in optimizer.param_groups:
+        group['lr'] = lr
+
+
+def load_checkpoint(args, model, optimizer, fix_loaded=False):
+    """reference utils.py:34-86: resume ``model`` (and, when nothing was skipped, ``optimizer``) from
+    ``checkpoint/<resume_exp>/checkpoint.pth`` (``model_best.pth`` in val / test mode); sets ``args.start_epoch``."""
+    if args.resume_exp is None:
+        args.resume_exp = args.exp_name
+    fname = 'model_best.pth' if args.mode in ['val', 'test'] else 'checkpoint.pth'
+    load_name = os.path.join('checkpoint', args.resume_exp, fname)
+    print("loading checkpoint %s" % load_name)
+    checkpoint = _read(load_name, getattr(model, 'device', None))
+    args.start_epoch = checkpoint['epoch'] if args.resume_exp == args.exp_name else 0
+    own = model.state_dict()
+    picked, partial = _matching_entries(own, checkpoint['state_dict'], report_missing_keys=True)
+    own.update(picked)
+    model.load_state_dict(own)
+    if not partial and optimizer is not None and args.resume_exp is not None and args.mode != 'test':
+        optimizer.load_state_dict(checkpoint['optimizer'])
+        update_lr(optimizer, args.lr)
+    if fix_loaded:
+        for key, param in model.named_parameters():
+            if key in picked:
+                print(key)
+                param.requires_grad = False
+    print("loaded checkpoint %s" % load_name)
+
+
+def lossy_load_state_dict(net, ckpt_state_dict, opt=None, ckpt_optimizer=None):
+    """reference utils.py:89-107: copy every entry that fits, ignore the rest."""
+    own = net.state_dict()
+    picked, partial = _matching_entries(own, ckpt_state_dict, report_missing_keys=False)
+    own.update(picked)
+    net.load_state_dict(own)
+    if opt is not None and not partial:
+        opt.load_state_dict(ckpt_optimizer)
+
+
+def save_checkpoint(state, is_best, exp_name, filename='checkpoint.pth'):
+    """reference utils.py:110-118."""
+    directory = os.path.join('checkpoint', exp_name)
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, filename)
+    torch.save(state, path)
+    if is_best:
+        shutil.copyfile(path, os.path.join(directory, 'model_best.pth'))

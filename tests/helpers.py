@@ -13,7 +13,7 @@ def make_args(**kw):
              attenuate=False, learnable_per_layer_per_step_inner_loop_learning_rate=False,
              enable_inner_loop_optimizable_bn_params=False, second_order=False, first_order_to_second_order_epoch=-1,
              use_multi_step_loss_optimization=False, multi_step_loss_num_epochs=1, random_seed=12345, cuda=False,
-             num_gpu=0, pretrained_model=None, weight_decay=1e-4)
+             num_gpu=0, pretrained_model=None, weight_decay=1e-4, load_checkpoint=False, exp_name='exp', resume_exp=None)
     d.update(kw)
     return argparse.Namespace(**d)
 

@@ -215,3 +215,86 @@ def test_outer_optimizer_state_interchanges_with_reference_checkpoints():
         assert len(st) == len(msd["state"]) and torch.equal(st[1]["exp_avg"], msd["state"][1]["exp_avg"])
     finally:
         backbone.set_default_ops(saved)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_checkpoint_files_interchange_with_the_reference(tmp_path, monkeypatch):
+    """SURVEY 8f rank 3 (utils.py:34-118, meta_learning_system.py:154-170): a checkpoint written by the REFERENCE's
+    ``save_checkpoint`` resumes this package's system (``--resume``; ``model_best.pth`` in val mode); a checkpoint
+    written here is restored by the REFERENCE's ``load_checkpoint``; ``--pretrained_model`` overlays a backbone file
+    with the reference's lossy matching rules (unknown keys and shape mismatches are skipped)."""
+    import contextlib
+    import io
+    from oracle import reference_shims as rs
+    from oracle.ops_ref import RefOps
+    from meta_interpolation_b200 import backbone, utils as my_utils
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    from helpers import make_args
+
+    over = dict(model="sepconv", loss="1*L1", optimizer="Adam", number_of_training_steps_per_iter=2, metasgd=True)
+    ref, rargs = rs.build_system(batch_size=1, **over)
+    import utils as ref_utils
+    monkeypatch.chdir(tmp_path)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():                       # move every tensor off its init so equality means "loaded"
+        for p in ref.parameters():
+            p.add_(torch.rand(p.shape, generator=g) * 1e-2)
+    ref_state = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    ref_utils.save_checkpoint({"epoch": 3, "arch": rargs, "state_dict": ref.state_dict(), "best_PSNR": 31.5}, False,
+                              "expA")
+    best = {k: v + 1.0 for k, v in ref_state.items()}
+    ref_utils.save_checkpoint({"epoch": 7, "arch": rargs, "state_dict": best, "best_PSNR": 33.0}, True, "expB")
+
+    ops = RefOps()
+    saved = backbone._default_ops
+    backbone.set_default_ops(ops)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            # reference file -> this package, through the constructor's --resume branch
+            a1 = make_args(batch_size=1, load_checkpoint=True, exp_name="expA", **over)
+            mine = SceneAdaptiveInterpolation(a1, ops=ops)
+            assert a1.start_epoch == 3 and a1.resume_exp == "expA"
+            assert list(mine.state_dict()) == list(ref_state)
+            for k, v in mine.state_dict().items():
+                assert torch.equal(v, ref_state[k]), k
+            # val mode reads model_best.pth; resuming another experiment restarts the epoch counter
+            a2 = make_args(batch_size=1, load_checkpoint=True, exp_name="fresh", resume_exp="expB", mode="val", **over)
+            other = SceneAdaptiveInterpolation(a2, ops=ops)
+            assert a2.start_epoch == 0
+            for k, v in other.state_dict().items():
+                assert torch.equal(v, best[k]), k
+
+            # this package -> the reference's own loader
+            with torch.no_grad():
+                for p in mine.parameters():
+                    p.mul_(1.5)
+            my_utils.save_checkpoint({"epoch": 11, "arch": a1, "state_dict": mine.state_dict(), "best_PSNR": 30.0},
+                                     True, "expC")
+            assert sorted(os.listdir("checkpoint/expC")) == ["checkpoint.pth", "model_best.pth"]
+            ref2, rargs2 = rs.build_system(batch_size=1, exp_name="expC", resume_exp=None, mode="train", **over)
+            # (the reference calls torch.load(path) bare; torch >= 2.6 then refuses the pickled Namespace under 'arch',
+            # for its own files too -- give its call the torch default it was written against)
+            plain_load = torch.load
+            monkeypatch.setattr(torch, "load", lambda f, *a, **k: plain_load(f, *a, **dict(k, weights_only=False)))
+            ref_utils._original_load_checkpoint(rargs2, ref2, None)
+            monkeypatch.setattr(torch, "load", plain_load)
+            assert rargs2.start_epoch == 11
+            want = mine.state_dict()
+            for k, v in ref2.state_dict().items():
+                assert torch.equal(v, want[k]), k
+
+            # --pretrained_model: lossy overlay of a backbone file
+            net_state = {k: v + 2.0 for k, v in mine.net.state_dict().items()}
+            first, second = list(net_state)[:2]
+            net_state[first] = torch.zeros(1, 2, 3)                  # wrong shape: skipped
+            net_state["not.a.parameter"] = torch.zeros(4)            # unknown key: ignored
+            torch.save({"state_dict": net_state}, "backbone.pth")
+            a3 = make_args(batch_size=1, pretrained_model="backbone.pth", **over)
+            third = SceneAdaptiveInterpolation(a3, ops=ops)
+            fresh = SceneAdaptiveInterpolation(make_args(batch_size=1, **over), ops=ops)
+            got, init = third.net.state_dict(), fresh.net.state_dict()
+            assert torch.equal(got[first], init[first])
+            assert torch.equal(got[second], net_state[second])
+    finally:
+        backbone.set_default_ops(saved)
