@@ -240,7 +240,7 @@ def test_moment_rule_combinations_graph_path_matches_compat_path(ref_ops, kw):
     that rule is chaotic at practical rates in the reference too); train and validation iterations."""
     from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
     g = torch.Generator().manual_seed(4)
-    frames = [torch.rand(2, 3, 32, 40, generator=g) for _ in range(7)]
+    frames = [torch.rand(1, 3, 32, 40, generator=g) for _ in range(7)]
     res = {}
     for fast in (True, False):
         s = SceneAdaptiveInterpolation(make_args(number_of_evaluation_steps_per_iter=2, fast_path=fast, **kw),

@@ -33,7 +33,7 @@ def _prepare(system, l2f):
         system.optimizer.param_groups[0]["lr"] = 1.0
 
 
-def _worker(rank, world, port, fast, out_dir, l2f=False):
+def _worker(rank, world, port, out_dir, l2f=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -46,15 +46,16 @@ def _worker(rank, world, port, fast, out_dir, l2f=False):
     from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
     ops = RefOps()
     backbone.set_default_ops(ops)
-    args = make_args(batch_size=2, number_of_training_steps_per_iter=1, fast_path=fast, attenuate=l2f)
-    system = SceneAdaptiveInterpolation(args, ops=ops)
-    _prepare(system, l2f)
-    g = torch.Generator().manual_seed(11)
-    frames = [torch.rand(2, 3, 32, 32, generator=g) for _ in range(7)]
-    losses, preds, _ = system.run_train_iter(frames, epoch=0)
-    mine = [i for i, p in enumerate(preds) if torch.is_tensor(p)]
-    torch.save({"flat": system.net.arena.flat.clone(), "tasks": mine, "loss": float(losses["loss"]),
-                "extra": _extra_state(system)}, os.path.join(out_dir, "rank%d.pt" % rank))
+    for fast in (True, False):          # both execution paths in one rendezvous (process start-up dominates)
+        args = make_args(batch_size=2, number_of_training_steps_per_iter=1, fast_path=fast, attenuate=l2f)
+        system = SceneAdaptiveInterpolation(args, ops=ops)
+        _prepare(system, l2f)
+        g = torch.Generator().manual_seed(11)
+        frames = [torch.rand(2, 3, 32, 32, generator=g) for _ in range(7)]
+        losses, preds, _ = system.run_train_iter(frames, epoch=0)
+        mine = [i for i, p in enumerate(preds) if torch.is_tensor(p)]
+        torch.save({"flat": system.net.arena.flat.clone(), "tasks": mine, "loss": float(losses["loss"]),
+                    "extra": _extra_state(system)}, os.path.join(out_dir, "rank%d_fast%d.pt" % (rank, int(fast))))
     dist.destroy_process_group()
 
 
@@ -81,34 +82,36 @@ def _single(fast, l2f=False):
         backbone.set_default_ops(saved)
 
 
-@pytest.mark.parametrize("fast", [True, False])
-def test_two_ranks_equal_one_rank(tmp_path, fast):
+def _load(tmp_path, rank, fast):
+    return torch.load(os.path.join(str(tmp_path), "rank%d_fast%d.pt" % (rank, int(fast))))
+
+
+def test_two_ranks_equal_one_rank(tmp_path):
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, fast, str(tmp_path)), nprocs=2, join=True)
-    r0 = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
-    r1 = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
-    assert r0["tasks"] == [0] and r1["tasks"] == [1]           # each rank adapted its own shard
-    assert torch.equal(r0["flat"], r1["flat"])                   # identical outer step on every rank
-    single, loss = _single(fast)
-    # outer SGD step: theta - lr * mean-gradient; the two summation orders agree to fp32 rounding
-    assert (r0["flat"] - single).abs().max().item() <= 1e-9
-    assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for fast in (True, False):
+        r0, r1 = _load(tmp_path, 0, fast), _load(tmp_path, 1, fast)
+        assert r0["tasks"] == [0] and r1["tasks"] == [1]           # each rank adapted its own shard
+        assert torch.equal(r0["flat"], r1["flat"])                   # identical outer step on every rank
+        single, loss = _single(fast)
+        # outer SGD step: theta - lr * mean-gradient; the two summation orders agree to fp32 rounding
+        assert (r0["flat"] - single).abs().max().item() <= 1e-9, fast
+        assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6, fast
 
 
-@pytest.mark.parametrize("fast", [True, False])
-def test_two_ranks_equal_one_rank_l2f(tmp_path, fast):
+def test_two_ranks_equal_one_rank_l2f(tmp_path):
     """BASELINE configs[3] shape of the problem (L2F sharded over ranks): the attenuator / gamma_mult outer gradients
     are gathered into their flat group BEFORE the all-reduce on the graph path, so two ranks reproduce one."""
     port = _free_port()
-    mp.spawn(_worker, args=(2, port, fast, str(tmp_path), True), nprocs=2, join=True)
-    r0 = torch.load(os.path.join(str(tmp_path), "rank0.pt"))
-    r1 = torch.load(os.path.join(str(tmp_path), "rank1.pt"))
-    assert torch.equal(r0["flat"], r1["flat"])
-    single, loss, extra = _single(fast, True)
-    scale = max(1.0, single.abs().max().item())
-    assert (r0["flat"] - single).abs().max().item() <= 1e-5 * scale
-    assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6
-    for k, v in extra.items():
-        assert torch.equal(r0["extra"][k], r1["extra"][k]), k
-        d = (r0["extra"][k] - v).abs().max().item()
-        assert d <= 1e-4 * max(v.abs().max().item(), 1e-6), (k, d)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), True), nprocs=2, join=True)
+    for fast in (True, False):
+        r0, r1 = _load(tmp_path, 0, fast), _load(tmp_path, 1, fast)
+        assert torch.equal(r0["flat"], r1["flat"])
+        single, loss, extra = _single(fast, True)
+        scale = max(1.0, single.abs().max().item())
+        assert (r0["flat"] - single).abs().max().item() <= 1e-5 * scale, fast
+        assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6, fast
+        for k, v in extra.items():
+            assert torch.equal(r0["extra"][k], r1["extra"][k]), k
+            d = (r0["extra"][k] - v).abs().max().item()
+            assert d <= 1e-4 * max(v.abs().max().item(), 1e-6), (k, d, fast)
