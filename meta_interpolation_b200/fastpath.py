@@ -241,11 +241,9 @@ class FastPath:
         if a.optimizer not in ('SGD', 'Adam', 'Adamax'):
             return False
         if a.optimizer != 'SGD':
-            # moment rules are graph-captured with a fixed LSLR table, and as Meta-SGD + Adamax (the authors'
-            # scripts/run_sepconv.sh operating point); Meta-SGD + Adam fails in the reference for K >= 2 (F11)
+            # moment rules are graph-captured with an LSLR table (fixed or learnable), and as Meta-SGD + Adamax (the
+            # authors' scripts/run_sepconv.sh operating point); Meta-SGD + Adam fails in the reference for K >= 2 (F11)
             if a.attenuate or (a.metasgd and a.optimizer != 'Adamax'):
-                return False
-            if not a.metasgd and a.learnable_per_layer_per_step_inner_loop_learning_rate:
                 return False
         if a.attenuate:
             # L2F (reference :231-272) is graph-captured for the plain fixed-lr LSLR rule; its combinations with
@@ -361,10 +359,16 @@ class FastPath:
             lr, per_element, stride = self.sys.alpha.flat, True, 0
         else:
             lr, per_element, stride = self.sys.lr_table, False, self.sys.lr_table.shape[1]
+        keep = self.learnable_lr
+        if keep:
+            lane.gsteps[step].flat.copy_(w_in)          # w_k, turned into w_k - w_{k+1} below
         ops.inner_update(w_in, lane.gstep.flat, lane.fast.flat,
                          lane.exp_avg.flat if lane.exp_avg is not None else None,
                          lane.exp_avg_sq.flat if lane.exp_avg_sq is not None else None,
                          lr, per_element, stride, 0 if self.metasgd else step, self.seg, self.skip, self.rule, step + 1)
+        if keep:
+            # learnable per-step lr: dL/dlr[t][k] = -<dir_k[t], G[t]> with dir_k = (w_k - w_{k+1}) / lr[t][k]
+            ops.axpby(lane.fast.flat, -1.0, lane.gsteps[step].flat, 1.0)
         for name in net.conv_names:
             if net.is_routed(name + ".weight"):
                 ops.weight_to_dgrad(lane.fast.kernel_view(name + ".weight"), out=lane.wt_buffer(name))
@@ -484,14 +488,17 @@ class FastPath:
                 ops.fill(lane.dots, 0.0)
                 ops.segment_dot(lane.gsteps[j].flat, G, self.seg, lane.dots)
                 # only routed tensors are adapted; un-routed rows keep a zero gradient
-                lane.acc_lr[:, j].add_(lane.dots * self.routed_mask, alpha=-scale)
+                if self.rule == RULE_SGD:        # gsteps[j] = g_j
+                    lane.acc_lr[:, j].add_(lane.dots * self.routed_mask, alpha=-scale)
+                else:                            # gsteps[j] = w_j - w_{j+1} = lr[:, j] * dir_j
+                    lane.acc_lr[:, j].add_(lane.dots * self.routed_mask / self.sys.lr_table[:, j], alpha=-scale)
 
     def adapt_and_query(self, lane, frames, task, num_steps, epoch, training, scale, msl, msl_w):
         """Inner loop + query for one task on ``lane``.  Returns (task_loss tensor[1], pred [1,3,H,W])."""
         h, w = frames[0].shape[2], frames[0].shape[3]
         sysm = self.sys
         support_idxs = sysm.support_idxs
-        if self.learnable_lr and training:
+        if self.learnable_lr:      # (also when evaluating: support graphs are shared between training and evaluation)
             while len(lane.gsteps) < num_steps:
                 lane.gsteps.append(Arena(self.net.layout, self.ops.device))
         extras = training and (self.metasgd or self.learnable_lr)

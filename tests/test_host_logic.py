@@ -232,20 +232,30 @@ def test_moment_rules_graph_path_matches_compat_path_on_outer_gradients(ref_ops,
 @pytest.mark.parametrize("kw", [
     dict(optimizer="Adamax", metasgd=True, use_multi_step_loss_optimization=True, multi_step_loss_num_epochs=5,
          inner_lr=1e-4, number_of_training_steps_per_iter=2),
-    dict(optimizer="Adamax", inner_lr=1e-7, number_of_training_steps_per_iter=3)],
-    ids=["metasgd_adamax_msl", "lslr_adamax_k3"])
+    dict(optimizer="Adamax", inner_lr=1e-7, number_of_training_steps_per_iter=3),
+    dict(optimizer="Adam", inner_lr=1e-5, number_of_training_steps_per_iter=2,
+         learnable_per_layer_per_step_inner_loop_learning_rate=True, eval_first=True),
+    dict(optimizer="SGD", inner_lr=1e-5, number_of_training_steps_per_iter=2,
+         learnable_per_layer_per_step_inner_loop_learning_rate=True, eval_first=True)],
+    ids=["metasgd_adamax_msl", "lslr_adamax_k3", "learnable_lr_adam", "learnable_lr_sgd_eval_first"])
 def test_moment_rule_combinations_graph_path_matches_compat_path(ref_ops, kw):
     """Meta-SGD-Adamax under the multi-step loss (alpha gradient per step from (theta - w_k)/alpha) and the
     LSLR-Adamax quirk over three steps (exp_avg persists, exp_inf does not; inner_loop_optimizers.py:229-236; tiny lr:
-    that rule is chaotic at practical rates in the reference too); train and validation iterations."""
+    that rule is chaotic at practical rates in the reference too); learnable per-step rates under Adam (lr gradient
+    from the stored weight deltas); train and validation iterations, validation FIRST in the learnable-lr cases (a
+    ``--mode val`` run evaluates before any training iteration has sized the per-step buffers)."""
     from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
     g = torch.Generator().manual_seed(4)
     frames = [torch.rand(1, 3, 32, 40, generator=g) for _ in range(7)]
     res = {}
+    kw = dict(kw)
+    eval_first = kw.pop("eval_first", False)
     for fast in (True, False):
         s = SceneAdaptiveInterpolation(make_args(number_of_evaluation_steps_per_iter=2, fast_path=fast, **kw),
                                        ops=ref_ops)
         assert s.fast_path_supported() == fast
+        if eval_first:
+            s.run_validation_iter(frames)
         opt, seen = s.optimizer, {}
         orig = opt.step
 

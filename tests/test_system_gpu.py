@@ -198,3 +198,38 @@ def test_full_size_sepconv_graph_path_equals_compat_path(cuda_ops):
     assert abs(res[True][0] - res[False][0]) <= LOSS_TOL
     assert (res[True][1] - res[False][1]).abs().max().item() <= PRED_TOL
     assert abs(res[True][2] - res[False][2]) < 0.01
+
+
+def test_learnable_lr_adam_graph_path_vs_compat_path(cuda_ops):
+    """Learnable per-step LSLR rates under the Adam inner rule: validation first (support graphs are shared between
+    evaluation and training), then a meta-iteration; the graph path's lr gradient -<w_k - w_{k+1}, G> / lr is held
+    against autograd through the compat path.  TF32 on both sides: 5 % of the largest entry."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    g = torch.Generator().manual_seed(21)
+    frames = [torch.rand(2, 3, 48, 64, generator=g).cuda() for _ in range(7)]
+    res = {}
+    for fast in (True, False):
+        s = SceneAdaptiveInterpolation(make_args(cuda=True, optimizer="Adam", number_of_training_steps_per_iter=2,
+                                                 number_of_evaluation_steps_per_iter=2, fast_path=fast,
+                                                 learnable_per_layer_per_step_inner_loop_learning_rate=True),
+                                       ops=cuda_ops)
+        assert s.fast_path_supported() == fast
+        lv, _, _ = s.run_validation_iter(frames)
+        opt, seen = s.optimizer, {}
+        orig = opt.step
+
+        def step(opt=opt, seen=seen, orig=orig):
+            opt.gather_grads()
+            for gr in opt.flat_groups:
+                seen[gr.name] = gr.grad.detach().clone()
+            orig()
+        opt.step = step
+        lt, preds, _ = s.run_train_iter(frames, epoch=0)
+        res[fast] = (float(lv["loss"].detach()), float(lt["loss"].detach()), torch.cat(preds).detach().clone(), seen)
+    a, b = res[True], res[False]
+    assert abs(a[0] - b[0]) <= LOSS_TOL and abs(a[1] - b[1]) <= LOSS_TOL
+    assert (a[2] - b[2]).abs().max().item() <= PRED_TOL
+    assert len(b[3]) == 2
+    for k, gb in b[3].items():
+        assert gb.abs().max().item() > 0, k
+        assert (a[3][k] - gb).abs().max().item() <= 5e-2 * gb.abs().max().item(), k
