@@ -291,6 +291,18 @@ int mi_segment_dot(const float* a, const float* b, const int32_t* seg, float* ou
 int mi_segment_scale(const float* x, const float* scale, const int32_t* seg, const float* mask, float* y, float alpha,
                      int accumulate, size_t count, mi_stream_t stream);
 
+/* ------------------------------------------------------------------ input staging
+ * data/vimeo_septuplet.py:50-78 in one launch: per-task random crop (:56-61), temporal flip (:64-66), BGR->RGB (:69),
+ * HWC uint8 -> CHW float (/255 unless voxelflow, :72-75), per-channel (x - mean) / std (:77-78).
+ *   src      : device [tasks][frames][src_h][src_w][3] uint8, as cv2.imread decodes (bgr=1) or RGB (bgr=0)
+ *   dst      : device [frames][tasks][3][h][w] float -- frame f of the meta-batch is dst[f] ([tasks,3,h,w], NCHW)
+ *   y0, x0   : device int32 [tasks] crop origins (y0+h <= src_h, x0+w <= src_w: the caller checks, it drew them)
+ *   reversed : device uint8 [tasks], non-zero = frames in reverse temporal order
+ *   mean3, std3 : HOST float[3] or both NULL (no normalisation) */
+int mi_septuplet_prepare(const uint8_t* src, float* dst, const int32_t* y0, const int32_t* x0,
+                         const uint8_t* reversed, int tasks, int frames, int src_h, int src_w, int h, int w,
+                         int bgr, int div255, const float* mean3, const float* std3, mi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

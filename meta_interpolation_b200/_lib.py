@@ -80,6 +80,8 @@ SIGNATURES = {
     "mi_addcmul": (_i, [_f, _fl, _f, _f, _sz, _st]),
     "mi_segment_dot": (_i, [_f, _f, _f, _f, _sz, _st]),
     "mi_segment_scale": (_i, [_f, _f, _f, _f, _f, _fl, _i, _sz, _st]),
+    # (src, dst, y0, x0, reversed: device addresses; mean3 / std3: HOST float[3] or NULL)
+    "mi_septuplet_prepare": (_i, [_f, _f, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, C.c_void_p, C.c_void_p, _st]),
 }
 
 

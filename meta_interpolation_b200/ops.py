@@ -516,6 +516,25 @@ class CudaOps:
         _lib.check(self.lib.mi_psnr_accumulate(pred.data_ptr(), target.data_ptr(), sq_out.data_ptr(), pred.numel(),
                                                self._stream()), "mi_psnr_accumulate")
 
+    def septuplet_prepare(self, src, y0, x0, reversed_, h, w, bgr=True, div255=True, mean=None, std=None):
+        """Decoded uint8 frames [tasks,frames,H,W,3] -> float [frames,tasks,3,h,w]: crop, temporal flip, channel order,
+        /255 and normalisation of data/vimeo_septuplet.py:50-78 in one launch."""
+        import ctypes as C
+        assert src.dtype == torch.uint8 and src.is_cuda and src.is_contiguous() and src.dim() == 5 and src.shape[4] == 3
+        tasks, frames, sh, sw, _ = src.shape
+        assert y0.dtype == torch.int32 and x0.dtype == torch.int32 and reversed_.dtype == torch.uint8
+        assert y0.numel() == tasks and x0.numel() == tasks and reversed_.numel() == tasks
+        assert (mean is None) == (std is None)
+        out = torch.empty(frames, tasks, 3, h, w, device=src.device, dtype=torch.float32)
+        m = (C.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
+        s = (C.c_float * 3)(*[float(v) for v in std]) if std is not None else None
+        _lib.check(self.lib.mi_septuplet_prepare(src.data_ptr(), out.data_ptr(), y0.data_ptr(), x0.data_ptr(),
+                                                 reversed_.data_ptr(), tasks, frames, sh, sw, int(h), int(w), int(bgr),
+                                                 int(div255), C.cast(m, C.c_void_p) if m is not None else None,
+                                                 C.cast(s, C.c_void_p) if s is not None else None, self._stream()),
+                   "mi_septuplet_prepare")
+        return out
+
     def inner_update(self, w_in, g, w_out, exp_avg, exp_avg_sq, lr, lr_per_element, lr_stride, num_step, seg, skip,
                      rule, step_count):
         _lib.check(self.lib.mi_inner_update(w_in.data_ptr(), g.data_ptr(), w_out.data_ptr(), self._p(exp_avg),

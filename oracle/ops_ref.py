@@ -510,6 +510,27 @@ class RefOps:
         d = (q(pred) - q(target)).div(255)
         sq_out.add_(d.pow(2).double().sum())
 
+    def septuplet_prepare(self, src, y0, x0, reversed_, h, w, bgr=True, div255=True, mean=None, std=None):
+        """data/vimeo_septuplet.py:50-78 frame by frame: crop (:59-61), temporal flip (:64-66), BGR->RGB (:69),
+        HWC->CHW float (/255 unless voxelflow, :72-75), Normalize = (x - mean) / std (:77-78)."""
+        tasks, frames = src.shape[:2]
+        out = torch.empty(frames, tasks, 3, h, w, dtype=torch.float32)
+        for b in range(tasks):
+            order = list(range(frames))[::-1] if int(reversed_[b]) else list(range(frames))
+            for f, fs in enumerate(order):
+                im = src[b, fs, int(y0[b]):int(y0[b]) + h, int(x0[b]):int(x0[b]) + w, :]
+                if bgr:
+                    im = im[:, :, [2, 1, 0]]
+                t = im.permute(2, 0, 1).contiguous().float()
+                if div255:
+                    t = t / 255
+                if mean is not None:
+                    m = torch.tensor(mean, dtype=torch.float32).view(3, 1, 1)
+                    s = torch.tensor(std, dtype=torch.float32).view(3, 1, 1)
+                    t = (t - m) / s
+                out[f, b] = t
+        return out
+
     def inner_update(self, w_in, g, w_out, exp_avg, exp_avg_sq, lr, lr_per_element, lr_stride, num_step, seg, skip,
                      rule, step_count):
         n = w_in.numel()
