@@ -253,7 +253,8 @@ class FastPath:
                 return False
             if len(system.get_inner_loop_parameter_dict(system.net.named_parameters())) != len(system.net.param_names):
                 return False
-        if not all(t.split('*')[1] in LOSS_KIND for t in a.loss.split('+')):
+        kinds = [t.split('*')[1] for t in a.loss.split('+')]
+        if not all(k in LOSS_KIND or (k == 'Super' and a.model == 'superslomo') for k in kinds):
             return False
         if a.metasgd and a.optimizer == 'SGD' and any(not system.net.is_routed(n) for n in system.net.param_names):
             return False   # the reference itself fails here for K>=2
@@ -283,7 +284,11 @@ class FastPath:
         self.skip = torch.tensor([0 if self.net.is_routed(n) else 1 for n in self.net.param_names], dtype=torch.uint8,
                                  device=dev)
         self.numel = torch.tensor([float(lay.logical_numel(n)) for n in self.net.param_names], device=dev)
-        self.loss_terms = [(LOSS_KIND[t.split('*')[1]], float(t.split('*')[0])) for t in a.loss.split('+')]
+        terms = [(t.split('*')[1], float(t.split('*')[0])) for t in a.loss.split('+')]
+        self.loss_terms = [(LOSS_KIND[k], w) for k, w in terms if k in LOSS_KIND]
+        # the `Super` loss (loss.py:246-274) differentiates through SuperSloMo's auxiliary outputs on the tape
+        self.super_weight = sum(w for k, w in terms if k == 'Super') if any(k == 'Super' for k, _ in terms) else None
+        self.super_terms = system.criterion.super_terms
         self.meta_wt = {}
         # measured on B200, SepConv 256x448 K=5: 1 lane 22.7, 2 lanes 27.9, 3 lanes 29.2, 4 lanes 30.1 tasks/s
         lanes = os.environ.get('MI_B200_TASK_STREAMS', getattr(a, 'task_streams', 4))
@@ -324,8 +329,19 @@ class FastPath:
 
         return provider
 
+    def _seed_loss(self, prog, tape, out, n_pairs, backward=True):
+        """Loss value of the pass into ``prog.loss`` and, when ``backward``, the gradient seeds on the tape."""
+        grad = self._loss(prog, out.data, n_pairs)
+        if backward and grad is not None:
+            out.grad = grad
+        if self.super_weight is not None:
+            self.super_terms.seed(tape, out, self.net.aux_vars, prog.tgt, prog.f0, prog.f1,
+                                  self.super_weight * n_pairs, prog.loss, backward)
+
     def _loss(self, prog, pred, n_pairs):
         self.ops.fill(prog.loss, 0.0)
+        if not self.loss_terms:
+            return None
         grad = torch.empty_like(pred)
         first = True
         for kind, weight in self.loss_terms:
@@ -344,7 +360,7 @@ class FastPath:
             sink = _Sink(lane, 'inner', step=step_slot)
             tape = Tape(self.ops, self._provider(lane, src), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
-            out.grad = self._loss(prog, out.data, prog.f0.shape[0])
+            self._seed_loss(prog, tape, out, prog.f0.shape[0])
             tape.backward()
             if self.rule != RULE_SGD:
                 self._moment_update(lane, src, step_slot)
@@ -381,7 +397,7 @@ class FastPath:
             sink = _Sink(lane, 'store')
             tape = Tape(self.ops, self._provider(lane, 'meta'), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
-            out.grad = self._loss(prog, out.data, prog.f0.shape[0])
+            self._seed_loss(prog, tape, out, prog.f0.shape[0])
             tape.backward()
         return body
 
@@ -426,9 +442,8 @@ class FastPath:
             tape = Tape(self.ops, self._provider(lane, src), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             prog.pred = out.data
-            g = self._loss(prog, out.data, 1)
+            self._seed_loss(prog, tape, out, 1, backward)
             if backward:
-                out.grad = g
                 tape.backward()
         return body
 
@@ -570,7 +585,7 @@ class FastPath:
         losses = {'loss': stacked.mean()}
         total = stacked.mean().detach().cpu().numpy()
         losses['total'] = total
-        if len(self.loss_terms) == 1:
+        if len(loss_name_terms) == 1:
             losses[loss_name_terms[0]] = total
         for idx, item in enumerate(msl_w):
             losses['loss_importance_vector_{}'.format(idx)] = item.detach().cpu().numpy()

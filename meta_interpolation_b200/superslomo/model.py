@@ -115,6 +115,8 @@ class MetaSuperSloMo(MetaBackbone):
         out = t.blend(g0f, g1f, v0, None, 1 - tt, tt, 0.0, ops.BLEND_RATIO_COMPLEMENT)
         self._aux = dict(canvas=canvas, f01=f01.data, f10=f10.data, g0=g0.data, g1=g1.data,
                          window=(top, left, height, width))
+        # the same tensors as tape Vars: the `Super` loss (loss.py:258-274) differentiates through them
+        self.aux_vars = dict(f01=f01, f10=f10, g0=g0, g1=g1, i0=i0, i1=i1, window=(top, left, height, width))
         return t.to_nchw(out, top, left, height, width)
 
     # ------------------------------------------------------------------ reference plugin API

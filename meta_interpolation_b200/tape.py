@@ -451,6 +451,49 @@ class Tape:
         self.nodes.append(bwd)
         return y
 
+    def to_nchw_shared(self, x, y0, x0, h, w):
+        """``to_nchw`` for a Var that has other consumers too (the auxiliary outputs of SuperSloMo that feed the
+        ``Super`` loss, superslomo/model.py:631-643): the cropped gradient is ADDED to whatever else reaches ``x``."""
+        ops = self.ops
+        x.consumers += 1
+        y = Var(ops.nhwc_window_to_nchw(x.data, y0, x0, h, w), requires_grad=x.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            n, hh, ww, c = x.data.shape
+            full = ops.zeros_act(n, hh, ww, c)
+            ops.nchw_to_nhwc_window(g.contiguous(), full, y0, x0)
+            self._own_or_add(x, full)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
+    def from_nchw(self, x):
+        """NCHW image Var -> NHWC activation Var (entry of a feature extractor applied to a prediction)."""
+        ops = self.ops
+        x.consumers += 1
+        n, c, h, w = x.data.shape
+        data = ops.empty_act(n, h, w, c)
+        ops.nchw_to_nhwc_window(x.data.contiguous(), data, 0, 0)
+        y = Var(data, requires_grad=x.requires_grad)
+
+        def bwd():
+            g = y.grad
+            if g is None or not x.requires_grad:
+                return
+            gn = ops.nhwc_window_to_nchw(g, 0, 0, h, w)
+            if x.grad is None:
+                x.grad = gn
+            else:
+                ops.axpby(gn, 1.0, x.grad, 1.0)
+            y.grad = None
+
+        self.nodes.append(bwd)
+        return y
+
     def concat(self, buf, parts, consts=()):
         """Var over the concat buffer ``buf``: ``parts`` = [(Var, c0, c1)] were produced in place (``out=`` slices),
         ``consts`` = [(tensor, c0, c1)] are constants copied in now."""

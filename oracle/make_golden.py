@@ -45,6 +45,10 @@ CASES = {
                                        number_of_training_steps_per_iter=2), 64, 2),
     "superslomo_lslr_sgd_k1_ragged": (dict(model="superslomo", loss="1*L1", optimizer="SGD",
                                            number_of_training_steps_per_iter=1), (72, 80), 1),
+    # the loss of the authors' scripts/run_superslomo.sh (loss.py:246-274); the ImageNet VGG16 is not available
+    # offline, so torchvision's vgg16() is handed a seeded random conv4_3 (oracle/super_loss.py) on both sides
+    "superslomo_super_sgd_k1": (dict(model="superslomo", loss="1*Super", optimizer="SGD",
+                                     number_of_training_steps_per_iter=1, _vgg_seed=0), 64, 1),
     # configs[4] in miniature: rrin MAML++ (multi-step loss + learnable per-step lr), K=2
     "rrin_msl_learnable_k2": (dict(model="rrin", loss="1*L1", optimizer="SGD", number_of_training_steps_per_iter=2,
                                    learnable_per_layer_per_step_inner_loop_learning_rate=True,
@@ -89,6 +93,21 @@ def run_case(name, over, size, batch):
     from oracle import maml
     over = dict(over)
     gain = over.pop("_weight_gain", None)
+    vgg_seed = over.pop("_vgg_seed", None)
+    vgg_state = None
+    if vgg_seed is not None:
+        from oracle.super_loss import seeded_vgg16_state
+        rs.install()
+        import loss as ref_loss
+        import torchvision.models as tv_models
+        vgg_state = seeded_vgg16_state(vgg_seed)
+        real_vgg16 = tv_models.vgg16
+
+        def seeded_vgg16(pretrained=False, **kw):
+            m = real_vgg16(weights=None)
+            m.load_state_dict(vgg_state, strict=False)
+            return m
+        ref_loss.models.vgg16 = seeded_vgg16
     system, args = rs.build_system(batch_size=batch, **over)
     if gain is not None:
         with torch.no_grad():
@@ -105,7 +124,7 @@ def run_case(name, over, size, batch):
                             outer_lr=args.outer_lr,
                             learnable_lr=args.learnable_per_layer_per_step_inner_loop_learning_rate, loss=args.loss,
                             attenuate=args.attenuate, use_msl=args.use_multi_step_loss_optimization,
-                            msl_epochs=args.multi_step_loss_num_epochs, attenuator_state=att_state)
+                            msl_epochs=args.multi_step_loss_num_epochs, attenuator_state=att_state, vgg_state=vgg_state)
     record = {}
     o_loss, o_preds, o_psnrs, o_grads = ora.run_train_iter(frames, 0, record=record)
 
@@ -152,6 +171,7 @@ def run_case(name, over, size, batch):
         oracle_vs_reference_post_step_maxabs=pin,
         attenuator_state=att_state,
         weight_gain=gain,
+        vgg_seed=vgg_seed,
     )
     os.makedirs(GOLDEN, exist_ok=True)
     path = os.path.join(GOLDEN, name + ".pt")

@@ -32,8 +32,9 @@ def msl_weights(num_steps, epoch, msl_epochs):
     return torch.Tensor(w)
 
 
-def criterion(loss_spec, out, target):
-    """loss.py:325-350 for the L1/MSE terms: {'L1': w*l, ..., 'total': sum}."""
+def criterion(loss_spec, out, target, extras=None):
+    """loss.py:325-350 for the L1/MSE/Super terms: {'L1': w*l, ..., 'total': sum}.  ``extras`` (Super only) =
+    (aux dict of the superslomo forward, I0, I1, vgg16 conv4_3 state)."""
     losses = {}
     total = 0
     for term in loss_spec.split("+"):
@@ -42,6 +43,10 @@ def criterion(loss_spec, out, target):
             l = (out - target).abs().mean()
         elif kind == "MSE":
             l = ((out - target) ** 2).mean()
+        elif kind == "Super":
+            from .super_loss import super_loss
+            aux, i0, i1, vgg_state = extras
+            l = super_loss(out, target, aux, i0, i1, vgg_state)
         else:
             raise NotImplementedError(kind)
         losses[kind] = float(weight) * l
@@ -66,8 +71,9 @@ class OracleSystem:
 
     def __init__(self, model, params, *, optimizer="SGD", metasgd=False, num_steps=1, inner_lr=1e-5,
                  outer_lr=1e-5, learnable_lr=False, loss="1*L1", attenuate=False, use_msl=False,
-                 msl_epochs=1, attenuator_state=None):
+                 msl_epochs=1, attenuator_state=None, vgg_state=None):
         self.model = model
+        self.vgg_state = vgg_state      # torchvision vgg16 conv4_3 weights for the Super loss
         self.backbone = bb.BACKBONES[model]
         self.params = OrderedDict((k, nn.Parameter(v.detach().clone())) for k, v in params.items())
         self.optimizer_name = optimizer
@@ -110,6 +116,10 @@ class OracleSystem:
 
     # ------------------------------------------------------------------ pieces
     def net_forward(self, f0, f1, target, fast):
+        if "Super" in self.loss_spec:        # meta_learning_system.py:499-501: the plugin's extra outputs feed the loss
+            from .backbones_flow import superslomo_forward
+            out, aux = superslomo_forward(f0, f1, fast, self.params, full=True)
+            return criterion(self.loss_spec, out, target, (aux, f0, f1, self.vgg_state)), out
         out = self.backbone["forward"](f0, f1, fast, self.params)
         return criterion(self.loss_spec, out, target), out
 

@@ -343,3 +343,41 @@ def test_outer_optimizer_state_dict_round_trip(ref_ops, opt):
     b.run_train_iter(batches[1], epoch=0)
     for (k, x), (_, y) in zip(a.state_dict().items(), b.state_dict().items()):
         assert torch.equal(x, y), k
+
+
+def test_super_loss_system_against_reference_golden(ref_ops):
+    """`--loss 1*Super` (loss.py:246-274, scripts/run_superslomo.sh): one meta-iteration of the graph path against the
+    golden generated by the unmodified reference with a seeded random VGG16 conv4_3 on both sides (the ImageNet
+    weights are not available offline); loss, predictions, PSNR and the post-step parameters."""
+    from oracle.super_loss import seeded_vgg16_state
+    fx = load_golden("superslomo_super_sgd_k1")
+    system = system_from_fixture(fx, ref_ops, fast_path=True, vgg16_weights=seeded_vgg16_state(fx["vgg_seed"]))
+    assert system.fast_path_supported()
+    grads, orig = {}, system.optimizer.step
+
+    def step():
+        for k in fx["grad_digest"]:
+            grads[k] = system.net_grad.reference_view(k).detach().clone()
+        orig()
+    system.optimizer.step = step
+    losses, preds, metrics = system.run_train_iter(list(fx["frames"]), epoch=0, do_evaluation=True)
+    assert abs(float(losses["loss"]) - fx["loss"]) <= 2e-6 * fx["loss"]
+    assert float(losses["Super"]) == float(losses["total"])
+    assert len(grads) == 92                                   # every SuperSloMo tensor receives a meta-gradient
+    for k, (d, head) in fx["grad_digest"].items():            # the reference's own outer gradients
+        mine = digest(grads[k])[0]
+        # (sum, sum|.|, sum of squares): fp32 summation-order noise, measured against the absolute sum
+        assert abs(float(mine[0] - d[0])) <= 3e-4 * float(d[1]) and abs(float(mine[1] - d[1])) <= 3e-4 * float(d[1]), \
+            (k, mine, d)
+        assert abs(float(mine[2] - d[2])) <= 1e-3 * float(d[2]), (k, mine, d)
+    assert (torch.cat(preds) - fx["preds"]).abs().max().item() <= 2e-6
+    assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+    own = dict(system.net.named_parameters())
+    for k, (d, head) in fx["post_digest"].items():
+        assert torch.allclose(digest(own[k])[0], d, rtol=1e-5, atol=1e-8), k
+    # validation (forward-only query) reports the same loss the training query of an identical system would
+    lv, _, _ = system.run_validation_iter(list(fx["frames"]))
+    assert torch.isfinite(lv["loss"]).item()
+    compat = system_from_fixture(fx, ref_ops, fast_path=False, vgg16_weights=seeded_vgg16_state(fx["vgg_seed"]))
+    with pytest.raises(NotImplementedError):
+        compat.run_train_iter(list(fx["frames"]), epoch=0)

@@ -298,3 +298,39 @@ def test_checkpoint_files_interchange_with_the_reference(tmp_path, monkeypatch):
             assert torch.equal(got[second], net_state[second])
     finally:
         backbone.set_default_ops(saved)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
+def test_super_loss_equals_live_reference():
+    """oracle/super_loss.py against the reference's SuperSloMoLoss (loss.py:246-274) on the auxiliary outputs of the
+    SuperSloMo oracle, value and gradient; torchvision's vgg16() is handed the same seeded random weights on the
+    reference side (the ImageNet weights cannot be downloaded here)."""
+    from oracle import reference_shims as rs, super_loss as sl, backbones_flow as bf
+    rs.install()
+    import loss as ref_loss
+    import torchvision.models as tv_models
+    state = sl.seeded_vgg16_state(0)
+    real = tv_models.vgg16
+
+    def seeded(pretrained=False, **kw):
+        m = real(weights=None)
+        m.load_state_dict(state, strict=False)
+        return m
+    saved = ref_loss.models.vgg16
+    ref_loss.models.vgg16 = seeded
+    try:
+        crit = ref_loss.SuperSloMoLoss()
+    finally:
+        ref_loss.models.vgg16 = saved
+    params = {k: v.clone().requires_grad_(True) for k, v in bb.seeded_params("superslomo", 12345).items()}
+    g = torch.Generator().manual_seed(1)
+    i0, i1, hr = (torch.rand(2, 3, 64, 64, generator=g) - 0.4 for _ in range(3))
+    out, aux = bf.superslomo_forward(i0, i1, params, params, full=True)
+    a = crit(out, hr, I0=i0, I1=i1, **aux)
+    b = sl.super_loss(out, hr, aux, i0, i1, state)
+    assert abs(float(a) - float(b)) <= 1e-6 * abs(float(a))
+    ga = torch.autograd.grad(a, list(params.values()), retain_graph=True)
+    gb = torch.autograd.grad(b, list(params.values()))
+    for k, x, y in zip(params, ga, gb):
+        assert (x - y).abs().max().item() <= 1e-6 * max(1.0, x.abs().max().item()), k

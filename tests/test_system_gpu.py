@@ -233,3 +233,23 @@ def test_learnable_lr_adam_graph_path_vs_compat_path(cuda_ops):
     for k, gb in b[3].items():
         assert gb.abs().max().item() > 0, k
         assert (a[3][k] - gb).abs().max().item() <= 5e-2 * gb.abs().max().item(), k
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MI_B200_UNVERIFIED_GPU_TESTS") != "1",
+                    reason="added after the round's GPU budget was spent: the Super-loss path is verified on the CPU "
+                           "against the reference (tests/test_host_logic.py) and uses GPU-tested kernels only, but this "
+                           "test itself has not run on a B200 yet; set MI_B200_UNVERIFIED_GPU_TESTS=1 to run it")
+def test_super_loss_train_iter_against_reference_golden(cuda_ops):
+    from oracle.super_loss import seeded_vgg16_state
+    fx = load_golden("superslomo_super_sgd_k1")
+    system = system_from_fixture(fx, cuda_ops, fast_path=True, cuda_graphs=True,
+                                 vgg16_weights=seeded_vgg16_state(fx["vgg_seed"]))
+    frames = [f.cuda() for f in fx["frames"]]
+    for _ in range(2):      # eager, then captured
+        fresh = system_from_fixture(fx, cuda_ops, fast_path=True, cuda_graphs=True,
+                                    vgg16_weights=seeded_vgg16_state(fx["vgg_seed"]))
+        losses, preds, metrics = fresh.run_train_iter(frames, epoch=0, do_evaluation=True)
+        assert abs(float(losses["loss"]) - fx["loss"]) <= 5e-3 * fx["loss"]       # TF32 VGG16 + loss of O(100)
+        assert (torch.cat(preds).cpu() - fx["preds"]).abs().max().item() <= PRED_TOL
+        assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+    del system
