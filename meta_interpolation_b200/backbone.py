@@ -105,50 +105,60 @@ class StoreSink:
             self.grads[bn] = gb
 
 
+def build_tape(net, frame0, frame1, names, tensors):
+    """Tape forward of ``net`` with the given (possibly substituted) parameter tensors; returns (tape, output Var)."""
+    ops = net.ops
+    table = dict(zip(names, tensors))
+    cache = {}
+
+    def provider(name):
+        p = cache.get(name)
+        if p is None:
+            w = kernel_weight_view(ops, table[name + ".weight"].detach())
+            b = table.get(name + ".bias")
+            p = ConvParam(name, w, None if b is None else b.detach().contiguous())
+            cache[name] = p
+        return p
+
+    def vectors(name):
+        slot = net.bn_slot(name)
+        return (table[name + ".weight"].detach(), table[name + ".bias"].detach(), slot.running_mean,
+                slot.running_var, slot.eps)
+
+    tape = Tape(ops, provider, sink=None, vectors=vectors)
+    out = net.build_graph(tape, frame0.detach().contiguous(), frame1.detach().contiguous())
+    return tape, out
+
+
+def collect_grads(net, tape, names, needs):
+    """Tape backward with a StoreSink; gradients in the reference's OIHW form for the tensors autograd asks for."""
+    wanted = {n for n, need in zip(names, needs) if need}
+    sink = StoreSink(net.ops, wanted, vec_like=lambda name: net.bn_slot(name).weight.detach())
+    tape.sink = sink
+    tape.backward()
+    grads = []
+    for n, need in zip(names, needs):
+        g = sink.grads.get(n) if need else None
+        if g is not None and g.dim() == 4:
+            g = g.permute(0, 3, 1, 2)
+        grads.append(g)
+    return grads
+
+
 class _BackboneFunction(torch.autograd.Function):
     """forward: tape forward; backward: tape backward with a StoreSink."""
 
     @staticmethod
     def forward(ctx, net, frame0, frame1, names, *tensors):
-        ops = net.ops
-        table = dict(zip(names, tensors))
-        cache = {}
-
-        def provider(name):
-            p = cache.get(name)
-            if p is None:
-                w = kernel_weight_view(ops, table[name + ".weight"].detach())
-                b = table.get(name + ".bias")
-                p = ConvParam(name, w, None if b is None else b.detach().contiguous())
-                cache[name] = p
-            return p
-
-        def vectors(name):
-            slot = net.bn_slot(name)
-            return (table[name + ".weight"].detach(), table[name + ".bias"].detach(), slot.running_mean,
-                    slot.running_var, slot.eps)
-
-        tape = Tape(ops, provider, sink=None, vectors=vectors)
-        out = net.build_graph(tape, frame0.detach().contiguous(), frame1.detach().contiguous())
+        tape, out = build_tape(net, frame0, frame1, names, tensors)
         ctx.tape, ctx.out_var, ctx.names, ctx.net = tape, out, names, net
         ctx.shapes = [tuple(t.shape) for t in tensors]
         return out.data.clone() if net.clone_output else out.data
 
     @staticmethod
     def backward(ctx, grad_out):
-        net, tape = ctx.net, ctx.tape
-        needs = ctx.needs_input_grad[4:]
-        wanted = {n for n, need in zip(ctx.names, needs) if need}
-        sink = StoreSink(net.ops, wanted, vec_like=lambda name: net.bn_slot(name).weight.detach())
-        tape.sink = sink
         ctx.out_var.grad = grad_out.contiguous()
-        tape.backward()
-        grads = []
-        for n, need in zip(ctx.names, needs):
-            g = sink.grads.get(n) if need else None
-            if g is not None and g.dim() == 4:
-                g = g.permute(0, 3, 1, 2)
-            grads.append(g)
+        grads = collect_grads(ctx.net, ctx.tape, ctx.names, ctx.needs_input_grad[4:])
         ctx.tape = ctx.out_var = None
         return (None, None, None, None) + tuple(grads)
 
@@ -248,7 +258,8 @@ class MetaBackbone(nn.Module):
         return ConvParam(name, w, b)
 
     # -- reference plugin API ---------------------------------------------------------------------
-    def forward(self, frame0, frame1, params=None, **kwargs):
+    def resolve_params(self, params=None):
+        """(names, tensors) the forward pass reads: ``params`` entries where the reference routes them, else own."""
         own = dict(self.named_parameters())
         names, tensors = [], []
         for n in self.param_names:
@@ -257,7 +268,11 @@ class MetaBackbone(nn.Module):
                 t = params[n]
             names.append(n)
             tensors.append(t)
-        return _BackboneFunction.apply(self, frame0, frame1, tuple(names), *tensors)
+        return tuple(names), tensors
+
+    def forward(self, frame0, frame1, params=None, **kwargs):
+        names, tensors = self.resolve_params(params)
+        return _BackboneFunction.apply(self, frame0, frame1, names, *tensors)
 
     def zero_grad(self, params=None, set_to_none=True):
         # reference sepconv/model.py:352-367 (host-syncing prints dropped; semantics: clear .grad)

@@ -3,8 +3,8 @@
 ``Loss(args)`` parses ``'w*TYPE+...'`` and ``forward(sr, hr)`` returns
 ``{'<TYPE>': w*l, ..., 'total': sum}``.  L1 and MSE (the hot-path losses) are one
 fused value+gradient kernel (``mi_loss_fwd_bwd``).  ``Super`` (reference loss.py:246-274,
-the loss of scripts/run_superslomo.sh) is evaluated on the tape of the graph path
-(``SuperTerms``): its reconstruction / warping / smoothness terms are ``mi_loss_fwd_bwd``
+the loss of scripts/run_superslomo.sh) is evaluated on the tape (``SuperTerms``; graph path:
+fastpath.py, compat path: ``forward_with_plugin``): its reconstruction / warping / smoothness terms are ``mi_loss_fwd_bwd``
 launches on crops of the SuperSloMo tape, its perceptual term runs VGG16 conv4_3 through
 the same convolution engines on a side tape.  VGG / GAN / SSIM terms are outside SURVEY
 section 8 and raise NotImplementedError.
@@ -12,7 +12,7 @@ section 8 and raise NotImplementedError.
 import torch
 import torch.nn as nn
 
-from .backbone import default_ops
+from .backbone import build_tape, collect_grads, default_ops
 from .ops import ACT_NONE, ACT_RELU
 from .tape import ConvParam, Tape, Var
 
@@ -129,6 +129,42 @@ class _PixelLoss(torch.autograd.Function):
         return grad * g, None, None, None
 
 
+class _PluginLossFunction(torch.autograd.Function):
+    """Compat-path form of a loss that differentiates through the plugin's auxiliary outputs (``Super``): the tape
+    forward, ALL loss terms and their gradient seeds happen in ``forward``; ``backward`` runs the tape once and scales
+    the parameter gradients by the incoming d/dtotal (first order, like every other path of this package)."""
+
+    @staticmethod
+    def forward(ctx, net, terms, specs, frame0, frame1, target, names, *tensors):
+        ops = net.ops
+        tape, out = build_tape(net, frame0, frame1, names, tensors)
+        f0, f1, tgt = (t.detach().contiguous() for t in (frame0, frame1, target))
+        values = []
+        for kind, weight in specs:
+            value = torch.zeros(1, device=out.data.device, dtype=torch.float32)
+            if kind == 'Super':
+                terms.seed(tape, out, net.aux_vars, tgt, f0, f1, weight, value, True)
+            else:
+                g = torch.empty_like(out.data)
+                ops.loss_fwd_bwd(out.data, tgt, Loss.KINDS[kind], weight, value, g)
+                if out.grad is None:
+                    out.grad = g
+                else:
+                    ops.axpby(g, 1.0, out.grad, 1.0)
+            values.append(value)
+        ctx.tape, ctx.names, ctx.net = tape, names, net
+        per_term = torch.cat(values)
+        pred = out.data.clone() if net.clone_output else out.data
+        ctx.mark_non_differentiable(pred, per_term)
+        return per_term.sum(), pred, per_term
+
+    @staticmethod
+    def backward(ctx, g_total, g_pred, g_terms):
+        grads = collect_grads(ctx.net, ctx.tape, ctx.names, ctx.needs_input_grad[7:])
+        ctx.tape = None
+        return (None,) * 7 + tuple(None if g is None else g * g_total for g in grads)
+
+
 def load_vgg16_state(args):
     """torchvision's vgg16 weights for the Super loss: ``args.vgg16_weights`` (a saved vgg16 state_dict, for machines
     without network access) or torchvision's ImageNet weights exactly as loss.py:249 fetches them."""
@@ -164,8 +200,8 @@ class Loss(nn.modules.loss._Loss):
         loss = 0
         losses = {}
         if self.super_terms is not None:
-            raise NotImplementedError('the Super loss is evaluated on the graph-captured path (fastpath.py); the '
-                                      'autograd compat path does not differentiate the plugin\'s auxiliary outputs')
+            raise NotImplementedError('the Super loss differentiates through the plugin\'s auxiliary outputs: use '
+                                      'forward_with_plugin (net_forward does) instead of forward(sr, hr)')
         for l in self.loss:
             _loss = _PixelLoss.apply(sr, hr, self.KINDS[l['type']], ops)
             effective = l['weight'] * _loss
@@ -173,3 +209,14 @@ class Loss(nn.modules.loss._Loss):
             loss = loss + effective
         losses['total'] = loss
         return losses
+
+    def forward_with_plugin(self, net, frame0, frame1, target, params=None):
+        """Plugin forward + every loss term in one differentiable step (reference meta_learning_system.py:496-501 for
+        superslomo: ``criterion(output[0], target, **output[1])``); returns (losses dict, prediction)."""
+        names, tensors = net.resolve_params(params)
+        specs = tuple((l['type'], l['weight']) for l in self.loss)
+        total, pred, per_term = _PluginLossFunction.apply(net, self.super_terms, specs, frame0, frame1, target, names,
+                                                          *tensors)
+        losses = {l['type']: per_term[i] for i, l in enumerate(self.loss)}
+        losses['total'] = total
+        return losses, pred

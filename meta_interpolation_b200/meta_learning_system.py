@@ -256,6 +256,9 @@ class SceneAdaptiveInterpolation(nn.Module):
     def net_forward(self, frame0, frame1, target, weights, backup_running_statistics, training, num_step):
         """reference :475-509."""
         kwargs = {'backup_running_statistics': backup_running_statistics, 'num_step': num_step}
+        if self.criterion.super_terms is not None:
+            # the Super loss differentiates through the plugin's auxiliary outputs: forward and loss are one step
+            return self.criterion.forward_with_plugin(self.net, frame0, frame1, target, weights)
         output = self.net.forward(frame0, frame1, params=weights, **kwargs)
         if self.args.model == 'superslomo':
             output[1]['I0'], output[1]['I1'] = frame0, frame1

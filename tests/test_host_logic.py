@@ -378,6 +378,12 @@ def test_super_loss_system_against_reference_golden(ref_ops):
     # validation (forward-only query) reports the same loss the training query of an identical system would
     lv, _, _ = system.run_validation_iter(list(fx["frames"]))
     assert torch.isfinite(lv["loss"]).item()
+    # the compat path (autograd over one fused forward+loss step) reproduces the same golden
     compat = system_from_fixture(fx, ref_ops, fast_path=False, vgg16_weights=seeded_vgg16_state(fx["vgg_seed"]))
-    with pytest.raises(NotImplementedError):
-        compat.run_train_iter(list(fx["frames"]), epoch=0)
+    assert not compat.fast_path_supported()
+    losses, preds, metrics = compat.run_train_iter(list(fx["frames"]), epoch=0, do_evaluation=True)
+    assert abs(float(losses["loss"]) - fx["loss"]) <= 2e-6 * fx["loss"]
+    assert (torch.cat(preds) - fx["preds"]).abs().max().item() <= 2e-6
+    own = dict(compat.net.named_parameters())
+    for k, (d, head) in fx["post_digest"].items():
+        assert torch.allclose(digest(own[k])[0], d, rtol=1e-5, atol=1e-8), k
