@@ -100,3 +100,30 @@ def test_dataset_and_provider_equal_live_reference(tmp_path, model):
         if getter == "get_train_batches":
             assert wf[0].shape[-2:] == (24, 24) and 0 < flips < 5          # both orders occurred
     assert mine.total_train_iters_produced == ref.total_train_iters_produced
+
+
+def test_provider_with_worker_processes(tmp_path):
+    """Decode-only workers in separate processes (the reference's default is --num_workers 5): every staged batch
+    equals the oracle staging of the raw frames and augmentation decisions the workers returned."""
+    from torch.utils.data import DataLoader
+    from oracle.make_golden_data import build_tree
+    from meta_interpolation_b200.data import MetaLearningSystemDataLoader
+    build_tree(str(tmp_path), n_train=4, n_test=1, h=30, w=34)
+    provider = MetaLearningSystemDataLoader(_args(tmp_path, num_workers=2), ops=RefOps())
+    provider.dataset.crop_size = 16
+    provider.dataset.switch_set("train")
+    seen = 0
+    for staged, meta in DataLoader(provider.dataset, batch_size=2, shuffle=False, num_workers=2):
+        frames = provider.dataset.to_device(staged)
+        assert len(frames) == 7 and frames[0].shape == (2, 3, 16, 16)
+        for b in range(2):
+            y0, x0 = int(staged["y0"][b]), int(staged["x0"][b])
+            order = range(6, -1, -1) if bool(staged["reversed"][b]) else range(7)
+            for f, fs in enumerate(order):
+                want = staged["raw"][b, fs, y0:y0 + 16, x0:x0 + 16][:, :, [2, 1, 0]].permute(2, 0, 1).float() / 255
+                assert torch.equal(frames[f][b], want)
+            assert ("im7.png" in meta["imgpaths"][0][b]) == bool(staged["reversed"][b])
+        seen += 1
+    assert seen == 2
+    batches = list(provider.get_train_batches(total_batches=1))
+    assert len(batches) == 1 and batches[0][0][0].shape == (2, 3, 16, 16)
