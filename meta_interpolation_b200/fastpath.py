@@ -246,11 +246,8 @@ class FastPath:
             if a.attenuate or (a.metasgd and a.optimizer != 'Adamax'):
                 return False
         if a.attenuate:
-            # L2F (reference :231-272) is graph-captured for the plain fixed-lr LSLR rule; its combinations with
-            # Meta-SGD / learnable lr / the multi-step loss stay on the compat path
-            if a.metasgd or a.learnable_per_layer_per_step_inner_loop_learning_rate or \
-                    a.use_multi_step_loss_optimization:
-                return False
+            # L2F (reference :231-272) is graph-captured for the SGD inner rule (LSLR fixed / learnable, Meta-SGD,
+            # with or without the multi-step loss) when every tensor is in the inner-loop dict
             if len(system.get_inner_loop_parameter_dict(system.net.named_parameters())) != len(system.net.param_names):
                 return False
         kinds = [t.split('*')[1] for t in a.loss.split('+')]
@@ -490,7 +487,8 @@ class FastPath:
         """alpha / lr outer gradients from the stored per-task query gradient G (Appx E4)."""
         ops = self.ops
         G = lane.gquery.flat
-        ops.axpby(G, scale, lane.acc_theta.flat, 1.0)                     # dL/dtheta += scale * G
+        if not self.l2f:                                                      # (L2F: gamma (.) G, see _l2f_outer)
+            ops.axpby(G, scale, lane.acc_theta.flat, 1.0)                     # dL/dtheta += scale * G
         if self.metasgd and self.rule != RULE_SGD:
             # alpha is constant over the K steps, so the update directions sum to (theta - w_K) / alpha
             alpha = self.sys.alpha.flat
@@ -524,9 +522,12 @@ class FastPath:
             self._support_step(lane, frames, task, step, h, w, support_idxs)
             if msl:
                 wk = float(msl_w[step])
-                if extras:
+                if extras or (self.l2f and training):
                     prog = self._query(lane, frames, task, 'fast', h, w, 'store', 1.0)
-                    self._outer_extras(lane, scale * wk, step + 1)
+                    if self.l2f:
+                        self._l2f_outer(lane, emb, scale * wk)
+                    if extras:
+                        self._outer_extras(lane, scale * wk, step + 1)
                 else:
                     prog = self._query(lane, frames, task, 'fast', h, w, 'accum', scale * wk)
                 task_loss += wk * prog.loss
@@ -537,6 +538,8 @@ class FastPath:
             elif self.l2f:
                 prog = self._query(lane, frames, task, src, h, w, 'store', 1.0)
                 self._l2f_outer(lane, emb, scale)
+                if extras:
+                    self._outer_extras(lane, scale, num_steps)
             elif extras:
                 prog = self._query(lane, frames, task, src, h, w, 'store', 1.0)
                 self._outer_extras(lane, scale, num_steps)

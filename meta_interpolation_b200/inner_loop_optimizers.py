@@ -79,23 +79,33 @@ class _InnerUpdate(torch.autograd.Function):
                          _storage_1d(state['exp_avg_sq']) if 'exp_avg_sq' in state else None,
                          _storage_1d(klr) if per_element else klr, per_element, 0, num_step, seg, None, rule,
                          state.get('step', 1))
-        ctx.save_for_backward(kw, out, klr)
-        ctx.per_element, ctx.num_step, ctx.lr_shape = per_element, num_step, tuple(lr.shape)
+        # SGD: the update direction IS the gradient; keep it instead of recovering it from w - w', which loses
+        # most of its bits once lr * g drops towards the spacing of the weights (inner_lr defaults to 1e-5)
+        ctx.save_for_backward(kw, kg if rule == RULE_SGD else out, klr)
+        ctx.per_element, ctx.num_step, ctx.lr_shape, ctx.rule = per_element, num_step, tuple(lr.shape), rule
         return _reference_form(out)
 
     @staticmethod
     def backward(ctx, g_out):
-        kw, out, klr = ctx.saved_tensors
+        kw, second, klr = ctx.saved_tensors
         g_w = g_out if ctx.needs_input_grad[0] else None
         g_lr = None
         if ctx.needs_input_grad[1]:
-            # update = w - lr*dir  =>  d/dlr = -<dir, G>  (SURVEY Appx E4); dir recovered as (w - w')/lr
-            rg = _reference_form(kw) - _reference_form(out)
-            if ctx.per_element:
-                g_lr = -(rg / _reference_form(klr)) * g_out
-            else:
-                g_lr = torch.zeros(ctx.lr_shape, device=g_out.device, dtype=g_out.dtype)
-                g_lr[ctx.num_step] = -(rg * g_out).sum() / klr[ctx.num_step]
+            # update = w - lr*dir  =>  d/dlr = -<dir, G>  (SURVEY Appx E4)
+            if ctx.rule == RULE_SGD:                     # dir = g (saved)
+                direction = _reference_form(second)
+                if ctx.per_element:
+                    g_lr = -direction * g_out
+                else:
+                    g_lr = torch.zeros(ctx.lr_shape, device=g_out.device, dtype=g_out.dtype)
+                    g_lr[ctx.num_step] = -(direction * g_out).sum()
+            else:                                        # moment rules: dir recovered as (w - w')/lr
+                rg = _reference_form(kw) - _reference_form(second)
+                if ctx.per_element:
+                    g_lr = -(rg / _reference_form(klr)) * g_out
+                else:
+                    g_lr = torch.zeros(ctx.lr_shape, device=g_out.device, dtype=g_out.dtype)
+                    g_lr[ctx.num_step] = -(rg * g_out).sum() / klr[ctx.num_step]
         return g_w, g_lr, None, None, None, None, None, None
 
 

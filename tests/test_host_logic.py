@@ -387,3 +387,41 @@ def test_super_loss_system_against_reference_golden(ref_ops):
     own = dict(compat.net.named_parameters())
     for k, (d, head) in fx["post_digest"].items():
         assert torch.allclose(digest(own[k])[0], d, rtol=1e-5, atol=1e-8), k
+
+
+@pytest.mark.parametrize("kw,hw", [
+    (dict(model="superslomo", metasgd=True, number_of_training_steps_per_iter=2), (64, 64)),
+    (dict(model="sepconv", learnable_per_layer_per_step_inner_loop_learning_rate=True,
+          use_multi_step_loss_optimization=True, multi_step_loss_num_epochs=5, number_of_training_steps_per_iter=2),
+     (32, 40))], ids=["l2f_metasgd", "l2f_learnable_lr_msl"])
+def test_l2f_combinations_graph_path_matches_compat_path(ref_ops, kw, hw):
+    """L2F (--attenuate) combined with Meta-SGD, and with learnable per-step rates under the multi-step loss: the graph
+    path's outer gradients (theta through gamma, alpha / lr from the stored query gradient, attenuator and gamma_mult
+    from dL/dgamma_i = <G_i, theta_i> per query pass) against autograd through the compat path."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    g = torch.Generator().manual_seed(6)
+    shift = 0.4 if kw["model"] == "superslomo" else 0.0
+    frames = [torch.rand(1, 3, *hw, generator=g) - shift for _ in range(7)]
+    res = {}
+    for fast in (True, False):
+        s = SceneAdaptiveInterpolation(make_args(attenuate=True, inner_lr=1e-4, fast_path=fast, **kw), ops=ref_ops)
+        assert s.fast_path_supported() == fast
+        with torch.no_grad():
+            s.gamma_mult.fill_(0.3)
+        opt, seen = s.optimizer, {}
+        orig = opt.step
+
+        def step(opt=opt, seen=seen, orig=orig):
+            opt.gather_grads()
+            for gr in opt.flat_groups:
+                seen[gr.name] = gr.grad.detach().clone()
+            orig()
+        opt.step = step
+        lt, pt, _ = s.run_train_iter(frames, epoch=0)
+        res[fast] = (float(lt["loss"].detach()), torch.cat(pt), seen)
+    a, b = res[True], res[False]
+    assert abs(a[0] - b[0]) <= 2e-6 and (a[1] - b[1]).abs().max().item() <= 5e-6
+    assert len(b[2]) == 3                                   # theta, alpha | lr, and the L2F group
+    for k, gb in b[2].items():
+        assert gb.abs().max().item() > 0, k
+        assert (a[2][k] - gb).abs().max().item() <= 1e-4 * gb.abs().max().item() + 1e-12, k
