@@ -28,6 +28,11 @@ METRIC = "septuplet-tasks/sec (K=5 inner steps, 256x448)"
 WORKLOAD = "sepconv MAML K=5 inner steps, 256x448 synthetic Vimeo-septuplet, meta-batch=8 per GPU, LSLR-SGD, 1*L1"
 
 
+def bench_config(world):
+    return {"workload": WORKLOAD, "tasks_per_gpu": TASKS_PER_GPU, "global_batch": TASKS_PER_GPU * world,
+            "l2": "256 MB flush write between steps; per-step working set >> 126 MB L2"}
+
+
 def make_args(batch, cuda=True):
     return argparse.Namespace(
         model='sepconv', loss='1*L1', optimizer='SGD', inner_lr=1e-5, outer_lr=1e-5, batch_size=batch, mode='train',
@@ -153,8 +158,10 @@ def run_ours(a):
     value = batch * a.steps / (ms / 1e3)
 
     # ---- end-to-end leg (pinned host frames -> device every step, loss read back every step)
-    h2d = sum(f.numel() * 4 for f in host_sets[0]) // world   # each rank copies the tasks it adapts
+    h2d = sum(f.numel() * 4 for f in host_sets[0])   # whole job: each rank copies the 1/world of it that it adapts
     loss_host = torch.zeros(1).pin_memory()
+    per_rank = batch // world
+    preds_host = torch.zeros(per_rank, 3, H, W).pin_memory()   # run_train_iter's second result: the rank's predictions
 
     def step_e2e(i):
         l2_flush.zero_()
@@ -165,6 +172,8 @@ def run_ours(a):
             frames[t][rank * per:(rank + 1) * per].copy_(hs[t][rank * per:(rank + 1) * per], non_blocking=True)
         losses, preds, _ = system.run_train_iter(frames, epoch=0)
         loss_host.copy_(losses['loss'].detach().reshape(1), non_blocking=True)
+        for j in range(per_rank):          # the predictions of the tasks this rank adapted, back to the host
+            preds_host[j].copy_(preds[rank * per_rank + j].reshape(3, H, W), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     step_e2e(0)
@@ -173,19 +182,32 @@ def run_ours(a):
 
     # the instrumented roofline iteration contains the meta-gradient all-reduce: every rank must take part
     extra = extra_sections(system, a, rank)
+    del system, dev_sets
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    other = None
+    if not a.no_other_configs:
+        from bench_sections import other_configs_section
+        other = other_configs_section(rank, world, timed)
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": "tasks/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (tf32 tensor-core conv, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "tasks_per_gpu": TASKS_PER_GPU, "global_batch": batch,
-                       "l2": "256 MB flush write between steps; per-step working set >> 126 MB L2"},
+            "config": bench_config(world),
             "clocks": clocks,
             "e2e": {"value": round(e2e, 4), "unit": "tasks/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": world * (4 + int(preds_host.numel() * 4)),
+                    "bytes_scope": "all ranks together; result read back = loss + every prediction [3,256,448]"},
             "gpu_launches": int(launches),
         }
         line.update(extra)
+        if other is not None:
+            line["config"]["other_configs"] = other
+        if world == 1 and not a.no_gpu_reference:
+            from bench_sections import gpu_reference_section
+            line["gpu_reference"] = gpu_reference_section(line["e2e"]["value"])
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -219,6 +241,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-other-configs", dest="no_other_configs", action="store_true",
+                    help="skip the C3/C4/C5 legs (BASELINE configs[2..4]) after the timed region")
+    ap.add_argument("--no-gpu-reference", dest="no_gpu_reference", action="store_true",
+                    help="skip timing the unmodified reference's own GPU path (baseline/_ref) at N=1")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -45,6 +45,24 @@ def roofline_section(system):
     finally:
         system.use_cuda_graphs = saved
         fast.use_graphs = fast_saved
+    # device time of the same one-task step replayed as CUDA graphs on ONE stream (no launch gaps, no lane overlap):
+    # the denominator of `share_of_step`, which therefore counts every kernel of the step, tagged or not
+    step_ms = None
+    if fast_saved:
+        lanes_saved = fast.n_lanes
+        fast.n_lanes = 1
+        try:
+            for _ in range(3):
+                system.run_train_iter(frames, epoch=0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            system.run_train_iter(frames, epoch=0)
+            e1.record()
+            torch.cuda.synchronize()
+            step_ms = e0.elapsed_time(e1)
+        finally:
+            fast.n_lanes = lanes_saved
     peaks = measured_peaks()
     total_ms = sum(v["ms"] for v in summ.values())
     conv_tags = ("fprop_tc_halo", "fprop_tc_halo_stream", "fprop_tc", "wgrad_tc_kx", "wgrad_tc", "fprop_simt",
@@ -66,7 +84,9 @@ def roofline_section(system):
         "traffic_launch": NCU_TRAFFIC_LAUNCH.get(dom),
         "peak_source": peaks["source"] + "; dense bf16 sustained (kernel timed inside a long step); the kernel "
                        "computes in TF32, whose tensor-pipe ceiling is half the bf16 one (frac 0.5 = TF32 peak)",
-        "share_of_instrumented_step": round(d["ms"] / total_ms, 3) if total_ms > 0 else None,
+        "share_of_tagged_kernels": round(d["ms"] / total_ms, 3) if total_ms > 0 else None,
+        "share_of_step": round(d["ms"] / step_ms, 3) if step_ms else None,
+        "one_task_step_ms_single_stream_graphs": round(step_ms, 3) if step_ms else None,
         "avg_launch_us": round(d["ms"] * 1e3 / max(d["launches"], 1), 2),
         "algorithmic_gflop_per_launch": round(d["flops"] / max(d["launches"], 1) / 1e9, 3),
         "instrumented_step_ms": round(wall_ms, 2), "per_kernel": breakdown,
@@ -117,13 +137,24 @@ def cpu_baseline_section():
                       "a task; %.1f s measured, task time extrapolated x5.5" % dt}
 
 
+def _all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use the box."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def cpu_reference_run(steps, warmup, world):
-    """--impl reference: the reference's algorithm on the host cores (pinned oracle port; the reference itself
-    is unpackaged Python that cannot travel to the GPU box).  Each step is the bounded sample above."""
-    threads = torch.get_num_threads()
+    """--impl reference: the reference's algorithm on the host cores (pinned oracle port; SepConv has no CPU path in
+    the reference itself, sepconv.py:293-294).  Each step is the bounded sample above."""
+    threads = _all_host_threads()
     system = _oracle_system(1)
     frames = bench.synthetic_septuplets(1, 100)
-    for _ in range(min(warmup, 1)):
+    for _ in range(warmup):
         _cpu_pass(system, frames)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -133,10 +164,107 @@ def cpu_reference_run(steps, warmup, world):
     value = 1.0 / per_task
     return {
         "impl": "reference", "metric": bench.METRIC, "value": round(value, 5), "unit": "tasks/s", "n_gpus": world,
-        "steps": steps, "warmup": min(warmup, 1), "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(dt * 1e3, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": bench.WORKLOAD},
+        "config": bench.bench_config(world),
         "cpu_baseline": {"value": round(value, 5), "unit": "tasks/s", "cores": threads, "kind": "port",
-                         "sample": "each step = 1 support step of one 256x448 task (2 of its 11 passes), x5.5"},
+                         "sample": "each step = 1 support step of one 256x448 task (2 of its 11 passes); "
+                                   "tasks/s = 1 / (5.5 x step time); rank 0 only, all host threads"},
         "e2e": {"value": round(value, 5), "unit": "tasks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+
+
+# --------------------------------------------------------------------------------------------- other configs
+OTHER_CONFIGS = {
+    # BASELINE.json configs[2..4]: (flags, (H, W), global meta-batch, GPUs the config is quoted on, scaling)
+    "C3 superslomo Meta-SGD K=5 256x448": (dict(model="superslomo", loss="1*L1", optimizer="SGD", metasgd=True,
+                                                number_of_training_steps_per_iter=5), (256, 448), 4, "weak", None),
+    "C4 cain L2F K=3 512x512": (dict(model="cain", loss="1*L1", optimizer="SGD", attenuate=True,
+                                     number_of_training_steps_per_iter=3), (512, 512), 4, "weak", 0.4),
+    "C5 rrin MAML++ MSL K=5 256x448": (dict(model="rrin", loss="1*L1", optimizer="SGD",
+                                            number_of_training_steps_per_iter=5,
+                                            learnable_per_layer_per_step_inner_loop_learning_rate=True,
+                                            use_multi_step_loss_optimization=True, multi_step_loss_num_epochs=1),
+                                       (256, 448), 64, "strong", None),
+}
+
+
+def _normalise(frames, model):
+    if model == "superslomo":
+        mean = torch.tensor([0.429, 0.431, 0.397]).view(1, 3, 1, 1)
+        return [f - mean for f in frames]
+    return frames
+
+
+def other_configs_section(rank, world, timed):
+    """BASELINE configs[2..4] after the headline's timed region: 3 warm-up + 3 timed `run_train_iter` each, frames
+    resident in HBM, device time (max over ranks).  C3 / C4 keep 4 tasks per GPU (weak scaling: 32 tasks on 8 GPUs,
+    16 on 4); C5 is the strong-scaling sweep, 64 tasks split over the N ranks."""
+    import gc
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    out = {}
+    for name, (over, (h, w), tasks, scaling, gain) in OTHER_CONFIGS.items():
+        batch = tasks * world if scaling == "weak" else tasks
+        if batch % world:
+            out[name] = {"skipped": "%d tasks do not split over %d ranks" % (batch, world)}
+            continue
+        a = bench.make_args(batch)
+        for k, v in over.items():
+            setattr(a, k, v)
+        a.number_of_evaluation_steps_per_iter = a.number_of_training_steps_per_iter
+        system = SceneAdaptiveInterpolation(a)
+        if gain is not None:   # cain's default init explodes through 125 stacked convs (SURVEY 8d): seeded init x0.4
+            with torch.no_grad():
+                for p in system.net.parameters():
+                    if p.dim() == 4:
+                        p.mul_(gain)
+        per = batch // world
+        local = bench.synthetic_septuplets(per, 321 + rank, h, w)
+        frames = [torch.zeros(batch, 3, h, w, device="cuda") for _ in range(7)]
+        for t in range(7):      # only this rank's tasks are ever read
+            frames[t][rank * per:(rank + 1) * per].copy_(_normalise(local, over["model"])[t])
+        for _ in range(3):
+            system.run_train_iter(frames, epoch=0)
+        steps = 3
+        ms = timed(lambda i: system.run_train_iter(frames, epoch=0), steps)
+        out[name] = {"value": round(batch * steps / (ms / 1e3), 3), "unit": "tasks/s", "global_batch": batch,
+                     "tasks_per_gpu": per, "scaling": scaling, "ms_per_step": round(ms / steps, 2), "steps": steps,
+                     "warmup": 3, "graph_path": bool(system.fast_path_supported())}
+        del system, frames
+        gc.collect()
+        torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------- GPU reference
+def gpu_reference_section(our_e2e):
+    """north_star's denominator: the UNMODIFIED reference (staged copy under baseline/_ref, its own cupy kernel
+    strings through NVRTC, cuDNN with its default allow_tf32=True) timed on the same GPU right after our arm, same
+    workload (8 tasks per step, frames resident on the device -- the reference's `run_train_iter` takes device
+    tensors).  Runs in a subprocess with one visible GPU; `ratio` = our end-to-end tasks/s / its tasks/s."""
+    import subprocess
+    import sys
+    script = os.path.join(ROOT, "baseline", "reference_gpu.py")
+    if not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "meta_learning_system.py")):
+        return {"unavailable": "baseline/_ref (staged copy of the reference) is not present"}
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    out = {}
+    for tf32 in (True, False):
+        cmd = [sys.executable, script, "--model", "sepconv", "--batch", str(bench.TASKS_PER_GPU), "--steps", "3",
+               "--warmup", "2"] + ([] if tf32 else ["--no-tf32"])
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+            line = json.loads(res.stdout.strip().splitlines()[-1]) if res.returncode == 0 else \
+                {"error": res.stderr.strip().splitlines()[-1][:300] if res.stderr.strip() else "rc %d" % res.returncode}
+        except Exception as e:      # noqa: BLE001 -- a failed reference run must not take the bench line with it
+            line = {"error": repr(e)[:300]}
+        out["allow_tf32" if tf32 else "fp32"] = line
+    ref = out["allow_tf32"].get("tasks_per_s")
+    out["ratio_e2e_over_reference_tf32"] = round(our_e2e / ref, 2) if ref else None
+    ref32 = out["fp32"].get("tasks_per_s")
+    out["ratio_e2e_over_reference_fp32"] = round(our_e2e / ref32, 2) if ref32 else None
+    out["what"] = ("unmodified reference run_train_iter on this GPU: sepconv K=5 256x448, 8 tasks per step, 2 warm-up "
+                   "+ 3 timed steps, wall clock between torch.cuda.synchronize()")
+    return out

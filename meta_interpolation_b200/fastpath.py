@@ -128,6 +128,7 @@ class _Program:
         self.f1 = torch.zeros(n, 3, h, w, device=dev)
         self.tgt = torch.zeros(n, 3, h, w, device=dev)
         self.loss = torch.zeros(1, device=dev)
+        self.terms = torch.zeros(max(1, len(lane.fp.loss_terms)), device=dev)   # per-term values (multi-term losses)
         self.pred = None
         self.body = body
         self.graph = None
@@ -187,6 +188,9 @@ class _Lane:
         self.l2f_records = []    # (task embedding, dL/dgamma) per adapted task, consumed once per meta-batch
         self.gsteps = []
         self.dots = torch.zeros(len(net.param_names), device=dev)
+        # what the reference's loss AverageMeters see (meta_learning_system.py:323-332): every query pass's loss dict
+        self.log_sum = torch.zeros(1 + len(fp.loss_terms), device=dev)
+        self.log_n = 0
         self.programs = {}
         self.fast_wt = {}    # rotated (dgrad-layout) copies of the fast weights, written by the fused update
         # lane 0 accumulates straight into the optimizer's flat gradient buffers; the others into private
@@ -286,6 +290,8 @@ class FastPath:
         # the `Super` loss (loss.py:246-274) differentiates through SuperSloMo's auxiliary outputs on the tape
         self.super_weight = sum(w for k, w in terms if k == 'Super') if any(k == 'Super' for k, _ in terms) else None
         self.super_terms = system.criterion.super_terms
+        self.term_names = [k for k, _ in terms]
+        self.multi_term = len(terms) > 1
         self.meta_wt = {}
         # measured on B200, SepConv 256x448 K=5: 1 lane 22.7, 2 lanes 27.9, 3 lanes 29.2, 4 lanes 30.1 tasks/s
         lanes = os.environ.get('MI_B200_TASK_STREAMS', getattr(a, 'task_streams', 4))
@@ -336,19 +342,23 @@ class FastPath:
                                   self.super_weight * n_pairs, prog.loss, backward)
 
     def _loss(self, prog, pred, n_pairs):
+        """Pixel-loss terms of the pass: value into ``prog.loss`` (and, when the loss string has several terms, each
+        term's own value into ``prog.terms`` for the per-term log the reference keeps, loss.py:325-350)."""
         self.ops.fill(prog.loss, 0.0)
         if not self.loss_terms:
             return None
         grad = torch.empty_like(pred)
-        first = True
-        for kind, weight in self.loss_terms:
-            if first:
-                self.ops.loss_fwd_bwd(pred, prog.tgt, kind, weight * n_pairs, prog.loss, grad)
-                first = False
-            else:
-                g2 = torch.empty_like(pred)
-                self.ops.loss_fwd_bwd(pred, prog.tgt, kind, weight * n_pairs, prog.loss, g2)
-                self.ops.axpby(g2, 1.0, grad, 1.0)
+        if not self.multi_term:
+            kind, weight = self.loss_terms[0]
+            self.ops.loss_fwd_bwd(pred, prog.tgt, kind, weight * n_pairs, prog.loss, grad)
+            return grad
+        self.ops.fill(prog.terms, 0.0)
+        for i, (kind, weight) in enumerate(self.loss_terms):
+            g = grad if i == 0 else torch.empty_like(pred)
+            self.ops.loss_fwd_bwd(pred, prog.tgt, kind, weight * n_pairs, prog.terms[i:i + 1], g)
+            if i:
+                self.ops.axpby(g, 1.0, grad, 1.0)
+        prog.loss.add_(prog.terms.sum())
         return grad
 
     def _support_body(self, lane, src, step_slot):
@@ -481,6 +491,10 @@ class FastPath:
         prog.f1[0].copy_(frames[ti[2]][task])
         prog.tgt[0].copy_(frames[ti[1]][task])
         prog.run()
+        lane.log_sum[0:1].add_(prog.loss)
+        if self.multi_term and self.loss_terms:
+            lane.log_sum[1:].add_(prog.terms)
+        lane.log_n += 1
         return prog
 
     def _outer_extras(self, lane, scale, steps_done):
@@ -554,6 +568,10 @@ class FastPath:
         losses_dev, preds = [None] * len(task_ids), [None] * len(task_ids)
         multi = self.n_lanes > 1
         main = torch.cuda.current_stream(self.ops.device) if multi else None
+        for lane in self.lanes:          # (run_test_iter never reads the log: start every meta-batch from zero)
+            if lane.log_n:
+                lane.log_sum.zero_()
+                lane.log_n = 0
         if multi:
             for lane in self.lanes:
                 lane.stream.wait_stream(main)      # inputs, zeroed gradients and rotated weights are ready
@@ -571,6 +589,27 @@ class FastPath:
                 main.wait_stream(lane.stream)
         return losses_dev, preds
 
+    def _logged_losses(self):
+        """{'total': ..., '<term>': ...}: averages over every query pass of the meta-batch, as the reference's
+        ``update_loss_metrics`` / ``get_across_task_loss_metrics`` report them (:323-344), then reset."""
+        n = sum(lane.log_n for lane in self.lanes)
+        out = {}
+        if n:
+            tot = (torch.stack([lane.log_sum for lane in self.lanes]).sum(0) / n).cpu().numpy()
+            out['total'] = tot[0]
+            pixel = [self.term_names[i] for i in range(len(self.term_names)) if self.term_names[i] in LOSS_KIND]
+            if not self.multi_term:
+                out[self.term_names[0]] = tot[0]
+            else:
+                for i, name in enumerate(pixel):
+                    out[name] = tot[1 + i]
+                if 'Super' in self.term_names:
+                    out['Super'] = tot[0] - tot[1:].sum()
+        for lane in self.lanes:
+            lane.log_sum.zero_()
+            lane.log_n = 0
+        return out
+
     def _finish(self, frames, task_ids, losses_dev, preds, do_evaluation, msl_w, loss_name_terms):
         sysm = self.sys
         n_tasks = len(frames[0])
@@ -584,21 +623,18 @@ class FastPath:
                                                 ops=self.ops)
                 metrics['psnr'].update(psnr)
                 metrics['ssim'].update(ssim)
-        stacked = torch.cat(losses_dev)
-        losses = {'loss': stacked.mean()}
-        total = stacked.mean().detach().cpu().numpy()
-        losses['total'] = total
-        if len(loss_name_terms) == 1:
-            losses[loss_name_terms[0]] = total
+        losses = {'loss': torch.cat(losses_dev).mean() if losses_dev else torch.zeros((), device=self.ops.device)}
+        losses.update(self._logged_losses())
         for idx, item in enumerate(msl_w):
             losses['loss_importance_vector_{}'.format(idx)] = item.detach().cpu().numpy()
         return losses, per_task, metrics
 
-    def train_iter(self, frames, epoch, task_ids, world, do_evaluation):
+    def train_iter(self, frames, epoch, task_ids, n_global, do_evaluation):
+        """``task_ids``: the tasks of the meta-batch this rank adapts (possibly none); ``n_global``: size of the whole
+        meta-batch -- every outer gradient is scaled by 1/n_global so the ranks' SUM is the reference's mean."""
         sysm, a = self.sys, self.sys.args
         msl_w = sysm.get_per_step_loss_importance_vector()
         msl = a.use_multi_step_loss_optimization and epoch < a.multi_step_loss_num_epochs
-        n_global = len(task_ids) * world
         scale = 1.0 / n_global
         sysm.optimizer.zero_grad()
         for g in sysm._groups:

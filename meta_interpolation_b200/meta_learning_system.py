@@ -280,11 +280,35 @@ class SceneAdaptiveInterpolation(nn.Module):
         return 0, 1
 
     def _local_tasks(self, n_tasks):
+        """Tasks of the meta-batch this rank adapts: the contiguous block [r*B/R, (r+1)*B/R) (floor division, so a
+        meta-batch that does not divide by the world size -- the short last batch of an epoch -- is split raggedly
+        and a rank may get none).  Gradients are scaled by 1/B (the global count) on every rank, so the SUM
+        all-reduce is the reference's mean over the whole meta-batch whatever the split."""
         rank, world = self._world()
-        if world == 1 or n_tasks % world != 0:
-            return list(range(n_tasks)), 1
-        per = n_tasks // world
-        return list(range(rank * per, (rank + 1) * per)), world
+        return list(range(rank * n_tasks // world, (rank + 1) * n_tasks // world))
+
+    def _allreduce_logged(self, losses, metrics, n_local, n_tasks):
+        """one scalar all-reduce so every rank logs the meta-batch's loss / PSNR / SSIM, not its shard's."""
+        rank, world = self._world()
+        if world == 1:
+            return
+        # the same keys on every rank, whether or not it adapted a task: 'loss', 'total' and the loss string's terms
+        keys = ['loss', 'total'] + [t.split('*')[1] for t in self.args.loss.split('+')]
+        vals = [float(n_local) * float(torch.as_tensor(losses[k]).detach().reshape(-1)[0])
+                if (n_local and k in losses) else 0.0 for k in keys]
+        vals += [metrics['psnr'].sum, metrics['ssim'].sum, float(metrics['psnr'].count)]
+        buf = torch.tensor(vals, dtype=torch.float64, device=self.device)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        out = buf.tolist()
+        for i, k in enumerate(keys):
+            mean = out[i] / max(n_tasks, 1)
+            losses[k] = torch.tensor(mean, dtype=torch.float32, device=self.device) if k == 'loss' else \
+                np.float32(mean)
+        n_eval = out[-1]
+        for name, total in (('psnr', out[-3]), ('ssim', out[-2])):
+            m = metrics[name]
+            m.sum, m.count = total, int(n_eval)
+            m.avg = total / n_eval if n_eval else 0
 
     # ------------------------------------------------------------------ forward (compat control flow)
     def _denorm(self, pred):
@@ -416,19 +440,33 @@ class SceneAdaptiveInterpolation(nn.Module):
         if not self.training:
             self.train()
         data_batch = [frame.to(device=self.device) for frame in data_batch]
-        task_ids, world = self._local_tasks(len(data_batch[0]))
+        n_tasks = len(data_batch[0])
+        task_ids = self._local_tasks(n_tasks)
 
         if self.fast_path_supported():
-            losses, preds, metrics = self.fast_path().train_iter(data_batch, epoch, task_ids, world, do_evaluation)
+            losses, preds, metrics = self.fast_path().train_iter(data_batch, epoch, task_ids, n_tasks, do_evaluation)
             self._allreduce_grads()
             self.optimizer.step()
-        else:
+        elif task_ids:
             losses, preds, metrics = self.train_forward_prop(data_batch=data_batch, epoch=epoch,
                                                              do_evaluation=do_evaluation, task_ids=task_ids)
-            self.meta_update(loss=losses['loss'] / world)
+            # mean over the local tasks -> this rank's share of the mean over the whole meta-batch
+            self.meta_update(loss=losses['loss'] * (len(task_ids) / n_tasks))
+        else:      # more ranks than tasks: nothing to adapt here, but the collective and the step still happen
+            losses, preds, metrics = self._empty_results(n_tasks)
+            self.optimizer.zero_grad()
+            self._allreduce_grads()
+            self.optimizer.step()
+        self._allreduce_logged(losses, metrics, len(task_ids), n_tasks)
         self.optimizer.zero_grad()
         self.zero_grad()
         return losses, preds, metrics
+
+    def _empty_results(self, n_tasks):
+        losses = {'loss': torch.zeros((), device=self.device), 'total': np.float32(0.0)}
+        for idx, item in enumerate(self.get_per_step_loss_importance_vector()):
+            losses['loss_importance_vector_{}'.format(idx)] = item.detach().cpu().numpy()
+        return losses, [[] for _ in range(n_tasks)], {'psnr': utils.AverageMeter(), 'ssim': utils.AverageMeter()}
 
     def run_validation_iter(self, data_batch):
         """reference :608-627."""

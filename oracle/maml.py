@@ -199,3 +199,28 @@ class OracleSystem:
         num_steps = self.num_steps if num_steps is None else num_steps
         loss, preds, psnrs = self.forward(frames, epoch, num_steps, training=False)
         return loss.detach(), preds, psnrs
+
+    def run_test_iter(self, frames, num_steps=None):
+        """meta_learning_system.py:630-697: 4-frame clips, support triplets (0,1,2) and (1,2,3), then the frame
+        between frames 1 and 2 from the adapted weights.  Only superslomo is de-normalised (:686-690); every other
+        backbone returns the raw network output [3,H,W]."""
+        num_steps = self.num_steps if num_steps is None else num_steps
+        support_idxs = ((0, 1, 2), (1, 2, 3))
+        outs = []
+        for task in range(frames[0].shape[0]):
+            fast = OrderedDict(self.params)
+            state = {}
+            if self.attenuate:
+                sl = self._support_loss(frames, task, fast, support_idxs)
+                g = torch.autograd.grad(sl, list(fast.values()), create_graph=False, allow_unused=True)
+                emb = torch.stack([x.mean() for x in g])
+                gamma = (1 - self.gamma_mult * self.attenuator(emb)).clamp(0, 1)
+                fast = OrderedDict((k, gamma[i] * v) for i, (k, v) in enumerate(fast.items()))
+            for step in range(num_steps):
+                sl = self._support_loss(frames, task, fast, support_idxs)
+                fast, _ = self.inner_update(sl, fast, state, step)
+            with torch.no_grad():
+                out = self.backbone["forward"](frames[1][task:task + 1], frames[2][task:task + 1], fast, self.params)
+            out = out.detach()[0]
+            outs.append(bb.denormalise(self.model, out) if self.model == "superslomo" else out)
+        return outs

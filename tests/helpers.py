@@ -19,7 +19,12 @@ def make_args(**kw):
 
 
 def load_golden(name):
-    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    fx = torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+    if fx.get("frames") is None and fx.get("frames_u8") is not None:
+        # full-size fixtures keep their structured frames as uint8 (oracle/make_golden.py::normalise_u8)
+        from oracle.make_golden import normalise_u8
+        fx["frames"] = torch.stack(normalise_u8(fx["frames_u8"], fx["args"]["model"]))
+    return fx
 
 
 def golden_names():
@@ -37,6 +42,10 @@ def oracle_from_fixture(fx):
     init = bb.seeded_params(a["model"], a["random_seed"])
     if fx.get("weight_gain") is not None:
         init = {k: (v * fx["weight_gain"] if v.dim() == 4 else v) for k, v in init.items()}
+    if fx.get("init_transform") is not None:
+        from oracle.make_golden import apply_init_transform
+        init = {k: v.clone() for k, v in init.items()}
+        apply_init_transform(init.items(), fx["init_transform"])
     return maml.OracleSystem(a["model"], init, optimizer=a["optimizer"],
                              metasgd=a["metasgd"], num_steps=a["number_of_training_steps_per_iter"],
                              inner_lr=a["inner_lr"], outer_lr=a["outer_lr"],
@@ -57,4 +66,7 @@ def system_from_fixture(fx, ops, **extra):
             for p in system.net.parameters():
                 if p.dim() == 4:
                     p.mul_(fx["weight_gain"])
+    if fx.get("init_transform") is not None:
+        from oracle.make_golden import apply_init_transform
+        apply_init_transform(system.net.named_parameters(), fx["init_transform"])
     return system

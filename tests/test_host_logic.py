@@ -425,3 +425,42 @@ def test_l2f_combinations_graph_path_matches_compat_path(ref_ops, kw, hw):
     for k, gb in b[2].items():
         assert gb.abs().max().item() > 0, k
         assert (a[2][k] - gb).abs().max().item() <= 1e-4 * gb.abs().max().item() + 1e-12, k
+
+
+TEST_ITER_GOLDEN = ["test_iter_sepconv_k2", "test_iter_superslomo_k2", "test_iter_voxelflow_k1", "test_iter_rrin_l2f_k1"]
+
+
+def system_for_test_iter(fx, ops, fast):
+    s = system_from_fixture(fx, ops, fast_path=fast)
+    if fx.get("gamma_mult") is not None:
+        with torch.no_grad():
+            s.gamma_mult.fill_(fx["gamma_mult"])
+    return s
+
+
+@pytest.mark.parametrize("name", TEST_ITER_GOLDEN)
+@pytest.mark.parametrize("fast", [True, False])
+def test_run_test_iter_against_reference_golden(ref_ops, name, fast):
+    """run_test_iter (reference meta_learning_system.py:630-697) against what the UNMODIFIED reference returned for
+    the same 4-frame clips (oracle/make_golden.py --test-iter): only superslomo is de-normalised, L2F attenuates from
+    the test-mode support triplets."""
+    fx = load_golden(name)
+    s = system_for_test_iter(fx, ref_ops, fast)
+    assert s.fast_path_supported() == fast
+    outs = s.run_test_iter(list(fx["frames"]))
+    assert len(outs) == fx["outputs"].shape[0]
+    for a, b in zip(outs, fx["outputs"]):
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("name", TEST_ITER_GOLDEN)
+def test_oracle_run_test_iter_reproduces_reference_golden(name):
+    fx = load_golden(name)
+    ora = oracle_from_fixture(fx)
+    ora.num_steps = fx["args"]["number_of_evaluation_steps_per_iter"]
+    if fx.get("gamma_mult") is not None:
+        with torch.no_grad():
+            ora.gamma_mult.fill_(fx["gamma_mult"])
+    outs = ora.run_test_iter(list(fx["frames"]))
+    for a, b in zip(outs, fx["outputs"]):
+        assert (a - b).abs().max().item() <= 1e-6

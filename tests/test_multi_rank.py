@@ -33,7 +33,7 @@ def _prepare(system, l2f):
         system.optimizer.param_groups[0]["lr"] = 1.0
 
 
-def _worker(rank, world, port, out_dir, l2f=False):
+def _worker(rank, world, port, out_dir, l2f=False, batch=2):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -47,19 +47,20 @@ def _worker(rank, world, port, out_dir, l2f=False):
     ops = RefOps()
     backbone.set_default_ops(ops)
     for fast in (True, False):          # both execution paths in one rendezvous (process start-up dominates)
-        args = make_args(batch_size=2, number_of_training_steps_per_iter=1, fast_path=fast, attenuate=l2f)
+        args = make_args(batch_size=batch, number_of_training_steps_per_iter=1, fast_path=fast, attenuate=l2f)
         system = SceneAdaptiveInterpolation(args, ops=ops)
         _prepare(system, l2f)
         g = torch.Generator().manual_seed(11)
-        frames = [torch.rand(2, 3, 32, 32, generator=g) for _ in range(7)]
-        losses, preds, _ = system.run_train_iter(frames, epoch=0)
+        frames = [torch.rand(batch, 3, 32, 32, generator=g) for _ in range(7)]
+        losses, preds, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
         mine = [i for i, p in enumerate(preds) if torch.is_tensor(p)]
         torch.save({"flat": system.net.arena.flat.clone(), "tasks": mine, "loss": float(losses["loss"]),
+                    "total": float(losses["total"]), "psnr": float(metrics["psnr"].avg),
                     "extra": _extra_state(system)}, os.path.join(out_dir, "rank%d_fast%d.pt" % (rank, int(fast))))
     dist.destroy_process_group()
 
 
-def _single(fast, l2f=False):
+def _single(fast, l2f=False, batch=2, full=False):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import make_args
     from oracle.ops_ref import RefOps
@@ -69,12 +70,15 @@ def _single(fast, l2f=False):
     saved = backbone._default_ops
     backbone.set_default_ops(ops)
     try:
-        args = make_args(batch_size=2, number_of_training_steps_per_iter=1, fast_path=fast, attenuate=l2f)
+        args = make_args(batch_size=batch, number_of_training_steps_per_iter=1, fast_path=fast, attenuate=l2f)
         system = SceneAdaptiveInterpolation(args, ops=ops)
         _prepare(system, l2f)
         g = torch.Generator().manual_seed(11)
-        frames = [torch.rand(2, 3, 32, 32, generator=g) for _ in range(7)]
-        losses, _, _ = system.run_train_iter(frames, epoch=0)
+        frames = [torch.rand(batch, 3, 32, 32, generator=g) for _ in range(7)]
+        losses, _, metrics = system.run_train_iter(frames, epoch=0, do_evaluation=True)
+        if full:
+            return (system.net.arena.flat.clone(), float(losses["loss"]), float(losses["total"]),
+                    float(metrics["psnr"].avg))
         if l2f:
             return system.net.arena.flat.clone(), float(losses["loss"]), _extra_state(system)
         return system.net.arena.flat.clone(), float(losses["loss"])
@@ -96,7 +100,26 @@ def test_two_ranks_equal_one_rank(tmp_path):
         single, loss = _single(fast)
         # outer SGD step: theta - lr * mean-gradient; the two summation orders agree to fp32 rounding
         assert (r0["flat"] - single).abs().max().item() <= 1e-9, fast
-        assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6, fast
+        # the logged loss is all-reduced: every rank reports the meta-batch's value, not its shard's
+        assert abs(r0["loss"] - loss) <= 1e-6 and abs(r1["loss"] - loss) <= 1e-6, fast
+
+
+@pytest.mark.parametrize("batch,shards", [(3, ([0], [1, 2])), (1, ([], [0]))])
+def test_meta_batch_not_divisible_by_world_size(tmp_path, batch, shards):
+    """The short last batch of an epoch (DataLoader drop_last=False): tasks are split raggedly, every outer gradient
+    is scaled by 1/B, so the SUM all-reduce is still the mean over the meta-batch; a rank with no task only takes
+    part in the collective and the step."""
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path), False, batch), nprocs=2, join=True)
+    for fast in (True, False):
+        r0, r1 = _load(tmp_path, 0, fast), _load(tmp_path, 1, fast)
+        assert (r0["tasks"], r1["tasks"]) == tuple(list(s) for s in shards)
+        assert torch.equal(r0["flat"], r1["flat"])
+        single, loss, total, psnr = _single(fast, batch=batch, full=True)
+        assert (r0["flat"] - single).abs().max().item() <= 1e-8, fast
+        for r in (r0, r1):
+            assert abs(r["loss"] - loss) <= 1e-6 and abs(r["total"] - total) <= 1e-6, fast
+            assert abs(r["psnr"] - psnr) <= 1e-4, fast
 
 
 def test_two_ranks_equal_one_rank_l2f(tmp_path):
@@ -110,7 +133,7 @@ def test_two_ranks_equal_one_rank_l2f(tmp_path):
         single, loss, extra = _single(fast, True)
         scale = max(1.0, single.abs().max().item())
         assert (r0["flat"] - single).abs().max().item() <= 1e-5 * scale, fast
-        assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss) <= 1e-6, fast
+        assert abs(r0["loss"] - loss) <= 1e-6 and abs(r1["loss"] - loss) <= 1e-6, fast
         for k, v in extra.items():
             assert torch.equal(r0["extra"][k], r1["extra"][k]), k
             d = (r0["extra"][k] - v).abs().max().item()
