@@ -82,7 +82,21 @@ int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt,
                     int accumulate, int n, int h, int wd, int cin, int cout, int k,
                     int engine, mi_stream_t stream);
 
-int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, mi_stream_t stream);
+/* round_tf32 != 0: the rotated copy is rounded to the TF32 grid (see "TF32 operand convention" below) */
+int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, int round_tf32,
+                       mi_stream_t stream);
+
+/* TF32 operand convention of the tensor-core engine (MI_ENGINE_AUTO / MI_ENGINE_TC).  tcgen05 `kind::tf32` reads the
+ * upper 19 bits of each fp32 operand, i.e. it TRUNCATES: a relative bias of -2^-11 per operand that accumulates
+ * coherently through a deep conv stack (cuDNN's allow_tf32 path, which the reference runs by default, behaves the
+ * same way).  To stay within the fp32 tolerance of the reference's exact path this library keeps every operand ON
+ * the TF32 grid by round-to-nearest at the producer, where truncation is then a no-op:
+ *   - conv outputs (fprop and dgrad, both CUDA engines unless MI_ENGINE_SIMT is forced) are stored rounded;
+ *   - weights are read from rounded copies (mi_round_tf32 / wr_out / mi_weight_to_dgrad(round_tf32=1)), the fp32
+ *     master copy that the inner and outer updates modify stays exact;
+ *   - activations produced by other kernels are rounded in place by the caller before a conv reads them.
+ * y[r][0:c] = rn_tf32(x[r][0:c]) for `rows` rows of strides ldx / ldy (y may alias x). */
+int mi_round_tf32(const float* x, int ldx, float* y, int ldy, int c, size_t rows, mi_stream_t stream);
 
 /* workspace bytes mi_conv2d_wgrad needs for this shape */
 size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k, int engine);
@@ -97,28 +111,32 @@ size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k,
  *   gsum_w,gsum_b : optional running sum of g over inner steps (Meta-SGD outer grad of alpha, SURVEY Appx E4)
  *   scale : multiplies g in ACCUM mode.
  *   wt_out, ldwt : optional (SGD modes only): the updated weight is also written in the dgrad layout of
- *                  mi_weight_to_dgrad, so the next inner step needs no rotation launch. */
+ *                  mi_weight_to_dgrad, so the next inner step needs no rotation launch.
+ *   wr_out : optional (SGD modes only): TF32-rounded copy of w_out in the same layout (what the next fprop reads);
+ *            when given, wt_out is rounded too. */
 int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy,
                     int n, int h, int wd, int cin, int cout, int k, int ldw,
                     int mode, float scale,
                     float* grad_w, float* grad_b,
                     const float* w_in, const float* b_in, float* w_out, float* b_out,
                     const float* lr_w, const float* lr_b, float* gsum_w, float* gsum_b,
-                    float* wt_out, int ldwt,
+                    float* wt_out, int ldwt, float* wr_out,
                     void* workspace, size_t workspace_bytes, int engine, mi_stream_t stream);
 
 /* ------------------------------------------------------------------ pointwise / resampling
  * avg/max pool 2x2 s2  : sepconv/model.py:197-209, voxel_flow.py:243, superslomo/model.py:69, rrin/unet.py:139
  * bilinear x2 upsample : sepconv/model.py:191 (align_corners=True); voxel_flow.py:400, superslomo/model.py:139,
  *                        rrin/unet.py:184 (align_corners=False) */
-int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t stream);
+/* round_tf32 (here and below): store the result rounded to the TF32 grid because a tensor-core conv reads it next
+ * (TF32 operand convention above); 0 keeps the exact fp32 value. */
+int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int round_tf32, mi_stream_t stream);
 int mi_avgpool2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c, mi_stream_t stream);
 int mi_maxpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t stream);
 int mi_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* dx, int lddx, int accumulate,
                     int n, int h, int wd, int c, mi_stream_t stream);
-int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners, mi_stream_t stream);
+int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners, int round_tf32, mi_stream_t stream);
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
-                     int align_corners, mi_stream_t stream);
+                     int align_corners, int round_tf32, mi_stream_t stream);
 /* Region-of-interest forms.  SepConv crops its prediction to the frame (modulePaddingOutput, sepconv/model.py:264-266,
  * 350), so the four filter Subnets (:313-347) are only needed on the part of the padded canvas whose receptive field
  * reaches the surviving window; the Subnet chain is evaluated on that crop.
@@ -129,21 +147,23 @@ int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumul
  *   mi_window_copy: dst[dy0:dy0+h, dx0:dx0+wd] (+)= src[sy0:sy0+h, sx0:sx0+wd] (crop, and its adjoint). */
 int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align_corners,
                             int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
-                            mi_stream_t stream);
+                            int round_tf32, mi_stream_t stream);
 /* mask_y (optional, shaped like dx): the post-activation tensor that was upsampled; dx is then the gradient w.r.t.
  * its pre-activation (dx *= act'(mask_y)), saving the separate mi_act_bwd pass. */
 int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                             int align_corners, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0,
-                            int hx0, const float* mask_y, int ldmask, int mask_act, float mask_slope,
+                            int hx0, const float* mask_y, int ldmask, int mask_act, float mask_slope, int round_tf32,
                             mi_stream_t stream);
 int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, float* dst, int ldd, int dh, int dw,
                    int dy0, int dx0, int n, int h, int wd, int c, int accumulate, mi_stream_t stream);
 /* y = a + b  (skip adds, sepconv/model.py:294-309) ; a,b,y may alias */
-int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t stream);
+int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, int round_tf32, mi_stream_t stream);
 /* dst (+)= src over a channel slice; used for concat/split and gradient fan-in */
 int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size_t pixels, int c, mi_stream_t stream);
 /* in place: dy *= act'(y) with y the post-activation tensor */
-int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c, mi_stream_t stream);
+/* round_tf32 != 0: the masked gradient is also rounded to the TF32 grid (it is the next dgrad / wgrad operand) */
+int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c,
+               int round_tf32, mi_stream_t stream);
 int mi_fill(float* p, float v, size_t count, mi_stream_t stream);
 
 /* ------------------------------------------------------------------ glue of the flow-based backbones
@@ -224,7 +244,8 @@ int mi_interior_bcast_add(const float* dy, float* dx, int lddx, int n, int h, in
  * (clamp|reflect)(y - pad_top, x - pad_left).  mode 0 = replicate
  * (sepconv/model.py:254-269), 1 = reflect (model_utils.py:17-28, voxel_flow.py:360-368). */
 int mi_frames_to_canvas(const float* f0, const float* f1, float* canvas, int ldc,
-                        int n, int h, int wd, int ch, int cw, int pad_top, int pad_left, int mode, mi_stream_t stream);
+                        int n, int h, int wd, int ch, int cw, int pad_top, int pad_left, int mode, int round_tf32,
+                        mi_stream_t stream);
 /* NHWC window -> NCHW [n,c,h,w] (the crop of sepconv/model.py:349) and back (gradient of the crop, zero elsewhere is the caller's fill) */
 int mi_nhwc_window_to_nchw(const float* src, int lds, float* dst, int n, int hs, int ws, int y0, int x0, int h, int wd, int c, mi_stream_t stream);
 int mi_nchw_to_nhwc_window(const float* src, float* dst, int ldd, int n, int hs, int ws, int y0, int x0, int h, int wd, int c, mi_stream_t stream);
@@ -245,7 +266,7 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
 int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
                    float* g_vert, float* g_horiz, int ldg,
                    int n, int c, int fh, int fw, int gh, int gw, int oh, int ow,
-                   int gy0, int gx0, int iy0, int ix0, int taps, mi_stream_t stream);
+                   int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32, mi_stream_t stream);
 
 /* ------------------------------------------------------------------ bilinear backward warp (grid_sample)
  * variant 0: superslomo backWarp / rrin warp (superslomo/model.py:292-302, rrin/model.py:8-21):
@@ -265,6 +286,11 @@ int mi_loss_fwd_bwd(const float* pred, const float* target, float* grad, float* 
                     int kind, float weight, mi_stream_t stream);
 /* utils.py:171-204: sum over elements of ((q(p)-q(t))/255)^2 into sq_out[0] (double); psnr = -10 log10(sq/count + 1e-8) on host */
 int mi_psnr_accumulate(const float* pred, const float* target, double* sq_out, size_t count, mi_stream_t stream);
+/* utils.py:195-204 -> pytorch_msssim/__init__.py:19-75 (ssim, size_average, val_range): pred/target NCHW [c,h,w] in
+ * [0,1], quantised to 8 bits in the kernel; `window_host` = the normalised 1-D Gaussian of `win` (<= 11) taps (HOST
+ * pointer, read at call time); sum_out[0] += sum of the SSIM map over c x (h-win+1) x (w-win+1); mean on the host. */
+int mi_ssim_accumulate(const float* pred, const float* target, double* sum_out, int c, int h, int w,
+                       const float* window_host, int win, float val_range, mi_stream_t stream);
 
 /* ------------------------------------------------------------------ inner-loop rules on flat arenas
  * (inner_loop_optimizers.py:150-244, 335-426).  `seg` maps each 1024-float chunk of the arena to a tensor id;

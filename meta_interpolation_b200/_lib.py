@@ -25,22 +25,23 @@ SIGNATURES = {
     "mi_prof_summary": (_i, [_i, C.c_void_p]),
     "mi_conv2d_fprop": (_i, [_f, _i, _f, _i, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _i, _st]),
     "mi_conv2d_dgrad": (_i, [_f, _i, _f, _i, _f, _i, _f, _i, _i, _fl, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
-    "mi_weight_to_dgrad": (_i, [_f, _i, _f, _i, _i, _i, _i, _st]),
+    "mi_weight_to_dgrad": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _st]),
+    "mi_round_tf32": (_i, [_f, _i, _f, _i, _i, _sz, _st]),
     "mi_conv2d_wgrad_workspace": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mi_conv2d_wgrad": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _f, _f, _f, _f, _f, _f, _f, _f, _f,
-                             _f, _f, _i, _f, _sz, _i, _st]),
-    "mi_avgpool2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _st]),
+                             _f, _f, _i, _f, _f, _sz, _i, _st]),
+    "mi_avgpool2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _st]),
     "mi_avgpool2_bwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _st]),
     "mi_maxpool2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _st]),
     "mi_maxpool2_bwd": (_i, [_f, _i, _f, _i, _f, _i, _i, _i, _i, _i, _i, _st]),
-    "mi_upsample2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _st]),
-    "mi_upsample2_bwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _st]),
-    "mi_upsample2_window_fwd": (_i, [_f, _i, _f, _i] + [_i] * 13 + [_st]),
-    "mi_upsample2_window_bwd": (_i, [_f, _i, _f, _i] + [_i] * 14 + [_f, _i, _i, _fl, _st]),
+    "mi_upsample2_fwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_upsample2_bwd": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_upsample2_window_fwd": (_i, [_f, _i, _f, _i] + [_i] * 14 + [_st]),
+    "mi_upsample2_window_bwd": (_i, [_f, _i, _f, _i] + [_i] * 14 + [_f, _i, _i, _fl, _i, _st]),
     "mi_window_copy": (_i, [_f, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
-    "mi_add": (_i, [_f, _i, _f, _i, _f, _i, _sz, _i, _st]),
+    "mi_add": (_i, [_f, _i, _f, _i, _f, _i, _sz, _i, _i, _st]),
     "mi_copy": (_i, [_f, _i, _f, _i, _i, _sz, _i, _st]),
-    "mi_act_bwd": (_i, [_f, _i, _f, _i, _i, _fl, _sz, _i, _st]),
+    "mi_act_bwd": (_i, [_f, _i, _f, _i, _i, _fl, _sz, _i, _i, _st]),
     "mi_fill": (_i, [_f, _fl, _sz, _st]),
     "mi_bn_eval_fwd": (_i, [_f, _i, _f, _i, _f, _f, _f, _f, _fl, _i, _fl, _sz, _i, _st]),
     "mi_bn_eval_bwd_workspace": (_sz, [_sz, _i]),
@@ -65,15 +66,16 @@ SIGNATURES = {
     "mi_scale_add": (_i, [_f, _i, _f, _f, _i, _f, _i, _i, _sz, _i, _st]),
     "mi_scale_bwd": (_i, [_f, _i, _f, _f, _i, _i, _i, _sz, _i, _st]),
     "mi_interior_bcast_add": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _fl, _st]),
-    "mi_frames_to_canvas": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
+    "mi_frames_to_canvas": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nhwc_window_to_nchw": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nchw_to_nhwc_window": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_sepconv_fwd": (_i, [_f, _f, _f, _i, _f] + [_i] * 13 + [_st]),
-    "mi_sepconv_bwd": (_i, [_f, _f, _f, _i, _f, _f, _f, _i] + [_i] * 13 + [_st]),
+    "mi_sepconv_bwd": (_i, [_f, _f, _f, _i, _f, _f, _f, _i] + [_i] * 14 + [_st]),
     "mi_warp_fwd": (_i, [_f, _i, _f, _i, _f, _i, _i, _i, _i, _i, _i, _fl, _fl, _st]),
     "mi_warp_bwd": (_i, [_f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _fl, _fl, _st]),
     "mi_loss_fwd_bwd": (_i, [_f, _f, _f, _f, _sz, _i, _fl, _st]),
     "mi_psnr_accumulate": (_i, [_f, _f, _f, _sz, _st]),
+    "mi_ssim_accumulate": (_i, [_f, _f, _f, _i, _i, _i, C.c_void_p, _i, _fl, _st]),
     "mi_inner_update": (_i, [_f, _f, _f, _f, _f, _f, _i, _i, _i, _f, _f, _sz, _i, _i, _st]),
     "mi_outer_step": (_i, [_f, _f, _f, _f, _sz, _i, _fl, _fl, _fl, _fl, _fl, _i, _st]),
     "mi_axpby": (_i, [_f, _fl, _f, _fl, _sz, _st]),

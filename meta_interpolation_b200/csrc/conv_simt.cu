@@ -4,9 +4,20 @@
 // not take (k=5/7 stems with Cin 6/20, Cout<=5 heads, unaligned strides) and is
 // the on-device cross-check of the TF32 tensor-core engine in conv_tc.cu.
 // Replaces F.conv2d + its autograd (reference model_utils.py:360).
+#include <cstdlib>
+
 #include "mi_common.cuh"
 
 std::atomic<unsigned long long> g_mi_launches{0};
+
+bool mi_tf32_rn_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MI_B200_TF32_RN");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
 
 namespace {
 
@@ -22,7 +33,7 @@ __global__ void __launch_bounds__(256)
 conv_fprop_simt_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, int ldw,
                        const float* __restrict__ bias, float* __restrict__ y, int ldy,
                        const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope, int accumulate,
-                       int n, int h, int wd, int cin, int cout, int k, int act, float slope, int vec_ok) {
+                       int n, int h, int wd, int cin, int cout, int k, int act, float slope, int vec_ok, int rnd) {
     __shared__ float As[BK][BM + PADS];
     __shared__ float Bs[BK][BN + PADS];
 
@@ -120,7 +131,7 @@ conv_fprop_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
             if (mask_y) v *= mi_act_grad(mask_y[m * ldmask + co], mask_act, mask_slope);
             float* yp = y + m * ldy + co;
             if (accumulate) v += *yp;
-            *yp = v;
+            *yp = rnd ? mi_rn_tf32(v) : v;
         }
     }
 }
@@ -130,7 +141,7 @@ conv_fprop_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
 // (co >= cout) are not touched: weight buffers are allocated zeroed and nothing ever writes those lanes.
 __global__ void __launch_bounds__(256)
 weight_to_dgrad_tiled_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt, int cin, int cout,
-                             int kk) {
+                             int kk, int rnd) {
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -144,13 +155,34 @@ weight_to_dgrad_tiled_kernel(const float* __restrict__ w, int ldw, float* __rest
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int ci = ci0 + ty + 8 * r, co = co0 + tx;
-        if (ci < cin && co < cout) wt[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = tile[tx][ty + 8 * r];
+        if (ci < cin && co < cout) {
+            const float v = tile[tx][ty + 8 * r];
+            wt[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = rnd ? mi_rn_tf32(v) : v;
+        }
+    }
+}
+
+// y[r][0:c] = rn_tf32(x[r][0:c]) over rows of an NHWC activation (or a flat buffer); in place when y == x
+__global__ void round_tf32_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int c,
+                                  long long rows, int vec) {
+    const int per = vec ? c / 4 : c;
+    const long long total = rows * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / per;
+        const int j = (int)(i % per);
+        if (vec) {
+            const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * j);
+            *reinterpret_cast<float4*>(y + r * ldy + 4 * j) = mi_rn_tf32(v);
+        } else {
+            y[r * ldy + j] = mi_rn_tf32(x[r * ldx + j]);
+        }
     }
 }
 
 // wt[ci][k-1-ky][k-1-kx][co] = w[co][ky][kx][ci]
 __global__ void weight_to_dgrad_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt,
-                                       int cin, int cout, int k) {
+                                       int cin, int cout, int k, int rnd) {
     const long long total = (long long)cin * k * k * ldwt;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -160,7 +192,7 @@ __global__ void weight_to_dgrad_kernel(const float* __restrict__ w, int ldw, flo
         const int ci = (int)(r / (k * k));
         float v = 0.f;
         if (co < cout) v = w[((long long)co * k * k + (k * k - 1 - tap)) * ldw + ci];
-        wt[i] = v;
+        wt[i] = rnd ? mi_rn_tf32(v) : v;
     }
 }
 
@@ -284,7 +316,7 @@ __global__ void __launch_bounds__(256)
 conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, int ldw,
                         const float* __restrict__ bias, float* __restrict__ y, int ldy,
                         const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope, int accumulate,
-                        int n, int h, int wd, int cin, int cout, int k, int act, float slope, int vec_x) {
+                        int n, int h, int wd, int cin, int cout, int k, int act, float slope, int vec_x, int rnd) {
     extern __shared__ __align__(16) float sw[];      // [k*k][cin][SC]
     const int kk = k * k, pad = k >> 1;
     for (int i = threadIdx.x; i < kk * cin * SC; i += blockDim.x) {
@@ -344,7 +376,7 @@ conv_fprop_small_kernel(const float* __restrict__ x, int ldx, const float* __res
             float v = mi_act_apply(acc[co], act, slope);
             if (mp) v *= mi_act_grad(mp[co], mask_act, mask_slope);
             if (accumulate) v += yp[co];
-            yp[co] = v;
+            yp[co] = rnd ? mi_rn_tf32(v) : v;
         }
     }
 }
@@ -451,7 +483,7 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
                                     float* __restrict__ w_out, float* __restrict__ b_out,
                                     const float* __restrict__ lr_w, const float* __restrict__ lr_b,
                                     float* __restrict__ gsum_w, float* __restrict__ gsum_b,
-                                    float* __restrict__ wt_out, int ldwt) {
+                                    float* __restrict__ wt_out, int ldwt, float* __restrict__ wr_out, int rnd) {
     const long long wsz = (long long)cout * kk * ldw;
     const long long wsz32 = (wsz + 31) & ~31LL;
     const long long total = wsz32 + (long long)cout * 32;
@@ -487,11 +519,15 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
                 const float wn = w_in[e] - l * g;
                 w_out[e] = wn;
                 if (grad_w) grad_w[e] = g;
+                // copies the tensor-core kernels read: rounded to the TF32 grid when the caller keeps such a copy for
+                // fprop (wr_out), so the hardware's operand truncation becomes a no-op (see mi_rn_tf32)
+                const float wq = (wr_out && rnd) ? mi_rn_tf32(wn) : wn;
+                if (wr_out) wr_out[e] = wq;
                 if (wt_out) {
                     const long long r = e / ldw;
                     const int tap = (int)(r % kk);
                     const int co = (int)(r / kk);
-                    wt_out[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = wn;
+                    wt_out[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = wq;
                 }
             }
             if (gsum_w) gsum_w[e] += g;
@@ -521,15 +557,16 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
 
 }  // namespace
 
-int mi_weight_to_dgrad_launch(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, cudaStream_t st) {
+int mi_weight_to_dgrad_launch(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, int rnd,
+                              cudaStream_t st) {
     if (cin >= 32 && cout >= 32) {
         weight_to_dgrad_tiled_kernel<<<dim3(mi_cdiv(cin, 32), mi_cdiv(cout, 32), k * k), 256, 0, st>>>(w, ldw, wt, ldwt, cin,
-                                                                                                    cout, k * k);
+                                                                                                    cout, k * k, rnd);
     } else {
         const long long total = (long long)cin * k * k * ldwt;
         int blocks = mi_cdiv(total, 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
-        weight_to_dgrad_kernel<<<blocks, 256, 0, st>>>(w, ldw, wt, ldwt, cin, cout, k);
+        weight_to_dgrad_kernel<<<blocks, 256, 0, st>>>(w, ldw, wt, ldwt, cin, cout, k, rnd);
     }
     MI_LAUNCHED();
     MI_RETURN_LAST();
@@ -573,13 +610,14 @@ int mi_bias_splits(long long m_total) {
 int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int bias_splits, int cin, int cout, int k,
                            int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
                            float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
-                           float* gsum_b, float* wt_out, int ldwt, cudaStream_t stream) {
+                           float* gsum_b, float* wt_out, int ldwt, float* wr_out, cudaStream_t stream) {
     const long long total = (((long long)cout * k * k * ldw + 31) & ~31LL) + (long long)cout * 32;
     int blocks = mi_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     mi_prof_begin(MI_TAG_WGRAD_FINISH, 0.0, 4.0 * (double)total * (splits + 2), stream);
     wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, bias_splits, cin, cout, k * k, ldw, mode, scale, grad_w,
-                                                    grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, wt_out, ldwt);
+                                                    grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, wt_out, ldwt,
+                                                    wr_out, mi_tf32_rn_enabled() ? 1 : 0);
     mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
@@ -587,7 +625,8 @@ int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int
 
 static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                              const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n,
-                             int h, int wd, int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
+                             int h, int wd, int cin, int cout, int k, int act, float slope, int rnd,
+                             cudaStream_t stream) {
     const long long m_total = (long long)n * h * wd;
     if (small_cout_fprop_ok(cin, cout, k) && m_total >= 4096) {   // (one thread per pixel: pointless on 1x1 maps)
         const int sc = cout <= 8 ? 8 : 16;
@@ -610,11 +649,11 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
         if (sc == 8)
             conv_fprop_small_kernel<8><<<(int)blocks, 256, sm, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask,
                                                                         mask_act, mask_slope, accumulate, n, h, wd, cin,
-                                                                        cout, k, act, slope, vx);
+                                                                        cout, k, act, slope, vx, rnd);
         else
             conv_fprop_small_kernel<16><<<(int)blocks, 256, sm, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask,
                                                                          mask_act, mask_slope, accumulate, n, h, wd, cin,
-                                                                         cout, k, act, slope, vx);
+                                                                         cout, k, act, slope, vx, rnd);
         mi_prof_end(stream);
         MI_LAUNCHED();
         MI_RETURN_LAST();
@@ -625,7 +664,7 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
                   stream);
     conv_fprop_simt_kernel<<<grid, 256, 0, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask, mask_act,
                                                      mask_slope, accumulate, n, h, wd, cin, cout, k, act, slope,
-                                                     vec_ok);
+                                                     vec_ok, rnd);
     mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
@@ -645,8 +684,9 @@ int mi_conv2d_fprop(const float* x, int ldx, const float* w, int ldw, const floa
         if (rc != MI_ERR_UNSUPPORTED || engine == MI_ENGINE_TC) return rc;
     }
     if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
+    // exact-fp32 engine: results stay unrounded; AUTO falling back to these kernels keeps the TF32-grid convention
     return fprop_simt_launch(x, ldx, w, ldw, bias, y, ldy, nullptr, 0, 0, 0.f, 0, n, h, wd, cin, cout, k, act, slope,
-                             mi_cs(stream));
+                             engine != MI_ENGINE_SIMT && mi_tf32_rn_enabled(), mi_cs(stream));
 }
 
 int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt, float* dx, int lddx, const float* mask_y,
@@ -663,12 +703,28 @@ int mi_conv2d_dgrad(const float* dy, int lddy, const float* wt, int ldwt, float*
     }
     if (engine == MI_ENGINE_TC) return MI_ERR_UNSUPPORTED;
     return fprop_simt_launch(dy, lddy, wt, ldwt, nullptr, dx, lddx, mask_y, ldmask, mask_act, mask_slope, accumulate,
-                             n, h, wd, cout, cin, k, MI_ACT_NONE, 0.f, mi_cs(stream));
+                             n, h, wd, cout, cin, k, MI_ACT_NONE, 0.f, engine != MI_ENGINE_SIMT && mi_tf32_rn_enabled(),
+                             mi_cs(stream));
 }
 
-int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, mi_stream_t stream) {
+int mi_weight_to_dgrad(const float* w, int ldw, float* wt, int ldwt, int cin, int cout, int k, int round_tf32,
+                       mi_stream_t stream) {
     if (!w || !wt || ldw < cin || ldwt < cout) return MI_ERR_BAD_ARG;
-    return mi_weight_to_dgrad_launch(w, ldw, wt, ldwt, cin, cout, k, mi_cs(stream));
+    return mi_weight_to_dgrad_launch(w, ldw, wt, ldwt, cin, cout, k, round_tf32 && mi_tf32_rn_enabled(), mi_cs(stream));
+}
+
+int mi_round_tf32(const float* x, int ldx, float* y, int ldy, int c, size_t rows, mi_stream_t stream) {
+    if (!x || !y || c <= 0 || ldx < c || ldy < c) return MI_ERR_BAD_ARG;
+    if (rows == 0) return MI_OK;
+    const bool flat = (ldx == c && ldy == c);
+    const bool vec = (c % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && mi_al16(x) && mi_al16(y);
+    const long long total = vec ? (long long)rows * (c / 4) : (long long)rows * c;
+    int blocks = mi_cdiv(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    (void)flat;
+    round_tf32_kernel<<<blocks, 256, 0, mi_cs(stream)>>>(x, ldx, y, ldy, c, (long long)rows, vec ? 1 : 0);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
 }
 
 
@@ -683,14 +739,15 @@ size_t mi_conv2d_wgrad_workspace(int n, int h, int wd, int cin, int cout, int k,
 int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
                     int k, int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in,
                     const float* b_in, float* w_out, float* b_out, const float* lr_w, const float* lr_b,
-                    float* gsum_w, float* gsum_b, float* wt_out, int ldwt, void* workspace, size_t workspace_bytes,
-                    int engine, mi_stream_t stream) {
+                    float* gsum_w, float* gsum_b, float* wt_out, int ldwt, float* wr_out, void* workspace,
+                    size_t workspace_bytes, int engine, mi_stream_t stream) {
     if (!x || !dy || !workspace || n <= 0 || h <= 0 || wd <= 0 || cin <= 0 || cout <= 0 || (k & 1) == 0 ||
         ldx < cin || lddy < cout || ldw < cin)
         return MI_ERR_BAD_ARG;
     if ((mode == MI_WG_STORE || mode == MI_WG_ACCUM) && (!grad_w)) return MI_ERR_BAD_ARG;
     if ((mode == MI_WG_SGD_SCALAR || mode == MI_WG_SGD_TENSOR) && (!w_in || !w_out || !lr_w)) return MI_ERR_BAD_ARG;
     if (wt_out && (ldwt < cout || (mode != MI_WG_SGD_SCALAR && mode != MI_WG_SGD_TENSOR))) return MI_ERR_BAD_ARG;
+    if (wr_out && mode != MI_WG_SGD_SCALAR && mode != MI_WG_SGD_TENSOR) return MI_ERR_BAD_ARG;
     const int splits = mi_wgrad_splits(n, h, wd, cin, cout, k);
     const size_t wsz = (size_t)cout * k * k * ldw;
     const size_t need = ((size_t)splits * wsz + (size_t)(splits > 256 ? splits : 256) * cout) * sizeof(float);
@@ -742,9 +799,9 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
     // 512x512x9); there the updated weight is rotated by the tiled transpose right after instead
     const bool rotate_after = wt_out && (long long)cin * cout >= 128LL * 128;
     rc = mi_wgrad_finish_launch(ws_w, ws_b, splits, bias_splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
-                                w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, rotate_after ? nullptr : wt_out, ldwt, st);
+                                w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, rotate_after ? nullptr : wt_out, ldwt, wr_out, st);
     if (rc != 0 || !rotate_after) return rc;
-    return mi_weight_to_dgrad_launch(w_out, ldw, wt_out, ldwt, cin, cout, k, st);
+    return mi_weight_to_dgrad_launch(w_out, ldw, wt_out, ldwt, cin, cout, k, wr_out != nullptr, st);
 }
 
 int mi_version(void) { return 100; }

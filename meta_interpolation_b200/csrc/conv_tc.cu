@@ -154,6 +154,7 @@ __device__ __forceinline__ uint32_t instr_desc(int m, int n, int a_mn_major, int
 struct EpiArgs {
     int cout, cout_store, act, mask_act, accumulate;   // cout_store = cout rounded up to 4 when the row stride allows
     float slope, mask_slope;
+    int rnd;   // round what is stored to the TF32 grid (the next tensor-core conv then reads it exactly)
 };
 
 __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const float* __restrict__ sbias, int co,
@@ -203,6 +204,10 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
                 o[4 * g + 0] += a[g].x; o[4 * g + 1] += a[g].y; o[4 * g + 2] += a[g].z; o[4 * g + 3] += a[g].w;
             }
         }
+        if (e.rnd) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = mi_rn_tf32(o[j]);
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g)
             *(reinterpret_cast<float4*>(yrow + co) + g) = make_float4(o[4 * g], o[4 * g + 1], o[4 * g + 2], o[4 * g + 3]);
@@ -226,6 +231,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
                     const float4 a = *reinterpret_cast<const float4*>(yrow + c);
                     r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
                 }
+                if (e.rnd) r = mi_rn_tf32(r);
                 *reinterpret_cast<float4*>(yrow + c) = r;
             } else {
 #pragma unroll
@@ -234,7 +240,7 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&v)[32], const fl
                         float val = o[4 * g + q];
                         if (mrow) val *= mi_act_grad(__ldg(mrow + c + q), e.mask_act, e.mask_slope);
                         if (e.accumulate) val += yrow[c + q];
-                        yrow[c + q] = val;
+                        yrow[c + q] = e.rnd ? mi_rn_tf32(val) : val;
                     }
                 }
             }
@@ -312,6 +318,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t (&v)[32]
                 const float4 a = *reinterpret_cast<const float4*>(dst);
                 r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
             }
+            if (e.rnd) r = mi_rn_tf32(r);
             *reinterpret_cast<float4*>(dst) = r;
         } else {
             const float rv[4] = {r.x, r.y, r.z, r.w};
@@ -321,7 +328,7 @@ __device__ __forceinline__ void epilogue_chunk_coalesced(const uint32_t (&v)[32]
                     float val = rv[q];
                     if (mask_y) val *= mi_act_grad(__ldg(mask_y + pix * ldmask + c + q), e.mask_act, e.mask_slope);
                     if (e.accumulate) val += dst[q];
-                    dst[q] = val;
+                    dst[q] = e.rnd ? mi_rn_tf32(val) : val;
                 }
             }
         }
@@ -396,6 +403,7 @@ __device__ __forceinline__ void epilogue_half_coalesced(const uint32_t (&v)[16],
                 const float4 a = *reinterpret_cast<const float4*>(dst);
                 r.x += a.x; r.y += a.y; r.z += a.z; r.w += a.w;
             }
+            if (e.rnd) r = mi_rn_tf32(r);
             *reinterpret_cast<float4*>(dst) = r;
         } else {
             const float rv[4] = {r.x, r.y, r.z, r.w};
@@ -405,7 +413,7 @@ __device__ __forceinline__ void epilogue_half_coalesced(const uint32_t (&v)[16],
                     float val = rv[q];
                     if (mask_y) val *= mi_act_grad(__ldg(mask_y + pix * ldmask + c + q), e.mask_act, e.mask_slope);
                     if (e.accumulate) val += dst[q];
-                    dst[q] = val;
+                    dst[q] = e.rnd ? mi_rn_tf32(val) : val;
                 }
             }
         }
@@ -422,12 +430,12 @@ __device__ __forceinline__ void epilogue_half_scalar(const uint32_t (&v)[16], co
         float val = mi_act_apply(__uint_as_float(v[j]) + sbias[j], e.act, e.slope);
         if (mrow) val *= mi_act_grad(__ldg(mrow + co + j), e.mask_act, e.mask_slope);
         if (e.accumulate) val += yrow[co + j];
-        yrow[co + j] = val;
+        yrow[co + j] = e.rnd ? mi_rn_tf32(val) : val;
     }
 }
 
 struct FpropParams {
-    int n, h, w, cin, cout, k, tw, th, tiles_x, tiles_y, bn, stages, act, accumulate, mask_act, ldy, ldmask;
+    int n, h, w, cin, cout, k, tw, th, tiles_x, tiles_y, bn, stages, act, accumulate, mask_act, ldy, ldmask, rnd;
     float slope, mask_slope;
     const float* bias;
     const float* mask_y;
@@ -539,7 +547,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
         EpiArgs ea;
-        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate; ea.rnd = p.rnd;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
         ea.cout_store = p.cout;   // lanes past cout are never written: they may belong to the next concat slice
         RowMap rm;
@@ -574,6 +582,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 constexpr int HALO_H = 18, HT_W = 8, HT_H = 16;
 
 struct HaloParams {
+    int rnd;
     int n, h, w, cin, cout, chunks, bn, stages, tiles_x, tiles_y, total_tiles, act, accumulate, mask_act, ldy, ldmask,
         halo_w;
     uint32_t halo_bytes, halo_stride;   // bytes one TMA box delivers / 1024-aligned distance between stages
@@ -759,7 +768,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
         const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
         EpiArgs ea;
-        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate; ea.rnd = p.rnd;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
         ea.cout_store = p.cout;   // lanes past cout are never written: they may belong to the next concat slice
         float* stage = epi_stage + (warp - 2) * 32 * EPI16_PITCH;
@@ -816,6 +825,7 @@ conv_fprop_tc_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
 // small-channel halo kernel is the fastest of the family).  Persistent CTAs walk (pixel tile, 64-cout tile) work
 // items; accumulators are double buffered in TMEM so the epilogue of one item overlaps the MMAs of the next.
 struct HaloStreamParams {
+    int rnd;
     int n, h, w, cin, cout, chunks, n_tiles, tiles_x, tiles_y, total_tiles, items, act, accumulate, mask_act, ldy,
         ldmask, halo_w;
     uint32_t halo_bytes, halo_stride;
@@ -950,7 +960,7 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
         const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
         EpiArgs ea;
-        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate; ea.rnd = p.rnd;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
         ea.cout_store = p.cout;   // lanes past cout are never written: they may belong to the next concat slice
         const int r = q * 32 + lane;
@@ -1007,6 +1017,7 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
 // descriptor view of the halo box shifted by ky rows and kx pixels.  Persistent CTAs over (pixel tile, cout tile) items,
 // double-buffered TMEM accumulators, the eight-warp epilogue of the 3x3 halo kernels.
 struct HaloRowsParams {
+    int rnd;
     int n, h, w, cin, cout, k, chunks, bn, n_tiles, tiles_x, tiles_y, total_tiles, items, act, accumulate, mask_act,
         ldy, ldmask, halo_w, sa, sb;
     uint32_t halo_bytes, halo_stride;
@@ -1140,7 +1151,7 @@ conv_fprop_tc_halo_rows_kernel(const __grid_constant__ CUtensorMap map_x, const 
         const bool vec = ((p.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.mask_y || (((p.ldmask & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.mask_y) & 15) == 0)));
         EpiArgs ea;
-        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate;
+        ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate; ea.rnd = p.rnd;
         ea.slope = p.slope; ea.mask_slope = p.mask_slope;
         ea.cout_store = p.cout;
         const int r = q * 32 + lane;
@@ -1658,7 +1669,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         hp.tiles_x = mi_cdiv(wd, HT_W);
         hp.tiles_y = mi_cdiv(h, HT_H);
         hp.total_tiles = hp.tiles_x * hp.tiles_y * n;
-        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
+        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act; hp.rnd = mi_tf32_rn_enabled();
         hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
         const size_t b_total = (size_t)9 * hp.chunks * hp.bn * ROW_BYTES;
         const size_t budget = 227 * 1024 - 22 * 1024 - 2048;   // 227 KB per CTA minus static smem (epilogue tiles, bias)
@@ -1719,7 +1730,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         hp.halo_w = halo_pitch();
         hp.halo_bytes = (uint32_t)hp.halo_w * HALO_H * ROW_BYTES;
         hp.halo_stride = (hp.halo_bytes + 1023u) & ~1023u;
-        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
+        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act; hp.rnd = mi_tf32_rn_enabled();
         hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
         const size_t stage_bytes = (size_t)hp.halo_stride + 9 * (size_t)HS_BN * ROW_BYTES;
         const size_t smem = HS_STAGES * stage_bytes + (2 * HS_STAGES + 5) * 8 + 1024;
@@ -1779,7 +1790,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
         int sb = (int)((200 * 1024 - (size_t)hp.sa * hp.halo_stride) / b_stage);
         if (sb > 4) sb = 4;
         hp.sb = sb;
-        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act;
+        hp.act = act; hp.slope = slope; hp.accumulate = accumulate; hp.mask_act = mask_act; hp.rnd = mi_tf32_rn_enabled();
         hp.mask_slope = mask_slope; hp.ldy = ldy; hp.ldmask = ldmask; hp.bias = bias; hp.mask_y = mask_y; hp.y = y;
         if (sb >= 2) {
             const size_t smem = (size_t)hp.sa * hp.halo_stride + (size_t)sb * b_stage + (2 * hp.sa + 2 * sb + 5) * 8 + 1024;
@@ -1812,6 +1823,7 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
     // 128-pixel tiles is bound by how many SMs take part: shrink the channel tile until the grid covers the chip.
     while (p.bn > 64 && (long long)p.tiles_x * p.tiles_y * n * mi_cdiv(cout, p.bn) < num_sms()) p.bn >>= 1;
     p.act = act; p.slope = slope; p.accumulate = accumulate; p.mask_act = mask_act; p.mask_slope = mask_slope;
+    p.rnd = mi_tf32_rn_enabled();
     p.ldy = ldy; p.ldmask = ldmask; p.bias = bias; p.mask_y = mask_y; p.y = y;
     const size_t stage_bytes = (size_t)(BM + p.bn) * ROW_BYTES;
     int stages = (int)((200 * 1024) / stage_bytes);

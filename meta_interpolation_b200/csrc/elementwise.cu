@@ -44,9 +44,21 @@ __device__ __forceinline__ void st4(float* p, const F4& r, int valid, bool vec) 
     }
 }
 
+// store rounded to the TF32 grid (the value is about to be a tensor-core conv operand, see mi_rn_tf32)
+__device__ __forceinline__ void st4(float* p, F4 r, int valid, bool vec, int rnd) {
+    if (rnd) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r.v[q] = mi_rn_tf32(r.v[q]);
+    }
+    st4(p, r, valid, vec);
+}
+// the launchers pass `vec | rnd << 1` in the kernels' `vec` parameter
+#define MI_SPLIT_VEC_RND(vec, rnd) const int rnd = (vec) >> 1; (vec) &= 1
+
 // ----------------------------------------------------------------------------- pooling
 __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
                                     int wd, int c, int vec) {
+    MI_SPLIT_VEC_RND(vec, rnd);
     const int oh = h >> 1, ow = wd >> 1, cg = (c + 3) >> 2;
     const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
@@ -62,7 +74,7 @@ __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int ldx, float*
         F4 o;
 #pragma unroll
         for (int q = 0; q < 4; ++q) o.v[q] = 0.25f * ((a.v[q] + b.v[q]) + (cc.v[q] + d.v[q]));
-        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * g, o, valid, vec);
+        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * g, o, valid, vec, rnd);
     }
 }
 
@@ -166,6 +178,7 @@ struct UpWin { int full_h, full_w, ly0, lx0, hy0, hx0, oh, ow; };
 
 __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
                                      int wd, int c, int align, int vec, UpWin g) {
+    MI_SPLIT_VEC_RND(vec, rnd);
     const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
@@ -187,7 +200,7 @@ __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             o.v[q] = (1.f - ty) * ((1.f - tx) * v00.v[q] + tx * v01.v[q]) + ty * ((1.f - tx) * v10.v[q] + tx * v11.v[q]);
-        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * gi, o, valid, vec);
+        st4(y + ((long long)(nn * oh + oy) * ow + ox) * ldy + 4 * gi, o, valid, vec, rnd);
     }
 }
 
@@ -198,6 +211,7 @@ __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
                                      int accumulate, int n, int h, int wd, int c, int align, int vec, UpWin g,
                                      const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope) {
+    MI_SPLIT_VEC_RND(vec, rnd);
     const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
@@ -246,7 +260,7 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
             for (int q = 0; q < 4; ++q)
                 if (q < valid) acc.v[q] *= mi_act_grad(mp[q], mask_act, mask_slope);
         }
-        st4(d, acc, valid, vec);
+        st4(d, acc, valid, vec, rnd);
     }
 }
 
@@ -277,6 +291,7 @@ __global__ void window_copy_kernel(const float* __restrict__ s, int lds, int sh,
 // ----------------------------------------------------------------------------- simple pointwise
 __global__ void add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
                            float* __restrict__ y, int ldy, long long pixels, int c, int vec) {
+    MI_SPLIT_VEC_RND(vec, rnd);
     const int cg = (c + 3) >> 2;
     const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
@@ -287,7 +302,7 @@ __global__ void add_kernel(const float* __restrict__ a, int lda, const float* __
         F4 o;
 #pragma unroll
         for (int q = 0; q < 4; ++q) o.v[q] = u.v[q] + v.v[q];
-        st4(y + p * ldy + 4 * g, o, valid, vec);
+        st4(y + p * ldy + 4 * g, o, valid, vec, rnd);
     }
 }
 
@@ -311,7 +326,7 @@ __global__ void copy_kernel(const float* __restrict__ s, int lds, float* __restr
 }
 
 __global__ void act_bwd_kernel(float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
-                               float slope, long long pixels, int c, int vec) {
+                               float slope, long long pixels, int c, int vec, int rnd) {
     const int cg = (c + 3) >> 2;
     const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
@@ -322,6 +337,10 @@ __global__ void act_bwd_kernel(float* __restrict__ dy, int lddy, const float* __
         const F4 v = ld4(y + p * ldy + 4 * g, valid, vec);
 #pragma unroll
         for (int q = 0; q < 4; ++q) d.v[q] *= mi_act_grad(v.v[q], act, slope);
+        if (rnd) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d.v[q] = mi_rn_tf32(d.v[q]);
+        }
         st4(dy + p * lddy + 4 * g, d, valid, vec);
     }
 }
@@ -351,7 +370,7 @@ __device__ __forceinline__ int reflect_idx(int i, int nsz) {
 
 __global__ void frames_to_canvas_kernel(const float* __restrict__ f0, const float* __restrict__ f1,
                                         float* __restrict__ canvas, int ldc, int n, int h, int wd, int ch, int cw,
-                                        int pad_top, int pad_left, int mode) {
+                                        int pad_top, int pad_left, int mode, int rnd) {
     const long long total = (long long)n * ch * cw;
     GRID_STRIDE(i, total) {
         long long p = i;
@@ -371,8 +390,9 @@ __global__ void frames_to_canvas_kernel(const float* __restrict__ f0, const floa
         float* d = canvas + i * ldc;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            d[c] = f0[src + c * plane];
-            d[3 + c] = f1[src + c * plane];
+            const float a = f0[src + c * plane], b = f1[src + c * plane];
+            d[c] = rnd ? mi_rn_tf32(a) : a;
+            d[3 + c] = rnd ? mi_rn_tf32(b) : b;
         }
         for (int c = 6; c < ldc; ++c) d[c] = 0.f;
     }
@@ -451,6 +471,74 @@ __global__ void psnr_accumulate_kernel(const float* __restrict__ pred, const flo
         double v = 0.0;
         for (int q = 0; q < TPB / 32; ++q) v += red[q];
         atomicAdd(sq_out, v);
+    }
+}
+
+// ----------------------------------------------------------------------------- SSIM
+// utils.py:195-204 -> pytorch_msssim/__init__.py:19-75 (size_average, val_range=255): both images are quantised to
+// 8 bits, the five 11x11 Gaussian-windowed moments (x, y, xx, yy, xy) are "valid" convolutions, and the SSIM map is
+// averaged over every channel and pixel.  One CTA owns a 32x16 tile of one channel plane: the quantised
+// (32+10)x(16+10) inputs are staged in shared memory once, the window is applied separably (rows, then columns), and
+// the tile's SSIM sum goes to one double atomic.  All inputs are integers <= 255, so the products are exact in fp32.
+constexpr int SS_TX = 32, SS_TY = 16, SS_MAXWIN = 11;
+struct SsimWindow { float g[SS_MAXWIN]; };
+
+__global__ void __launch_bounds__(SS_TX* SS_TY)
+ssim_accumulate_kernel(const float* __restrict__ pred, const float* __restrict__ target, double* __restrict__ sum_out,
+                       int h, int w, int win, SsimWindow wnd, float c1, float c2) {
+    __shared__ float sp[SS_TY + SS_MAXWIN - 1][SS_TX + SS_MAXWIN - 1];
+    __shared__ float st[SS_TY + SS_MAXWIN - 1][SS_TX + SS_MAXWIN - 1];
+    __shared__ float hz[5][SS_TY + SS_MAXWIN - 1][SS_TX];
+    __shared__ double red[SS_TX * SS_TY / 32];
+    const int tid = threadIdx.x;
+    const int ox0 = blockIdx.x * SS_TX, oy0 = blockIdx.y * SS_TY;
+    const int oh = h - win + 1, ow = w - win + 1;
+    const size_t plane = (size_t)blockIdx.z * h * w;
+    const int rows = SS_TY + win - 1, cols = SS_TX + win - 1;
+    for (int i = tid; i < rows * cols; i += SS_TX * SS_TY) {
+        const int r = i / cols, c = i % cols;
+        const int y = oy0 + r, x = ox0 + c;
+        float a = 0.f, b = 0.f;
+        if (y < h && x < w) {
+            a = rintf(fminf(fmaxf(pred[plane + (size_t)y * w + x] * 255.f, 0.f), 255.f));
+            b = rintf(fminf(fmaxf(target[plane + (size_t)y * w + x] * 255.f, 0.f), 255.f));
+        }
+        sp[r][c] = a;
+        st[r][c] = b;
+    }
+    __syncthreads();
+    for (int i = tid; i < rows * SS_TX; i += SS_TX * SS_TY) {
+        const int r = i / SS_TX, c = i % SS_TX;
+        float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+        for (int k = 0; k < win; ++k) {
+            const float g = wnd.g[k], a = sp[r][c + k], b = st[r][c + k];
+            m1 += g * a; m2 += g * b; s11 += g * (a * a); s22 += g * (b * b); s12 += g * (a * b);
+        }
+        hz[0][r][c] = m1; hz[1][r][c] = m2; hz[2][r][c] = s11; hz[3][r][c] = s22; hz[4][r][c] = s12;
+    }
+    __syncthreads();
+    const int tx = tid % SS_TX, ty = tid / SS_TX;
+    double local = 0.0;
+    if (oy0 + ty < oh && ox0 + tx < ow) {
+        float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+        for (int k = 0; k < win; ++k) {
+            const float g = wnd.g[k];
+            m1 += g * hz[0][ty + k][tx]; m2 += g * hz[1][ty + k][tx]; s11 += g * hz[2][ty + k][tx];
+            s22 += g * hz[3][ty + k][tx]; s12 += g * hz[4][ty + k][tx];
+        }
+        const float mu11 = m1 * m1, mu22 = m2 * m2, mu12 = m1 * m2;
+        const float v1 = 2.f * (s12 - mu12) + c2;
+        const float v2 = (s11 - mu11) + (s22 - mu22) + c2;
+        local = (double)(((2.f * mu12 + c1) * v1) / ((mu11 + mu22 + c1) * v2));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((tid & 31) == 0) red[tid >> 5] = local;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int q = 0; q < SS_TX * SS_TY / 32; ++q) v += red[q];
+        atomicAdd(sum_out, v);
     }
 }
 
@@ -568,11 +656,14 @@ static inline bool mi_vec_ok(const void* p, int ld, int c) {
         MI_RETURN_LAST();                                                      \
     } while (0)
 
+static inline int mi_rnd_bit(int round_tf32) { return (round_tf32 && mi_tf32_rn_enabled()) ? 2 : 0; }
+
 extern "C" {
 
-int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t s) {
+int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int round_tf32,
+                    mi_stream_t s) {
     if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
-    const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
+    const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     LAUNCH(avgpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, vec);
 }
 int mi_avgpool2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
@@ -592,16 +683,16 @@ int mi_maxpool2_bwd(const float* x, int ldx, const float* dy, int lddy, float* d
            wd, c);
 }
 int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align,
-                     mi_stream_t s) {
+                     int round_tf32, mi_stream_t s) {
     if (!x || !y) return MI_ERR_BAD_ARG;
-    const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
+    const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
     LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
-                     int align, mi_stream_t s) {
+                     int align, int round_tf32, mi_stream_t s) {
     if (!dy || !dx) return MI_ERR_BAD_ARG;
-    const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
+    const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
     LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
            vec, g, nullptr, 0, 0, 0.f);
@@ -611,18 +702,20 @@ static bool up_window_ok(int h, int wd, int full_h, int full_w, int ly0, int lx0
            ly0 + h <= full_h && lx0 + wd <= full_w && hy0 + oh <= 2 * full_h && hx0 + ow <= 2 * full_w;
 }
 int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, int align,
-                            int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0, mi_stream_t s) {
+                            int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0, int round_tf32,
+                            mi_stream_t s) {
     if (!x || !y || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0)) return MI_ERR_BAD_ARG;
-    const int vec = mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c);
+    const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
     LAUNCH(upsample2_fwd_kernel, (long long)n * oh * ow * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                             int align, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
-                            const float* mask_y, int ldmask, int mask_act, float mask_slope, mi_stream_t s) {
+                            const float* mask_y, int ldmask, int mask_act, float mask_slope, int round_tf32,
+                            mi_stream_t s) {
     if (!dy || !dx || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0) || (mask_y && ldmask < c))
         return MI_ERR_BAD_ARG;
-    const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
+    const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
     LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
            vec, g, mask_y, ldmask, mask_act, mask_slope);
@@ -636,9 +729,10 @@ int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, 
     LAUNCH(window_copy_kernel, (long long)n * h * wd * ((c + 3) / 4), s, src, lds, sh, sw, sy0, sx0, dst, ldd, dh, dw, dy0,
            dx0, n, h, wd, c, accumulate, vec);
 }
-int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, mi_stream_t s) {
+int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, int round_tf32,
+           mi_stream_t s) {
     if (!a || !b || !y) return MI_ERR_BAD_ARG;
-    const int vec = mi_vec_ok(a, lda, c) && mi_vec_ok(b, ldb, c) && mi_vec_ok(y, ldy, c);
+    const int vec = (mi_vec_ok(a, lda, c) && mi_vec_ok(b, ldb, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     LAUNCH(add_kernel, (long long)pixels * ((c + 3) / 4), s, a, lda, b, ldb, y, ldy, (long long)pixels, c, vec);
 }
 int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size_t pixels, int c, mi_stream_t s) {
@@ -647,11 +741,12 @@ int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size
     LAUNCH(copy_kernel, (long long)pixels * ((c + 3) / 4), s, src, lds, dst, ldd, accumulate, (long long)pixels, c, vec);
 }
 int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c,
-               mi_stream_t s) {
+               int round_tf32, mi_stream_t s) {
     if (!dy || !y) return MI_ERR_BAD_ARG;
-    if (act == MI_ACT_NONE) return MI_OK;
+    if (act == MI_ACT_NONE && !round_tf32) return MI_OK;
     const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(y, ldy, c);
-    LAUNCH(act_bwd_kernel, (long long)pixels * ((c + 3) / 4), s, dy, lddy, y, ldy, act, slope, (long long)pixels, c, vec);
+    LAUNCH(act_bwd_kernel, (long long)pixels * ((c + 3) / 4), s, dy, lddy, y, ldy, act, slope, (long long)pixels, c, vec,
+           round_tf32 && mi_tf32_rn_enabled());
 }
 int mi_fill(float* p, float v, size_t count, mi_stream_t s) {
     if (!p) return MI_ERR_BAD_ARG;
@@ -669,10 +764,10 @@ int mi_addcmul(float* y, float a, const float* x1, const float* x2, size_t count
     LAUNCH(addcmul_kernel, (long long)count, s, y, a, x1, x2, (long long)count);
 }
 int mi_frames_to_canvas(const float* f0, const float* f1, float* canvas, int ldc, int n, int h, int wd, int ch, int cw,
-                        int pad_top, int pad_left, int mode, mi_stream_t s) {
+                        int pad_top, int pad_left, int mode, int round_tf32, mi_stream_t s) {
     if (!f0 || !f1 || !canvas || ldc < 6) return MI_ERR_BAD_ARG;
     LAUNCH(frames_to_canvas_kernel, (long long)n * ch * cw, s, f0, f1, canvas, ldc, n, h, wd, ch, cw, pad_top,
-           pad_left, mode);
+           pad_left, mode, mi_rnd_bit(round_tf32) ? 1 : 0);
 }
 int mi_nhwc_window_to_nchw(const float* src, int lds, float* dst, int n, int hs, int ws, int y0, int x0, int h, int wd,
                            int c, mi_stream_t s) {
@@ -692,6 +787,19 @@ int mi_loss_fwd_bwd(const float* pred, const float* target, float* grad, float* 
 int mi_psnr_accumulate(const float* pred, const float* target, double* sq_out, size_t count, mi_stream_t s) {
     if (!pred || !target || !sq_out) return MI_ERR_BAD_ARG;
     LAUNCH(psnr_accumulate_kernel, (long long)count, s, pred, target, sq_out, (long long)count);
+}
+int mi_ssim_accumulate(const float* pred, const float* target, double* sum_out, int c, int h, int w,
+                       const float* window_host, int win, float val_range, mi_stream_t s) {
+    if (!pred || !target || !sum_out || !window_host || win < 1 || win > SS_MAXWIN || h < win || w < win || c < 1)
+        return MI_ERR_BAD_ARG;
+    SsimWindow wnd;
+    for (int i = 0; i < SS_MAXWIN; ++i) wnd.g[i] = i < win ? window_host[i] : 0.f;
+    const float c1 = (float)((0.01 * val_range) * (0.01 * val_range));
+    const float c2 = (float)((0.03 * val_range) * (0.03 * val_range));
+    dim3 grid(mi_cdiv(w - win + 1, SS_TX), mi_cdiv(h - win + 1, SS_TY), c);
+    ssim_accumulate_kernel<<<grid, SS_TX * SS_TY, 0, mi_cs(s)>>>(pred, target, sum_out, h, w, win, wnd, c1, c2);
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
 }
 int mi_inner_update(const float* w_in, const float* g, float* w_out, float* exp_avg, float* exp_avg_sq,
                     const float* lr, int lr_per_element, int lr_stride, int num_step, const int32_t* seg,

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(TX* TY, MINB)
 sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ vert, const float* __restrict__ horiz,
                    int ldf, const float* __restrict__ grad_out, float* __restrict__ g_vert,
                    float* __restrict__ g_horiz, int ldg, int fh, int fw, int gh, int gw, int oh, int ow, int gy0,
-                   int gx0, int iy0, int ix0) {
+                   int gx0, int iy0, int ix0, int rnd) {
     extern __shared__ float smem[];
     constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
     const int n_idx = blockIdx.z;
@@ -216,7 +216,7 @@ sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ ve
             float gv = 0.f;
 #pragma unroll
             for (int cc = 0; cc < C; ++cc) gv = fmaf(go[cc], t[cc], gv);
-            gvs[i] = gv;
+            gvs[i] = rnd ? mi_rn_tf32(gv) : gv;      // (the filter gradients are the next dgrad / wgrad operands)
         }
         if (4 * q + 4 <= F) {
             reinterpret_cast<float4*>(gvp)[q] = make_float4(gvs[0], gvs[1], gvs[2], gvs[3]);
@@ -227,6 +227,10 @@ sepconv_bwd_kernel(const float* __restrict__ frame, const float* __restrict__ ve
         }
     }
     float* ghp = g_horiz + gpix * ldg;
+    if (rnd) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) gh_acc[f] = mi_rn_tf32(gh_acc[f]);
+    }
 #pragma unroll
     for (int g = 0; g < F / 4; ++g)
         reinterpret_cast<float4*>(ghp)[g] =
@@ -268,7 +272,8 @@ __global__ void sepconv_bwd_generic_kernel(const float* __restrict__ frame, cons
                                            const float* __restrict__ horiz, int ldf,
                                            const float* __restrict__ grad_out, float* __restrict__ g_vert,
                                            float* __restrict__ g_horiz, int ldg, int n, int c, int fh, int fw, int gh,
-                                           int gw, int oh, int ow, int gy0, int gx0, int iy0, int ix0, int taps) {
+                                           int gw, int oh, int ow, int gy0, int gx0, int iy0, int ix0, int taps,
+                                           int rnd) {
     // one thread per (pixel, tap index k): computes g_vert[k] and g_horiz[k]
     const long long total = (long long)n * oh * ow * taps;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -295,8 +300,8 @@ __global__ void sepconv_bwd_generic_kernel(const float* __restrict__ frame, cons
             av = fmaf(go, tv, av);
             ah = fmaf(go, th, ah);
         }
-        g_vert[gpix * ldg + kidx] = av;
-        g_horiz[gpix * ldg + kidx] = ah;
+        g_vert[gpix * ldg + kidx] = rnd ? mi_rn_tf32(av) : av;
+        g_horiz[gpix * ldg + kidx] = rnd ? mi_rn_tf32(ah) : ah;
     }
 }
 
@@ -365,7 +370,8 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
 
 int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
                    float* g_vert, float* g_horiz, int ldg, int n, int c, int fh, int fw, int gh, int gw, int oh,
-                   int ow, int gy0, int gx0, int iy0, int ix0, int taps, mi_stream_t stream) {
+                   int ow, int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32, mi_stream_t stream) {
+    const int rnd = (round_tf32 && mi_tf32_rn_enabled()) ? 1 : 0;
     if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !grad_out || !g_vert ||
         !g_horiz || ldg < taps)
         return MI_ERR_BAD_ARG;
@@ -387,17 +393,17 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
         mi_prof_begin(MI_TAG_SEPCONV_BWD, 2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51), 4.0 * px * (4 * 51 + 3 + 3), st);
         if (variant_minb(1) == 1)
             sepconv_bwd_kernel<51, 3, 1><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz,
-                                                                    ldg, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
+                                                                    ldg, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, rnd);
         else
             sepconv_bwd_kernel<51, 3, 2><<<grid, TX * TY, sm, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz,
-                                                                    ldg, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0);
+                                                                    ldg, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, rnd);
         mi_prof_end(st);
     } else {
         const long long total = (long long)n * oh * ow * taps;
         int blocks = mi_cdiv(total, 128);
         if (blocks > 148 * 16) blocks = 148 * 16;
         sepconv_bwd_generic_kernel<<<blocks, 128, 0, st>>>(frame, vert, horiz, ldf, grad_out, g_vert, g_horiz, ldg, n,
-                                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps);
+                                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps, rnd);
     }
     MI_LAUNCHED();
     MI_RETURN_LAST();

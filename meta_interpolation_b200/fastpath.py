@@ -75,7 +75,8 @@ class _Sink:
                 return
             fast = lane.fast
             spec = WgradSpec(w_in=p.w, b_in=p.b, w_out=fast.kernel_view(wn),
-                             b_out=fast.kernel_view(bn) if has_b else None, wt_out=lane.wt_buffer(p.name))
+                             b_out=fast.kernel_view(bn) if has_b else None, wt_out=lane.wt_buffer(p.name),
+                             wr_out=lane.fast_r.kernel_view(wn) if fp.ops.tf32_rn else None)
             if fp.metasgd:
                 spec.mode = WG_SGD_TENSOR
                 spec.lr_w = fp.sys.alpha.kernel_view(wn)
@@ -177,6 +178,8 @@ class _Lane:
         self.stream = torch.cuda.Stream(device=dev) if (cuda and fp.n_lanes > 1) else None
         self.capture_stream = torch.cuda.Stream(device=dev) if cuda else None
         self.fast = Arena(lay, dev)
+        # TF32-rounded shadow of the fast weights: what fprop reads (the exact copy above is what updates read/write)
+        self.fast_r = Arena(lay, dev) if ops.tf32_rn else self.fast
         self.cur_lr = torch.zeros(len(net.param_names), device=dev)
         self.gsum = Arena(lay, dev) if (fp.metasgd and fp.rule == RULE_SGD) else None
         # Adam / Adamax inner rules: gradient of the step in flight and the per-task moments
@@ -245,9 +248,12 @@ class FastPath:
         if a.optimizer not in ('SGD', 'Adam', 'Adamax'):
             return False
         if a.optimizer != 'SGD':
-            # moment rules are graph-captured with an LSLR table (fixed or learnable), and as Meta-SGD + Adamax (the
-            # authors' scripts/run_sepconv.sh operating point); Meta-SGD + Adam fails in the reference for K >= 2 (F11)
-            if a.attenuate or (a.metasgd and a.optimizer != 'Adamax'):
+            # moment rules are graph-captured with an LSLR table (fixed or learnable), as Meta-SGD + Adamax (the
+            # authors' scripts/run_sepconv.sh operating point) and as Meta-SGD + Adam with ONE inner step (the point of
+            # scripts/run_voxelflow.sh and run_cain.sh; the reference itself fails for K >= 2)
+            if a.attenuate:
+                return False
+            if a.metasgd and a.optimizer == 'Adam' and a.number_of_training_steps_per_iter != 1:
                 return False
         if a.attenuate:
             # L2F (reference :231-272) is graph-captured for the SGD inner rule (LSLR fixed / learnable, Meta-SGD,
@@ -293,6 +299,7 @@ class FastPath:
         self.term_names = [k for k, _ in terms]
         self.multi_term = len(terms) > 1
         self.meta_wt = {}
+        self.meta_r = Arena(self.net.layout, self.ops.device) if self.ops.tf32_rn else self.net.arena
         # measured on B200, SepConv 256x448 K=5: 1 lane 22.7, 2 lanes 27.9, 3 lanes 29.2, 4 lanes 30.1 tasks/s
         lanes = os.environ.get('MI_B200_TASK_STREAMS', getattr(a, 'task_streams', 4))
         self.n_lanes = max(1, int(lanes)) if self.ops.name == 'cuda' else 1
@@ -302,6 +309,8 @@ class FastPath:
         """dgrad needs the rotated/transposed filter; for meta-parameters (un-routed tensors in support passes,
         everything at step 0 and in K=0 query passes) it only changes with the outer step, so it is rebuilt once
         per meta-batch into persistent buffers instead of once per pass."""
+        if self.ops.tf32_rn:        # one launch: the rounded shadow of the whole meta arena (what fprop reads)
+            self.ops.round_tf32(self.net.arena.flat, out=self.meta_r.flat)
         for name in self.net.conv_names:
             w = self.net.arena.kernel_view(name + ".weight")
             buf = self.meta_wt.get(name)
@@ -324,9 +333,11 @@ class FastPath:
                     b = fast.kernel_view(name + ".bias") if net._spec[name][4] else None
                     p = ConvParam(name, w, b)
                     p._wt = lane.wt_buffer(name)     # kept current by the fused update of the previous step
+                    p._wr = lane.fast_r.kernel_view(name + ".weight")
                 else:
                     p = net.meta_param(name)
                     p._wt = self.meta_wt.get(name)   # rotated copy refreshed once per meta-batch
+                    p._wr = self.meta_r.kernel_view(name + ".weight")
                 cache[name] = p
             return p
 
@@ -392,6 +403,8 @@ class FastPath:
         if keep:
             # learnable per-step lr: dL/dlr[t][k] = -<dir_k[t], G[t]> with dir_k = (w_k - w_{k+1}) / lr[t][k]
             ops.axpby(lane.fast.flat, -1.0, lane.gsteps[step].flat, 1.0)
+        if ops.tf32_rn:
+            ops.round_tf32(lane.fast.flat, out=lane.fast_r.flat)
         for name in net.conv_names:
             if net.is_routed(name + ".weight"):
                 ops.weight_to_dgrad(lane.fast.kernel_view(name + ".weight"), out=lane.wt_buffer(name))
@@ -424,6 +437,8 @@ class FastPath:
             gamma = (1 - sysm.gamma_mult * sysm.attenuator(emb)).clamp(0, 1).contiguous()
         lane.gamma = gamma
         ops.segment_scale(self.net.arena.flat, gamma, self.seg, None, lane.fast.flat, 1.0, False)
+        if ops.tf32_rn:
+            ops.round_tf32(lane.fast.flat, out=lane.fast_r.flat)
         for name in self.net.conv_names:                   # rotated copies of the attenuated weights for step 0
             if self.net.is_routed(name + ".weight"):
                 ops.weight_to_dgrad(lane.fast.kernel_view(name + ".weight"), out=lane.wt_buffer(name))

@@ -91,9 +91,6 @@ class SceneAdaptiveInterpolation(nn.Module):
         elif args.model == 'voxelflow':  # reference :78-79
             self.mean = torch.FloatTensor([0.5 * 255] * 3).to(self.device).unsqueeze(1).unsqueeze(2)
             self.std = torch.FloatTensor([0.5 * 255] * 3).to(self.device).unsqueeze(1).unsqueeze(2)
-            if args.optimizer == 'Adam':
-                raise NotImplementedError('voxelflow + Adam uses per-group lr/decay policies (reference :134-136) '
-                                          'that the flat outer optimizer does not implement')
 
         self.inner_learning_rate = args.inner_lr
         if self.args.metasgd:
@@ -119,9 +116,21 @@ class SceneAdaptiveInterpolation(nn.Module):
         self._build_flat_groups()
         kind = self.args.optimizer if self.args.optimizer in ('Adam', 'Adamax') else 'SGD'
         betas = (0.9, 0.999) if kind == 'Adamax' else (0.9, 0.99)
-        self.optimizer = FusedOuterOptimizer(self._groups, self.ops, kind, lr=args.outer_lr, betas=betas)
-        # checkpoints exchange optimizer state in the order of the reference's Adam(self.trainable_parameters())
-        self.optimizer.set_reference_order(list(self.trainable_parameters()))
+        if kind == 'Adam' and args.model == 'voxelflow':
+            # reference :133-136: Adam over net.get_optim_policies() with weight_decay and torch's default betas.
+            # The policies hold the backbone's tensors only (conv weights / conv bias / BN scale+shift), so learnable
+            # inner rates, Meta-SGD alphas and the attenuator are NOT stepped at this operating point (the one of the
+            # authors' scripts/run_voxelflow.sh); 'lr_mult' / 'decay_mult' are carried as group keys that stock Adam
+            # never reads: every group steps with the same lr and decay.
+            policies = self.net.get_optim_policies()
+            self.optimizer = FusedOuterOptimizer(self._groups[:1], self.ops, kind, lr=args.outer_lr,
+                                                 betas=(0.9, 0.999), weight_decay=args.weight_decay)
+            self.optimizer.set_reference_order([p for g in policies for p in g['params']], policies)
+            self._groups = self._groups[:1]        # what is stepped is what is all-reduced
+        else:
+            self.optimizer = FusedOuterOptimizer(self._groups, self.ops, kind, lr=args.outer_lr, betas=betas)
+            # checkpoints exchange optimizer state in the order of the reference's Adam(self.trainable_parameters())
+            self.optimizer.set_reference_order(list(self.trainable_parameters()))
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer=self.optimizer, mode='min', factor=0.2,
                                                                     patience=5)
         self.criterion = Loss(args, ops=self.ops)

@@ -50,11 +50,12 @@ def _ldw(w):
 class WgradSpec:
     """What the weight-gradient finishing stage does (include/mi_b200.h MI_WG_*)."""
     __slots__ = ("mode", "scale", "grad_w", "grad_b", "w_in", "b_in", "w_out", "b_out", "lr_w", "lr_b", "gsum_w",
-                 "gsum_b", "wt_out")
+                 "gsum_b", "wt_out", "wr_out")
 
     def __init__(self, mode=WG_STORE, scale=1.0, grad_w=None, grad_b=None, w_in=None, b_in=None, w_out=None,
-                 b_out=None, lr_w=None, lr_b=None, gsum_w=None, gsum_b=None, wt_out=None):
+                 b_out=None, lr_w=None, lr_b=None, gsum_w=None, gsum_b=None, wt_out=None, wr_out=None):
         self.wt_out = wt_out        # SGD modes: also emit the updated weight in the dgrad (rotated) layout
+        self.wr_out = wr_out        # SGD modes: TF32-rounded copy of the updated weight (what the next fprop reads)
         self.mode, self.scale = mode, scale
         self.grad_w, self.grad_b = grad_w, grad_b
         self.w_in, self.b_in, self.w_out, self.b_out = w_in, b_in, w_out, b_out
@@ -73,6 +74,9 @@ class CudaOps:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         env = os.environ.get("MI_B200_ENGINE", "").lower()   # debugging aid: force one conv engine everywhere
         self.engine = {"simt": ENGINE_SIMT, "tc": ENGINE_TC}.get(env, engine)
+        # TF32 operand convention (include/mi_b200.h): with a tensor-core engine every conv operand is kept on the TF32
+        # grid by round-to-nearest at its producer; the exact-fp32 engine rounds nothing
+        self.tf32_rn = self.engine != ENGINE_SIMT and os.environ.get("MI_B200_TF32_RN", "1") != "0"
         self._ws = None
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays (counted at capture time)
 
@@ -159,19 +163,37 @@ class CudaOps:
                    "mi_conv2d_fprop")
         return y
 
-    def weight_to_dgrad(self, w, out=None):
+    def weight_to_dgrad(self, w, out=None, rnd=None):
+        """Rotated / transposed copy of a KRSC weight for dgrad; rounded to the TF32 grid under ``tf32_rn``."""
         cout, k, _, cin = w.shape
         wt = out if out is not None else self.empty_weight(cin, cout, k)
+        rnd = self.tf32_rn if rnd is None else rnd
         _lib.check(self.lib.mi_weight_to_dgrad(w.data_ptr(), _ldw(w), wt.data_ptr(), _ldw(wt), cin, cout, k,
-                                               self._stream()), "mi_weight_to_dgrad")
+                                               1 if rnd else 0, self._stream()), "mi_weight_to_dgrad")
         return wt
+
+    def round_tf32(self, x, out=None):
+        """Round-to-nearest onto the TF32 grid: an NHWC activation / KRSC weight view (rows of the last dim, any row
+        stride) or a flat contiguous buffer; in place unless ``out`` is given."""
+        y = x if out is None else out
+        if x.dim() == 1:
+            c, rows, ldx, ldy = 4, x.numel() // 4, 4, 4
+            assert x.numel() % 4 == 0 and x.is_contiguous() and y.is_contiguous()
+        else:
+            c = x.shape[-1]
+            rows = x.numel() // c
+            ldx, ldy = _ld(x), _ld(y)
+        _lib.check(self.lib.mi_round_tf32(x.data_ptr(), ldx, y.data_ptr(), ldy, c, rows, self._stream()),
+                   "mi_round_tf32")
+        return y
 
     def conv_dgrad(self, dy, w, wt=None, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0, out=None, accumulate=False,
                    engine=None):
         n, h, wd, cout = dy.shape
         k, cin = w.shape[1], w.shape[3]
         if wt is None:
-            wt = self.weight_to_dgrad(w)
+            eng = self.engine if engine is None else engine
+            wt = self.weight_to_dgrad(w, rnd=self.tf32_rn and eng != ENGINE_SIMT)
         dx = out if out is not None else self.empty_act(n, h, wd, cin)
         _lib.check(self.lib.mi_conv2d_dgrad(dy.data_ptr(), _ld(dy), wt.data_ptr(), _ldw(wt), dx.data_ptr(), _ld(dx),
                                             self._p(mask_y), 0 if mask_y is None else _ld(mask_y), mask_act,
@@ -191,15 +213,16 @@ class CudaOps:
                                             spec.mode, float(spec.scale), p(spec.grad_w), p(spec.grad_b), p(spec.w_in),
                                             p(spec.b_in), p(spec.w_out), p(spec.b_out), p(spec.lr_w), p(spec.lr_b),
                                             p(spec.gsum_w), p(spec.gsum_b), p(spec.wt_out),
-                                            0 if spec.wt_out is None else _ldw(spec.wt_out), ws.data_ptr(),
+                                            0 if spec.wt_out is None else _ldw(spec.wt_out), p(spec.wr_out),
+                                            ws.data_ptr(),
                                             ws.numel(), eng, self._stream()), "mi_conv2d_wgrad")
 
     # ------------------------------------------------------------------ resampling / pointwise
-    def avgpool_fwd(self, x):
+    def avgpool_fwd(self, x, rnd=False):
         n, h, w, c = x.shape
         y = self.empty_act(n, h // 2, w // 2, c)
-        _lib.check(self.lib.mi_avgpool2_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c, self._stream()),
-                   "mi_avgpool2_fwd")
+        _lib.check(self.lib.mi_avgpool2_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c, int(rnd),
+                                            self._stream()), "mi_avgpool2_fwd")
         return y
 
     def avgpool_bwd(self, dy, dx, accumulate):
@@ -219,39 +242,41 @@ class CudaOps:
         _lib.check(self.lib.mi_maxpool2_bwd(x.data_ptr(), _ld(x), dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx),
                                             int(accumulate), n, h, w, c, self._stream()), "mi_maxpool2_bwd")
 
-    def upsample_fwd(self, x, align_corners, out=None):
+    def upsample_fwd(self, x, align_corners, out=None, rnd=False):
         n, h, w, c = x.shape
         y = out if out is not None else self.empty_act(n, 2 * h, 2 * w, c)
         _lib.check(self.lib.mi_upsample2_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c,
-                                             int(align_corners), self._stream()), "mi_upsample2_fwd")
+                                             int(align_corners), int(rnd), self._stream()), "mi_upsample2_fwd")
         return y
 
-    def upsample_bwd(self, dy, dx, align_corners, accumulate, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0):
+    def upsample_bwd(self, dy, dx, align_corners, accumulate, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0,
+                     rnd=False):
         n, h, w, c = dx.shape
         if mask_y is not None:   # fused activation derivative: the plain upsample is the window that covers everything
             return self.upsample_window_bwd(dy, dx, align_corners, accumulate, (h, w), (0, 0), (0, 0), mask_y,
-                                            mask_act, mask_slope)
+                                            mask_act, mask_slope, rnd=rnd)
         _lib.check(self.lib.mi_upsample2_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n, h, w,
-                                             c, int(align_corners), self._stream()), "mi_upsample2_bwd")
+                                             c, int(align_corners), int(rnd), self._stream()), "mi_upsample2_bwd")
 
-    def upsample_window_fwd(self, x, align_corners, full_hw, lo_origin, hi_origin, hi_hw):
+    def upsample_window_fwd(self, x, align_corners, full_hw, lo_origin, hi_origin, hi_hw, rnd=False):
         """x = rows/cols [lo_origin, +x.shape) of a full_hw grid -> rows/cols [hi_origin, +hi_hw) of its x2 upsampling."""
         n, h, w, c = x.shape
         y = self.empty_act(n, hi_hw[0], hi_hw[1], c)
         _lib.check(self.lib.mi_upsample2_window_fwd(x.data_ptr(), _ld(x), y.data_ptr(), _ld(y), n, h, w, c,
                                                     int(align_corners), full_hw[0], full_hw[1], lo_origin[0],
                                                     lo_origin[1], hi_hw[0], hi_hw[1], hi_origin[0], hi_origin[1],
-                                                    self._stream()), "mi_upsample2_window_fwd")
+                                                    int(rnd), self._stream()), "mi_upsample2_window_fwd")
         return y
 
     def upsample_window_bwd(self, dy, dx, align_corners, accumulate, full_hw, lo_origin, hi_origin, mask_y=None,
-                            mask_act=ACT_NONE, mask_slope=0.0):
+                            mask_act=ACT_NONE, mask_slope=0.0, rnd=False):
         n, h, w, c = dx.shape
         _lib.check(self.lib.mi_upsample2_window_bwd(dy.data_ptr(), _ld(dy), dx.data_ptr(), _ld(dx), int(accumulate), n,
                                                     h, w, c, int(align_corners), full_hw[0], full_hw[1], lo_origin[0],
                                                     lo_origin[1], dy.shape[1], dy.shape[2], hi_origin[0], hi_origin[1],
                                                     self._p(mask_y), 0 if mask_y is None else _ld(mask_y), mask_act,
-                                                    float(mask_slope), self._stream()), "mi_upsample2_window_bwd")
+                                                    float(mask_slope), int(rnd), self._stream()),
+                   "mi_upsample2_window_bwd")
 
     def window_copy(self, src, src_origin, dst, dst_origin, hw, accumulate=False):
         """dst[:, dy0:dy0+h, dx0:dx0+w] (+)= src[:, sy0:sy0+h, sx0:sx0+w] between two NHWC buffers."""
@@ -261,11 +286,11 @@ class CudaOps:
                                            dst.data_ptr(), _ld(dst), dh, dw, dst_origin[0], dst_origin[1], n, hw[0],
                                            hw[1], c, int(accumulate), self._stream()), "mi_window_copy")
 
-    def add(self, a, b, out=None):
+    def add(self, a, b, out=None, rnd=False):
         n, h, w, c = a.shape
         y = out if out is not None else self.empty_act(n, h, w, c)
         _lib.check(self.lib.mi_add(a.data_ptr(), _ld(a), b.data_ptr(), _ld(b), y.data_ptr(), _ld(y), n * h * w, c,
-                                   self._stream()), "mi_add")
+                                   int(rnd), self._stream()), "mi_add")
         return y
 
     def copy(self, src, dst, accumulate=False):
@@ -273,10 +298,10 @@ class CudaOps:
         _lib.check(self.lib.mi_copy(src.data_ptr(), _ld(src), dst.data_ptr(), _ld(dst), int(accumulate), n * h * w, c,
                                     self._stream()), "mi_copy")
 
-    def act_bwd(self, dy, y, act, slope=0.0):
+    def act_bwd(self, dy, y, act, slope=0.0, rnd=False):
         n, h, w, c = y.shape
         _lib.check(self.lib.mi_act_bwd(dy.data_ptr(), _ld(dy), y.data_ptr(), _ld(y), act, float(slope), n * h * w, c,
-                                       self._stream()), "mi_act_bwd")
+                                       1 if rnd else 0, self._stream()), "mi_act_bwd")
 
     def fill(self, t, value):
         assert t.is_contiguous()
@@ -445,13 +470,14 @@ class CudaOps:
                                                   float(scale), self._stream()), "mi_interior_bcast_add")
 
     # ------------------------------------------------------------------ frames in / prediction out
-    def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode):
+    def frames_to_canvas(self, f0, f1, ch, cw, pad_top, pad_left, mode, rnd=False):
         """f0, f1: NCHW [n,3,h,w] contiguous -> NHWC canvas [n,ch,cw,6] (ld 8)."""
         n, c, h, w = f0.shape
         assert c == 3 and f0.is_contiguous() and f1.is_contiguous()
         y = self.empty_act(n, ch, cw, 6)
         _lib.check(self.lib.mi_frames_to_canvas(f0.data_ptr(), f1.data_ptr(), y.data_ptr(), _ld(y), n, h, w, ch, cw,
-                                                pad_top, pad_left, mode, self._stream()), "mi_frames_to_canvas")
+                                                pad_top, pad_left, mode, int(rnd), self._stream()),
+                   "mi_frames_to_canvas")
         return y
 
     def nhwc_window_to_nchw(self, src, y0, x0, h, w):
@@ -480,15 +506,15 @@ class CudaOps:
                                            self._stream()), "mi_sepconv_fwd")
         return out
 
-    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0):
+    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0, rnd=False):
         n, c, fh, fw = frame.shape
         _, gh, gw, taps = vert.shape
         oh, ow = grad_out.shape[2], grad_out.shape[3]
         assert grad_out.is_contiguous() and _ld(g_vert) == _ld(g_horiz) and _ld(vert) == _ld(horiz)
         _lib.check(self.lib.mi_sepconv_bwd(frame.data_ptr(), vert.data_ptr(), horiz.data_ptr(), _ld(vert),
                                            grad_out.data_ptr(), g_vert.data_ptr(), g_horiz.data_ptr(), _ld(g_vert), n,
-                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps, self._stream()),
-                   "mi_sepconv_bwd")
+                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps, int(rnd),
+                                           self._stream()), "mi_sepconv_bwd")
 
     # ------------------------------------------------------------------ warp
     def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0, out=None):
@@ -515,6 +541,16 @@ class CudaOps:
         assert pred.is_contiguous() and target.is_contiguous() and sq_out.dtype == torch.float64
         _lib.check(self.lib.mi_psnr_accumulate(pred.data_ptr(), target.data_ptr(), sq_out.data_ptr(), pred.numel(),
                                                self._stream()), "mi_psnr_accumulate")
+
+    def ssim_accumulate(self, pred, target, window, sum_out, val_range=255.0):
+        """sum_out[0] (double) += sum of the SSIM map of two [c,h,w] images in [0,1] (8-bit quantised in the kernel);
+        ``window`` = normalised 1-D Gaussian (CPU float32 tensor, <= 11 taps)."""
+        c, h, w = pred.shape
+        assert pred.is_contiguous() and target.is_contiguous() and sum_out.dtype == torch.float64
+        assert window.device.type == "cpu" and window.dtype == torch.float32 and window.is_contiguous()
+        _lib.check(self.lib.mi_ssim_accumulate(pred.data_ptr(), target.data_ptr(), sum_out.data_ptr(), c, h, w,
+                                               window.data_ptr(), window.numel(), float(val_range), self._stream()),
+                   "mi_ssim_accumulate")
 
     def septuplet_prepare(self, src, y0, x0, reversed_, h, w, bgr=True, div255=True, mean=None, std=None):
         """Decoded uint8 frames [tasks,frames,H,W,3] -> float [frames,tasks,3,h,w]: crop, temporal flip, channel order,

@@ -57,11 +57,15 @@ class FusedOuterOptimizer(torch.optim.Optimizer):
     # ``trainable_parameters()`` (utils.py:34-75, experiment_builder.py save/load).  The moments here live in flat
     # buffers, so ``state_dict`` / ``load_state_dict`` translate to and from the stock per-parameter layout
     # (``state[i] = {step, exp_avg, exp_avg_sq | exp_inf}`` in the order of ``ref_order``).
-    def set_reference_order(self, params):
-        """Parameter order of the reference's optimizer (``nn.Module.parameters()`` order of its system)."""
+    def set_reference_order(self, params, policies=None):
+        """Parameter order of the reference's optimizer (``nn.Module.parameters()`` order of its system).
+        ``policies``: the reference's list of param-group dicts when it builds its optimizer from several groups
+        (voxelflow's ``get_optim_policies``); their extra keys and sizes shape ``state_dict()['param_groups']``."""
         own = {id(p) for g in self.flat_groups for p, _ in g.members}
         assert {id(p) for p in params} == own, "reference order must list exactly the optimised parameters"
         self._ref_order = list(params)
+        self._ref_policies = None if policies is None else [
+            ({k: v for k, v in g.items() if k != 'params'}, len(g['params'])) for g in policies]
 
     def _moment_views(self):
         """{id(param): (exp_avg view, second-moment view)} shaped like the parameter (views of the flat buffers)."""
@@ -84,8 +88,19 @@ class FusedOuterOptimizer(torch.optim.Optimizer):
                 state[i] = {"step": torch.tensor(float(self._step)), "exp_avg": m.detach().clone().contiguous(),
                             second: v.detach().clone().contiguous()}
         hp = dict(self.param_groups[0])
-        hp["params"] = list(range(len(order)))
-        return {"state": state, "param_groups": [hp], "fused_step": self._step}
+        policies = getattr(self, "_ref_policies", None)
+        if policies is None:
+            hp["params"] = list(range(len(order)))
+            groups = [hp]
+        else:
+            groups, first = [], 0
+            for extra, count in policies:
+                g = dict(hp)
+                g.update(extra)
+                g["params"] = list(range(first, first + count))
+                groups.append(g)
+                first += count
+        return {"state": state, "param_groups": groups, "fused_step": self._step}
 
     def load_state_dict(self, state_dict):
         order = getattr(self, "_ref_order", None) or [p for g in self.flat_groups for p, _ in g.members]

@@ -133,7 +133,8 @@ class MetaNetwork(MetaBackbone):
         from ..tape import Var
         n, _, height, width = frame0.shape
         ch, cw = canvas_size(height, width)
-        canvas = Var(t.ops.frames_to_canvas(frame0, frame1, ch, cw, 25, 25, 0), requires_grad=False)
+        canvas = Var(t.ops.frames_to_canvas(frame0, frame1, ch, cw, 25, 25, 0, rnd=t.ops.tf32_rn), requires_grad=False)
+        canvas.clean = t.ops.tf32_rn
 
         c1 = self._basic(t, canvas, "moduleConv1")
         c2 = self._basic(t, t.avgpool(c1), "moduleConv2")

@@ -14,7 +14,7 @@ from .ops import ACT_NONE
 
 class Var:
     """An NHWC activation (or NCHW image for frames/predictions) plus its gradient slot."""
-    __slots__ = ("data", "grad", "requires_grad", "act", "slope", "consumers", "grad_masked")
+    __slots__ = ("data", "grad", "requires_grad", "act", "slope", "consumers", "grad_masked", "clean", "grad_clean")
 
     def __init__(self, data, requires_grad=True):
         self.data = data
@@ -24,20 +24,34 @@ class Var:
         self.slope = 0.0
         self.consumers = 0         # ops reading this Var (decides whether the act mask can be fused)
         self.grad_masked = False   # True once .grad already is the gradient w.r.t. the PRE-activation
+        self.clean = False         # True when .data is known to lie on the TF32 grid (its producer stored it rounded)
+        self.grad_clean = False    # True when .grad was written once, rounded, by a kernel that takes the flag
 
 
 class ConvParam:
-    """Weights of one conv as the kernels see them (KRSC weight view, bias vector)."""
-    __slots__ = ("name", "w", "b", "_wt")
+    """Weights of one conv as the kernels see them: ``w`` the exact fp32 KRSC view (what updates read and write),
+    ``wr`` the copy fprop reads and ``wt`` the rotated copy dgrad reads -- both rounded to the TF32 grid when the
+    operator table follows the TF32 operand convention (include/mi_b200.h), else ``wr`` is ``w`` itself."""
+    __slots__ = ("name", "w", "b", "_wt", "_wr")
 
     def __init__(self, name, w, b):
         self.name, self.w, self.b = name, w, b
         self._wt = None
+        self._wr = None
 
     def wt(self, ops):
         if self._wt is None:
             self._wt = ops.weight_to_dgrad(self.w)
         return self._wt
+
+    def wr(self, ops):
+        if self._wr is None:
+            if not ops.tf32_rn:
+                self._wr = self.w
+            else:
+                cout, k, _, cin = self.w.shape
+                self._wr = ops.round_tf32(self.w, out=ops.empty_weight(cout, cin, k))
+        return self._wr
 
 
 class Tape:
@@ -65,21 +79,40 @@ class Tape:
             fn()
         self.nodes = []
 
+    def _on_grid(self, x):
+        """A conv is about to read ``x`` as a tensor-core operand: put it on the TF32 grid (in place, once) unless a
+        conv epilogue already did.  Rounding is idempotent, so other readers of the buffer are unaffected beyond the
+        rounding itself."""
+        if self.ops.tf32_rn and not x.clean:
+            self.ops.round_tf32(x.data)
+            x.clean = True
+
+    def _grad_on_grid(self, y, act, slope):
+        """``y.grad`` is about to be the operand of this conv's dgrad / wgrad.  Born masked from the consumer conv's
+        dgrad epilogue it already is on the grid; otherwise the (possibly trivial) activation-derivative pass rounds
+        it on the way."""
+        ops = self.ops
+        if y.grad_masked or (act == ACT_NONE and y.grad_clean):
+            return
+        if act != ACT_NONE or ops.tf32_rn:
+            ops.act_bwd(y.grad, y.data, act, slope, rnd=ops.tf32_rn)
+
     # ------------------------------------------------------------------ ops
     def conv(self, x, name, act=ACT_NONE, slope=0.0, out=None):
         ops = self.ops
         p = self.params(name)
         k = p.w.shape[1]
         x.consumers += 1
-        y = Var(ops.conv_fprop(x.data, p.w, p.b, act, slope, out=out))
+        self._on_grid(x)
+        y = Var(ops.conv_fprop(x.data, p.wr(ops), p.b, act, slope, out=out))
         y.act, y.slope = act, slope
+        y.clean = ops.tf32_rn
 
         def bwd():
             dy = y.grad
             if dy is None:
                 return
-            if act != ACT_NONE and not y.grad_masked:
-                ops.act_bwd(dy, y.data, act, slope)
+            self._grad_on_grid(y, act, slope)
             # dgrad first: a fused-update sink may overwrite p.w in place, and the rotated copy
             # p.wt must come from the weights this forward pass actually used
             if x.requires_grad:
@@ -101,7 +134,8 @@ class Tape:
     def avgpool(self, x):
         ops = self.ops
         x.consumers += 1
-        y = Var(ops.avgpool_fwd(x.data))
+        y = Var(ops.avgpool_fwd(x.data, rnd=ops.tf32_rn))
+        y.clean = ops.tf32_rn
 
         def bwd():
             if y.grad is None or not x.requires_grad:
@@ -120,6 +154,7 @@ class Tape:
         ops = self.ops
         x.consumers += 1
         y = Var(ops.maxpool_fwd(x.data))
+        y.clean = x.clean          # a maximum of grid values is a grid value
 
         def bwd():
             if y.grad is None or not x.requires_grad:
@@ -137,7 +172,8 @@ class Tape:
     def upsample(self, x, align_corners, out=None):
         ops = self.ops
         x.consumers += 1
-        y = Var(ops.upsample_fwd(x.data, align_corners, out=out))
+        y = Var(ops.upsample_fwd(x.data, align_corners, out=out, rnd=ops.tf32_rn))
+        y.clean = ops.tf32_rn
 
         def bwd():
             if y.grad is None or not x.requires_grad:
@@ -147,8 +183,8 @@ class Tape:
                 if x.consumers == 1 and x.act != ACT_NONE:
                     # sole consumer of an activated conv output: its activation derivative is applied here, so
                     # x.grad is born as the pre-activation gradient and the conv skips its act_bwd pass
-                    ops.upsample_bwd(y.grad, x.grad, align_corners, False, x.data, x.act, x.slope)
-                    x.grad_masked = True
+                    ops.upsample_bwd(y.grad, x.grad, align_corners, False, x.data, x.act, x.slope, rnd=ops.tf32_rn)
+                    x.grad_masked = True       # (and on the TF32 grid: the producing conv's dgrad / wgrad read it next)
                 else:
                     ops.upsample_bwd(y.grad, x.grad, align_corners, False)
             else:
@@ -166,6 +202,7 @@ class Tape:
         buf = ops.empty_act(n, h, w, c)
         ops.window_copy(x.data, (y0, x0), buf, (0, 0), (h, w))
         y = Var(buf, requires_grad=x.requires_grad)
+        y.clean = x.clean
 
         def bwd():
             g = y.grad
@@ -183,7 +220,8 @@ class Tape:
         """x2 bilinear upsample of a window of a larger grid, evaluated only on a window of the result."""
         ops = self.ops
         x.consumers += 1
-        y = Var(ops.upsample_window_fwd(x.data, align_corners, full_hw, lo_origin, hi_origin, hi_hw))
+        y = Var(ops.upsample_window_fwd(x.data, align_corners, full_hw, lo_origin, hi_origin, hi_hw, rnd=ops.tf32_rn))
+        y.clean = ops.tf32_rn
 
         def bwd():
             if y.grad is None or not x.requires_grad:
@@ -192,7 +230,7 @@ class Tape:
                 x.grad = ops.empty_like_act(x.data)
                 if x.consumers == 1 and x.act != ACT_NONE:
                     ops.upsample_window_bwd(y.grad, x.grad, align_corners, False, full_hw, lo_origin, hi_origin, x.data,
-                                            x.act, x.slope)
+                                            x.act, x.slope, rnd=ops.tf32_rn)
                     x.grad_masked = True
                 else:
                     ops.upsample_window_bwd(y.grad, x.grad, align_corners, False, full_hw, lo_origin, hi_origin)
@@ -207,7 +245,8 @@ class Tape:
         ops = self.ops
         a.consumers += 1
         b.consumers += 1
-        y = Var(ops.add(a.data, b.data))
+        y = Var(ops.add(a.data, b.data, rnd=ops.tf32_rn))
+        y.clean = ops.tf32_rn
 
         def bwd():
             g = y.grad
@@ -236,6 +275,10 @@ class Tape:
         y = Var(buf)
         for v, _, _ in parts:
             v.consumers += 1
+        # on the TF32 grid when every slice was stored rounded and the slices tile the buffer (constants copied in by
+        # `concat` are not tracked: their presence leaves the flag off)
+        covered = sum(c1 - c0 for _, c0, c1 in parts) == buf.shape[-1]
+        y.clean = covered and all(v.clean for v, _, _ in parts)
 
         def bwd():
             g = y.grad
@@ -270,7 +313,9 @@ class Tape:
             assert vert.grad is None and horiz.grad is None, "sepconv filters have a single consumer"
             vert.grad = ops.zeros_act(n, gh, gw, taps)
             horiz.grad = ops.zeros_act(n, gh, gw, taps)
-            ops.sepconv_bwd(frame, vert.data, horiz.data, g, vert.grad, horiz.grad, gy0, gx0, iy0, ix0)
+            ops.sepconv_bwd(frame, vert.data, horiz.data, g, vert.grad, horiz.grad, gy0, gx0, iy0, ix0,
+                            rnd=ops.tf32_rn)
+            vert.grad_clean = horiz.grad_clean = ops.tf32_rn     # (zero outside the window is on the grid too)
             y.grad = None
 
         self.nodes.append(bwd)
@@ -534,16 +579,17 @@ class Tape:
         k = p.w.shape[1]
         x.consumers += 1
         ops.ring_fix(x.data, ring_mode)
-        y = Var(ops.conv_fprop(x.data, p.w, p.b, act, slope))
+        self._on_grid(x)
+        y = Var(ops.conv_fprop(x.data, p.wr(ops), p.b, act, slope))
         y.act, y.slope = act, slope
+        y.clean = ops.tf32_rn
 
         def bwd():
             dy = y.grad
             if dy is None:
                 return
             ops.ring_fix(dy, ops.RING_ZERO)      # ring outputs are never consumed
-            if act != ACT_NONE and not y.grad_masked:
-                ops.act_bwd(dy, y.data, act, slope)
+            self._grad_on_grid(y, act, slope)
             if x.requires_grad:
                 if x.consumers == 1 and x.act != ACT_NONE and x.grad is None:
                     g = ops.conv_dgrad(dy, p.w, wt=p.wt(ops), mask_y=x.data, mask_act=x.act, mask_slope=x.slope)

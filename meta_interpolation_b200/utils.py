@@ -72,13 +72,38 @@ def ssim(img1, img2, window_size=11, val_range=255):
     return (((2 * mu1_mu2 + c1) * v1) / ((mu1_sq + mu2_sq + c1) * v2)).mean()
 
 
+_WINDOWS = {}
+
+
+def gaussian_1d(size):
+    """pytorch_msssim/__init__.py:7-9: normalised float32 Gaussian (sigma 1.5) of ``size`` taps, on the host."""
+    g = _WINDOWS.get(size)
+    if g is None:
+        g = torch.Tensor([math.exp(-(x - size // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(size)])
+        g = (g / g.sum()).contiguous()
+        _WINDOWS[size] = g
+    return g
+
+
+def calc_metrics_device(ops, im_pred, im_gt):
+    """PSNR and SSIM of one [3,H,W] pair with two kernels and ONE host read (utils.py:195-204)."""
+    pred, gt = im_pred.detach().contiguous(), im_gt.detach().contiguous()
+    c, h, w = pred.shape
+    win = min(11, h, w)
+    acc = torch.zeros(2, dtype=torch.float64, device=pred.device)
+    ops.psnr_accumulate(pred, gt, acc[0:1])
+    ops.ssim_accumulate(pred, gt, gaussian_1d(win), acc[1:2], 255.0)
+    sq, ss = acc.tolist()
+    psnr = -10 * math.log10(sq / pred.numel() + 1e-8)
+    return psnr, torch.tensor(ss / (c * (h - win + 1) * (w - win + 1)), dtype=torch.float32, device=pred.device)
+
+
 def calc_metrics(im_pred, im_gt, ops=None):
     """reference utils.py:195-204 -> (psnr, ssim) for one [3,H,W] pair in [0,1]."""
     if ops is not None and ops.name == "cuda":
-        psnr = calc_psnr_device(ops, im_pred.detach(), im_gt.detach())
-    else:
-        d = (quantize(im_pred.detach(), 1.) - quantize(im_gt.detach(), 1.)).div(255)
-        psnr = -10 * math.log10(float(d.pow(2).mean()) + 1e-8)
+        return calc_metrics_device(ops, im_pred, im_gt)
+    d = (quantize(im_pred.detach(), 1.) - quantize(im_gt.detach(), 1.)).div(255)
+    psnr = -10 * math.log10(float(d.pow(2).mean()) + 1e-8)
     s = ssim(quantize(im_pred.detach(), 1.).unsqueeze(0), quantize(im_gt.detach(), 1.).unsqueeze(0), val_range=255)
     return psnr, s
 

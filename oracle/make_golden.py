@@ -38,6 +38,10 @@ CASES = {
     # BASELINE configs[0]: voxelflow, batch 1, 128x128, 1 inner step, CPU-runnable
     "voxelflow_lslr_sgd_k1_mse": (dict(model="voxelflow", loss="1*MSE", optimizer="SGD",
                                        number_of_training_steps_per_iter=1), 128, 1),
+    # the operating point of the authors' scripts/run_voxelflow.sh: Meta-SGD with the Adam inner rule, K=1, and the
+    # outer Adam built from net.get_optim_policies() with weight decay (meta_learning_system.py:133-136)
+    "voxelflow_metasgd_adam_k1": (dict(model="voxelflow", loss="1*MSE", optimizer="Adam", metasgd=True,
+                                       number_of_training_steps_per_iter=1), 64, 2),
     "voxelflow_lslr_sgd_k2_ragged": (dict(model="voxelflow", loss="1*L1", optimizer="SGD",
                                           number_of_training_steps_per_iter=2), (72, 88), 1),
     # configs[2] in miniature: superslomo Meta-SGD (SGD rule), K=2
@@ -235,7 +239,8 @@ def run_case(name, over, size, batch):
                             outer_lr=args.outer_lr,
                             learnable_lr=args.learnable_per_layer_per_step_inner_loop_learning_rate, loss=args.loss,
                             attenuate=args.attenuate, use_msl=args.use_multi_step_loss_optimization,
-                            msl_epochs=args.multi_step_loss_num_epochs, attenuator_state=att_state, vgg_state=vgg_state)
+                            msl_epochs=args.multi_step_loss_num_epochs, attenuator_state=att_state, vgg_state=vgg_state,
+                            weight_decay=args.weight_decay)
     record = {}
     o_loss, o_preds, o_psnrs, o_grads = ora.run_train_iter(frames, 0, record=record)
 
@@ -269,7 +274,7 @@ def run_case(name, over, size, batch):
             "number_of_training_steps_per_iter", "number_of_evaluation_steps_per_iter",
             "learnable_per_layer_per_step_inner_loop_learning_rate", "use_multi_step_loss_optimization",
             "multi_step_loss_num_epochs", "second_order", "first_order_to_second_order_epoch",
-            "enable_inner_loop_optimizable_bn_params")},
+            "enable_inner_loop_optimizable_bn_params", "weight_decay")},
         frames=torch.stack(frames) if frames_u8 is None else None, frames_u8=frames_u8,
         loss=float(losses["loss"]), psnr=float(metrics["psnr"].avg), ssim=float(metrics["ssim"].avg),
         preds=torch.cat([p.detach() for p in preds]),
@@ -277,6 +282,7 @@ def run_case(name, over, size, batch):
         init_digest={k: digest(v)[0] for k, v in init.items()},
         grad_digest={k[4:]: digest(v) for k, v in grads_ref.items() if k.startswith("net.") and v is not None},
         post_digest={k: digest(v) for k, v in post.items()},
+        delta_digest={k: digest(post[k] - init[k]) for k in post},      # the outer step itself (post - init)
         lr_grads={k: (None if v is None else v.clone()) for k, v in grads_ref.items()
                   if k.startswith("inner_loop_optimizer.") and v is not None and v.numel() <= 64},
         oracle_vs_reference_post_step_maxabs=pin,

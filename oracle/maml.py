@@ -71,7 +71,7 @@ class OracleSystem:
 
     def __init__(self, model, params, *, optimizer="SGD", metasgd=False, num_steps=1, inner_lr=1e-5,
                  outer_lr=1e-5, learnable_lr=False, loss="1*L1", attenuate=False, use_msl=False,
-                 msl_epochs=1, attenuator_state=None, vgg_state=None):
+                 msl_epochs=1, attenuator_state=None, vgg_state=None, weight_decay=1e-4):
         self.model = model
         self.vgg_state = vgg_state      # torchvision vgg16 conv4_3 weights for the Super loss
         self.backbone = bb.BACKBONES[model]
@@ -99,7 +99,11 @@ class OracleSystem:
             self.gamma_mult = nn.Parameter(torch.zeros(1))
         # outer optimizer, meta_learning_system.py:132-143 (same flag as the inner rule, Q6)
         tp = self.trainable_parameters()
-        if optimizer == "Adam":
+        if optimizer == "Adam" and model == "voxelflow":
+            # :133-136: Adam over net.get_optim_policies() -- the backbone's tensors only, torch's default betas,
+            # weight_decay; the groups' lr_mult / decay_mult keys are never read by torch.optim.Adam
+            self.optimizer = torch.optim.Adam(list(self.params.values()), lr=outer_lr, weight_decay=weight_decay)
+        elif optimizer == "Adam":
             self.optimizer = torch.optim.Adam(tp, lr=outer_lr, betas=(0.9, 0.99))
         elif optimizer == "Adamax":
             self.optimizer = torch.optim.Adamax(tp, lr=outer_lr, betas=(0.9, 0.999))

@@ -61,10 +61,27 @@ def act_grad(y, act, slope):
 class RefOps:
     name = "ref"
 
-    def __init__(self, device="cpu", dtype=torch.float32):
+    def __init__(self, device="cpu", dtype=torch.float32, tf32_rn=False):
         self.device = torch.device(device)
         self.dtype = dtype
         self._launches = 0
+        # exact fp32 arithmetic by default; tf32_rn=True only exercises the host logic of the TF32 operand convention
+        # (rounded weight copies, rounding passes) -- the convolutions themselves stay exact
+        self.tf32_rn = tf32_rn
+        # producers that can store their result on the TF32 grid (rnd=True), like their CUDA counterparts
+        for name, outs in (("avgpool_fwd", None), ("upsample_fwd", None), ("upsample_window_fwd", None),
+                           ("add", None), ("frames_to_canvas", None), ("sepconv_bwd", (4, 5)),
+                           ("upsample_bwd", (1,)), ("upsample_window_bwd", (1,))):
+            setattr(self, name, self._rounding(getattr(self, name), outs))
+
+    def _rounding(self, fn, outs):
+        def wrapped(*a, rnd=False, **k):
+            y = fn(*a, **k)
+            if rnd:
+                for t in ([y] if outs is None else [a[i] for i in outs]):
+                    self.round_tf32(t)
+            return y
+        return wrapped
 
     def launch_count(self):
         return self._launches
@@ -99,11 +116,21 @@ class RefOps:
         out.copy_(y)
         return out
 
-    def weight_to_dgrad(self, w, out=None):
+    def weight_to_dgrad(self, w, out=None, rnd=None):
         cout, k, _, cin = w.shape
         wt = out if out is not None else self.empty_weight(cin, cout, k)
         wt.copy_(torch.flip(w, dims=(1, 2)).permute(3, 1, 2, 0))
+        if self.tf32_rn if rnd is None else rnd:
+            self.round_tf32(wt)
         return wt
+
+    def round_tf32(self, x, out=None):
+        """cvt.rna.tf32.f32: round to nearest (ties away from zero) onto the 10-bit-mantissa grid."""
+        y = x if out is None else out
+        i = x.contiguous().view(torch.int32)
+        r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+        y.copy_(torch.where(torch.isfinite(x), r, x))
+        return y
 
     def conv_dgrad(self, dy, w, wt=None, mask_y=None, mask_act=ACT_NONE, mask_slope=0.0, out=None, accumulate=False,
                    engine=None):
@@ -138,8 +165,11 @@ class RefOps:
             lr_w = spec.lr_w.reshape(-1)[0] if spec.mode == WG_SGD_SCALAR else spec.lr_w
             new_w = spec.w_in - lr_w * gw
             spec.w_out.copy_(new_w)
+            rounded = getattr(spec, "wr_out", None) is not None
+            if rounded:
+                self.round_tf32(new_w.contiguous(), out=spec.wr_out)
             if getattr(spec, "wt_out", None) is not None:
-                self.weight_to_dgrad(new_w, out=spec.wt_out)
+                self.weight_to_dgrad(new_w, out=spec.wt_out, rnd=rounded)
             if spec.grad_w is not None:
                 spec.grad_w.copy_(gw)
             if has_b:
@@ -235,8 +265,10 @@ class RefOps:
     def copy(self, src, dst, accumulate=False):
         dst.add_(src) if accumulate else dst.copy_(src)
 
-    def act_bwd(self, dy, y, act, slope=0.0):
+    def act_bwd(self, dy, y, act, slope=0.0, rnd=False):
         dy.mul_(act_grad(y, act, slope))
+        if rnd:
+            self.round_tf32(dy)
 
     def fill(self, t, value):
         t.fill_(value)
@@ -509,6 +541,21 @@ class RefOps:
         q = lambda t: t.mul(255).clamp(0, 255).round()
         d = (q(pred) - q(target)).div(255)
         sq_out.add_(d.pow(2).double().sum())
+
+    def ssim_accumulate(self, pred, target, window, sum_out, val_range=255.0):
+        """pytorch_msssim/__init__.py:19-75 on the 8-bit quantised images (utils.py:195-204); sum of the SSIM map."""
+        q = lambda t: t.mul(255).clamp(0, 255).round()
+        a, b = q(pred).unsqueeze(0), q(target).unsqueeze(0)
+        c = a.shape[1]
+        w2 = window.unsqueeze(1).mm(window.unsqueeze(0)).unsqueeze(0).unsqueeze(0).expand(c, 1, -1, -1).contiguous()
+        F = torch.nn.functional
+        mu1, mu2 = F.conv2d(a, w2, groups=c), F.conv2d(b, w2, groups=c)
+        s1 = F.conv2d(a * a, w2, groups=c) - mu1.pow(2)
+        s2 = F.conv2d(b * b, w2, groups=c) - mu2.pow(2)
+        s12 = F.conv2d(a * b, w2, groups=c) - mu1 * mu2
+        c1, c2 = (0.01 * val_range) ** 2, (0.03 * val_range) ** 2
+        v1, v2 = 2.0 * s12 + c2, s1 + s2 + c2
+        sum_out.add_((((2 * mu1 * mu2 + c1) * v1) / ((mu1.pow(2) + mu2.pow(2) + c1) * v2)).double().sum())
 
     def septuplet_prepare(self, src, y0, x0, reversed_, h, w, bgr=True, div255=True, mean=None, std=None):
         """data/vimeo_septuplet.py:50-78 frame by frame: crop (:59-61), temporal flip (:64-66), BGR->RGB (:69),

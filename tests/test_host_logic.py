@@ -109,7 +109,8 @@ def test_flow_plugins_names_init_forward_and_routing(ref_ops, model):
 
 FLOW_GOLDEN = ["voxelflow_lslr_sgd_k1_mse", "voxelflow_lslr_sgd_k2_ragged", "superslomo_metasgd_sgd_k2",
                "superslomo_lslr_sgd_k1_ragged", "rrin_msl_learnable_k2", "rrin_lslr_sgd_k1_ragged",
-               "cain_l2f_sgd_k1", "cain_lslr_sgd_k2_ragged", "cain_lslr_sgd_k2_gain04", "cain_l2f_sgd_k1_gain04"]
+               "cain_l2f_sgd_k1", "cain_lslr_sgd_k2_ragged", "cain_lslr_sgd_k2_gain04", "cain_l2f_sgd_k1_gain04",
+               "voxelflow_metasgd_adam_k1"]
 
 
 @pytest.mark.parametrize("name", FLOW_GOLDEN)
@@ -125,11 +126,39 @@ def test_flow_systems_against_reference_golden(ref_ops, name, fast):
     assert abs(float(losses["loss"]) - fx["loss"]) <= 1e-5 * max(1.0, abs(fx["loss"]))
     assert (torch.cat(preds) - fx["preds"]).abs().max().item() <= 2e-4 * scale
     assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01          # north_star tolerance
+    if abs(fx["loss"]) < 5:
+        assert abs(float(metrics["ssim"].avg) - fx["ssim"]) < 1e-4   # pytorch_msssim restatement (utils.ssim)
     own = dict(system.net.named_parameters())
     tol = 0.2 if fx["args"]["model"] == "cain" else 5e-3
     for k, (d, head) in fx["post_digest"].items():
         mine = digest(own[k])[0]
         assert torch.allclose(mine[1:], d[1:], rtol=tol, atol=1e-8), k
+    if fx.get("delta_digest") is not None:
+        # the outer step itself (post - init): for voxelflow + Adam it is the policy-built Adam with weight decay
+        # (reference :133-136), a sign-like step of outer_lr per element
+        init = oracle_from_fixture(fx).params
+        for k, (d, head) in fx["delta_digest"].items():
+            mine = digest(own[k].detach() - init[k].detach())[0]
+            assert torch.allclose(mine[1:], d[1:], rtol=2e-2, atol=1e-12), k
+
+
+def test_voxelflow_adam_optimizer_follows_the_reference_policies(ref_ops):
+    """reference :133-136 + voxel_flow.py:307-350: three param groups (conv weights / conv bias / BN scale+shift)
+    over the backbone's tensors only, weight_decay from args, torch's default betas; Meta-SGD alphas are NOT stepped."""
+    from meta_interpolation_b200.meta_learning_system import SceneAdaptiveInterpolation
+    s = SceneAdaptiveInterpolation(make_args(model="voxelflow", optimizer="Adam", metasgd=True, loss="1*MSE"),
+                                   ops=ref_ops)
+    sd = s.optimizer.state_dict()
+    assert [g["name"] for g in sd["param_groups"]] == ["model weight", "model bias", "model bn scale/shift"]
+    assert [len(g["params"]) for g in sd["param_groups"]] == [8, 1, 14]
+    assert [(g["lr_mult"], g["decay_mult"]) for g in sd["param_groups"]] == [(1, 1), (2, 0), (1, 1)]
+    assert all(g["betas"] == (0.9, 0.999) and g["weight_decay"] == 1e-4 for g in sd["param_groups"])
+    assert s.fast_path_supported()
+    alpha0 = s.alpha.flat.clone()
+    g = torch.Generator().manual_seed(2)
+    frames = [torch.rand(1, 3, 64, 64, generator=g) * 2 - 1 for _ in range(7)]
+    s.run_train_iter(frames, epoch=0)
+    assert torch.equal(s.alpha.flat, alpha0)
 
 
 def test_state_dict_keys_match_reference_schema(ref_ops):
@@ -464,3 +493,40 @@ def test_oracle_run_test_iter_reproduces_reference_golden(name):
     outs = ora.run_test_iter(list(fx["frames"]))
     for a, b in zip(outs, fx["outputs"]):
         assert (a - b).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("name,fast", [("sepconv_lslr_sgd_k2", True), ("sepconv_lslr_sgd_k2", False),
+                                       ("sepconv_metasgd_adamax_k2", True), ("sepconv_l2f_sgd_k1", True),
+                                       ("cain_lslr_sgd_k2_gain04", True)])
+def test_tf32_operand_convention_host_logic(name, fast):
+    """The TF32 operand convention (include/mi_b200.h): fprop reads TF32-rounded weight copies (meta shadow arena,
+    per-lane fast shadow written by the fused update / after the flat moment update / after the L2F attenuation),
+    dgrad rounded rotated copies, activations and gradients are rounded before a conv reads them, and the exact fp32
+    master weights are what the updates see.  Run with an operator table that rounds like the GPU but convolves
+    exactly: results must stay within the rounding noise of the golden (and the masters must NOT be on the grid)."""
+    from oracle.ops_ref import RefOps
+    from meta_interpolation_b200 import backbone
+    ops = RefOps(tf32_rn=True)
+    saved = backbone._default_ops
+    backbone.set_default_ops(ops)
+    try:
+        fx = load_golden(name)
+        system = system_from_fixture(fx, ops, fast_path=fast)
+        assert system.fast_path_supported() == fast
+        losses, preds, metrics = system.run_train_iter(list(fx["frames"]), epoch=0, do_evaluation=True)
+        assert abs(float(losses["loss"]) - fx["loss"]) <= 5e-4 * max(1.0, abs(fx["loss"]))
+        assert (torch.cat(preds) - fx["preds"]).abs().max().item() <= 2e-3 * max(1.0, fx["preds"].abs().max().item())
+        assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+        flat = system.net.arena.flat
+        grid = ops.round_tf32(flat.clone())
+        assert (grid != flat).any()                       # the master copy keeps its low mantissa bits
+        if fast:
+            fp = system.fast_path()
+            assert torch.equal(ops.round_tf32(fp.meta_r.flat.clone()), fp.meta_r.flat)      # the shadow is on the grid
+            lane = fp.lanes[0]
+            for n in system.net.conv_names:
+                if system.net.is_routed(n + ".weight"):
+                    w, wr = lane.fast.kernel_view(n + ".weight"), lane.fast_r.kernel_view(n + ".weight")
+                    assert torch.equal(ops.round_tf32(w.clone().contiguous()), wr.contiguous()), n
+    finally:
+        backbone.set_default_ops(saved)

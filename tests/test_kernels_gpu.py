@@ -485,3 +485,56 @@ def test_ragged_slice_never_writes_neighbouring_channels(cuda_ops, c, width):
         ops.conv_fprop(xd, wd, None, ACT_NONE, 0.0, out=full[..., :c])
         assert torch.equal(full[..., c:].cpu(), torch.full((n, h, w, width - c), 7.0)), "conv: neighbours touched"
         close(full[..., :c], REF.conv_fprop(xc, wc, None), 4e-3, "conv into slice")
+
+
+@pytest.mark.parametrize("hw", [(256, 448), (37, 53), (11, 11), (9, 40)])
+def test_ssim_kernel_against_pytorch_msssim_restatement(cuda_ops, hw):
+    """mi_ssim_accumulate (utils.py:195-204 -> pytorch_msssim/__init__.py:19-75) vs the ATen restatement: structured
+    and noisy pairs, windows clipped by small images, ragged tiles."""
+    from meta_interpolation_b200.utils import gaussian_1d
+    g = torch.Generator().manual_seed(4)
+    h, w = hw
+    base = torch.rand(3, h, w, generator=g)
+    for noise in (0.02, 0.5):
+        other = (base + noise * torch.randn(3, h, w, generator=g)).clamp(-0.2, 1.2)
+        win = gaussian_1d(min(11, h, w))
+        sr, sd = torch.zeros(1, dtype=torch.float64), torch.zeros(1, dtype=torch.float64, device="cuda")
+        REF.ssim_accumulate(base, other, win, sr)
+        cuda_ops.ssim_accumulate(base.cuda(), other.cuda(), win, sd)
+        n = 3 * (h - win.numel() + 1) * (w - win.numel() + 1)
+        assert abs(sr.item() - sd.item()) / n <= 2e-5, (hw, noise, sr.item() / n, sd.item() / n)
+
+
+def test_round_tf32_kernel_and_rounded_weight_copies(cuda_ops):
+    """mi_round_tf32 == cvt.rna.tf32.f32 (restated with integer arithmetic in oracle/ops_ref.py): flat buffers,
+    NHWC rows with a pixel stride (neighbouring channels untouched), in place and out of place; the rotated dgrad
+    copy is rounded on request."""
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(4096, generator=g) * 3
+    assert torch.equal(cuda_ops.round_tf32(x.cuda().clone()).cpu(), REF.round_tf32(x.clone()))
+    buf = torch.randn(2, 5, 7, 12, generator=g)
+    view_c, view_r = buf.cuda().clone(), buf.clone()
+    cuda_ops.round_tf32(view_c[..., 2:9])                 # 7 channels of a 12-float pixel stride
+    REF.round_tf32(view_r[..., 2:9])
+    assert torch.equal(view_c.cpu(), view_r)
+    assert torch.equal(view_c.cpu()[..., :2], buf[..., :2]) and torch.equal(view_c.cpu()[..., 9:], buf[..., 9:])
+    w = cuda_ops.empty_weight(40, 37, 3)
+    w.copy_(torch.randn(40, 3, 3, 37, generator=g))
+    wt = cuda_ops.weight_to_dgrad(w, rnd=True)
+    assert torch.equal(wt.cpu(), REF.weight_to_dgrad(w.cpu(), rnd=True))
+    assert not torch.equal(wt.cpu(), REF.weight_to_dgrad(w.cpu(), rnd=False))
+
+
+def test_tensor_core_conv_outputs_lie_on_the_tf32_grid(cuda_ops):
+    """TF32 operand convention: fprop / dgrad epilogues of the tensor-core engine store round-to-nearest TF32 values,
+    so the next conv's hardware truncation is exact."""
+    if not cuda_ops.tf32_rn:
+        pytest.skip("exact-fp32 engine forced")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = cuda_ops.empty_act(2, 40, 56, 64); x.copy_(torch.rand(2, 40, 56, 64, device="cuda", generator=g))
+    w = cuda_ops.empty_weight(51, 64, 3); w.copy_(torch.rand(51, 3, 3, 64, device="cuda", generator=g) - 0.5)
+    b = torch.rand(51, device="cuda", generator=g)
+    y = cuda_ops.conv_fprop(x, w, b, 1, 0.0)
+    assert torch.equal(y.contiguous(), cuda_ops.round_tf32(y.contiguous().clone()))
+    dx = cuda_ops.conv_dgrad(y, w)
+    assert torch.equal(dx.contiguous(), cuda_ops.round_tf32(dx.contiguous().clone()))

@@ -32,6 +32,7 @@ def test_train_iter_against_reference_golden(cuda_ops, name, fast, graphs):
     assert abs(float(losses["loss"]) - fx["loss"]) <= LOSS_TOL
     assert (torch.cat(preds).cpu() - fx["preds"]).abs().max().item() <= PRED_TOL
     assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+    assert abs(float(metrics["ssim"].avg) - fx["ssim"]) < 2e-3      # on-device SSIM kernel vs the reference's value
     if fx["args"]["optimizer"] == "SGD":
         own = dict(system.net.named_parameters())
         for k, (d, head) in fx["post_digest"].items():
@@ -100,7 +101,7 @@ def test_linearity_property_full_size_conv(cuda_ops):
 
 FLOW_GOLDEN = ["voxelflow_lslr_sgd_k1_mse", "voxelflow_lslr_sgd_k2_ragged", "superslomo_metasgd_sgd_k2",
                "superslomo_lslr_sgd_k1_ragged", "rrin_msl_learnable_k2", "rrin_lslr_sgd_k1_ragged",
-               "cain_l2f_sgd_k1_gain04", "cain_lslr_sgd_k2_gain04"]
+               "cain_l2f_sgd_k1_gain04", "cain_lslr_sgd_k2_gain04", "voxelflow_metasgd_adam_k1"]
 
 
 def _run_flow_case(ops, name, fast, graphs, loss_tol, pred_tol):
@@ -116,6 +117,8 @@ def _run_flow_case(ops, name, fast, graphs, loss_tol, pred_tol):
     assert abs(float(losses["loss"].detach()) - fx["loss"]) <= loss_tol * max(1.0, abs(fx["loss"]))
     assert (torch.cat(preds).cpu() - fx["preds"]).abs().max().item() <= pred_tol * scale
     assert abs(metrics["psnr"].avg - fx["psnr"]) < 0.01
+    if abs(fx["loss"]) < 5:          # (not cain's exploded default init)
+        assert abs(float(metrics["ssim"].avg) - fx["ssim"]) < 2e-3
     return system, fx
 
 
@@ -297,6 +300,7 @@ def test_full_size_train_iter_against_reference_golden(cuda_ops, name):
         dl = abs(float(losses["loss"].detach()) - fx["loss"])
         dp = (torch.cat(preds).cpu() - fx["preds"]).abs().max().item()
         dpsnr = abs(metrics["psnr"].avg - fx["psnr"])
+        dssim = abs(float(metrics["ssim"].avg) - fx["ssim"])
         # meta-gradient of every tensor: |g|_1 and |g|_2^2 against the reference's digests
         from meta_interpolation_b200.arena import Arena
         garena = Arena(system.net.layout, system.device, data=seen["net"])
@@ -316,11 +320,12 @@ def test_full_size_train_iter_against_reference_golden(cuda_ops, name):
             den = max(float(d[1]), 1e-30)
             worst_post = max(worst_post, abs(float(mine[1]) - float(d[1])) / den)
         _record_parity(dict(case=name, iteration=it, loss=fx["loss"], d_loss=dl, pred_scale=scale, d_pred_maxabs=dp,
-                            psnr=fx["psnr"], d_psnr=dpsnr, worst_grad_l2_rel=worst_g, worst_grad_tensor=worst_name,
+                            psnr=fx["psnr"], d_psnr=dpsnr, ssim=fx["ssim"], d_ssim=dssim, worst_grad_l2_rel=worst_g, worst_grad_tensor=worst_name,
                             worst_post_l1_rel=worst_post))
         assert dl <= LOSS_TOL * max(1.0, abs(fx["loss"])), (it, dl)
         assert dp <= PRED_TOL * scale, (it, dp)
         assert dpsnr < 0.01, (it, dpsnr)
+        assert dssim < 2e-3, (it, dssim)
         assert worst_g <= 5e-2, (it, worst_name, worst_g)     # TF32 operands, up to 2e5-pixel reductions
         assert worst_post <= 5e-2, (it, worst_post)
 
