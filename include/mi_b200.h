@@ -259,14 +259,21 @@ int mi_nchw_to_nhwc_window(const float* src, float* dst, int ldd, int n, int hs,
  * With gy0=gx0=0, iy0=ix0=0, fh=oh+F-1 this is exactly the reference op on a pre-padded input; with
  * gy0=gx0=25, iy0=ix0=-25 on the raw frame it is the op fused with modulePaddingInput, modulePad and
  * modulePaddingOutput (SURVEY Appx A.1).  No gradient w.r.t. frame is ever needed (sepconv.py:319). */
+/* Tap-planar workspace (optional, F = 51, c = 3): the kernels that keep four pixels per thread read the filters
+ * as [image][tap][oh][ow] (one cache line per tap per 32 pixels instead of 32 lines).  `planar` of
+ * mi_sepconv_planar_bytes(n, oh, ow, taps) bytes is filled by the forward (one transposing pass) and can be handed to
+ * the backward of the same call (planar_valid = 1), which also needs `planar_grad` of the same size as scratch for
+ * the planar gradients before they are returned to NHWC.  NULL selects the kernels that read NHWC filters directly. */
+size_t mi_sepconv_planar_bytes(int n, int oh, int ow, int taps);
 int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, int ldf, float* out,
                    int n, int c, int fh, int fw, int gh, int gw, int oh, int ow,
-                   int gy0, int gx0, int iy0, int ix0, int taps, mi_stream_t stream);
+                   int gy0, int gx0, int iy0, int ix0, int taps, float* planar, mi_stream_t stream);
 /* g_vert/g_horiz get the gradient inside the window; the caller zero-fills the rest of the grid. */
 int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
                    float* g_vert, float* g_horiz, int ldg,
                    int n, int c, int fh, int fw, int gh, int gw, int oh, int ow,
-                   int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32, mi_stream_t stream);
+                   int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32,
+                   float* planar, int planar_valid, float* planar_grad, mi_stream_t stream);
 
 /* ------------------------------------------------------------------ bilinear backward warp (grid_sample)
  * variant 0: superslomo backWarp / rrin warp (superslomo/model.py:292-302, rrin/model.py:8-21):

@@ -69,8 +69,9 @@ SIGNATURES = {
     "mi_frames_to_canvas": (_i, [_f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nhwc_window_to_nchw": (_i, [_f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
     "mi_nchw_to_nhwc_window": (_i, [_f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _i, _st]),
-    "mi_sepconv_fwd": (_i, [_f, _f, _f, _i, _f] + [_i] * 13 + [_st]),
-    "mi_sepconv_bwd": (_i, [_f, _f, _f, _i, _f, _f, _f, _i] + [_i] * 14 + [_st]),
+    "mi_sepconv_planar_bytes": (_sz, [_i, _i, _i, _i]),
+    "mi_sepconv_fwd": (_i, [_f, _f, _f, _i, _f] + [_i] * 13 + [_f, _st]),
+    "mi_sepconv_bwd": (_i, [_f, _f, _f, _i, _f, _f, _f, _i] + [_i] * 14 + [_f, _i, _f, _st]),
     "mi_warp_fwd": (_i, [_f, _i, _f, _i, _f, _i, _i, _i, _i, _i, _i, _fl, _fl, _st]),
     "mi_warp_bwd": (_i, [_f, _i, _f, _i, _f, _i, _f, _i, _f, _i, _i, _i, _i, _i, _i, _i, _fl, _fl, _st]),
     "mi_loss_fwd_bwd": (_i, [_f, _f, _f, _f, _sz, _i, _fl, _st]),

@@ -13,8 +13,19 @@
 #include <cstdlib>
 
 #include "mi_common.cuh"
+#include "sepconv_quad.cuh"
 
 namespace {
+
+// MI_B200_SEPCONV_QUAD=0 selects the first-generation kernels below (A/B measurements)
+bool use_quad() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MI_B200_SEPCONV_QUAD");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
 
 constexpr int TX = 32;
 constexpr int TY = 8;
@@ -331,12 +342,36 @@ int variant_minb(int which) {
 
 extern "C" {
 
+size_t mi_sepconv_planar_bytes(int n, int oh, int ow, int taps) {
+    return (size_t)2 * n * taps * oh * ow * sizeof(float);
+}
+
 int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, int ldf, float* out, int n, int c,
                    int fh, int fw, int gh, int gw, int oh, int ow, int gy0, int gx0, int iy0, int ix0, int taps,
-                   mi_stream_t stream) {
+                   float* planar, mi_stream_t stream) {
     if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !out) return MI_ERR_BAD_ARG;
     cudaStream_t st = mi_cs(stream);
-    if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && mi_al16(vert) && mi_al16(horiz)) {
+    if (taps == 51 && c == 3 && planar && use_quad()) {
+        static bool attr_set = false;
+        const size_t sm = quad::smem_bytes<51, 3>();
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(quad::sepconv_fwd_quad_kernel<51, 3>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        float* vpl = planar;
+        float* hpl = planar + (size_t)n * 51 * oh * ow;
+        const double px = (double)n * oh * ow;
+        mi_prof_begin(MI_TAG_SEPCONV_FWD, 2.0 * px * (3 * 51 * 51 + 3 * 51), 4.0 * px * (2 * 51 + 3 + 3), st);
+        quad::filters_to_planar_kernel<51><<<dim3(mi_cdiv(ow, 32), oh, 2 * n), 256, 0, st>>>(vert, horiz, ldf, vpl, hpl, gh,
+                                                                                            gw, gy0, gx0, oh, ow);
+        MI_LAUNCHED();
+        const quad::Args qa = {fh, fw, oh, ow, iy0, ix0};
+        dim3 grid(mi_cdiv(ow, quad::BX), mi_cdiv(oh, quad::BY), n);
+        quad::sepconv_fwd_quad_kernel<51, 3><<<grid, quad::NT, sm, st>>>(frame, vpl, hpl, out, qa);
+        mi_prof_end(st);
+    } else if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && mi_al16(vert) && mi_al16(horiz)) {
         static bool attr_set = false;
         const size_t sm = (size_t)3 * GeoF<51>::WIN_H * GeoF<51>::PITCH * sizeof(float);
         if (!attr_set) {
@@ -370,14 +405,43 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
 
 int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
                    float* g_vert, float* g_horiz, int ldg, int n, int c, int fh, int fw, int gh, int gw, int oh,
-                   int ow, int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32, mi_stream_t stream) {
+                   int ow, int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32, float* planar,
+                   int planar_valid, float* planar_grad, mi_stream_t stream) {
     const int rnd = (round_tf32 && mi_tf32_rn_enabled()) ? 1 : 0;
     if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !grad_out || !g_vert ||
         !g_horiz || ldg < taps)
         return MI_ERR_BAD_ARG;
     cudaStream_t st = mi_cs(stream);
-    if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && ldg >= 52 && (ldg & 3) == 0 && mi_al16(vert) &&
-        mi_al16(horiz) && mi_al16(g_vert) && mi_al16(g_horiz)) {
+    if (taps == 51 && c == 3 && planar && planar_grad && use_quad()) {
+        static bool attr_set = false;
+        const size_t sm = quad::smem_bytes<51, 3>();
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(quad::sepconv_bwd_quad_kernel<51, 3>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (e != cudaSuccess) return (int)e;
+            attr_set = true;
+        }
+        const size_t half = (size_t)n * 51 * oh * ow;
+        float* vpl = planar;
+        float* hpl = planar + half;
+        float* gvpl = planar_grad;
+        float* ghpl = planar_grad + half;
+        const double px = (double)n * oh * ow;
+        mi_prof_begin(MI_TAG_SEPCONV_BWD, 2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51), 4.0 * px * (4 * 51 + 3 + 3), st);
+        const dim3 tgrid(mi_cdiv(ow, 32), oh, 2 * n);
+        if (!planar_valid) {      // the forward of this call did not leave its planar filters behind
+            quad::filters_to_planar_kernel<51><<<tgrid, 256, 0, st>>>(vert, horiz, ldf, vpl, hpl, gh, gw, gy0, gx0, oh, ow);
+            MI_LAUNCHED();
+        }
+        const quad::Args qa = {fh, fw, oh, ow, iy0, ix0};
+        dim3 grid(mi_cdiv(ow, quad::BX), mi_cdiv(oh, quad::BY), 2 * n);
+        quad::sepconv_bwd_quad_kernel<51, 3><<<grid, quad::NT, sm, st>>>(frame, vpl, hpl, grad_out, gvpl, ghpl, qa);
+        MI_LAUNCHED();
+        quad::planar_to_filters_kernel<51><<<tgrid, 256, 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0, gx0, oh,
+                                                                 ow, rnd);
+        mi_prof_end(st);
+    } else if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && ldg >= 52 && (ldg & 3) == 0 && mi_al16(vert) &&
+               mi_al16(horiz) && mi_al16(g_vert) && mi_al16(g_horiz)) {
         static bool attr_set = false;
         const size_t sm = smem_bytes<51>(3);
         if (!attr_set) {

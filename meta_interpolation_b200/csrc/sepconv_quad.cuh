@@ -1,0 +1,355 @@
+// Adaptive separable convolution, second generation: four vertically adjacent pixels per thread.
+//
+// The first kernels (sepconv.cu) keep one pixel's whole 51-tap filter in registers and reuse every staged window
+// value for two pixels: one shared-memory load per two FMAs, i.e. a ceiling of half the FP32 pipe (one 32-lane LDS
+// wavefront per cycle per SM against four FMA issue slots); ncu showed 23-29 % of the FMA roof.  Here a thread owns
+// the pixels (y0..y0+3, x): their windows are the same 51 columns of rows shifted by one, so a staged value feeds
+// FOUR FMAs.  What one thread can hold in registers is 4 pixels x 26 taps, so every quantity is produced in two
+// passes over the taps it is indexed by:
+//
+//   forward   out[c]  = sum_fy V[fy] * T[c][fy],  T[c][fy] = sum_fx H[fx] * in[c][y+fy][x+fx]
+//             pass over fx in [0,26) then [26,51): registers hold H (4 x 26), the partial T is folded into the 12
+//             output accumulators at once (the sum over fx is linear), nothing is spilled between passes
+//   gradH     gH[fx]  = sum_{c,fy} (gO[c] V[fy]) * in[c][y+fy][x+fx]
+//             registers hold the 4 x 26 accumulators of one half of fx, the loop runs over window rows
+//   gradV     gV[fy]  = sum_{c,fx} (gO[c] H[fx]) * in[c][y+fy][x+fx]
+//             the transposed walk: accumulators for one half of fy, the loop runs over window COLUMNS
+//
+// (the reference evaluates the same sums per output with 3 x 2601 global loads, sepconv/sepconv_op/sepconv.py:5-30,
+// 138-190).  Lanes of a warp are consecutive x, so every shared-memory access -- along a row or down a column -- is a
+// conflict-free 128-byte wavefront.  Per 104 FMAs a thread issues 26-29 LDS: the shared-memory pipe and the FMA pipe
+// are balanced, neither waits for HBM (the 51x51x3 windows of a 32x16 tile are staged once, 66 KB, three CTAs / SM).
+//
+// Filter layout.  The filters arrive as NHWC conv outputs: the 51 taps of a pixel are contiguous and consecutive
+// pixels are 208 bytes apart, so a warp reading "tap fy of my pixel" touches 32 different cache lines.  With one LDS
+// per four FMAs left, those uncoalesced loads became the bottleneck of the first version of these kernels (measured:
+// no faster than the two-pixel kernels).  The filters of the output window are therefore first transposed to
+// tap-planar form [image][tap][y][x] (one coalesced pass, kept for the backward), where "tap fy of 32 consecutive
+// pixels" is ONE 128-byte line; the backward writes its gradients planar as well and a second transposing pass
+// returns them to NHWC (rounded to the TF32 grid on request: they are the next conv's operands).
+#pragma once
+
+namespace quad {
+
+constexpr int QY = 4;                    // pixels per thread
+constexpr int BX = 32, BY = 16;          // pixel tile of a CTA
+constexpr int NT = BX * (BY / QY);       // 128 threads
+constexpr int HALF_A = 26;               // taps [0, 26) and [26, 51)
+
+template <int F>
+struct Geo {
+    static constexpr int WIN_W = BX + F - 1;
+    static constexpr int WIN_H = BY + F - 1;
+    static constexpr int PITCH = WIN_W + 1;
+};
+template <int F, int C>
+constexpr size_t smem_bytes() { return (size_t)C * Geo<F>::WIN_H * Geo<F>::PITCH * sizeof(float); }
+
+template <int F, int C>
+__device__ __forceinline__ void stage(float* smem, const float* __restrict__ frame, int fh, int fw, int n_idx,
+                                      int y_base, int x_base) {
+    // one warp per window row, lanes along it (three 128-byte wavefronts per row): no per-element division, and the
+    // rows of a warp are independent loads the compiler can keep in flight together
+    constexpr int WW = Geo<F>::WIN_W, WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    const long long plane = (long long)fh * fw;
+    const float* fb = frame + (long long)n_idx * C * plane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int sx[(WW + 31) / 32];
+#pragma unroll
+    for (int j = 0; j < (WW + 31) / 32; ++j) sx[j] = min(max(x_base + lane + 32 * j, 0), fw - 1);   // replicate border
+#pragma unroll 2
+    for (int rr = warp; rr < C * WH; rr += NT / 32) {
+        const int cc = rr / WH, r = rr - cc * WH;
+        const int sy = min(max(y_base + r, 0), fh - 1);
+        const float* src = fb + cc * plane + (long long)sy * fw;
+        float* dst = smem + rr * P;
+#pragma unroll
+        for (int j = 0; j < (WW + 31) / 32; ++j)
+            if (lane + 32 * j < WW) dst[lane + 32 * j] = __ldg(src + sx[j]);
+    }
+}
+
+// Planar filters of the quad owned by this thread: tap t of pixel k is base[t * plane + off[k]].
+struct QuadTaps {
+    const float* base;
+    long long plane;
+    int off[QY];
+    __device__ __forceinline__ float at(int k, int t) const { return __ldg(base + (long long)t * plane + off[k]); }
+};
+
+// taps [T0, T0 + NTAP) of the four pixels -> registers
+template <int T0, int NTAP>
+__device__ __forceinline__ void load_taps(float (&h)[QY][HALF_A], const QuadTaps& q) {
+#pragma unroll
+    for (int f = 0; f < NTAP; ++f)
+#pragma unroll
+        for (int k = 0; k < QY; ++k) h[k][f] = q.at(k, T0 + f);
+}
+
+// One pass of the forward kernel over the horizontal taps [T0, T0 + NTAP).
+template <int F, int C, int T0, int NTAP>
+__device__ __forceinline__ void fwd_pass(const float* win, const QuadTaps& hp, const QuadTaps& vp,
+                                         float (&acc)[QY][C]) {
+    constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    float h[QY][HALF_A];
+    load_taps<T0, NTAP>(h, hp);
+    float vn[QY];                                       // taps of the NEXT row, fetched a row ahead of their use
+#pragma unroll
+    for (int k = 0; k < QY; ++k) vn[k] = k == 0 ? vp.at(0, 0) : 0.f;
+#pragma unroll 1
+    for (int r = 0; r < F + QY - 1; ++r) {             // window row relative to the first pixel of the quad
+        float v[QY];
+#pragma unroll
+        for (int k = 0; k < QY; ++k) {
+            v[k] = vn[k];
+            const int fy = r + 1 - k;                   // row r + 1 is tap fy of pixel k
+            vn[k] = (fy >= 0 && fy < F) ? vp.at(k, fy) : 0.f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            const float* row = win + (cc * WH + r) * P + T0;
+            float t[QY];
+#pragma unroll
+            for (int k = 0; k < QY; ++k) t[k] = 0.f;
+#pragma unroll
+            for (int f = 0; f < NTAP; ++f) {
+                const float in = row[f];
+#pragma unroll
+                for (int k = 0; k < QY; ++k) t[k] = fmaf(in, h[k][f], t[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < QY; ++k) acc[k][cc] = fmaf(v[k], t[k], acc[k][cc]);
+        }
+    }
+}
+
+struct Args {
+    int fh, fw, oh, ow, iy0, ix0;
+};
+
+// planar filters [image][tap][oh][ow] of the quad (y0..y0+3, x); rows past the image reuse the last valid one
+template <int F>
+__device__ __forceinline__ QuadTaps quad_taps(const float* planar, const Args& a, int n_idx, int y0, int x) {
+    QuadTaps q;
+    q.plane = (long long)a.oh * a.ow;
+    q.base = planar + (long long)n_idx * F * q.plane;
+#pragma unroll
+    for (int k = 0; k < QY; ++k) q.off[k] = min(y0 + k, a.oh - 1) * a.ow + x;
+    return q;
+}
+
+template <int F, int C>
+__global__ void __launch_bounds__(NT, 3)
+sepconv_fwd_quad_kernel(const float* __restrict__ frame, const float* __restrict__ vert_pl,
+                        const float* __restrict__ horiz_pl, float* __restrict__ out, Args a) {
+    extern __shared__ float smem[];
+    constexpr int P = Geo<F>::PITCH;
+    const int n_idx = blockIdx.z;
+    const int tx = threadIdx.x % BX, tq = threadIdx.x / BX;
+    const int oy_base = blockIdx.y * BY, ox_base = blockIdx.x * BX;
+    stage<F, C>(smem, frame, a.fh, a.fw, n_idx, oy_base + a.iy0, ox_base + a.ix0);
+    __syncthreads();
+    const int y0 = oy_base + QY * tq, x = ox_base + tx;
+    if (y0 >= a.oh || x >= a.ow) return;
+    const QuadTaps hp = quad_taps<F>(horiz_pl, a, n_idx, y0, x);
+    const QuadTaps vp = quad_taps<F>(vert_pl, a, n_idx, y0, x);
+    float acc[QY][C];
+#pragma unroll
+    for (int k = 0; k < QY; ++k)
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) acc[k][cc] = 0.f;
+    const float* win = smem + (QY * tq) * P + tx;
+    fwd_pass<F, C, 0, HALF_A>(win, hp, vp, acc);
+    fwd_pass<F, C, HALF_A, F - HALF_A>(win, hp, vp, acc);
+#pragma unroll
+    for (int k = 0; k < QY; ++k) {
+        if (y0 + k >= a.oh) break;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc)
+            out[(((long long)n_idx * C + cc) * a.oh + y0 + k) * a.ow + x] = acc[k][cc];
+    }
+}
+
+// gradHorizontal for the taps [T0, T0 + NTAP): the loop runs over window rows.
+template <int F, int C, int T0, int NTAP>
+__device__ __forceinline__ void gh_pass(const float* win, const QuadTaps& vp, const float (&go)[QY][C],
+                                        float* gout, long long plane, const int (&goff)[QY], const bool (&ok)[QY]) {
+    constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    float acc[QY][HALF_A];
+#pragma unroll
+    for (int k = 0; k < QY; ++k)
+#pragma unroll
+        for (int f = 0; f < NTAP; ++f) acc[k][f] = 0.f;
+    float vn[QY];
+#pragma unroll
+    for (int k = 0; k < QY; ++k) vn[k] = k == 0 ? vp.at(0, 0) : 0.f;
+#pragma unroll 1
+    for (int r = 0; r < F + QY - 1; ++r) {
+        float v[QY];
+#pragma unroll
+        for (int k = 0; k < QY; ++k) {
+            v[k] = vn[k];
+            const int fy = r + 1 - k;
+            vn[k] = (fy >= 0 && fy < F) ? vp.at(k, fy) : 0.f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            const float* row = win + (cc * WH + r) * P + T0;
+            float coef[QY];
+#pragma unroll
+            for (int k = 0; k < QY; ++k) coef[k] = go[k][cc] * v[k];
+#pragma unroll
+            for (int f = 0; f < NTAP; ++f) {
+                const float in = row[f];
+#pragma unroll
+                for (int k = 0; k < QY; ++k) acc[k][f] = fmaf(coef[k], in, acc[k][f]);
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NTAP; ++f)
+#pragma unroll
+        for (int k = 0; k < QY; ++k)
+            if (ok[k]) gout[(long long)(T0 + f) * plane + goff[k]] = acc[k][f];
+}
+
+// gradVertical for the taps fy in [T0, T0 + NTAP): the loop runs over window columns (= horizontal taps).
+template <int F, int C, int T0, int NTAP>
+__device__ __forceinline__ void gv_pass(const float* win, const QuadTaps& hp, const float (&go)[QY][C],
+                                        float* gout, long long plane, const int (&goff)[QY], const bool (&ok)[QY]) {
+    constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
+    float acc[QY][HALF_A];
+#pragma unroll
+    for (int k = 0; k < QY; ++k)
+#pragma unroll
+        for (int j = 0; j < NTAP; ++j) acc[k][j] = 0.f;
+    float hn[QY];
+#pragma unroll
+    for (int k = 0; k < QY; ++k) hn[k] = hp.at(k, 0);
+#pragma unroll 1
+    for (int fx = 0; fx < F; ++fx) {
+        float hk[QY];
+#pragma unroll
+        for (int k = 0; k < QY; ++k) {
+            hk[k] = hn[k];
+            hn[k] = hp.at(k, min(fx + 1, F - 1));
+        }
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            // window rows T0 .. T0 + NTAP + 2 (relative to the quad's first pixel) of column x + fx
+            const float* col = win + (cc * WH + T0) * P + fx;
+            float coef[QY];
+#pragma unroll
+            for (int k = 0; k < QY; ++k) coef[k] = go[k][cc] * hk[k];
+#pragma unroll
+            for (int jj = 0; jj < NTAP + QY - 1; ++jj) {
+                const float in = col[jj * P];
+#pragma unroll
+                for (int k = 0; k < QY; ++k) {
+                    const int j = jj - k;          // row T0 + jj is tap fy = T0 + jj - k of pixel k
+                    if (j >= 0 && j < NTAP) acc[k][j] = fmaf(coef[k], in, acc[k][j]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NTAP; ++j)
+#pragma unroll
+        for (int k = 0; k < QY; ++k)
+            if (ok[k]) gout[(long long)(T0 + j) * plane + goff[k]] = acc[k][j];
+}
+
+// blockIdx.z = 2 * image + which: which 0 -> gradHorizontal, 1 -> gradVertical (two independent halves of the work,
+// each staging the same window, so one launch fills the GPU with twice the CTAs).  Filters in and gradients out are
+// tap-planar [image][tap][oh][ow].
+template <int F, int C>
+__global__ void __launch_bounds__(NT, 3)
+sepconv_bwd_quad_kernel(const float* __restrict__ frame, const float* __restrict__ vert_pl,
+                        const float* __restrict__ horiz_pl, const float* __restrict__ grad_out,
+                        float* __restrict__ gv_pl, float* __restrict__ gh_pl, Args a) {
+    extern __shared__ float smem[];
+    constexpr int P = Geo<F>::PITCH;
+    const int n_idx = blockIdx.z >> 1, which = blockIdx.z & 1;
+    const int tx = threadIdx.x % BX, tq = threadIdx.x / BX;
+    const int oy_base = blockIdx.y * BY, ox_base = blockIdx.x * BX;
+    stage<F, C>(smem, frame, a.fh, a.fw, n_idx, oy_base + a.iy0, ox_base + a.ix0);
+    __syncthreads();
+    const int y0 = oy_base + QY * tq, x = ox_base + tx;
+    if (y0 >= a.oh || x >= a.ow) return;
+    const QuadTaps fp = quad_taps<F>(which ? horiz_pl : vert_pl, a, n_idx, y0, x);   // gradV needs H, gradH needs V
+    const long long plane = (long long)a.oh * a.ow;
+    float* gout = (which ? gv_pl : gh_pl) + (long long)n_idx * F * plane;
+    bool ok[QY];
+    int goff[QY];
+    float go[QY][C];
+#pragma unroll
+    for (int k = 0; k < QY; ++k) {
+        ok[k] = y0 + k < a.oh;
+        goff[k] = fp.off[k];
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc)
+            go[k][cc] = ok[k] ? __ldg(grad_out + ((long long)n_idx * C + cc) * plane + goff[k]) : 0.f;
+    }
+    const float* win = smem + (QY * tq) * P + tx;
+    if (which == 0) {
+        gh_pass<F, C, 0, HALF_A>(win, fp, go, gout, plane, goff, ok);
+        gh_pass<F, C, HALF_A, F - HALF_A>(win, fp, go, gout, plane, goff, ok);
+    } else {
+        gv_pass<F, C, 0, HALF_A>(win, fp, go, gout, plane, goff, ok);
+        gv_pass<F, C, HALF_A, F - HALF_A>(win, fp, go, gout, plane, goff, ok);
+    }
+}
+
+// NHWC filters [n][gh][gw][ld] (window at (gy0, gx0)) -> tap-planar [n][F][oh][ow].  One CTA = 32 consecutive pixels
+// of one row: the 32 x F block is read as one contiguous run and written as F 128-byte lines.
+template <int F>
+__global__ void __launch_bounds__(256)
+filters_to_planar_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int ld, float* __restrict__ dst0,
+                         float* __restrict__ dst1, int gh, int gw, int gy0, int gx0, int oh, int ow) {
+    __shared__ float tile[32][F + 2];
+    const float* src = blockIdx.z & 1 ? src1 : src0;
+    float* dst = blockIdx.z & 1 ? dst1 : dst0;
+    const int n_idx = blockIdx.z >> 1, y = blockIdx.y, x0 = blockIdx.x * 32;
+    const int npx = min(32, ow - x0);
+    const float* row = src + (((long long)n_idx * gh + gy0 + y) * gw + gx0 + x0) * ld;
+    for (int i = threadIdx.x; i < npx * ld; i += 256) {
+        const int px = i / ld, t = i - px * ld;
+        if (t < F) tile[px][t] = __ldg(row + i);
+    }
+    __syncthreads();
+    const long long plane = (long long)oh * ow;
+    float* out = dst + (long long)n_idx * F * plane + (long long)y * ow + x0;
+    for (int i = threadIdx.x; i < F * 32; i += 256) {
+        const int t = i >> 5, px = i & 31;
+        if (px < npx) out[(long long)t * plane + px] = tile[px][t];
+    }
+}
+
+// tap-planar gradients [n][F][oh][ow] -> NHWC [n][gh][gw][ld] window (rounded to the TF32 grid on request)
+template <int F>
+__global__ void __launch_bounds__(256)
+planar_to_filters_kernel(const float* __restrict__ src0, const float* __restrict__ src1, float* __restrict__ dst0,
+                         float* __restrict__ dst1, int ld, int gh, int gw, int gy0, int gx0, int oh, int ow, int rnd) {
+    __shared__ float tile[32][F + 2];
+    const float* src = blockIdx.z & 1 ? src1 : src0;
+    float* dst = blockIdx.z & 1 ? dst1 : dst0;
+    const int n_idx = blockIdx.z >> 1, y = blockIdx.y, x0 = blockIdx.x * 32;
+    const int npx = min(32, ow - x0);
+    const long long plane = (long long)oh * ow;
+    const float* in = src + (long long)n_idx * F * plane + (long long)y * ow + x0;
+    for (int i = threadIdx.x; i < F * 32; i += 256) {
+        const int t = i >> 5, px = i & 31;
+        if (px < npx) {
+            const float v = __ldg(in + (long long)t * plane + px);
+            tile[px][t] = rnd ? mi_rn_tf32(v) : v;
+        }
+    }
+    __syncthreads();
+    float* row = dst + (((long long)n_idx * gh + gy0 + y) * gw + gx0 + x0) * ld;
+    for (int i = threadIdx.x; i < npx * ld; i += 256) {
+        const int px = i / ld, t = i - px * ld;
+        if (t < F) row[i] = tile[px][t];       // pad lanes of the NHWC rows are never written
+    }
+}
+
+}  // namespace quad

@@ -495,18 +495,25 @@ class CudaOps:
                                                    c, self._stream()), "mi_nchw_to_nhwc_window")
 
     # ------------------------------------------------------------------ adaptive separable convolution
-    def sepconv_fwd(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0):
-        """frame NCHW [n,c,fh,fw]; vert/horiz NHWC [n,gh,gw,F]; -> NCHW [n,c,oh,ow]."""
+    def sepconv_planar(self, n, oh, ow, taps):
+        """Workspace for the tap-planar copies of one sepconv call's two filter tensors (see include/mi_b200.h)."""
+        nbytes = int(self.lib.mi_sepconv_planar_bytes(n, oh, ow, taps))
+        return torch.empty(nbytes // 4, device=self.device, dtype=torch.float32)
+
+    def sepconv_fwd(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0, planar=None):
+        """frame NCHW [n,c,fh,fw]; vert/horiz NHWC [n,gh,gw,F]; -> NCHW [n,c,oh,ow].  ``planar`` (from
+        ``sepconv_planar``) selects the four-pixels-per-thread kernels and receives the planar filters."""
         n, c, fh, fw = frame.shape
         _, gh, gw, taps = vert.shape
         assert frame.is_contiguous() and _ld(vert) == _ld(horiz)
         out = torch.empty(n, c, oh, ow, device=self.device, dtype=torch.float32)
         _lib.check(self.lib.mi_sepconv_fwd(frame.data_ptr(), vert.data_ptr(), horiz.data_ptr(), _ld(vert),
                                            out.data_ptr(), n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps,
-                                           self._stream()), "mi_sepconv_fwd")
+                                           self._p(planar), self._stream()), "mi_sepconv_fwd")
         return out
 
-    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0, rnd=False):
+    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0, rnd=False, planar=None,
+                    planar_valid=False, planar_grad=None):
         n, c, fh, fw = frame.shape
         _, gh, gw, taps = vert.shape
         oh, ow = grad_out.shape[2], grad_out.shape[3]
@@ -514,7 +521,8 @@ class CudaOps:
         _lib.check(self.lib.mi_sepconv_bwd(frame.data_ptr(), vert.data_ptr(), horiz.data_ptr(), _ld(vert),
                                            grad_out.data_ptr(), g_vert.data_ptr(), g_horiz.data_ptr(), _ld(g_vert), n,
                                            c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps, int(rnd),
-                                           self._stream()), "mi_sepconv_bwd")
+                                           self._p(planar), int(planar_valid), self._p(planar_grad), self._stream()),
+                   "mi_sepconv_bwd")
 
     # ------------------------------------------------------------------ warp
     def warp_fwd(self, img, flow, variant, sx=1.0, sy=1.0, out=None):

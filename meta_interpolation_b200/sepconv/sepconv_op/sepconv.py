@@ -29,7 +29,8 @@ class FunctionSepconv(torch.autograd.Function):
         v.copy_(vertical.permute(0, 2, 3, 1))     # NCHW API boundary -> NHWC filter layout
         h.copy_(horizontal.permute(0, 2, 3, 1))
         ctx.save_for_backward(input, v, h)
-        return ops.sepconv_fwd(input, v, h, ho, wo, 0, 0, 0, 0)
+        ctx.planar = ops.sepconv_planar(n, ho, wo, f) if (f == 51 and c == 3) else None
+        return ops.sepconv_fwd(input, v, h, ho, wo, 0, 0, 0, 0, planar=ctx.planar)
 
     @staticmethod
     def backward(ctx, gradOutput):
@@ -38,7 +39,9 @@ class FunctionSepconv(torch.autograd.Function):
         n, ho, wo, f = v.shape
         gv = ops.zeros_act(n, ho, wo, f)
         gh = ops.zeros_act(n, ho, wo, f)
-        ops.sepconv_bwd(input, v, h, gradOutput.contiguous(), gv, gh, 0, 0, 0, 0)
+        scratch = ops.sepconv_planar(n, ho, wo, f) if ctx.planar is not None else None
+        ops.sepconv_bwd(input, v, h, gradOutput.contiguous(), gv, gh, 0, 0, 0, 0, planar=ctx.planar,
+                        planar_valid=ctx.planar is not None, planar_grad=scratch)
         return None, gv.permute(0, 3, 1, 2).contiguous(), gh.permute(0, 3, 1, 2).contiguous()
 
 

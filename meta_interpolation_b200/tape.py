@@ -303,7 +303,10 @@ class Tape:
         ops = self.ops
         vert.consumers += 1
         horiz.consumers += 1
-        y = Var(ops.sepconv_fwd(frame, vert.data, horiz.data, oh, ow, gy0, gx0, iy0, ix0))
+        n_img, taps_f = frame.shape[0], vert.data.shape[3]
+        # tap-planar copies of the two filter tensors: written by the forward, read again by the backward
+        planar = ops.sepconv_planar(n_img, oh, ow, taps_f) if (taps_f == 51 and frame.shape[1] == 3) else None
+        y = Var(ops.sepconv_fwd(frame, vert.data, horiz.data, oh, ow, gy0, gx0, iy0, ix0, planar=planar))
 
         def bwd():
             g = y.grad
@@ -313,8 +316,9 @@ class Tape:
             assert vert.grad is None and horiz.grad is None, "sepconv filters have a single consumer"
             vert.grad = ops.zeros_act(n, gh, gw, taps)
             horiz.grad = ops.zeros_act(n, gh, gw, taps)
+            scratch = ops.sepconv_planar(n_img, oh, ow, taps_f) if planar is not None else None
             ops.sepconv_bwd(frame, vert.data, horiz.data, g, vert.grad, horiz.grad, gy0, gx0, iy0, ix0,
-                            rnd=ops.tf32_rn)
+                            rnd=ops.tf32_rn, planar=planar, planar_valid=planar is not None, planar_grad=scratch)
             vert.grad_clean = horiz.grad_clean = ops.tf32_rn     # (zero outside the window is on the grid too)
             y.grad = None
 

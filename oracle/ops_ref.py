@@ -475,14 +475,18 @@ class RefOps:
         xs = (torch.arange(ow + taps - 1) + ix0).clamp(0, fw - 1)
         return frame[:, :, ys][:, :, :, xs]
 
-    def sepconv_fwd(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0):
+    def sepconv_planar(self, n, oh, ow, taps):
+        return None           # (a workspace of the CUDA kernels; the restatement needs none)
+
+    def sepconv_fwd(self, frame, vert, horiz, oh, ow, gy0, gx0, iy0, ix0, planar=None):
         taps = vert.shape[3]
         inp = self._sep_input(frame, oh, ow, iy0, ix0, taps)
         v = _nchw(vert[:, gy0:gy0 + oh, gx0:gx0 + ow, :])
         h = _nchw(horiz[:, gy0:gy0 + oh, gx0:gx0 + ow, :])
         return sepconv_forward(inp, v, h)
 
-    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0):
+    def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0, planar=None,
+                    planar_valid=False, planar_grad=None):
         taps = vert.shape[3]
         oh, ow = grad_out.shape[2], grad_out.shape[3]
         inp = self._sep_input(frame, oh, ow, iy0, ix0, taps)

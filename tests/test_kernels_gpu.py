@@ -116,7 +116,18 @@ def test_conv_wgrad_simt_modes(cuda_ops, shape):
     w3d, wt3 = cuda_ops.empty_weight(cout, cin, k), cuda_ops.empty_weight(cin, cout, k)
     cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_SGD_SCALAR, w_in=wd, b_in=bd, w_out=w3d, b_out=b2d,
                                                   lr_w=lr.cuda(), lr_b=lr.cuda(), wt_out=wt3), engine=ENGINE_SIMT)
-    close(wt3, cuda_ops.weight_to_dgrad(w3d).cpu(), 0.0, "fused rotated weight == weight_to_dgrad(updated weight)")
+    close(wt3, cuda_ops.weight_to_dgrad(w3d, rnd=False).cpu(), 0.0,
+          "fused rotated weight == weight_to_dgrad(updated weight)")
+    # ... and, with a TF32-rounded fprop copy requested (wr_out), both copies are on the TF32 grid while the master
+    # copy w_out stays exact (TF32 operand convention, include/mi_b200.h)
+    w4d, wt4, wr4 = (cuda_ops.empty_weight(cout, cin, k), cuda_ops.empty_weight(cin, cout, k),
+                     cuda_ops.empty_weight(cout, cin, k))
+    cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_SGD_SCALAR, w_in=wd, b_in=bd, w_out=w4d, b_out=b2d,
+                                                  lr_w=lr.cuda(), lr_b=lr.cuda(), wt_out=wt4, wr_out=wr4),
+                        engine=ENGINE_SIMT)
+    close(w4d, w3d.cpu(), 0.0, "master copy unchanged by wr_out")
+    close(wr4, REF.round_tf32(w3d.cpu().contiguous()), 0.0, "wr_out == rn_tf32(w_out)")
+    close(wt4, cuda_ops.weight_to_dgrad(w3d, rnd=True).cpu(), 0.0, "rotated copy rounded with wr_out")
     with pytest.raises(Exception):      # only the SGD modes own an updated weight to rotate
         cuda_ops.conv_wgrad(xd, dyd, k, ld, WgradSpec(WG_STORE, grad_w=gwd, grad_b=gbd, wt_out=wt3), engine=ENGINE_SIMT)
     # pad lanes of the KRSC storage stay zero
@@ -127,7 +138,8 @@ def test_conv_wgrad_simt_modes(cuda_ops, shape):
 
 def test_weight_to_dgrad(cuda_ops):
     wc, wd = weight_pair(cuda_ops, 7, 5, 3, 11)
-    close(cuda_ops.weight_to_dgrad(wd), REF.weight_to_dgrad(wc), 0.0, "weight_to_dgrad")
+    close(cuda_ops.weight_to_dgrad(wd, rnd=False), REF.weight_to_dgrad(wc, rnd=False), 0.0, "weight_to_dgrad")
+    close(cuda_ops.weight_to_dgrad(wd, rnd=True), REF.weight_to_dgrad(wc, rnd=True), 0.0, "weight_to_dgrad, rounded")
 
 
 @pytest.mark.parametrize("c", [3, 32, 51])
@@ -189,10 +201,16 @@ def test_frames_to_canvas_and_windows(cuda_ops, mode, hw):
     close(cuda_ops.nhwc_window_to_nchw(cd, pt, pl, h, w), REF.nhwc_window_to_nchw(cc, pt, pl, h, w), 0.0, "window")
 
 
+@pytest.mark.parametrize("planar", [False, True])
 @pytest.mark.parametrize("geom", [dict(taps=51, c=3, h=40, w=70), dict(taps=51, c=3, h=9, w=33),
                                   dict(taps=5, c=2, h=6, w=7)])
-def test_sepconv_fused_geometry(cuda_ops, geom):
+def test_sepconv_fused_geometry(cuda_ops, geom, planar):
+    """Both kernel generations: filters read as NHWC rows (two pixels per thread) and, with the tap-planar workspace,
+    four pixels per thread; the backward with the planar filters left by the forward and re-made by itself; rounded
+    gradients on request."""
     taps, c, h, w = geom["taps"], geom["c"], geom["h"], geom["w"]
+    if planar and taps != 51:
+        pytest.skip("the planar kernels exist for F = 51, c = 3")
     pad = taps // 2
     gh, gw = h + 2 * pad + 3, w + 2 * pad + 5
     g = torch.Generator().manual_seed(22)
@@ -200,15 +218,27 @@ def test_sepconv_fused_geometry(cuda_ops, geom):
     vc, vd = act_pair(cuda_ops, 2, gh, gw, taps, 23, 0.2)
     hc, hd = act_pair(cuda_ops, 2, gh, gw, taps, 24, 0.2)
     oc = REF.sepconv_fwd(frame, vc, hc, h, w, pad, pad, -pad, -pad)
-    od = cuda_ops.sepconv_fwd(frame.cuda(), vd, hd, h, w, pad, pad, -pad, -pad)
+    ws = cuda_ops.sepconv_planar(2, h, w, taps) if planar else None
+    od = cuda_ops.sepconv_fwd(frame.cuda(), vd, hd, h, w, pad, pad, -pad, -pad, planar=ws)
     close(od, oc, 2e-5, "sepconv fwd")
     go = torch.rand(2, c, h, w, generator=g) - 0.5
     gvc, ghc = REF.zeros_act(2, gh, gw, taps), REF.zeros_act(2, gh, gw, taps)
     gvd, ghd = cuda_ops.zeros_act(2, gh, gw, taps), cuda_ops.zeros_act(2, gh, gw, taps)
     REF.sepconv_bwd(frame, vc, hc, go, gvc, ghc, pad, pad, -pad, -pad)
-    cuda_ops.sepconv_bwd(frame.cuda(), vd, hd, go.cuda(), gvd, ghd, pad, pad, -pad, -pad)
+    scratch = cuda_ops.sepconv_planar(2, h, w, taps) if planar else None
+    cuda_ops.sepconv_bwd(frame.cuda(), vd, hd, go.cuda(), gvd, ghd, pad, pad, -pad, -pad, planar=ws,
+                         planar_valid=planar, planar_grad=scratch)
     close(gvd, gvc, 3e-5, "sepconv gV")
     close(ghd, ghc, 3e-5, "sepconv gH")
+    if planar:      # a backward that has to transpose the filters itself, with rounded outputs
+        ws2 = cuda_ops.sepconv_planar(2, h, w, taps)
+        gv2, gh2 = cuda_ops.zeros_act(2, gh, gw, taps), cuda_ops.zeros_act(2, gh, gw, taps)
+        cuda_ops.sepconv_bwd(frame.cuda(), vd, hd, go.cuda(), gv2, gh2, pad, pad, -pad, -pad, rnd=True, planar=ws2,
+                             planar_valid=False, planar_grad=scratch)
+        close(gv2, REF.round_tf32(gvc.clone().contiguous()), 3e-4, "sepconv gV, rounded")
+        assert torch.equal(gv2.contiguous(), cuda_ops.round_tf32(gv2.contiguous().clone())) or not cuda_ops.tf32_rn
+        # outside the window nothing was written
+        assert float(gv2[:, :pad].abs().max()) == 0.0 and float(gh2[:, :, :pad].abs().max()) == 0.0
 
 
 def test_function_sepconv_dropin_matches_reference_op(cuda_ops):

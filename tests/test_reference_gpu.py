@@ -86,9 +86,11 @@ def test_fused_canvas_geometry_against_reference_padding_chain(cuda_ops, ref_sep
     rgv, rgh = torch.autograd.grad(ref_out, (vv, hh), go)
     vn = ops.empty_act(n, 384, 512, 51); vn.copy_(v.permute(0, 2, 3, 1))
     hn = ops.empty_act(n, 384, 512, 51); hn.copy_(h.permute(0, 2, 3, 1))
-    out = ops.sepconv_fwd(frame, vn, hn, H, W, 25, 25, -25, -25)
+    ws = ops.sepconv_planar(n, H, W, 51)          # the four-pixels-per-thread kernels (what the backbone runs)
+    out = ops.sepconv_fwd(frame, vn, hn, H, W, 25, 25, -25, -25, planar=ws)
     gv, gh = ops.zeros_act(n, 384, 512, 51), ops.zeros_act(n, 384, 512, 51)
-    ops.sepconv_bwd(frame, vn, hn, go, gv, gh, 25, 25, -25, -25)
+    ops.sepconv_bwd(frame, vn, hn, go, gv, gh, 25, 25, -25, -25, planar=ws, planar_valid=True,
+                    planar_grad=ops.sepconv_planar(n, H, W, 51))
     torch.cuda.synchronize()
     assert (out - ref_out).abs().max().item() <= 2e-5 * ref_out.abs().max().item()
     for name, a, b in (("gV", gv, rgv), ("gH", gh, rgh)):

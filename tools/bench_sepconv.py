@@ -31,12 +31,16 @@ def main():
     go = torch.rand(n, 3, h, w, device="cuda")
     gv, ghh = ops.zeros_act(n, gh, gw, 51), ops.zeros_act(n, gh, gw, 51)
     px = n * h * w
-    ms = timeit(lambda: ops.sepconv_fwd(frame, v, hh, h, w, 1, 1, -25, -25))
-    print("MINB=%s fwd %7.1f us  %5.1f TFLOP/s fp32" % (os.environ.get("MI_B200_SEPCONV_MINB"), ms * 1e3,
-                                                       2.0 * px * (3 * 51 * 51 + 3 * 51) / ms / 1e9))
-    ms = timeit(lambda: ops.sepconv_bwd(frame, v, hh, go, gv, ghh, 1, 1, -25, -25))
-    print("MINB=%s bwd %7.1f us  %5.1f TFLOP/s fp32" % (os.environ.get("MI_B200_SEPCONV_MINB"), ms * 1e3,
-                                                       2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51) / ms / 1e9))
+    for planar in (False, True):
+        ws = ops.sepconv_planar(n, h, w, 51) if planar else None
+        ws2 = ops.sepconv_planar(n, h, w, 51) if planar else None
+        tag = "planar filters, 4 px/thread (transposes included)" if planar else "NHWC filters, 2 px/thread"
+        ms = timeit(lambda: ops.sepconv_fwd(frame, v, hh, h, w, 1, 1, -25, -25, planar=ws))
+        print("%-52s fwd %7.1f us  %5.1f TFLOP/s fp32" % (tag, ms * 1e3, 2.0 * px * (3 * 51 * 51 + 3 * 51) / ms / 1e9))
+        ms = timeit(lambda: ops.sepconv_bwd(frame, v, hh, go, gv, ghh, 1, 1, -25, -25, planar=ws, planar_valid=planar,
+                                            planar_grad=ws2))
+        print("%-52s bwd %7.1f us  %5.1f TFLOP/s fp32" % (tag, ms * 1e3,
+                                                         2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51) / ms / 1e9))
 
 
 if __name__ == "__main__":

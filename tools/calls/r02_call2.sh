@@ -2,8 +2,8 @@
 # round 2, GPU call 2: TF32 round-to-nearest operand convention -- parity, A/B against truncation, cost
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_full_size.jsonl
-python -m pytest tests -m gpu -q --timeout 900 -x > gpurun_out/r02_t2_all.log 2>&1
-echo "all rc=$?"; tail -12 gpurun_out/r02_t2_all.log
+python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/r02_t2_all.log 2>&1
+echo "all rc=$?"; tail -30 gpurun_out/r02_t2_all.log | cut -c1-300
 cp gpurun_out/parity_full_size.jsonl gpurun_out/r02_parity_full_size_rn.jsonl
 rm -f gpurun_out/parity_full_size.jsonl
 MI_B200_TF32_RN=0 python -m pytest tests/test_system_gpu.py -m gpu -q --timeout 900 -k "full_size_train_iter" > gpurun_out/r02_t2_trunc.log 2>&1
