@@ -1009,6 +1009,8 @@ conv_fprop_tc_halo_stream_kernel(const __grid_constant__ CUtensorMap map_x, cons
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)(2 * HS_BN));
 }
 
+#include "conv_tc_kxs.cuh"
+
 // ------------------------------------------------------------------------------------------ fprop, 5x5 / 7x7
 // The 5x5 / 7x7 layers of superslomo and voxelflow.  Their filter bank is too large for a pipeline stage (49 taps x 32
 // couts x 128 B = 196 KB per 32-channel chunk), so it streams one FILTER ROW at a time: the halo box of a chunk
@@ -1645,6 +1647,120 @@ int num_sms() {
     return v;
 }
 
+// Filter-column-stacked 3x3 kernel (conv_tc_kxs.cuh).  MI_B200_KXS=0 keeps the halo kernels (A/B switch), =2 forces the
+// stacked kernel even where its 14-of-16-column tiles cover the image worse than the 8x16 halo tiles, =3 additionally
+// forces its generic (per-thread store) epilogue.
+int kxs_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MI_B200_KXS");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+bool kxs_enabled(int n, int h, int wd) {
+    // Measured on B200 (tools/bench_conv.py, profiles/r02_conv_kxs_vs_halo.txt): faster than the halo kernels on every
+    // SepConv layer shape, including the 12x16 / 24x32 ones where 14-column tiles cover the image badly (more, shorter
+    // work items there), so the stacked kernel takes every eligible 3x3 layer.
+    (void)n; (void)h; (void)wd;
+    return kxs_mode() != 0;
+}
+
+int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
+               const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd,
+               int cin, int cout, int act, float slope, cudaStream_t stream) {
+    const bool stream_w = cin > 64 || cout > 64;
+    KxsParams kp;
+    kp.n = n; kp.h = h; kp.w = wd; kp.cin = cin; kp.cout = cout;
+    kp.chunks = mi_cdiv(cin, KCH);
+    kp.bn = stream_w ? 64 : (cout <= 32 ? 32 : 64);
+    kp.tiles_x = mi_cdiv(wd, KX_OW);
+    kp.tiles_y = mi_cdiv(h, KX_H);
+    kp.total_tiles = kp.tiles_x * kp.tiles_y * n;
+    kp.n_tiles = stream_w ? mi_cdiv(cout, kp.bn) : 1;
+    kp.items = kp.total_tiles * kp.n_tiles;
+    kp.act = act; kp.slope = slope; kp.accumulate = accumulate; kp.mask_act = mask_act; kp.rnd = mi_tf32_rn_enabled();
+    kp.mask_slope = mask_slope; kp.ldy = ldy; kp.ldmask = ldmask; kp.bias = bias; kp.mask_y = mask_y; kp.y = y;
+    const size_t b_chunk = (size_t)9 * kp.bn * ROW_BYTES;
+    // dynamic shared memory: [resident weights] [S stages] [epilogue staging 28 KB] [barriers] + 1 KB alignment slack;
+    // 227 KB per CTA minus the static part (bias table)
+    const size_t budget = 227 * 1024 - 3072 - 128;   // static: bias table, tmem slot, alignment
+    const size_t fixed = KX_STAGING + 256 + 1024;
+    size_t smem;
+    if (stream_w) {
+        kp.stages = 2;
+        smem = 2 * (KX_BOX_BYTES + b_chunk) + fixed;
+        if (smem > budget) return MI_ERR_UNSUPPORTED;
+    } else {
+        const size_t b_total = kp.chunks * b_chunk;
+        int stages = (int)((budget - fixed - b_total) / KX_BOX_BYTES);
+        if (stages > 4) stages = 4;
+        if (stages < 2) return MI_ERR_UNSUPPORTED;
+        kp.stages = stages;
+        smem = b_total + (size_t)stages * KX_BOX_BYTES + fixed;
+    }
+    const bool vec = aligned_view(y, ldy) && (!mask_y || aligned_view(mask_y, ldmask));
+    int epi = KXS_EPI_GENERIC;
+    if (vec && kxs_mode() != 3) {
+        if (!mask_y && !accumulate) epi = KXS_EPI_PLAIN;
+        else if (!(mask_y && accumulate)) epi = KXS_EPI_OPERAND;
+    }
+    CUtensorMap map_x, map_w, map_y, map_op;
+    if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, KX_W, KX_BOX_H)) return MI_ERR_UNSUPPORTED;
+    if (!make_weight_map(&map_w, w, ldw, cout, 9, cin, kp.bn)) return MI_ERR_UNSUPPORTED;
+    if (epi != KXS_EPI_GENERIC) {
+        // (channels below cout & ~3 only: see the ragged-tail note in conv_tc_kxs.cuh)
+        if (!make_act_map(&map_y, y, ldy, n, h, wd, cout & ~3, KX_OW, KX_H)) return MI_ERR_UNSUPPORTED;
+        if (epi == KXS_EPI_OPERAND && mask_y) {
+            if (!make_act_map(&map_op, mask_y, ldmask, n, h, wd, cout & ~3, KX_OW, KX_H)) return MI_ERR_UNSUPPORTED;
+        } else {
+            map_op = map_y;
+        }
+    } else {
+        map_y = map_x; map_op = map_x;     // unused
+    }
+    typedef void (*KxsKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KxsParams);
+    static const KxsKernel kernels[2][3] = {
+        {conv_fprop_tc_kxs_kernel<false, 0>, conv_fprop_tc_kxs_kernel<false, 1>, conv_fprop_tc_kxs_kernel<false, 2>},
+        {conv_fprop_tc_kxs_kernel<true, 0>, conv_fprop_tc_kxs_kernel<true, 1>, conv_fprop_tc_kxs_kernel<true, 2>}};
+    static bool attr = false;
+    if (!attr) {
+        for (int a = 0; a < 2; ++a)
+            for (int b = 0; b < 3; ++b) {
+                cudaError_t e = cudaFuncSetAttribute(kernels[a][b], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)budget);
+                if (e != cudaSuccess) return (int)e;
+            }
+        attr = true;
+    }
+    const int grid = kp.items < num_sms() ? kp.items : num_sms();
+    static unsigned long long* dbg_buf = nullptr;
+    static int dbg_on = -1;
+    if (dbg_on < 0) { const char* e = getenv("MI_B200_DEBUG_TIMING"); dbg_on = (e && e[0] == '1') ? 1 : 0; }
+    kp.dbg = nullptr;
+    if (dbg_on) {
+        if (!dbg_buf) cudaMalloc(&dbg_buf, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), stream);
+        kp.dbg = dbg_buf;
+    }
+    mi_prof_begin(stream_w ? MI_TAG_FPROP_STREAM : MI_TAG_FPROP_HALO, mi_conv_flops(n, h, wd, cin, cout, 3),
+                  mi_conv_bytes(n, h, wd, cin, cout, 3), stream);
+    kernels[stream_w ? 1 : 0][epi]<<<grid, HALO_THREADS, smem, stream>>>(map_x, map_w, map_y, map_op, kp);
+    mi_prof_end(stream);
+    if (dbg_on) {
+        unsigned long long d[16];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(d, dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[kxs%s cta0] items=%llu producer: wait_empty=%llu total=%llu | mma: wait_weights=%llu "
+                "wait_full=%llu wait_tmem_empty=%llu total=%llu | epilogue: wait_acc=%llu tmem_ld=%llu "
+                "math+store=%llu total=%llu cycles (stages=%d bn=%d chunks=%d n_tiles=%d grid=%d epi=%d)\n",
+                stream_w ? "-stream" : "", d[10], d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], kp.stages,
+                kp.bn, kp.chunks, kp.n_tiles, grid, epi);
+    }
+    MI_LAUNCHED();
+    MI_RETURN_LAST();
+}
+
 }  // namespace
 
 bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, const float* y, int ldy, int n, int h,
@@ -1661,6 +1777,11 @@ bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, cons
 int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                 const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd,
                 int cin, int cout, int k, int act, float slope, cudaStream_t stream) {
+    if (k == 3 && cout <= 512 && kxs_enabled(n, h, wd)) {
+        const int rc = launch_kxs(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask, mask_act, mask_slope, accumulate, n, h, wd,
+                                  cin, cout, act, slope, stream);
+        if (rc != MI_ERR_UNSUPPORTED) return rc;
+    }
     if (k == 3 && cin <= 64 && cout <= 64 && halo_enabled()) {
         HaloParams hp;
         hp.n = n; hp.h = h; hp.w = wd; hp.cin = cin; hp.cout = cout;

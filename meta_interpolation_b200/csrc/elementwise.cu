@@ -56,17 +56,18 @@ __device__ __forceinline__ void st4(float* p, F4 r, int valid, bool vec, int rnd
 #define MI_SPLIT_VEC_RND(vec, rnd) const int rnd = (vec) >> 1; (vec) &= 1
 
 // ----------------------------------------------------------------------------- pooling
+template <typename IDX>
 __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
                                     int wd, int c, int vec) {
     MI_SPLIT_VEC_RND(vec, rnd);
     const int oh = h >> 1, ow = wd >> 1, cg = (c + 3) >> 2;
     const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
-        long long p = i / cg;
-        const int ox = (int)(p % ow); p /= ow;
-        const int oy = (int)(p % oh);
-        const int nn = (int)(p / oh);
+        const int g = (int)((IDX)i % (IDX)cg);
+        IDX p = (IDX)i / (IDX)cg;
+        const int ox = (int)(p % (IDX)ow); p /= (IDX)ow;
+        const int oy = (int)(p % (IDX)oh);
+        const int nn = (int)(p / (IDX)oh);
         const int valid = min(4, c - 4 * g);
         const float* s = x + ((long long)(nn * h + 2 * oy) * wd + 2 * ox) * ldx + 4 * g;
         const F4 a = ld4(s, valid, vec), b = ld4(s + ldx, valid, vec);
@@ -78,16 +79,17 @@ __global__ void avgpool2_fwd_kernel(const float* __restrict__ x, int ldx, float*
     }
 }
 
+template <typename IDX>
 __global__ void avgpool2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
                                     int accumulate, int n, int h, int wd, int c, int vec) {
     const int oh = h >> 1, ow = wd >> 1, cg = (c + 3) >> 2;
     const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
-        long long p = i / cg;
-        const int xx = (int)(p % wd); p /= wd;
-        const int yy = (int)(p % h);
-        const int nn = (int)(p / h);
+        const int g = (int)((IDX)i % (IDX)cg);
+        IDX p = (IDX)i / (IDX)cg;
+        const int xx = (int)(p % (IDX)wd); p /= (IDX)wd;
+        const int yy = (int)(p % (IDX)h);
+        const int nn = (int)(p / (IDX)h);
         const int valid = min(4, c - 4 * g);
         F4 v = ld4(dy + ((long long)(nn * oh + (yy >> 1)) * ow + (xx >> 1)) * lddy + 4 * g, valid, vec);
         float* d = dx + ((long long)(nn * h + yy) * wd + xx) * lddx + 4 * g;
@@ -176,17 +178,18 @@ __device__ __forceinline__ void up2_src(int o, int in_size, int align, int& i0, 
 // The plain x2 upsample is the window that covers everything.
 struct UpWin { int full_h, full_w, ly0, lx0, hy0, hx0, oh, ow; };
 
+template <typename IDX>
 __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int n, int h,
                                      int wd, int c, int align, int vec, UpWin g) {
     MI_SPLIT_VEC_RND(vec, rnd);
     const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * oh * ow * cg;
     GRID_STRIDE(i, total) {
-        const int gi = (int)(i % cg);
-        long long p = i / cg;
-        const int ox = (int)(p % ow); p /= ow;
-        const int oy = (int)(p % oh);
-        const int nn = (int)(p / oh);
+        const int gi = (int)((IDX)i % (IDX)cg);
+        IDX p = (IDX)i / (IDX)cg;
+        const int ox = (int)(p % (IDX)ow); p /= (IDX)ow;
+        const int oy = (int)(p % (IDX)oh);
+        const int nn = (int)(p / (IDX)oh);
         const int valid = min(4, c - 4 * gi);
         int y0, y1, x0, x1; float ty, tx;
         up2_src(oy + g.hy0, g.full_h, align, y0, y1, ty);
@@ -208,6 +211,7 @@ __global__ void upsample2_fwd_kernel(const float* __restrict__ x, int ldx, float
 // inputs (i0,i1); the outputs that can touch input i lie within [2i-3, 2i+3]; membership is tested exactly.
 // Optional mask: `mask_y` is the post-activation tensor whose x2 upsampling is being differentiated (same shape as
 // dx); the result is then the gradient w.r.t. its PRE-activation, which saves the separate act_bwd pass.
+template <typename IDX>
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
                                      int accumulate, int n, int h, int wd, int c, int align, int vec, UpWin g,
                                      const float* __restrict__ mask_y, int ldmask, int mask_act, float mask_slope) {
@@ -215,11 +219,11 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
     const int oh = g.oh, ow = g.ow, cg = (c + 3) >> 2;
     const long long total = (long long)n * h * wd * cg;
     GRID_STRIDE(i, total) {
-        const int gi = (int)(i % cg);
-        long long p = i / cg;
-        const int xx = (int)(p % wd); p /= wd;
-        const int yy = (int)(p % h);
-        const int nn = (int)(p / h);
+        const int gi = (int)((IDX)i % (IDX)cg);
+        IDX p = (IDX)i / (IDX)cg;
+        const int xx = (int)(p % (IDX)wd); p /= (IDX)wd;
+        const int yy = (int)(p % (IDX)h);
+        const int nn = (int)(p / (IDX)h);
         const int valid = min(4, c - 4 * gi);
         const int gy = yy + g.ly0, gx = xx + g.lx0;          // position on the full low-resolution grid
         float wy[6]; int oy_[6]; int ny = 0;
@@ -265,17 +269,18 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
 }
 
 // dst window (+)= src window, both NHWC buffers with their own extents (crop of a region of interest and its adjoint)
+template <typename IDX>
 __global__ void window_copy_kernel(const float* __restrict__ s, int lds, int sh, int sw, int sy0, int sx0,
                                    float* __restrict__ d, int ldd, int dh, int dw, int dy0, int dx0, int n, int h,
                                    int w, int c, int accumulate, int vec) {
     const int cg = (c + 3) >> 2;
     const long long total = (long long)n * h * w * cg;
     GRID_STRIDE(i, total) {
-        const int gi = (int)(i % cg);
-        long long p = i / cg;
-        const int xx = (int)(p % w); p /= w;
-        const int yy = (int)(p % h);
-        const int nn = (int)(p / h);
+        const int gi = (int)((IDX)i % (IDX)cg);
+        IDX p = (IDX)i / (IDX)cg;
+        const int xx = (int)(p % (IDX)w); p /= (IDX)w;
+        const int yy = (int)(p % (IDX)h);
+        const int nn = (int)(p / (IDX)h);
         const int valid = min(4, c - 4 * gi);
         F4 v = ld4(s + (((long long)nn * sh + sy0 + yy) * sw + sx0 + xx) * lds + 4 * gi, valid, vec);
         float* q4 = d + (((long long)nn * dh + dy0 + yy) * dw + dx0 + xx) * ldd + 4 * gi;
@@ -289,33 +294,35 @@ __global__ void window_copy_kernel(const float* __restrict__ s, int lds, int sh,
 }
 
 // ----------------------------------------------------------------------------- simple pointwise
+template <typename IDX>
 __global__ void add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
                            float* __restrict__ y, int ldy, long long pixels, int c, int vec) {
     MI_SPLIT_VEC_RND(vec, rnd);
     const int cg = (c + 3) >> 2;
     const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
-        const long long p = i / cg;
+        const int g = (int)((IDX)i % (IDX)cg);
+        const IDX p = (IDX)i / (IDX)cg;
         const int valid = min(4, c - 4 * g);
-        const F4 u = ld4(a + p * lda + 4 * g, valid, vec), v = ld4(b + p * ldb + 4 * g, valid, vec);
+        const F4 u = ld4(a + (long long)p * lda + 4 * g, valid, vec), v = ld4(b + (long long)p * ldb + 4 * g, valid, vec);
         F4 o;
 #pragma unroll
         for (int q = 0; q < 4; ++q) o.v[q] = u.v[q] + v.v[q];
-        st4(y + p * ldy + 4 * g, o, valid, vec, rnd);
+        st4(y + (long long)p * ldy + 4 * g, o, valid, vec, rnd);
     }
 }
 
+template <typename IDX>
 __global__ void copy_kernel(const float* __restrict__ s, int lds, float* __restrict__ d, int ldd, int accumulate,
                             long long pixels, int c, int vec) {
     const int cg = (c + 3) >> 2;
     const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
-        const long long p = i / cg;
+        const int g = (int)((IDX)i % (IDX)cg);
+        const IDX p = (IDX)i / (IDX)cg;
         const int valid = min(4, c - 4 * g);
-        F4 v = ld4(s + p * lds + 4 * g, valid, vec);
-        float* q4 = d + p * ldd + 4 * g;
+        F4 v = ld4(s + (long long)p * lds + 4 * g, valid, vec);
+        float* q4 = d + (long long)p * ldd + 4 * g;
         if (accumulate) {
             const F4 o = ld4(q4, valid, vec);
 #pragma unroll
@@ -325,23 +332,24 @@ __global__ void copy_kernel(const float* __restrict__ s, int lds, float* __restr
     }
 }
 
+template <typename IDX>
 __global__ void act_bwd_kernel(float* __restrict__ dy, int lddy, const float* __restrict__ y, int ldy, int act,
                                float slope, long long pixels, int c, int vec, int rnd) {
     const int cg = (c + 3) >> 2;
     const long long total = pixels * cg;
     GRID_STRIDE(i, total) {
-        const int g = (int)(i % cg);
-        const long long p = i / cg;
+        const int g = (int)((IDX)i % (IDX)cg);
+        const IDX p = (IDX)i / (IDX)cg;
         const int valid = min(4, c - 4 * g);
-        F4 d = ld4(dy + p * lddy + 4 * g, valid, vec);
-        const F4 v = ld4(y + p * ldy + 4 * g, valid, vec);
+        F4 d = ld4(dy + (long long)p * lddy + 4 * g, valid, vec);
+        const F4 v = ld4(y + (long long)p * ldy + 4 * g, valid, vec);
 #pragma unroll
         for (int q = 0; q < 4; ++q) d.v[q] *= mi_act_grad(v.v[q], act, slope);
         if (rnd) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) d.v[q] = mi_rn_tf32(d.v[q]);
         }
-        st4(dy + p * lddy + 4 * g, d, valid, vec);
+        st4(dy + (long long)p * lddy + 4 * g, d, valid, vec);
     }
 }
 
@@ -656,6 +664,18 @@ static inline bool mi_vec_ok(const void* p, int ld, int c) {
         MI_RETURN_LAST();                                                      \
     } while (0)
 
+// 32-bit index arithmetic whenever the work fits (always, for the tensors of this path): the 64-bit divisions of the
+// index decomposition were most of the instructions of the resampling kernels
+#define LAUNCH_IDX(kernel, work, stream, ...)                                           \
+    do {                                                                                \
+        if ((long long)(work) < (1LL << 31))                                            \
+            kernel<unsigned><<<grid_for(work), TPB, 0, mi_cs(stream)>>>(__VA_ARGS__);   \
+        else                                                                            \
+            kernel<long long><<<grid_for(work), TPB, 0, mi_cs(stream)>>>(__VA_ARGS__);  \
+        MI_LAUNCHED();                                                                  \
+        MI_RETURN_LAST();                                                               \
+    } while (0)
+
 static inline int mi_rnd_bit(int round_tf32) { return (round_tf32 && mi_tf32_rn_enabled()) ? 2 : 0; }
 
 extern "C" {
@@ -664,13 +684,13 @@ int mi_avgpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, in
                     mi_stream_t s) {
     if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
     const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
-    LAUNCH(avgpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, vec);
+    LAUNCH_IDX(avgpool2_fwd_kernel, (long long)n * (h / 2) * (wd / 2) * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, vec);
 }
 int mi_avgpool2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                     mi_stream_t s) {
     if (!dy || !dx || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
     const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c);
-    LAUNCH(avgpool2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, vec);
+    LAUNCH_IDX(avgpool2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, vec);
 }
 int mi_maxpool2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, int wd, int c, mi_stream_t s) {
     if (!x || !y || (h & 1) || (wd & 1)) return MI_ERR_BAD_ARG;
@@ -687,14 +707,14 @@ int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, i
     if (!x || !y) return MI_ERR_BAD_ARG;
     const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
-    LAUNCH(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
+    LAUNCH_IDX(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                      int align, int round_tf32, mi_stream_t s) {
     if (!dy || !dx) return MI_ERR_BAD_ARG;
     const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd};
-    LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
+    LAUNCH_IDX(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
            vec, g, nullptr, 0, 0, 0.f);
 }
 static bool up_window_ok(int h, int wd, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0) {
@@ -707,7 +727,7 @@ int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, i
     if (!x || !y || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0)) return MI_ERR_BAD_ARG;
     const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
-    LAUNCH(upsample2_fwd_kernel, (long long)n * oh * ow * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
+    LAUNCH_IDX(upsample2_fwd_kernel, (long long)n * oh * ow * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
                             int align, int full_h, int full_w, int ly0, int lx0, int oh, int ow, int hy0, int hx0,
@@ -717,7 +737,7 @@ int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int 
         return MI_ERR_BAD_ARG;
     const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow};
-    LAUNCH(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
+    LAUNCH_IDX(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
            vec, g, mask_y, ldmask, mask_act, mask_slope);
 }
 int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, float* dst, int ldd, int dh, int dw,
@@ -726,26 +746,26 @@ int mi_window_copy(const float* src, int lds, int sh, int sw, int sy0, int sx0, 
         sy0 + h > sh || sx0 + wd > sw || dy0 + h > dh || dx0 + wd > dw)
         return MI_ERR_BAD_ARG;
     const int vec = mi_vec_ok(src, lds, c) && mi_vec_ok(dst, ldd, c);
-    LAUNCH(window_copy_kernel, (long long)n * h * wd * ((c + 3) / 4), s, src, lds, sh, sw, sy0, sx0, dst, ldd, dh, dw, dy0,
+    LAUNCH_IDX(window_copy_kernel, (long long)n * h * wd * ((c + 3) / 4), s, src, lds, sh, sw, sy0, sx0, dst, ldd, dh, dw, dy0,
            dx0, n, h, wd, c, accumulate, vec);
 }
 int mi_add(const float* a, int lda, const float* b, int ldb, float* y, int ldy, size_t pixels, int c, int round_tf32,
            mi_stream_t s) {
     if (!a || !b || !y) return MI_ERR_BAD_ARG;
     const int vec = (mi_vec_ok(a, lda, c) && mi_vec_ok(b, ldb, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
-    LAUNCH(add_kernel, (long long)pixels * ((c + 3) / 4), s, a, lda, b, ldb, y, ldy, (long long)pixels, c, vec);
+    LAUNCH_IDX(add_kernel, (long long)pixels * ((c + 3) / 4), s, a, lda, b, ldb, y, ldy, (long long)pixels, c, vec);
 }
 int mi_copy(const float* src, int lds, float* dst, int ldd, int accumulate, size_t pixels, int c, mi_stream_t s) {
     if (!src || !dst) return MI_ERR_BAD_ARG;
     const int vec = mi_vec_ok(src, lds, c) && mi_vec_ok(dst, ldd, c);
-    LAUNCH(copy_kernel, (long long)pixels * ((c + 3) / 4), s, src, lds, dst, ldd, accumulate, (long long)pixels, c, vec);
+    LAUNCH_IDX(copy_kernel, (long long)pixels * ((c + 3) / 4), s, src, lds, dst, ldd, accumulate, (long long)pixels, c, vec);
 }
 int mi_act_bwd(float* dy, int lddy, const float* y, int ldy, int act, float slope, size_t pixels, int c,
                int round_tf32, mi_stream_t s) {
     if (!dy || !y) return MI_ERR_BAD_ARG;
     if (act == MI_ACT_NONE && !round_tf32) return MI_OK;
     const int vec = mi_vec_ok(dy, lddy, c) && mi_vec_ok(y, ldy, c);
-    LAUNCH(act_bwd_kernel, (long long)pixels * ((c + 3) / 4), s, dy, lddy, y, ldy, act, slope, (long long)pixels, c, vec,
+    LAUNCH_IDX(act_bwd_kernel, (long long)pixels * ((c + 3) / 4), s, dy, lddy, y, ldy, act, slope, (long long)pixels, c, vec,
            round_tf32 && mi_tf32_rn_enabled());
 }
 int mi_fill(float* p, float v, size_t count, mi_stream_t s) {

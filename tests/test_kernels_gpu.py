@@ -262,9 +262,10 @@ def test_function_sepconv_dropin_matches_reference_op(cuda_ops):
         FunctionSepconv.apply(inp, v, h)   # CPU tensors: same error as the reference (sepconv.py:293-294)
 
 
+@pytest.mark.parametrize("c", [3, 4, 5, 1])      # 16-byte pixels take the vector kernels (c <= 4), c = 5 the scalar ones
 @pytest.mark.parametrize("variant,sx,sy", [(0, 1.0, 1.0), (1, -0.5, -0.5), (1, 0.5, 0.5)])
-def test_warp(cuda_ops, variant, sx, sy):
-    n, h, w, c = 2, 12, 17, 3
+def test_warp(cuda_ops, variant, sx, sy, c):
+    n, h, w = 2, 12, 17
     ic, idv = act_pair(cuda_ops, n, h, w, c, 26)
     fc, fd = act_pair(cuda_ops, n, h, w, 2, 27, 3.0 if variant == 0 else 0.6)
     close(cuda_ops.warp_fwd(idv, fd, variant, sx, sy), REF.warp_fwd(ic, fc, variant, sx, sy), 1e-5, "warp fwd")
@@ -273,6 +274,9 @@ def test_warp(cuda_ops, variant, sx, sy):
     REF.warp_bwd(ic, fc, goc, gfc, variant, sx, sy)
     cuda_ops.warp_bwd(idv, fd, god, gfd, variant, sx, sy)
     close(gfd, gfc, 2e-4, "warp flow grad")
+    REF.warp_bwd(ic, fc, goc, gfc, variant, sx, sy, accumulate=True)
+    cuda_ops.warp_bwd(idv, fd, god, gfd, variant, sx, sy, accumulate=True)
+    close(gfd, gfc, 2e-4, "warp flow grad, accumulated")
 
 
 def test_identity_flow_is_half_pixel_shift(cuda_ops):
