@@ -65,8 +65,8 @@ def roofline_section(system):
             fast.n_lanes = lanes_saved
     peaks = measured_peaks()
     total_ms = sum(v["ms"] for v in summ.values())
-    conv_tags = ("fprop_tc_halo", "fprop_tc_halo_stream", "fprop_tc", "wgrad_tc_kx", "wgrad_tc", "fprop_simt",
-                 "wgrad_simt")
+    conv_tags = ("fprop_tc_kxs", "fprop_tc_halo", "fprop_tc_halo_stream", "fprop_tc", "wgrad_tc_kx", "wgrad_tc",
+                 "fprop_simt", "wgrad_simt")
     dom = max(conv_tags, key=lambda t: summ[t]["ms"])
     d = summ[dom]
     achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
@@ -93,15 +93,18 @@ def roofline_section(system):
     }
 
 
-KERNEL_NAMES = {"fprop_tc_halo": "conv_fprop_tc_halo_kernel", "fprop_tc_halo_stream": "conv_fprop_tc_halo_stream_kernel",
+KERNEL_NAMES = {"fprop_tc_kxs": "conv_fprop_tc_kxs_kernel", "fprop_tc_halo": "conv_fprop_tc_halo_kernel", "fprop_tc_halo_stream": "conv_fprop_tc_halo_stream_kernel",
                 "fprop_tc": "conv_fprop_tc_kernel", "wgrad_tc_kx": "conv_wgrad_tc_kx_kernel",
                 "wgrad_tc": "conv_wgrad_tc_kernel", "fprop_simt": "conv_fprop_simt_kernel",
                 "wgrad_simt": "conv_wgrad_simt_kernel"}
 # filled from the committed ncu captures (profiles/); None = not captured this round.  The capture is of ONE launch
 # (named in NCU_TRAFFIC_LAUNCH, with its algorithmic bytes), while `achieved` averages all launches of the kernel.
-NCU_TRAFFIC_LAUNCH = {"fprop_tc_halo": "51->51 3x3 on the 258x450 region of interest, N=2: 10.9 GFLOP, 94.7 MB "
+NCU_TRAFFIC_LAUNCH = {"fprop_tc_kxs": "51->51 3x3 on the 258x450 region of interest, N=2: 10.9 GFLOP, 94.7 MB "
+                                      "algorithmic (profiles/r02_ncu_kxs_51x51_258x450.txt)",
+                      "fprop_tc_halo": "51->51 3x3 on the 258x450 region of interest, N=2: 10.9 GFLOP, 94.7 MB "
                                        "algorithmic (profiles/r01c_ncu_conv_fprop_halo_51x51_258x450.txt)"}
-NCU_TRAFFIC_BYTES = {"fprop_tc_halo": 48479488 + 6179072}   # dram read + write of that launch
+# dram read + write of that launch (the output of the layer mostly stays in L2, hence less than the algorithmic bytes)
+NCU_TRAFFIC_BYTES = {"fprop_tc_kxs": 48453376 + 6992128, "fprop_tc_halo": 48479488 + 6179072}
 
 
 # --------------------------------------------------------------------------------------------- CPU legs

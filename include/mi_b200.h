@@ -52,11 +52,25 @@ const char* mi_error_string(int code);
 unsigned long long mi_launch_count(void);
 /* 1 if the tcgen05 path was compiled in and the current device is sm_100 */
 int mi_tc_available(void);
+/* CTAs one persistent tensor-core launch may occupy (default and 0: every SM of the device; the environment variable
+ * MI_B200_SM_BUDGET overrides both).  The host side narrows it when several task lanes are in flight (one lane per
+ * task, meta_learning_system.py:383 loops over the tasks of a meta-batch): launches of different lanes then run side
+ * by side on disjoint SMs and each CTA walks more tiles, so per-CTA set-up is paid fewer times per layer.  Grid sizes
+ * are fixed when a launch is captured into a CUDA graph.  Returns the value in force. */
+int mi_set_sm_budget(int ctas);
+/* Pad-lane policy of the tensor-core convolutions.  NHWC rows are padded to a multiple of 4 channels (16-byte rows for
+ * TMA); a bulk tensor store clips its innermost dimension at 16-byte granularity, so storing a 51-channel row through
+ * TMA also writes lane 51.  Off (default): lanes past `cout` are never written -- they may be the first channels of a
+ * neighbouring concat slice -- and a ragged tail of 1-3 channels is stored with scalar accesses.  On: when the output
+ * row stride equals cout rounded up to 4, the caller states that those lanes are padding of this very tensor, and they
+ * are overwritten with zeros.  The host side switches it on around calls whose output it allocated itself (ops.py).
+ * Returns the previous value. */
+int mi_set_pad_lanes_scratch(int on);
 
 /* per-launch CUDA-event timing of the hot kernels (bench.py roofline section).  tag: 0 fprop/dgrad tcgen05 per-tap,
  * 1 wgrad tcgen05 per-tap, 2 fprop/dgrad SIMT, 3 wgrad SIMT, 4 sepconv fwd, 5 sepconv bwd, 6 wgrad finish,
  * 7 fprop/dgrad tcgen05 halo (resident weights), 8 fprop/dgrad tcgen05 halo (streamed weights), 9 wgrad tcgen05
- * filter-column.
+ * filter-column, 10 fprop/dgrad tcgen05 with the filter columns stacked along N (the default 3x3 engine).
  * out[4] = {launches, total ms, algorithmic flops, algorithmic bytes}.  Not usable under graph capture. */
 int mi_prof_enable(int on);
 int mi_prof_summary(int tag, double* out);

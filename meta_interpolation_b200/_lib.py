@@ -21,6 +21,8 @@ SIGNATURES = {
     "mi_error_string": (C.c_char_p, [_i]),
     "mi_launch_count": (C.c_ulonglong, []),
     "mi_tc_available": (_i, []),
+    "mi_set_sm_budget": (_i, [_i]),
+    "mi_set_pad_lanes_scratch": (_i, [_i]),
     "mi_prof_enable": (_i, [_i]),
     "mi_prof_summary": (_i, [_i, C.c_void_p]),
     "mi_conv2d_fprop": (_i, [_f, _i, _f, _i, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _fl, _i, _st]),

@@ -572,6 +572,30 @@ int mi_weight_to_dgrad_launch(const float* w, int ldw, float* wt, int ldwt, int 
     MI_RETURN_LAST();
 }
 
+// CTAs one persistent tensor-core launch may occupy (default: every SM).  With several task lanes in flight a smaller
+// budget lets the launches of different lanes run side by side on disjoint SMs: each CTA then walks more tiles, so the
+// per-CTA fixed costs (barrier / TMEM set-up, first operand loads, epilogue drain) are paid fewer times per layer.
+static int g_sm_count = 0, g_sm_env = -1, g_sm_budget = 0;
+static void sm_budget_init() {
+    if (g_sm_count) return;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    g_sm_count = sms > 0 ? sms : 148;
+    const char* e = getenv("MI_B200_SM_BUDGET");
+    g_sm_env = (e && atoi(e) > 0 && atoi(e) < g_sm_count) ? atoi(e) : 0;
+    g_sm_budget = g_sm_count;
+}
+int mi_sm_budget() {
+    sm_budget_init();
+    return g_sm_env ? g_sm_env : g_sm_budget;
+}
+extern "C" int mi_set_sm_budget(int ctas) {
+    sm_budget_init();
+    g_sm_budget = (ctas > 0 && ctas < g_sm_count) ? ctas : g_sm_count;
+    return mi_sm_budget();
+}
+
 int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
     const long long m_total = (long long)n * h * wd;
     if (small_cout_wgrad_ok(cin, cout, k)) {
@@ -586,7 +610,7 @@ int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
         const long long tiles = (long long)n * mi_cdiv(h, 8) * mi_cdiv(wd, 8);
         const long long per_split = (long long)k * mi_cdiv(cin, 64) * mi_cdiv(cout, 128);   // CTAs of one split-K slice
         long long s = tiles / 4;
-        const long long cap = 148 / per_split;
+        const long long cap = mi_sm_budget() / per_split;
         if (s > cap) s = cap;
         if (s < 1) s = 1;
         return (int)s;

@@ -1636,16 +1636,7 @@ int halo_pitch() {
     return v;
 }
 
-int num_sms() {
-    static int v = 0;
-    if (!v) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        if (v <= 0) v = 148;
-    }
-    return v;
-}
+int num_sms() { return mi_sm_budget(); }   // CTAs a persistent launch may occupy (conv_simt.cu)
 
 // Filter-column-stacked 3x3 kernel (conv_tc_kxs.cuh).  MI_B200_KXS=0 keeps the halo kernels (A/B switch), =2 forces the
 // stacked kernel even where its 14-of-16-column tiles cover the image worse than the 8x16 halo tiles, =3 additionally
@@ -1665,6 +1656,8 @@ bool kxs_enabled(int n, int h, int wd) {
     (void)n; (void)h; (void)wd;
     return kxs_mode() != 0;
 }
+
+int g_pad_lanes_scratch = 0;
 
 int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
                const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd,
@@ -1709,15 +1702,20 @@ int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bi
     if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, KX_W, KX_BOX_H)) return MI_ERR_UNSUPPORTED;
     if (!make_weight_map(&map_w, w, ldw, cout, 9, cin, kp.bn)) return MI_ERR_UNSUPPORTED;
     if (epi != KXS_EPI_GENERIC) {
-        // (channels below cout & ~3 only: see the ragged-tail note in conv_tc_kxs.cuh)
-        if (!make_act_map(&map_y, y, ldy, n, h, wd, cout & ~3, KX_OW, KX_H)) return MI_ERR_UNSUPPORTED;
+        // channels below cout & ~3 only (see the ragged-tail note in conv_tc_kxs.cuh) -- unless the pad lanes of the
+        // row are the caller's to overwrite (mi_set_pad_lanes_scratch), then the whole padded row goes through TMA
+        const int cpad = (cout + 3) & ~3;
+        const bool pad_ok = g_pad_lanes_scratch && ldy == cpad && (!mask_y || ldmask == cpad);
+        kp.c_tma = pad_ok ? cpad : (cout & ~3);
+        if (!make_act_map(&map_y, y, ldy, n, h, wd, kp.c_tma, KX_OW, KX_H)) return MI_ERR_UNSUPPORTED;
         if (epi == KXS_EPI_OPERAND && mask_y) {
-            if (!make_act_map(&map_op, mask_y, ldmask, n, h, wd, cout & ~3, KX_OW, KX_H)) return MI_ERR_UNSUPPORTED;
+            if (!make_act_map(&map_op, mask_y, ldmask, n, h, wd, kp.c_tma, KX_OW, KX_H)) return MI_ERR_UNSUPPORTED;
         } else {
             map_op = map_y;
         }
     } else {
         map_y = map_x; map_op = map_x;     // unused
+        kp.c_tma = cout & ~3;
     }
     typedef void (*KxsKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const KxsParams);
     static const KxsKernel kernels[2][3] = {
@@ -1743,9 +1741,9 @@ int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bi
         cudaMemsetAsync(dbg_buf, 0, 16 * sizeof(unsigned long long), stream);
         kp.dbg = dbg_buf;
     }
-    mi_prof_begin(stream_w ? MI_TAG_FPROP_STREAM : MI_TAG_FPROP_HALO, mi_conv_flops(n, h, wd, cin, cout, 3),
+    mi_prof_begin(MI_TAG_FPROP_KXS, mi_conv_flops(n, h, wd, cin, cout, 3),
                   mi_conv_bytes(n, h, wd, cin, cout, 3), stream);
-    kernels[stream_w ? 1 : 0][epi]<<<grid, HALO_THREADS, smem, stream>>>(map_x, map_w, map_y, map_op, kp);
+    kernels[stream_w ? 1 : 0][epi]<<<grid, KXS_THREADS, smem, stream>>>(map_x, map_w, map_y, map_op, kp);
     mi_prof_end(stream);
     if (dbg_on) {
         unsigned long long d[16];
@@ -1753,9 +1751,10 @@ int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bi
         cudaMemcpy(d, dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[kxs%s cta0] items=%llu producer: wait_empty=%llu total=%llu | mma: wait_weights=%llu "
                 "wait_full=%llu wait_tmem_empty=%llu total=%llu | epilogue: wait_acc=%llu tmem_ld=%llu "
-                "math+store=%llu total=%llu cycles (stages=%d bn=%d chunks=%d n_tiles=%d grid=%d epi=%d)\n",
+                "math+store=%llu total=%llu cycles (stages=%d bn=%d chunks=%d n_tiles=%d grid=%d epi=%d) | mma issue loops: "
+                "%llu cycles over %llu stages | epilogue leader: store wait_read=%llu staging wait=%llu\n",
                 stream_w ? "-stream" : "", d[10], d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], kp.stages,
-                kp.bn, kp.chunks, kp.n_tiles, grid, epi);
+                kp.bn, kp.chunks, kp.n_tiles, grid, epi, d[11], d[12], d[13], d[14]);
     }
     MI_LAUNCHED();
     MI_RETURN_LAST();
@@ -2104,3 +2103,9 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
 }
 
 extern "C" int mi_tc_available(void) { return (device_is_sm100() && encode_fn()) ? 1 : 0; }
+
+extern "C" int mi_set_pad_lanes_scratch(int on) {
+    const int prev = g_pad_lanes_scratch;
+    g_pad_lanes_scratch = on ? 1 : 0;
+    return prev;
+}

@@ -44,11 +44,16 @@ constexpr uint32_t KX_STAGING = 2 * KX_OUT_BOX;                      // two 32-c
 //                       thread combines its own 64 bytes in place; then the same bulk store
 //   2  generic          unaligned views, or mask and accumulate together: the per-thread path of the halo kernels
 enum { KXS_EPI_PLAIN = 0, KXS_EPI_OPERAND = 1, KXS_EPI_GENERIC = 2 };
+// warp 0 producer, warp 1 MMA, warps 2-9 epilogue, warp 10 output stores.  The store warp exists because the thread that
+// issues a bulk store has to wait until TMA has READ the staging tile before anyone may overwrite it (~1400 cycles
+// for two boxes, per-role counters); while an epilogue warp did that, its share of the NEXT accumulator stayed unread
+// in TMEM and the MMA lane waited for the buffer.
+constexpr int KXS_THREADS = 352;
 
 struct KxsParams {
     int rnd;
     int n, h, w, cin, cout, chunks, bn, stages, n_tiles, tiles_x, tiles_y, total_tiles, items, act, accumulate, mask_act,
-        ldy, ldmask;
+        ldy, ldmask, c_tma;             // c_tma: channels the TMA store / operand load covers (see the epilogue)
     unsigned long long* dbg;            // optional per-role cycle counters of CTA 0 (MI_B200_DEBUG_TIMING=1)
     float slope, mask_slope;
     const float* bias;
@@ -75,7 +80,9 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+// named barriers between the 8 epilogue warps and the store warp (288 threads): one side arrives, the other waits
+__device__ __forceinline__ void kxs_bar_sync(int id) { asm volatile("bar.sync %0, 288;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void kxs_bar_arrive(int id) { asm volatile("bar.arrive %0, 288;" ::"r"(id) : "memory"); }
 
 // sigmoid / tanh epilogues (a handful of head layers): out of line, so the hot epilogue stays small
 __device__ __noinline__ float kxs_act_rare(float v, int act, float slope) { return mi_act_apply(v, act, slope); }
@@ -92,7 +99,7 @@ __device__ __noinline__ float kxs_act_grad_rare(float y, int act, float slope) {
     }
 
 template <bool STREAM, int EPI>
-__global__ void __launch_bounds__(HALO_THREADS)
+__global__ void __launch_bounds__(KXS_THREADS)
 conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                          const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_op,
                          const KxsParams p) {
@@ -114,7 +121,7 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     const uint32_t tmem_cols = 2 * nstack <= 256 ? 256u : 512u;
 
     __shared__ float sbias[512];
-    for (int i = threadIdx.x; i < 512; i += HALO_THREADS) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
+    for (int i = threadIdx.x; i < 512; i += KXS_THREADS) sbias[i] = (p.bias && i < p.cout) ? p.bias[i] : 0.f;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
@@ -191,63 +198,74 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             p.dbg[0] = (unsigned long long)t_empty; p.dbg[1] = (unsigned long long)(clock64() - t_begin);
         }
     } else if (warp == 1) {
+        // The issuing lane's work BETWEEN two stages is on the critical path: tcgen05.mma blocks at issue once a couple
+        // of instructions are queued, so the tensor pipe runs dry while this warp walks from the last MMA of a stage
+        // to the first of the next (per-role counters: ~100 cycles per MMA inside the issue loop, i.e. the pipe's own
+        // pace, plus ~410 cycles per stage outside it).  Hence: stage slot / phase tracked incrementally (no div/mod),
+        // operand descriptors advanced from two bases built once, cycle counters only when debugging.
         const uint32_t idesc = instr_desc(BM, nstack, 0, 0);
+        const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
         const long long t_begin = clock64();
-        long long t_w = 0, t_full = 0, t_tmem = 0;
+        long long t_w = 0, t_full = 0, t_tmem = 0, t_issue = 0, c0 = 0;
         if (!STREAM) {
             mbar_wait(smem_u32(&bars[2 * S + 4]), 0);
             t_w = clock64() - t_begin;
             tc_fence_after();
             if (my_items == 0 && p.chunks > 1) mbar_wait(smem_u32(&bars[2 * S + 5]), 0);   // in-flight TMA must land
         }
-        const uint32_t b_base = smem_u32(smem);
+        const uint64_t ad_base = smem_desc(smem_u32(smem_a), 16, 1024);
+        const uint64_t bd_base = smem_desc(STREAM ? smem_u32(smem_a) + KX_BOX_BYTES : smem_u32(smem), 16, 1024);
+        const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
+        const uint32_t tfull0 = smem_u32(&bars[2 * S]), tempty0 = smem_u32(&bars[2 * S + 2]);
         const int last_ksteps = (p.cin - (p.chunks - 1) * KCH + 7) / 8;
-        int it = 0;
+        const int last_ch = p.chunks - 1;
+        int s = 0, it = 0;
+        uint32_t ph = 0, s_off = 0;                 // phase of stage slot s; byte offset of slot s
         for (int t = 0; t < my_items; ++t) {
             const int buf = t & 1;
-            const uint32_t use = (uint32_t)(t >> 1);
-            long long c0 = clock64();
-            mbar_wait(smem_u32(&bars[2 * S + 2 + buf]), (use & 1u) ^ 1u);   // epilogue drained this buffer
-            t_tmem += clock64() - c0;
+            if (dbg) c0 = clock64();
+            mbar_wait(tempty0 + 8u * (uint32_t)buf, (((uint32_t)t >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
+            if (dbg) t_tmem += clock64() - c0;
             tc_fence_after();
             const uint32_t d_addr = tmem_base + (uint32_t)(buf * nstack);
-            for (int ch = 0; ch < p.chunks; ++ch, ++it) {
-                const int s = it % S;
-                const uint32_t ph = (uint32_t)(it / S) & 1u;
-                c0 = clock64();
-                mbar_wait(smem_u32(&bars[s]), ph);
-                t_full += clock64() - c0;
+            for (int ch = 0; ch <= last_ch; ++ch, ++it) {
+                if (dbg) c0 = clock64();
+                mbar_wait(full0 + 8u * (uint32_t)s, ph);
+                if (dbg) t_full += clock64() - c0;
                 if (!STREAM && t == 0 && ch == 1) {
-                    c0 = clock64();
+                    if (dbg) c0 = clock64();
                     mbar_wait(smem_u32(&bars[2 * S + 5]), 0);      // second half of the filter bank
-                    t_w += clock64() - c0;
+                    if (dbg) t_w += clock64() - c0;
                 }
                 tc_fence_after();
+                if (dbg) c0 = clock64();
                 if (elect_one()) {
-                    const uint32_t a_base = smem_u32(smem_a + (size_t)s * stage_bytes);
-                    const uint64_t ad0 = smem_desc(a_base, 16, 1024);
-                    const uint64_t bd0 = smem_desc(STREAM ? a_base + KX_BOX_BYTES : b_base + (uint32_t)ch * b_chunk, 16, 1024);
-                    if (ch < p.chunks - 1 || last_ksteps == 4) { MI_KXS_MMAS(4) }
+                    const uint64_t ad0 = desc_advance(ad_base, s_off);
+                    const uint64_t bd0 = desc_advance(bd_base, STREAM ? s_off : (uint32_t)ch * b_chunk);
+                    if (ch < last_ch || last_ksteps == 4) { MI_KXS_MMAS(4) }
                     else if (last_ksteps == 3) { MI_KXS_MMAS(3) }
                     else if (last_ksteps == 2) { MI_KXS_MMAS(2) }
                     else { MI_KXS_MMAS(1) }
-                    umma_commit(smem_u32(&bars[S + s]));
-                    if (ch == p.chunks - 1) umma_commit(smem_u32(&bars[2 * S + buf]));
+                    umma_commit(empty0 + 8u * (uint32_t)s);
+                    if (ch == last_ch) umma_commit(tfull0 + 8u * (uint32_t)buf);
                 }
                 __syncwarp();
+                if (dbg) t_issue += clock64() - c0;
+                if (++s == S) { s = 0; s_off = 0; ph ^= 1u; } else { s_off += stage_bytes; }
             }
         }
-        if (p.dbg && blockIdx.x == 0 && lane == 0) {
+        if (dbg && lane == 0) {
             p.dbg[2] = (unsigned long long)t_w; p.dbg[3] = (unsigned long long)t_full;
             p.dbg[4] = (unsigned long long)t_tmem; p.dbg[5] = (unsigned long long)(clock64() - t_begin);
+            p.dbg[11] = (unsigned long long)t_issue; p.dbg[12] = (unsigned long long)it;
         }
-    } else {
+    } else if (warp < 10) {
         const int q = warp & 3;               // TMEM lane quarter this warp may read
         const int half = (warp - 2) >> 2;     // which 16-column half of every 32-column chunk it owns
         const int r = q * 32 + lane;
         const int row_i = r >> 4, col_i = r & 15;
         const bool col_ok = (col_i >= 1) && (col_i <= KX_OW);
-        long long e_wait = 0, e_ld = 0, e_st = 0;
+        long long e_wait = 0, e_ld = 0, e_st = 0, e_b1 = 0;
         const long long e_begin = clock64();
         EpiArgs ea;
         ea.cout = p.cout; ea.act = p.act; ea.mask_act = p.mask_act; ea.accumulate = p.accumulate; ea.rnd = p.rnd;
@@ -260,11 +278,12 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
         const uint32_t stg = smem_u32(staging);
         const uint32_t my_row = stg + (uint32_t)slot * ROW_BYTES;
         const uint32_t swz = (uint32_t)(slot & 7);
-        const bool leader = (warp == 2) && (lane == 0);
         // The tensor maps of y / the operand cover the channels below cout & ~3: TMA clips the innermost dimension at
         // 16-byte granularity (a 18-channel slice of a 20-channel buffer had its neighbours 18..19 overwritten), so a
         // ragged tail of 1-3 channels is stored by the thread that holds it, with plain scalar accesses.
-        const int c_tma = p.cout & ~3, c_tail = p.cout & 3;
+        // (When the caller owns the pad lanes of the row -- mi_set_pad_lanes_scratch -- c_tma is cout rounded UP to 4 and
+        // the pad lanes are stored as zeros.)
+        const int c_tma = p.c_tma, c_tail = c_tma < p.cout ? p.cout - c_tma : 0;
         const uint32_t op_bar = smem_u32(&bars[2 * S + 6]);
         auto item_coords = [&](int t, int& co0, int& x0, int& y0, int& img) {
             const int item = (int)blockIdx.x + t * (int)gridDim.x;
@@ -275,15 +294,6 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
             img = tile; x0 = tx_i * KX_OW; y0 = ty_i * KX_H;
         };
-        auto load_operand = [&](int t) {          // leader only: mask / previous-y boxes of item t into the staging tile
-            int co0, x0, y0, img;
-            item_coords(t, co0, x0, y0, img);
-            const int nbox = (p.bn > 32 && co0 + 32 < c_tma) ? 2 : 1;
-            mbar_expect_tx(op_bar, (uint32_t)nbox * KX_OUT_BOX);
-            for (int b = 0; b < nbox; ++b)
-                tma_load_4d(stg + (uint32_t)b * KX_OUT_BOX, &map_op, op_bar, co0 + 32 * b, x0, y0, img);
-        };
-        if (EPI == KXS_EPI_OPERAND && leader && my_items > 0) load_operand(0);
         for (int t = 0; t < my_items; ++t) {
             const int buf = t & 1;
             const uint32_t use = (uint32_t)(t >> 1);
@@ -354,8 +364,10 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                     }
                 }
             } else {
+                const long long cb = clock64();
                 if (EPI == KXS_EPI_OPERAND) mbar_wait(op_bar, (uint32_t)t & 1u);   // operand landed => staging is ours
-                else epi_bar(1);                                                    // previous store has left the tile
+                else kxs_bar_sync(1);                                               // previous store has left the tile
+                e_b1 += clock64() - cb;
                 if (col_ok) {
 #pragma unroll
                     for (int pc = 0; pc < 2; ++pc) {
@@ -381,6 +393,13 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                                     }
                                 }
                                 if (ea.rnd) v = mi_rn_tf32(v);
+                                const int cg = co0 + 32 * pc + 16 * half + 4 * g;
+                                if (cg + 4 > p.cout) {              // pad lanes (and the channels past them) hold zeros
+                                    if (cg + 1 > p.cout) v.x = 0.f;
+                                    if (cg + 2 > p.cout) v.y = 0.f;
+                                    if (cg + 3 > p.cout) v.z = 0.f;
+                                    v.w = 0.f;
+                                }
                                 asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
                                              ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                             }
@@ -411,23 +430,65 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                     }
                 }
                 fence_async_smem();
-                epi_bar(2);
-                if (leader) {
-                    for (int b = 0; b < npiece; ++b)
-                        if (co0 + 32 * b < c_tma)
-                            tma_store_4d(&map_y, stg + (uint32_t)b * KX_OUT_BOX, co0 + 32 * b, x0, y0, img);
-                    tma_store_commit();
-                    tma_store_wait_read();
-                    if (EPI == KXS_EPI_OPERAND && t + 1 < my_items) load_operand(t + 1);
-                }
+                kxs_bar_arrive(2);                  // staged: the store warp takes it from here
             }
             e_st += clock64() - c1;
         }
-        if (EPI != KXS_EPI_GENERIC && leader) tma_store_wait_all();
         if (p.dbg && blockIdx.x == 0 && threadIdx.x == 64) {
             p.dbg[6] = (unsigned long long)e_wait; p.dbg[7] = (unsigned long long)e_ld;
             p.dbg[8] = (unsigned long long)e_st; p.dbg[9] = (unsigned long long)(clock64() - e_begin);
             p.dbg[10] = (unsigned long long)my_items;
+            p.dbg[14] = (unsigned long long)e_b1;
+        }
+    } else if (EPI != KXS_EPI_GENERIC) {
+        // store warp: per item, wait for the staged tile, issue one bulk store per 32-channel box, wait until TMA has
+        // read the tile, then hand it back -- as the landing zone of the next item's operand (mask / previous y), or
+        // plainly free
+        const uint32_t stg = smem_u32(staging);
+        const uint32_t op_bar = smem_u32(&bars[2 * S + 6]);
+        const int c_tma = p.c_tma;
+        long long e_wr = 0;
+        auto item_coords = [&](int t, int& co0, int& x0, int& y0, int& img) {
+            const int item = (int)blockIdx.x + t * (int)gridDim.x;
+            const int nt = STREAM ? item % p.n_tiles : 0;
+            co0 = nt * p.bn;
+            int tile = STREAM ? item / p.n_tiles : item;
+            const int tx_i = tile % p.tiles_x; tile /= p.tiles_x;
+            const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
+            img = tile; x0 = tx_i * KX_OW; y0 = ty_i * KX_H;
+        };
+        auto load_operand = [&](int t) {          // one lane: mask / previous-y boxes of item t into the staging tile
+            int co0, x0, y0, img;
+            item_coords(t, co0, x0, y0, img);
+            const int nbox = (p.bn > 32 && co0 + 32 < c_tma) ? 2 : 1;
+            mbar_expect_tx(op_bar, (uint32_t)nbox * KX_OUT_BOX);
+            for (int b = 0; b < nbox; ++b)
+                tma_load_4d(stg + (uint32_t)b * KX_OUT_BOX, &map_op, op_bar, co0 + 32 * b, x0, y0, img);
+        };
+        if (EPI == KXS_EPI_OPERAND) {
+            if (my_items > 0 && elect_one()) load_operand(0);
+            __syncwarp();
+        } else {
+            kxs_bar_arrive(1);                       // the staging tile starts out free
+        }
+        for (int t = 0; t < my_items; ++t) {
+            int co0, x0, y0, img;
+            item_coords(t, co0, x0, y0, img);
+            kxs_bar_sync(2);                         // all eight epilogue warps have staged item t
+            if (elect_one()) {
+                for (int b = 0; b < 2; ++b)
+                    if (32 * b < p.bn && co0 + 32 * b < c_tma)
+                        tma_store_4d(&map_y, stg + (uint32_t)b * KX_OUT_BOX, co0 + 32 * b, x0, y0, img);
+                tma_store_commit();
+                const long long cw = clock64();
+                tma_store_wait_read();
+                e_wr += clock64() - cw;
+                if (EPI == KXS_EPI_OPERAND && t + 1 < my_items) load_operand(t + 1);
+                if (t + 1 == my_items) tma_store_wait_all();
+                if (p.dbg && blockIdx.x == 0 && t + 1 == my_items) p.dbg[13] = (unsigned long long)e_wr;
+            }
+            __syncwarp();
+            if (EPI == KXS_EPI_PLAIN && t + 1 < my_items) kxs_bar_arrive(1);
         }
     }
     tc_fence_before();

@@ -18,7 +18,7 @@ extern std::atomic<unsigned long long> g_mi_launches;
 // per-launch profiling hooks (profile.cu); no-ops unless mi_prof_enable(1)
 enum { MI_TAG_FPROP_TC = 0, MI_TAG_WGRAD_TC = 1, MI_TAG_FPROP_SIMT = 2, MI_TAG_WGRAD_SIMT = 3, MI_TAG_SEPCONV_FWD = 4,
        MI_TAG_SEPCONV_BWD = 5, MI_TAG_WGRAD_FINISH = 6, MI_TAG_FPROP_HALO = 7, MI_TAG_FPROP_STREAM = 8,
-       MI_TAG_WGRAD_KX = 9 };
+       MI_TAG_WGRAD_KX = 9, MI_TAG_FPROP_KXS = 10 };
 void mi_prof_begin(int tag, double flops, double bytes, cudaStream_t s);
 void mi_prof_end(cudaStream_t s);
 static inline double mi_conv_flops(int n, int h, int w, int cin, int cout, int k) {
@@ -73,6 +73,7 @@ int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int
                            float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
                            float* gsum_b, float* wt_out, int ldwt, float* wr_out, cudaStream_t stream);
 int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k);
+int mi_sm_budget();
 
 // tcgen05 entry points (conv_tc.cu); return MI_ERR_UNSUPPORTED when the shape is not eligible
 int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,

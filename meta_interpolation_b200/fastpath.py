@@ -300,10 +300,16 @@ class FastPath:
         self.multi_term = len(terms) > 1
         self.meta_wt = {}
         self.meta_r = Arena(self.net.layout, self.ops.device) if self.ops.tf32_rn else self.net.arena
-        # measured on B200, SepConv 256x448 K=5: 1 lane 22.7, 2 lanes 27.9, 3 lanes 29.2, 4 lanes 30.1 tasks/s
-        lanes = os.environ.get('MI_B200_TASK_STREAMS', getattr(a, 'task_streams', 4))
+        # Lanes and the SM budget of a persistent tensor-core launch go together (measured on B200, SepConv 256x448
+        # K=5, 8 tasks per step, profiles/r02_sm_budget_sweep.txt): 4 lanes x 148 CTAs 43.8 tasks/s, 4 x 74 47.1,
+        # 8 x 50 49.0, 8 x 37 49.8, 8 x 24 50.4, 8 x 18 49.0, 8 x 12 42.7.  A conv CTA owns its SM (~220 KB of shared
+        # memory), so launches of different lanes never share one; with a quarter of the SMs each, four of them run
+        # side by side and every CTA walks four times as many tiles per set-up (barriers, TMEM, first operand loads,
+        # epilogue drain), which is what the 15-25 us launches of this path are short of.
+        lanes = os.environ.get('MI_B200_TASK_STREAMS', getattr(a, 'task_streams', 8))
         self.n_lanes = max(1, int(lanes)) if self.ops.name == 'cuda' else 1
         self.lanes = [_Lane(self, i) for i in range(self.n_lanes)]
+        self.sm_budget = 0                       # CTAs per persistent launch for the current call (0 = every SM)
 
     def refresh_meta_wt(self):
         """dgrad needs the rotated/transposed filter; for meta-parameters (un-routed tensors in support passes,
@@ -470,6 +476,7 @@ class FastPath:
         return body
 
     def _program(self, lane, key, body, n, h, w):
+        key = key + (self.sm_budget,)        # grid sizes are baked into the captured graph
         p = lane.programs.get(key)
         if p is None:
             p = _Program(lane, body, n, h, w)
@@ -580,9 +587,12 @@ class FastPath:
     # ------------------------------------------------------------------ meta-batch drivers
     def _run_tasks(self, frames, task_ids, num_steps, epoch, training, scale, msl, msl_w):
         """Deal the tasks round-robin to the lanes; lanes run concurrently on their own streams."""
-        losses_dev, preds = [None] * len(task_ids), [None] * len(task_ids)
         multi = self.n_lanes > 1
         main = torch.cuda.current_stream(self.ops.device) if multi else None
+        # host copy of the multi-step-loss weights, taken ONCE: reading a device scalar per step (`float(msl_w[step])`)
+        # is a stream synchronisation on the lane being fed, i.e. the host could not enqueue work for the other lanes
+        # and the tasks of an MSL run (BASELINE configs[4]) executed one after the other
+        msl_w = [float(v) for v in (msl_w.tolist() if torch.is_tensor(msl_w) else msl_w)]
         for lane in self.lanes:          # (run_test_iter never reads the log: start every meta-batch from zero)
             if lane.log_n:
                 lane.log_sum.zero_()
@@ -590,6 +600,21 @@ class FastPath:
         if multi:
             for lane in self.lanes:
                 lane.stream.wait_stream(main)      # inputs, zeroed gradients and rotated weights are ready
+        # lanes that will actually be busy share the SMs (see __init__): four ways with eight or more tasks in flight,
+        # two ways below that -- with as many tasks as shares the end of the meta-batch, where lanes run dry one by one,
+        # would leave most SMs idle (measured at 4 tasks: superslomo 35.3 / 37.8 / 37.1 and cain 18.5 / 19.7 / 18.0
+        # tasks/s for 1 / 2 / 4 shares, profiles/r02_sm_budget_sweep.txt)
+        busy = min(len(task_ids), self.n_lanes)
+        ways = 4 if busy >= 8 else (2 if busy >= 2 else 1)
+        self.sm_budget = self.ops.set_sm_budget(0) // ways if ways > 1 else 0
+        self.ops.set_sm_budget(self.sm_budget)
+        try:
+            return self._deal_tasks(frames, task_ids, num_steps, epoch, training, scale, msl, msl_w, multi, main)
+        finally:
+            self.ops.set_sm_budget(0)
+
+    def _deal_tasks(self, frames, task_ids, num_steps, epoch, training, scale, msl, msl_w, multi, main):
+        losses_dev, preds = [None] * len(task_ids), [None] * len(task_ids)
         for i, t in enumerate(task_ids):
             lane = self.lanes[i % self.n_lanes]
             if multi:

@@ -14,6 +14,7 @@ test-suite can inject the oracle's table (oracle/ops_ref.py) to check the host
 logic without a GPU; nothing in this package imports the oracle.
 """
 import os
+import weakref
 
 import torch
 
@@ -69,6 +70,7 @@ class CudaOps:
 
     def __init__(self, device=None, engine=ENGINE_AUTO):
         self.lib = _lib.load()
+        self._padded = {}        # data_ptr of a padded activation buffer -> (row stride, channels)
         if not torch.cuda.is_available():
             raise _lib.MiB200Error("CudaOps needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -95,12 +97,26 @@ class CudaOps:
             buf.fill_(float("nan"))
         if zero_pad and ld != c:
             buf[..., c:].zero_()
-        return buf[..., :c] if ld != c else buf
+        return self._padded_view(buf, c)
 
     def zeros_act(self, n, h, w, c):
-        ld = pad4(c)
-        buf = torch.zeros(n, h, w, ld, device=self.device, dtype=torch.float32)
-        return buf[..., :c] if ld != c else buf
+        buf = torch.zeros(n, h, w, pad4(c), device=self.device, dtype=torch.float32)
+        return self._padded_view(buf, c)
+
+    def _padded_view(self, buf, c):
+        """[..., :c] of a buffer this table allocated with 1-3 pad lanes per row.  The allocation is remembered (until
+        the buffer dies), so a tensor-core convolution writing into the view may be told that the pad lanes are its own
+        (mi_set_pad_lanes_scratch): a slice of somebody else's tensor with the same strides never qualifies."""
+        if buf.shape[-1] == c:
+            return buf
+        key = buf.data_ptr()
+        self._padded[key] = (buf.shape[-1], c)
+        weakref.finalize(buf, self._padded.pop, key, None)
+        return buf[..., :c]
+
+    def _owns_pad_lanes(self, t):
+        rec = self._padded.get(t.data_ptr())
+        return rec is not None and rec == (t.stride(-2), t.shape[-1]) and t.storage_offset() == 0
 
     def empty_like_act(self, t):
         n, h, w, c = t.shape
@@ -136,7 +152,7 @@ class CudaOps:
 
     # ------------------------------------------------------------------ per-launch profiling (bench roofline)
     PROF_TAGS = {"fprop_tc": 0, "wgrad_tc": 1, "fprop_simt": 2, "wgrad_simt": 3, "sepconv_fwd": 4, "sepconv_bwd": 5,
-                 "wgrad_finish": 6, "fprop_tc_halo": 7, "fprop_tc_halo_stream": 8, "wgrad_tc_kx": 9}
+                 "wgrad_finish": 6, "fprop_tc_halo": 7, "fprop_tc_halo_stream": 8, "wgrad_tc_kx": 9, "fprop_tc_kxs": 10}
 
     def prof_enable(self, on):
         _lib.check(self.lib.mi_prof_enable(1 if on else 0), "mi_prof_enable")
@@ -157,11 +173,22 @@ class CudaOps:
         cout, k = w.shape[0], w.shape[1]
         assert w.shape[3] == cin
         y = out if out is not None else self.empty_act(n, h, wd, cout)
-        _lib.check(self.lib.mi_conv2d_fprop(x.data_ptr(), _ld(x), w.data_ptr(), _ldw(w), self._p(b), y.data_ptr(),
-                                            _ld(y), n, h, wd, cin, cout, k, act, float(slope),
-                                            self.engine if engine is None else engine, self._stream()),
-                   "mi_conv2d_fprop")
+        scratch = (cout & 3) and self._owns_pad_lanes(y)
+        if scratch:
+            self.lib.mi_set_pad_lanes_scratch(1)
+        try:
+            rc = self.lib.mi_conv2d_fprop(x.data_ptr(), _ld(x), w.data_ptr(), _ldw(w), self._p(b), y.data_ptr(),
+                                          _ld(y), n, h, wd, cin, cout, k, act, float(slope),
+                                          self.engine if engine is None else engine, self._stream())
+        finally:
+            if scratch:
+                self.lib.mi_set_pad_lanes_scratch(0)
+        _lib.check(rc, "mi_conv2d_fprop")
         return y
+
+    def set_sm_budget(self, ctas):
+        """CTAs a persistent tensor-core launch may occupy from now on (0 = every SM); returns the value in force."""
+        return int(self.lib.mi_set_sm_budget(int(ctas)))
 
     def weight_to_dgrad(self, w, out=None, rnd=None):
         """Rotated / transposed copy of a KRSC weight for dgrad; rounded to the TF32 grid under ``tf32_rn``."""
@@ -195,11 +222,18 @@ class CudaOps:
             eng = self.engine if engine is None else engine
             wt = self.weight_to_dgrad(w, rnd=self.tf32_rn and eng != ENGINE_SIMT)
         dx = out if out is not None else self.empty_act(n, h, wd, cin)
-        _lib.check(self.lib.mi_conv2d_dgrad(dy.data_ptr(), _ld(dy), wt.data_ptr(), _ldw(wt), dx.data_ptr(), _ld(dx),
-                                            self._p(mask_y), 0 if mask_y is None else _ld(mask_y), mask_act,
-                                            float(mask_slope), 1 if accumulate else 0, n, h, wd, cin, cout, k,
-                                            self.engine if engine is None else engine, self._stream()),
-                   "mi_conv2d_dgrad")
+        scratch = (cin & 3) and self._owns_pad_lanes(dx)
+        if scratch:
+            self.lib.mi_set_pad_lanes_scratch(1)
+        try:
+            rc = self.lib.mi_conv2d_dgrad(dy.data_ptr(), _ld(dy), wt.data_ptr(), _ldw(wt), dx.data_ptr(), _ld(dx),
+                                          self._p(mask_y), 0 if mask_y is None else _ld(mask_y), mask_act,
+                                          float(mask_slope), 1 if accumulate else 0, n, h, wd, cin, cout, k,
+                                          self.engine if engine is None else engine, self._stream())
+        finally:
+            if scratch:
+                self.lib.mi_set_pad_lanes_scratch(0)
+        _lib.check(rc, "mi_conv2d_dgrad")
         return dx
 
     def conv_wgrad(self, x, dy, k, ldw, spec, engine=None):

@@ -116,6 +116,9 @@ class RefOps:
         out.copy_(y)
         return out
 
+    def set_sm_budget(self, ctas):
+        return 0          # (a launch-geometry hint of the CUDA table; nothing to do on the CPU)
+
     def weight_to_dgrad(self, w, out=None, rnd=None):
         cout, k, _, cin = w.shape
         wt = out if out is not None else self.empty_weight(cin, cout, k)
