@@ -255,8 +255,8 @@ def gpu_reference_section(our_e2e):
         env.pop(k, None)
     out = {}
     for tf32 in (True, False):
-        cmd = [sys.executable, script, "--model", "sepconv", "--batch", str(bench.TASKS_PER_GPU), "--steps", "3",
-               "--warmup", "2"] + ([] if tf32 else ["--no-tf32"])
+        cmd = [sys.executable, script, "--model", "sepconv", "--batch", str(bench.TASKS_PER_GPU), "--steps", "5",
+               "--warmup", "3"] + ([] if tf32 else ["--no-tf32"])
         try:
             res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
             line = json.loads(res.stdout.strip().splitlines()[-1]) if res.returncode == 0 else \
@@ -268,6 +268,6 @@ def gpu_reference_section(our_e2e):
     out["ratio_e2e_over_reference_tf32"] = round(our_e2e / ref, 2) if ref else None
     ref32 = out["fp32"].get("tasks_per_s")
     out["ratio_e2e_over_reference_fp32"] = round(our_e2e / ref32, 2) if ref32 else None
-    out["what"] = ("unmodified reference run_train_iter on this GPU: sepconv K=5 256x448, 8 tasks per step, 2 warm-up "
-                   "+ 3 timed steps, wall clock between torch.cuda.synchronize()")
+    out["what"] = ("unmodified reference run_train_iter on this GPU: sepconv K=5 256x448, 8 tasks per step, 3 warm-up "
+                   "+ 5 timed steps, wall clock between torch.cuda.synchronize()")
     return out

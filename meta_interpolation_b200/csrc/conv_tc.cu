@@ -1386,12 +1386,15 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Both single-lane roles run on warp-uniform control flow with elect.sync: under `if (lane == 0)` the compiler wraps
+    // every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop (seen in the SASS of the first version of this
+    // kernel), which with the rolled row loop made the issuing lane, not the tensor pipe, set the pace.
     if (warp == 0) {
-        if (lane == 0) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(smem_u32(&bars[p.stages + s]), ph ^ 1u);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(smem_u32(&bars[p.stages + s]), ph ^ 1u);
+            if (elect_one()) {
                 int t = t_begin + it;
                 const int tx_i = t % p.tiles_x; t /= p.tiles_x;
                 const int ty_i = t % p.tiles_y; t /= p.tiles_y;
@@ -1405,30 +1408,38 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 for (int j = 0; j < p.nb; ++j)
                     tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - pad, y0 - pad, img);
             }
+            __syncwarp();
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc(BM, (int)ncols, 1, 1);   // both operands MN-major, N = k taps x 32 channels
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % p.stages;
-                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                mbar_wait(smem_u32(&bars[s]), ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
-                // A: 4 MN blocks (32 couts each) one dY box apart; B: 3 MN blocks (ky = 0,1,2) one tile row apart.
-                // K = 8 pixels = one tile row = two 4-pixel swizzle atoms 512 B apart (SBO).
-                const uint64_t ad0 = smem_desc(a_addr, a_box, 512, 1);
+        const uint32_t idesc = instr_desc(BM, (int)ncols, 1, 1);   // both operands MN-major, N = k taps x 32 channels
+        // A: 4 MN blocks (32 couts each) one dY box apart; B: k MN blocks (ky = 0..k-1) one tile row apart.
+        // K = 8 pixels = one tile row = two 4-pixel swizzle atoms 512 B apart (SBO).
+        const uint64_t ad_base = smem_desc(smem_u32(smem), a_box, 512, 1);
+        const uint64_t bd_base = smem_desc(smem_u32(smem) + a_bytes, row_bytes, 512, 1);
+        int s = 0;
+        uint32_t ph = 0, s_off = 0;
+        for (int it = 0; it < iters; ++it) {
+            mbar_wait(smem_u32(&bars[s]), ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint64_t ad0 = desc_advance(ad_base, s_off);
                 for (int j = 0; j < p.nb; ++j) {
-                    const uint64_t bd0 = smem_desc(b_addr + (uint32_t)j * b_box, row_bytes, 512, 1);
+                    const uint64_t bd0 = desc_advance(bd_base, s_off + (uint32_t)j * b_box);
                     const uint32_t d_addr = tmem_base + (uint32_t)j * ncols;
-                    for (int r = 0; r < p.rows; ++r)
-                        umma_tf32(d_addr, desc_advance(ad0, (uint32_t)r * row_bytes),
-                                  desc_advance(bd0, (uint32_t)r * row_bytes), idesc, (it > 0 || r > 0) ? 1u : 0u);
+#define MI_WGKX_ROWS(R0, R1)                                                                                        \
+    _Pragma("unroll") for (int r = R0; r < R1; ++r)                                                                 \
+        umma_tf32(d_addr, desc_advance(ad0, (uint32_t)r * 1024u), desc_advance(bd0, (uint32_t)r * 1024u), idesc,   \
+                  (it > 0 || r > 0) ? 1u : 0u);
+                    MI_WGKX_ROWS(0, 8)
+                    if (p.rows == 16) { MI_WGKX_ROWS(8, 16) }
+#undef MI_WGKX_ROWS
                 }
                 umma_commit(smem_u32(&bars[p.stages + s]));
+                if (it + 1 == iters) umma_commit(smem_u32(&bars[2 * p.stages]));
             }
-            umma_commit(smem_u32(&bars[2 * p.stages]));
+            __syncwarp();
+            if (++s == p.stages) { s = 0; s_off = 0; ph ^= 1u; } else { s_off += stage_bytes; }
         }
     } else {
         const int q = warp & 3;
@@ -1640,7 +1651,7 @@ int num_sms() { return mi_sm_budget(); }   // CTAs a persistent launch may occup
 
 // Filter-column-stacked 3x3 kernel (conv_tc_kxs.cuh).  MI_B200_KXS=0 keeps the halo kernels (A/B switch), =2 forces the
 // stacked kernel even where its 14-of-16-column tiles cover the image worse than the 8x16 halo tiles, =3 additionally
-// forces its generic (per-thread store) epilogue.
+// forces its generic (per-thread store) epilogue, =4 keeps the two-box staging tile everywhere (A/B of the third stage).
 int kxs_mode() {
     static int v = -1;
     if (v < 0) {
@@ -1678,8 +1689,15 @@ int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bi
     // dynamic shared memory: [resident weights] [S stages] [epilogue staging 28 KB] [barriers] + 1 KB alignment slack;
     // 227 KB per CTA minus the static part (bias table)
     const size_t budget = 227 * 1024 - 3072 - 128;   // static: bias table, tmem slot, alignment
-    const size_t fixed = KX_STAGING + 256 + 1024;
+    const bool vec = aligned_view(y, ldy) && (!mask_y || aligned_view(mask_y, ldmask));
+    int epi = KXS_EPI_GENERIC;
+    if (vec && kxs_mode() != 3) {
+        if (!mask_y && !accumulate) epi = KXS_EPI_PLAIN;
+        else if (!(mask_y && accumulate)) epi = KXS_EPI_OPERAND;
+    }
+    size_t fixed = KX_STAGING + 256 + 1024;
     size_t smem;
+    kp.one_box = 0;
     if (stream_w) {
         kp.stages = 2;
         smem = 2 * (KX_BOX_BYTES + b_chunk) + fixed;
@@ -1687,16 +1705,19 @@ int launch_kxs(const float* x, int ldx, const float* w, int ldw, const float* bi
     } else {
         const size_t b_total = kp.chunks * b_chunk;
         int stages = (int)((budget - fixed - b_total) / KX_BOX_BYTES);
+        // two stages leave the box loads exposed (per-role counters: the MMA lane waits ~330 cycles per stage for data
+        // on the 64-channel layers, whose 147 KB of weights leave room for no more); a plain epilogue can go through
+        // one 14 KB staging box in two rounds and give the room to a third stage
+        if (stages == 2 && epi == KXS_EPI_PLAIN && kxs_mode() == 5 &&
+            (budget - (fixed - KX_OUT_BOX) - b_total) / KX_BOX_BYTES >= 3) {
+            kp.one_box = 1;
+            fixed -= KX_OUT_BOX;
+            stages = 3;
+        }
         if (stages > 4) stages = 4;
         if (stages < 2) return MI_ERR_UNSUPPORTED;
         kp.stages = stages;
         smem = b_total + (size_t)stages * KX_BOX_BYTES + fixed;
-    }
-    const bool vec = aligned_view(y, ldy) && (!mask_y || aligned_view(mask_y, ldmask));
-    int epi = KXS_EPI_GENERIC;
-    if (vec && kxs_mode() != 3) {
-        if (!mask_y && !accumulate) epi = KXS_EPI_PLAIN;
-        else if (!(mask_y && accumulate)) epi = KXS_EPI_OPERAND;
     }
     CUtensorMap map_x, map_w, map_y, map_op;
     if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, KX_W, KX_BOX_H)) return MI_ERR_UNSUPPORTED;

@@ -53,7 +53,8 @@ constexpr int KXS_THREADS = 352;
 struct KxsParams {
     int rnd;
     int n, h, w, cin, cout, chunks, bn, stages, n_tiles, tiles_x, tiles_y, total_tiles, items, act, accumulate, mask_act,
-        ldy, ldmask, c_tma;             // c_tma: channels the TMA store / operand load covers (see the epilogue)
+        ldy, ldmask, c_tma,             // c_tma: channels the TMA store / operand load covers (see the epilogue)
+        one_box;                        // plain epilogue through ONE 14 KB staging box, freeing room for a third stage
     unsigned long long* dbg;            // optional per-role cycle counters of CTA 0 (MI_B200_DEBUG_TIMING=1)
     float slope, mask_slope;
     const float* bias;
@@ -112,7 +113,7 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
     uint8_t* smem_a = STREAM ? smem : smem + (size_t)p.chunks * b_chunk;
     const int S = p.stages;
     uint8_t* staging = smem_a + (size_t)S * stage_bytes;            // epilogue tile(s), 1024-aligned
-    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + KX_STAGING);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(staging + (p.one_box ? KX_OUT_BOX : KX_STAGING));
     // bars: [0,S) full, [S,2S) empty, 2S..2S+1 tmem full[2], 2S+2..2S+3 tmem empty[2], 2S+4.. weights of chunk c (resident),
     //       2S+6 = epilogue operand (mask / previous y) landed in the staging tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 3);
@@ -364,6 +365,9 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                     }
                 }
             } else {
+              // one round per item -- or, with a single staging box (p.one_box, plain mode), one round per 32-channel box
+              const int rounds = (EPI == KXS_EPI_PLAIN && p.one_box) ? npiece : 1;
+              for (int rd = 0; rd < rounds; ++rd) {
                 const long long cb = clock64();
                 if (EPI == KXS_EPI_OPERAND) mbar_wait(op_bar, (uint32_t)t & 1u);   // operand landed => staging is ours
                 else kxs_bar_sync(1);                                               // previous store has left the tile
@@ -371,10 +375,11 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 if (col_ok) {
 #pragma unroll
                     for (int pc = 0; pc < 2; ++pc) {
-                        if (pc < npiece) {
+                        if (pc < npiece && (rounds == 1 || pc == rd)) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const uint32_t a = my_row + (uint32_t)pc * KX_OUT_BOX + ((((uint32_t)(4 * half + g)) ^ swz) << 4);
+                                const uint32_t a = my_row + (rounds == 1 ? (uint32_t)pc * KX_OUT_BOX : 0u) +
+                                                   ((((uint32_t)(4 * half + g)) ^ swz) << 4);
                                 float4 v = make_float4(acc[pc][4 * g], acc[pc][4 * g + 1], acc[pc][4 * g + 2], acc[pc][4 * g + 3]);
                                 if (EPI == KXS_EPI_OPERAND) {
                                     float4 o;
@@ -406,7 +411,7 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                         }
                     }
                 }
-                if (c_tail && c_tma >= co0 && c_tma < co0 + p.bn && half == (((c_tma - co0) >> 4) & 1)) {
+                if (rd == 0 && c_tail && c_tma >= co0 && c_tma < co0 + p.bn && half == (((c_tma - co0) >> 4) & 1)) {
                     const int oy = y0 + row_i, ox = x0 + col_i - 1;
                     if (col_ok && oy < p.h && ox < p.w) {
                         const long long pix = ((long long)img * p.h + oy) * p.w + ox;
@@ -431,6 +436,7 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 }
                 fence_async_smem();
                 kxs_bar_arrive(2);                  // staged: the store warp takes it from here
+              }
             }
             e_st += clock64() - c1;
         }
@@ -474,21 +480,30 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
         for (int t = 0; t < my_items; ++t) {
             int co0, x0, y0, img;
             item_coords(t, co0, x0, y0, img);
-            kxs_bar_sync(2);                         // all eight epilogue warps have staged item t
-            if (elect_one()) {
-                for (int b = 0; b < 2; ++b)
-                    if (32 * b < p.bn && co0 + 32 * b < c_tma)
-                        tma_store_4d(&map_y, stg + (uint32_t)b * KX_OUT_BOX, co0 + 32 * b, x0, y0, img);
-                tma_store_commit();
-                const long long cw = clock64();
-                tma_store_wait_read();
-                e_wr += clock64() - cw;
-                if (EPI == KXS_EPI_OPERAND && t + 1 < my_items) load_operand(t + 1);
-                if (t + 1 == my_items) tma_store_wait_all();
-                if (p.dbg && blockIdx.x == 0 && t + 1 == my_items) p.dbg[13] = (unsigned long long)e_wr;
+            const int npiece = (p.bn > 32 && co0 + 32 < p.cout) ? 2 : 1;       // as the epilogue warps count them
+            const int rounds = (EPI == KXS_EPI_PLAIN && p.one_box) ? npiece : 1;
+            for (int rd = 0; rd < rounds; ++rd) {
+                const bool last = (t + 1 == my_items) && (rd + 1 == rounds);
+                kxs_bar_sync(2);                     // all eight epilogue warps have staged item t (round rd)
+                if (elect_one()) {
+                    if (rounds == 1) {
+                        for (int b = 0; b < 2; ++b)
+                            if (32 * b < p.bn && co0 + 32 * b < c_tma)
+                                tma_store_4d(&map_y, stg + (uint32_t)b * KX_OUT_BOX, co0 + 32 * b, x0, y0, img);
+                    } else if (co0 + 32 * rd < c_tma) {
+                        tma_store_4d(&map_y, stg, co0 + 32 * rd, x0, y0, img);
+                    }
+                    tma_store_commit();
+                    const long long cw = clock64();
+                    tma_store_wait_read();
+                    e_wr += clock64() - cw;
+                    if (EPI == KXS_EPI_OPERAND && t + 1 < my_items) load_operand(t + 1);
+                    if (last) tma_store_wait_all();
+                    if (p.dbg && blockIdx.x == 0 && last) p.dbg[13] = (unsigned long long)e_wr;
+                }
+                __syncwarp();
+                if (EPI == KXS_EPI_PLAIN && !last) kxs_bar_arrive(1);
             }
-            __syncwarp();
-            if (EPI == KXS_EPI_PLAIN && t + 1 < my_items) kxs_bar_arrive(1);
         }
     }
     tc_fence_before();
