@@ -1,4 +1,5 @@
-// Adaptive separable convolution, second generation: four vertically adjacent pixels per thread.
+// Adaptive separable convolution, second generation: four vertically adjacent pixels per thread, their FMAs issued in
+// pairs (FFMA2).
 //
 // The first kernels (sepconv.cu) keep one pixel's whole 51-tap filter in registers and reuse every staged window
 // value for two pixels: one shared-memory load per two FMAs, i.e. a ceiling of half the FP32 pipe (one 32-lane LDS
@@ -31,6 +32,21 @@
 
 namespace quad {
 
+// Two FMAs of neighbouring pixels in ONE instruction: c0 += a0 * b, c1 += a1 * b (Blackwell's packed `fma.rn.f32x2`,
+// SASS FFMA2; each half is an ordinary IEEE fma, so results are bit-identical to two FFMAs).  The staged window value
+// `b` is shared by the pixels of a quad; ptxas encodes the duplicated pair as a scalar-broadcast operand
+// (`FFMA2 R4, R10.F32x2.HI_LO, R114.F32, R4.F32x2.HI_LO`), and the pack / unpack moves below disappear into register
+// allocation.  ncu on the scalar form: issue slots 72 % busy with the FMA pipe 50 % active -- the kernels were short of
+// ISSUE slots (104 FFMA + ~28 LDS + address arithmetic per row pass), which this halves for the FMA part.
+__device__ __forceinline__ void ffma2(float& c0, float& c1, float a0, float a1, float b) {
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c0), "=f"(c1) : "l"(rd));
+}
+
 constexpr int QY = 4;                    // pixels per thread
 constexpr int BX = 32, BY = 16;          // pixel tile of a CTA
 constexpr int NT = BX * (BY / QY);       // 128 threads
@@ -57,7 +73,9 @@ __device__ __forceinline__ void stage(float* smem, const float* __restrict__ fra
     int sx[(WW + 31) / 32];
 #pragma unroll
     for (int j = 0; j < (WW + 31) / 32; ++j) sx[j] = min(max(x_base + lane + 32 * j, 0), fw - 1);   // replicate border
-#pragma unroll 2
+    // (eight window rows = 24 independent 128-byte loads per warp in flight: the CTAs of a launch start together, so
+    // the staging phases of the three CTAs of an SM coincide and nothing else hides their latency)
+#pragma unroll 8
     for (int rr = warp; rr < C * WH; rr += NT / 32) {
         const int cc = rr / WH, r = rr - cc * WH;
         const int sy = min(max(y_base + r, 0), fh - 1);
@@ -93,17 +111,23 @@ __device__ __forceinline__ void fwd_pass(const float* win, const QuadTaps& hp, c
     constexpr int WH = Geo<F>::WIN_H, P = Geo<F>::PITCH;
     float h[QY][HALF_A];
     load_taps<T0, NTAP>(h, hp);
-    float vn[QY];                                       // taps of the NEXT row, fetched a row ahead of their use
+    // vertical taps are fetched TWO rows ahead of their use: one row of work (~500 cycles) did not cover the latency
+    // of the planar-filter loads (ncu: long-scoreboard stalls on the first use of the prefetched tap)
+    float vn[QY], vnn[QY];
 #pragma unroll
-    for (int k = 0; k < QY; ++k) vn[k] = k == 0 ? vp.at(0, 0) : 0.f;
+    for (int k = 0; k < QY; ++k) {
+        vn[k] = k == 0 ? vp.at(0, 0) : 0.f;             // row 0 is tap -k of pixel k
+        vnn[k] = k <= 1 ? vp.at(k, 1 - k) : 0.f;        // row 1 is tap 1 - k
+    }
 #pragma unroll 1
     for (int r = 0; r < F + QY - 1; ++r) {             // window row relative to the first pixel of the quad
         float v[QY];
 #pragma unroll
         for (int k = 0; k < QY; ++k) {
             v[k] = vn[k];
-            const int fy = r + 1 - k;                   // row r + 1 is tap fy of pixel k
-            vn[k] = (fy >= 0 && fy < F) ? vp.at(k, fy) : 0.f;
+            vn[k] = vnn[k];
+            const int fy = r + 2 - k;                   // row r + 2 is tap fy of pixel k
+            vnn[k] = (fy >= 0 && fy < F) ? vp.at(k, fy) : 0.f;
         }
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) {
@@ -114,8 +138,8 @@ __device__ __forceinline__ void fwd_pass(const float* win, const QuadTaps& hp, c
 #pragma unroll
             for (int f = 0; f < NTAP; ++f) {
                 const float in = row[f];
-#pragma unroll
-                for (int k = 0; k < QY; ++k) t[k] = fmaf(in, h[k][f], t[k]);
+                ffma2(t[0], t[1], h[0][f], h[1][f], in);
+                ffma2(t[2], t[3], h[2][f], h[3][f], in);
             }
 #pragma unroll
             for (int k = 0; k < QY; ++k) acc[k][cc] = fmaf(v[k], t[k], acc[k][cc]);
@@ -180,17 +204,21 @@ __device__ __forceinline__ void gh_pass(const float* win, const QuadTaps& vp, co
     for (int k = 0; k < QY; ++k)
 #pragma unroll
         for (int f = 0; f < NTAP; ++f) acc[k][f] = 0.f;
-    float vn[QY];
+    float vn[QY], vnn[QY];                              // two rows ahead, as in the forward pass
 #pragma unroll
-    for (int k = 0; k < QY; ++k) vn[k] = k == 0 ? vp.at(0, 0) : 0.f;
+    for (int k = 0; k < QY; ++k) {
+        vn[k] = k == 0 ? vp.at(0, 0) : 0.f;
+        vnn[k] = k <= 1 ? vp.at(k, 1 - k) : 0.f;
+    }
 #pragma unroll 1
     for (int r = 0; r < F + QY - 1; ++r) {
         float v[QY];
 #pragma unroll
         for (int k = 0; k < QY; ++k) {
             v[k] = vn[k];
-            const int fy = r + 1 - k;
-            vn[k] = (fy >= 0 && fy < F) ? vp.at(k, fy) : 0.f;
+            vn[k] = vnn[k];
+            const int fy = r + 2 - k;
+            vnn[k] = (fy >= 0 && fy < F) ? vp.at(k, fy) : 0.f;
         }
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) {
@@ -201,8 +229,8 @@ __device__ __forceinline__ void gh_pass(const float* win, const QuadTaps& vp, co
 #pragma unroll
             for (int f = 0; f < NTAP; ++f) {
                 const float in = row[f];
-#pragma unroll
-                for (int k = 0; k < QY; ++k) acc[k][f] = fmaf(coef[k], in, acc[k][f]);
+                ffma2(acc[0][f], acc[1][f], coef[0], coef[1], in);
+                ffma2(acc[2][f], acc[3][f], coef[2], coef[3], in);
             }
         }
     }
@@ -223,16 +251,20 @@ __device__ __forceinline__ void gv_pass(const float* win, const QuadTaps& hp, co
     for (int k = 0; k < QY; ++k)
 #pragma unroll
         for (int j = 0; j < NTAP; ++j) acc[k][j] = 0.f;
-    float hn[QY];
+    float hn[QY], hnn[QY];                              // two columns ahead
 #pragma unroll
-    for (int k = 0; k < QY; ++k) hn[k] = hp.at(k, 0);
+    for (int k = 0; k < QY; ++k) {
+        hn[k] = hp.at(k, 0);
+        hnn[k] = hp.at(k, 1);
+    }
 #pragma unroll 1
     for (int fx = 0; fx < F; ++fx) {
         float hk[QY];
 #pragma unroll
         for (int k = 0; k < QY; ++k) {
             hk[k] = hn[k];
-            hn[k] = hp.at(k, min(fx + 1, F - 1));
+            hn[k] = hnn[k];
+            hnn[k] = hp.at(k, min(fx + 2, F - 1));
         }
 #pragma unroll
         for (int cc = 0; cc < C; ++cc) {
@@ -244,10 +276,14 @@ __device__ __forceinline__ void gv_pass(const float* win, const QuadTaps& hp, co
 #pragma unroll
             for (int jj = 0; jj < NTAP + QY - 1; ++jj) {
                 const float in = col[jj * P];
+                // row T0 + jj is tap fy = T0 + jj - k of pixel k: pixels (0, 1) and (2, 3) pair up, one tap apart
 #pragma unroll
-                for (int k = 0; k < QY; ++k) {
-                    const int j = jj - k;          // row T0 + jj is tap fy = T0 + jj - k of pixel k
-                    if (j >= 0 && j < NTAP) acc[k][j] = fmaf(coef[k], in, acc[k][j]);
+                for (int kp = 0; kp < QY; kp += 2) {
+                    const int j0 = jj - kp, j1 = jj - kp - 1;
+                    const bool v0 = j0 >= 0 && j0 < NTAP, v1 = j1 >= 0 && j1 < NTAP;
+                    if (v0 && v1) ffma2(acc[kp][v0 ? j0 : 0], acc[kp + 1][v1 ? j1 : 0], coef[kp], coef[kp + 1], in);
+                    else if (v0) acc[kp][v0 ? j0 : 0] = fmaf(coef[kp], in, acc[kp][v0 ? j0 : 0]);
+                    else if (v1) acc[kp + 1][v1 ? j1 : 0] = fmaf(coef[kp + 1], in, acc[kp + 1][v1 ? j1 : 0]);
                 }
             }
         }
