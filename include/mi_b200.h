@@ -137,6 +137,15 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy,
                     float* wt_out, int ldwt, float* wr_out,
                     void* workspace, size_t workspace_bytes, int engine, mi_stream_t stream);
 
+/* Deferred finishing (north_star: "no extra elementwise launch between inner steps").  Between _begin and _flush the
+ * finishing stage of every mi_conv2d_wgrad call -- split-K / bias reduction and the store / accumulate / fused
+ * inner-loop update of update_params (inner_loop_optimizers.py:136-147, 324-332), including the rotated (`wt_out`) and
+ * TF32-rounded (`wr_out`) copies -- is recorded instead of launched; _flush issues one launch per 20 layers on
+ * `stream`.  While deferring, every call must be given its OWN workspace, kept alive until the flush, and the outputs
+ * of the finishing stage (gradients, updated weights) are not valid before the flush. */
+int mi_wgrad_defer_begin(void);
+int mi_wgrad_defer_flush(mi_stream_t stream);
+
 /* ------------------------------------------------------------------ pointwise / resampling
  * avg/max pool 2x2 s2  : sepconv/model.py:197-209, voxel_flow.py:243, superslomo/model.py:69, rrin/unet.py:139
  * bilinear x2 upsample : sepconv/model.py:191 (align_corners=True); voxel_flow.py:400, superslomo/model.py:139,

@@ -22,6 +22,8 @@ SIGNATURES = {
     "mi_launch_count": (C.c_ulonglong, []),
     "mi_tc_available": (_i, []),
     "mi_set_sm_budget": (_i, [_i]),
+    "mi_wgrad_defer_begin": (_i, []),
+    "mi_wgrad_defer_flush": (_i, [_st]),
     "mi_set_pad_lanes_scratch": (_i, [_i]),
     "mi_prof_enable": (_i, [_i]),
     "mi_prof_summary": (_i, [_i, C.c_void_p]),

@@ -6,6 +6,8 @@
 // Replaces F.conv2d + its autograd (reference model_utils.py:360).
 #include <cstdlib>
 
+#include <algorithm>
+#include <vector>
 #include "mi_common.cuh"
 
 std::atomic<unsigned long long> g_mi_launches{0};
@@ -476,19 +478,34 @@ static bool small_cout_wgrad_ok(int cin, int cout, int k) { return cout <= SC_MA
 // 256 partials was a 46 us serial tail on the small layers).  In the SGD modes the updated weight can also be
 // written in the rotated layout dgrad reads (wt_out[ci][kk-1-tap][co]), which removes the per-step
 // weight_to_dgrad launch of every adapted layer.
-__global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float* __restrict__ ws_b, int splits,
-                                    int bias_splits, int cin, int cout, int kk, int ldw, int mode, float scale,
-                                    float* __restrict__ grad_w, float* __restrict__ grad_b,
-                                    const float* __restrict__ w_in, const float* __restrict__ b_in,
-                                    float* __restrict__ w_out, float* __restrict__ b_out,
-                                    const float* __restrict__ lr_w, const float* __restrict__ lr_b,
-                                    float* __restrict__ gsum_w, float* __restrict__ gsum_b,
-                                    float* __restrict__ wt_out, int ldwt, float* __restrict__ wr_out, int rnd) {
+struct FinishDesc {
+    const float* ws_w; const float* ws_b;
+    int splits, bias_splits, cin, cout, kk, ldw, mode, ldwt, rnd;
+    float scale;
+    float* grad_w; float* grad_b;
+    const float* w_in; const float* b_in;
+    float* w_out; float* b_out;
+    const float* lr_w; const float* lr_b;
+    float* gsum_w; float* gsum_b;
+    float* wt_out; float* wr_out;
+};
+
+__device__ __forceinline__ void wgrad_finish_body(const FinishDesc& d, long long first, long long stride) {
+    const float* __restrict__ ws_w = d.ws_w;
+    const float* __restrict__ ws_b = d.ws_b;
+    const int splits = d.splits, bias_splits = d.bias_splits, cin = d.cin, cout = d.cout, kk = d.kk, ldw = d.ldw,
+              mode = d.mode, ldwt = d.ldwt, rnd = d.rnd;
+    const float scale = d.scale;
+    float* grad_w = d.grad_w; float* grad_b = d.grad_b;
+    const float* w_in = d.w_in; const float* b_in = d.b_in;
+    float* w_out = d.w_out; float* b_out = d.b_out;
+    const float* lr_w = d.lr_w; const float* lr_b = d.lr_b;
+    float* gsum_w = d.gsum_w; float* gsum_b = d.gsum_b;
+    float* wt_out = d.wt_out; float* wr_out = d.wr_out;
     const long long wsz = (long long)cout * kk * ldw;
     const long long wsz32 = (wsz + 31) & ~31LL;
     const long long total = wsz32 + (long long)cout * 32;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
+    for (long long i = first; i < total; i += stride) {
         if (i < wsz32) {
             if (i >= wsz) continue;
             const long long e = i;
@@ -553,6 +570,19 @@ __global__ void wgrad_finish_kernel(const float* __restrict__ ws_w, const float*
             if (gsum_b) gsum_b[c] += g;
         }
     }
+}
+
+__global__ void wgrad_finish_kernel(const FinishDesc d) {
+    wgrad_finish_body(d, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// The finishing stages of SEVERAL layers in one launch (deferred mode, mi_wgrad_defer_begin / _flush): blockIdx.y picks
+// the layer, blockIdx.x strides over its elements; the descriptors travel by value in the kernel parameters.
+constexpr int FINISH_BATCH = 20;
+struct FinishBatch { FinishDesc d[FINISH_BATCH]; };
+__global__ void wgrad_finish_batch_kernel(const __grid_constant__ FinishBatch b) {
+    wgrad_finish_body(b.d[blockIdx.y], (long long)blockIdx.x * blockDim.x + threadIdx.x,
+                      (long long)gridDim.x * blockDim.x);
 }
 
 }  // namespace
@@ -631,20 +661,82 @@ int mi_bias_splits(long long m_total) {
     return (int)s;
 }
 
+// Deferred mode: between mi_wgrad_defer_begin() and mi_wgrad_defer_flush() the finishing stage of every weight
+// gradient (split-K reduction, bias reduction, store / accumulate / fused update, rotated and rounded copies) is
+// recorded instead of launched, and the flush issues ONE launch per FINISH_BATCH layers -- the backward pass of a
+// support step then carries a couple of finishing launches instead of one per layer.  The caller keeps every layer's
+// workspace alive and distinct until the flush.
+namespace {
+bool g_defer = false;
+std::vector<FinishDesc> g_deferred;
+struct RotateJob { const float* w; int ldw; float* wt; int ldwt, cin, cout, k, rnd; };
+std::vector<RotateJob> g_rotate;
+
+int finish_blocks(const FinishDesc& d) {
+    const long long total = (((long long)d.cout * d.kk * d.ldw + 31) & ~31LL) + (long long)d.cout * 32;
+    int blocks = mi_cdiv(total, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    return blocks;
+}
+}  // namespace
+
 int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int bias_splits, int cin, int cout, int k,
                            int ldw, int mode, float scale, float* grad_w, float* grad_b, const float* w_in, const float* b_in,
                            float* w_out, float* b_out, const float* lr_w, const float* lr_b, float* gsum_w,
                            float* gsum_b, float* wt_out, int ldwt, float* wr_out, cudaStream_t stream) {
+    FinishDesc d;
+    d.ws_w = ws_w; d.ws_b = ws_b; d.splits = splits; d.bias_splits = bias_splits; d.cin = cin; d.cout = cout;
+    d.kk = k * k; d.ldw = ldw; d.mode = mode; d.ldwt = ldwt; d.rnd = mi_tf32_rn_enabled() ? 1 : 0; d.scale = scale;
+    d.grad_w = grad_w; d.grad_b = grad_b; d.w_in = w_in; d.b_in = b_in; d.w_out = w_out; d.b_out = b_out;
+    d.lr_w = lr_w; d.lr_b = lr_b; d.gsum_w = gsum_w; d.gsum_b = gsum_b; d.wt_out = wt_out; d.wr_out = wr_out;
+    if (g_defer) {
+        g_deferred.push_back(d);
+        return MI_OK;
+    }
     const long long total = (((long long)cout * k * k * ldw + 31) & ~31LL) + (long long)cout * 32;
-    int blocks = mi_cdiv(total, 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
     mi_prof_begin(MI_TAG_WGRAD_FINISH, 0.0, 4.0 * (double)total * (splits + 2), stream);
-    wgrad_finish_kernel<<<blocks, 256, 0, stream>>>(ws_w, ws_b, splits, bias_splits, cin, cout, k * k, ldw, mode, scale, grad_w,
-                                                    grad_b, w_in, b_in, w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, wt_out, ldwt,
-                                                    wr_out, mi_tf32_rn_enabled() ? 1 : 0);
+    wgrad_finish_kernel<<<finish_blocks(d), 256, 0, stream>>>(d);
     mi_prof_end(stream);
     MI_LAUNCHED();
     MI_RETURN_LAST();
+}
+
+extern "C" int mi_wgrad_defer_begin(void) {
+    g_defer = true;
+    g_deferred.clear();
+    g_rotate.clear();
+    return MI_OK;
+}
+
+extern "C" int mi_wgrad_defer_flush(mi_stream_t stream) {
+    cudaStream_t st = mi_cs(stream);
+    g_defer = false;
+    for (size_t first = 0; first < g_deferred.size(); first += FINISH_BATCH) {
+        const int count = (int)std::min<size_t>(FINISH_BATCH, g_deferred.size() - first);
+        FinishBatch b;
+        int blocks = 1;
+        double bytes = 0.0;
+        for (int i = 0; i < FINISH_BATCH; ++i) {
+            b.d[i] = g_deferred[first + (i < count ? i : 0)];
+            if (i < count) {
+                blocks = std::max(blocks, finish_blocks(b.d[i]));
+                bytes += 4.0 * (double)b.d[i].cout * b.d[i].kk * b.d[i].ldw * (b.d[i].splits + 2);
+            }
+        }
+        mi_prof_begin(MI_TAG_WGRAD_FINISH, 0.0, bytes, st);
+        wgrad_finish_batch_kernel<<<dim3(blocks, count), 256, 0, st>>>(b);
+        mi_prof_end(st);
+        MI_LAUNCHED();
+        cudaError_t e = cudaPeekAtLastError();
+        if (e != cudaSuccess) { g_deferred.clear(); g_rotate.clear(); return (int)e; }
+    }
+    g_deferred.clear();
+    for (const RotateJob& r : g_rotate) {
+        const int rc = mi_weight_to_dgrad_launch(r.w, r.ldw, r.wt, r.ldwt, r.cin, r.cout, r.k, r.rnd, st);
+        if (rc != 0) { g_rotate.clear(); return rc; }
+    }
+    g_rotate.clear();
+    return MI_OK;
 }
 
 static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
@@ -825,6 +917,10 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
     rc = mi_wgrad_finish_launch(ws_w, ws_b, splits, bias_splits, cin, cout, k, ldw, mode, scale, grad_w, grad_b, w_in, b_in,
                                 w_out, b_out, lr_w, lr_b, gsum_w, gsum_b, rotate_after ? nullptr : wt_out, ldwt, wr_out, st);
     if (rc != 0 || !rotate_after) return rc;
+    if (g_defer) {      // the rotation reads the UPDATED weight: it follows the deferred finishing launch
+        g_rotate.push_back(RotateJob{w_out, ldw, wt_out, ldwt, cin, cout, k, wr_out != nullptr});
+        return MI_OK;
+    }
     return mi_weight_to_dgrad_launch(w_out, ldw, wt_out, ldwt, cin, cout, k, wr_out != nullptr, st);
 }
 

@@ -378,6 +378,16 @@ class FastPath:
         prog.loss.add_(prog.terms.sum())
         return grad
 
+    def _backward(self, tape):
+        """Backward pass of a captured body: the per-layer finishing launches of the weight gradients (split-K reduction
+        + fused inner-loop update) are collected and issued together after the last layer -- the dgrad of a layer runs
+        before its weight gradient and nothing in the pass reads an updated weight, so the order is free."""
+        self.ops.begin_deferred_wgrad()
+        try:
+            tape.backward()
+        finally:
+            self.ops.flush_deferred_wgrad()
+
     def _support_body(self, lane, src, step_slot):
         def body(prog):
             self.ops.set_workspace_slot(lane.index)
@@ -385,7 +395,7 @@ class FastPath:
             tape = Tape(self.ops, self._provider(lane, src), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             self._seed_loss(prog, tape, out, prog.f0.shape[0])
-            tape.backward()
+            self._backward(tape)
             if self.rule != RULE_SGD:
                 self._moment_update(lane, src, step_slot)
         return body
@@ -424,7 +434,7 @@ class FastPath:
             tape = Tape(self.ops, self._provider(lane, 'meta'), sink, vectors=self.net.meta_bn)
             out = self.net.build_graph(tape, prog.f0, prog.f1)
             self._seed_loss(prog, tape, out, prog.f0.shape[0])
-            tape.backward()
+            self._backward(tape)
         return body
 
     def _attenuate(self, lane, frames, task, h, w, support_idxs):
@@ -472,7 +482,7 @@ class FastPath:
             prog.pred = out.data
             self._seed_loss(prog, tape, out, 1, backward)
             if backward:
-                tape.backward()
+                self._backward(tape)
         return body
 
     def _program(self, lane, key, body, n, h, w):

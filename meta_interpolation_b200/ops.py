@@ -236,12 +236,29 @@ class CudaOps:
         _lib.check(rc, "mi_conv2d_dgrad")
         return dx
 
+    def begin_deferred_wgrad(self):
+        """From here to ``flush_deferred_wgrad`` the finishing stage of every ``conv_wgrad`` (reduction of the split-K
+        partials, bias, store / accumulate / fused update) is recorded and then issued as one launch per 20 layers."""
+        _lib.check(self.lib.mi_wgrad_defer_begin(), "mi_wgrad_defer_begin")
+        self._deferred_ws = []
+
+    def flush_deferred_wgrad(self):
+        held, self._deferred_ws = self._deferred_ws, None
+        _lib.check(self.lib.mi_wgrad_defer_flush(self._stream()), "mi_wgrad_defer_flush")
+        del held           # the partials of each layer had to stay alive (and distinct) until this point
+
     def conv_wgrad(self, x, dy, k, ldw, spec, engine=None):
         n, h, wd, cin = x.shape
         cout = dy.shape[3]
         eng = self.engine if engine is None else engine
         need = self.lib.mi_conv2d_wgrad_workspace(n, h, wd, cin, cout, k, eng)
-        ws = self.workspace(need)
+        if getattr(self, "_deferred_ws", None) is not None:
+            ws = torch.empty(int(need), device=self.device, dtype=torch.uint8)
+            if _POISON:
+                ws.fill_(255)
+            self._deferred_ws.append(ws)
+        else:
+            ws = self.workspace(need)
         p = self._p
         _lib.check(self.lib.mi_conv2d_wgrad(x.data_ptr(), _ld(x), dy.data_ptr(), _ld(dy), n, h, wd, cin, cout, k, ldw,
                                             spec.mode, float(spec.scale), p(spec.grad_w), p(spec.grad_b), p(spec.w_in),

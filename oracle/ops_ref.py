@@ -116,6 +116,12 @@ class RefOps:
         out.copy_(y)
         return out
 
+    def begin_deferred_wgrad(self):
+        pass              # (the CPU mirror finishes every weight gradient in place)
+
+    def flush_deferred_wgrad(self):
+        pass
+
     def set_sm_budget(self, ctas):
         return 0          # (a launch-geometry hint of the CUDA table; nothing to do on the CPU)
 
