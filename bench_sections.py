@@ -100,11 +100,11 @@ KERNEL_NAMES = {"fprop_tc_kxs": "conv_fprop_tc_kxs_kernel", "fprop_tc_halo": "co
 # filled from the committed ncu captures (profiles/); None = not captured this round.  The capture is of ONE launch
 # (named in NCU_TRAFFIC_LAUNCH, with its algorithmic bytes), while `achieved` averages all launches of the kernel.
 NCU_TRAFFIC_LAUNCH = {"fprop_tc_kxs": "51->51 3x3 on the 258x450 region of interest, N=2: 10.9 GFLOP, 94.7 MB "
-                                      "algorithmic (profiles/r02_ncu_kxs_51x51_258x450.txt)",
+                                      "algorithmic (profiles/r02b_ncu_kxs_51x51_258x450.txt)",
                       "fprop_tc_halo": "51->51 3x3 on the 258x450 region of interest, N=2: 10.9 GFLOP, 94.7 MB "
                                        "algorithmic (profiles/r01c_ncu_conv_fprop_halo_51x51_258x450.txt)"}
 # dram read + write of that launch (the output of the layer mostly stays in L2, hence less than the algorithmic bytes)
-NCU_TRAFFIC_BYTES = {"fprop_tc_kxs": 48453376 + 6992128, "fprop_tc_halo": 48479488 + 6179072}
+NCU_TRAFFIC_BYTES = {"fprop_tc_kxs": 48465920 + 4976896, "fprop_tc_halo": 48479488 + 6179072}
 
 
 # --------------------------------------------------------------------------------------------- CPU legs

@@ -485,12 +485,24 @@ class FastPath:
                 self._backward(tape)
         return body
 
+    MAX_PROGRAMS_PER_LANE = 32   # ~5 programs serve one (frame size, SM share); see _program
+
     def _program(self, lane, key, body, n, h, w):
+        """The captured program for `key` on this lane, least-recently-used bounded: every entry owns static input
+        buffers and a CUDA graph with a private memory pool, and the key contains what is baked into the graph (frame
+        size, the accumulation scale -- which changes with the multi-step-loss epoch and with a short last batch --
+        and the SM share), so validation on many frame sizes or a long MSL run would otherwise grow without bound."""
         key = key + (self.sm_budget,)        # grid sizes are baked into the captured graph
-        p = lane.programs.get(key)
+        progs = lane.programs
+        p = progs.pop(key, None)
         if p is None:
+            if len(progs) >= self.MAX_PROGRAMS_PER_LANE:
+                if self.ops.name == 'cuda':
+                    torch.cuda.synchronize() # the evicted graph may still be executing on the lane's stream
+                for old in list(progs)[:len(progs) - self.MAX_PROGRAMS_PER_LANE + 1]:
+                    del progs[old]           # (dicts keep insertion order: the front is the least recently used)
             p = _Program(lane, body, n, h, w)
-            lane.programs[key] = p
+        progs[key] = p                       # (re)inserted at the back: most recently used
         return p
 
     # ------------------------------------------------------------------ one task

@@ -530,3 +530,22 @@ def test_tf32_operand_convention_host_logic(name, fast):
                     assert torch.equal(ops.round_tf32(w.clone().contiguous()), wr.contiguous()), n
     finally:
         backbone.set_default_ops(saved)
+
+
+def test_program_cache_is_lru_bounded(ref_ops):
+    """ADVICE (round 1): captured programs were cached forever per lane -- one set per frame size, accumulation scale
+    and SM share.  The cache now evicts the least recently used entry."""
+    fx = load_golden("sepconv_lslr_sgd_k2")
+    system = system_from_fixture(fx, ref_ops, fast_path=True)
+    fp = system.fast_path()
+    lane = fp.lanes[0]
+    fp.MAX_PROGRAMS_PER_LANE = 2
+    body = lambda prog: None
+    a = fp._program(lane, ('query', 'a'), body, 1, 8, 8)
+    b = fp._program(lane, ('query', 'b'), body, 1, 8, 8)
+    assert fp._program(lane, ('query', 'a'), body, 1, 8, 8) is a          # a hit refreshes the entry ...
+    c = fp._program(lane, ('query', 'c'), body, 1, 8, 8)
+    keys = [k[:2] for k in lane.programs]
+    assert keys == [('query', 'a'), ('query', 'c')] and len(lane.programs) == 2   # ... so b, not a, was evicted
+    assert fp._program(lane, ('query', 'b'), body, 1, 8, 8) is not b
+    assert c is lane.programs[('query', 'c', fp.sm_budget)]
