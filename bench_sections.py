@@ -42,7 +42,18 @@ def roofline_section(system):
         summ = ops.prof_summary()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ops.prof_enable(False)
+        # the same instrumented iteration at the SM share of the timed run (8 tasks in flight: a persistent launch
+        # takes a quarter of the SMs and four of them run side by side)
+        fast.force_sm_shares = 4
+        system.run_train_iter(frames, epoch=0)
+        torch.cuda.synchronize()
+        ops.prof_enable(True)
+        system.run_train_iter(frames, epoch=0)
+        summ_share = ops.prof_summary()
+        ops.prof_enable(False)
+        share_ctas = ops.set_sm_budget(0) // 4
     finally:
+        fast.force_sm_shares = None
         system.use_cuda_graphs = saved
         fast.use_graphs = fast_saved
     # device time of the same one-task step replayed as CUDA graphs on ONE stream (no launch gaps, no lane overlap):
@@ -90,7 +101,20 @@ def roofline_section(system):
         "avg_launch_us": round(d["ms"] * 1e3 / max(d["launches"], 1), 2),
         "algorithmic_gflop_per_launch": round(d["flops"] / max(d["launches"], 1) / 1e9, 3),
         "instrumented_step_ms": round(wall_ms, 2), "per_kernel": breakdown,
+        # the timed run does not launch this kernel on the whole chip: with 8 tasks in flight a launch gets a quarter
+        # of the SMs (fastpath.py).  Same per-launch event timing at that share; `frac_of_share` = achieved / (peak x
+        # CTAs / SMs), the fraction of what the launch's own SMs can do (the headline `frac` above stays whole-chip)
+        "at_sm_share": _share_view(summ_share[dom], share_ctas, ops.set_sm_budget(0), peak),
     }
+
+
+def _share_view(d, ctas, sms, peak):
+    if not d["launches"] or d["ms"] <= 0:
+        return None
+    achieved = d["flops"] / (d["ms"] * 1e-3) / 1e12
+    return {"ctas_per_launch": ctas, "sms": sms, "achieved": round(achieved, 2), "unit": "TFLOP/s",
+            "avg_launch_us": round(d["ms"] * 1e3 / d["launches"], 2),
+            "frac_of_share": round(achieved / (peak * ctas / sms), 4)}
 
 
 KERNEL_NAMES = {"fprop_tc_kxs": "conv_fprop_tc_kxs_kernel", "fprop_tc_halo": "conv_fprop_tc_halo_kernel", "fprop_tc_halo_stream": "conv_fprop_tc_halo_stream_kernel",

@@ -628,6 +628,7 @@ class FastPath:
         # tasks/s for 1 / 2 / 4 shares, profiles/r02_sm_budget_sweep.txt)
         busy = min(len(task_ids), self.n_lanes)
         ways = 4 if busy >= 8 else (2 if busy >= 2 else 1)
+        ways = getattr(self, 'force_sm_shares', None) or ways     # (bench.py: instrument one task at the 8-task share)
         self.sm_budget = self.ops.set_sm_budget(0) // ways if ways > 1 else 0
         self.ops.set_sm_budget(self.sm_budget)
         try:
