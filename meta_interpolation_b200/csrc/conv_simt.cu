@@ -467,6 +467,46 @@ conv_wgrad_small_kernel(const float* __restrict__ x, int ldx, const float* __res
 }
 
 // eligibility of the small-Cout kernels (exact fp32; used by both engines)
+// Feature maps of a handful of pixels (CAIN's channel attention runs two 1x1 convs on the [N, C, 1, 1] output of a
+// global average pool: 1200 launches per 512x512 task, ~12 us each on the 64x64-tile kernel above, i.e. 14 % of the
+// task spent on matrix-vector products of a few hundred FMAs).  One WARP per output element: lanes stride over the
+// (tap, cin) products with coalesced weight reads and combine with shuffles in a fixed order; same epilogue.
+__global__ void __launch_bounds__(256)
+conv_fprop_tiny_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w, int ldw,
+                       const float* __restrict__ bias, float* __restrict__ y, int ldy, const float* __restrict__ mask_y,
+                       int ldmask, int mask_act, float mask_slope, int accumulate, int n, int h, int wd, int cin,
+                       int cout, int k, int act, float slope, int rnd) {
+    const int lane = threadIdx.x & 31;
+    const long long o = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;      // output element of this warp
+    const long long m_total = (long long)n * h * wd;
+    if (o >= m_total * cout) return;
+    const long long m = o / cout;
+    const int co = (int)(o - m * cout);
+    const int ox = (int)(m % wd), oy = (int)((m / wd) % h), img = (int)(m / ((long long)wd * h));
+    const int pad = k >> 1;
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+        const int iy = oy + ky - pad;
+        if (iy < 0 || iy >= h) continue;
+        for (int kx = 0; kx < k; ++kx) {
+            const int ix = ox + kx - pad;
+            if (ix < 0 || ix >= wd) continue;
+            const float* xp = x + (((long long)img * h + iy) * wd + ix) * ldx;
+            const float* wp = w + ((long long)co * k * k + ky * k + kx) * ldw;
+            for (int c = lane; c < cin; c += 32) acc = fmaf(xp[c], wp[c], acc);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane != 0) return;
+    float v = acc + (bias ? bias[co] : 0.f);
+    v = mi_act_apply(v, act, slope);
+    if (mask_y) v *= mi_act_grad(mask_y[m * ldmask + co], mask_act, mask_slope);
+    float* yp = y + m * ldy + co;
+    if (accumulate) v += *yp;
+    *yp = rnd ? mi_rn_tf32(v) : v;
+}
+
 static bool small_cout_fprop_ok(int cin, int cout, int k) {
     return cout <= 16 && (size_t)k * k * cin * (cout <= 8 ? 8 : 16) * sizeof(float) <= 96 * 1024;
 }
@@ -770,6 +810,17 @@ static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, c
             conv_fprop_small_kernel<16><<<(int)blocks, 256, sm, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask,
                                                                          mask_act, mask_slope, accumulate, n, h, wd, cin,
                                                                          cout, k, act, slope, vx, rnd);
+        mi_prof_end(stream);
+        MI_LAUNCHED();
+        MI_RETURN_LAST();
+    }
+    if (m_total <= 16) {          // a few pixels: one warp per output element
+        const long long warps = m_total * cout;
+        mi_prof_begin(MI_TAG_FPROP_SIMT, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k),
+                      stream);
+        conv_fprop_tiny_kernel<<<mi_cdiv(warps * 32, 256), 256, 0, stream>>>(x, ldx, w, ldw, bias, y, ldy, mask_y, ldmask,
+                                                                         mask_act, mask_slope, accumulate, n, h, wd,
+                                                                         cin, cout, k, act, slope, rnd);
         mi_prof_end(stream);
         MI_LAUNCHED();
         MI_RETURN_LAST();

@@ -345,6 +345,65 @@ interior_reduce_kernel(const float* __restrict__ x, int ldx, const float* __rest
     cluster.sync();                                   // remote shared memory stays alive until CTA 0 has read it
 }
 
+// The same reduction with 16-byte loads for 16-byte-aligned rows: 8 lanes x float4 cover the 32 channels of a group,
+// 128 pixel lanes, four independent loads per thread = 64 KB in flight per CTA (the scalar form above kept 16 KB in
+// flight on 96 of the 148 SMs and ran at 1.5 TB/s: 9 % of a CAIN task).
+__global__ void __cluster_dims__(1, 1, IR_CLUSTER) __launch_bounds__(1024)
+interior_reduce_vec_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mul, int ldm,
+                           float* __restrict__ out, int h, int w, int c, int ring, float scale) {
+    __shared__ float red[128][33];
+    __shared__ float part[32];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int img = blockIdx.x;
+    const int c4 = blockIdx.y * 32 + threadIdx.x * 4;          // first of this thread's four channels
+    const int ih = h - 2 * ring, iw = w - 2 * ring;
+    const long long npix = (long long)ih * iw;
+    const long long per = (npix + IR_CLUSTER - 1) / IR_CLUSTER;
+    const long long q_end = min(npix, (long long)(rank + 1) * per);
+    float4 s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < c) {                                               // (c is a multiple of 4 on this path)
+        const float* bx = x + (long long)img * h * w * ldx + c4;
+        const float* bm = mul ? mul + (long long)img * h * w * ldm + c4 : nullptr;
+        for (long long q = (long long)rank * per + threadIdx.y; q < q_end; q += 512) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long qq = q + 128 * u;
+                if (qq < q_end) {
+                    const int y0 = (int)(qq / iw), x0 = (int)(qq - (long long)y0 * iw);
+                    const long long o0 = (long long)(y0 + ring) * w + x0 + ring;
+                    float4 a = __ldg(reinterpret_cast<const float4*>(bx + o0 * ldx));
+                    if (bm) {
+                        const float4 m = __ldg(reinterpret_cast<const float4*>(bm + o0 * ldm));
+                        a.x *= m.x; a.y *= m.y; a.z *= m.z; a.w *= m.w;
+                    }
+                    s[u].x += a.x; s[u].y += a.y; s[u].z += a.z; s[u].w += a.w;
+                }
+            }
+        }
+    }
+    float* r = &red[threadIdx.y][threadIdx.x * 4];
+    r[0] = (s[0].x + s[1].x) + (s[2].x + s[3].x); r[1] = (s[0].y + s[1].y) + (s[2].y + s[3].y);
+    r[2] = (s[0].z + s[1].z) + (s[2].z + s[3].z); r[3] = (s[0].w + s[1].w) + (s[2].w + s[3].w);
+    __syncthreads();
+    const int tid = threadIdx.y * 8 + threadIdx.x;
+    if (tid < 32) {
+        float t = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 128; ++j) t += red[j][tid];
+        part[tid] = t;
+    }
+    cluster.sync();                                   // every CTA's partial row is in its shared memory
+    if (rank == 0 && tid < 32 && blockIdx.y * 32 + tid < c) {
+        float t = 0.f;
+        for (int rr = 0; rr < IR_CLUSTER; ++rr) t += cluster.map_shared_rank(part, rr)[tid];
+        out[(long long)img * c + blockIdx.y * 32 + tid] = t * scale;
+    }
+    cluster.sync();                                   // remote shared memory stays alive until CTA 0 has read it
+}
+
 // out = o * s[n,c] + res   (RCAB: x * y then out += res, model_utils.py:955,985)
 __global__ void scale_add_kernel(const float* __restrict__ o, int ldo, const float* __restrict__ s,
                                  const float* __restrict__ res, int ldr, float* __restrict__ out, int ldout,
@@ -507,8 +566,13 @@ int mi_depth_to_space_bwd(const float* gout, float* gin, int ldi, int n, int h, 
 int mi_interior_reduce(const float* x, int ldx, const float* mul, int ldm, float* out, int n, int h, int wd, int c,
                        int ring, float scale, mi_stream_t stream) {
     if (!x || !out || ring < 0 || h <= 2 * ring || wd <= 2 * ring) return MI_ERR_BAD_ARG;
-    interior_reduce_kernel<<<dim3(n, mi_cdiv(c, 32), IR_CLUSTER), dim3(32, 32), 0, mi_cs(stream)>>>(x, ldx, mul, ldm, out,
-                                                                                                   h, wd, c, ring, scale);
+    const bool vec = (c % 4 == 0) && (ldx % 4 == 0) && mi_al16(x) && (!mul || ((ldm % 4 == 0) && mi_al16(mul)));
+    if (vec)
+        interior_reduce_vec_kernel<<<dim3(n, mi_cdiv(c, 32), IR_CLUSTER), dim3(8, 128), 0, mi_cs(stream)>>>(
+            x, ldx, mul, ldm, out, h, wd, c, ring, scale);
+    else
+        interior_reduce_kernel<<<dim3(n, mi_cdiv(c, 32), IR_CLUSTER), dim3(32, 32), 0, mi_cs(stream)>>>(x, ldx, mul, ldm, out,
+                                                                                                       h, wd, c, ring, scale);
     MI_LAUNCHED();
     MI_RETURN_LAST();
 }

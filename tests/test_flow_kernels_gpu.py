@@ -177,7 +177,22 @@ def test_space_depth_roundtrip_and_reference(cuda_ops, hw, r):
     assert abs(lhs - rhs) <= 1e-4 * max(1.0, abs(lhs))
 
 
-@pytest.mark.parametrize("geom", [(1, 10, 10, 192, 1), (2, 6, 9, 12, 1), (2, 5, 7, 64, 0), (1, 66, 66, 192, 1)])
+@pytest.mark.parametrize("geom", [(1, 9, 9, 32, 1), (2, 33, 20, 8, 0), (1, 12, 12, 64, 1)])
+def test_interior_reduce_scalar_and_vector_paths(cuda_ops, geom):
+    """16-byte-aligned rows take the float4 kernel; a channel slice that starts one float into a wider buffer (rows not
+    16-byte aligned) takes the scalar one.  Same answer."""
+    n, h, w, c, ring = geom
+    xc, xd = act_pair(cuda_ops, n, h, w, c + 4, 64)
+    mc, md = act_pair(cuda_ops, n, h, w, c + 4, 65)
+    for lo in (0, 1):
+        xs, ms = xd[..., lo:lo + c], md[..., lo:lo + c]
+        xr, mr = xc[..., lo:lo + c].contiguous(), mc[..., lo:lo + c].contiguous()
+        close(cuda_ops.interior_reduce(xs, None, ring, 0.25), REF.interior_reduce(xr, None, ring, 0.25), 2e-5, "reduce")
+        close(cuda_ops.interior_reduce(xs, ms, ring, 1.0), REF.interior_reduce(xr, mr, ring, 1.0), 2e-5, "reduce * mul")
+
+
+@pytest.mark.parametrize("geom", [(1, 10, 10, 192, 1), (2, 6, 9, 12, 1), (2, 5, 7, 64, 0), (1, 66, 66, 192, 1),
+                                  (2, 130, 130, 192, 1), (1, 40, 56, 100, 1)])   # many pixels per cluster rank
 def test_channel_attention_pieces(cuda_ops, geom):
     """Global average pool, per-channel rescale + residual and their adjoints (MetaCALayer, model_utils.py:931-953)."""
     n, h, w, c, ring = geom

@@ -41,6 +41,8 @@ CONV_SHAPES = [
     # few-output-channel heads (flow / mask / RGB): the per-pixel forward and per-(tap,cin) weight-gradient kernels
     (2, 16, 24, 32, 5, 3), (1, 20, 28, 32, 4, 3), (1, 12, 12, 64, 3, 5), (2, 9, 11, 32, 2, 3), (1, 40, 33, 33, 8, 3),
     (1, 70, 90, 32, 4, 3), (2, 12, 20, 32, 10, 3), (1, 16, 16, 32, 9, 3), (1, 10, 14, 64, 3, 5), (1, 6, 6, 250, 2, 3),
+    # feature maps of a few pixels (CAIN's channel attention: 1x1 convs on [N, C, 1, 1]): one warp per output element
+    (2, 1, 1, 192, 12, 1), (2, 1, 1, 12, 192, 1), (1, 1, 1, 64, 4, 1), (4, 2, 2, 70, 33, 3), (1, 3, 5, 40, 7, 3),
 ]
 
 
