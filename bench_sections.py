@@ -203,7 +203,10 @@ def cpu_reference_run(steps, warmup, world):
 
 # --------------------------------------------------------------------------------------------- other configs
 OTHER_CONFIGS = {
-    # BASELINE.json configs[2..4]: (flags, (H, W), global meta-batch, GPUs the config is quoted on, scaling)
+    # BASELINE.json configs[0] (the reference's CPU plumbing case, here on the GPU: one task per GPU) and configs[2..4]:
+    # (flags, (H, W), global meta-batch, scaling, init gain)
+    "C1 voxelflow K=1 128x128": (dict(model="voxelflow", loss="1*MSE", optimizer="SGD",
+                                      number_of_training_steps_per_iter=1), (128, 128), 1, "weak", None),
     "C3 superslomo Meta-SGD K=5 256x448": (dict(model="superslomo", loss="1*L1", optimizer="SGD", metasgd=True,
                                                 number_of_training_steps_per_iter=5), (256, 448), 4, "weak", None),
     "C4 cain L2F K=3 512x512": (dict(model="cain", loss="1*L1", optimizer="SGD", attenuate=True,
@@ -220,6 +223,8 @@ def _normalise(frames, model):
     if model == "superslomo":
         mean = torch.tensor([0.429, 0.431, 0.397]).view(1, 3, 1, 1)
         return [f - mean for f in frames]
+    if model == "voxelflow":
+        return [(f * 255 - 127.5) / 127.5 for f in frames]
     return frames
 
 
