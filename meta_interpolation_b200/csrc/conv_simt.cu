@@ -925,8 +925,11 @@ int mi_conv2d_wgrad(const float* x, int ldx, const float* dy, int lddy, int n, i
     int rc = MI_ERR_UNSUPPORTED;
     int bias_splits = splits;   // the SIMT kernel emits one bias partial per split-K slice
     if (engine != MI_ENGINE_SIMT && mi_tc_wgrad_eligible(x, ldx, dy, lddy, n, h, wd, cin, cout, k))
-        rc = mi_tc_wgrad_partials(x, ldx, dy, lddy, n, h, wd, cin, cout, k, ldw, ws_w, ws_b, splits, st);
-    if (rc == 0) bias_splits = mi_bias_splits((long long)n * h * wd);
+    {
+        int tc_bias_splits = 0;
+        rc = mi_tc_wgrad_partials(x, ldx, dy, lddy, n, h, wd, cin, cout, k, ldw, ws_w, ws_b, splits, &tc_bias_splits, st);
+        if (rc == 0) bias_splits = tc_bias_splits;
+    }
     if (rc == MI_ERR_UNSUPPORTED && engine != MI_ENGINE_TC && small_cout_wgrad_ok(cin, cout, k)) {
         const long long m_total = (long long)n * h * wd;
         const long long chunk = (m_total + splits - 1) / splits;

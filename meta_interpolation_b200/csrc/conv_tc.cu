@@ -1334,6 +1334,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 struct WgradKxParams {
     int n, h, w, cin, cout, k, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb, ci_tiles;
     float* ws_w;
+    float* ws_b;      // != nullptr: the bias-gradient partial of every split is produced here too (see the producer warp)
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -1371,10 +1372,16 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     // finite contents for the aliased A blocks of the last stage
     for (uint32_t i = threadIdx.x; i < tail_pad / 16; i += NTHREADS)
         reinterpret_cast<float4*>(smem + (size_t)p.stages * stage_bytes)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // The bias gradient rides along: the dY boxes of every tile pass through this CTA's shared memory anyway, and the
+    // four epilogue warps have nothing to do until the accumulator is final.  In the CTA of the centre filter column
+    // and the first cin block, epilogue warp q sums box q over the pixels of every stage (lane l = channel
+    // co0 + 32 q + l) and releases the stage together with the MMA lane (the `empty` barrier then counts 1 + na
+    // arrivals); one partial per split-K slice replaces a separate pass over dY (`bias_partial_kernel`) per layer.
+    const bool do_bias = p.ws_b != nullptr && kx == (p.k >> 1) && ci0 == 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
-            mbar_init(smem_u32(&bars[p.stages + s]), 1);
+            mbar_init(smem_u32(&bars[p.stages + s]), do_bias ? 1u + (uint32_t)p.na : 1u);
         }
         mbar_init(smem_u32(&bars[2 * p.stages]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1445,6 +1452,34 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         const int q = warp & 3;
         const int co = co0 + q * 32 + lane;
         const int kk2 = p.k * p.k;
+        if (do_bias && q < p.na) {
+            // box rows are 128-byte pixel rows in the SWIZZLE_128B_ATOM_32B pattern (cute's Swizzle<2,5,2>): the
+            // 32-byte chunk index is XOR-ed with the pixel-row index mod 4
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int npix = p.rows * 8;
+            const uint32_t lane_off = ((uint32_t)(lane & 7)) << 2, chunk = (uint32_t)lane >> 3;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < iters; ++it) {
+                mbar_wait(smem_u32(&bars[s]), ph);
+                const uint32_t bj = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)q * a_box + lane_off;
+                for (int px = 0; px < npix; px += 8) {          // pixel row px + i has swizzle phase i & 3
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("ld.shared.f32 %0, [%1];"
+                                     : "=f"(v[i]) : "r"(bj + (uint32_t)(px + i) * ROW_BYTES + ((chunk ^ (uint32_t)(i & 3)) << 5)));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] += v[i];
+                }
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars[p.stages + s])) : "memory");
+                if (++s == p.stages) { s = 0; ph ^= 1u; }
+            }
+            if (co < p.cout)
+                p.ws_b[(long long)split * p.cout + co] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        }
         float* dst0 = p.ws_w + (long long)split * p.cout * kk2 * p.ldw + (long long)co * kk2 * p.ldw;
         if (iters > 0) {
             mbar_wait(smem_u32(&bars[2 * p.stages]), 0);
@@ -2020,7 +2055,9 @@ bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, in
 }
 
 int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
-                         int k, int ldw, float* ws_w, float* ws_b, int splits, cudaStream_t stream) {
+                         int k, int ldw, float* ws_w, float* ws_b, int splits, int* bias_splits_out,
+                         cudaStream_t stream) {
+    *bias_splits_out = mi_bias_splits((long long)n * h * wd);
     if (mi_tc_wgrad_kx_shape(cin, cout, k)) {
         WgradKxParams q;
         q.n = n; q.h = h; q.w = wd; q.cin = cin; q.cout = cout; q.k = k; q.ldw = ldw;
@@ -2029,6 +2066,9 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         q.ci_tiles = mi_cdiv(cin, 64);
         const int co_tiles = mi_cdiv(cout, BM);
         q.ws_w = ws_w;
+        static int bias_fused = -1;      // MI_B200_WGRAD_BIAS_FUSED=0: separate bias_partial_kernel pass (A/B switch)
+        if (bias_fused < 0) { const char* e = getenv("MI_B200_WGRAD_BIAS_FUSED"); bias_fused = (e && e[0] == '0') ? 0 : 1; }
+        q.ws_b = bias_fused ? ws_b : nullptr;
         const size_t row_bytes = 8 * ROW_BYTES;
         // Tile height: every pipeline stage costs the MMA lane one barrier wait (~450 cycles), so the narrow layers
         // (one or two boxes per operand: 8-16 MMAs per 8-row stage) take 16-row tiles when three stages still fit.
@@ -2069,12 +2109,17 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         MI_LAUNCHED();
         cudaError_t e = cudaPeekAtLastError();
         if (e != cudaSuccess) return (int)e;
+        if (q.ws_b) {                    // one bias partial per split-K slice came out of the kernel itself
+            *bias_splits_out = splits;
+            return MI_OK;
+        }
         const long long m_total = (long long)n * h * wd;
         const int bsplits = mi_bias_splits(m_total);
         const long long chunk = (m_total + bsplits - 1) / bsplits;
         const int vec = mi_al16(dy) && (lddy % 4 == 0) && ((cout % 4 == 0) || lddy == ((cout + 3) & ~3));
         bias_partial_kernel<<<dim3(bsplits, mi_cdiv(cout, 32)), 256, 0, stream>>>(dy, lddy, ws_b, cout, m_total, chunk, vec);
         MI_LAUNCHED();
+        *bias_splits_out = bsplits;
         MI_RETURN_LAST();
     }
     WgradParams p;

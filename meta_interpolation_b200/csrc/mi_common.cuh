@@ -80,7 +80,8 @@ int mi_tc_fprop(const float* x, int ldx, const float* w, int ldw, const float* b
                 const float* mask_y, int ldmask, int mask_act, float mask_slope, int accumulate,
                 int n, int h, int wd, int cin, int cout, int k, int act, float slope, cudaStream_t stream);
 int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
-                         int k, int ldw, float* ws_w, float* ws_b, int splits, cudaStream_t stream);
+                         int k, int ldw, float* ws_w, float* ws_b, int splits, int* bias_splits_out,
+                         cudaStream_t stream);
 bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, const float* y, int ldy, int n, int h,
                           int wd, int cin, int cout, int k);
 bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
