@@ -8,8 +8,10 @@
 // wgrad  : D[128 couts][BN cins] += dY[P pixels][128 couts]^T * X_tap[P pixels][BN cins] per pixel chunk:
 //          the reduction (pixels) is the slow dimension of both NHWC tensors, so both operands are MN-major.
 //
-// Warp roles per CTA (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer
-// (one lane), warps 2-5 = epilogue (tcgen05.ld -> registers -> bias/activation/mask -> global).
+// Warp roles per CTA: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), then the
+// epilogue warps (tcgen05.ld -> registers -> bias/activation/mask -> global): four in the per-tap kernels and the
+// weight-gradient kernels (192 threads), eight in the halo kernels (320), eight plus a store warp in the default 3x3
+// engine, the filter-column-stacked kernel of conv_tc_kxs.cuh (352).
 // Replaces cuDNN's F.conv2d kernels used by the reference (model_utils.py:360).
 #include <cuda.h>
 #include <cstdio>

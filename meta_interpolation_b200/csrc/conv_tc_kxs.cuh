@@ -1,10 +1,11 @@
 // 3x3 fprop / dgrad with the three filter COLUMNS stacked along the MMA N dimension (included by conv_tc.cu inside its
 // anonymous namespace, after the PTX wrappers and the epilogue helpers).
 //
-// Why: in SS mode a `tcgen05.mma kind::tf32` of 128 x N x 8 costs max(~64, N/2) cycles on B200 -- the 128 x 32-byte
-// A-operand fetch from shared memory sets a floor that N <= 128 never reaches (per-role cycle counters of the halo
-// kernels: 55-70 cycles per MMA for N = 32, 64 and 128 alike).  The halo kernels issue nine N = Cout <= 64 MMAs per
-// 8-channel K slice, i.e. they run the tensor pipe at <= 50 % by construction.  Here ONE MMA serves three taps:
+// Why: in SS mode a `tcgen05.mma kind::tf32` of 128 x N x 8 does not get cheaper below N ~ 128 on B200 -- the
+// 128 x 32-byte A-operand fetch from shared memory sets a floor (per-role cycle counters: 60-72 cycles per MMA at
+// N = 64 in the halo kernels, ~100 at N = 192 here, against a tensor-pipe floor of N / 2).  The halo kernels issue nine
+// N = Cout <= 64 MMAs per 8-channel K slice, i.e. they run the tensor pipe at <= 50 % by construction (ncu: 32.5 %).
+// Here ONE MMA serves three taps (ncu: 47-49 % on a 148-CTA launch, 59-61 % at the 37-CTA share of the 8-lane run):
 //
 //     D[p][(kx, co)] += sum_ci  Xbox[row(p) + ky][col(p)][ci] * W[ky][kx][ci][co]          (N = 3 * Cout-tile = 192)
 //
@@ -23,9 +24,9 @@
 // STREAM = false: all weights of the layer (Cin, Cout <= 64) stay resident in shared memory.
 // STREAM = true : > 64 channels; a pipeline stage carries the box of one 32-channel chunk and the nine
 //                 {64 cout x 32 cin} weight tiles of that chunk; persistent CTAs walk (pixel tile, 64-cout tile) items.
-// Warp roles as in the halo kernels: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane
-// quarter, 16 columns each).  The epilogue releases the accumulator buffer as soon as its TMEM reads are done, before
-// the activation / staging / global stores.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quarter, 16 columns each),
+// warp 10 output stores (see KXS_THREADS).  The epilogue releases the accumulator buffer as soon as its TMEM reads
+// are done, before the activation / staging / stores.
 
 constexpr int KX_W = 16, KX_OW = 14, KX_H = 8, KX_BOX_H = 10;
 constexpr uint32_t KX_BOX_BYTES = KX_W * KX_BOX_H * ROW_BYTES;       // 20 KB, a multiple of 1024
