@@ -62,6 +62,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols)
                  : "memory");
@@ -1336,7 +1343,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_co
 struct WgradKxParams {
     int n, h, w, cin, cout, k, ldw, rows, tiles_x, tiles_y, total_tiles, tiles_per_split, stages, na, nb, ci_tiles;
     float* ws_w;
-    float* ws_b;      // != nullptr: the bias-gradient partial of every split is produced here too (see the producer warp)
+    float* ws_b;      // != nullptr: the bias-gradient partial of every split is produced here too (see the epilogue warps)
+    int merged;       // 3x3, Cin a multiple of 64: both 32-channel halves of the X block in ONE N = 192 MMA per tile row
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -1414,14 +1422,21 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 mbar_expect_tx(full, stage_bytes);
                 for (int j = 0; j < p.na; ++j)
                     tma_load_4d(base + j * a_box, &map_dy, full, co0 + j * KCH, x0, y0, img);
-                for (int j = 0; j < p.nb; ++j)
-                    tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - pad, y0 - pad, img);
+                if (p.merged) {
+                    // one 5-D box {32 ch, 8 px, 2 halves, R+2 rows}: in shared memory the two 32-channel halves of a tile
+                    // row follow each other, so (ky, half) are six MN blocks at ONE stride of 1024 bytes
+                    tma_load_5d(base + a_bytes, &map_x, full, 0, x0 + kx - pad, ci0 / KCH, y0 - pad, img);
+                } else {
+                    for (int j = 0; j < p.nb; ++j)
+                        tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - pad, y0 - pad, img);
+                }
             }
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
         const uint32_t idesc = instr_desc(BM, (int)ncols, 1, 1);   // both operands MN-major, N = k taps x 32 channels
+        const uint32_t idesc2 = instr_desc(BM, 2 * (int)ncols, 1, 1);
         // A: 4 MN blocks (32 couts each) one dY box apart; B: k MN blocks (ky = 0..k-1) one tile row apart.
         // K = 8 pixels = one tile row = two 4-pixel swizzle atoms 512 B apart (SBO).
         const uint64_t ad_base = smem_desc(smem_u32(smem), a_box, 512, 1);
@@ -1433,6 +1448,17 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
             tc_fence_after();
             if (elect_one()) {
                 const uint64_t ad0 = desc_advance(ad_base, s_off);
+                if (p.merged) {
+                    // N = 192: the dY fetch of a tile row is shared by six (ky, half) blocks instead of three
+                    const uint64_t bd0 = desc_advance(bd_base, s_off);
+#define MI_WGKX_ROWS2(R0, R1)                                                                                       \
+    _Pragma("unroll") for (int r = R0; r < R1; ++r)                                                                 \
+        umma_tf32(tmem_base, desc_advance(ad0, (uint32_t)r * 1024u), desc_advance(bd0, (uint32_t)r * 2048u), idesc2,\
+                  (it > 0 || r > 0) ? 1u : 0u);
+                    MI_WGKX_ROWS2(0, 8)
+                    if (p.rows == 16) { MI_WGKX_ROWS2(8, 16) }
+#undef MI_WGKX_ROWS2
+                } else
                 for (int j = 0; j < p.nb; ++j) {
                     const uint64_t bd0 = desc_advance(bd_base, s_off + (uint32_t)j * b_box);
                     const uint32_t d_addr = tmem_base + (uint32_t)j * ncols;
@@ -1491,7 +1517,8 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
             for (int ky = 0; ky < p.k; ++ky) {
                 uint32_t v[32];
                 if (iters > 0) {
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)j * ncols + (uint32_t)(ky * 32), v);
+                    const uint32_t col = p.merged ? (uint32_t)((ky * 2 + j) * 32) : (uint32_t)j * ncols + (uint32_t)(ky * 32);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + col, v);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
@@ -2095,7 +2122,24 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         CUtensorMap map_dy, map_x;
         if (!make_act_map(&map_dy, dy, lddy, n, h, wd, cout, 8, q.rows, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return MI_ERR_UNSUPPORTED;
-        if (!make_act_map(&map_x, x, ldx, n, h, wd, cin, 8, q.rows + k - 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        static int merge_on = -1;        // MI_B200_WGRAD_MERGED=0: two N = 96 MMAs per tile row everywhere (A/B switch)
+        if (merge_on < 0) { const char* e = getenv("MI_B200_WGRAD_MERGED"); merge_on = (e && e[0] == '0') ? 0 : 1; }
+        q.merged = (merge_on && k == 3 && q.nb == 2 && cin % 64 == 0) ? 1 : 0;
+        if (q.merged) {
+            // x[n][y][x][half][c32]: the channel dimension split in two so that one box brings both halves of a tile row
+            EncodeTiledFn fn = encode_fn();
+            cuuint64_t dims[5] = {(cuuint64_t)KCH, (cuuint64_t)wd, (cuuint64_t)(cin / KCH), (cuuint64_t)h, (cuuint64_t)n};
+            cuuint64_t strides[4] = {(cuuint64_t)ldx * 4, (cuuint64_t)KCH * 4, (cuuint64_t)wd * ldx * 4,
+                                     (cuuint64_t)h * wd * ldx * 4};
+            cuuint32_t box[5] = {(cuuint32_t)KCH, 8, 2, (cuuint32_t)(q.rows + k - 1), 1};
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            if (!fn || fn(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                q.merged = 0;            // the driver refused the 5-D view: two 4-D boxes as before
+        }
+        if (!q.merged &&
+            !make_act_map(&map_x, x, ldx, n, h, wd, cin, 8, q.rows + k - 1, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return MI_ERR_UNSUPPORTED;
         static bool attr_kx = false;
         if (!attr_kx) {
