@@ -80,6 +80,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // named barriers between the 8 epilogue warps and the store warp (288 threads): one side arrives, the other waits
@@ -368,6 +369,10 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             } else {
               // one round per item -- or, with a single staging box (p.one_box, plain mode), one round per 32-channel box
               const int rounds = (EPI == KXS_EPI_PLAIN && p.one_box) ? npiece : 1;
+              // Cout <= 32: an item fills ONE box, so items alternate between the two boxes of the staging tile and the
+              // store of item t overlaps the staging of item t + 1 (these layers are the cheapest per tile -- 12 MMAs
+              // of N = 96 -- and were paced by the store round trip, per-role counters)
+              const uint32_t alt_off = (p.bn <= 32 && !p.one_box) ? (uint32_t)(t & 1) * KX_OUT_BOX : 0u;
               for (int rd = 0; rd < rounds; ++rd) {
                 const long long cb = clock64();
                 if (EPI == KXS_EPI_OPERAND) mbar_wait(op_bar, (uint32_t)t & 1u);   // operand landed => staging is ours
@@ -379,7 +384,7 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                         if (pc < npiece && (rounds == 1 || pc == rd)) {
 #pragma unroll
                             for (int g = 0; g < 4; ++g) {
-                                const uint32_t a = my_row + (rounds == 1 ? (uint32_t)pc * KX_OUT_BOX : 0u) +
+                                const uint32_t a = my_row + (rounds == 1 ? (uint32_t)pc * KX_OUT_BOX : 0u) + alt_off +
                                                    ((((uint32_t)(4 * half + g)) ^ swz) << 4);
                                 float4 v = make_float4(acc[pc][4 * g], acc[pc][4 * g + 1], acc[pc][4 * g + 2], acc[pc][4 * g + 3]);
                                 if (EPI == KXS_EPI_OPERAND) {
@@ -464,13 +469,15 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
             const int ty_i = tile % p.tiles_y; tile /= p.tiles_y;
             img = tile; x0 = tx_i * KX_OW; y0 = ty_i * KX_H;
         };
+        const bool alt = p.bn <= 32 && !p.one_box;          // items alternate between the two staging boxes
         auto load_operand = [&](int t) {          // one lane: mask / previous-y boxes of item t into the staging tile
             int co0, x0, y0, img;
             item_coords(t, co0, x0, y0, img);
             const int nbox = (p.bn > 32 && co0 + 32 < c_tma) ? 2 : 1;
+            const uint32_t dst = stg + (alt ? (uint32_t)(t & 1) * KX_OUT_BOX : 0u);
             mbar_expect_tx(op_bar, (uint32_t)nbox * KX_OUT_BOX);
             for (int b = 0; b < nbox; ++b)
-                tma_load_4d(stg + (uint32_t)b * KX_OUT_BOX, &map_op, op_bar, co0 + 32 * b, x0, y0, img);
+                tma_load_4d(dst + (uint32_t)b * KX_OUT_BOX, &map_op, op_bar, co0 + 32 * b, x0, y0, img);
         };
         if (EPI == KXS_EPI_OPERAND) {
             if (my_items > 0 && elect_one()) load_operand(0);
@@ -487,7 +494,9 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                 const bool last = (t + 1 == my_items) && (rd + 1 == rounds);
                 kxs_bar_sync(2);                     // all eight epilogue warps have staged item t (round rd)
                 if (elect_one()) {
-                    if (rounds == 1) {
+                    if (alt) {
+                        if (co0 < c_tma) tma_store_4d(&map_y, stg + (uint32_t)(t & 1) * KX_OUT_BOX, co0, x0, y0, img);
+                    } else if (rounds == 1) {
                         for (int b = 0; b < 2; ++b)
                             if (32 * b < p.bn && co0 + 32 * b < c_tma)
                                 tma_store_4d(&map_y, stg + (uint32_t)b * KX_OUT_BOX, co0 + 32 * b, x0, y0, img);
@@ -496,7 +505,8 @@ conv_fprop_tc_kxs_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
                     }
                     tma_store_commit();
                     const long long cw = clock64();
-                    tma_store_wait_read();
+                    if (alt) tma_store_wait_read_but_one();     // the OTHER box (item t - 1) has been read: it is free
+                    else tma_store_wait_read();
                     e_wr += clock64() - cw;
                     if (EPI == KXS_EPI_OPERAND && t + 1 < my_items) load_operand(t + 1);
                     if (last) tma_store_wait_all();
