@@ -678,7 +678,8 @@ int mi_wgrad_splits(int n, int h, int wd, int cin, int cout, int k) {
         // filter-column kernel: grid = (3, splits) persistent CTAs over 8x8-pixel tiles; one wave of the 148 SMs,
         // at least four tiles per CTA so the pipeline fills
         const long long tiles = (long long)n * mi_cdiv(h, 8) * mi_cdiv(wd, 8);
-        const long long per_split = (long long)k * mi_cdiv(cin, 64) * mi_cdiv(cout, 128);   // CTAs of one split-K slice
+        const long long groups = mi_tc_wgrad_kx_pair(cin, cout, k) ? (k + 1) / 2 : k;      // filter-column groups
+        const long long per_split = groups * mi_cdiv(cin, 64) * mi_cdiv(cout, 128);          // CTAs of one split-K slice
         long long s = tiles / 4;
         const long long cap = mi_sm_budget() / per_split;
         if (s > cap) s = cap;

@@ -1345,6 +1345,7 @@ struct WgradKxParams {
     float* ws_w;
     float* ws_b;      // != nullptr: the bias-gradient partial of every split is produced here too (see the epilogue warps)
     int merged;       // 3x3, Cin a multiple of 64: both 32-channel halves of the X block in ONE N = 192 MMA per tile row
+    int pair;         // Cout <= 64: TWO filter columns per CTA in the two halves of the M = 128 accumulator (see kernel)
 };
 
 __global__ void __launch_bounds__(NTHREADS)
@@ -1357,12 +1358,18 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const uint32_t b_box = (uint32_t)(p.rows + p.k - 1) * row_bytes; // X box  {32 ch, 8 px, R+k-1 rows}
     const int pad = p.k >> 1;
     const uint32_t ncols = 32u * (uint32_t)p.k;                      // accumulator columns per X box: k taps x 32 cin
-    const uint32_t a_bytes = (uint32_t)p.na * a_box, b_bytes = (uint32_t)p.nb * b_box;
+    // Paired mode (Cout <= 64, i.e. at most two dY boxes): with one filter column per CTA half of the 128 accumulator
+    // rows were padding.  The gradient of tap (ky, kx) is sum_q X[q + ky - pad][ci] * dY[q - (kx - pad)][co] over the X
+    // pixels q of the tile, so ONE unshifted X box serves two filter columns if the dY boxes are the ones that shift:
+    // A = [dY shifted for kx_a | dY shifted for kx_b] fills all four MN blocks, rows 0..63 of D belong to kx_a and
+    // rows 64..127 (32..63 for Cout <= 32) to kx_b, and a layer needs ceil(k / 2) CTAs per split-K slice instead of k.
+    const int a_slots = p.pair ? 2 * p.na : p.na;
+    const uint32_t a_bytes = (uint32_t)a_slots * a_box, b_bytes = (uint32_t)p.nb * b_box;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     // the M=128 A descriptor always spans four 32-channel blocks; blocks past `na` alias whatever follows (the X
     // boxes, the next stage, or the zeroed tail pad after the last stage) and only feed accumulator rows >= cout,
     // which are never read back
-    const uint32_t tail_pad = (uint32_t)(4 - p.na) * a_box;
+    const uint32_t tail_pad = (uint32_t)(4 - a_slots) * a_box;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes + tail_pad);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
     uint32_t tmem_cols = 32;                                         // nb * k * 32 accumulator columns -> power of two
@@ -1371,8 +1378,10 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // blockIdx.x = kx + 3 * (cin tile of 64 + ci_tiles * cout tile of 128): wider layers are cut into channel blocks,
     // each block re-reading its dY / X boxes (3 * ci_tiles and 3 * co_tiles passes instead of 9 * tiles of the per-tap form)
-    const int kx = (int)blockIdx.x % p.k;
-    const int ct = (int)blockIdx.x / p.k;
+    const int groups = p.pair ? (p.k + 1) / 2 : p.k;                // filter-column groups per (cin, cout) block
+    const int kx = p.pair ? 2 * ((int)blockIdx.x % groups) : (int)blockIdx.x % groups;   // (first) filter column of this CTA
+    const bool kxb_ok = p.pair && kx + 1 < p.k;                    // paired mode: the second column exists
+    const int ct = (int)blockIdx.x / groups;
     const int ci0 = (ct % p.ci_tiles) * 64, co0 = (ct / p.ci_tiles) * BM;
     const int split = blockIdx.y;
     const int t_begin = split * p.tiles_per_split;
@@ -1387,7 +1396,9 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
     // and the first cin block, epilogue warp q sums box q over the pixels of every stage (lane l = channel
     // co0 + 32 q + l) and releases the stage together with the MMA lane (the `empty` barrier then counts 1 + na
     // arrivals); one partial per split-K slice replaces a separate pass over dY (`bias_partial_kernel`) per layer.
-    const bool do_bias = p.ws_b != nullptr && kx == (p.k >> 1) && ci0 == 0;
+    // (paired mode: the unshifted dY, the one of the centre column, is slot 0 or slot 1 of this CTA's pair)
+    const int bias_slot = pad - kx;
+    const bool do_bias = p.ws_b != nullptr && ci0 == 0 && (p.pair ? (bias_slot == 0 || (bias_slot == 1 && kxb_ok)) : kx == pad);
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&bars[s]), 1);
@@ -1419,16 +1430,22 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
                 const int x0 = tx_i * 8, y0 = ty_i * p.rows;
                 const uint32_t full = smem_u32(&bars[s]);
                 const uint32_t base = smem_u32(smem + (size_t)s * stage_bytes);
-                mbar_expect_tx(full, stage_bytes);
+                // paired mode: X stays put and the dY boxes shift (slot 0: column kx, slot 1: column kx + 1); otherwise
+                // dY stays put and X shifts
+                const int xs = p.pair ? 0 : kx - pad;
+                mbar_expect_tx(full, stage_bytes - ((p.pair && !kxb_ok) ? (uint32_t)p.na * a_box : 0u));
                 for (int j = 0; j < p.na; ++j)
-                    tma_load_4d(base + j * a_box, &map_dy, full, co0 + j * KCH, x0, y0, img);
+                    tma_load_4d(base + j * a_box, &map_dy, full, co0 + j * KCH, x0 + (p.pair ? pad - kx : 0), y0, img);
+                if (kxb_ok)
+                    for (int j = 0; j < p.na; ++j)
+                        tma_load_4d(base + (p.na + j) * a_box, &map_dy, full, co0 + j * KCH, x0 + pad - kx - 1, y0, img);
                 if (p.merged) {
                     // one 5-D box {32 ch, 8 px, 2 halves, R+2 rows}: in shared memory the two 32-channel halves of a tile
                     // row follow each other, so (ky, half) are six MN blocks at ONE stride of 1024 bytes
-                    tma_load_5d(base + a_bytes, &map_x, full, 0, x0 + kx - pad, ci0 / KCH, y0 - pad, img);
+                    tma_load_5d(base + a_bytes, &map_x, full, 0, x0 + xs, ci0 / KCH, y0 - pad, img);
                 } else {
                     for (int j = 0; j < p.nb; ++j)
-                        tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + kx - pad, y0 - pad, img);
+                        tma_load_4d(base + a_bytes + j * b_box, &map_x, full, ci0 + j * KCH, x0 + xs, y0 - pad, img);
                 }
             }
             __syncwarp();
@@ -1478,9 +1495,14 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
         }
     } else {
         const int q = warp & 3;
-        const int co = co0 + q * 32 + lane;
+        // accumulator rows 32 q .. 32 q + 31: cout block q -- or, in paired mode, cout block q % na of filter column
+        // kx + q / na
+        const int slot = p.pair ? q / p.na : 0;
+        const int kx_q = kx + slot;
+        const bool rows_ok = p.pair ? (slot == 0 || (slot == 1 && kxb_ok)) : true;
+        const int co = co0 + (p.pair ? q % p.na : q) * 32 + lane;
         const int kk2 = p.k * p.k;
-        if (do_bias && q < p.na) {
+        if (do_bias && (p.pair ? (slot == bias_slot) : q < p.na)) {
             // box rows are 128-byte pixel rows in the SWIZZLE_128B_ATOM_32B pattern (cute's Swizzle<2,5,2>): the
             // 32-byte chunk index is XOR-ed with the pixel-row index mod 4
             float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1523,10 +1545,10 @@ conv_wgrad_tc_kx_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] = 0u;
                 }
-                if (co >= p.cout) continue;
+                if (co >= p.cout || !rows_ok) continue;
                 const int cb = ci0 + j * KCH;
                 if (cb >= p.cin) continue;
-                float* dst = dst0 + (ky * p.k + kx) * p.ldw;
+                float* dst = dst0 + (ky * p.k + kx_q) * p.ldw;
                 if (cb + 32 <= p.ldw) {
 #pragma unroll
                     for (int g = 0; g < 8; ++g)
@@ -2073,6 +2095,16 @@ bool mi_tc_wgrad_kx_shape(int cin, int cout, int k) {
            encode_fn();
 }
 
+// Cout <= 64: two filter columns share a CTA (the halves of the M = 128 accumulator); MI_B200_WGRAD_PAIR=0: A/B switch
+bool mi_tc_wgrad_kx_pair(int cin, int cout, int k) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MI_B200_WGRAD_PAIR");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on && cout <= 64 && mi_tc_wgrad_kx_shape(cin, cout, k);
+}
+
 bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
                           int k) {
     (void)n;
@@ -2098,18 +2130,23 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
         static int bias_fused = -1;      // MI_B200_WGRAD_BIAS_FUSED=0: separate bias_partial_kernel pass (A/B switch)
         if (bias_fused < 0) { const char* e = getenv("MI_B200_WGRAD_BIAS_FUSED"); bias_fused = (e && e[0] == '0') ? 0 : 1; }
         q.ws_b = bias_fused ? ws_b : nullptr;
+        q.pair = mi_tc_wgrad_kx_pair(cin, cout, k) ? 1 : 0;
+        const int a_slots = q.pair ? 2 * q.na : q.na;
         const size_t row_bytes = 8 * ROW_BYTES;
         // Tile height: every pipeline stage costs the MMA lane one barrier wait (~450 cycles), so the narrow layers
         // (one or two boxes per operand: 8-16 MMAs per 8-row stage) take 16-row tiles when three stages still fit.
         // (the split count was sized on 8x8 tiles; with 16 rows a CTA simply walks half as many, twice as large)
         int rows = 16, stages = 0;
         size_t stage_bytes = 0, tail = 0;
+        static int min16 = -1;           // MI_B200_WGRAD_MIN16: stages a 16-row tile must leave room for (default 3)
+        if (min16 < 0) { const char* e = getenv("MI_B200_WGRAD_MIN16"); min16 = e ? atoi(e) : 3; }
+        const int min_stages16 = min16;
         for (;; rows = 8) {
-            stage_bytes = (size_t)q.na * rows * row_bytes + (size_t)q.nb * (rows + k - 1) * row_bytes;
-            tail = (size_t)(4 - q.na) * rows * row_bytes;
+            stage_bytes = (size_t)a_slots * rows * row_bytes + (size_t)q.nb * (rows + k - 1) * row_bytes;
+            tail = (size_t)(4 - a_slots) * rows * row_bytes;
             stages = (int)((200 * 1024 - tail) / stage_bytes);
             if (stages > 6) stages = 6;
-            if (rows == 8 || (stages >= 3 && h >= 16)) break;
+            if (rows == 8 || (stages >= min_stages16 && h >= 16)) break;
         }
         if (stages < 2) return MI_ERR_UNSUPPORTED;
         q.rows = rows;
@@ -2148,7 +2185,7 @@ int mi_tc_wgrad_partials(const float* x, int ldx, const float* dy, int lddy, int
             if (e != cudaSuccess) return (int)e;
             attr_kx = true;
         }
-        dim3 grid(k * q.ci_tiles * co_tiles, splits);
+        dim3 grid((q.pair ? (k + 1) / 2 : k) * q.ci_tiles * co_tiles, splits);
         mi_prof_begin(MI_TAG_WGRAD_KX, mi_conv_flops(n, h, wd, cin, cout, k), mi_conv_bytes(n, h, wd, cin, cout, k), stream);
         conv_wgrad_tc_kx_kernel<<<grid, NTHREADS, smem, stream>>>(map_dy, map_x, q);
         mi_prof_end(stream);

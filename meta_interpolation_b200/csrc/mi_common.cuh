@@ -87,3 +87,4 @@ bool mi_tc_fprop_eligible(const float* x, int ldx, const float* w, int ldw, cons
 bool mi_tc_wgrad_eligible(const float* x, int ldx, const float* dy, int lddy, int n, int h, int wd, int cin, int cout,
                           int k);
 bool mi_tc_wgrad_kx_shape(int cin, int cout, int k);
+bool mi_tc_wgrad_kx_pair(int cin, int cout, int k);
