@@ -141,12 +141,10 @@ conv_fprop_simt_kernel(const float* __restrict__ x, int ldx, const float* __rest
 // Tiled form of the rotation for layers wide enough to fill 32x32 tiles: per tap it is a (cout x cin) transpose, done
 // through shared memory so both the read (along cin) and the write (along cout) are 128-byte rows.  Pad lanes of wt
 // (co >= cout) are not touched: weight buffers are allocated zeroed and nothing ever writes those lanes.
-__global__ void __launch_bounds__(256)
-weight_to_dgrad_tiled_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt, int cin, int cout,
-                             int kk, int rnd) {
+__device__ __forceinline__ void weight_to_dgrad_tile(const float* __restrict__ w, int ldw, float* __restrict__ wt,
+                                                     int ldwt, int cin, int cout, int kk, int rnd, int ci0, int co0,
+                                                     int tap) {
     __shared__ float tile[32][33];
-    const int tap = blockIdx.z;
-    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -162,6 +160,28 @@ weight_to_dgrad_tiled_kernel(const float* __restrict__ w, int ldw, float* __rest
             wt[((long long)ci * kk + (kk - 1 - tap)) * ldwt + co] = rnd ? mi_rn_tf32(v) : v;
         }
     }
+}
+__global__ void __launch_bounds__(256)
+weight_to_dgrad_tiled_kernel(const float* __restrict__ w, int ldw, float* __restrict__ wt, int ldwt, int cin, int cout,
+                             int kk, int rnd) {
+    weight_to_dgrad_tile(w, ldw, wt, ldwt, cin, cout, kk, rnd, blockIdx.x * 32, blockIdx.y * 32, blockIdx.z);
+}
+// The rotations of SEVERAL layers in one launch (the deferred finishing stage queues one per adapted layer with at least
+// 128 x 128 channels: 22 launches of 3-7 us per backward pass of the SepConv backbone): blockIdx.y picks the layer,
+// blockIdx.x its (cin tile, cout tile, tap) item; the grid is sized for the largest layer and the others' surplus blocks
+// leave at once.
+struct RotateJob { const float* w; int ldw; float* wt; int ldwt, cin, cout, k, rnd; };
+constexpr int ROTATE_BATCH = 32;
+struct RotateBatch { RotateJob j[ROTATE_BATCH]; };
+__global__ void __launch_bounds__(256) weight_to_dgrad_batch_kernel(const __grid_constant__ RotateBatch b) {
+    const RotateJob& r = b.j[blockIdx.y];
+    const int tci = (r.cin + 31) >> 5, tco = (r.cout + 31) >> 5, kk = r.k * r.k;
+    int t = blockIdx.x;
+    if (t >= tci * tco * kk) return;
+    const int ci_t = t % tci; t /= tci;
+    const int co_t = t % tco;
+    const int tap = t / tco;
+    weight_to_dgrad_tile(r.w, r.ldw, r.wt, r.ldwt, r.cin, r.cout, kk, r.rnd, ci_t * 32, co_t * 32, tap);
 }
 
 // y[r][0:c] = rn_tf32(x[r][0:c]) over rows of an NHWC activation (or a flat buffer); in place when y == x
@@ -710,7 +730,6 @@ int mi_bias_splits(long long m_total) {
 namespace {
 bool g_defer = false;
 std::vector<FinishDesc> g_deferred;
-struct RotateJob { const float* w; int ldw; float* wt; int ldwt, cin, cout, k, rnd; };
 std::vector<RotateJob> g_rotate;
 
 int finish_blocks(const FinishDesc& d) {
@@ -772,12 +791,33 @@ extern "C" int mi_wgrad_defer_flush(mi_stream_t stream) {
         if (e != cudaSuccess) { g_deferred.clear(); g_rotate.clear(); return (int)e; }
     }
     g_deferred.clear();
+    // rotated copies of the updated filters: the tiled ones batched (MI_B200_ROTATE_BATCH=0: one launch per layer)
+    static int batch_on = -1;
+    if (batch_on < 0) { const char* e = getenv("MI_B200_ROTATE_BATCH"); batch_on = (e && e[0] == '0') ? 0 : 1; }
+    RotateBatch rb;
+    int queued = 0, blocks = 0;
+    auto flush_rotations = [&]() -> int {
+        if (!queued) return 0;
+        for (int i = queued; i < ROTATE_BATCH; ++i) rb.j[i] = rb.j[0];
+        weight_to_dgrad_batch_kernel<<<dim3(blocks, queued), 256, 0, st>>>(rb);
+        MI_LAUNCHED();
+        queued = 0; blocks = 0;
+        return (int)cudaPeekAtLastError();
+    };
     for (const RotateJob& r : g_rotate) {
-        const int rc = mi_weight_to_dgrad_launch(r.w, r.ldw, r.wt, r.ldwt, r.cin, r.cout, r.k, r.rnd, st);
+        int rc = 0;
+        if (batch_on && r.cin >= 32 && r.cout >= 32) {
+            rb.j[queued++] = r;
+            blocks = std::max(blocks, mi_cdiv(r.cin, 32) * mi_cdiv(r.cout, 32) * r.k * r.k);
+            if (queued == ROTATE_BATCH) rc = flush_rotations();
+        } else {
+            rc = mi_weight_to_dgrad_launch(r.w, r.ldw, r.wt, r.ldwt, r.cin, r.cout, r.k, r.rnd, st);
+        }
         if (rc != 0) { g_rotate.clear(); return rc; }
     }
+    const int rc = flush_rotations();
     g_rotate.clear();
-    return MI_OK;
+    return rc;
 }
 
 static int fprop_simt_launch(const float* x, int ldx, const float* w, int ldw, const float* bias, float* y, int ldy,
