@@ -3,6 +3,8 @@
 // strides allow), grids are sized in multiples of the 148 SMs.
 #include "mi_common.cuh"
 
+#include <algorithm>
+
 namespace {
 
 constexpr int TPB = 256;
@@ -275,82 +277,110 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
 // ---- strip forms of the two kernels above (default; MI_B200_UPSAMPLE_STRIP=0 selects the per-pixel forms) ----------
 // One thread = one column position (x, 4-channel group) walking a STRIP of rows; blockIdx.y = strip, blockIdx.z = image.
 // What was per output value in the per-pixel form is now per thread (the index decomposition: one division instead of
-// six; the horizontal source coordinates / weights) or uniform over the block (the vertical ones), and a source row is
-// fetched once per thread for all the rows of the strip it feeds: the per-pixel forms were issue-bound at 0.4 (forward)
-// and 0.3 (backward) of the HBM rate (28 / 40 us for 75 MB on the 64-channel 137x233 -> 258x450 Subnet upsample).
-// Rows per thread (`strip`): 8 at most, fewer when the launch would otherwise not fill the chip (up_strip_grid).
+// six; the horizontal source coordinates / weights) or per block (the vertical ones: a table in shared memory), and a
+// source row is fetched once per thread for all the rows of the strip it feeds.  The per-pixel forms were issue-bound
+// at 0.4 (forward) and 0.3 (backward) of the HBM rate (28 / 40 us for 75 MB on the 137x233 -> 258x450 Subnet upsample):
+// ncu counts ~400 instructions per 16 bytes stored there.  Offsets inside an image are 32-bit (the launcher checks).
+// Rows per thread (`strip`): UP_STRIP_MAX at most, fewer when the launch would otherwise not fill the chip
+// (up_strip_grid).  VEC / RND are the two bits of the per-pixel kernels' `vec` parameter, fixed at compile time here.
+constexpr int UP_STRIP_MAX = 8;
+constexpr int UP_SLOTS = UP_STRIP_MAX / 2 + 2;          // source rows a strip of output rows can touch
+constexpr int UP_TPB = 256;
 
-// forward: `strip` output rows per thread.  hx(row) = (1-tx) x[row][x0] + tx x[row][x1] is kept for the two source rows
-// of the previous output row: consecutive output rows share at least one of them.
-__global__ void upsample2_fwd_strip_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int h,
-                                           int wd, int c, int align, int vec, UpWin g, int strip) {
-    MI_SPLIT_VEC_RND(vec, rnd);
+// forward.  The strip's source rows are blended horizontally ONCE, hx(row) = (1-tx) x[row][x0] + tx x[row][x1], all
+// loads of the strip in flight together, and parked in the thread's own column of a shared-memory table (a register
+// file that can be indexed); an output row then is (1-ty) hx[slot0] + ty hx[slot1] with the block's row table.
+template <bool VEC, bool RND>
+__global__ void __launch_bounds__(UP_TPB)
+upsample2_fwd_strip_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int h, int wd, int c,
+                           int align, UpWin g, int strip) {
+    __shared__ float4 s_h[UP_SLOTS][UP_TPB];
+    __shared__ int s_slot0[UP_STRIP_MAX], s_slot1[UP_STRIP_MAX];
+    __shared__ float s_ty[UP_STRIP_MAX];
+    __shared__ int s_base, s_nrows;
+    const int oy0 = blockIdx.y * strip, rows = min(strip, g.oh - oy0);
+    if (threadIdx.x == 0) {
+        int first = 0, last = 0;
+        for (int r = 0; r < rows; ++r) {
+            int y0, y1; float ty;
+            up2_src(oy0 + r + g.hy0, g.full_h, align, g.sy, y0, y1, ty);
+            y0 = min(max(y0 - g.ly0, 0), h - 1); y1 = min(max(y1 - g.ly0, 0), h - 1);
+            if (r == 0) first = y0;
+            s_slot0[r] = min(y0 - first, UP_SLOTS - 1); s_slot1[r] = min(y1 - first, UP_SLOTS - 1); s_ty[r] = ty;
+            last = y1;
+        }
+        s_base = first; s_nrows = min(last - first + 1, UP_SLOTS);
+    }
+    __syncthreads();
     const int cg = (c + 3) >> 2;
-    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned j = blockIdx.x * UP_TPB + threadIdx.x;
     const int ox = (int)(j / (unsigned)cg), gi = (int)(j - (unsigned)ox * (unsigned)cg);
     if (ox >= g.ow) return;
-    const int nn = blockIdx.z, oy0 = blockIdx.y * strip, oy1 = min(oy0 + strip, g.oh);
     const int valid = min(4, c - 4 * gi);
     int x0, x1; float tx;
     up2_src(ox + g.hx0, g.full_w, align, g.sx, x0, x1, tx);
     x0 = min(max(x0 - g.lx0, 0), wd - 1); x1 = min(max(x1 - g.lx0, 0), wd - 1);
-    const float* b0 = x + (size_t)nn * h * wd * ldx + (size_t)x0 * ldx + 4 * gi;
-    const float* b1 = x + (size_t)nn * h * wd * ldx + (size_t)x1 * ldx + 4 * gi;
-    float* po = y + ((size_t)nn * g.oh * g.ow + ox) * ldy + 4 * gi;
-    int rowA = -1, rowB = -1;
-    F4 hA, hB;
+    const float* px = x + (size_t)blockIdx.z * h * wd * ldx + 4 * gi;
+    const int base = s_base, nrows = s_nrows, rowpitch = wd * ldx;
+    const int off0 = base * rowpitch + x0 * ldx, off1 = base * rowpitch + x1 * ldx;
+    F4 v0[UP_SLOTS], v1[UP_SLOTS];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) hA.v[q] = hB.v[q] = 0.f;
-    for (int oy = oy0; oy < oy1; ++oy) {
-        int y0, y1; float ty;
-        up2_src(oy + g.hy0, g.full_h, align, g.sy, y0, y1, ty);
-        y0 = min(max(y0 - g.ly0, 0), h - 1); y1 = min(max(y1 - g.ly0, 0), h - 1);
-        F4 n0, n1;
-        if (y0 == rowA) n0 = hA;
-        else if (y0 == rowB) n0 = hB;
-        else {
-            const F4 v0 = ld4(b0 + (size_t)y0 * wd * ldx, valid, vec), v1 = ld4(b1 + (size_t)y0 * wd * ldx, valid, vec);
+    for (int q = 0; q < UP_SLOTS; ++q)
+        if (q < nrows) { v0[q] = ld4(px + off0 + q * rowpitch, valid, VEC); v1[q] = ld4(px + off1 + q * rowpitch, valid, VEC); }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) n0.v[q] = (1.f - tx) * v0.v[q] + tx * v1.v[q];
-        }
-        if (y1 == y0) n1 = n0;
-        else if (y1 == rowB) n1 = hB;
-        else if (y1 == rowA) n1 = hA;
-        else {
-            const F4 v0 = ld4(b0 + (size_t)y1 * wd * ldx, valid, vec), v1 = ld4(b1 + (size_t)y1 * wd * ldx, valid, vec);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) n1.v[q] = (1.f - tx) * v0.v[q] + tx * v1.v[q];
-        }
-        hA = n0; rowA = y0; hB = n1; rowB = y1;
+    for (int q = 0; q < UP_SLOTS; ++q)
+        if (q < nrows)
+            s_h[q][threadIdx.x] = make_float4((1.f - tx) * v0[q].v[0] + tx * v1[q].v[0], (1.f - tx) * v0[q].v[1] + tx * v1[q].v[1],
+                                              (1.f - tx) * v0[q].v[2] + tx * v1[q].v[2], (1.f - tx) * v0[q].v[3] + tx * v1[q].v[3]);
+    float* po = y + (size_t)blockIdx.z * g.oh * g.ow * ldy + (oy0 * g.ow + ox) * ldy + 4 * gi;
+    const int opitch = g.ow * ldy;
+    for (int r = 0; r < rows; ++r) {
+        const float4 n0 = s_h[s_slot0[r]][threadIdx.x], n1 = s_h[s_slot1[r]][threadIdx.x];
+        const float ty = s_ty[r];
         F4 o;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o.v[q] = (1.f - ty) * n0.v[q] + ty * n1.v[q];
-        st4(po + (size_t)oy * g.ow * ldy, o, valid, vec, rnd);
+        o.v[0] = (1.f - ty) * n0.x + ty * n1.x; o.v[1] = (1.f - ty) * n0.y + ty * n1.y;
+        o.v[2] = (1.f - ty) * n0.z + ty * n1.z; o.v[3] = (1.f - ty) * n0.w + ty * n1.w;
+        st4(po + r * opitch, o, valid, VEC, RND);
     }
 }
 
 // backward: `strip` input rows per thread.  The thread walks the output rows that feed its strip in ascending order;
-// per output row it reduces the (at most six) horizontal contributions r = sum_b wx[b] dy[o][b] once and adds
-// (1-t) r / t r to the two input rows the output row was interpolated from, which only ever are the current row and
-// the next one: two running accumulators, a row is finished (accumulate / activation mask / store) when the walk
-// leaves it.  Every dy row is read once per thread instead of once per input row it feeds.
-__global__ void upsample2_bwd_strip_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
-                                           int accumulate, int h, int wd, int c, int align, int vec, UpWin g,
-                                           const float* __restrict__ mask_y, int ldmask, int mask_act,
-                                           float mask_slope, int strip) {
-    MI_SPLIT_VEC_RND(vec, rnd);
-    const int cg = (c + 3) >> 2, oh = g.oh, ow = g.ow;
-    const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+// per output row it reduces the horizontal contributions r = sum_b wx[b] dy[o][b] once and adds (1-t) r / t r to the two
+// input rows the output row was interpolated from, which only ever are the current row and the next one: two running
+// accumulators, a row is finished (accumulate / activation mask / store) when the walk leaves it.  Every dy row is read
+// once per thread instead of once per input row it feeds.
+constexpr int UP_CAND = 6;                               // candidate output columns 2 gx - 2 .. 2 gx + 3 of input column gx
+constexpr int UP_WALK = 2 * UP_STRIP_MAX + UP_CAND;      // output rows that can feed a strip
+template <bool VEC, bool RND>
+__global__ void __launch_bounds__(UP_TPB)
+upsample2_bwd_strip_kernel(const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx, int accumulate,
+                           int h, int wd, int c, int align, UpWin g, const float* __restrict__ mask_y, int ldmask,
+                           int mask_act, float mask_slope, int strip) {
+    __shared__ int s_a[UP_WALK], s_b[UP_WALK];
+    __shared__ float s_t[UP_WALK];
+    const int oh = g.oh, ow = g.ow;
+    const int yy0 = blockIdx.y * strip, yy1 = min(yy0 + strip, h) - 1;        // local rows of the strip, inclusive
+    const int gy0 = yy0 + g.ly0, gy1 = yy1 + g.ly0;                           // ... on the full low-resolution grid
+    // The source coordinate of output o lies in [o / 2 - 1 / 2, o / 2] for either convention, so outputs below 2 gy - 2
+    // interpolate from rows gy - 2 and gy - 1 at most and never feed gy; 2 gy + 3 can, when the product rounds below
+    // gy + 1 (the same holds for the columns).
+    const int o_lo = max(g.hy0, 2 * gy0 - 2), o_hi = min(g.hy0 + oh - 1, 2 * gy1 + 3);
+    if ((int)threadIdx.x <= o_hi - o_lo && threadIdx.x < UP_WALK) {
+        int a, b; float t; up2_src(o_lo + threadIdx.x, g.full_h, align, g.sy, a, b, t);
+        s_a[threadIdx.x] = a; s_b[threadIdx.x] = b; s_t[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int cg = (c + 3) >> 2;
+    const unsigned j = blockIdx.x * UP_TPB + threadIdx.x;
     const int xx = (int)(j / (unsigned)cg), gi = (int)(j - (unsigned)xx * (unsigned)cg);
     if (xx >= wd) return;
-    const int nn = blockIdx.z, yy0 = blockIdx.y * strip, yy1 = min(yy0 + strip, h) - 1;         // local rows, inclusive
     const int valid = min(4, c - 4 * gi);
-    // horizontal weights of the candidate output columns 2 gx - 2 .. 2 gx + 3 (zero: not a contributor).  The source
-    // coordinate of output o lies in [o / 2 - 1 / 2, o / 2] for either convention, so 2 gx - 3 interpolates from
-    // columns gx - 2 and gx - 1 at most and can never feed gx; 2 gx + 3 can, when the product rounds below gx + 1.
-    constexpr int UP_CAND = 6;
+    // horizontal weights of the candidate output columns (zero: not a contributor).  Every candidate is LOADED, from a
+    // clamped address when it cannot contribute, and enters with weight zero: loads under a per-thread condition
+    // became one divergent branch per column and row, each waiting for its own load.
     const int gx = xx + g.lx0, oxb = 2 * gx - 2;
     float wx[UP_CAND];
+    int col[UP_CAND];
 #pragma unroll
     for (int k = 0; k < UP_CAND; ++k) {
         const int o = oxb + k;
@@ -359,40 +389,35 @@ __global__ void upsample2_bwd_strip_kernel(const float* __restrict__ dy, int ldd
         if (a == gx) wgt += 1.f - t;
         if (b == gx) wgt += t;
         wx[k] = (o >= g.hx0 && o < g.hx0 + ow) ? wgt : 0.f;
+        col[k] = min(max(o - g.hx0, 0), ow - 1) * lddy;
     }
-    // (every candidate column is LOADED, from a clamped address when it cannot contribute, and enters with weight zero:
-    // loads under a per-thread condition became one divergent branch per column and row, each waiting for its own load)
-    int col[UP_CAND];
-#pragma unroll
-    for (int k = 0; k < UP_CAND; ++k) col[k] = min(max(oxb - g.hx0 + k, 0), ow - 1) * lddy;
-    const float* pin = dy + (size_t)nn * oh * ow * lddy + 4 * gi;
-    float* pdx = dx + ((size_t)nn * h * wd + xx) * lddx + 4 * gi;
-    const float* pm = mask_y ? mask_y + ((size_t)nn * h * wd + xx) * ldmask + 4 * gi : nullptr;
-    const int gy0 = yy0 + g.ly0, gy1 = yy1 + g.ly0;                  // strip rows on the full low-resolution grid
+    const float* pin = dy + (size_t)blockIdx.z * oh * ow * lddy + 4 * gi;
+    float* pdx = dx + (size_t)blockIdx.z * h * wd * lddx + xx * lddx + 4 * gi;
+    const float* pm = mask_y ? mask_y + (size_t)blockIdx.z * h * wd * ldmask + xx * ldmask + 4 * gi : nullptr;
+    const int ipitch = ow * lddy, dpitch = wd * lddx, mpitch = wd * ldmask;
     int cur = gy0;                                                   // acc0 belongs to row cur, acc1 to row cur + 1
     F4 acc0, acc1;
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc0.v[q] = acc1.v[q] = 0.f;
     auto finish = [&](int grow, F4 acc) {
         const int yy = grow - g.ly0;
-        float* d = pdx + (size_t)yy * wd * lddx;
+        float* d = pdx + yy * dpitch;
         if (accumulate) {
-            const F4 o = ld4(d, valid, vec);
+            const F4 o = ld4(d, valid, VEC);
 #pragma unroll
             for (int q = 0; q < 4; ++q) acc.v[q] += o.v[q];
         }
         if (pm) {
-            const float* mp = pm + (size_t)yy * wd * ldmask;
+            const F4 m = ld4(pm + yy * mpitch, valid, VEC);
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (q < valid) acc.v[q] *= mi_act_grad(mp[q], mask_act, mask_slope);
+            for (int q = 0; q < 4; ++q) acc.v[q] *= mi_act_grad(m.v[q], mask_act, mask_slope);
         }
-        st4(d, acc, valid, vec, rnd);
+        st4(d, acc, valid, VEC, RND);
     };
-    const int o_lo = max(g.hy0, 2 * gy0 - 2), o_hi = min(g.hy0 + oh - 1, 2 * gy1 + 3);   // (as for the columns)
     for (int o = o_lo; o <= o_hi; ++o) {
-        int a, b; float t; up2_src(o, g.full_h, align, g.sy, a, b, t);
+        const int a = s_a[o - o_lo], b = s_b[o - o_lo];
         if (b < gy0 || a > gy1) continue;                            // feeds rows outside the strip only
+        const float t = s_t[o - o_lo];
         while (cur < a) {                                            // (uniform over the block)
             finish(cur, acc0);
             acc0 = acc1;
@@ -400,10 +425,10 @@ __global__ void upsample2_bwd_strip_kernel(const float* __restrict__ dy, int ldd
             for (int q = 0; q < 4; ++q) acc1.v[q] = 0.f;
             ++cur;
         }
-        const float* prow = pin + (size_t)(o - g.hy0) * ow * lddy;
+        const float* prow = pin + (o - g.hy0) * ipitch;
         F4 v[UP_CAND];
 #pragma unroll
-        for (int k = 0; k < UP_CAND; ++k) v[k] = ld4(prow + col[k], valid, vec);
+        for (int k = 0; k < UP_CAND; ++k) v[k] = ld4(prow + col[k], valid, VEC);
         F4 r;
 #pragma unroll
         for (int q = 0; q < 4; ++q) r.v[q] = wx[0] * v[0].v[q];
@@ -854,24 +879,32 @@ static bool up_strip_enabled() {
 }
 // strip launches of the x2 resampling kernels: `cols` x `rows` positions walked per image (output pixels forward, input
 // pixels backward); false = geometry outside the grid limits, the caller launches the per-pixel form
-static bool up_strip_grid(int n, int rows, int cols, int c, dim3& grid, int& strip) {
+static bool up_strip_grid(int n, int rows, int cols, int c, long long image_elems, dim3& grid, int& strip) {
     const long long per_row = (long long)cols * ((c + 3) / 4);
-    // as many rows per thread as leave at least half of the chip's thread slots (148 x 2048) filled
-    static int forced = -1;                                  // MI_B200_UPSAMPLE_ROWS=1/2/4/8: fixed height (tuning aid)
+    static int forced = -1;                                  // MI_B200_UPSAMPLE_ROWS=1..8: fixed height (tuning aid)
     if (forced < 0) { const char* e = getenv("MI_B200_UPSAMPLE_ROWS"); forced = e ? atoi(e) : 0; }
-    strip = 8;
+    // as many rows per thread as leave at least half of the chip's thread slots (148 x 2048) filled
+    strip = UP_STRIP_MAX;
     while (strip > 1 && per_row * rows * n / strip < 148LL * 1024) strip >>= 1;
-    if (forced >= 1 && forced <= 64) strip = forced;
-    const long long gx = (per_row + TPB - 1) / TPB, gy = (rows + strip - 1) / strip;
-    if (!up_strip_enabled() || n < 1 || n > 65535 || gy < 1 || gy > 65535 || gx < 1 || gx > 0x7fffffffLL / TPB) return false;
+    if (forced >= 1 && forced <= UP_STRIP_MAX) strip = forced;
+    const long long gx = (per_row + UP_TPB - 1) / UP_TPB, gy = (rows + strip - 1) / strip;
+    if (!up_strip_enabled() || n < 1 || n > 65535 || gy < 1 || gy > 65535 || gx < 1 || gx > 0x7fffffffLL / UP_TPB ||
+        image_elems >= (1LL << 31))
+        return false;
     grid = dim3((unsigned)gx, (unsigned)gy, (unsigned)n);
     return true;
 }
-#define LAUNCH_UP_STRIP(kernel, grid, stream, ...)                      \
-    do {                                                                \
-        kernel<<<grid, TPB, 0, mi_cs(stream)>>>(__VA_ARGS__);           \
-        MI_LAUNCHED();                                                  \
-        MI_RETURN_LAST();                                               \
+// `vec` = VEC | RND << 1 as the per-pixel kernels take it
+#define LAUNCH_UP_STRIP(kernel, vec, grid, stream, ...)                                                     \
+    do {                                                                                                    \
+        switch ((vec) & 3) {                                                                                \
+            case 0: kernel<false, false><<<grid, UP_TPB, 0, mi_cs(stream)>>>(__VA_ARGS__); break;           \
+            case 1: kernel<true, false><<<grid, UP_TPB, 0, mi_cs(stream)>>>(__VA_ARGS__); break;            \
+            case 2: kernel<false, true><<<grid, UP_TPB, 0, mi_cs(stream)>>>(__VA_ARGS__); break;            \
+            default: kernel<true, true><<<grid, UP_TPB, 0, mi_cs(stream)>>>(__VA_ARGS__); break;            \
+        }                                                                                                   \
+        MI_LAUNCHED();                                                                                      \
+        MI_RETURN_LAST();                                                                                   \
     } while (0)
 
 extern "C" {
@@ -904,8 +937,8 @@ int mi_upsample2_fwd(const float* x, int ldx, float* y, int ldy, int n, int h, i
     const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd, up2_scale(h), up2_scale(wd)};
     dim3 grid; int strip;
-    if (up_strip_grid(n, g.oh, g.ow, c, grid, strip))
-        LAUNCH_UP_STRIP(upsample2_fwd_strip_kernel, grid, s, x, ldx, y, ldy, h, wd, c, align, vec, g, strip);
+    if (up_strip_grid(n, g.oh, g.ow, c, std::max((long long)g.oh * g.ow * ldy, (long long)h * wd * ldx), grid, strip))
+        LAUNCH_UP_STRIP(upsample2_fwd_strip_kernel, vec, grid, s, x, ldx, y, ldy, h, wd, c, align, g, strip);
     LAUNCH_IDX(upsample2_fwd_kernel, (long long)n * h * wd * 4 * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
@@ -914,8 +947,8 @@ int mi_upsample2_bwd(const float* dy, int lddy, float* dx, int lddx, int accumul
     const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {h, wd, 0, 0, 0, 0, 2 * h, 2 * wd, up2_scale(h), up2_scale(wd)};
     dim3 grid; int strip;
-    if (up_strip_grid(n, h, wd, c, grid, strip))
-        LAUNCH_UP_STRIP(upsample2_bwd_strip_kernel, grid, s, dy, lddy, dx, lddx, accumulate, h, wd, c, align, vec, g,
+    if (up_strip_grid(n, h, wd, c, std::max((long long)g.oh * g.ow * lddy, (long long)h * wd * lddx), grid, strip))
+        LAUNCH_UP_STRIP(upsample2_bwd_strip_kernel, vec, grid, s, dy, lddy, dx, lddx, accumulate, h, wd, c, align, g,
                         nullptr, 0, 0, 0.f, strip);
     LAUNCH_IDX(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
            vec, g, nullptr, 0, 0, 0.f);
@@ -931,8 +964,8 @@ int mi_upsample2_window_fwd(const float* x, int ldx, float* y, int ldy, int n, i
     const int vec = (mi_vec_ok(x, ldx, c) && mi_vec_ok(y, ldy, c)) | mi_rnd_bit(round_tf32);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow, up2_scale(full_h), up2_scale(full_w)};
     dim3 grid; int strip;
-    if (up_strip_grid(n, oh, ow, c, grid, strip))
-        LAUNCH_UP_STRIP(upsample2_fwd_strip_kernel, grid, s, x, ldx, y, ldy, h, wd, c, align, vec, g, strip);
+    if (up_strip_grid(n, oh, ow, c, std::max((long long)oh * ow * ldy, (long long)h * wd * ldx), grid, strip))
+        LAUNCH_UP_STRIP(upsample2_fwd_strip_kernel, vec, grid, s, x, ldx, y, ldy, h, wd, c, align, g, strip);
     LAUNCH_IDX(upsample2_fwd_kernel, (long long)n * oh * ow * ((c + 3) / 4), s, x, ldx, y, ldy, n, h, wd, c, align, vec, g);
 }
 int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int accumulate, int n, int h, int wd, int c,
@@ -941,11 +974,13 @@ int mi_upsample2_window_bwd(const float* dy, int lddy, float* dx, int lddx, int 
                             mi_stream_t s) {
     if (!dy || !dx || !up_window_ok(h, wd, full_h, full_w, ly0, lx0, oh, ow, hy0, hx0) || (mask_y && ldmask < c))
         return MI_ERR_BAD_ARG;
-    const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c)) | mi_rnd_bit(round_tf32);
+    const int vec = (mi_vec_ok(dy, lddy, c) && mi_vec_ok(dx, lddx, c) && (!mask_y || mi_vec_ok(mask_y, ldmask, c))) |
+                    mi_rnd_bit(round_tf32);
     const UpWin g = {full_h, full_w, ly0, lx0, hy0, hx0, oh, ow, up2_scale(full_h), up2_scale(full_w)};
     dim3 grid; int strip;
-    if (up_strip_grid(n, h, wd, c, grid, strip))
-        LAUNCH_UP_STRIP(upsample2_bwd_strip_kernel, grid, s, dy, lddy, dx, lddx, accumulate, h, wd, c, align, vec, g,
+    if (up_strip_grid(n, h, wd, c, std::max({(long long)oh * ow * lddy, (long long)h * wd * lddx, (long long)h * wd * ldmask}),
+                      grid, strip))
+        LAUNCH_UP_STRIP(upsample2_bwd_strip_kernel, vec, grid, s, dy, lddy, dx, lddx, accumulate, h, wd, c, align, g,
                         mask_y, ldmask, mask_act, mask_slope, strip);
     LAUNCH_IDX(upsample2_bwd_kernel, (long long)n * h * wd * ((c + 3) / 4), s, dy, lddy, dx, lddx, accumulate, n, h, wd, c, align,
            vec, g, mask_y, ldmask, mask_act, mask_slope);
