@@ -540,7 +540,7 @@ static bool small_cout_wgrad_ok(int cin, int cout, int k) { return cout <= SC_MA
 // weight_to_dgrad launch of every adapted layer.
 struct FinishDesc {
     const float* ws_w; const float* ws_b;
-    int splits, bias_splits, cin, cout, kk, ldw, mode, ldwt, rnd;
+    int splits, bias_splits, cin, cout, kk, ldw, mode, ldwt, rnd, vec;
     float scale;
     float* grad_w; float* grad_b;
     const float* w_in; const float* b_in;
@@ -563,10 +563,71 @@ __device__ __forceinline__ void wgrad_finish_body(const FinishDesc& d, long long
     float* gsum_w = d.gsum_w; float* gsum_b = d.gsum_b;
     float* wt_out = d.wt_out; float* wr_out = d.wr_out;
     const long long wsz = (long long)cout * kk * ldw;
-    const long long wsz32 = (wsz + 31) & ~31LL;
+    // Vector form of the weight part (rows padded to 4 lanes, every buffer 16-byte aligned, fewer than 2^31 elements:
+    // the launcher sets d.vec): one thread per 4 consecutive input channels, 32-bit index arithmetic.  The scalar form
+    // spends a 64-bit division and a 64-bit modulo per ELEMENT and was bound by those, not by the partials it reads
+    // (142 us for the 22 M weights of the SepConv backbone, 2.5 x the time of its memory traffic).
+    const long long wsz32 = d.vec ? ((wsz / 4 + 31) & ~31LL) : ((wsz + 31) & ~31LL);
     const long long total = wsz32 + (long long)cout * 32;
     for (long long i = first; i < total; i += stride) {
-        if (i < wsz32) {
+        if (i < wsz32 && d.vec) {
+            if (i >= wsz / 4) continue;
+            const unsigned e = 4u * (unsigned)i, uldw = (unsigned)ldw;
+            const unsigned row = e / uldw, ci = e - row * uldw;
+            if ((int)ci >= cin) continue;  // (a group of pad lanes only; cannot happen with rows padded to 4)
+            float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0, g3 = g0;
+            int sp = 0;
+            const float* q = ws_w + e;
+            for (; sp + 3 < splits; sp += 4, q += 4 * wsz) {
+                const float4 a0 = *reinterpret_cast<const float4*>(q), a1 = *reinterpret_cast<const float4*>(q + wsz),
+                             a2 = *reinterpret_cast<const float4*>(q + 2 * wsz), a3 = *reinterpret_cast<const float4*>(q + 3 * wsz);
+                g0.x += a0.x; g0.y += a0.y; g0.z += a0.z; g0.w += a0.w;
+                g1.x += a1.x; g1.y += a1.y; g1.z += a1.z; g1.w += a1.w;
+                g2.x += a2.x; g2.y += a2.y; g2.z += a2.z; g2.w += a2.w;
+                g3.x += a3.x; g3.y += a3.y; g3.z += a3.z; g3.w += a3.w;
+            }
+            for (; sp < splits; ++sp, q += wsz) {
+                const float4 a0 = *reinterpret_cast<const float4*>(q);
+                g0.x += a0.x; g0.y += a0.y; g0.z += a0.z; g0.w += a0.w;
+            }
+            float g[4] = {(g0.x + g1.x) + (g2.x + g3.x), (g0.y + g1.y) + (g2.y + g3.y), (g0.z + g1.z) + (g2.z + g3.z),
+                          (g0.w + g1.w) + (g2.w + g3.w)};
+            // pad lanes of the row (ci + lane >= cin): gradient zero, so every store below rewrites what was there
+#pragma unroll
+            for (int l = 0; l < 4; ++l) g[l] = ((int)ci + l < cin) ? g[l] : 0.f;
+            const float4 gv = make_float4(g[0], g[1], g[2], g[3]);
+            if (mode == MI_WG_STORE) {
+                *reinterpret_cast<float4*>(grad_w + e) = gv;
+            } else if (mode == MI_WG_ACCUM) {
+                float4 o = *reinterpret_cast<const float4*>(grad_w + e);
+                o.x += scale * g[0]; o.y += scale * g[1]; o.z += scale * g[2]; o.w += scale * g[3];
+                *reinterpret_cast<float4*>(grad_w + e) = o;
+            } else {
+                float4 l4;
+                if (mode == MI_WG_SGD_SCALAR) { const float l = lr_w[0]; l4 = make_float4(l, l, l, l); }
+                else l4 = *reinterpret_cast<const float4*>(lr_w + e);
+                const float4 wi = *reinterpret_cast<const float4*>(w_in + e);
+                const float wn[4] = {wi.x - l4.x * g[0], wi.y - l4.y * g[1], wi.z - l4.z * g[2], wi.w - l4.w * g[3]};
+                *reinterpret_cast<float4*>(w_out + e) = make_float4(wn[0], wn[1], wn[2], wn[3]);
+                if (grad_w) *reinterpret_cast<float4*>(grad_w + e) = gv;
+                float wq[4];
+#pragma unroll
+                for (int l = 0; l < 4; ++l) wq[l] = (wr_out && rnd) ? mi_rn_tf32(wn[l]) : wn[l];
+                if (wr_out) *reinterpret_cast<float4*>(wr_out + e) = make_float4(wq[0], wq[1], wq[2], wq[3]);
+                if (wt_out) {
+                    const unsigned co = row / (unsigned)kk, tap = row - co * (unsigned)kk;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+                        if ((int)ci + l < cin)
+                            wt_out[((long long)(ci + l) * kk + (kk - 1 - (int)tap)) * ldwt + co] = wq[l];
+                }
+            }
+            if (gsum_w) {
+                float4 o = *reinterpret_cast<const float4*>(gsum_w + e);
+                o.x += g[0]; o.y += g[1]; o.z += g[2]; o.w += g[3];
+                *reinterpret_cast<float4*>(gsum_w + e) = o;
+            }
+        } else if (i < wsz32) {
             if (i >= wsz) continue;
             const long long e = i;
             const int ci = (int)(e % ldw);
@@ -733,7 +794,8 @@ std::vector<FinishDesc> g_deferred;
 std::vector<RotateJob> g_rotate;
 
 int finish_blocks(const FinishDesc& d) {
-    const long long total = (((long long)d.cout * d.kk * d.ldw + 31) & ~31LL) + (long long)d.cout * 32;
+    const long long wsz = (long long)d.cout * d.kk * d.ldw;
+    const long long total = (((d.vec ? wsz / 4 : wsz) + 31) & ~31LL) + (long long)d.cout * 32;
     int blocks = mi_cdiv(total, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     return blocks;
@@ -749,6 +811,11 @@ int mi_wgrad_finish_launch(const float* ws_w, const float* ws_b, int splits, int
     d.kk = k * k; d.ldw = ldw; d.mode = mode; d.ldwt = ldwt; d.rnd = mi_tf32_rn_enabled() ? 1 : 0; d.scale = scale;
     d.grad_w = grad_w; d.grad_b = grad_b; d.w_in = w_in; d.b_in = b_in; d.w_out = w_out; d.b_out = b_out;
     d.lr_w = lr_w; d.lr_b = lr_b; d.gsum_w = gsum_w; d.gsum_b = gsum_b; d.wt_out = wt_out; d.wr_out = wr_out;
+    static int vec_on = -1;                                  // MI_B200_FINISH_VEC=0: scalar form of the weight part
+    if (vec_on < 0) { const char* e = getenv("MI_B200_FINISH_VEC"); vec_on = (e && e[0] == '0') ? 0 : 1; }
+    d.vec = vec_on && ldw % 4 == 0 && (long long)cout * k * k * ldw < (1LL << 31) && mi_al16(ws_w) && mi_al16(grad_w) &&
+            mi_al16(w_in) && mi_al16(w_out) && mi_al16(gsum_w) && mi_al16(wr_out) &&
+            (mode != MI_WG_SGD_TENSOR || mi_al16(lr_w));
     if (g_defer) {
         g_deferred.push_back(d);
         return MI_OK;
