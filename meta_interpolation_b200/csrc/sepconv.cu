@@ -27,6 +27,26 @@ bool use_quad() {
     return on == 1;
 }
 
+// threads per block of the layout transposes around the quad kernels (MI_B200_SEPCONV_TPOSE_NT=64/128/256: tuning aid)
+int tpose_nt() {
+    static int nt = 0;
+    if (!nt) {
+        const char* e = getenv("MI_B200_SEPCONV_TPOSE_NT");
+        const int v = e ? atoi(e) : 0;
+        nt = (v == 64 || v == 128 || v == 256) ? v : quad::TPOSE_NT;
+    }
+    return nt;
+}
+
+// float4 form of the transposes: NHWC rows of exactly 52 floats, planar rows a multiple of 4 pixels, aligned bases,
+// 32-bit offsets inside an image's planes (MI_B200_SEPCONV_TPOSE_VEC=0: scalar form)
+bool tpose_vec(const float* a, const float* b, int ld, const float* pa, const float* pb, int oh, int ow) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("MI_B200_SEPCONV_TPOSE_VEC"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on && ld == 52 && ow % 4 == 0 && mi_al16(a) && mi_al16(b) && mi_al16(pa) && mi_al16(pb) &&
+           51LL * oh * ow < (1LL << 31);
+}
+
 constexpr int TX = 32;
 constexpr int TY = 8;
 
@@ -364,8 +384,12 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
         float* hpl = planar + (size_t)n * 51 * oh * ow;
         const double px = (double)n * oh * ow;
         mi_prof_begin(MI_TAG_SEPCONV_FWD, 2.0 * px * (3 * 51 * 51 + 3 * 51), 4.0 * px * (2 * 51 + 3 + 3), st);
-        quad::filters_to_planar_kernel<51><<<dim3(mi_cdiv(ow, 32), oh, 2 * n), 256, 0, st>>>(vert, horiz, ldf, vpl, hpl, gh,
-                                                                                            gw, gy0, gx0, oh, ow);
+        if (tpose_vec(vert, horiz, ldf, vpl, hpl, oh, ow))
+            quad::filters_to_planar_kernel<51, true><<<dim3(mi_cdiv(ow, 32), oh, 2 * n), tpose_nt(), 0, st>>>(
+                vert, horiz, ldf, vpl, hpl, gh, gw, gy0, gx0, oh, ow);
+        else
+            quad::filters_to_planar_kernel<51, false><<<dim3(mi_cdiv(ow, 32), oh, 2 * n), tpose_nt(), 0, st>>>(
+                vert, horiz, ldf, vpl, hpl, gh, gw, gy0, gx0, oh, ow);
         MI_LAUNCHED();
         const quad::Args qa = {fh, fw, oh, ow, iy0, ix0};
         dim3 grid(mi_cdiv(ow, quad::BX), mi_cdiv(oh, quad::BY), n);
@@ -430,15 +454,24 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
         mi_prof_begin(MI_TAG_SEPCONV_BWD, 2.0 * px * (2 * 3 * 51 * 51 + 2 * 3 * 51), 4.0 * px * (4 * 51 + 3 + 3), st);
         const dim3 tgrid(mi_cdiv(ow, 32), oh, 2 * n);
         if (!planar_valid) {      // the forward of this call did not leave its planar filters behind
-            quad::filters_to_planar_kernel<51><<<tgrid, 256, 0, st>>>(vert, horiz, ldf, vpl, hpl, gh, gw, gy0, gx0, oh, ow);
+            if (tpose_vec(vert, horiz, ldf, vpl, hpl, oh, ow))
+                quad::filters_to_planar_kernel<51, true><<<tgrid, tpose_nt(), 0, st>>>(vert, horiz, ldf, vpl, hpl, gh, gw, gy0,
+                                                                                     gx0, oh, ow);
+            else
+                quad::filters_to_planar_kernel<51, false><<<tgrid, tpose_nt(), 0, st>>>(vert, horiz, ldf, vpl, hpl, gh, gw, gy0,
+                                                                                      gx0, oh, ow);
             MI_LAUNCHED();
         }
         const quad::Args qa = {fh, fw, oh, ow, iy0, ix0};
         dim3 grid(mi_cdiv(ow, quad::BX), mi_cdiv(oh, quad::BY), 2 * n);
         quad::sepconv_bwd_quad_kernel<51, 3><<<grid, quad::NT, sm, st>>>(frame, vpl, hpl, grad_out, gvpl, ghpl, qa);
         MI_LAUNCHED();
-        quad::planar_to_filters_kernel<51><<<tgrid, 256, 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0, gx0, oh,
-                                                                 ow, rnd);
+        if (tpose_vec(g_vert, g_horiz, ldg, gvpl, ghpl, oh, ow))
+            quad::planar_to_filters_kernel<51, true><<<tgrid, tpose_nt(), 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0,
+                                                                                 gx0, oh, ow, rnd);
+        else
+            quad::planar_to_filters_kernel<51, false><<<tgrid, tpose_nt(), 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0,
+                                                                                  gx0, oh, ow, rnd);
         mi_prof_end(st);
     } else if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && ldg >= 52 && (ldg & 3) == 0 && mi_al16(vert) &&
                mi_al16(horiz) && mi_al16(g_vert) && mi_al16(g_horiz)) {

@@ -337,8 +337,14 @@ sepconv_bwd_quad_kernel(const float* __restrict__ frame, const float* __restrict
 }
 
 // NHWC filters [n][gh][gw][ld] (window at (gy0, gx0)) -> tap-planar [n][F][oh][ow].  One CTA = 32 consecutive pixels
-// of one row: the 32 x F block is read as one contiguous run and written as F 128-byte lines.
-template <int F>
+// of one row: the 32 x F block is read as one contiguous run and written as F 128-byte lines.  A block moves 6.5 KB
+// in, then 6.5 KB out, with a barrier in between, so the bytes in flight per SM are set by the number of resident
+// blocks: launched with quad::TPOSE_NT = 128 threads (16 blocks per SM) rather than 256 (8).
+// VEC (rows of F + 1 floats, ow a multiple of 4, 16-byte aligned bases: the launcher checks): both sides move float4s.
+// ncu on the scalar form: issue slots 78 % busy, 60 instructions per element (a division, 64-bit address arithmetic
+// and a bounds test per 4 bytes) at 35 % of the HBM rate -- instruction-bound, not memory-bound.
+constexpr int TPOSE_NT = 128;
+template <int F, bool VEC>
 __global__ void __launch_bounds__(256)
 filters_to_planar_kernel(const float* __restrict__ src0, const float* __restrict__ src1, int ld, float* __restrict__ dst0,
                          float* __restrict__ dst1, int gh, int gw, int gy0, int gx0, int oh, int ow) {
@@ -348,21 +354,43 @@ filters_to_planar_kernel(const float* __restrict__ src0, const float* __restrict
     const int n_idx = blockIdx.z >> 1, y = blockIdx.y, x0 = blockIdx.x * 32;
     const int npx = min(32, ow - x0);
     const float* row = src + (((long long)n_idx * gh + gy0 + y) * gw + gx0 + x0) * ld;
-    for (int i = threadIdx.x; i < npx * ld; i += 256) {
-        const int px = i / ld, t = i - px * ld;
-        if (t < F) tile[px][t] = __ldg(row + i);
-    }
-    __syncthreads();
+    const int nt = blockDim.x;
     const long long plane = (long long)oh * ow;
     float* out = dst + (long long)n_idx * F * plane + (long long)y * ow + x0;
-    for (int i = threadIdx.x; i < F * 32; i += 256) {
-        const int t = i >> 5, px = i & 31;
-        if (px < npx) out[(long long)t * plane + px] = tile[px][t];
+    if constexpr (VEC) {
+        constexpr int G = (F + 1) / 4;                       // float4 groups of a pixel's row
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        for (int i = threadIdx.x; i < npx * G; i += nt) {
+            const int px = i / G, t = 4 * (i - px * G);
+            const float4 v = __ldg(row4 + i);
+            tile[px][t] = v.x; tile[px][t + 1] = v.y; tile[px][t + 2] = v.z; tile[px][t + 3] = v.w;   // (t + 3 <= F: the pad lane)
+        }
+        __syncthreads();
+        const int plane_i = (int)plane;                      // (F * plane < 2^31: the launcher checks)
+        for (int i = threadIdx.x; i < F * 8; i += nt) {
+            const int t = i >> 3, px = 4 * (i & 7);
+            float* o = out + t * plane_i + px;
+            if (px + 3 < npx) {
+                *reinterpret_cast<float4*>(o) = make_float4(tile[px][t], tile[px + 1][t], tile[px + 2][t], tile[px + 3][t]);
+            } else {
+                for (int q = 0; px + q < npx; ++q) o[q] = tile[px + q][t];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < npx * ld; i += nt) {
+            const int px = i / ld, t = i - px * ld;
+            if (t < F) tile[px][t] = __ldg(row + i);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < F * 32; i += nt) {
+            const int t = i >> 5, px = i & 31;
+            if (px < npx) out[(long long)t * plane + px] = tile[px][t];
+        }
     }
 }
 
 // tap-planar gradients [n][F][oh][ow] -> NHWC [n][gh][gw][ld] window (rounded to the TF32 grid on request)
-template <int F>
+template <int F, bool VEC>
 __global__ void __launch_bounds__(256)
 planar_to_filters_kernel(const float* __restrict__ src0, const float* __restrict__ src1, float* __restrict__ dst0,
                          float* __restrict__ dst1, int ld, int gh, int gw, int gy0, int gx0, int oh, int ow, int rnd) {
@@ -373,18 +401,47 @@ planar_to_filters_kernel(const float* __restrict__ src0, const float* __restrict
     const int npx = min(32, ow - x0);
     const long long plane = (long long)oh * ow;
     const float* in = src + (long long)n_idx * F * plane + (long long)y * ow + x0;
-    for (int i = threadIdx.x; i < F * 32; i += 256) {
-        const int t = i >> 5, px = i & 31;
-        if (px < npx) {
-            const float v = __ldg(in + (long long)t * plane + px);
-            tile[px][t] = rnd ? mi_rn_tf32(v) : v;
-        }
-    }
-    __syncthreads();
     float* row = dst + (((long long)n_idx * gh + gy0 + y) * gw + gx0 + x0) * ld;
-    for (int i = threadIdx.x; i < npx * ld; i += 256) {
-        const int px = i / ld, t = i - px * ld;
-        if (t < F) row[i] = tile[px][t];       // pad lanes of the NHWC rows are never written
+    const int nt = blockDim.x;
+    if constexpr (VEC) {
+        const int plane_i = (int)plane;
+        for (int i = threadIdx.x; i < F * 8; i += nt) {
+            const int t = i >> 3, px = 4 * (i & 7);
+            const float* p = in + t * plane_i + px;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (px + 3 < npx) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
+                for (int q = 0; px + q < npx; ++q) v[q] = __ldg(p + q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tile[px + q][t] = rnd ? mi_rn_tf32(v[q]) : v[q];
+        }
+        __syncthreads();
+        constexpr int G = (F + 1) / 4;
+        for (int i = threadIdx.x; i < npx * G; i += nt) {
+            const int px = i / G, g = i - px * G, t = 4 * g;
+            float* o = row + px * (F + 1) + t;
+            if (t + 3 < F) {
+                *reinterpret_cast<float4*>(o) = make_float4(tile[px][t], tile[px][t + 1], tile[px][t + 2], tile[px][t + 3]);
+            } else {                                          // pad lanes of the NHWC rows are never written
+                for (int q = 0; t + q < F; ++q) o[q] = tile[px][t + q];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < F * 32; i += nt) {
+            const int t = i >> 5, px = i & 31;
+            if (px < npx) {
+                const float v = __ldg(in + (long long)t * plane + px);
+                tile[px][t] = rnd ? mi_rn_tf32(v) : v;
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < npx * ld; i += nt) {
+            const int px = i / ld, t = i - px * ld;
+            if (t < F) row[i] = tile[px][t];   // pad lanes of the NHWC rows are never written
+        }
     }
 }
 
