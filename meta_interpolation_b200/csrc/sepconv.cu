@@ -431,12 +431,20 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
                    float* g_vert, float* g_horiz, int ldg, int n, int c, int fh, int fw, int gh, int gw, int oh,
                    int ow, int gy0, int gx0, int iy0, int ix0, int taps, int round_tf32, float* planar,
                    int planar_valid, float* planar_grad, mi_stream_t stream) {
-    const int rnd = (round_tf32 && mi_tf32_rn_enabled()) ? 1 : 0;
+    const int rnd = ((round_tf32 & 1) && mi_tf32_rn_enabled()) ? 1 : 0;
+    const int zero_outside = (round_tf32 & MI_SEPCONV_ZERO_OUTSIDE) ? 1 : 0;
     if (!args_ok(frame, vert, horiz, n, c, fh, fw, gh, gw, oh, ow, gy0, gx0, taps, ldf) || !grad_out || !g_vert ||
         !g_horiz || ldg < taps)
         return MI_ERR_BAD_ARG;
     cudaStream_t st = mi_cs(stream);
-    if (taps == 51 && c == 3 && planar && planar_grad && use_quad()) {
+    const bool quad_path = taps == 51 && c == 3 && planar && planar_grad && use_quad();
+    if (zero_outside && !quad_path) {       // (the quad path zero-fills inside its last launch)
+        const size_t bytes = (size_t)n * gh * gw * ldg * sizeof(float);
+        cudaError_t e = cudaMemsetAsync(g_vert, 0, bytes, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g_horiz, 0, bytes, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (quad_path) {
         static bool attr_set = false;
         const size_t sm = quad::smem_bytes<51, 3>();
         if (!attr_set) {
@@ -466,12 +474,13 @@ int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, in
         dim3 grid(mi_cdiv(ow, quad::BX), mi_cdiv(oh, quad::BY), 2 * n);
         quad::sepconv_bwd_quad_kernel<51, 3><<<grid, quad::NT, sm, st>>>(frame, vpl, hpl, grad_out, gvpl, ghpl, qa);
         MI_LAUNCHED();
+        const dim3 pgrid(mi_cdiv(ow, 32), zero_outside ? gh : oh, 2 * n);
         if (tpose_vec(g_vert, g_horiz, ldg, gvpl, ghpl, oh, ow))
-            quad::planar_to_filters_kernel<51, true><<<tgrid, tpose_nt(), 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0,
-                                                                                 gx0, oh, ow, rnd);
+            quad::planar_to_filters_kernel<51, true><<<pgrid, tpose_nt(), 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0,
+                                                                                 gx0, oh, ow, rnd, zero_outside);
         else
-            quad::planar_to_filters_kernel<51, false><<<tgrid, tpose_nt(), 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0,
-                                                                                  gx0, oh, ow, rnd);
+            quad::planar_to_filters_kernel<51, false><<<pgrid, tpose_nt(), 0, st>>>(gvpl, ghpl, g_vert, g_horiz, ldg, gh, gw, gy0,
+                                                                                  gx0, oh, ow, rnd, zero_outside);
         mi_prof_end(st);
     } else if (taps == 51 && c == 3 && ldf >= 52 && (ldf & 3) == 0 && ldg >= 52 && (ldg & 3) == 0 && mi_al16(vert) &&
                mi_al16(horiz) && mi_al16(g_vert) && mi_al16(g_horiz)) {

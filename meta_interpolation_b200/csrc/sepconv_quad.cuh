@@ -389,15 +389,36 @@ filters_to_planar_kernel(const float* __restrict__ src0, const float* __restrict
     }
 }
 
-// tap-planar gradients [n][F][oh][ow] -> NHWC [n][gh][gw][ld] window (rounded to the TF32 grid on request)
+// tap-planar gradients [n][F][oh][ow] -> NHWC [n][gh][gw][ld] window (rounded to the TF32 grid on request); with
+// `zero_outside` (grid.y = gh) the rest of the grid is zero-filled in the same launch -- the caller's two 48 MB fills
+// of a backward pass touched every byte of the window a second time
 template <int F, bool VEC>
 __global__ void __launch_bounds__(256)
 planar_to_filters_kernel(const float* __restrict__ src0, const float* __restrict__ src1, float* __restrict__ dst0,
-                         float* __restrict__ dst1, int ld, int gh, int gw, int gy0, int gx0, int oh, int ow, int rnd) {
+                         float* __restrict__ dst1, int ld, int gh, int gw, int gy0, int gx0, int oh, int ow, int rnd,
+                         int zero_outside) {
     __shared__ float tile[32][F + 2];
     const float* src = blockIdx.z & 1 ? src1 : src0;
     float* dst = blockIdx.z & 1 ? dst1 : dst0;
-    const int n_idx = blockIdx.z >> 1, y = blockIdx.y, x0 = blockIdx.x * 32;
+    const int n_idx = blockIdx.z >> 1, x0 = blockIdx.x * 32;
+    int y = blockIdx.y;
+    if (zero_outside) {
+        // blockIdx.y walks the rows of the whole grid: rows outside the window are zeroed by the blocks of the row
+        // together, the margins left / right of the window by the first / last block of a window row
+        const int r = blockIdx.y;
+        float* grow = dst + ((long long)n_idx * gh + r) * gw * ld;
+        if (r < gy0 || r >= gy0 + oh) {
+            const int total = gw * ld, per = (total + gridDim.x - 1) / gridDim.x;
+            const int lo = blockIdx.x * per, hi = min(total, lo + per);
+            for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) grow[i] = 0.f;
+            return;
+        }
+        if (blockIdx.x == 0)
+            for (int i = threadIdx.x; i < gx0 * ld; i += blockDim.x) grow[i] = 0.f;
+        if (blockIdx.x == gridDim.x - 1)
+            for (int i = (gx0 + ow) * ld + threadIdx.x; i < gw * ld; i += blockDim.x) grow[i] = 0.f;
+        y = r - gy0;
+    }
     const int npx = min(32, ow - x0);
     const long long plane = (long long)oh * ow;
     const float* in = src + (long long)n_idx * F * plane + (long long)y * ow + x0;

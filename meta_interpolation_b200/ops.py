@@ -564,15 +564,18 @@ class CudaOps:
         return out
 
     def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0, rnd=False, planar=None,
-                    planar_valid=False, planar_grad=None):
+                    planar_valid=False, planar_grad=None, zero_outside=False):
+        """``zero_outside``: g_vert / g_horiz are fresh (uninitialised) buffers and the call zero-fills what lies outside
+        the window itself (MI_SEPCONV_ZERO_OUTSIDE); otherwise the caller has zero-filled them."""
         n, c, fh, fw = frame.shape
         _, gh, gw, taps = vert.shape
         oh, ow = grad_out.shape[2], grad_out.shape[3]
         assert grad_out.is_contiguous() and _ld(g_vert) == _ld(g_horiz) and _ld(vert) == _ld(horiz)
         _lib.check(self.lib.mi_sepconv_bwd(frame.data_ptr(), vert.data_ptr(), horiz.data_ptr(), _ld(vert),
                                            grad_out.data_ptr(), g_vert.data_ptr(), g_horiz.data_ptr(), _ld(g_vert), n,
-                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps, int(rnd),
-                                           self._p(planar), int(planar_valid), self._p(planar_grad), self._stream()),
+                                           c, fh, fw, gh, gw, oh, ow, gy0, gx0, iy0, ix0, taps,
+                                           int(bool(rnd)) | (2 if zero_outside else 0), self._p(planar),
+                                           int(planar_valid), self._p(planar_grad), self._stream()),
                    "mi_sepconv_bwd")
 
     # ------------------------------------------------------------------ warp

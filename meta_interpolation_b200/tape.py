@@ -314,11 +314,13 @@ class Tape:
                 return
             n, gh, gw, taps = vert.data.shape
             assert vert.grad is None and horiz.grad is None, "sepconv filters have a single consumer"
-            vert.grad = ops.zeros_act(n, gh, gw, taps)
-            horiz.grad = ops.zeros_act(n, gh, gw, taps)
+            # fresh buffers: the op zero-fills outside the window in the launch that writes the window
+            vert.grad = ops.empty_act(n, gh, gw, taps)
+            horiz.grad = ops.empty_act(n, gh, gw, taps)
             scratch = ops.sepconv_planar(n_img, oh, ow, taps_f) if planar is not None else None
             ops.sepconv_bwd(frame, vert.data, horiz.data, g, vert.grad, horiz.grad, gy0, gx0, iy0, ix0,
-                            rnd=ops.tf32_rn, planar=planar, planar_valid=planar is not None, planar_grad=scratch)
+                            rnd=ops.tf32_rn, planar=planar, planar_valid=planar is not None, planar_grad=scratch,
+                            zero_outside=True)
             vert.grad_clean = horiz.grad_clean = ops.tf32_rn     # (zero outside the window is on the grid too)
             y.grad = None
 

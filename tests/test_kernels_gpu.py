@@ -232,6 +232,13 @@ def test_sepconv_fused_geometry(cuda_ops, geom, planar):
                          planar_valid=planar, planar_grad=scratch)
     close(gvd, gvc, 3e-5, "sepconv gV")
     close(ghd, ghc, 3e-5, "sepconv gH")
+    # the call zero-fills outside the window itself (MI_SEPCONV_ZERO_OUTSIDE): NaN-filled buffers come back equal to
+    # the gradients written into zero-filled ones, pad lanes of the rows aside
+    gv3, gh3 = cuda_ops.empty_act(2, gh, gw, taps), cuda_ops.empty_act(2, gh, gw, taps)
+    gv3.fill_(float("nan")); gh3.fill_(float("nan"))
+    cuda_ops.sepconv_bwd(frame.cuda(), vd, hd, go.cuda(), gv3, gh3, pad, pad, -pad, -pad, planar=ws,
+                         planar_valid=planar, planar_grad=scratch, zero_outside=True)
+    assert torch.equal(gv3.cpu(), gvd.cpu()) and torch.equal(gh3.cpu(), ghd.cpu()), "zero_outside changes the result"
     if planar:      # a backward that has to transpose the filters itself, with rounded outputs
         ws2 = cuda_ops.sepconv_planar(2, h, w, taps)
         gv2, gh2 = cuda_ops.zeros_act(2, gh, gw, taps), cuda_ops.zeros_act(2, gh, gw, taps)
