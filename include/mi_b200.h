@@ -293,7 +293,8 @@ int mi_sepconv_fwd(const float* frame, const float* vert, const float* horiz, in
                    int gy0, int gx0, int iy0, int ix0, int taps, float* planar, mi_stream_t stream);
 /* g_vert/g_horiz get the gradient inside the window; the caller zero-fills the rest of the grid -- or sets
  * MI_SEPCONV_ZERO_OUTSIDE in `round_tf32` (bit 0 of which is the rounding request) and the call defines every pixel of
- * the [n,gh,gw] grids itself: zero outside the window, in the launch that writes the window. */
+ * the [n,gh,gw] grids itself: zero outside the window (and in the pad lanes ldg - taps of its rows), in the launch that
+ * writes the window. */
 #define MI_SEPCONV_ZERO_OUTSIDE 2
 int mi_sepconv_bwd(const float* frame, const float* vert, const float* horiz, int ldf, const float* grad_out,
                    float* g_vert, float* g_horiz, int ldg,

@@ -446,7 +446,9 @@ planar_to_filters_kernel(const float* __restrict__ src0, const float* __restrict
             float* o = row + px * (F + 1) + t;
             if (t + 3 < F) {
                 *reinterpret_cast<float4*>(o) = make_float4(tile[px][t], tile[px][t + 1], tile[px][t + 2], tile[px][t + 3]);
-            } else {                                          // pad lanes of the NHWC rows are never written
+            } else if (zero_outside && t + 3 == F) {          // the caller's fresh buffer: the pad lane is zeroed too,
+                *reinterpret_cast<float4*>(o) = make_float4(tile[px][t], tile[px][t + 1], tile[px][t + 2], 0.f);   // whole sectors
+            } else {                                          // pad lanes of somebody's NHWC rows are never written
                 for (int q = 0; t + q < F; ++q) o[q] = tile[px][t + q];
             }
         }

@@ -495,7 +495,10 @@ class RefOps:
         return sepconv_forward(inp, v, h)
 
     def sepconv_bwd(self, frame, vert, horiz, grad_out, g_vert, g_horiz, gy0, gx0, iy0, ix0, planar=None,
-                    planar_valid=False, planar_grad=None):
+                    planar_valid=False, planar_grad=None, zero_outside=False):
+        if zero_outside:   # fresh buffers: the op defines the whole grids (MI_SEPCONV_ZERO_OUTSIDE of the C ABI)
+            g_vert.zero_()
+            g_horiz.zero_()
         taps = vert.shape[3]
         oh, ow = grad_out.shape[2], grad_out.shape[3]
         inp = self._sep_input(frame, oh, ow, iy0, ix0, taps)

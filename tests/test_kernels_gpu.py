@@ -239,6 +239,7 @@ def test_sepconv_fused_geometry(cuda_ops, geom, planar):
     cuda_ops.sepconv_bwd(frame.cuda(), vd, hd, go.cuda(), gv3, gh3, pad, pad, -pad, -pad, planar=ws,
                          planar_valid=planar, planar_grad=scratch, zero_outside=True)
     assert torch.equal(gv3.cpu(), gvd.cpu()) and torch.equal(gh3.cpu(), ghd.cpu()), "zero_outside changes the result"
+    assert not torch.isnan(gv3).any() and not torch.isnan(gh3).any()
     if planar:      # a backward that has to transpose the filters itself, with rounded outputs
         ws2 = cuda_ops.sepconv_planar(2, h, w, taps)
         gv2, gh2 = cuda_ops.zeros_act(2, gh, gw, taps), cuda_ops.zeros_act(2, gh, gw, taps)
