@@ -279,8 +279,10 @@ __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, int lddy, flo
 // What was per output value in the per-pixel form is now per thread (the index decomposition: one division instead of
 // six; the horizontal source coordinates / weights) or per block (the vertical ones: a table in shared memory), and a
 // source row is fetched once per thread for all the rows of the strip it feeds.  The per-pixel forms were issue-bound
-// at 0.4 (forward) and 0.3 (backward) of the HBM rate (28 / 40 us for 75 MB on the 137x233 -> 258x450 Subnet upsample):
-// ncu counts ~400 instructions per 16 bytes stored there.  Offsets inside an image are 32-bit (the launcher checks).
+// at 0.4 (forward) and 0.3 (backward) of the HBM rate (28 / 40 us for 75 MB on the 137x233 -> 258x450 Subnet upsample);
+// ncu still counted 130 (forward) and 500 (backward) instructions per 16 bytes stored in the first strip version, which
+// recomputed the vertical weights per thread and row and carried 64-bit offsets -- hence the table and the 32-bit
+// offsets inside an image (the launcher checks that they fit).
 // Rows per thread (`strip`): UP_STRIP_MAX at most, fewer when the launch would otherwise not fill the chip
 // (up_strip_grid).  VEC / RND are the two bits of the per-pixel kernels' `vec` parameter, fixed at compile time here.
 constexpr int UP_STRIP_MAX = 8;
